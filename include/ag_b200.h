@@ -1,0 +1,190 @@
+/*
+ * ag_b200.h — C ABI of the B200-native grasp-hypothesis hot path.
+ *
+ * This is the drop-in boundary for agile_grasp's `Localization::localizeHands` +
+ * `Localization::predictAntipodalHands` path.  Everything is POD: plain pointers, sizes,
+ * int status codes; no C++/torch/Eigen/PCL types cross it.  The C++ shim in
+ * include/agile_grasp/localization.h (same class/method names as the reference) sits on top
+ * of exactly these entry points.
+ *
+ * Reference interfaces replaced (paths relative to the reference repo):
+ *   ag_localize            <- Localization::localizeHands(cloud,size_left,indices,...)
+ *                             include/agile_grasp/localization.h:115-116, src/agile_grasp/localization.cpp:3-140
+ *   ag_classify            <- Localization::predictAntipodalHands -> Learning::classify
+ *                             include/agile_grasp/localization.h:104-105, src/agile_grasp/learning.cpp:165-247
+ *   ag_svm_load            <- CvSVM::load call in src/agile_grasp/learning.cpp:181-185 (same on-disk YAML)
+ *   ag_set_params          <- Localization setters include/agile_grasp/localization.h:148-259
+ *   ag_preprocess          <- NaN removal / filterWorkspace / voxelizeCloud, localization.cpp:17-45,216-355
+ *   ag_fit_quadrics        <- HandSearch::findQuadrics + Quadric, hand_search.cpp:65-113, quadric.cpp:14-305
+ *   ag_hand_sweep          <- HandSearch::findHands(private) + RotatingHand/FingerHand/Antipodal,
+ *                             hand_search.cpp:116-206, rotating_hand.cpp:19-177, finger_hand.cpp, antipodal.cpp
+ *   ag_hog_svm             <- Learning::convertToImage + cv::HOGDescriptor::compute + CvSVM::predict,
+ *                             learning.cpp:194-226,320-365
+ *
+ * Error model: every function returns 0 on success, <0 on error; ag_last_error() gives the
+ * message (thread-local).  The reference's "print and return an empty vector" behaviour
+ * (localization.cpp:9-15) is reproduced by the C++ shim on top of these codes.
+ *
+ * There is NO CPU fallback behind this ABI: if no CUDA device is usable, ag_create fails.
+ */
+#ifndef AG_B200_H_
+#define AG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AG_OK 0
+#define AG_ERR_INVALID (-1)
+#define AG_ERR_CUDA (-2)
+#define AG_ERR_IO (-3)
+#define AG_ERR_CAPACITY (-4)
+#define AG_ERR_EMPTY (-5)
+
+#define AG_IMAGE_COLS 100        /* Learning::num_horizontal_cells_, learning.h:64 */
+#define AG_IMAGE_ROWS 80         /* Learning::num_vertical_cells_ */
+#define AG_IMAGE_WORDS 250       /* 100*80 bits packed in uint32, bit (row*100+col) */
+#define AG_HOG_DIM 3528          /* 2 windows x 1764, learning.cpp:222 */
+#define AG_NUM_ORIENTATIONS 8    /* rotating_hand.cpp:13 */
+
+/* flags for ag_localize */
+#define AG_FLAG_CALC_ANTIPODAL 1u   /* calculates_antipodal: all-points r=0.01 normals pass */
+#define AG_FLAG_KEEP_POINTS 2u      /* also materialise points_for_learning on the host */
+
+/* Parameters = the union of Localization's setters (localization.h:148-259), HandSearch's
+ * hard-coded radii (hand_search.h:85, hand_search.cpp:20) and the Localization ctor args. */
+typedef struct ag_params {
+  double finger_width;         /* 0.01  find_grasps.cpp:13 */
+  double hand_outer_diameter;  /* 0.09 */
+  double hand_depth;           /* 0.06 */
+  double hand_height;          /* 0.02 */
+  double init_bite;            /* 0.01 */
+  double workspace[6];         /* xmin xmax ymin ymax zmin zmax */
+  double cam_tf_left[16];      /* row-major 4x4; only the translation column is used */
+  double cam_tf_right[16];
+  double nn_radius_taubin;     /* 0.03 */
+  double nn_radius_hands;      /* 0.08 */
+  double nn_radius_normals;    /* 0.01, all-points pass when calculates_antipodal */
+  double voxel_size;           /* 0.003 localization.cpp:43 */
+  int32_t num_samples;         /* used when no explicit indices are given */
+  int32_t num_threads;         /* CPU oracle only; ignored by the GPU path */
+  int32_t deterministic_normals; /* 1 = Quadric(is_deterministic=true) (parity mode) */
+  int32_t filters_boundaries;  /* Localization ctor arg, localization.h:84 */
+  int32_t fix_cam_source;      /* 0 reproduces the reference's pre-NaN camera labelling quirk */
+  int32_t reserved;
+  uint64_t seed;               /* sample-index RNG seed when indices are not supplied */
+} ag_params;
+
+/* One grasp hypothesis = GraspHypothesis (grasp_hypothesis.h:46-231) minus the variable-length
+ * members, plus bookkeeping.  `center`/`surface_center`/`width` of Grasp.msg map to
+ * bottom / surface / width (grasp_localizer.cpp:137-146). */
+typedef struct ag_grasp {
+  double axis[3];
+  double approach[3];
+  double binormal[3];
+  double bottom[3];
+  double surface[3];
+  double width;
+  float score;            /* SVM decision value sum (label +1 <=> score <= 0); NaN until classified */
+  int32_t sample_index;   /* index of the sample in the voxelised cloud */
+  int32_t sample_slot;    /* position of the sample in the sample list */
+  int32_t orientation;    /* 0..7, angle = -pi + orientation*pi/4 */
+  int32_t cam_source;
+  int32_t num_points;     /* number of points_for_learning (box points) */
+  int32_t image_id;       /* handle of the device/host grasp image of this hypothesis */
+  uint8_t half_antipodal;
+  uint8_t full_antipodal;
+  uint8_t label;          /* 1 if the SVM says antipodal (kept by classify) */
+  uint8_t reserved;
+} ag_grasp;
+
+/* Per-sample local frame = the outputs of Quadric that are used downstream. */
+typedef struct ag_frame {
+  double normal[3];
+  double axis[3];      /* curvature axis */
+  double binormal[3];
+  int32_t num_neighbors;
+  int32_t majority_cam;
+} ag_frame;
+
+typedef struct ag_timings {
+  float h2d_ms, preprocess_ms, grid_ms, normals_all_ms, quadric_ms, sweep_ms, hog_svm_ms, d2h_ms, total_ms;
+  int32_t n_in, n_voxels, n_samples, n_hyp;
+  int64_t taubin_neighbor_points;   /* sum over samples of n_T(s): algorithmic bytes = 16 * this */
+  int64_t hand_neighbor_points;     /* sum over samples of n_H(s) */
+  int64_t taubin_candidates;        /* points actually scanned by the hash-grid walk */
+  int64_t hand_candidates;
+} ag_timings;
+
+typedef struct ag_ctx ag_ctx;
+typedef struct ag_svm ag_svm;
+
+const char* ag_last_error(void);
+void ag_default_params(ag_params* p);
+
+ag_ctx* ag_create(int device);
+void ag_destroy(ag_ctx* ctx);
+int ag_set_params(ag_ctx* ctx, const ag_params* p);
+int ag_get_params(ag_ctx* ctx, ag_params* p);
+int ag_get_timings(ag_ctx* ctx, ag_timings* t);
+void ag_free(void* p);
+
+/* SVM model in OpenCV-2.4 YAML ("!!opencv-ml-svm"), LINEAR or POLY kernels. */
+ag_svm* ag_svm_load(const char* path);
+void ag_svm_free(ag_svm* svm);
+int ag_svm_info(const ag_svm* svm, int* kernel_type, int* var_count, int* sv_total, double* rho);
+
+/* Full path, host buffers in -> host grasp list out.
+ * points: n_in records, `stride` bytes apart, x,y,z float32 at byte offsets 0,4,8
+ * (pcl::PointXYZRGBA has stride 32).  indices: sample indices into the VOXELISED cloud
+ * (may be NULL/0 -> num_samples are drawn).  The grasp images stay resident on the device
+ * for a following ag_classify.  *out is malloc'ed; release with ag_free. */
+int ag_localize(ag_ctx* ctx, const void* points, int stride, int n_in, int size_left,
+                const int* indices, int n_indices, unsigned flags, ag_grasp** out, int* n_out);
+
+/* Same, but the cloud is already resident in device memory (device pointer, same layout). */
+int ag_localize_device(ag_ctx* ctx, const void* d_points, int stride, int n_in, int size_left,
+                       const int* indices, int n_indices, unsigned flags, ag_grasp** out, int* n_out);
+
+/* Score hypotheses returned by the last ag_localize on this context (image_id refers to the
+ * device-resident grasp images).  Fills score/label in place; `keep` (may be NULL) gets 1 for
+ * hypotheses the reference would return from predictAntipodalHands. */
+int ag_classify(ag_ctx* ctx, const ag_svm* svm, ag_grasp* grasps, int n, uint8_t* keep);
+
+/* Variable-length members of GraspHypothesis for hypothesis `image_id` of the last ag_localize
+ * (requires AG_FLAG_KEEP_POINTS): points_for_learning (3 x m, column-major doubles) and the
+ * camera source of each column. */
+int ag_get_points(ag_ctx* ctx, int image_id, double** pts3xm, int32_t** cam, int* m);
+int ag_get_images(ag_ctx* ctx, uint32_t** bits, int* n_images);   /* AG_IMAGE_WORDS per image */
+
+/* ---- stage-level entry points (used by the parity tests and by callers that want one stage) */
+
+/* NaN removal + workspace filter + voxelisation. Outputs malloc'ed: xyz (3 floats per voxel), cam. */
+int ag_preprocess(ag_ctx* ctx, const void* points, int stride, int n_in, int size_left,
+                  float** xyz_out, int32_t** cam_out, int* n_out);
+
+/* Load an already-voxelised cloud (skips preprocessing) and build the hash grid. */
+int ag_set_cloud(ag_ctx* ctx, const float* xyz, const int32_t* cam, int n);
+
+/* Radius search on the current cloud; returns neighbour indices in ascending index order. */
+int ag_radius_search(ag_ctx* ctx, const float q[3], double radius, int32_t** idx_out, int* n_out);
+
+/* Taubin quadric fit + local frame for the given sample indices of the current cloud. */
+int ag_fit_quadrics(ag_ctx* ctx, const int* indices, int n_indices, double radius, ag_frame* frames_out);
+
+/* Hand sweep for the given samples with caller-supplied frames (normal + curvature axis).
+ * cloud_normals: 3 doubles per cloud point (may be NULL = all zero). */
+int ag_hand_sweep(ag_ctx* ctx, const int* indices, int n_indices, const ag_frame* frames,
+                  const double* cloud_normals, unsigned flags, ag_grasp** out, int* n_out);
+
+/* HOG descriptor + SVM decision value for n packed grasp images (AG_IMAGE_WORDS uint32 each).
+ * descriptors (may be NULL): n x AG_HOG_DIM floats. */
+int ag_hog_svm(ag_ctx* ctx, const ag_svm* svm, const uint32_t* images, int n,
+               float* descriptors, float* scores);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AG_B200_H_ */
