@@ -1,0 +1,105 @@
+// ag_internal.h — host-side context and the launcher prototypes of each stage.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "ag_common.cuh"
+
+namespace ag {
+
+void set_error(const std::string& msg);
+
+// growable device buffer
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);
+  void release();
+  template <typename T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+
+// constants of the hand model, evaluated on the host with the same libm as the reference
+// (finger_hand.cpp:8-15, rotating_hand.cpp:12-15,90, finger_hand.cpp:199-204, antipodal.cpp:14)
+struct HandConst {
+  double spacing[20];      // finger slot positions
+  double finger_width, outer_diameter, depth, hand_height, init_bite;
+  double cosv[8], sinv[8]; // cos/sin of the 8 hand orientations
+  double bite[12];         // deepening sequence d_t (d_0 = init_bite, d_t = d_{t-1} + 0.005)
+  double back[12];         // back_of_hand at d_t = -1.0 * (depth - d_t)
+  double lim[12];          // back[t] + depth (points-in-box limit)
+  int n_depths;            // number of valid entries (d_t <= depth)
+  double cos_thresh;       // cos(20 deg)
+  double cam[2][3];        // camera origins
+  double img_cell;         // (0.05 - -0.05) / 100
+  double half_od;          // outer_diameter / 2.0
+};
+
+struct SvmModel {
+  int kernel = 0;  // 0 linear, 1 poly
+  int degree = 0;
+  double gamma = 1, coef0 = 0, rho = 0;
+  int var_count = 0, sv_total = 0, sv_count = 0;
+  std::vector<float> sv;      // sv_total x var_count
+  std::vector<double> alpha;  // sv_count
+  std::vector<int> index;
+  // device copies (created lazily per device)
+  int device = -1;
+  float* d_sv = nullptr;
+  double* d_alpha = nullptr;
+  int* d_index = nullptr;
+};
+
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  ag_params params;
+  HandConst hand;
+  // raw input + preprocessing
+  DevBuf raw, keys, keys_sorted, keys_unique, cub_tmp, block_counts, misc;
+  void* h_pinned = nullptr;  // pinned staging for inputs / outputs
+  size_t h_pinned_cap = 0;
+  // voxelised cloud (API index space) and cell-sorted copy
+  DevBuf vox;        // float4: xyz + cam (as int bits)
+  DevBuf cell_ids, cell_ids_sorted, perm, perm_sorted, cell_start, pts, inv;
+  DevBuf normals;    // double x 3 per voxel point (cloud_normals_)
+  GridDesc grid;
+  int n_vox = 0;
+  // samples
+  DevBuf samples, moments, frames, nn_counts;
+  int n_samples = 0;
+  // sweep outputs
+  DevBuf grasps_raw, valid, images_raw, hyp_slots, grasps, counters, scores, descriptors, sweep_dbg;
+  int n_hyp = 0;
+  bool images_valid = false;
+  bool keep_points = false;
+  // host copies for ag_get_points
+  std::vector<ag_grasp> last_grasps;
+  ag_timings timings;
+  cudaEvent_t ev[10];
+};
+
+int ctx_pinned(Ctx* c, size_t bytes);
+
+// ---- stage launchers (each returns AG_OK or an error code); all work is enqueued on c->stream
+int preprocess_device(Ctx* c, const void* d_points, int stride, int n_in, int size_left);  // -> c->vox, c->n_vox
+int set_cloud_device(Ctx* c, int n);  // cloud already in c->vox (ag_set_cloud)
+int set_normals_device(Ctx* c, const double* h_normals);  // cloud_normals_ supplied by the caller
+int build_grid(Ctx* c);                                                                    // -> c->pts, c->cell_start
+int fit_quadrics_device(Ctx* c, const int* d_indices, int n, double radius, ag_frame* d_frames,
+                        bool write_normals);
+int hand_sweep_device(Ctx* c, const int* d_indices, int n, const ag_frame* d_frames, unsigned flags);
+int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d_image_ids, int n,
+                   float* d_descriptors, float* d_scores);
+int radius_search_device(Ctx* c, const float q[3], double radius, std::vector<int>& out);
+
+void compute_hand_const(const ag_params& p, HandConst& h);
+int svm_to_device(SvmModel* svm, int device);
+
+}  // namespace ag

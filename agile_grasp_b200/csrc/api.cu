@@ -1,0 +1,669 @@
+// api.cu — the extern "C" ABI declared in include/ag_b200.h: context, parameters, SVM model file
+// loader, the full localize/classify path and the stage-level entry points.
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+#include "ag_internal.h"
+
+namespace ag {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+
+int DevBuf::reserve(size_t bytes) {
+  if (bytes <= cap) return 0;
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+  size_t want = bytes + bytes / 4 + 256;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+    p = nullptr;
+    return AG_ERR_CUDA;
+  }
+  cap = want;
+  return 0;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+
+int ctx_pinned(Ctx* c, size_t bytes) {
+  if (bytes <= c->h_pinned_cap) return 0;
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  c->h_pinned = nullptr;
+  c->h_pinned_cap = 0;
+  size_t want = bytes + bytes / 4 + 4096;
+  cudaError_t e = cudaMallocHost(&c->h_pinned, want);
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMallocHost failed: ") + cudaGetErrorString(e));
+    return AG_ERR_CUDA;
+  }
+  c->h_pinned_cap = want;
+  return 0;
+}
+
+
+// stratified sorted distinct sample draw (replaces the time-seeded pcl::RandomSample,
+// hand_search.cpp:36-39): stratum k = [floor(k n/S), floor((k+1) n/S)), one index from each
+static inline uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+static void draw_samples(int n, int S, uint64_t seed, std::vector<int>& out) {
+  if (S > n) S = n;
+  out.resize(S);
+  for (int k = 0; k < S; k++) {
+    const int64_t lo = (int64_t(k) * n) / S, hi = (int64_t(k + 1) * n) / S;
+    const uint64_t h = splitmix64(seed ^ splitmix64(uint64_t(k)));
+    out[k] = int(lo + int64_t(h % uint64_t(hi - lo)));
+  }
+}
+
+// ---- SVM model file (OpenCV 2.4 YAML, svm_032015_linear_20_20_same:1-16,780-789) -------------
+static bool read_list(const std::string& text, size_t& pos, std::vector<double>& out) {
+  const size_t lb = text.find('[', pos);
+  if (lb == std::string::npos) return false;
+  const size_t rb = text.find(']', lb);
+  if (rb == std::string::npos) return false;
+  const char* p = text.c_str() + lb + 1;
+  const char* end = text.c_str() + rb;
+  while (p < end) {
+    while (p < end && (*p == ' ' || *p == ',' || *p == '\n' || *p == '\r' || *p == '\t')) p++;
+    if (p >= end) break;
+    char* q;
+    const double v = std::strtod(p, &q);
+    if (q == p) return false;
+    out.push_back(v);
+    p = q;
+  }
+  pos = rb + 1;
+  return true;
+}
+static bool read_scalar(const std::string& text, const char* key, size_t from, double& v) {
+  const std::string k = std::string(key) + ":";
+  const size_t p = text.find(k, from);
+  if (p == std::string::npos) return false;
+  const char* s = text.c_str() + p + k.size();
+  char* q;
+  v = std::strtod(s, &q);
+  return q != s;
+}
+
+static SvmModel* load_svm(const char* path) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f.good()) {
+    set_error(std::string("Error: File ") + path + " does not exist!");  // learning.cpp:172-178
+    return nullptr;
+  }
+  std::stringstream ss;
+  ss << f.rdbuf();
+  const std::string text = ss.str();
+  if (text.find("opencv-ml-svm") == std::string::npos) {
+    set_error("not an !!opencv-ml-svm file");
+    return nullptr;
+  }
+  SvmModel* m = new SvmModel;
+  auto bad = [&](const char* why) {
+    set_error(std::string("SVM file: ") + why);
+    delete m;
+    return static_cast<SvmModel*>(nullptr);
+  };
+  const size_t kp = text.find("kernel:");
+  if (kp == std::string::npos) return bad("kernel missing");
+  const std::string kline = text.substr(kp, text.find('}', kp) - kp);
+  if (kline.find("LINEAR") != std::string::npos) m->kernel = 0;
+  else if (kline.find("POLY") != std::string::npos) m->kernel = 1;
+  else return bad("only LINEAR and POLY kernels are supported");
+  double v;
+  if (m->kernel == 1) {
+    if (read_scalar(kline, "degree", 0, v)) m->degree = int(v);
+    if (read_scalar(kline, "gamma", 0, v)) m->gamma = v;
+    if (read_scalar(kline, "coef0", 0, v)) m->coef0 = v;
+    if (m->degree < 1) return bad("POLY degree must be a positive integer");
+  }
+  if (!read_scalar(text, "var_count", 0, v)) return bad("var_count missing");
+  m->var_count = int(v);
+  if (!read_scalar(text, "sv_total", 0, v)) return bad("sv_total missing");
+  m->sv_total = int(v);
+  size_t pos = text.find("support_vectors:");
+  if (pos == std::string::npos) return bad("support_vectors missing");
+  m->sv.reserve(size_t(m->sv_total) * m->var_count);
+  for (int k = 0; k < m->sv_total; k++) {
+    std::vector<double> row;
+    if (!read_list(text, pos, row) || int(row.size()) != m->var_count) return bad("bad support vector row");
+    for (double d : row) m->sv.push_back(float(d));
+  }
+  const size_t df = text.find("decision_functions:", pos);
+  if (df == std::string::npos) return bad("decision_functions missing");
+  if (!read_scalar(text, "sv_count", df, v)) return bad("sv_count missing");
+  m->sv_count = int(v);
+  if (!read_scalar(text, "rho", df, v)) return bad("rho missing");
+  m->rho = v;
+  size_t ap = text.find("alpha:", df);
+  if (ap == std::string::npos || !read_list(text, ap, m->alpha) || int(m->alpha.size()) != m->sv_count)
+    return bad("bad alpha");
+  m->index.resize(m->sv_count);
+  for (int k = 0; k < m->sv_count; k++) m->index[k] = k;
+  size_t ip = text.find("index:", ap);
+  if (ip != std::string::npos) {
+    std::vector<double> idx;
+    if (read_list(text, ip, idx) && int(idx.size()) == m->sv_count)
+      for (int k = 0; k < m->sv_count; k++) m->index[k] = int(idx[k]);
+  }
+  for (int k : m->index)
+    if (k < 0 || k >= m->sv_total) return bad("index out of range");
+  return m;
+}
+
+static float elapsed(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  return ms;
+}
+
+// the full device-side path, cloud already in device memory
+static int localize_core(Ctx* c, const void* d_points, int stride, int n_in, int size_left, const int* indices,
+                         int n_indices, unsigned flags, ag_grasp** out, int* n_out) {
+  *out = nullptr;
+  *n_out = 0;
+  std::memset(&c->timings, 0, sizeof(c->timings));
+  c->timings.n_in = n_in;
+  c->images_valid = false;
+  c->n_hyp = 0;
+  cudaStream_t st = c->stream;
+  cudaEventRecord(c->ev[1], st);
+  int rc = preprocess_device(c, d_points, stride, n_in, size_left);
+  if (rc) return rc;
+  cudaEventRecord(c->ev[2], st);
+  c->timings.n_voxels = c->n_vox;
+  if (c->n_vox == 0) return AG_OK;
+  rc = build_grid(c);
+  if (rc) return rc;
+  cudaEventRecord(c->ev[3], st);
+  if (c->counters.reserve(64)) return AG_ERR_CUDA;
+  AG_CUDA_CHECK(cudaMemsetAsync(c->counters.p, 0, 64, st));
+  const int n = c->n_vox;
+  // samples
+  std::vector<int> idx;
+  if (indices && n_indices > 0) {
+    idx.assign(indices, indices + n_indices);
+    for (int i : idx)
+      if (i < 0 || i >= n) {
+        set_error("sample index out of range of the voxelised cloud");
+        return AG_ERR_INVALID;
+      }
+  } else {
+    draw_samples(n, c->params.num_samples, c->params.seed, idx);
+  }
+  const int S = int(idx.size());
+  c->n_samples = S;
+  c->timings.n_samples = S;
+  if (c->samples.reserve(size_t(std::max(S, n)) * 4) || c->frames.reserve(size_t(std::max(S, 1)) * sizeof(ag_frame)))
+    return AG_ERR_CUDA;
+  if (flags & AG_FLAG_CALC_ANTIPODAL) {
+    // hand_search.cpp:17-26: normals for ALL points with radius 0.01
+    DevBuf all_idx, all_frames;
+    if (all_idx.reserve(size_t(n) * 4) || all_frames.reserve(size_t(n) * sizeof(ag_frame))) return AG_ERR_CUDA;
+    std::vector<int> iota(n);
+    for (int i = 0; i < n; i++) iota[i] = i;
+    AG_CUDA_CHECK(cudaMemcpyAsync(all_idx.p, iota.data(), size_t(n) * 4, cudaMemcpyHostToDevice, st));
+    rc = fit_quadrics_device(c, all_idx.as<int>(), n, c->params.nn_radius_normals, all_frames.as<ag_frame>(), true);
+    AG_CUDA_CHECK(cudaStreamSynchronize(st));
+    all_idx.release();
+    all_frames.release();
+    if (rc) return rc;
+    AG_CUDA_CHECK(cudaMemsetAsync(c->counters.p, 0, 64, st));
+  }
+  cudaEventRecord(c->ev[4], st);
+  AG_CUDA_CHECK(cudaMemcpyAsync(c->samples.p, idx.data(), size_t(S) * 4, cudaMemcpyHostToDevice, st));
+  rc = fit_quadrics_device(c, c->samples.as<int>(), S, c->params.nn_radius_taubin, c->frames.as<ag_frame>(), true);
+  if (rc) return rc;
+  cudaEventRecord(c->ev[5], st);
+  rc = hand_sweep_device(c, c->samples.as<int>(), S, c->frames.as<ag_frame>(),
+                         c->params.filters_boundaries ? 0x100u : 0u);
+  if (rc) return rc;
+  cudaEventRecord(c->ev[6], st);
+  const int Hn = c->n_hyp;
+  ag_grasp* res = static_cast<ag_grasp*>(std::malloc(std::max<size_t>(1, size_t(Hn)) * sizeof(ag_grasp)));
+  if (Hn > 0) AG_CUDA_CHECK(cudaMemcpyAsync(res, c->grasps.p, size_t(Hn) * sizeof(ag_grasp), cudaMemcpyDeviceToHost, st));
+  unsigned long long ctr[8];
+  AG_CUDA_CHECK(cudaMemcpyAsync(ctr, c->counters.p, 64, cudaMemcpyDeviceToHost, st));
+  cudaEventRecord(c->ev[7], st);
+  AG_CUDA_CHECK(cudaStreamSynchronize(st));
+  c->timings.preprocess_ms = elapsed(c->ev[1], c->ev[2]);
+  c->timings.grid_ms = elapsed(c->ev[2], c->ev[3]);
+  c->timings.normals_all_ms = elapsed(c->ev[3], c->ev[4]);
+  c->timings.quadric_ms = elapsed(c->ev[4], c->ev[5]);
+  c->timings.sweep_ms = elapsed(c->ev[5], c->ev[6]);
+  c->timings.d2h_ms = elapsed(c->ev[6], c->ev[7]);
+  c->timings.total_ms = elapsed(c->ev[0], c->ev[7]);
+  c->timings.n_hyp = Hn;
+  c->timings.taubin_neighbor_points = int64_t(ctr[0]);
+  c->timings.taubin_candidates = int64_t(ctr[1]);
+  c->timings.hand_neighbor_points = int64_t(ctr[2]);
+  c->timings.hand_candidates = int64_t(ctr[3]);
+  c->last_grasps.assign(res, res + Hn);
+  *out = res;
+  *n_out = Hn;
+  return AG_OK;
+}
+
+}  // namespace ag
+
+using namespace ag;
+
+struct ag_ctx {
+  Ctx c;
+};
+struct ag_svm {
+  SvmModel* m;
+};
+
+extern "C" {
+
+const char* ag_last_error(void) { return g_error.c_str(); }
+
+void ag_default_params(ag_params* p) {
+  std::memset(p, 0, sizeof(*p));
+  p->finger_width = 0.01;  // find_grasps.cpp:13-17
+  p->hand_outer_diameter = 0.09;
+  p->hand_depth = 0.06;
+  p->hand_height = 0.02;
+  p->init_bite = 0.01;
+  const double ws[6] = {-10, 10, -10, 10, -10, 10};
+  std::memcpy(p->workspace, ws, sizeof(ws));
+  const double base_tf[16] = {0, 0.445417, 0.895323, 0.215, 1, 0, 0, -0.015, 0, 0.895323, -0.445417, 0.23, 0, 0, 0, 1};
+  std::memcpy(p->cam_tf_left, base_tf, sizeof(base_tf));
+  std::memcpy(p->cam_tf_right, base_tf, sizeof(base_tf));
+  p->nn_radius_taubin = 0.03;  // hand_search.h:85
+  p->nn_radius_hands = 0.08;
+  p->nn_radius_normals = 0.01;  // hand_search.cpp:20
+  p->voxel_size = 0.003;        // localization.cpp:43
+  p->num_samples = 2000;        // find_grasps.cpp:11
+  p->num_threads = 1;
+  p->deterministic_normals = 1;
+  p->filters_boundaries = 0;
+  p->fix_cam_source = 0;
+  p->seed = 20150320;
+}
+
+ag_ctx* ag_create(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error(std::string("no CUDA device available (there is no CPU fallback): ") +
+              (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    return nullptr;
+  }
+  if (device < 0 || device >= count) {
+    set_error("device index out of range");
+    return nullptr;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    set_error("cudaSetDevice failed");
+    return nullptr;
+  }
+  ag_ctx* h = new ag_ctx;
+  Ctx& c = h->c;
+  c.device = device;
+  if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error("cudaStreamCreate failed");
+    delete h;
+    return nullptr;
+  }
+  for (auto& ev : c.ev) cudaEventCreate(&ev);
+  ag_default_params(&c.params);
+  compute_hand_const(c.params, c.hand);
+  std::memset(&c.timings, 0, sizeof(c.timings));
+  std::memset(&c.grid, 0, sizeof(c.grid));
+  return h;
+}
+
+void ag_destroy(ag_ctx* h) {
+  if (!h) return;
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  cudaStreamSynchronize(c.stream);
+  for (DevBuf* b : {&c.raw, &c.keys, &c.keys_sorted, &c.keys_unique, &c.cub_tmp, &c.block_counts, &c.misc, &c.vox,
+                    &c.cell_ids, &c.cell_ids_sorted, &c.perm, &c.perm_sorted, &c.cell_start, &c.pts, &c.inv,
+                    &c.normals, &c.samples, &c.moments, &c.frames, &c.nn_counts, &c.grasps_raw, &c.valid,
+                    &c.images_raw, &c.hyp_slots, &c.grasps, &c.counters, &c.scores, &c.descriptors, &c.sweep_dbg})
+    b->release();
+  if (c.h_pinned) cudaFreeHost(c.h_pinned);
+  for (auto& ev : c.ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(c.stream);
+  delete h;
+}
+
+int ag_set_params(ag_ctx* h, const ag_params* p) {
+  if (!h || !p) return AG_ERR_INVALID;
+  if (!(p->voxel_size > 0) || !(p->nn_radius_taubin > 0) || !(p->nn_radius_hands > 0) || !(p->hand_depth > 0)) {
+    set_error("invalid parameters");
+    return AG_ERR_INVALID;
+  }
+  h->c.params = *p;
+  compute_hand_const(h->c.params, h->c.hand);
+  return AG_OK;
+}
+int ag_get_params(ag_ctx* h, ag_params* p) {
+  *p = h->c.params;
+  return AG_OK;
+}
+int ag_get_timings(ag_ctx* h, ag_timings* t) {
+  *t = h->c.timings;
+  return AG_OK;
+}
+void ag_free(void* p) { std::free(p); }
+
+ag_svm* ag_svm_load(const char* path) {
+  SvmModel* m = load_svm(path);
+  if (!m) return nullptr;
+  ag_svm* s = new ag_svm;
+  s->m = m;
+  return s;
+}
+void ag_svm_free(ag_svm* s) {
+  if (!s) return;
+  if (s->m->d_sv) {
+    cudaFree(s->m->d_sv);
+    cudaFree(s->m->d_alpha);
+    cudaFree(s->m->d_index);
+  }
+  delete s->m;
+  delete s;
+}
+int ag_svm_info(const ag_svm* s, int* kernel_type, int* var_count, int* sv_total, double* rho) {
+  if (kernel_type) *kernel_type = s->m->kernel;
+  if (var_count) *var_count = s->m->var_count;
+  if (sv_total) *sv_total = s->m->sv_total;
+  if (rho) *rho = s->m->rho;
+  return AG_OK;
+}
+
+int ag_localize(ag_ctx* h, const void* points, int stride, int n_in, int size_left, const int* indices, int n_indices,
+                unsigned flags, ag_grasp** out, int* n_out) {
+  if (!h || !out || !n_out) return AG_ERR_INVALID;
+  *out = nullptr;
+  *n_out = 0;
+  if (n_in <= 0 || size_left == 0 || !points) {  // localization.cpp:9-15
+    set_error("Input cloud is empty!");
+    return AG_ERR_EMPTY;
+  }
+  if (stride < 12) {
+    set_error("stride must be >= 12 bytes");
+    return AG_ERR_INVALID;
+  }
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  const size_t bytes = size_t(n_in) * stride;
+  if (c.raw.reserve(bytes)) return AG_ERR_CUDA;
+  cudaEventRecord(c.ev[0], c.stream);
+  AG_CUDA_CHECK(cudaMemcpyAsync(c.raw.p, points, bytes, cudaMemcpyHostToDevice, c.stream));
+  int rc = localize_core(&c, c.raw.p, stride, n_in, size_left, indices, n_indices, flags, out, n_out);
+  c.timings.h2d_ms = elapsed(c.ev[0], c.ev[1]);
+  return rc;
+}
+
+int ag_localize_device(ag_ctx* h, const void* d_points, int stride, int n_in, int size_left, const int* indices,
+                       int n_indices, unsigned flags, ag_grasp** out, int* n_out) {
+  if (!h || !out || !n_out) return AG_ERR_INVALID;
+  if (n_in <= 0 || size_left == 0 || !d_points) {
+    set_error("Input cloud is empty!");
+    return AG_ERR_EMPTY;
+  }
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  cudaEventRecord(c.ev[0], c.stream);
+  return localize_core(&c, d_points, stride, n_in, size_left, indices, n_indices, flags, out, n_out);
+}
+
+int ag_classify(ag_ctx* h, const ag_svm* svm, ag_grasp* grasps, int n, uint8_t* keep) {
+  if (!h || !svm) return AG_ERR_INVALID;
+  if (n <= 0) return AG_OK;
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  if (!c.images_valid) {
+    set_error("ag_classify: no grasp images resident (call ag_localize / ag_hand_sweep first)");
+    return AG_ERR_INVALID;
+  }
+  std::vector<int> slots(n);
+  for (int i = 0; i < n; i++) {
+    const int id = grasps[i].image_id;
+    if (id < 0 || id >= c.n_hyp) {
+      set_error("ag_classify: image_id does not belong to the last localize call");
+      return AG_ERR_INVALID;
+    }
+    slots[i] = id;
+  }
+  cudaEventRecord(c.ev[8], c.stream);
+  // image_id h -> raw slot hyp_slots[h]; build the slot list on the device
+  DevBuf& sc = c.scores;
+  if (sc.reserve(size_t(n) * 8 + 64)) return AG_ERR_CUDA;
+  float* d_scores = sc.as<float>();
+  int* d_ids = reinterpret_cast<int*>(d_scores + n);
+  // translate ids to raw slots on the host side of the table (small D2H avoided: keep a host copy)
+  std::vector<int> raw_slots(c.n_hyp);
+  AG_CUDA_CHECK(cudaMemcpyAsync(raw_slots.data(), c.hyp_slots.p, size_t(c.n_hyp) * 4, cudaMemcpyDeviceToHost, c.stream));
+  AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  for (int i = 0; i < n; i++) slots[i] = raw_slots[slots[i]];
+  AG_CUDA_CHECK(cudaMemcpyAsync(d_ids, slots.data(), size_t(n) * 4, cudaMemcpyHostToDevice, c.stream));
+  int rc = hog_svm_device(&c, svm->m, c.images_raw.as<uint32_t>(), d_ids, n, nullptr, d_scores);
+  if (rc) return rc;
+  std::vector<float> sc_h(n);
+  AG_CUDA_CHECK(cudaMemcpyAsync(sc_h.data(), d_scores, size_t(n) * 4, cudaMemcpyDeviceToHost, c.stream));
+  cudaEventRecord(c.ev[9], c.stream);
+  AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  c.timings.hog_svm_ms = elapsed(c.ev[8], c.ev[9]);
+  for (int i = 0; i < n; i++) {
+    grasps[i].score = sc_h[i];
+    // CvSVM::predict: vote[sum > 0 ? 0 : 1], class_labels = [-1, 1] => label +1 <=> sum <= 0
+    grasps[i].label = sc_h[i] > 0 ? 0 : 1;
+    if (keep) keep[i] = grasps[i].label;
+  }
+  return AG_OK;
+}
+
+int ag_get_points(ag_ctx*, int, double**, int32_t**, int*) {
+  set_error("ag_get_points: not implemented in this build");
+  return AG_ERR_INVALID;
+}
+
+int ag_get_images(ag_ctx* h, uint32_t** bits, int* n_images) {
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  *bits = nullptr;
+  *n_images = 0;
+  if (!c.images_valid) {
+    set_error("no grasp images resident");
+    return AG_ERR_INVALID;
+  }
+  const int n = c.n_hyp;
+  std::vector<int> raw_slots(n);
+  uint32_t* out = static_cast<uint32_t*>(std::malloc(std::max<size_t>(1, size_t(n)) * AG_IMAGE_WORDS * 4));
+  if (n > 0) {
+    AG_CUDA_CHECK(cudaMemcpy(raw_slots.data(), c.hyp_slots.p, size_t(n) * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++)
+      AG_CUDA_CHECK(cudaMemcpy(out + size_t(i) * AG_IMAGE_WORDS,
+                               c.images_raw.as<uint32_t>() + size_t(raw_slots[i]) * AG_IMAGE_WORDS, AG_IMAGE_WORDS * 4,
+                               cudaMemcpyDeviceToHost));
+  }
+  *bits = out;
+  *n_images = n;
+  return AG_OK;
+}
+
+// ---- stage-level entry points ----------------------------------------------------------------
+int ag_preprocess(ag_ctx* h, const void* points, int stride, int n_in, int size_left, float** xyz_out,
+                  int32_t** cam_out, int* n_out) {
+  if (!h || !xyz_out || !cam_out || !n_out) return AG_ERR_INVALID;
+  *xyz_out = nullptr;
+  *cam_out = nullptr;
+  *n_out = 0;
+  if (n_in <= 0 || size_left == 0 || !points) {
+    set_error("Input cloud is empty!");
+    return AG_ERR_EMPTY;
+  }
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  const size_t bytes = size_t(n_in) * stride;
+  if (c.raw.reserve(bytes)) return AG_ERR_CUDA;
+  AG_CUDA_CHECK(cudaMemcpyAsync(c.raw.p, points, bytes, cudaMemcpyHostToDevice, c.stream));
+  int rc = preprocess_device(&c, c.raw.p, stride, n_in, size_left);
+  if (rc) return rc;
+  rc = build_grid(&c);
+  if (rc) return rc;
+  const int n = c.n_vox;
+  std::vector<float4> v(n);
+  if (n > 0) AG_CUDA_CHECK(cudaMemcpyAsync(v.data(), c.vox.p, size_t(n) * 16, cudaMemcpyDeviceToHost, c.stream));
+  AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  float* xyz = static_cast<float*>(std::malloc(std::max<size_t>(1, size_t(n)) * 12));
+  int32_t* cam = static_cast<int32_t*>(std::malloc(std::max<size_t>(1, size_t(n)) * 4));
+  for (int i = 0; i < n; i++) {
+    xyz[3 * i] = v[i].x;
+    xyz[3 * i + 1] = v[i].y;
+    xyz[3 * i + 2] = v[i].z;
+    int ci;
+    std::memcpy(&ci, &v[i].w, 4);
+    cam[i] = ci;
+  }
+  *xyz_out = xyz;
+  *cam_out = cam;
+  *n_out = n;
+  return AG_OK;
+}
+
+int ag_set_cloud(ag_ctx* h, const float* xyz, const int32_t* cam, int n) {
+  if (!h || (n > 0 && !xyz)) return AG_ERR_INVALID;
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  c.images_valid = false;
+  std::vector<float4> v(n);
+  for (int i = 0; i < n; i++) {
+    v[i].x = xyz[3 * i];
+    v[i].y = xyz[3 * i + 1];
+    v[i].z = xyz[3 * i + 2];
+    const int ci = cam ? (cam[i] ? 1 : 0) : 0;
+    std::memcpy(&v[i].w, &ci, 4);
+  }
+  if (c.vox.reserve(std::max<size_t>(16, size_t(n) * 16))) return AG_ERR_CUDA;
+  if (n > 0) AG_CUDA_CHECK(cudaMemcpyAsync(c.vox.p, v.data(), size_t(n) * 16, cudaMemcpyHostToDevice, c.stream));
+  AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  int rc = set_cloud_device(&c, n);
+  if (rc) return rc;
+  return build_grid(&c);
+}
+
+int ag_radius_search(ag_ctx* h, const float q[3], double radius, int32_t** idx_out, int* n_out) {
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  std::vector<int> res;
+  int rc = radius_search_device(&c, q, radius, res);
+  if (rc) return rc;
+  std::sort(res.begin(), res.end());
+  int32_t* o = static_cast<int32_t*>(std::malloc(std::max<size_t>(1, res.size()) * 4));
+  std::memcpy(o, res.data(), res.size() * 4);
+  *idx_out = o;
+  *n_out = int(res.size());
+  return AG_OK;
+}
+
+int ag_fit_quadrics(ag_ctx* h, const int* indices, int n_indices, double radius, ag_frame* frames_out) {
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  if (n_indices <= 0) return AG_OK;
+  for (int i = 0; i < n_indices; i++)
+    if (indices[i] < 0 || indices[i] >= c.n_vox) {
+      set_error("sample index out of range");
+      return AG_ERR_INVALID;
+    }
+  if (c.samples.reserve(size_t(n_indices) * 4) || c.frames.reserve(size_t(n_indices) * sizeof(ag_frame)) ||
+      c.counters.reserve(64))
+    return AG_ERR_CUDA;
+  AG_CUDA_CHECK(cudaMemsetAsync(c.counters.p, 0, 64, c.stream));
+  AG_CUDA_CHECK(cudaMemcpyAsync(c.samples.p, indices, size_t(n_indices) * 4, cudaMemcpyHostToDevice, c.stream));
+  int rc = fit_quadrics_device(&c, c.samples.as<int>(), n_indices, radius, c.frames.as<ag_frame>(), false);
+  if (rc) return rc;
+  AG_CUDA_CHECK(cudaMemcpyAsync(frames_out, c.frames.p, size_t(n_indices) * sizeof(ag_frame), cudaMemcpyDeviceToHost,
+                                c.stream));
+  AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  return AG_OK;
+}
+
+int ag_hand_sweep(ag_ctx* h, const int* indices, int n_indices, const ag_frame* frames, const double* cloud_normals,
+                  unsigned flags, ag_grasp** out, int* n_out) {
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  *out = nullptr;
+  *n_out = 0;
+  if (n_indices <= 0) return AG_OK;
+  for (int i = 0; i < n_indices; i++)
+    if (indices[i] < 0 || indices[i] >= c.n_vox) {
+      set_error("sample index out of range");
+      return AG_ERR_INVALID;
+    }
+  if (c.samples.reserve(size_t(n_indices) * 4) || c.frames.reserve(size_t(n_indices) * sizeof(ag_frame)) ||
+      c.counters.reserve(64))
+    return AG_ERR_CUDA;
+  AG_CUDA_CHECK(cudaMemsetAsync(c.counters.p, 0, 64, c.stream));
+  AG_CUDA_CHECK(cudaMemcpyAsync(c.samples.p, indices, size_t(n_indices) * 4, cudaMemcpyHostToDevice, c.stream));
+  AG_CUDA_CHECK(cudaMemcpyAsync(c.frames.p, frames, size_t(n_indices) * sizeof(ag_frame), cudaMemcpyHostToDevice,
+                                c.stream));
+  int rc = set_normals_device(&c, cloud_normals);
+  if (rc) return rc;
+  rc = hand_sweep_device(&c, c.samples.as<int>(), n_indices, c.frames.as<ag_frame>(), flags & 0x100u);
+  if (rc) return rc;
+  const int Hn = c.n_hyp;
+  ag_grasp* res = static_cast<ag_grasp*>(std::malloc(std::max<size_t>(1, size_t(Hn)) * sizeof(ag_grasp)));
+  if (Hn > 0) AG_CUDA_CHECK(cudaMemcpy(res, c.grasps.p, size_t(Hn) * sizeof(ag_grasp), cudaMemcpyDeviceToHost));
+  *out = res;
+  *n_out = Hn;
+  return AG_OK;
+}
+
+int ag_sweep_debug(ag_ctx* h, int n_samples, int32_t* slab_counts, int32_t* debug8) {
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  if (slab_counts) AG_CUDA_CHECK(cudaMemcpy(slab_counts, c.sweep_dbg.p, size_t(n_samples) * 4, cudaMemcpyDeviceToHost));
+  if (debug8)
+    AG_CUDA_CHECK(cudaMemcpy(debug8, c.sweep_dbg.as<int>() + n_samples, size_t(n_samples) * 32, cudaMemcpyDeviceToHost));
+  return AG_OK;
+}
+
+int ag_hog_svm(ag_ctx* h, const ag_svm* svm, const uint32_t* images, int n, float* descriptors, float* scores) {
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  if (n <= 0) return AG_OK;
+  DevBuf img, sc;
+  if (img.reserve(size_t(n) * AG_IMAGE_WORDS * 4) || sc.reserve(size_t(n) * 4)) return AG_ERR_CUDA;
+  if (descriptors && c.descriptors.reserve(size_t(n) * AG_HOG_DIM * 4)) return AG_ERR_CUDA;
+  AG_CUDA_CHECK(cudaMemcpyAsync(img.p, images, size_t(n) * AG_IMAGE_WORDS * 4, cudaMemcpyHostToDevice, c.stream));
+  int rc = hog_svm_device(&c, svm->m, img.as<uint32_t>(), nullptr, n, descriptors ? c.descriptors.as<float>() : nullptr,
+                          sc.as<float>());
+  if (rc == AG_OK) {
+    cudaMemcpyAsync(scores, sc.p, size_t(n) * 4, cudaMemcpyDeviceToHost, c.stream);
+    if (descriptors)
+      cudaMemcpyAsync(descriptors, c.descriptors.p, size_t(n) * AG_HOG_DIM * 4, cudaMemcpyDeviceToHost, c.stream);
+    cudaError_t e = cudaStreamSynchronize(c.stream);
+    if (e != cudaSuccess) {
+      set_error(std::string("hog_svm: ") + cudaGetErrorString(e));
+      rc = AG_ERR_CUDA;
+    }
+  }
+  img.release();
+  sc.release();
+  return rc;
+}
+
+}  // extern "C"

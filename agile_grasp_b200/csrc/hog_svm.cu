@@ -1,0 +1,329 @@
+// hog_svm.cu — grasp image -> HOG(3528) -> SVM decision value, one CTA per hypothesis.
+//
+// Replaces (reference paths): cv::HOGDescriptor::compute as configured at
+// src/agile_grasp/learning.cpp:194-195,220 (default-constructed descriptor: block 16, stride 8,
+// cell 8, 9 bins, gamma correction, sigma 4, L2-Hys 0.2; winSize 64x64, winStride 32, padding 0
+// => 2 windows x 7x7 blocks x 36 = 3528 floats) and CvSVM::predict at learning.cpp:225-226.
+//
+// The image is binary, so after OpenCV's sqrt gamma LUT every pixel gradient is one of 9 cases
+// (dx,dy in {-s,0,+s}, s = sqrt(255.f)); magnitude/angle for the 9 cases are tabulated from
+// cv::cartToPolar (which uses a polynomial atan: the diagonals are NOT k*pi/4).  Block histograms
+// are accumulated by one thread per (block, cell) walking that cell's 144 contributing pixels in
+// exactly OpenCV's order (count1 | count2 | count4 lists, column-major inside the block) with
+// separate binary32 multiply and add, so the descriptor is bit-identical to OpenCV's; the two
+// windows share 4 of their 7 block columns, so only 11x7 = 77 distinct blocks are computed.
+// Compiled with -fmad=false.
+
+#include <cmath>
+#include <cstring>
+
+#include "ag_internal.h"
+
+namespace ag {
+
+namespace {
+
+constexpr int W = AG_IMAGE_COLS, H = AG_IMAGE_ROWS;
+constexpr int NB = 9, BS = 16, CS = 8;
+constexpr int UBX = 11, UBY = 7, NUB = UBX * UBY;  // distinct blocks
+constexpr int CELL_LIST = 144;                      // pixels contributing to one cell of a block
+constexpr int kThreads = 320;                       // >= 77*4 = 308 (block, cell) work items
+
+struct CellEntry {
+  int ofs;    // pixel offset inside the image relative to the block origin: i*W + j
+  float w;    // gradWeight * histWeight (rounded binary32 product, as OpenCV forms it)
+};
+struct HogTables {
+  CellEntry cell[4][CELL_LIST];
+  float g0[9], g1[9];  // magnitude split between the two nearest bins, per gradient case
+  int h0[9], h1[9];
+};
+__constant__ HogTables c_hog;
+
+// cv::cartToPolar(dx,dy) for (sign dx, sign dy): index (sy+1)*3 + (sx+1); values measured from
+// cv2 4.13 (tools/gen_hog_tables.py), stored as bit patterns
+const uint32_t kMagBits[9] = {0x41b4aa5a, 0x417f7fe0, 0x41b4aa5a, 0x417f7fe0, 0x0, 0x417f7fe0, 0x41b4aa5a, 0x417f7fe0,
+                              0x41b4aa5a};
+const uint32_t kAngBits[9] = {0x407b5116, 0x4096cbe4, 0x40afef3d, 0x40490fdb, 0x0, 0x0, 0x4016ce9f, 0x3fc90fdb,
+                              0x3f4904f0};
+
+void build_tables(HogTables& T) {
+  auto u2f = [](uint32_t u) {
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+  };
+  // HOGDescriptor::computeGradient: bin = angle*(nbins/pi) - 0.5, linear split between 2 bins
+  const float angleScale = float(NB / M_PI);
+  for (int k = 0; k < 9; k++) {
+    const float mag = u2f(kMagBits[k]);
+    float angle = u2f(kAngBits[k]) * angleScale - 0.5f;
+    int hidx = int(std::floor(angle));
+    angle -= float(hidx);
+    T.g0[k] = mag * (1.f - angle);
+    T.g1[k] = mag * angle;
+    if (hidx < 0) hidx += NB;
+    else if (hidx >= NB) hidx -= NB;
+    T.h0[k] = hidx;
+    hidx++;
+    if (hidx >= NB) hidx = 0;
+    T.h1[k] = hidx;
+  }
+  // HOGCache::init: gaussian weights exp(-(di^2+dj^2)/(2 sigma^2)), di = i - 8, sigma = 4, and the
+  // bilinear cell interpolation classes; we regroup OpenCV's per-pixel lists into per-cell lists
+  // that preserve the order in which each histogram bin receives its contributions.
+  float weights[BS][BS];
+  const float sigma = 4.0f, scale = 1.f / (sigma * sigma * 2);
+  float d2[BS];
+  for (int i = 0; i < BS; i++) {
+    d2[i] = float(i) - BS * 0.5f;
+    d2[i] *= d2[i];
+  }
+  for (int i = 0; i < BS; i++)
+    for (int j = 0; j < BS; j++) weights[i][j] = std::exp(-(d2[i] + d2[j]) * scale);
+  struct Contribution {
+    int cell, ofs;
+    float w;
+  };
+  std::vector<Contribution> lists[3];  // pixels touching 1, 2, 4 cells
+  for (int j = 0; j < BS; j++)
+    for (int i = 0; i < BS; i++) {
+      float cellX = (j + 0.5f) / CS - 0.5f, cellY = (i + 0.5f) / CS - 0.5f;
+      const int ix0 = int(std::floor(cellX)), iy0 = int(std::floor(cellY));
+      const int ix1 = ix0 + 1, iy1 = iy0 + 1;
+      cellX -= ix0;
+      cellY -= iy0;
+      auto in = [](int v) { return v >= 0 && v < 2; };
+      const float gw = weights[i][j];
+      const int ofs = i * W + j;
+      const float wx[2] = {1.f - cellX, cellX}, wy[2] = {1.f - cellY, cellY};
+      const bool bx = in(ix0) && in(ix1), by = in(iy0) && in(iy1);
+      std::vector<Contribution>& dst = lists[(bx ? 1 : 0) + (by ? 1 : 0)];
+      if (bx && by) {  // order: (x0,y0) (x1,y0) (x0,y1) (x1,y1)
+        dst.push_back({ix0 * 2 + iy0, ofs, gw * (wx[0] * wy[0])});
+        dst.push_back({ix1 * 2 + iy0, ofs, gw * (wx[1] * wy[0])});
+        dst.push_back({ix0 * 2 + iy1, ofs, gw * (wx[0] * wy[1])});
+        dst.push_back({ix1 * 2 + iy1, ofs, gw * (wx[1] * wy[1])});
+      } else if (bx) {  // two cells along x; y clamps to the one valid cell (weight cellY or 1-cellY)
+        const int cy = in(iy0) ? iy0 : iy1;
+        const float wyv = in(iy0) ? 1.f - cellY : cellY;
+        dst.push_back({ix0 * 2 + cy, ofs, gw * (wx[0] * wyv)});
+        dst.push_back({ix1 * 2 + cy, ofs, gw * (wx[1] * wyv)});
+      } else if (by) {
+        const int cx = in(ix0) ? ix0 : ix1;
+        const float wxv = in(ix0) ? 1.f - cellX : cellX;
+        dst.push_back({cx * 2 + iy0, ofs, gw * (wxv * wy[0])});
+        dst.push_back({cx * 2 + iy1, ofs, gw * (wxv * wy[1])});
+      } else {
+        const int cx = in(ix0) ? ix0 : ix1, cy = in(iy0) ? iy0 : iy1;
+        const float wxv = in(ix0) ? 1.f - cellX : cellX, wyv = in(iy0) ? 1.f - cellY : cellY;
+        dst.push_back({cx * 2 + cy, ofs, gw * (wxv * wyv)});
+      }
+    }
+  int fill[4] = {0, 0, 0, 0};
+  for (int cls = 0; cls < 3; cls++)
+    for (const Contribution& c : lists[cls]) {
+      T.cell[c.cell][fill[c.cell]].ofs = c.ofs;
+      T.cell[c.cell][fill[c.cell]].w = c.w;
+      fill[c.cell]++;
+    }
+}
+
+__device__ __forceinline__ int reflect101(int p, int len) {  // cv::borderInterpolate, BORDER_REFLECT_101
+  return p < 0 ? -p : (p >= len ? 2 * len - 2 - p : p);
+}
+
+struct SvmDev {
+  const float* sv;
+  const double* alpha;
+  const int* index;
+  int sv_total, sv_count, kernel, degree;
+  double gamma, coef0, rho;
+};
+
+__global__ void __launch_bounds__(kThreads)
+k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slots, int n, SvmDev svm,
+          float* __restrict__ descriptors, float* __restrict__ scores) {
+  __shared__ uint32_t s_bits[AG_IMAGE_WORDS];
+  __shared__ uint8_t s_case[W * H];
+  __shared__ float s_hist[NUB * 36];
+  __shared__ float s_K[1280];       // kernel values per support vector (sv_total <= 1280 in-smem)
+  __shared__ double s_part[kThreads / 32];
+  const int hyp = blockIdx.x;
+  if (hyp >= n) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t* src = images + size_t(image_slots ? image_slots[hyp] : hyp) * AG_IMAGE_WORDS;
+  for (int i = tid; i < AG_IMAGE_WORDS; i += kThreads) s_bits[i] = src[i];
+  __syncthreads();
+  // gradient case per pixel
+  auto px = [&](int y, int x) -> int {
+    const int b = y * W + x;
+    return (s_bits[b >> 5] >> (b & 31)) & 1u;
+  };
+  for (int p = tid; p < W * H; p += kThreads) {
+    const int y = p / W, x = p % W;
+    const int sx = px(y, reflect101(x + 1, W)) - px(y, reflect101(x - 1, W));
+    const int sy = px(reflect101(y + 1, H), x) - px(reflect101(y - 1, H), x);
+    s_case[p] = uint8_t((sy + 1) * 3 + (sx + 1));
+  }
+  __syncthreads();
+  // block histograms: one thread per (distinct block, cell)
+  if (tid < NUB * 4) {
+    const int ub = tid >> 2, cell = tid & 3;
+    const int ubx = ub / UBY, uby = ub % UBY;
+    const uint8_t* gc = s_case + (uby * 8) * W + ubx * 8;
+    float h[9];
+#pragma unroll
+    for (int b = 0; b < 9; b++) h[b] = 0.f;
+    for (int v = 0; v < CELL_LIST; v++) {
+      const CellEntry ce = c_hog.cell[cell][v];
+      const int c = gc[ce.ofs];
+      if (c == 4) continue;  // zero gradient: adds +0 to both bins
+      const float a0 = __fmul_rn(c_hog.g0[c], ce.w), a1 = __fmul_rn(c_hog.g1[c], ce.w);
+      const int b0 = c_hog.h0[c], b1 = c_hog.h1[c];
+#pragma unroll
+      for (int b = 0; b < 9; b++) {
+        if (b == b0) h[b] = __fadd_rn(h[b], a0);
+        if (b == b1) h[b] = __fadd_rn(h[b], a1);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < 9; b++) s_hist[ub * 36 + cell * 9 + b] = h[b];
+  }
+  __syncthreads();
+  // L2-Hys normalisation per block (HOGCache::normalizeBlockHistogram), 4 interleaved partial sums
+  if (tid < NUB) {
+    float* hist = s_hist + tid * 36;
+    float part[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < 36; i += 4)
+#pragma unroll
+      for (int l = 0; l < 4; l++) part[l] = __fadd_rn(part[l], __fmul_rn(hist[i + l], hist[i + l]));
+    float sum = __fadd_rn(__fadd_rn(part[0], part[1]), __fadd_rn(part[2], part[3]));
+    float scale = __fdiv_rn(1.f, __fadd_rn(__fsqrt_rn(sum), __fmul_rn(36.f, 0.1f)));
+    part[0] = part[1] = part[2] = part[3] = 0.f;
+    for (int i = 0; i < 36; i += 4)
+#pragma unroll
+      for (int l = 0; l < 4; l++) {
+        const float p = fminf(__fmul_rn(hist[i + l], scale), 0.2f);
+        hist[i + l] = p;
+        part[l] = __fadd_rn(part[l], __fmul_rn(p, p));
+      }
+    sum = __fadd_rn(__fadd_rn(part[0], part[1]), __fadd_rn(part[2], part[3]));
+    scale = __fdiv_rn(1.f, __fadd_rn(__fsqrt_rn(sum), 1e-3f));
+    for (int i = 0; i < 36; i++) hist[i] = __fmul_rn(hist[i], scale);
+  }
+  __syncthreads();
+  // descriptor element k -> histogram entry: k = ((w*7 + bx)*7 + by)*36 + e
+  auto desc_at = [&](int k) -> float {
+    const int e = k % 36, blk = k / 36;
+    const int by = blk % 7, bx = (blk / 7) % 7, w = blk / 49;
+    return s_hist[((w * 4 + bx) * UBY + by) * 36 + e];
+  };
+  if (descriptors)
+    for (int k = tid; k < AG_HOG_DIM; k += kThreads) descriptors[size_t(hyp) * AG_HOG_DIM + k] = desc_at(k);
+  // SVM kernel values (CvSVMKernel::calc_non_rbf_base): binary32 products, 4-term binary32 sums,
+  // binary64 accumulation; one warp per support vector
+  for (int j = warp; j < svm.sv_total; j += kThreads / 32) {
+    const float* sv = svm.sv + size_t(j) * AG_HOG_DIM;
+    double acc = 0.0;
+    for (int k4 = lane; k4 < AG_HOG_DIM / 4; k4 += 32) {
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(sv) + k4);
+      const int k = k4 * 4;
+      float t = __fmul_rn(s4.x, desc_at(k));
+      t = __fadd_rn(t, __fmul_rn(s4.y, desc_at(k + 1)));
+      t = __fadd_rn(t, __fmul_rn(s4.z, desc_at(k + 2)));
+      t = __fadd_rn(t, __fmul_rn(s4.w, desc_at(k + 3)));
+      acc += double(t);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float kv;
+      if (svm.kernel == 0) kv = float(acc * 1.0 + 0.0);
+      else {
+        kv = float(acc * svm.gamma + svm.coef0);
+        // cv::pow with an integer exponent: repeated binary32 multiplication
+        float b = kv, a = 1.f;
+        int p = svm.degree;
+        while (p > 1) {
+          if (p & 1) a = __fmul_rn(a, b);
+          b = __fmul_rn(b, b);
+          p >>= 1;
+        }
+        kv = __fmul_rn(a, b);
+      }
+      if (j < 1280) s_K[j] = kv;
+    }
+  }
+  __syncthreads();
+  // decision value: sum = -rho + sum_k alpha_k * K[index_k]   (CvSVM::predict)
+  double part = 0.0;
+  for (int kk = tid; kk < svm.sv_count; kk += kThreads) part += svm.alpha[kk] * double(s_K[svm.index[kk]]);
+  part = warp_sum(part);
+  if (lane == 0) s_part[warp] = part;
+  __syncthreads();
+  if (tid == 0) {
+    double sum = -svm.rho;
+    for (int w2 = 0; w2 < kThreads / 32; w2++) sum += s_part[w2];
+    scores[hyp] = float(sum);
+  }
+}
+
+bool g_tables_ready[64] = {false};
+
+}  // namespace
+
+int svm_to_device(SvmModel* svm, int device) {
+  if (svm->device == device && svm->d_sv) return AG_OK;
+  if (svm->d_sv) {
+    cudaFree(svm->d_sv);
+    cudaFree(svm->d_alpha);
+    cudaFree(svm->d_index);
+    svm->d_sv = nullptr;
+  }
+  AG_CUDA_CHECK(cudaMalloc(&svm->d_sv, svm->sv.size() * sizeof(float)));
+  AG_CUDA_CHECK(cudaMalloc(&svm->d_alpha, svm->alpha.size() * sizeof(double)));
+  AG_CUDA_CHECK(cudaMalloc(&svm->d_index, svm->index.size() * sizeof(int)));
+  AG_CUDA_CHECK(cudaMemcpy(svm->d_sv, svm->sv.data(), svm->sv.size() * sizeof(float), cudaMemcpyHostToDevice));
+  AG_CUDA_CHECK(cudaMemcpy(svm->d_alpha, svm->alpha.data(), svm->alpha.size() * sizeof(double), cudaMemcpyHostToDevice));
+  AG_CUDA_CHECK(cudaMemcpy(svm->d_index, svm->index.data(), svm->index.size() * sizeof(int), cudaMemcpyHostToDevice));
+  svm->device = device;
+  return AG_OK;
+}
+
+int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d_image_slots, int n,
+                   float* d_descriptors, float* d_scores) {
+  if (n <= 0) return AG_OK;
+  if (svm->var_count != AG_HOG_DIM) {
+    set_error("SVM var_count != 3528");
+    return AG_ERR_INVALID;
+  }
+  if (svm->sv_total > 1280) {
+    set_error("SVM has more than 1280 support vectors");
+    return AG_ERR_CAPACITY;
+  }
+  if (!g_tables_ready[c->device & 63]) {
+    HogTables T;
+    std::memset(&T, 0, sizeof(T));
+    build_tables(T);
+    AG_CUDA_CHECK(cudaMemcpyToSymbol(c_hog, &T, sizeof(T)));
+    g_tables_ready[c->device & 63] = true;
+  }
+  int rc = svm_to_device(svm, c->device);
+  if (rc) return rc;
+  SvmDev sd;
+  sd.sv = svm->d_sv;
+  sd.alpha = svm->d_alpha;
+  sd.index = svm->d_index;
+  sd.sv_total = svm->sv_total;
+  sd.sv_count = svm->sv_count;
+  sd.kernel = svm->kernel;
+  sd.degree = svm->degree;
+  sd.gamma = svm->gamma;
+  sd.coef0 = svm->coef0;
+  sd.rho = svm->rho;
+  k_hog_svm<<<n, kThreads, 0, c->stream>>>(d_images, d_image_slots, n, sd, d_descriptors, d_scores);
+  AG_CUDA_CHECK(cudaGetLastError());
+  return AG_OK;
+}
+
+}  // namespace ag

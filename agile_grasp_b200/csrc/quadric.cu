@@ -1,0 +1,561 @@
+// quadric.cu — Taubin quadric fit and local frame, one warp per sample.
+//
+// Replaces (reference paths): HandSearch::findQuadrics (src/agile_grasp/hand_search.cpp:65-113),
+// pcl::KdTreeFLANN::radiusSearch (:85), Quadric::fitQuadric (src/agile_grasp/quadric.cpp:14-157, LAPACK
+// dggev_ :330-363), Quadric::findTaubinNormalAxis (:159-251) and findAverageNormalAxis (:263-305).
+//
+// GPU formulation:
+//  * k_taubin_moments: each warp walks the <=3x3 z-contiguous cell columns that cover its sample's
+//    ball, tests membership with FLANN's exact binary32 arithmetic, compacts accepted points through a
+//    64-entry shared-memory ring and accumulates the 35 monomial moments of degree <=4 in binary64
+//    registers — in coordinates centred on the sample and scaled by 1/r (Taubin's fit is invariant
+//    under translation and uniform scale, and the centred problem is well conditioned whereas the
+//    reference's uncentred 10x10 pencil is not).  Warp-shuffle reduction, 36 doubles out per sample.
+//  * k_taubin_axes: builds M and N from the moments, eliminates the constant term
+//    (A - m m^T/n) u = lambda B u, Cholesky + cyclic Jacobi on the 9x9 symmetric-definite pencil in
+//    shared memory, then two more ball walks for the gradient normals: one accumulates sum g g^T and
+//    the symmetric order-6 moment tensor T = sum g^(x6) (28 numbers), the other evaluates
+//    sum_i (g_i . g_j)^6 = <T, g_j^(x6)> for every j — O(m) instead of the reference's O(m^2) — and
+//    takes the arg max with the reference's first-max tie-break in (distance, index) order.
+
+#include "ag_internal.h"
+
+namespace ag {
+
+namespace {
+
+constexpr int kWarps = 8;  // warps per CTA
+
+// ---- monomial bookkeeping ---------------------------------------------------------------------
+// index of the moment sum x^a y^b z^c, a+b+c <= 4
+__host__ __device__ constexpr int midx(int a, int b, int c) {
+  const int k = a * 25 + b * 5 + c;
+  return k == 0 ? 0 : k == 25 ? 1 : k == 5 ? 2 : k == 1 ? 3 : k == 50 ? 4 : k == 10 ? 5 : k == 2 ? 6 : k == 30 ? 7
+       : k == 6 ? 8 : k == 26 ? 9 : k == 75 ? 10 : k == 15 ? 11 : k == 3 ? 12 : k == 55 ? 13 : k == 51 ? 14
+       : k == 35 ? 15 : k == 11 ? 16 : k == 27 ? 17 : k == 7 ? 18 : k == 31 ? 19 : k == 100 ? 20 : k == 20 ? 21
+       : k == 4 ? 22 : k == 80 ? 23 : k == 76 ? 24 : k == 40 ? 25 : k == 16 ? 26 : k == 28 ? 27 : k == 8 ? 28
+       : k == 60 ? 29 : k == 12 ? 30 : k == 52 ? 31 : k == 56 ? 32 : k == 36 ? 33 : k == 32 ? 34 : -1;
+}
+constexpr int kNumMoments = 35;
+constexpr int kMomentStride = 36;  // + count of camera-1 neighbours
+
+// exponents of the quadric basis [x2 y2 z2 xy yz xz x y z 1] (quadric.cpp:40-73)
+__constant__ int c_basis[10][3] = {{2, 0, 0}, {0, 2, 0}, {0, 0, 2}, {1, 1, 0}, {0, 1, 1},
+                                   {1, 0, 1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 0, 0}};
+
+// ---- warp-level ball walk with compaction ----------------------------------------------------
+// Calls f(point, active) with all 32 lanes converged; `active` lanes hold distinct accepted
+// neighbours.  Batches are full (32 active) except the last one.
+template <typename F>
+__device__ __forceinline__ void walk_ball(const GPoint* __restrict__ pts, const int* __restrict__ cell_start,
+                                          const GridDesc& g, float qx, float qy, float qz, float r2, double rpad,
+                                          GPoint* ring /*64 entries, this warp's*/, int& n_cand, F&& f) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const QueryBox b = query_box(g, qx, qy, qz, rpad);
+  const int ncy = b.hi[1] - b.lo[1] + 1;
+  const int ncol = (b.hi[0] - b.lo[0] + 1) * ncy;
+  int head = 0, qn = 0;
+  auto push = [&](const GPoint& p, bool ok) {
+    unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (m == 0) return;
+    if (ok) ring[(head + qn + __popc(m & lt)) & 63] = p;
+    qn += __popc(m);
+    __syncwarp();
+    if (qn >= 32) {
+      GPoint v = ring[(head + lane) & 63];
+      __syncwarp();
+      f(v, true);
+      head = (head + 32) & 63;
+      qn -= 32;
+    }
+  };
+  for (int cbase = 0; cbase < ncol; cbase += 32) {
+    const int col = cbase + lane;
+    int s = 0, e = 0;
+    if (col < ncol) {
+      const int cx = b.lo[0] + col / ncy, cy = b.lo[1] + col % ncy;
+      s = __ldg(cell_start + cell_linear(g, cx, cy, b.lo[2]));
+      e = __ldg(cell_start + cell_linear(g, cx, cy, b.hi[2]) + 1);
+    }
+    const int ncur = min(32, ncol - cbase);
+    for (int k = 0; k < ncur; k++) {
+      const int rs = __shfl_sync(0xffffffffu, s, k), re = __shfl_sync(0xffffffffu, e, k);
+      n_cand += re - rs;
+      for (int j0 = rs; j0 < re; j0 += 64) {
+        const int ja = j0 + lane, jb = ja + 32;
+        GPoint pa, pb;
+        pa.x = pa.y = pa.z = 0.f; pa.tag = 0;
+        pb = pa;
+        if (ja < re) pa = pts[ja];
+        if (jb < re) pb = pts[jb];
+        push(pa, ja < re && dist2_flann(qx, qy, qz, pa.x, pa.y, pa.z) < r2);
+        if (j0 + 32 < re) push(pb, jb < re && dist2_flann(qx, qy, qz, pb.x, pb.y, pb.z) < r2);
+      }
+    }
+  }
+  if (qn > 0) {
+    GPoint v = ring[(head + lane) & 63];
+    __syncwarp();
+    f(v, lane < qn);
+  }
+}
+
+// ---- kernel 1: moments ------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarps * 32)
+k_taubin_moments(const GPoint* __restrict__ pts, const int* __restrict__ cell_start, GridDesc g,
+                 const float4* __restrict__ vox, const int* __restrict__ indices, int n_samples, float r2,
+                 double rpad, double inv_r, double* __restrict__ moments, int* __restrict__ nn_counts,
+                 unsigned long long* __restrict__ counters) {
+  __shared__ GPoint s_ring[kWarps][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * kWarps + warp;
+  if (s >= n_samples) return;
+  const float4 q = vox[indices[s]];
+  const double qx = double(q.x), qy = double(q.y), qz = double(q.z);
+  double acc[kNumMoments];
+#pragma unroll
+  for (int i = 0; i < kNumMoments; i++) acc[i] = 0.0;
+  int cam1 = 0, n_cand = 0;
+  walk_ball(pts, cell_start, g, q.x, q.y, q.z, r2, rpad, s_ring[warp], n_cand, [&](const GPoint& p, bool active) {
+    if (!active) return;
+    const double x = (double(p.x) - qx) * inv_r, y = (double(p.y) - qy) * inv_r, z = (double(p.z) - qz) * inv_r;
+    const double x2 = x * x, y2 = y * y, z2 = z * z, xy = x * y, yz = y * z, xz = x * z;
+    acc[0] += 1.0;
+    acc[1] += x; acc[2] += y; acc[3] += z;
+    acc[4] += x2; acc[5] += y2; acc[6] += z2; acc[7] += xy; acc[8] += yz; acc[9] += xz;
+    acc[10] += x2 * x; acc[11] += y2 * y; acc[12] += z2 * z; acc[13] += x2 * y; acc[14] += x2 * z;
+    acc[15] += x * y2; acc[16] += y2 * z; acc[17] += x * z2; acc[18] += y * z2; acc[19] += xy * z;
+    acc[20] += x2 * x2; acc[21] += y2 * y2; acc[22] += z2 * z2; acc[23] += x2 * xy; acc[24] += x2 * xz;
+    acc[25] += xy * y2; acc[26] += y2 * yz; acc[27] += xz * z2; acc[28] += yz * z2; acc[29] += x2 * y2;
+    acc[30] += y2 * z2; acc[31] += x2 * z2; acc[32] += x2 * yz; acc[33] += xy * yz; acc[34] += xz * yz;
+    cam1 += (p.tag & kTagCamBit) ? 1 : 0;
+  });
+#pragma unroll
+  for (int i = 0; i < kNumMoments; i++) acc[i] = warp_sum(acc[i]);
+  cam1 = __reduce_add_sync(0xffffffffu, cam1);
+  double* out = moments + size_t(s) * kMomentStride;
+  // lane i writes moment i (after the xor-reduction every lane holds every sum)
+#pragma unroll
+  for (int i = 0; i < kNumMoments; i++)
+    if (lane == (i & 31)) out[i] = acc[i];
+  if (lane == 0) {
+    out[35] = double(cam1);
+    nn_counts[s] = int(acc[0]);
+    atomicAdd(&counters[0], (unsigned long long)(acc[0]));
+    atomicAdd(&counters[1], (unsigned long long)(n_cand));
+  }
+}
+
+// ---- small dense helpers (per warp, shared memory, lane-parallel where it is cheap) -----------
+struct AxesSmem {
+  double A[81];   // Schur complement, later C = L^-1 A L^-T, diagonalised in place
+  double L[81];   // B, then its Cholesky factor
+  double V[81];   // Jacobi eigenvectors
+  double m[10];   // last column of M (9 entries) and n
+  double par[10]; // quadric parameters in centred/scaled coordinates
+  double T[28];   // weighted order-6 normal tensor
+  GPoint ring[64];
+};
+
+__device__ __forceinline__ void jacobi_rotate_params(double app, double aqq, double apq, double& c, double& s) {
+  // classic stable formulas (Golub & Van Loan 8.4)
+  if (apq == 0.0) {
+    c = 1.0;
+    s = 0.0;
+    return;
+  }
+  const double theta = (aqq - app) / (2.0 * apq);
+  const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+  c = 1.0 / sqrt(t * t + 1.0);
+  s = t * c;
+}
+
+// cyclic Jacobi on the n x n symmetric matrix A (row-major, stride n) with eigenvectors in V;
+// executed by one warp: every lane computes the rotation, lanes 0..n-1 apply it.
+template <int N>
+__device__ void warp_jacobi(double* A, double* V, int lane) {
+  for (int i = lane; i < N * N; i += 32) V[i] = (i / N == i % N) ? 1.0 : 0.0;
+  __syncwarp();
+  // Rotations are skipped when |a_pq| <= eps*sqrt(a_pp*a_qq) (the scaled criterion that gives
+  // positive-definite matrices high RELATIVE accuracy in their small eigenvalues / eigenvectors —
+  // the pair we need is the smallest one); a sweep without rotations ends the iteration.
+  for (int sweep = 0; sweep < 30; sweep++) {
+    bool rotated = false;
+    for (int p = 0; p < N - 1; p++)
+      for (int q = p + 1; q < N; q++) {
+        const double app = A[p * N + p], aqq = A[q * N + q], apq = A[p * N + q];
+        if (!(fabs(apq) > 1.0e-16 * sqrt(fabs(app * aqq)))) continue;  // uniform across the warp
+        rotated = true;
+        double c, s;
+        jacobi_rotate_params(app, aqq, apq, c, s);
+        __syncwarp();
+        if (lane < N) {  // columns p,q of A and V
+          const int k = lane;
+          const double akp = A[k * N + p], akq = A[k * N + q];
+          A[k * N + p] = c * akp - s * akq;
+          A[k * N + q] = s * akp + c * akq;
+          const double vkp = V[k * N + p], vkq = V[k * N + q];
+          V[k * N + p] = c * vkp - s * vkq;
+          V[k * N + q] = s * vkp + c * vkq;
+        }
+        __syncwarp();
+        if (lane < N) {  // rows p,q of A
+          const int k = lane;
+          const double apk = A[p * N + k], aqk = A[q * N + k];
+          A[p * N + k] = c * apk - s * aqk;
+          A[q * N + k] = s * apk + c * aqk;
+        }
+        __syncwarp();
+        if (lane == 0) A[p * N + q] = A[q * N + p] = 0.0;  // annihilated exactly by construction
+        __syncwarp();
+      }
+    if (!rotated) break;
+  }
+}
+
+// symmetric 3x3 eigen-decomposition in registers (every lane redundantly)
+__device__ void eig3(const double Cm[6] /*xx yy zz xy yz xz*/, double w[3], double V[3][3]) {
+  double a[3][3] = {{Cm[0], Cm[3], Cm[5]}, {Cm[3], Cm[1], Cm[4]}, {Cm[5], Cm[4], Cm[2]}};
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) V[i][j] = i == j ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 40; sweep++) {
+    const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+    const double diag = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
+    if (off <= 1e-34 * diag || off == 0.0) break;
+#pragma unroll
+    for (int p = 0; p < 2; p++)
+#pragma unroll
+      for (int q = p + 1; q < 3; q++) {
+        double c, s;
+        jacobi_rotate_params(a[p][p], a[q][q], a[p][q], c, s);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const double akp = a[k][p], akq = a[k][q];
+          a[k][p] = c * akp - s * akq;
+          a[k][q] = s * akp + c * akq;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const double apk = a[p][k], aqk = a[q][k];
+          a[p][k] = c * apk - s * aqk;
+          a[q][k] = s * apk + c * aqk;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - s * vkq;
+          V[k][q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  w[0] = a[0][0];
+  w[1] = a[1][1];
+  w[2] = a[2][2];
+}
+
+// gradient direction of the implicit quadric at (x,y,z)   (quadric.cpp:238-247)
+__device__ __forceinline__ void quad_normal(const double* par, double x, double y, double z, double g[3]) {
+  const double fx = 2.0 * par[0] * x + par[3] * y + par[5] * z + par[6];
+  const double fy = 2.0 * par[1] * y + par[3] * x + par[4] * z + par[7];
+  const double fz = 2.0 * par[2] * z + par[4] * y + par[5] * x + par[8];
+  const double inv = 1.0 / sqrt(fx * fx + fy * fy + fz * fz);
+  g[0] = fx * inv;
+  g[1] = fy * inv;
+  g[2] = fz * inv;
+}
+
+// the 28 monomials g^alpha, |alpha| = 6, in a fixed order (a descending, then b descending)
+__device__ __forceinline__ void monomials6(const double g[3], double out[28]) {
+  double px[7], py[7], pz[7];
+  px[0] = py[0] = pz[0] = 1.0;
+#pragma unroll
+  for (int k = 1; k <= 6; k++) {
+    px[k] = px[k - 1] * g[0];
+    py[k] = py[k - 1] * g[1];
+    pz[k] = pz[k - 1] * g[2];
+  }
+  int t = 0;
+#pragma unroll
+  for (int a = 6; a >= 0; a--)
+#pragma unroll
+    for (int b = 6 - a; b >= 0; b--) out[t++] = px[a] * py[b] * pz[6 - a - b];
+}
+__constant__ double c_multinomial6[28] = {
+    1,                          // a=6
+    6, 6,                       // a=5: b=1,0
+    15, 30, 15,                 // a=4: b=2,1,0
+    20, 60, 60, 20,             // a=3
+    15, 60, 90, 60, 15,         // a=2
+    6, 30, 60, 60, 30, 6,       // a=1
+    1, 6, 15, 20, 15, 6, 1};    // a=0
+
+// ---- kernel 2: eigen-solve + local axes -------------------------------------------------------
+__global__ void __launch_bounds__(kWarps * 32)
+k_taubin_axes(const GPoint* __restrict__ pts_c, const int* __restrict__ cell_start, GridDesc g,
+              const float4* __restrict__ vox, const int* __restrict__ indices,
+              int n_samples, float r2, double rpad, double inv_r, const double* __restrict__ moments,
+              double cam0x, double cam0y, double cam0z, double cam1x, double cam1y, double cam1z,
+              ag_frame* __restrict__ frames, double* normals_out /* may be null */) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  AxesSmem* sm_all = reinterpret_cast<AxesSmem*>(s_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * kWarps + warp;
+  if (s >= n_samples) return;
+  AxesSmem& sm = sm_all[warp];
+  const int idx = indices[s];
+  const float4 q = vox[idx];
+  const double qx = double(q.x), qy = double(q.y), qz = double(q.z);
+  const double* mom = moments + size_t(s) * kMomentStride;
+  const double n = mom[0];
+  ag_frame F;
+  F.num_neighbors = int(n);
+  const int major = (mom[35] > n - mom[35]) ? 1 : 0;  // quadric.cpp:217-226 (tie -> camera 0)
+  F.majority_cam = major;
+
+  // --- build the reduced pencil: A = M[0:9,0:9] - m m^T / n, B = N[0:9,0:9]
+  for (int e = lane; e < 81; e += 32) {
+    const int i = e / 9, j = e % 9;
+    const int* bi = c_basis[i];
+    const int* bj = c_basis[j];
+    const double mij = mom[midx(bi[0] + bj[0], bi[1] + bj[1], bi[2] + bj[2])];
+    const double mi = mom[midx(bi[0], bi[1], bi[2])], mj = mom[midx(bj[0], bj[1], bj[2])];
+    sm.A[e] = mij - mi * mj / n;
+    double bsum = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      if (bi[a] >= 1 && bj[a] >= 1) {
+        int ex[3] = {bi[0] + bj[0], bi[1] + bj[1], bi[2] + bj[2]};
+        ex[a] -= 2;
+        bsum += double(bi[a] * bj[a]) * mom[midx(ex[0], ex[1], ex[2])];
+      }
+    }
+    sm.L[e] = bsum;
+  }
+  if (lane < 9) sm.m[lane] = mom[midx(c_basis[lane][0], c_basis[lane][1], c_basis[lane][2])];
+  __syncwarp();
+
+  // --- Cholesky B = L L^T (lane-parallel over rows below the pivot); tiny ridge only if needed
+  bool ok = n >= 1.0;
+  {
+    double dmax = 0.0;
+    for (int i = 0; i < 9; i++) dmax = fmax(dmax, sm.L[i * 9 + i]);
+    if (!(dmax > 0.0)) ok = false;
+    const double tol = 1e-13 * dmax;
+    for (int k = 0; k < 9 && ok; k++) {
+      double piv = sm.L[k * 9 + k];
+      if (!(piv > tol)) piv = tol > 0 ? tol : 1e-300;  // singular direction (e.g. exactly planar data)
+      const double d = sqrt(piv);
+      __syncwarp();
+      if (lane == 0) sm.L[k * 9 + k] = d;
+      if (lane > k && lane < 9) sm.L[lane * 9 + k] /= d;
+      __syncwarp();
+      // trailing update: entries (i,j), k < j <= i < 9
+      for (int e = lane; e < 81; e += 32) {
+        const int i = e / 9, j = e % 9;
+        if (j > k && i >= j) sm.L[i * 9 + j] -= sm.L[i * 9 + k] * sm.L[j * 9 + k];
+      }
+      __syncwarp();
+    }
+  }
+  // --- C = L^-1 A L^-T : X = L^-1 A (columns in parallel), then C^T = L^-1 X^T
+  if (lane < 9) {
+    const int col = lane;
+    for (int i = 0; i < 9; i++) {
+      double v = sm.A[i * 9 + col];
+      for (int k = 0; k < i; k++) v -= sm.L[i * 9 + k] * sm.A[k * 9 + col];
+      sm.A[i * 9 + col] = v / sm.L[i * 9 + i];
+    }
+  }
+  __syncwarp();
+  if (lane < 9) {
+    const int row = lane;  // solve L y = (row of X)^T
+    for (int i = 0; i < 9; i++) {
+      double v = sm.A[row * 9 + i];
+      for (int k = 0; k < i; k++) v -= sm.L[i * 9 + k] * sm.A[row * 9 + k];
+      sm.A[row * 9 + i] = v / sm.L[i * 9 + i];
+    }
+  }
+  __syncwarp();
+  // symmetrise (round-off) and diagonalise
+  for (int e = lane; e < 81; e += 32) {
+    const int i = e / 9, j = e % 9;
+    if (i < j) {
+      const double v = 0.5 * (sm.A[i * 9 + j] + sm.A[j * 9 + i]);
+      sm.A[i * 9 + j] = v;
+      sm.A[j * 9 + i] = v;
+    }
+  }
+  __syncwarp();
+  warp_jacobi<9>(sm.A, sm.V, lane);
+  // smallest eigenvalue (quadric.cpp:149-152), u = L^-T y, j = -m.u/n
+  int mi = 0;
+  for (int k = 1; k < 9; k++)
+    if (sm.A[k * 9 + k] < sm.A[mi * 9 + mi]) mi = k;
+  __syncwarp();
+  if (lane == 0) {
+    double u[9];
+    for (int i = 8; i >= 0; i--) {
+      double v = sm.V[i * 9 + mi];
+      for (int k = i + 1; k < 9; k++) v -= sm.L[k * 9 + i] * u[k];
+      u[i] = v / sm.L[i * 9 + i];
+    }
+    double mu = 0.0;
+    for (int i = 0; i < 9; i++) {
+      sm.par[i] = u[i];
+      mu += sm.m[i] * u[i];
+    }
+    sm.par[9] = -mu / n;
+  }
+  __syncwarp();
+  double par[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) par[i] = sm.par[i];
+
+  // --- walk 2: C = sum g g^T and T = sum g^(x6)
+  double acc[34];
+#pragma unroll
+  for (int i = 0; i < 34; i++) acc[i] = 0.0;
+  int n_cand = 0;
+  walk_ball(pts_c, cell_start, g, q.x, q.y, q.z, r2, rpad, sm.ring, n_cand, [&](const GPoint& p, bool active) {
+    if (!active) return;
+    const double x = (double(p.x) - qx) * inv_r, y = (double(p.y) - qy) * inv_r, z = (double(p.z) - qz) * inv_r;
+    double gn[3], m6[28];
+    quad_normal(par, x, y, z, gn);
+    acc[0] += gn[0] * gn[0]; acc[1] += gn[1] * gn[1]; acc[2] += gn[2] * gn[2];
+    acc[3] += gn[0] * gn[1]; acc[4] += gn[1] * gn[2]; acc[5] += gn[0] * gn[2];
+    monomials6(gn, m6);
+#pragma unroll
+    for (int t = 0; t < 28; t++) acc[6 + t] += m6[t];
+  });
+#pragma unroll
+  for (int i = 0; i < 34; i++) acc[i] = warp_sum(acc[i]);
+  double w3[3], V3[3][3];
+  eig3(acc, w3, V3);
+  int m3 = 0;
+  if (w3[1] < w3[m3]) m3 = 1;
+  if (w3[2] < w3[m3]) m3 = 2;  // quadric.cpp:278-280
+  double ax[3] = {V3[0][m3], V3[1][m3], V3[2][m3]};
+  if (lane < 28) sm.T[lane] = acc[6 + lane] * c_multinomial6[lane];
+  __syncwarp();
+
+  // --- walk 3: j* = argmax_j sum_i (g_i.g_j)^6 = argmax_j <T, g_j^(x6)>, first max in (dist, index) order
+  double bestS = -1.0;
+  float bestD = 3.0e38f;
+  unsigned bestI = 0xFFFFFFFFu;
+  double bestG[3] = {0, 0, 0};
+  walk_ball(pts_c, cell_start, g, q.x, q.y, q.z, r2, rpad, sm.ring, n_cand, [&](const GPoint& p, bool active) {
+    if (!active) return;
+    const double x = (double(p.x) - qx) * inv_r, y = (double(p.y) - qy) * inv_r, z = (double(p.z) - qz) * inv_r;
+    double gn[3], m6[28];
+    quad_normal(par, x, y, z, gn);
+    monomials6(gn, m6);
+    double S = 0.0;
+#pragma unroll
+    for (int t = 0; t < 28; t++) S += sm.T[t] * m6[t];
+    const float d = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
+    const unsigned id = p.tag & kTagIndexMask;
+    const bool better = S > bestS || (S == bestS && (d < bestD || (d == bestD && id < bestI)));
+    if (better) {
+      bestS = S; bestD = d; bestI = id;
+      bestG[0] = gn[0]; bestG[1] = gn[1]; bestG[2] = gn[2];
+    }
+  });
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oS = __shfl_xor_sync(0xffffffffu, bestS, o);
+    const float oD = __shfl_xor_sync(0xffffffffu, bestD, o);
+    const unsigned oI = __shfl_xor_sync(0xffffffffu, bestI, o);
+    const double g0 = __shfl_xor_sync(0xffffffffu, bestG[0], o);
+    const double g1 = __shfl_xor_sync(0xffffffffu, bestG[1], o);
+    const double g2 = __shfl_xor_sync(0xffffffffu, bestG[2], o);
+    const bool better = oS > bestS || (oS == bestS && (oD < bestD || (oD == bestD && oI < bestI)));
+    if (better) {
+      bestS = oS; bestD = oD; bestI = oI;
+      bestG[0] = g0; bestG[1] = g1; bestG[2] = g2;
+    }
+  }
+  // --- frame (quadric.cpp:285-304)
+  double np[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    const double d0 = (r == 0 ? 1.0 : 0.0) - ax[r] * ax[0];
+    const double d1 = (r == 1 ? 1.0 : 0.0) - ax[r] * ax[1];
+    const double d2 = (r == 2 ? 1.0 : 0.0) - ax[r] * ax[2];
+    np[r] = (d0 * bestG[0] + d1 * bestG[1]) + d2 * bestG[2];
+  }
+  const double nrm = sqrt(np[0] * np[0] + (np[1] * np[1] + np[2] * np[2]));
+  double nor[3] = {np[0] / nrm, np[1] / nrm, np[2] / nrm};
+  double bin[3] = {ax[1] * nor[2] - ax[2] * nor[1], ax[2] * nor[0] - ax[0] * nor[2], ax[0] * nor[1] - ax[1] * nor[0]};
+  const double cx = major ? cam1x : cam0x, cy = major ? cam1y : cam0y, cz = major ? cam1z : cam0z;
+  const double t0 = qx - cx, t1 = qy - cy, t2 = qz - cz;
+  if (nor[0] * t0 + (nor[1] * t1 + nor[2] * t2) > 0) {
+    nor[0] = -nor[0]; nor[1] = -nor[1]; nor[2] = -nor[2];
+  }
+  if (bin[0] * t0 + (bin[1] * t1 + bin[2] * t2) > 0) {
+    bin[0] = -bin[0]; bin[1] = -bin[1]; bin[2] = -bin[2];
+  }
+  ax[0] = nor[1] * bin[2] - nor[2] * bin[1];
+  ax[1] = nor[2] * bin[0] - nor[0] * bin[2];
+  ax[2] = nor[0] * bin[1] - nor[1] * bin[0];
+  if (lane == 0) {
+    const bool good = ok && n >= 1.0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      F.normal[k] = good ? nor[k] : 0.0;
+      F.axis[k] = good ? ax[k] : 0.0;
+      F.binormal[k] = good ? bin[k] : 0.0;
+    }
+    frames[s] = F;
+    if (normals_out && n >= 1.0) {  // hand_search.cpp:102: cloud_normals_.col(idx) = normal
+      normals_out[size_t(3) * idx + 0] = F.normal[0];
+      normals_out[size_t(3) * idx + 1] = F.normal[1];
+      normals_out[size_t(3) * idx + 2] = F.normal[2];
+    }
+  }
+}
+
+// points that received a normal carry a tag bit so the sweep only fetches normals that exist
+__global__ void k_mark_normals(GPoint* pts, const int* __restrict__ inv, const int* __restrict__ indices, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicOr(&pts[inv[indices[i]]].tag, kTagNormalBit);
+}
+
+}  // namespace
+
+int fit_quadrics_device(Ctx* c, const int* d_indices, int n, double radius, ag_frame* d_frames, bool write_normals) {
+  if (n <= 0) return AG_OK;
+  if (c->n_vox <= 0) {
+    set_error("fit_quadrics: no cloud loaded");
+    return AG_ERR_EMPTY;
+  }
+  if (c->moments.reserve(size_t(n) * kMomentStride * sizeof(double)) || c->nn_counts.reserve(size_t(n) * 4) ||
+      c->counters.reserve(64))
+    return AG_ERR_CUDA;
+  const float r2 = float(radius * radius);  // PCL hands radius*radius to FLANN as float
+  const double rpad = sqrt(double(r2)) * (1.0 + 1e-5) + 1e-7;
+  const double inv_r = 1.0 / radius;
+  const int blocks = (n + kWarps - 1) / kWarps;
+  unsigned long long* ctr = c->counters.as<unsigned long long>();
+  k_taubin_moments<<<blocks, kWarps * 32, 0, c->stream>>>(c->pts.as<GPoint>(), c->cell_start.as<int>(), c->grid,
+                                                          c->vox.as<float4>(), d_indices, n, r2, rpad, inv_r,
+                                                          c->moments.as<double>(), c->nn_counts.as<int>(), ctr);
+  const size_t smem = sizeof(AxesSmem) * kWarps;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_taubin_axes, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    attr_set = true;
+  }
+  const HandConst& h = c->hand;
+  k_taubin_axes<<<blocks, kWarps * 32, smem, c->stream>>>(
+      c->pts.as<GPoint>(), c->cell_start.as<int>(), c->grid, c->vox.as<float4>(), d_indices, n, r2, rpad, inv_r, c->moments.as<double>(), h.cam[0][0], h.cam[0][1], h.cam[0][2], h.cam[1][0],
+      h.cam[1][1], h.cam[1][2], d_frames, write_normals ? c->normals.as<double>() : nullptr);
+  if (write_normals)
+    k_mark_normals<<<(n + 255) / 256, 256, 0, c->stream>>>(c->pts.as<GPoint>(), c->inv.as<int>(), d_indices, n);
+  AG_CUDA_CHECK(cudaGetLastError());
+  return AG_OK;
+}
+
+}  // namespace ag

@@ -1,0 +1,484 @@
+// sweep.cu — rotating-hand / finger-placement sweep, antipodal test and grasp-image rasterisation.
+// One CTA per sample, one warp per hand orientation.
+//
+// Replaces (reference paths): HandSearch::findHands private (src/agile_grasp/hand_search.cpp:116-206,
+// radius search :147, float centring :154-160), RotatingHand::transformPoints / evaluateHand
+// (src/agile_grasp/rotating_hand.cpp:19-177), FingerHand (src/agile_grasp/finger_hand.cpp:3-233),
+// Antipodal::evaluateGrasp (src/agile_grasp/antipodal.cpp:12-86), Localization::filterHands
+// (src/agile_grasp/localization.cpp:364-388) and the image half of Learning::createInstance /
+// convertToImage (src/agile_grasp/learning.cpp:320-400).
+//
+// GPU formulation.  The reference re-scans the slab points for every finger slot at
+// every deepening step.  Every boolean it derives is an existence test "is there a point with
+// y < d_t and x in some interval", so one pass per orientation that ORs 20-bit slot masks into the
+// 11 depth levels d_t reproduces all of them exactly: the same binary64 comparisons on the same
+// binary64 values, evaluated without FMA contraction (this file is compiled with -fmad=false and
+// the products/sums are written in the reference's left-to-right order).
+
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
+#include "ag_internal.h"
+
+namespace ag {
+
+namespace {
+
+constexpr int kThreads = 256;     // 8 warps = 8 orientations (rotating_hand.cpp:13)
+constexpr int kSlabCap = 6144;    // slab points kept in shared memory (96 KB)
+
+struct SlabPoint {  // centred neighbour, binary32 exactly as hand_search.cpp:157-158 produces it
+  float x, y, z;
+  uint32_t tag;
+};
+
+struct SweepArgs {
+  const GPoint* pts;
+  const int* cell_start;
+  const float4* vox;
+  const int* indices;
+  const ag_frame* frames;
+  const double* normals;  // 3 per voxel point, indexed by original index
+  ag_grasp* grasps;       // [n_samples * 8]
+  uint8_t* valid;         // [n_samples * 8]
+  uint32_t* images;       // [n_samples * 8 * 250]
+  int* debug;             // [n_samples * 8] or null
+  int* slab_counts;       // [n_samples] or null
+  unsigned long long* counters;
+  int* overflow;          // set to 1 if a slab exceeded kSlabCap
+  int n_samples;
+  float r2;
+  double rpad;
+  int filter_boundaries;
+  double workspace[6];
+};
+
+__device__ __forceinline__ double dot3e(const double a[3], const double b[3]) {
+  return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]);  // Eigen's unrolled 3-vector reduction order
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_hand_sweep(const SweepArgs A, const GridDesc g, const __grid_constant__ HandConst hc) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  SlabPoint* slab = reinterpret_cast<SlabPoint*>(s_raw);
+  __shared__ uint32_t s_img[8][AG_IMAGE_WORDS];
+  __shared__ int s_count;
+  __shared__ unsigned long long s_cand;
+
+  const int s = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const int idx = A.indices[s];
+  const float4 q = A.vox[idx];
+  const int sample_cam = __float_as_int(q.w) ? 1 : 0;  // hands_cam_source (hand_search.cpp:40-42, App. B#3)
+  if (threadIdx.x == 0) {
+    s_count = 0;
+    s_cand = 0;
+  }
+  for (int i = lane; i < AG_IMAGE_WORDS; i += 32) s_img[warp][i] = 0u;
+
+  // ---- frame = [normal | normal x axis | axis]   (rotating_hand.cpp:25)
+  const ag_frame fr = A.frames[s];
+  double F[3][3];
+  {
+    const double* a = fr.normal;
+    const double* b = fr.axis;
+    const double nxa[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      F[r][0] = a[r];
+      F[r][1] = nxa[r];
+      F[r][2] = b[r];
+    }
+  }
+  __syncthreads();
+
+  // ---- phase A: gather the r = 0.08 ball, keep the |z_hand| < hand_height slab -----------------
+  {
+    const QueryBox b = query_box(g, q.x, q.y, q.z, A.rpad);
+    const int ncy = b.hi[1] - b.lo[1] + 1;
+    const int ncol = (b.hi[0] - b.lo[0] + 1) * ncy;
+    unsigned long long cand = 0, nball = 0;
+    for (int col = warp; col < ncol; col += 8) {
+      const int cx = b.lo[0] + col / ncy, cy = b.lo[1] + col % ncy;
+      const int rs = __ldg(A.cell_start + cell_linear(g, cx, cy, b.lo[2]));
+      const int re = __ldg(A.cell_start + cell_linear(g, cx, cy, b.hi[2]) + 1);
+      cand += (unsigned long long)(re - rs);
+      for (int j0 = rs; j0 < re; j0 += 32) {
+        const int j = j0 + lane;
+        bool keep = false;
+        SlabPoint sp;
+        sp.x = sp.y = sp.z = 0.f;
+        sp.tag = 0;
+        bool inball = false;
+        if (j < re) {
+          const GPoint p = A.pts[j];
+          if (dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z) < A.r2) {
+            inball = true;
+            // hand_search.cpp:157-158: subtraction in binary32, then cast
+            sp.x = __fsub_rn(p.x, q.x);
+            sp.y = __fsub_rn(p.y, q.y);
+            sp.z = __fsub_rn(p.z, q.z);
+            sp.tag = p.tag;
+            const double hz = (F[0][2] * double(sp.x) + F[1][2] * double(sp.y)) + F[2][2] * double(sp.z);
+            keep = hz > -1.0 * hc.hand_height && hz < hc.hand_height;  // rotating_hand.cpp:44
+          }
+        }
+        const unsigned mb = __ballot_sync(0xffffffffu, inball);
+        nball += __popc(mb);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&s_count, __popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          const int pos = base + __popc(m & lt);
+          if (keep && pos < kSlabCap) slab[pos] = sp;
+        }
+      }
+    }
+    if (lane == 0) atomicAdd(&s_cand, cand | (nball << 32));
+  }
+  __syncthreads();
+  const int k = s_count;
+  if (threadIdx.x == 0) {
+    if (A.slab_counts) A.slab_counts[s] = k;
+    atomicAdd(&A.counters[2], s_cand >> 32);
+    atomicAdd(&A.counters[3], s_cand & 0xFFFFFFFFull);
+    if (k > kSlabCap) atomicExch(A.overflow, 1);
+  }
+  const int o = warp;
+  const size_t slot = size_t(s) * 8 + o;
+  if (k > kSlabCap) {
+    if (lane == 0) A.valid[slot] = 0;
+    return;
+  }
+
+  // ---- phase B: orientation o -------------------------------------------------------------------
+  const double cs = hc.cosv[o], sn = hc.sinv[o];
+  const double msn = -1.0 * sn;  // rot = [cs -sn 0; sn cs 0; 0 0 1]   (rotating_hand.cpp:90)
+  // T = frame * rot^T ; approach = T*y, binormal = T*x   (rotating_hand.cpp:96,104)
+  double T[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    T[r][0] = (F[r][0] * cs + F[r][1] * msn) + F[r][2] * 0.0;
+    T[r][1] = (F[r][0] * sn + F[r][1] * cs) + F[r][2] * 0.0;
+    T[r][2] = (F[r][0] * 0.0 + F[r][1] * 0.0) + F[r][2] * 1.0;
+  }
+  double approach[3], binormal[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    approach[r] = (T[r][0] * 0.0 + T[r][1] * 1.0) + T[r][2] * 0.0;
+    binormal[r] = (T[r][0] * 1.0 + T[r][1] * 0.0) + T[r][2] * 0.0;
+  }
+  const double se[3] = {double(q.x), double(q.y), double(q.z)};
+  const double camv0[3] = {hc.cam[0][0] - se[0], hc.cam[0][1] - se[1], hc.cam[0][2] - se[2]};
+  const double camv1[3] = {hc.cam[1][0] - se[0], hc.cam[1][1] - se[1], hc.cam[1][2] - se[2]};
+  int status = 0, e_idx = -1, last = 0;
+  unsigned fingers_last = 0;
+  bool have = false;
+  double minY = 1e300, maxY = -1e300;
+  const bool cam_ok = !(dot3e(approach, camv0) > 0 && dot3e(approach, camv1) > 0);  // rotating_hand.cpp:99
+  if (cam_ok) {
+    // pass 1: slot masks per depth level
+    unsigned IN[12], SD[12];
+#pragma unroll
+    for (int t = 0; t < 12; t++) IN[t] = SD[t] = 0u;
+    for (int j = lane; j < k; j += 32) {
+      const SlabPoint p = slab[j];
+      const double px = double(p.x), py = double(p.y), pz = double(p.z);
+      const double hx = (F[0][0] * px + F[1][0] * py) + F[2][0] * pz;  // frame^T * p (rotating_hand.cpp:26)
+      const double hy = (F[0][1] * px + F[1][1] * py) + F[2][1] * pz;
+      const double rx = cs * hx + msn * hy;  // rot * p (rotating_hand.cpp:91); the 0*z term is exact
+      const double ry = sn * hx + cs * hy;
+      minY = fmin(minY, ry);
+      maxY = fmax(maxY, ry);
+      if (!(ry < hc.bite[hc.n_depths - 1])) continue;  // above the deepest bite: never cropped in
+      unsigned in_mask = 0u, sd_mask = 0u;
+#pragma unroll
+      for (int i = 0; i < 20; i++) {
+        const double lo = hc.spacing[i], hi = hc.spacing[i] + hc.finger_width;  // finger_hand.cpp:56-57
+        if (rx > lo && rx < hi) in_mask |= 1u << i;
+        const bool side = (i <= 10) ? (rx > hi) : (rx < lo);  // finger_hand.cpp:72-82
+        if (side) sd_mask |= 1u << i;
+      }
+#pragma unroll
+      for (int t = 0; t < 12; t++) {
+        if (t < hc.n_depths && ry < hc.bite[t]) {
+          IN[t] |= in_mask;
+          SD[t] |= sd_mask;
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 12; t++) {
+      IN[t] = __reduce_or_sync(0xffffffffu, IN[t]);
+      SD[t] = __reduce_or_sync(0xffffffffu, SD[t]);
+    }
+    minY = warp_min(minY);
+    maxY = warp_max(maxY);
+    // finger / hand logic at depth level t (finger_hand.cpp:20-115)
+    auto hand_at = [&](int t, unsigned& fingers) -> unsigned {
+      const bool abort = minY < hc.back[t];  // a cropped point behind the back of the hand (:37-40)
+      fingers = abort ? 0u : ((~IN[t]) & SD[t] & 0xFFFFFu);
+      return fingers & (fingers >> 10) & 0x3FFu;
+    };
+    status = 1;
+    unsigned f0;
+    const unsigned hand0 = k > 0 ? hand_at(0, f0) : 0u;
+    if (hand0) {  // rotating_hand.cpp:111
+      have = true;
+      status = 2;
+      const int len = __popc(hand0);
+      e_idx = __fns(hand0, 0, (len + 1) / 2);  // idx[ceil(len/2) - 1]   (finger_hand.cpp:190)
+      fingers_last = f0;
+      for (int t = 1; t < hc.n_depths; t++) {  // deepenHand (finger_hand.cpp:204-228)
+        unsigned ft;
+        const unsigned ht = hand_at(t, ft);
+        if (!((ht >> e_idx) & 1u)) break;
+        last = t;
+        fingers_last = ft;
+      }
+    }
+  }
+  if (A.debug && lane == 0)
+    A.debug[slot] = status | ((e_idx & 0xF) << 4) | (last << 8) | int(fingers_last << 12);
+  if (!have) {
+    if (lane == 0) A.valid[slot] = 0;
+    return;
+  }
+
+  // ---- grasp parameters (finger_hand.cpp:117-171, rotating_hand.cpp:118-154) --------------------
+  const double hor = hc.half_od + hc.spacing[e_idx];
+  double surface3[3], bottom3[3], surf_w[3], bot_w[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    surface3[r] = (T[r][0] * hor + T[r][1] * minY) + T[r][2] * 0.0;
+    bottom3[r] = (T[r][0] * hor + T[r][1] * maxY) + T[r][2] * 0.0;
+    surf_w[r] = surface3[r] + se[r];
+    bot_w[r] = bottom3[r] + se[r];
+  }
+  const double lim = hc.lim[last];  // back_of_hand + hand_depth   (rotating_hand.cpp:128)
+  // image orientation (learning.cpp:330-333, 382-383)
+  const double s2c[3] = {surf_w[0] - hc.cam[sample_cam][0], surf_w[1] - hc.cam[sample_cam][1],
+                         surf_w[2] - hc.cam[sample_cam][2]};
+  const bool keep_sign = dot3e(binormal, s2c) > 0;
+  const double left = hc.spacing[e_idx], right = hc.spacing[10 + e_idx];
+  double wmin = 100000.0, wmax = -100000.0;
+  int m_box = 0, numl = 0, numr = 0;
+  uint32_t* img = s_img[warp];
+  for (int j = lane; j < k; j += 32) {
+    const SlabPoint p = slab[j];
+    const double px = double(p.x), py = double(p.y), pz = double(p.z);
+    const double hx = (F[0][0] * px + F[1][0] * py) + F[2][0] * pz;
+    const double hy = (F[0][1] * px + F[1][1] * py) + F[2][1] * pz;
+    const double rx = cs * hx + msn * hy;
+    const double ry = sn * hx + cs * hy;
+    if (ry < hc.bite[0] && rx > left && rx < right) {  // finger_hand.cpp:159-167
+      wmin = fmin(wmin, rx);
+      wmax = fmax(wmax, rx);
+    }
+    if (ry < lim) {  // points in the box (rotating_hand.cpp:126-130)
+      m_box++;
+      // learning.cpp:320-365 on points_for_learning = rotated point - surface (frame mix-up kept)
+      const double bx = rx - surface3[0], by = ry - surface3[1];
+      const double hcell = floor(((keep_sign ? bx : -bx) - (-0.05)) / hc.img_cell);
+      const double vcell = floor((by - 0.0) / hc.img_cell);
+      const int h = int(fmin(99.0, fmax(0.0, hcell)));
+      const int v = int(fmin(79.0, fmax(0.0, vcell)));
+      const int bit = (AG_IMAGE_ROWS - 1 - v) * AG_IMAGE_COLS + h;
+      atomicOr(&img[bit >> 5], 1u << (bit & 31));
+      if (p.tag & kTagNormalBit) {  // antipodal.cpp:12-86 on rot * frame^T * normal
+        const double* nv = A.normals + size_t(3) * (p.tag & kTagIndexMask);
+        const double n0 = nv[0], n1 = nv[1], n2 = nv[2];
+        const double hn0 = (F[0][0] * n0 + F[1][0] * n1) + F[2][0] * n2;
+        const double hn1 = (F[0][1] * n0 + F[1][1] * n1) + F[2][1] * n2;
+        const double nrx = cs * hn0 + msn * hn1;
+        numl += (-1.0 * nrx > hc.cos_thresh) ? 1 : 0;
+        numr += (nrx > hc.cos_thresh) ? 1 : 0;
+      }
+    }
+  }
+  wmin = warp_min(wmin);
+  wmax = warp_max(wmax);
+  m_box = __reduce_add_sync(0xffffffffu, m_box);
+  numl = __reduce_add_sync(0xffffffffu, numl);
+  numr = __reduce_add_sync(0xffffffffu, numr);
+  __syncwarp();
+  bool keep_hyp = true;
+  if (A.filter_boundaries) {  // localization.cpp:364-388
+#pragma unroll
+    for (int kk = 0; kk < 6; kk++)
+      if (fabs(surf_w[kk / 2] - A.workspace[kk]) < 0.02) keep_hyp = false;
+  }
+  if (lane == 0) {
+    ag_grasp gr;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      gr.axis[r] = fr.axis[r];
+      gr.approach[r] = approach[r];
+      gr.binormal[r] = binormal[r];
+      gr.bottom[r] = bot_w[r];
+      gr.surface[r] = surf_w[r];
+    }
+    gr.width = wmax - wmin;
+    gr.score = __int_as_float(0x7FC00000);
+    gr.sample_index = idx;
+    gr.sample_slot = s;
+    gr.orientation = o;
+    gr.cam_source = sample_cam;
+    gr.num_points = m_box;
+    gr.image_id = -1;
+    gr.half_antipodal = (numl > 6 || numr > 6) ? 1 : 0;
+    gr.full_antipodal = (numl > 6 && numr > 6) ? 1 : 0;
+    gr.label = 0;
+    gr.reserved = 0;
+    A.grasps[slot] = gr;
+    A.valid[slot] = keep_hyp ? 1 : 0;
+  }
+  uint32_t* gimg = A.images + slot * AG_IMAGE_WORDS;
+  for (int i = lane; i < AG_IMAGE_WORDS; i += 32) gimg[i] = img[i];
+}
+
+// gather the surviving hypotheses in (sample, orientation) order = the reference's stable concat
+// (hand_search.cpp:194-200)
+__global__ void k_compact_grasps(const ag_grasp* __restrict__ raw, const int* __restrict__ slots,
+                                 const int* __restrict__ n_sel, ag_grasp* __restrict__ out, int cap) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= *n_sel || h >= cap) return;
+  ag_grasp gr = raw[slots[h]];
+  gr.image_id = h;
+  out[h] = gr;
+}
+
+// caller-supplied cloud_normals_: flag the points whose normal is non-zero
+__global__ void k_flag_normals(GPoint* pts, const int* __restrict__ inv, const double* __restrict__ normals, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool nz = normals && (normals[3 * size_t(i)] != 0.0 || normals[3 * size_t(i) + 1] != 0.0 ||
+                              normals[3 * size_t(i) + 2] != 0.0);
+  GPoint* p = pts + inv[i];
+  if (nz) atomicOr(&p->tag, kTagNormalBit);
+  else atomicAnd(&p->tag, ~kTagNormalBit);
+}
+
+}  // namespace
+
+int set_normals_device(Ctx* c, const double* h_normals) {
+  const int n = c->n_vox;
+  if (n <= 0) return AG_OK;
+  if (c->normals.reserve(size_t(n) * 24)) return AG_ERR_CUDA;
+  if (h_normals) AG_CUDA_CHECK(cudaMemcpyAsync(c->normals.p, h_normals, size_t(n) * 24, cudaMemcpyHostToDevice, c->stream));
+  else AG_CUDA_CHECK(cudaMemsetAsync(c->normals.p, 0, size_t(n) * 24, c->stream));
+  k_flag_normals<<<(n + 255) / 256, 256, 0, c->stream>>>(c->pts.as<GPoint>(), c->inv.as<int>(),
+                                                        h_normals ? c->normals.as<double>() : nullptr, n);
+  AG_CUDA_CHECK(cudaGetLastError());
+  AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  return AG_OK;
+}
+
+void compute_hand_const(const ag_params& p, HandConst& h) {
+  // finger_hand.cpp:8-15 — fs_half = LinSpaced(10, 0, od - fw) evaluated as low + i*step (Eigen 3.2)
+  const double hi = p.hand_outer_diameter - p.finger_width;
+  const double step = (hi - 0.0) / double(10 - 1);
+  for (int i = 0; i < 10; i++) {
+    const double v = 0.0 + double(i) * step;
+    h.spacing[i] = (v - p.hand_outer_diameter) + p.finger_width;
+    h.spacing[10 + i] = v;
+  }
+  h.finger_width = p.finger_width;
+  h.outer_diameter = p.hand_outer_diameter;
+  h.depth = p.hand_depth;
+  h.hand_height = p.hand_height;
+  h.init_bite = p.init_bite;
+  // rotating_hand.cpp:12-15 — first 8 of LinSpaced(9, -pi, pi); :90 cos/sin through libm
+  const double lo = -1.0 * M_PI, step_a = (M_PI - lo) / double(9 - 1);
+  for (int i = 0; i < 8; i++) {
+    const double a = lo + double(i) * step_a;
+    h.cosv[i] = cos(a);
+    h.sinv[i] = sin(a);
+  }
+  // finger_hand.cpp:199-204 — d = init + 0.005; d <= depth; d += 0.005 (binary64 accumulation)
+  h.n_depths = 0;
+  h.bite[h.n_depths++] = p.init_bite;
+  for (double d = p.init_bite + 0.005; d <= p.hand_depth && h.n_depths < 12; d += 0.005) h.bite[h.n_depths++] = d;
+  for (int t = 0; t < 12; t++) {
+    if (t >= h.n_depths) h.bite[t] = h.bite[h.n_depths - 1];
+    h.back[t] = -1.0 * (p.hand_depth - h.bite[t]);  // finger_hand.cpp:22
+    h.lim[t] = h.back[t] + p.hand_depth;            // rotating_hand.cpp:128
+  }
+  h.cos_thresh = cos(20.0 * M_PI / 180.0);  // antipodal.cpp:15 with thresh 20 (rotating_hand.cpp:162)
+  for (int a = 0; a < 3; a++) {
+    h.cam[0][a] = p.cam_tf_left[4 * a + 3];
+    h.cam[1][a] = p.cam_tf_right[4 * a + 3];
+  }
+  h.img_cell = (0.05 - (-0.05)) / double(AG_IMAGE_COLS);  // learning.cpp:322-324
+  h.half_od = p.hand_outer_diameter / 2.0;
+}
+
+int hand_sweep_device(Ctx* c, const int* d_indices, int n, const ag_frame* d_frames, unsigned flags) {
+  c->n_hyp = 0;
+  c->images_valid = false;
+  if (n <= 0) return AG_OK;
+  if (c->n_vox <= 0) {
+    set_error("hand_sweep: no cloud loaded");
+    return AG_ERR_EMPTY;
+  }
+  const size_t slots = size_t(n) * 8;
+  if (c->grasps_raw.reserve(slots * sizeof(ag_grasp)) || c->valid.reserve(slots + 64) ||
+      c->images_raw.reserve(slots * AG_IMAGE_WORDS * 4) || c->hyp_slots.reserve(slots * 4 + 16) ||
+      c->grasps.reserve(slots * sizeof(ag_grasp)) || c->counters.reserve(64) ||
+      c->sweep_dbg.reserve(size_t(n) * 4 + slots * 4))
+    return AG_ERR_CUDA;
+  SweepArgs A;
+  A.pts = c->pts.as<GPoint>();
+  A.cell_start = c->cell_start.as<int>();
+  A.vox = c->vox.as<float4>();
+  A.indices = d_indices;
+  A.frames = d_frames;
+  A.normals = c->normals.as<double>();
+  A.grasps = c->grasps_raw.as<ag_grasp>();
+  A.valid = c->valid.as<uint8_t>();
+  A.images = c->images_raw.as<uint32_t>();
+  A.slab_counts = c->sweep_dbg.as<int>();
+  A.debug = c->sweep_dbg.as<int>() + n;
+  A.counters = c->counters.as<unsigned long long>();
+  A.overflow = reinterpret_cast<int*>(c->counters.as<unsigned long long>() + 6);
+  A.n_samples = n;
+  const double radius = c->params.nn_radius_hands;
+  A.r2 = float(radius * radius);
+  A.rpad = sqrt(double(A.r2)) * (1.0 + 1e-5) + 1e-7;
+  A.filter_boundaries = (flags & 0x100u) ? 1 : 0;
+  for (int i = 0; i < 6; i++) A.workspace[i] = c->params.workspace[i];
+  const size_t smem = size_t(kSlabCap) * sizeof(SlabPoint);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_hand_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    attr_set = true;
+  }
+  AG_CUDA_CHECK(cudaMemsetAsync(A.overflow, 0, 8, c->stream));
+  k_hand_sweep<<<n, kThreads, smem, c->stream>>>(A, c->grid, c->hand);
+  // stable compaction of the valid (sample, orientation) slots
+  int* d_slots = c->hyp_slots.as<int>();
+  int* d_nsel = d_slots + slots;
+  size_t tmp = 0;
+  thrust::counting_iterator<int> iota(0);
+  cub::DeviceSelect::Flagged(nullptr, tmp, iota, A.valid, d_slots, d_nsel, int(slots), c->stream);
+  if (c->cub_tmp.reserve(tmp)) return AG_ERR_CUDA;
+  AG_CUDA_CHECK(cub::DeviceSelect::Flagged(c->cub_tmp.p, tmp, iota, A.valid, d_slots, d_nsel, int(slots), c->stream));
+  k_compact_grasps<<<int((slots + 255) / 256), 256, 0, c->stream>>>(A.grasps, d_slots, d_nsel,
+                                                                    c->grasps.as<ag_grasp>(), int(slots));
+  AG_CUDA_CHECK(cudaGetLastError());
+  int host[4] = {0, 0, 0, 0};
+  AG_CUDA_CHECK(cudaMemcpyAsync(&host[0], d_nsel, 4, cudaMemcpyDeviceToHost, c->stream));
+  AG_CUDA_CHECK(cudaMemcpyAsync(&host[1], A.overflow, 4, cudaMemcpyDeviceToHost, c->stream));
+  AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (host[1]) {
+    set_error("hand sweep: a sample's slab exceeded the shared-memory capacity (kSlabCap points)");
+    return AG_ERR_CAPACITY;
+  }
+  c->n_hyp = host[0];
+  c->images_valid = true;
+  return AG_OK;
+}
+
+}  // namespace ag

@@ -179,6 +179,11 @@ int ag_fit_quadrics(ag_ctx* ctx, const int* indices, int n_indices, double radiu
 int ag_hand_sweep(ag_ctx* ctx, const int* indices, int n_indices, const ag_frame* frames,
                   const double* cloud_normals, unsigned flags, ag_grasp** out, int* n_out);
 
+/* Diagnostics of the last sweep: slab point count per sample and, per (sample, orientation), a word
+ * status | hand_index<<4 | deepening_steps<<8 | finger_mask<<12 (status 0 camera-rejected, 1 no hand,
+ * 2 hypothesis). */
+int ag_sweep_debug(ag_ctx* ctx, int n_samples, int32_t* slab_counts, int32_t* debug8);
+
 /* HOG descriptor + SVM decision value for n packed grasp images (AG_IMAGE_WORDS uint32 each).
  * descriptors (may be NULL): n x AG_HOG_DIM floats. */
 int ag_hog_svm(ag_ctx* ctx, const ag_svm* svm, const uint32_t* images, int n,
