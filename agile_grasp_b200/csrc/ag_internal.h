@@ -83,6 +83,8 @@ struct Ctx {
   std::vector<ag_grasp> last_grasps;
   ag_timings timings;
   cudaEvent_t ev[10];
+  cudaEvent_t ev_k[3];   // around k_taubin_moments / k_taubin_axes
+  int launches = 0;      // own-kernel launch counter (reset per localize call)
 };
 
 int ctx_pinned(Ctx* c, size_t bytes);

@@ -182,6 +182,7 @@ static int localize_core(Ctx* c, const void* d_points, int stride, int n_in, int
   c->timings.n_in = n_in;
   c->images_valid = false;
   c->n_hyp = 0;
+  c->launches = 0;
   cudaStream_t st = c->stream;
   cudaEventRecord(c->ev[1], st);
   int rc = preprocess_device(c, d_points, stride, n_in, size_left);
@@ -250,6 +251,9 @@ static int localize_core(Ctx* c, const void* d_points, int stride, int n_in, int
   c->timings.d2h_ms = elapsed(c->ev[6], c->ev[7]);
   c->timings.total_ms = elapsed(c->ev[0], c->ev[7]);
   c->timings.n_hyp = Hn;
+  c->timings.moments_ms = elapsed(c->ev_k[0], c->ev_k[1]);
+  c->timings.axes_ms = elapsed(c->ev_k[1], c->ev_k[2]);
+  c->timings.kernel_launches = c->launches;
   c->timings.taubin_neighbor_points = int64_t(ctr[0]);
   c->timings.taubin_candidates = int64_t(ctr[1]);
   c->timings.hand_neighbor_points = int64_t(ctr[2]);
@@ -324,6 +328,7 @@ ag_ctx* ag_create(int device) {
     return nullptr;
   }
   for (auto& ev : c.ev) cudaEventCreate(&ev);
+  for (auto& ev : c.ev_k) cudaEventCreate(&ev);
   ag_default_params(&c.params);
   compute_hand_const(c.params, c.hand);
   std::memset(&c.timings, 0, sizeof(c.timings));
@@ -343,6 +348,7 @@ void ag_destroy(ag_ctx* h) {
     b->release();
   if (c.h_pinned) cudaFreeHost(c.h_pinned);
   for (auto& ev : c.ev) cudaEventDestroy(ev);
+  for (auto& ev : c.ev_k) cudaEventDestroy(ev);
   cudaStreamDestroy(c.stream);
   delete h;
 }
@@ -466,6 +472,7 @@ int ag_classify(ag_ctx* h, const ag_svm* svm, ag_grasp* grasps, int n, uint8_t* 
   cudaEventRecord(c.ev[9], c.stream);
   AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
   c.timings.hog_svm_ms = elapsed(c.ev[8], c.ev[9]);
+  c.timings.kernel_launches = c.launches;
   for (int i = 0; i < n; i++) {
     grasps[i].score = sc_h[i];
     // CvSVM::predict: vote[sum > 0 ? 0 : 1], class_labels = [-1, 1] => label +1 <=> sum <= 0

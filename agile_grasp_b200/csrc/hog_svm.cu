@@ -321,6 +321,7 @@ int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d
   sd.gamma = svm->gamma;
   sd.coef0 = svm->coef0;
   sd.rho = svm->rho;
+  c->launches += 1;
   k_hog_svm<<<n, kThreads, 0, c->stream>>>(d_images, d_image_slots, n, sd, d_descriptors, d_scores);
   AG_CUDA_CHECK(cudaGetLastError());
   return AG_OK;

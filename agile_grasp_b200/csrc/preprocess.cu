@@ -322,6 +322,7 @@ int preprocess_device(Ctx* c, const void* d_points, int stride, int n_in, int si
                                                c->keys_sorted.as<uint64_t>(), n_in, 0, 64, c->stream));
   AG_CUDA_CHECK(cub::DeviceSelect::Unique(c->cub_tmp.p, tmp2, c->keys_sorted.as<uint64_t>(),
                                           c->keys_unique.as<uint64_t>(), &st->n_unique, n_in, c->stream));
+  c->launches += quirk ? 6 : 4;  // init, [count, scan], classify, keys, emit (CUB kernels not counted)
   k_emit<<<nb, kBlock, 0, c->stream>>>(c->keys_unique.as<uint64_t>(), n_in, P.voxel_size, st, c->vox.as<float4>());
   AG_CUDA_CHECK(cudaGetLastError());
   return finish_cloud(c, true);
@@ -368,6 +369,7 @@ int build_grid(Ctx* c) {
   AG_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp2, c->cell_ids.as<uint32_t>(),
                                                 c->cell_ids_sorted.as<uint32_t>(), c->perm.as<int>(),
                                                 c->perm_sorted.as<int>(), n, 0, bits, c->stream));
+  c->launches += 2;  // cell_ids, gather
   k_gather<<<nb, kBlock, 0, c->stream>>>(c->vox.as<float4>(), c->perm_sorted.as<int>(), n, c->pts.as<GPoint>(),
                                          c->inv.as<int>());
   // cloud_normals_ is zeroed on every call (hand_search.cpp:13-14)

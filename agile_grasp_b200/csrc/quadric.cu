@@ -539,9 +539,11 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, double radius, ag_f
   const double inv_r = 1.0 / radius;
   const int blocks = (n + kWarps - 1) / kWarps;
   unsigned long long* ctr = c->counters.as<unsigned long long>();
+  cudaEventRecord(c->ev_k[0], c->stream);
   k_taubin_moments<<<blocks, kWarps * 32, 0, c->stream>>>(c->pts.as<GPoint>(), c->cell_start.as<int>(), c->grid,
                                                           c->vox.as<float4>(), d_indices, n, r2, rpad, inv_r,
                                                           c->moments.as<double>(), c->nn_counts.as<int>(), ctr);
+  cudaEventRecord(c->ev_k[1], c->stream);
   const size_t smem = sizeof(AxesSmem) * kWarps;
   static bool attr_set = false;
   if (!attr_set) {
@@ -552,6 +554,8 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, double radius, ag_f
   k_taubin_axes<<<blocks, kWarps * 32, smem, c->stream>>>(
       c->pts.as<GPoint>(), c->cell_start.as<int>(), c->grid, c->vox.as<float4>(), d_indices, n, r2, rpad, inv_r, c->moments.as<double>(), h.cam[0][0], h.cam[0][1], h.cam[0][2], h.cam[1][0],
       h.cam[1][1], h.cam[1][2], d_frames, write_normals ? c->normals.as<double>() : nullptr);
+  cudaEventRecord(c->ev_k[2], c->stream);
+  c->launches += write_normals ? 3 : 2;
   if (write_normals)
     k_mark_normals<<<(n + 255) / 256, 256, 0, c->stream>>>(c->pts.as<GPoint>(), c->inv.as<int>(), d_indices, n);
   AG_CUDA_CHECK(cudaGetLastError());

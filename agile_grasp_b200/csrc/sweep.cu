@@ -457,6 +457,7 @@ int hand_sweep_device(Ctx* c, const int* d_indices, int n, const ag_frame* d_fra
   }
   AG_CUDA_CHECK(cudaMemsetAsync(A.overflow, 0, 8, c->stream));
   k_hand_sweep<<<n, kThreads, smem, c->stream>>>(A, c->grid, c->hand);
+  c->launches += 2;  // + k_compact_grasps
   // stable compaction of the valid (sample, orientation) slots
   int* d_slots = c->hyp_slots.as<int>();
   int* d_nsel = d_slots + slots;

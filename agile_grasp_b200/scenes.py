@@ -147,6 +147,7 @@ def render(prims, cam_tf, seed, width=640, height=480, dropout=0.04, noise=0.001
     for prim in prims:
         depth = np.minimum(depth, _hit(prim, o, d))
     valid = np.isfinite(depth) & (depth < 4.0)
+    depth = np.where(valid, depth, 1.0)
     depth = depth + noise * depth * depth * rng.standard_normal(depth.shape)
     valid &= rng.random(depth.shape) >= dropout
     pts = o + depth[:, None] * d

@@ -1,0 +1,45 @@
+"""Sample sharding across ranks and the all-gather of the grasp list.
+
+Every sample's work is independent (the reference's two hot loops are plain `omp parallel for`,
+hand_search.cpp:77-80,135-138, followed by a stable concatenation, :194-200), so samples are split
+into contiguous ranges, one per rank; the voxelised cloud and the hash grid are replicated (each rank
+runs the deterministic preprocessing itself).  The only exchange step is one all-gather of the
+fixed-stride grasp records, after which every rank holds the reference's sample-major ordering.
+Works with any torch.distributed backend: NCCL on device tensors (bench.py), gloo on CPU (tests).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .ctypes_defs import GRASP_DTYPE
+
+
+def shard_range(n_items, rank, world):
+    """contiguous [lo, hi) of rank's share; sizes differ by at most one, order preserved"""
+    lo = (n_items * rank) // world
+    hi = (n_items * (rank + 1)) // world
+    return lo, hi
+
+
+def all_gather_grasps(local, device=None, group=None):
+    """local: numpy structured array (GRASP_DTYPE) of this rank's hypotheses, in sample order.
+    Returns the concatenation over ranks in rank order (= global sample order)."""
+    world = dist.get_world_size(group)
+    dev = torch.device("cpu") if device is None else device
+    n_local = torch.tensor([len(local)], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(counts, n_local, group=group)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1)
+    item = GRASP_DTYPE.itemsize
+    buf = np.zeros(cap * item, np.uint8)
+    buf[: len(local) * item] = np.frombuffer(np.ascontiguousarray(local).tobytes(), np.uint8)
+    send = torch.from_numpy(buf).to(dev)
+    recv = torch.empty(world * cap * item, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    host = recv.cpu().numpy().reshape(world, cap * item)
+    parts = [np.frombuffer(host[r, : counts[r] * item].tobytes(), dtype=GRASP_DTYPE) for r in range(world)]
+    out = np.concatenate(parts) if parts else np.zeros(0, GRASP_DTYPE)
+    out = out.copy()
+    out["image_id"] = -1  # images stay on the producing rank
+    return out, counts

@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py — grasp hypotheses/sec on the BASELINE.json configuration (307,200-point organised cloud,
+2000 samples, linear SVM), through the C ABI of libag_b200.so.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 2]
+
+A step = one pass of the hot path (ag_localize + ag_classify = Localization::localizeHands +
+predictAntipodalHands) over one synthetic cloud per rank.  N>1 is launched by torchrun, one rank per
+GPU: every rank processes its own cloud (weak scaling) and the step ends with one NCCL all-gather of
+the fixed-stride grasp records, so every rank holds the whole grasp list.
+
+  value : hyp/s with the cloud already resident in HBM (ag_localize_device), timed with CUDA events on
+          the library's own stream (ag_timings), max over ranks.
+  e2e   : hyp/s through the host-buffer entry points (pinned host cloud in, host grasp list out),
+          wall clock around the calls; H2D of the cloud and D2H of the records are inside.
+  roofline : the Taubin-moments kernel: algorithmic bytes (16 B per neighbour + 292 B out per sample)
+          over its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline : the CPU oracle (a port of the reference path, OpenMP over samples like the reference)
+          on this box's host cores.
+--impl reference runs only that CPU arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "grasp hypotheses/sec on 307k-pt cloud, 2000 samples; ms/cloud end-to-end"
+SVM_PATH = os.path.join(ROOT, "tests", "golden", "svm_032015_linear_20_20_same")
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_cloud(config, scene_offset):
+    from agile_grasp_b200 import scenes
+    pts, size_left, P, S = scenes.config_cloud(config, scene_offset=scene_offset)
+    return np.ascontiguousarray(pts), size_left, P, S
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of the reference path on all host threads."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    pts, size_left, P, S = make_cloud(args.config, 0)
+    cores = os.cpu_count() or 1
+    P.num_threads = cores
+    svm = O.Svm(SVM_PATH)
+    times, hyps = [], []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        H, tm, nv = O.localize(pts, size_left, P, None, 0, svm, True)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+            hyps.append(len(H))
+        del H
+    ms = 1e3 * float(np.mean(times))
+    value = float(np.sum(hyps) / np.sum(times))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "hyp/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"config{args.config}: 640x480 organised cloud (307200 pts), 2000 samples, linear SVM",
+                   "hypotheses_per_step": float(np.mean(hyps))},
+        "cpu_baseline": {"value": value, "unit": "hyp/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full clouds of the bench workload, OpenMP over samples on all "
+                                   f"{cores} host threads; std::set voxelisation and kd-tree as the reference; "
+                                   "SVM parsed once"},
+        "e2e": {"value": value, "unit": "hyp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from agile_grasp_b200 import api
+    from agile_grasp_b200.ctypes_defs import GRASP_DTYPE
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # a small pool of different scenes per rank so successive steps do not see identical inputs
+    pool = []
+    for k in range(2):
+        pts, size_left, P, S = make_cloud(args.config, scene_offset=rank * 2 + k)
+        pinned = torch.from_numpy(pts).pin_memory()
+        pool.append(dict(host=pinned, dev=pinned.to(dev), size_left=size_left, P=P, n=pts.shape[0],
+                         stride=pts.strides[0]))
+    ctx = api.Context(local_rank, pool[0]["P"])
+    svm = api.Svm(SVM_PATH)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    item = GRASP_DTYPE.itemsize
+
+    def gather(local_g):
+        if world == 1:
+            return len(local_g)
+        from agile_grasp_b200.shard import all_gather_grasps
+        merged, counts = all_gather_grasps(local_g, device=dev)
+        return len(merged)
+
+    def step_device(c):
+        g = ctx.localize_device(c["dev"].data_ptr(), c["stride"], c["n"], c["size_left"])
+        t1 = ctx.timings()
+        g, keep = ctx.classify(svm, g)
+        t2 = ctx.timings()
+        return g, t1, t2
+
+    def step_host(c):
+        g = ctx.localize(c["host"].numpy(), c["size_left"])
+        g, keep = ctx.classify(svm, g)
+        return g
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for w in range(args.warmup):
+        g, _, _ = step_device(pool[w % len(pool)])
+        gather(g)
+        step_host(pool[w % len(pool)])
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    # ---- timed: device-resident input (value)
+    dev_ms, hyps, mom_ms, mom_bytes, launches, comm_ms = [], [], [], [], [], []
+    stage = {}
+    barrier()
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        c = pool[k % len(pool)]
+        flush.fill_(k & 0xFF)  # L2 flush between timed iterations (outside the per-step event brackets)
+        torch.cuda.synchronize()
+        g, t1, t2 = step_device(c)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        total = gather(g)
+        e1.record()
+        torch.cuda.synchronize()
+        cm = e0.elapsed_time(e1) if world > 1 else 0.0
+        dev_ms.append(t1["total_ms"] + t2["hog_svm_ms"] + cm)
+        comm_ms.append(cm)
+        hyps.append(len(g))
+        mom_ms.append(t1["moments_ms"])
+        mom_bytes.append(16 * t1["taubin_neighbor_points"] + 292 * t1["n_samples"])
+        launches.append(t2["kernel_launches"])
+        for nm in ("preprocess_ms", "grid_ms", "quadric_ms", "sweep_ms", "d2h_ms", "moments_ms", "axes_ms"):
+            stage.setdefault(nm, []).append(t1[nm])
+        stage.setdefault("hog_svm_ms", []).append(t2["hog_svm_ms"])
+    barrier()
+    wall_dev = time.perf_counter() - wall0
+
+    # ---- timed: host buffers through the reference-facing entry points (e2e)
+    e2e_s, e2e_h = [], []
+    barrier()
+    for k in range(args.steps):
+        c = pool[k % len(pool)]
+        flush.fill_(k & 0xFF)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        g = step_host(c)
+        gather(g)
+        e2e_s.append(time.perf_counter() - t0)
+        e2e_h.append(len(g))
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- reduce over ranks: time = max, hypotheses = sum
+    t_dev = torch.tensor([sum(dev_ms), sum(e2e_s) * 1e3], dtype=torch.float64, device=dev)
+    n_h = torch.tensor([sum(hyps), sum(e2e_h)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n_h, op=dist.ReduceOp.SUM)
+    t_dev, n_h = t_dev.cpu().numpy(), n_h.cpu().numpy()
+
+    if rank == 0:
+        value = n_h[0] / (t_dev[0] * 1e-3)
+        e2e = n_h[1] / (t_dev[1] * 1e-3)
+        peak, peak_src = measured_peak()
+        achieved = float(np.sum(mom_bytes) / (np.sum(mom_ms) * 1e-3) / 1e9) if np.sum(mom_ms) > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "taubin_moments_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        c0 = pool[0]
+        line = {
+            "metric": METRIC, "value": float(value), "unit": "hyp/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": float(t_dev[0] / args.steps), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"config{args.config}: one 640x480 organised cloud (307200 pts, 32 B/pt) per rank "
+                                   "per step, 2000 samples, linear SVM svm_032015_linear_20_20_same",
+                       "l2": "flushed between timed iterations (256 MiB write)",
+                       "hypotheses_per_step": float(n_h[0] / args.steps),
+                       "multi_gpu": "one cloud per rank per step + NCCL all-gather of grasp records" if world > 1
+                       else "single GPU", "timer": "CUDA events on the library stream (ag_timings), max over ranks"},
+            "e2e": {"value": float(e2e), "unit": "hyp/s", "ms_per_cloud": float(t_dev[1] / args.steps),
+                    "h2d_bytes_per_step": int(c0["n"] * c0["stride"]),
+                    "d2h_bytes_per_step": int(np.mean(e2e_h) * (item + 4)),
+                    "timer": "wall clock around ag_localize + ag_classify (+ all-gather), pinned host cloud"},
+            "gpu_launches": int(np.sum(launches)),
+            "roofline": {"bound": "hbm", "kernel": "k_taubin_moments", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": float(np.mean(mom_bytes)),
+                         "launch_ms": float(np.mean(mom_ms))},
+            "stages_ms": {k: float(np.mean(v)) for k, v in stage.items()},
+            "comm_ms": float(np.mean(comm_ms)),
+            "wall_ms_per_step_incl_flush": float(1e3 * wall_dev / args.steps),
+            "clocks": clocks,
+        }
+        if world == 1:
+            try:
+                from oracle import oracle as O
+                P = c0["P"]
+                cores = os.cpu_count() or 1
+                P.num_threads = cores
+                osvm = O.Svm(SVM_PATH)
+                ts, hs = [], []
+                for _ in range(args.cpu_steps):
+                    t0 = time.perf_counter()
+                    H, tm, nv = O.localize(c0["host"].numpy(), c0["size_left"], P, None, 0, osvm, True)
+                    ts.append(time.perf_counter() - t0)
+                    hs.append(len(H))
+                    del H
+                line["cpu_baseline"] = {"value": float(np.sum(hs) / np.sum(ts)), "unit": "hyp/s", "cores": cores,
+                                        "kind": "port", "ms_per_cloud": float(1e3 * np.mean(ts)),
+                                        "sample": f"{args.cpu_steps} full clouds of the same workload, all {cores} "
+                                                  "host threads (OpenMP over samples, as the reference)"}
+            except Exception as e:  # the oracle is test infrastructure; never let it break the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": "hyp/s", "cores": 0, "kind": "port",
+                                        "sample": f"unavailable: {e}"}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

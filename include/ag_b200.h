@@ -116,6 +116,10 @@ typedef struct ag_timings {
   int64_t hand_neighbor_points;     /* sum over samples of n_H(s) */
   int64_t taubin_candidates;        /* points actually scanned by the hash-grid walk */
   int64_t hand_candidates;
+  float moments_ms;                 /* k_taubin_moments alone (the roofline-graded kernel), last call */
+  float axes_ms;                    /* k_taubin_axes alone */
+  int32_t kernel_launches;          /* launches of this library's own kernels in the last localize(+classify) */
+  int32_t reserved;
 } ag_timings;
 
 typedef struct ag_ctx ag_ctx;

@@ -47,7 +47,9 @@ int ago_radius_search(const ago_tree* t, const float* xyz, int n, const float q[
  * findTaubinNormalAxis: a,b,c,d,e,f,g,h,i,j of the implicit quadric), MN (200 per sample: M then
  * N, row-major 10x10), eigvals (10 per sample, alphar/beta).
  * sum_perm: 0 = reference summation order; k>0 = deterministic permutation #k of the neighbour
- * order for the M/N accumulation only (used to measure the reference's own rounding sensitivity). */
+ * order for the M/N accumulation only (used to measure the reference's own rounding sensitivity);
+ * -1 = extended-precision check solve (long double, sample-centred coordinates, no LAPACK): NOT the
+ * reference's arithmetic, used to measure how far dggev_ and the CUDA path each are from exact. */
 int ago_fit_quadrics(const float* xyz, const int32_t* cam, int n, const ago_tree* tree,
                      const int* indices, int n_indices, double radius, const ag_params* P, int sum_perm,
                      ag_frame* frames_out, double* params_out, double* MN_out, double* eigvals_out);

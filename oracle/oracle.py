@@ -63,11 +63,31 @@ def lib():
     L.ago_svm_decision.restype = C.c_float
     L.ago_localize.restype = C.c_void_p
     for path, sym in _find_lapack():
-        if L.ago_set_lapack(path.encode(), sym.encode()) == 0:
-            L._lapack = (path, sym)
+        if set_lapack(path, sym, L):
             break
     _LIB = L
     return L
+
+
+def set_lapack(path, sym, L=None):
+    """Select the dggev_ provider.  The wheel-bundled OpenBLAS needs its sibling libgfortran /
+    libquadmath, which are not on the loader path: preload them globally first."""
+    L = L or lib()
+    d = os.path.dirname(path)
+    for pat in ("libquadmath*.so*", "libgfortran*.so*"):
+        for dep in sorted(glob.glob(os.path.join(d, pat))):
+            try:
+                C.CDLL(dep, mode=C.RTLD_GLOBAL)
+            except OSError:
+                pass
+    if L.ago_set_lapack(path.encode(), sym.encode()) == 0:
+        L._lapack = (path, sym)
+        return True
+    return False
+
+
+def lapack_providers():
+    return _find_lapack()
 
 
 def _err():

@@ -397,10 +397,13 @@ static int fit_quadric(const float* xyz, const std::vector<int>& nn, QuadricFit&
 // A.4 Quadric::findTaubinNormalAxis + findAverageNormalAxis — quadric.cpp:159-305
 // (deterministic evaluation set = all neighbours, :204-212)
 // ---------------------------------------------------------------------------------------------
-static void local_axes(const float* xyz, const int32_t* cam, const std::vector<int>& nn, const QuadricFit& Q,
-                       const double sample[3], const double cam_origin[2][3], ag_frame& F) {
-  const double a = Q.params[0], b = Q.params[1], c = Q.params[2], d = Q.params[3], e = Q.params[4], f = Q.params[5],
-               g = Q.params[6], h = Q.params[7], i = Q.params[8];
+// `coords` (3 per neighbour) are the coordinates in which `par` is expressed: the raw metric
+// coordinates for the reference path, sample-centred 1/r-scaled ones for the extended-precision
+// check (gradient DIRECTIONS are the same in both because the map is a translation + uniform scale).
+static void local_axes(const std::vector<double>& coords, const int32_t* cam, const std::vector<int>& nn,
+                       const double* par, const double sample[3], const double cam_origin[2][3], ag_frame& F) {
+  const double a = par[0], b = par[1], c = par[2], d = par[3], e = par[4], f = par[5], g = par[6], h = par[7],
+               i = par[8];
   const int m = int(nn.size());
   // :217-226 majority camera (maxCoeff: first max wins -> tie = 0)
   double cnt[2] = {0, 0};
@@ -412,7 +415,7 @@ static void local_axes(const float* xyz, const int32_t* cam, const std::vector<i
   // :238-247 gradient normals
   std::vector<double> G(size_t(3) * m);
   for (int t = 0; t < m; t++) {
-    const double x = xyz[3 * nn[t]], y = xyz[3 * nn[t] + 1], z = xyz[3 * nn[t] + 2];
+    const double x = coords[3 * t], y = coords[3 * t + 1], z = coords[3 * t + 2];
     double fx = (((2.0 * a) * x + d * y) + f * z) + g;
     double fy = (((2.0 * b) * y + d * x) + e * z) + h;
     double fz = (((2.0 * c) * z + e * y) + f * x) + i;
@@ -475,6 +478,123 @@ static void local_axes(const float* xyz, const int32_t* cam, const std::vector<i
   F.majority_cam = major;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Extended-precision check solve (NOT a reference path): the same Taubin fit, but posed in
+// sample-centred, 1/r-scaled coordinates (exact in long double because the inputs are floats) and
+// solved as the reduced 9x9 symmetric-definite pencil (A - m m^T/n) u = lambda B u by Cholesky +
+// cyclic Jacobi in 80-bit long double.  It is accurate to ~1e-16 and is used to measure (a) how far
+// LAPACK's dggev_ on the reference's uncentred, ill-conditioned 10x10 pencil lands from the exact
+// answer and (b) how close the CUDA path is to it.
+// ---------------------------------------------------------------------------------------------
+typedef long double ld;
+static void fit_quadric_exact(const float* xyz, const std::vector<int>& nn, const float* q, double radius,
+                              double par_out[10], std::vector<double>& coords) {
+  static const int E[10][3] = {{2, 0, 0}, {0, 2, 0}, {0, 0, 2}, {1, 1, 0}, {0, 1, 1},
+                               {1, 0, 1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 0, 0}};
+  const int n = int(nn.size());
+  coords.resize(size_t(3) * n);
+  ld mom[5][5][5];
+  for (auto& a : mom) for (auto& b : a) for (auto& c : b) c = 0;
+  const ld inv_r = ld(1) / ld(radius);
+  for (int t = 0; t < n; t++) {
+    ld v[3];
+    for (int d = 0; d < 3; d++) {
+      v[d] = (ld(xyz[3 * nn[t] + d]) - ld(q[d])) * inv_r;
+      coords[3 * t + d] = double(v[d]);
+    }
+    ld px[5] = {1, 0, 0, 0, 0}, py[5] = {1, 0, 0, 0, 0}, pz[5] = {1, 0, 0, 0, 0};
+    for (int k = 1; k < 5; k++) { px[k] = px[k - 1] * v[0]; py[k] = py[k - 1] * v[1]; pz[k] = pz[k - 1] * v[2]; }
+    for (int a = 0; a < 5; a++)
+      for (int b = 0; a + b < 5; b++)
+        for (int c = 0; a + b + c < 5; c++) mom[a][b][c] += px[a] * py[b] * pz[c];
+  }
+  ld A[9][9], B[9][9], mv[9];
+  const ld nn_ = mom[0][0][0];
+  for (int i = 0; i < 9; i++) mv[i] = mom[E[i][0]][E[i][1]][E[i][2]];
+  for (int i = 0; i < 9; i++)
+    for (int j = 0; j < 9; j++) {
+      A[i][j] = mom[E[i][0] + E[j][0]][E[i][1] + E[j][1]][E[i][2] + E[j][2]] - mv[i] * mv[j] / nn_;
+      ld bs = 0;
+      for (int a = 0; a < 3; a++)
+        if (E[i][a] >= 1 && E[j][a] >= 1) {
+          int ex[3] = {E[i][0] + E[j][0], E[i][1] + E[j][1], E[i][2] + E[j][2]};
+          ex[a] -= 2;
+          bs += ld(E[i][a] * E[j][a]) * mom[ex[0]][ex[1]][ex[2]];
+        }
+      B[i][j] = bs;
+    }
+  // Cholesky B = L L^T
+  ld L[9][9] = {};
+  for (int j = 0; j < 9; j++) {
+    ld d = B[j][j];
+    for (int k = 0; k < j; k++) d -= L[j][k] * L[j][k];
+    if (!(d > 0)) d = 1e-300L;
+    L[j][j] = sqrtl(d);
+    for (int i = j + 1; i < 9; i++) {
+      ld v = B[i][j];
+      for (int k = 0; k < j; k++) v -= L[i][k] * L[j][k];
+      L[i][j] = v / L[j][j];
+    }
+  }
+  // C = L^-1 A L^-T
+  ld X[9][9], Cm[9][9];
+  for (int c = 0; c < 9; c++)
+    for (int i = 0; i < 9; i++) {
+      ld v = A[i][c];
+      for (int k = 0; k < i; k++) v -= L[i][k] * X[k][c];
+      X[i][c] = v / L[i][i];
+    }
+  for (int r = 0; r < 9; r++)
+    for (int i = 0; i < 9; i++) {
+      ld v = X[r][i];
+      for (int k = 0; k < i; k++) v -= L[i][k] * Cm[r][k];
+      Cm[r][i] = v / L[i][i];
+    }
+  for (int i = 0; i < 9; i++)
+    for (int j = i + 1; j < 9; j++) Cm[i][j] = Cm[j][i] = (Cm[i][j] + Cm[j][i]) / 2;
+  ld V[9][9] = {};
+  for (int i = 0; i < 9; i++) V[i][i] = 1;
+  for (int sweep = 0; sweep < 60; sweep++) {
+    bool rotated = false;
+    for (int p = 0; p < 8; p++)
+      for (int q2 = p + 1; q2 < 9; q2++) {
+        const ld apq = Cm[p][q2], app = Cm[p][p], aqq = Cm[q2][q2];
+        if (!(fabsl(apq) > 1e-19L * sqrtl(fabsl(app * aqq)))) continue;
+        rotated = true;
+        const ld theta = (aqq - app) / (2 * apq);
+        const ld tt = (theta >= 0 ? 1 : -1) / (fabsl(theta) + sqrtl(theta * theta + 1));
+        const ld c = 1 / sqrtl(tt * tt + 1), s2 = tt * c;
+        for (int k = 0; k < 9; k++) {
+          const ld akp = Cm[k][p], akq = Cm[k][q2];
+          Cm[k][p] = c * akp - s2 * akq;
+          Cm[k][q2] = s2 * akp + c * akq;
+          const ld vkp = V[k][p], vkq = V[k][q2];
+          V[k][p] = c * vkp - s2 * vkq;
+          V[k][q2] = s2 * vkp + c * vkq;
+        }
+        for (int k = 0; k < 9; k++) {
+          const ld apk = Cm[p][k], aqk = Cm[q2][k];
+          Cm[p][k] = c * apk - s2 * aqk;
+          Cm[q2][k] = s2 * apk + c * aqk;
+        }
+        Cm[p][q2] = Cm[q2][p] = 0;
+      }
+    if (!rotated) break;
+  }
+  int mi = 0;
+  for (int k = 1; k < 9; k++)
+    if (Cm[k][k] < Cm[mi][mi]) mi = k;
+  ld u[9];
+  for (int i = 8; i >= 0; i--) {
+    ld v = V[i][mi];
+    for (int k = i + 1; k < 9; k++) v -= L[k][i] * u[k];
+    u[i] = v / L[i][i];
+  }
+  ld mu = 0;
+  for (int i = 0; i < 9; i++) { par_out[i] = double(u[i]); mu += mv[i] * u[i]; }
+  par_out[9] = double(-mu / nn_);
+}
+
 // deterministic permutation used only for the summation-sensitivity probe
 static void permute(std::vector<int>& v, int k) {
   uint64_t s = 0x9E3779B97F4A7C15ull * uint64_t(k + 1);
@@ -505,19 +625,27 @@ int fit_quadrics(const float* xyz, const int32_t* cam, int n, const Tree* tree, 
     ag_frame F;
     std::memset(&F, 0, sizeof(F));
     if (!nn.empty()) {
-      QuadricFit Q;
-      std::vector<int> nn_sum = nn;
-      if (sum_perm > 0) permute(nn_sum, sum_perm);
-      if (fit_quadric(xyz, nn_sum, Q) != 0) {
-#pragma omp critical
-        {
-          err = -1;
-          errmsg = g_err;
-        }
-        continue;
-      }
+      QuadricFit Q = {};
       const double sample[3] = {double(q[0]), double(q[1]), double(q[2])};  // hand_search.cpp:95
-      local_axes(xyz, cam, nn, Q, sample, cam_origin, F);
+      std::vector<double> coords;
+      if (sum_perm < 0) {  // extended-precision check solve
+        fit_quadric_exact(xyz, nn, q, radius, Q.params, coords);
+      } else {
+        std::vector<int> nn_sum = nn;
+        if (sum_perm > 0) permute(nn_sum, sum_perm);
+        if (fit_quadric(xyz, nn_sum, Q) != 0) {
+#pragma omp critical
+          {
+            err = -1;
+            errmsg = g_err;
+          }
+          continue;
+        }
+        coords.resize(size_t(3) * nn.size());
+        for (size_t t = 0; t < nn.size(); t++)
+          for (int d = 0; d < 3; d++) coords[3 * t + d] = double(xyz[3 * nn[t] + d]);
+      }
+      local_axes(coords, cam, nn, Q.params, sample, cam_origin, F);
       if (params_out) std::memcpy(params_out + size_t(10) * s, Q.params, sizeof(Q.params));
       if (MN_out) {
         std::memcpy(MN_out + size_t(200) * s, Q.M, sizeof(Q.M));

@@ -1,0 +1,54 @@
+"""N>1 host logic on CPU: contiguous sample sharding + all-gather of grasp records (gloo, world_size 2)."""
+import os
+import socket
+
+import numpy as np
+import torch.multiprocessing as mp
+
+from agile_grasp_b200.ctypes_defs import GRASP_DTYPE
+from agile_grasp_b200.shard import shard_range
+
+
+def test_shard_ranges_partition():
+    for n in (0, 1, 7, 2000, 20001):
+        for w in (1, 2, 3, 8):
+            r = [shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[k][1] == r[k + 1][0] for k in range(w - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from agile_grasp_b200.shard import all_gather_grasps, shard_range
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # a fake global result: hypothesis k belongs to sample k // 2; each rank owns a contiguous sample range
+    S = 11
+    allg = np.zeros(2 * S - 3, GRASP_DTYPE)
+    allg["sample_slot"] = np.arange(len(allg)) // 2
+    allg["orientation"] = np.arange(len(allg)) % 2
+    allg["width"] = np.arange(len(allg)) * 0.5
+    lo, hi = shard_range(S, rank, world)
+    local = allg[(allg["sample_slot"] >= lo) & (allg["sample_slot"] < hi)]
+    merged, counts = all_gather_grasps(local)
+    np.save(os.path.join(out_dir, f"merged_{rank}.npy"), merged)
+    np.save(os.path.join(out_dir, f"expect_{rank}.npy"), allg)
+    assert sum(counts) == len(allg)
+    dist.destroy_process_group()
+
+
+def test_all_gather_grasps_gloo(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        m = np.load(tmp_path / f"merged_{r}.npy")
+        e = np.load(tmp_path / f"expect_{r}.npy")
+        assert len(m) == len(e)
+        for nm in ("sample_slot", "orientation", "width"):
+            assert np.array_equal(m[nm], e[nm])
