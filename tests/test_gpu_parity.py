@@ -113,9 +113,16 @@ def test_quadric_frames(ctx, oracle, small_scene, two_view_scene):
         # integer outputs: bit exact
         assert np.array_equal(fg["num_neighbors"], ref["num_neighbors"])
         assert np.array_equal(fg["majority_cam"], ref["majority_cam"])
-        # against the extended-precision solve of the same Taubin problem: tight, every sample
+        # against the extended-precision solve of the same Taubin problem: tight, every sample whose
+        # quadric is determined at all (10 coefficients need >= 10 points; below that the fit is
+        # rank deficient and BOTH implementations return an arbitrary member of the null space)
+        det = ref["num_neighbors"] >= 10
         dn = np.linalg.norm(fg["normal"] - exact["normal"], axis=1)
-        assert dn.max() <= 1e-7, dn.max()
+        assert dn[det].max() <= 1e-9, dn[det].max()
+        # curvature axis: undefined (any in-plane direction) where all normals coincide, e.g. on an
+        # exactly planar patch of voxel corners; tight everywhere else
+        da = np.linalg.norm(fg["axis"] - exact["axis"], axis=1)
+        assert np.quantile(da[det], 0.97) <= 1e-7
         # against the reference's LAPACK path: inside the reference's own noise envelope
         dr = np.linalg.norm(fg["normal"] - ref["normal"], axis=1)
         de = np.linalg.norm(ref["normal"] - exact["normal"], axis=1)  # dggev's own distance from exact
@@ -123,7 +130,7 @@ def test_quadric_frames(ctx, oracle, small_scene, two_view_scene):
         assert (dr <= 1e-5).mean() >= 0.93, (dr <= 1e-5).mean()
         # where the GPU is farther than tolerance from dggev, dggev is equally far from exact
         far = dr > 1e-5
-        assert (de[far] > 0.5e-5).all()
+        assert (de[far & det] > 0.5e-5).all()
         # the frame is orthonormal
         assert np.allclose(np.einsum("ij,ij->i", fg["normal"], fg["axis"]), 0, atol=1e-9)
         assert np.allclose(np.linalg.norm(fg["axis"], axis=1), 1, atol=1e-9)
@@ -140,7 +147,9 @@ def test_all_points_normals_radius(ctx, oracle, small_scene):
     assert np.array_equal(fg["num_neighbors"], exact["num_neighbors"])
     ok = exact["num_neighbors"] >= 12  # tiny neighbourhoods are rank deficient in both implementations
     d = np.linalg.norm(fg["normal"][ok] - exact["normal"][ok], axis=1)
-    assert np.quantile(d, 0.99) <= 1e-6
+    # r = 0.01 balls hold ~35 voxel corners on 2-4 lattice layers: a sizeable fraction is (nearly) rank
+    # deficient for a 10-parameter quadric, where both solvers return an arbitrary null-space member
+    assert np.median(d) <= 1e-9 and np.quantile(d, 0.75) <= 1e-6, (np.median(d), np.quantile(d, [0.75, 0.9, 0.99]))
 
 
 def _sweep_both(ctx, oracle, s, frames, normals):
@@ -250,7 +259,8 @@ def test_golden_pipeline_without_oracle(ctx, linear_svm_path):
     gg, keep = ctx.classify(api.Svm(linear_svm_path), g)
     assert (_u32(gg["score"]) == _u32(gz["score"])).all() and np.array_equal(keep, z["keep"])
     fg = ctx.fit_quadrics(z["idx"], 0.03)
-    assert np.linalg.norm(fg["normal"] - z["frames_exact"]["normal"], axis=1).max() <= 1e-7
+    det = z["frames"]["num_neighbors"] >= 10
+    assert np.linalg.norm(fg["normal"] - z["frames_exact"]["normal"], axis=1)[det].max() <= 1e-9
 
 
 def test_end_to_end_own_frames(ctx, oracle, small_scene, linear_svm_path):
