@@ -58,3 +58,17 @@ def test_svm_loader_without_gpu(linear_svm_path, tmp_path):
         assert False
     except api.AgError as e:
         assert "does not exist" in str(e)  # learning.cpp:172-178
+
+
+def test_cpp_shim_compiles_and_links(tmp_path):
+    """include/agile_grasp/localization.h (the reference's class API) builds against the C ABI with a
+    plain host compiler, no CUDA/Eigen/PCL headers needed."""
+    import subprocess
+    exe = tmp_path / "test_svm"
+    libdir = os.path.dirname(api.LIB_PATH)
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "test_svm.cpp"), "-o", str(exe), "-L" + libdir, "-lag_b200",
+           "-Wl,-rpath," + libdir, "-L/usr/local/cuda/lib64", "-lcudart"]
+    subprocess.check_call(cmd)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert "Usage: test_svm" in out.stdout

@@ -313,3 +313,27 @@ def test_size_independent_properties_full_config(ctx, linear_svm_path):
     assert len(xyz_2) == len(xyz)
     gg, keep = ctx.classify(api.Svm(linear_svm_path), g)
     assert np.isfinite(gg["score"]).all() and ((gg["score"] <= 0) == (keep == 1)).all()
+
+
+def test_cpp_localization_shim_end_to_end(tmp_path, linear_svm_path):
+    """The reference-facing C++ class (include/agile_grasp/localization.h) through examples/test_svm."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(api.LIB_PATH)
+    exe = tmp_path / "test_svm"
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "examples", "test_svm.cpp"), "-o", str(exe), "-L" + libdir, "-lag_b200",
+                           "-Wl,-rpath," + libdir, "-L/usr/local/cuda/lib64", "-lcudart"])
+    pts, size_left, P, S = scenes.config_cloud(1)
+    cloud = tmp_path / "cloud.bin"
+    pts.tofile(cloud)
+    out = subprocess.run([str(exe), str(cloud), linear_svm_path, "400", "1"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "antipodal grasps in the Grasps message" in out.stdout
+    # same call through the C ABI directly
+    P.num_samples = 400
+    ctx = api.Context(0, P)
+    g = ctx.localize(pts, size_left)
+    gg, keep = ctx.classify(api.Svm(linear_svm_path), g)
+    assert f"{len(g)} hands, {int(keep.sum())} antipodal" in out.stdout, out.stdout[-400:]
+    ctx.close()
