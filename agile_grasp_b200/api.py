@@ -19,7 +19,7 @@ _LIB = None
 EXPORTS = [
     "ag_last_error", "ag_default_params", "ag_create", "ag_destroy", "ag_set_params", "ag_get_params",
     "ag_get_timings", "ag_free", "ag_svm_load", "ag_svm_free", "ag_svm_info", "ag_localize", "ag_localize_device",
-    "ag_classify", "ag_get_points", "ag_get_images", "ag_preprocess", "ag_set_cloud", "ag_radius_search",
+    "ag_classify", "ag_set_svm", "ag_get_points", "ag_get_images", "ag_preprocess", "ag_set_cloud", "ag_radius_search",
     "ag_fit_quadrics", "ag_hand_sweep", "ag_sweep_debug", "ag_hog_svm",
 ]
 
@@ -49,6 +49,7 @@ def lib():
     L.ag_localize.argtypes = loc_args
     L.ag_localize_device.argtypes = loc_args
     L.ag_classify.argtypes = [vp, vp, C.POINTER(AgGrasp), C.c_int, C.POINTER(C.c_uint8)]
+    L.ag_set_svm.argtypes = [vp, vp]
     L.ag_get_images.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint32)), ip]
     L.ag_preprocess.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_float)),
                                 C.POINTER(C.POINTER(C.c_int32)), ip]
@@ -162,6 +163,11 @@ class Context:
         _check(lib().ag_classify(self.h, svm.h, g.ctypes.data_as(C.POINTER(AgGrasp)), g.shape[0],
                                  keep.ctypes.data_as(C.POINTER(C.c_uint8))))
         return g, keep
+
+    def set_svm(self, svm):
+        """fuse scoring into localize(); pass None to detach"""
+        self._svm = svm  # keep the model alive while attached
+        _check(lib().ag_set_svm(self.h, None if svm is None else svm.h))
 
     def images(self):
         bits = C.POINTER(C.c_uint32)()

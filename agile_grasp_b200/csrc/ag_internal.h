@@ -38,6 +38,8 @@ struct HandConst {
   double cam[2][3];        // camera origins
   double img_cell;         // (0.05 - -0.05) / 100
   double half_od;          // outer_diameter / 2.0
+  double inv_slot_step;    // 1 / spacing step (index estimate for the slot lookup)
+  int uniform_slots;       // 1 if the slot edge tables are strictly ascending (fast lookup valid)
 };
 
 struct SvmModel {
@@ -75,9 +77,11 @@ struct Ctx {
   DevBuf samples, moments, frames, nn_counts;
   int n_samples = 0;
   // sweep outputs
-  DevBuf grasps_raw, valid, images_raw, hyp_slots, grasps, counters, scores, descriptors, sweep_dbg;
+  DevBuf grasps_raw, valid, images_raw, hyp_slots, grasps, counters, scores, descriptors, sweep_dbg, overflow;
   int n_hyp = 0;
   bool images_valid = false;
+  SvmModel* attached_svm = nullptr;  // ag_set_svm: score inside ag_localize
+  bool scores_valid = false;         // last_grasps carry scores of attached_svm
   bool keep_points = false;
   // host copies for ag_get_points
   std::vector<ag_grasp> last_grasps;
@@ -98,7 +102,7 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, double radius, ag_f
                         bool write_normals);
 int hand_sweep_device(Ctx* c, const int* d_indices, int n, const ag_frame* d_frames, unsigned flags);
 int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d_image_ids, int n,
-                   float* d_descriptors, float* d_scores);
+                   float* d_descriptors, float* d_scores, ag_grasp* d_grasps_out = nullptr);
 int radius_search_device(Ctx* c, const float q[3], double radius, std::vector<int>& out);
 
 void compute_hand_const(const ag_params& p, HandConst& h);

@@ -181,6 +181,7 @@ static int localize_core(Ctx* c, const void* d_points, int stride, int n_in, int
   std::memset(&c->timings, 0, sizeof(c->timings));
   c->timings.n_in = n_in;
   c->images_valid = false;
+  c->scores_valid = false;
   c->n_hyp = 0;
   c->launches = 0;
   cudaStream_t st = c->stream;
@@ -237,6 +238,15 @@ static int localize_core(Ctx* c, const void* d_points, int stride, int n_in, int
   if (rc) return rc;
   cudaEventRecord(c->ev[6], st);
   const int Hn = c->n_hyp;
+  if (c->attached_svm && Hn > 0) {  // fused scoring: no extra host round trip
+    if (c->scores.reserve(size_t(Hn) * 8 + 64)) return AG_ERR_CUDA;
+    cudaEventRecord(c->ev[8], st);
+    rc = hog_svm_device(c, c->attached_svm, c->images_raw.as<uint32_t>(), c->hyp_slots.as<int>(), Hn, nullptr,
+                        c->scores.as<float>(), c->grasps.as<ag_grasp>());
+    if (rc) return rc;
+    cudaEventRecord(c->ev[9], st);
+    cudaEventRecord(c->ev[6], st);
+  }
   ag_grasp* res = static_cast<ag_grasp*>(std::malloc(std::max<size_t>(1, size_t(Hn)) * sizeof(ag_grasp)));
   if (Hn > 0) AG_CUDA_CHECK(cudaMemcpyAsync(res, c->grasps.p, size_t(Hn) * sizeof(ag_grasp), cudaMemcpyDeviceToHost, st));
   unsigned long long ctr[8];
@@ -249,6 +259,11 @@ static int localize_core(Ctx* c, const void* d_points, int stride, int n_in, int
   c->timings.quadric_ms = elapsed(c->ev[4], c->ev[5]);
   c->timings.sweep_ms = elapsed(c->ev[5], c->ev[6]);
   c->timings.d2h_ms = elapsed(c->ev[6], c->ev[7]);
+  if (c->attached_svm && Hn > 0) {
+    c->timings.hog_svm_ms = elapsed(c->ev[8], c->ev[9]);
+    c->timings.sweep_ms = elapsed(c->ev[5], c->ev[8]);
+    c->scores_valid = true;
+  }
   c->timings.total_ms = elapsed(c->ev[0], c->ev[7]);
   c->timings.n_hyp = Hn;
   c->timings.moments_ms = elapsed(c->ev_k[0], c->ev_k[1]);
@@ -344,7 +359,7 @@ void ag_destroy(ag_ctx* h) {
   for (DevBuf* b : {&c.raw, &c.keys, &c.keys_sorted, &c.keys_unique, &c.cub_tmp, &c.block_counts, &c.misc, &c.vox,
                     &c.cell_ids, &c.cell_ids_sorted, &c.perm, &c.perm_sorted, &c.cell_start, &c.pts, &c.inv,
                     &c.normals, &c.samples, &c.moments, &c.frames, &c.nn_counts, &c.grasps_raw, &c.valid,
-                    &c.images_raw, &c.hyp_slots, &c.grasps, &c.counters, &c.scores, &c.descriptors, &c.sweep_dbg})
+                    &c.images_raw, &c.hyp_slots, &c.grasps, &c.counters, &c.scores, &c.descriptors, &c.sweep_dbg, &c.overflow})
     b->release();
   if (c.h_pinned) cudaFreeHost(c.h_pinned);
   for (auto& ev : c.ev) cudaEventDestroy(ev);
@@ -444,28 +459,42 @@ int ag_classify(ag_ctx* h, const ag_svm* svm, ag_grasp* grasps, int n, uint8_t* 
     set_error("ag_classify: no grasp images resident (call ag_localize / ag_hand_sweep first)");
     return AG_ERR_INVALID;
   }
-  std::vector<int> slots(n);
+  bool identity = n == c.n_hyp;
   for (int i = 0; i < n; i++) {
     const int id = grasps[i].image_id;
     if (id < 0 || id >= c.n_hyp) {
       set_error("ag_classify: image_id does not belong to the last localize call");
       return AG_ERR_INVALID;
     }
-    slots[i] = id;
+    identity = identity && id == i;
+  }
+  if (c.scores_valid && c.attached_svm == svm->m) {
+    // already scored inside ag_localize (ag_set_svm): hand the results back
+    for (int i = 0; i < n; i++) {
+      const ag_grasp& r = c.last_grasps[grasps[i].image_id];
+      grasps[i].score = r.score;
+      grasps[i].label = r.label;
+      if (keep) keep[i] = r.label;
+    }
+    return AG_OK;
   }
   cudaEventRecord(c.ev[8], c.stream);
-  // image_id h -> raw slot hyp_slots[h]; build the slot list on the device
   DevBuf& sc = c.scores;
   if (sc.reserve(size_t(n) * 8 + 64)) return AG_ERR_CUDA;
   float* d_scores = sc.as<float>();
-  int* d_ids = reinterpret_cast<int*>(d_scores + n);
-  // translate ids to raw slots on the host side of the table (small D2H avoided: keep a host copy)
-  std::vector<int> raw_slots(c.n_hyp);
-  AG_CUDA_CHECK(cudaMemcpyAsync(raw_slots.data(), c.hyp_slots.p, size_t(c.n_hyp) * 4, cudaMemcpyDeviceToHost, c.stream));
-  AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
-  for (int i = 0; i < n; i++) slots[i] = raw_slots[slots[i]];
-  AG_CUDA_CHECK(cudaMemcpyAsync(d_ids, slots.data(), size_t(n) * 4, cudaMemcpyHostToDevice, c.stream));
-  int rc = hog_svm_device(&c, svm->m, c.images_raw.as<uint32_t>(), d_ids, n, nullptr, d_scores);
+  const int* d_slots = c.hyp_slots.as<int>();  // image_id h -> raw (sample, orientation) slot
+  if (!identity) {
+    // arbitrary subset / order: translate ids to raw slots through a host copy of the table
+    std::vector<int> raw_slots(c.n_hyp), slots(n);
+    AG_CUDA_CHECK(cudaMemcpyAsync(raw_slots.data(), c.hyp_slots.p, size_t(c.n_hyp) * 4, cudaMemcpyDeviceToHost, c.stream));
+    AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    for (int i = 0; i < n; i++) slots[i] = raw_slots[grasps[i].image_id];
+    int* d_ids = reinterpret_cast<int*>(d_scores + n);
+    AG_CUDA_CHECK(cudaMemcpyAsync(d_ids, slots.data(), size_t(n) * 4, cudaMemcpyHostToDevice, c.stream));
+    AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    d_slots = d_ids;
+  }
+  int rc = hog_svm_device(&c, svm->m, c.images_raw.as<uint32_t>(), d_slots, n, nullptr, d_scores);
   if (rc) return rc;
   std::vector<float> sc_h(n);
   AG_CUDA_CHECK(cudaMemcpyAsync(sc_h.data(), d_scores, size_t(n) * 4, cudaMemcpyDeviceToHost, c.stream));
@@ -479,6 +508,13 @@ int ag_classify(ag_ctx* h, const ag_svm* svm, ag_grasp* grasps, int n, uint8_t* 
     grasps[i].label = sc_h[i] > 0 ? 0 : 1;
     if (keep) keep[i] = grasps[i].label;
   }
+  return AG_OK;
+}
+
+int ag_set_svm(ag_ctx* h, const ag_svm* svm) {
+  if (!h) return AG_ERR_INVALID;
+  h->c.attached_svm = svm ? svm->m : nullptr;
+  h->c.scores_valid = false;
   return AG_OK;
 }
 

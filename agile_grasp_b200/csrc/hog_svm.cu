@@ -29,19 +29,21 @@ constexpr int UBX = 11, UBY = 7, NUB = UBX * UBY;  // distinct blocks
 constexpr int CELL_LIST = 144;                      // pixels contributing to one cell of a block
 constexpr int kThreads = 320;                       // >= 77*4 = 308 (block, cell) work items
 
-struct CellEntry {
-  int ofs;    // pixel offset inside the image relative to the block origin: i*W + j
-  float w;    // gradWeight * histWeight (rounded binary32 product, as OpenCV forms it)
+struct CellRun {     // consecutive rows of one block column that feed one cell, in OpenCV's order
+  short j, i0, len, first;  // block column, first block row, run length, index of the first weight
 };
+constexpr int kMaxRuns = 24;
 struct HogTables {
-  CellEntry cell[4][CELL_LIST];
-  float g0[9], g1[9];  // magnitude split between the two nearest bins, per gradient case
+  float w[4][CELL_LIST + 1];     // gradWeight * histWeight per contribution (+1: bank padding)
+  CellRun runs[4][kMaxRuns];
+  int n_runs[4];
+  float g0[9], g1[9];            // magnitude split between the two nearest bins, per gradient case
   int h0[9], h1[9];
 };
 __constant__ HogTables c_hog;
 
 // cv::cartToPolar(dx,dy) for (sign dx, sign dy): index (sy+1)*3 + (sx+1); values measured from
-// cv2 4.13 (tools/gen_hog_tables.py), stored as bit patterns
+// cv2 4.13 (tests/test_oracle_hog_svm.py checks them against the live library), stored as bit patterns
 const uint32_t kMagBits[9] = {0x41b4aa5a, 0x417f7fe0, 0x41b4aa5a, 0x417f7fe0, 0x0, 0x417f7fe0, 0x41b4aa5a, 0x417f7fe0,
                               0x41b4aa5a};
 const uint32_t kAngBits[9] = {0x407b5116, 0x4096cbe4, 0x40afef3d, 0x40490fdb, 0x0, 0x0, 0x4016ce9f, 0x3fc90fdb,
@@ -70,8 +72,9 @@ void build_tables(HogTables& T) {
     T.h1[k] = hidx;
   }
   // HOGCache::init: gaussian weights exp(-(di^2+dj^2)/(2 sigma^2)), di = i - 8, sigma = 4, and the
-  // bilinear cell interpolation classes; we regroup OpenCV's per-pixel lists into per-cell lists
-  // that preserve the order in which each histogram bin receives its contributions.
+  // bilinear cell interpolation classes; OpenCV's per-pixel lists (pixels touching 1 | 2 | 4 cells, each
+  // in column-major block order) are regrouped into per-cell lists that preserve the order in which
+  // each histogram bin receives its contributions, then cut into runs of consecutive rows.
   float weights[BS][BS];
   const float sigma = 4.0f, scale = 1.f / (sigma * sigma * 2);
   float d2[BS];
@@ -82,7 +85,7 @@ void build_tables(HogTables& T) {
   for (int i = 0; i < BS; i++)
     for (int j = 0; j < BS; j++) weights[i][j] = std::exp(-(d2[i] + d2[j]) * scale);
   struct Contribution {
-    int cell, ofs;
+    int cell, i, j;
     float w;
   };
   std::vector<Contribution> lists[3];  // pixels touching 1, 2, 4 cells
@@ -95,42 +98,52 @@ void build_tables(HogTables& T) {
       cellY -= iy0;
       auto in = [](int v) { return v >= 0 && v < 2; };
       const float gw = weights[i][j];
-      const int ofs = i * W + j;
       const float wx[2] = {1.f - cellX, cellX}, wy[2] = {1.f - cellY, cellY};
       const bool bx = in(ix0) && in(ix1), by = in(iy0) && in(iy1);
       std::vector<Contribution>& dst = lists[(bx ? 1 : 0) + (by ? 1 : 0)];
       if (bx && by) {  // order: (x0,y0) (x1,y0) (x0,y1) (x1,y1)
-        dst.push_back({ix0 * 2 + iy0, ofs, gw * (wx[0] * wy[0])});
-        dst.push_back({ix1 * 2 + iy0, ofs, gw * (wx[1] * wy[0])});
-        dst.push_back({ix0 * 2 + iy1, ofs, gw * (wx[0] * wy[1])});
-        dst.push_back({ix1 * 2 + iy1, ofs, gw * (wx[1] * wy[1])});
+        dst.push_back({ix0 * 2 + iy0, i, j, gw * (wx[0] * wy[0])});
+        dst.push_back({ix1 * 2 + iy0, i, j, gw * (wx[1] * wy[0])});
+        dst.push_back({ix0 * 2 + iy1, i, j, gw * (wx[0] * wy[1])});
+        dst.push_back({ix1 * 2 + iy1, i, j, gw * (wx[1] * wy[1])});
       } else if (bx) {  // two cells along x; y clamps to the one valid cell (weight cellY or 1-cellY)
         const int cy = in(iy0) ? iy0 : iy1;
         const float wyv = in(iy0) ? 1.f - cellY : cellY;
-        dst.push_back({ix0 * 2 + cy, ofs, gw * (wx[0] * wyv)});
-        dst.push_back({ix1 * 2 + cy, ofs, gw * (wx[1] * wyv)});
+        dst.push_back({ix0 * 2 + cy, i, j, gw * (wx[0] * wyv)});
+        dst.push_back({ix1 * 2 + cy, i, j, gw * (wx[1] * wyv)});
       } else if (by) {
         const int cx = in(ix0) ? ix0 : ix1;
         const float wxv = in(ix0) ? 1.f - cellX : cellX;
-        dst.push_back({cx * 2 + iy0, ofs, gw * (wxv * wy[0])});
-        dst.push_back({cx * 2 + iy1, ofs, gw * (wxv * wy[1])});
+        dst.push_back({cx * 2 + iy0, i, j, gw * (wxv * wy[0])});
+        dst.push_back({cx * 2 + iy1, i, j, gw * (wxv * wy[1])});
       } else {
         const int cx = in(ix0) ? ix0 : ix1, cy = in(iy0) ? iy0 : iy1;
         const float wxv = in(ix0) ? 1.f - cellX : cellX, wyv = in(iy0) ? 1.f - cellY : cellY;
-        dst.push_back({cx * 2 + cy, ofs, gw * (wxv * wyv)});
+        dst.push_back({cx * 2 + cy, i, j, gw * (wxv * wyv)});
       }
     }
   int fill[4] = {0, 0, 0, 0};
-  for (int cls = 0; cls < 3; cls++)
-    for (const Contribution& c : lists[cls]) {
-      T.cell[c.cell][fill[c.cell]].ofs = c.ofs;
-      T.cell[c.cell][fill[c.cell]].w = c.w;
-      fill[c.cell]++;
+  int last_i[4], last_j[4];
+  for (int c = 0; c < 4; c++) T.n_runs[c] = 0;
+  for (int cls = 0; cls < 3; cls++) {
+    for (int c = 0; c < 4; c++) last_i[c] = last_j[c] = -9;  // a run never spans two classes
+    for (const Contribution& ct : lists[cls]) {
+      const int c = ct.cell;
+      T.w[c][fill[c]] = ct.w;
+      if (ct.j == last_j[c] && ct.i == last_i[c] + 1) {
+        T.runs[c][T.n_runs[c] - 1].len++;
+      } else {
+        CellRun& r = T.runs[c][T.n_runs[c]++];
+        r.j = short(ct.j);
+        r.i0 = short(ct.i);
+        r.len = 1;
+        r.first = short(fill[c]);
+      }
+      last_i[c] = ct.i;
+      last_j[c] = ct.j;
+      fill[c]++;
     }
-}
-
-__device__ __forceinline__ int reflect101(int p, int len) {  // cv::borderInterpolate, BORDER_REFLECT_101
-  return p < 0 ? -p : (p >= len ? 2 * len - 2 - p : p);
+  }
 }
 
 struct SvmDev {
@@ -141,57 +154,107 @@ struct SvmDev {
   double gamma, coef0, rho;
 };
 
+constexpr int RW = 4;  // 32-bit words per image row (100 px -> 128-bit rows)
+
+__device__ __forceinline__ uint32_t bits_at(const uint32_t* img, int bit0) {  // 32 bits starting at bit0
+  const int w = bit0 >> 5, sh = bit0 & 31;
+  return __funnelshift_r(img[w], img[w + 1], sh);
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slots, int n, SvmDev svm,
-          float* __restrict__ descriptors, float* __restrict__ scores) {
-  __shared__ uint32_t s_bits[AG_IMAGE_WORDS];
-  __shared__ uint8_t s_case[W * H];
-  __shared__ float s_hist[NUB * 36];
-  __shared__ float s_K[1280];       // kernel values per support vector (sv_total <= 1280 in-smem)
+          float* __restrict__ descriptors, float* __restrict__ scores, ag_grasp* __restrict__ grasps_out) {
+  __shared__ uint32_t s_bits[AG_IMAGE_WORDS + 2];
+  __shared__ uint32_t s_row[H][RW];                 // row-aligned image
+  __shared__ uint32_t s_xp[H][RW], s_xn[H][RW], s_yp[H][RW], s_yn[H][RW];  // gradient sign bit-planes
+  __shared__ uint32_t s_col[W][3];                  // per column: 80-bit mask of non-zero-gradient pixels
+  __shared__ __align__(16) float s_hist[NUB * 36];
+  __shared__ float s_K[1280];                       // kernel values per support vector
   __shared__ double s_part[kThreads / 32];
   const int hyp = blockIdx.x;
   if (hyp >= n) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t* src = images + size_t(image_slots ? image_slots[hyp] : hyp) * AG_IMAGE_WORDS;
-  for (int i = tid; i < AG_IMAGE_WORDS; i += kThreads) s_bits[i] = src[i];
+  for (int i = tid; i < AG_IMAGE_WORDS + 2; i += kThreads) s_bits[i] = i < AG_IMAGE_WORDS ? src[i] : 0u;
   __syncthreads();
-  // gradient case per pixel
-  auto px = [&](int y, int x) -> int {
-    const int b = y * W + x;
-    return (s_bits[b >> 5] >> (b & 31)) & 1u;
-  };
-  for (int p = tid; p < W * H; p += kThreads) {
-    const int y = p / W, x = p % W;
-    const int sx = px(y, reflect101(x + 1, W)) - px(y, reflect101(x - 1, W));
-    const int sy = px(reflect101(y + 1, H), x) - px(reflect101(y - 1, H), x);
-    s_case[p] = uint8_t((sy + 1) * 3 + (sx + 1));
+  // 1. row-aligned copy: row r = bits [100 r, 100 r + 100)
+  {
+    const int r = tid >> 2, w = tid & 3;  // 320 threads = 80 rows x 4 words
+    uint32_t v = bits_at(s_bits, r * W + 32 * w);
+    if (w == 3) v &= 0xFu;  // columns 96..99
+    s_row[r][w] = v;
   }
   __syncthreads();
-  // block histograms: one thread per (distinct block, cell)
+  // 2. gradient sign planes ([-1,0,1] derivative with BORDER_REFLECT_101 on the binary image)
+  {
+    const int r = tid >> 2, w = tid & 3;
+    const uint32_t cur = s_row[r][w];
+    const uint32_t prev = w > 0 ? s_row[r][w - 1] : 0u, next = w < 3 ? s_row[r][w + 1] : 0u;
+    uint32_t R = (cur >> 1) | (next << 31);   // pixel x+1
+    uint32_t L = (cur << 1) | (prev >> 31);   // pixel x-1
+    if (w == 0) L = (L & ~1u) | ((cur >> 1) & 1u);                 // x = 0 : left neighbour is pixel 1
+    if (w == 3) R = (R & ~(1u << 3)) | (((cur >> 2) & 1u) << 3);   // x = 99: right neighbour is pixel 98
+    const uint32_t U = s_row[r == 0 ? 1 : r - 1][w], D = s_row[r == H - 1 ? H - 2 : r + 1][w];
+    const uint32_t valid = w == 3 ? 0xFu : 0xFFFFFFFFu;
+    s_xp[r][w] = R & ~L & valid;
+    s_xn[r][w] = L & ~R & valid;
+    s_yp[r][w] = D & ~U & valid;
+    s_yn[r][w] = U & ~D & valid;
+  }
+  __syncthreads();
+  // 3. column masks of pixels with a non-zero gradient
+  if (tid < W) {
+    const int x = tid, w = x >> 5, sh = x & 31;
+    uint32_t m0 = 0, m1 = 0, m2 = 0;
+    for (int r = 0; r < H; r++) {
+      const uint32_t nz = ((s_xp[r][w] | s_xn[r][w] | s_yp[r][w] | s_yn[r][w]) >> sh) & 1u;
+      if (r < 32) m0 |= nz << r;
+      else if (r < 64) m1 |= nz << (r - 32);
+      else m2 |= nz << (r - 64);
+    }
+    s_col[x][0] = m0;
+    s_col[x][1] = m1;
+    s_col[x][2] = m2;
+  }
+  __syncthreads();
+  // 4. block histograms: one thread per (distinct block, cell); only pixels with a gradient are visited,
+  //    in OpenCV's accumulation order
   if (tid < NUB * 4) {
     const int ub = tid >> 2, cell = tid & 3;
-    const int ubx = ub / UBY, uby = ub % UBY;
-    const uint8_t* gc = s_case + (uby * 8) * W + ubx * 8;
+    const int ox = (ub / UBY) * 8, oy = (ub % UBY) * 8;
     float h[9];
 #pragma unroll
     for (int b = 0; b < 9; b++) h[b] = 0.f;
-    for (int v = 0; v < CELL_LIST; v++) {
-      const CellEntry ce = c_hog.cell[cell][v];
-      const int c = gc[ce.ofs];
-      if (c == 4) continue;  // zero gradient: adds +0 to both bins
-      const float a0 = __fmul_rn(c_hog.g0[c], ce.w), a1 = __fmul_rn(c_hog.g1[c], ce.w);
-      const int b0 = c_hog.h0[c], b1 = c_hog.h1[c];
+    const int nr = c_hog.n_runs[cell];
+    for (int rI = 0; rI < nr; rI++) {
+      const CellRun run = c_hog.runs[cell][rI];
+      const int x = ox + run.j, y0 = oy + run.i0;
+      // bits y0 .. y0+len-1 of the 80-bit column mask
+      const int wq = y0 >> 5, sh = y0 & 31;
+      const uint32_t lo = s_col[x][wq], hi = wq < 2 ? s_col[x][wq + 1] : 0u;
+      uint32_t m = __funnelshift_r(lo, hi, sh) & ((1u << run.len) - 1u);
+      while (m) {
+        const int i = __ffs(m) - 1;
+        m &= m - 1;
+        const int y = y0 + i, wx = x >> 5, bx = x & 31;
+        const int sx = int((s_xp[y][wx] >> bx) & 1u) - int((s_xn[y][wx] >> bx) & 1u);
+        const int sy = int((s_yp[y][wx] >> bx) & 1u) - int((s_yn[y][wx] >> bx) & 1u);
+        const int c = (sy + 1) * 3 + (sx + 1);
+        const float wgt = c_hog.w[cell][run.first + i];
+        const float a0 = __fmul_rn(c_hog.g0[c], wgt), a1 = __fmul_rn(c_hog.g1[c], wgt);
+        const int b0 = c_hog.h0[c], b1 = c_hog.h1[c];
 #pragma unroll
-      for (int b = 0; b < 9; b++) {
-        if (b == b0) h[b] = __fadd_rn(h[b], a0);
-        if (b == b1) h[b] = __fadd_rn(h[b], a1);
+        for (int b = 0; b < 9; b++) {
+          if (b == b0) h[b] = __fadd_rn(h[b], a0);
+          if (b == b1) h[b] = __fadd_rn(h[b], a1);
+        }
       }
     }
 #pragma unroll
     for (int b = 0; b < 9; b++) s_hist[ub * 36 + cell * 9 + b] = h[b];
   }
   __syncthreads();
-  // L2-Hys normalisation per block (HOGCache::normalizeBlockHistogram), 4 interleaved partial sums
+  // 5. L2-Hys normalisation per block (HOGCache::normalizeBlockHistogram), 4 interleaved partial sums
   if (tid < NUB) {
     float* hist = s_hist + tid * 36;
     float part[4] = {0.f, 0.f, 0.f, 0.f};
@@ -213,45 +276,57 @@ k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slo
     for (int i = 0; i < 36; i++) hist[i] = __fmul_rn(hist[i], scale);
   }
   __syncthreads();
-  // descriptor element k -> histogram entry: k = ((w*7 + bx)*7 + by)*36 + e
-  auto desc_at = [&](int k) -> float {
-    const int e = k % 36, blk = k / 36;
-    const int by = blk % 7, bx = (blk / 7) % 7, w = blk / 49;
-    return s_hist[((w * 4 + bx) * UBY + by) * 36 + e];
+  // descriptor group k4 (4 consecutive floats) -> histogram entry: k = ((w*7 + bx)*7 + by)*36 + e
+  auto desc4 = [&](int k4) -> float4 {
+    const int blk = k4 / 9, e = (k4 - blk * 9) * 4;
+    const int by = blk % 7, bxw = blk / 7;          // bxw = w*7 + bx
+    const int ubx = (bxw / 7) * 4 + (bxw % 7);
+    return *reinterpret_cast<const float4*>(s_hist + (ubx * UBY + by) * 36 + e);
   };
   if (descriptors)
-    for (int k = tid; k < AG_HOG_DIM; k += kThreads) descriptors[size_t(hyp) * AG_HOG_DIM + k] = desc_at(k);
-  // SVM kernel values (CvSVMKernel::calc_non_rbf_base): binary32 products, 4-term binary32 sums,
-  // binary64 accumulation; one warp per support vector
-  for (int j = warp; j < svm.sv_total; j += kThreads / 32) {
-    const float* sv = svm.sv + size_t(j) * AG_HOG_DIM;
-    double acc = 0.0;
-    for (int k4 = lane; k4 < AG_HOG_DIM / 4; k4 += 32) {
-      const float4 s4 = __ldg(reinterpret_cast<const float4*>(sv) + k4);
-      const int k = k4 * 4;
-      float t = __fmul_rn(s4.x, desc_at(k));
-      t = __fadd_rn(t, __fmul_rn(s4.y, desc_at(k + 1)));
-      t = __fadd_rn(t, __fmul_rn(s4.z, desc_at(k + 2)));
-      t = __fadd_rn(t, __fmul_rn(s4.w, desc_at(k + 3)));
-      acc += double(t);
+    for (int k4 = tid; k4 < AG_HOG_DIM / 4; k4 += kThreads)
+      reinterpret_cast<float4*>(descriptors + size_t(hyp) * AG_HOG_DIM)[k4] = desc4(k4);
+  // 6. SVM kernel values (CvSVMKernel::calc_non_rbf_base): binary32 products, 4-term binary32 sums,
+  //    binary64 accumulation.  One support vector: the whole CTA shares the dot product; many: one warp each.
+  auto group_term = [&](const float* sv, int k4) -> double {
+    const float4 s4 = __ldg(reinterpret_cast<const float4*>(sv) + k4);
+    const float4 d4 = desc4(k4);
+    float t = __fmul_rn(s4.x, d4.x);
+    t = __fadd_rn(t, __fmul_rn(s4.y, d4.y));
+    t = __fadd_rn(t, __fmul_rn(s4.z, d4.z));
+    t = __fadd_rn(t, __fmul_rn(s4.w, d4.w));
+    return double(t);
+  };
+  auto kernel_value = [&](double acc) -> float {
+    if (svm.kernel == 0) return float(acc * 1.0 + 0.0);
+    float kv = float(acc * svm.gamma + svm.coef0);
+    float b = kv, a = 1.f;  // cv::pow with an integer exponent: repeated binary32 multiplication
+    int p = svm.degree;
+    while (p > 1) {
+      if (p & 1) a = __fmul_rn(a, b);
+      b = __fmul_rn(b, b);
+      p >>= 1;
     }
+    return __fmul_rn(a, b);
+  };
+  if (svm.sv_total == 1) {
+    double acc = 0.0;
+    for (int k4 = tid; k4 < AG_HOG_DIM / 4; k4 += kThreads) acc += group_term(svm.sv, k4);
     acc = warp_sum(acc);
-    if (lane == 0) {
-      float kv;
-      if (svm.kernel == 0) kv = float(acc * 1.0 + 0.0);
-      else {
-        kv = float(acc * svm.gamma + svm.coef0);
-        // cv::pow with an integer exponent: repeated binary32 multiplication
-        float b = kv, a = 1.f;
-        int p = svm.degree;
-        while (p > 1) {
-          if (p & 1) a = __fmul_rn(a, b);
-          b = __fmul_rn(b, b);
-          p >>= 1;
-        }
-        kv = __fmul_rn(a, b);
-      }
-      if (j < 1280) s_K[j] = kv;
+    if (lane == 0) s_part[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w2 = 0; w2 < kThreads / 32; w2++) t += s_part[w2];
+      s_K[0] = kernel_value(t);
+    }
+  } else {
+    for (int j = warp; j < svm.sv_total; j += kThreads / 32) {
+      const float* sv = svm.sv + size_t(j) * AG_HOG_DIM;
+      double acc = 0.0;
+      for (int k4 = lane; k4 < AG_HOG_DIM / 4; k4 += 32) acc += group_term(sv, k4);
+      acc = warp_sum(acc);
+      if (lane == 0 && j < 1280) s_K[j] = kernel_value(acc);
     }
   }
   __syncthreads();
@@ -259,12 +334,18 @@ k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slo
   double part = 0.0;
   for (int kk = tid; kk < svm.sv_count; kk += kThreads) part += svm.alpha[kk] * double(s_K[svm.index[kk]]);
   part = warp_sum(part);
+  __syncthreads();
   if (lane == 0) s_part[warp] = part;
   __syncthreads();
   if (tid == 0) {
     double sum = -svm.rho;
     for (int w2 = 0; w2 < kThreads / 32; w2++) sum += s_part[w2];
-    scores[hyp] = float(sum);
+    const float sc = float(sum);
+    scores[hyp] = sc;
+    if (grasps_out) {  // fused classify: write score and label into the compacted record
+      grasps_out[hyp].score = sc;
+      grasps_out[hyp].label = sc > 0.f ? 0 : 1;  // CvSVM::predict: label +1 <=> sum <= 0
+    }
   }
 }
 
@@ -291,7 +372,7 @@ int svm_to_device(SvmModel* svm, int device) {
 }
 
 int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d_image_slots, int n,
-                   float* d_descriptors, float* d_scores) {
+                   float* d_descriptors, float* d_scores, ag_grasp* d_grasps_out) {
   if (n <= 0) return AG_OK;
   if (svm->var_count != AG_HOG_DIM) {
     set_error("SVM var_count != 3528");
@@ -322,7 +403,7 @@ int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d
   sd.coef0 = svm->coef0;
   sd.rho = svm->rho;
   c->launches += 1;
-  k_hog_svm<<<n, kThreads, 0, c->stream>>>(d_images, d_image_slots, n, sd, d_descriptors, d_scores);
+  k_hog_svm<<<n, kThreads, 0, c->stream>>>(d_images, d_image_slots, n, sd, d_descriptors, d_scores, d_grasps_out);
   AG_CUDA_CHECK(cudaGetLastError());
   return AG_OK;
 }

@@ -18,6 +18,13 @@ namespace {
 constexpr int kBlock = 256;
 constexpr uint64_t kInvalidKey = ~0ull;
 
+// voxel key = cam | kx | ky | kz packed with per-axis bit widths derived from the workspace extent, so
+// the radix sort only touches the bits that can be set
+struct KeyBits {
+  int bx, by, bz;  // bits per axis (<= 21)
+  int total;       // 1 + bx + by + bz
+};
+
 struct PreState {
   int cam_min[2][3];  // ordered-int encoded float minima per camera
   int bb_min[3];      // bounding box of the voxelised cloud (ordered ints)
@@ -125,27 +132,32 @@ __global__ void k_classify(const char* pts, int stride, int n, int size_left, co
   bool keep = fin && double(x) >= w0 && double(x) <= w1 && double(y) >= w2 && double(y) <= w3 && double(z) >= w4 &&
               double(z) <= w5;
   if (i < n) flag[i] = keep ? uint8_t(1 + label) : uint8_t(0);
-  // minima (localization.cpp:256-277): warp-reduce, then one atomic per warp, camera and axis
-  for (int c = 0; c < 2; c++) {
-    bool mine = keep && label == c;
-    if (__ballot_sync(0xffffffffu, mine) == 0) continue;
-    int ox = mine ? float_to_ordered(x) : 0x7FFFFFFF;
-    int oy = mine ? float_to_ordered(y) : 0x7FFFFFFF;
-    int oz = mine ? float_to_ordered(z) : 0x7FFFFFFF;
-    ox = __reduce_min_sync(0xffffffffu, ox);
-    oy = __reduce_min_sync(0xffffffffu, oy);
-    oz = __reduce_min_sync(0xffffffffu, oz);
-    if ((threadIdx.x & 31) == 0) {
-      atomicMin(&st->cam_min[c][0], ox);
-      atomicMin(&st->cam_min[c][1], oy);
-      atomicMin(&st->cam_min[c][2], oz);
+  // minima (localization.cpp:256-277): warp reduce -> shared -> one atomic per block, camera and axis
+  __shared__ int s_min[6][kBlock / 32];
+  {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int ov[3] = {float_to_ordered(x), float_to_ordered(y), float_to_ordered(z)};
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      const bool mine = keep && label == c;
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        const int r = __reduce_min_sync(0xffffffffu, mine ? ov[a] : 0x7FFFFFFF);
+        if (lane == 0) s_min[c * 3 + a][w] = r;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      int r = s_min[threadIdx.x][0];
+      for (int k = 1; k < kBlock / 32; k++) r = min(r, s_min[threadIdx.x][k]);
+      if (r != 0x7FFFFFFF) atomicMin(&st->cam_min[threadIdx.x / 3][threadIdx.x % 3], r);
     }
   }
 }
 
 // key = cam<<63 | kx<<42 | ky<<21 | kz with k = floor((p - min)/cell) in binary64 (localization.cpp:289,357-362)
 __global__ void k_keys(const char* pts, int stride, int n, const uint8_t* flag, double cell, PreState* st,
-                       uint64_t* keys) {
+                       uint64_t* keys, KeyBits kb) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint8_t f = flag[i];
@@ -162,16 +174,18 @@ __global__ void k_keys(const char* pts, int stride, int n, const uint8_t* flag, 
   double kx = floor(__ddiv_rn(__dsub_rn(double(x), mx), cell));
   double ky = floor(__ddiv_rn(__dsub_rn(double(y), my), cell));
   double kz = floor(__ddiv_rn(__dsub_rn(double(z), mz), cell));
-  if (kx >= 2097152.0 || ky >= 2097152.0 || kz >= 2097152.0) {
+  if (kx >= double((1u << kb.bx) - 1u) || ky >= double((1u << kb.by) - 1u) || kz >= double((1u << kb.bz) - 1u)) {
     st->key_overflow = 1;
     keys[i] = kInvalidKey;
     return;
   }
-  keys[i] = (uint64_t(c) << 63) | (uint64_t(kx) << 42) | (uint64_t(ky) << 21) | uint64_t(kz);
+  keys[i] = (uint64_t(c) << (kb.bx + kb.by + kb.bz)) | (uint64_t(kx) << (kb.by + kb.bz)) | (uint64_t(ky) << kb.bz) |
+            uint64_t(kz);
 }
 
 // voxel corner = (float)(k*cell + min) (localization.cpp:318-351), camera-0 voxels first (key order)
-__global__ void k_emit(const uint64_t* keys_unique, int n_cap, double cell, PreState* st, float4* vox) {
+__global__ void k_emit(const uint64_t* keys_unique, int n_cap, double cell, PreState* st, float4* vox, KeyBits kb) {
+  __shared__ int s_red[6][kBlock / 32];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int nu = st->n_unique;
   bool ok = i < nu && i < n_cap;
@@ -180,8 +194,9 @@ __global__ void k_emit(const uint64_t* keys_unique, int n_cap, double cell, PreS
   if (i == nu - 1) st->n_vox = (key == kInvalidKey) ? nu - 1 : nu;
   float x = 0, y = 0, z = 0;
   if (ok) {
-    int c = int(key >> 63);
-    double kx = double((key >> 42) & 0x1FFFFF), ky = double((key >> 21) & 0x1FFFFF), kz = double(key & 0x1FFFFF);
+    int c = int((key >> (kb.bx + kb.by + kb.bz)) & 1u);
+    double kx = double((key >> (kb.by + kb.bz)) & ((1ull << kb.bx) - 1)), ky = double((key >> kb.bz) & ((1ull << kb.by) - 1)),
+           kz = double(key & ((1ull << kb.bz) - 1));
     double mx = double(ordered_to_float(st->cam_min[c][0]));
     double my = double(ordered_to_float(st->cam_min[c][1]));
     double mz = double(ordered_to_float(st->cam_min[c][2]));
@@ -190,16 +205,27 @@ __global__ void k_emit(const uint64_t* keys_unique, int n_cap, double cell, PreS
     z = float(__dadd_rn(__dmul_rn(kz, cell), mz));
     vox[i] = make_float4(x, y, z, __int_as_float(c));
   }
-  // bounding box for the hash grid
-  if (__ballot_sync(0xffffffffu, ok) == 0) return;
+  // bounding box for the hash grid: warp reduce -> shared -> one atomic per block and bound
   int v[3] = {float_to_ordered(x), float_to_ordered(y), float_to_ordered(z)};
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
   for (int a = 0; a < 3; a++) {
-    int lo = __reduce_min_sync(0xffffffffu, ok ? v[a] : 0x7FFFFFFF);
-    int hi = __reduce_max_sync(0xffffffffu, ok ? v[a] : int(0x80000000));
-    if ((threadIdx.x & 31) == 0) {
-      atomicMin(&st->bb_min[a], lo);
-      atomicMax(&st->bb_max[a], hi);
+    const int lo = __reduce_min_sync(0xffffffffu, ok ? v[a] : 0x7FFFFFFF);
+    const int hi = __reduce_max_sync(0xffffffffu, ok ? v[a] : int(0x80000000));
+    if (lane == 0) {
+      s_red[a][w] = lo;
+      s_red[3 + a][w] = hi;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    const int a = threadIdx.x;
+    int r = s_red[a][0];
+    for (int k = 1; k < kBlock / 32; k++) r = a < 3 ? min(r, s_red[a][k]) : max(r, s_red[a][k]);
+    if (a < 3) {
+      if (r != 0x7FFFFFFF) atomicMin(&st->bb_min[a], r);
+    } else {
+      if (r != int(0x80000000)) atomicMax(&st->bb_max[a - 3], r);
     }
   }
 }
@@ -256,7 +282,8 @@ static int finish_cloud(Ctx* c, bool have_bbox_on_device) {
   AG_CUDA_CHECK(cudaMemcpyAsync(&hs, state_ptr(c), sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
   AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   if (hs.key_overflow) {
-    set_error("voxel index exceeds 2^21 cells along one axis (workspace too large for voxel_size)");
+    set_error("voxel index exceeds the key range (workspace extent / voxel_size > 2^21 cells, or a point lies "
+              "outside the workspace box it passed)");
     return AG_ERR_CAPACITY;
   }
   (void)have_bbox_on_device;
@@ -301,6 +328,17 @@ int preprocess_device(Ctx* c, const void* d_points, int stride, int n_in, int si
   int* d_block = c->block_counts.as<int>();
   uint8_t* d_flag = reinterpret_cast<uint8_t*>(d_block + nb);
   const char* pts = static_cast<const char*>(d_points);
+  KeyBits kb;
+  {
+    int* b[3] = {&kb.bx, &kb.by, &kb.bz};
+    for (int a = 0; a < 3; a++) {
+      const double cells = floor((P.workspace[2 * a + 1] - P.workspace[2 * a]) / P.voxel_size) + 2.0;
+      int bits = 1;
+      while (bits < 21 && double(1u << bits) - 1.0 <= cells) bits++;
+      *b[a] = bits;
+    }
+    kb.total = 1 + kb.bx + kb.by + kb.bz;
+  }
   k_init_state<<<1, 32, 0, c->stream>>>(st);
   const bool quirk = !P.fix_cam_source && size_left < n_in;
   if (quirk) {
@@ -310,20 +348,20 @@ int preprocess_device(Ctx* c, const void* d_points, int stride, int n_in, int si
   k_classify<<<nb, kBlock, 0, c->stream>>>(pts, stride, n_in, size_left, quirk ? d_block : nullptr, P.workspace[0],
                                            P.workspace[1], P.workspace[2], P.workspace[3], P.workspace[4],
                                            P.workspace[5], d_flag, st);
-  k_keys<<<nb, kBlock, 0, c->stream>>>(pts, stride, n_in, d_flag, P.voxel_size, st, c->keys.as<uint64_t>());
+  k_keys<<<nb, kBlock, 0, c->stream>>>(pts, stride, n_in, d_flag, P.voxel_size, st, c->keys.as<uint64_t>(), kb);
   size_t tmp1 = 0, tmp2 = 0;
-  cub::DeviceRadixSort::SortKeys(nullptr, tmp1, c->keys.as<uint64_t>(), c->keys_sorted.as<uint64_t>(), n_in, 0, 64,
-                                 c->stream);
+  cub::DeviceRadixSort::SortKeys(nullptr, tmp1, c->keys.as<uint64_t>(), c->keys_sorted.as<uint64_t>(), n_in, 0,
+                                 kb.total, c->stream);
   cub::DeviceSelect::Unique(nullptr, tmp2, c->keys_sorted.as<uint64_t>(), c->keys_unique.as<uint64_t>(),
                             &st->n_unique, n_in, c->stream);
   size_t tmp = tmp1 > tmp2 ? tmp1 : tmp2;
   if (c->cub_tmp.reserve(tmp)) return AG_ERR_CUDA;
   AG_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(c->cub_tmp.p, tmp1, c->keys.as<uint64_t>(),
-                                               c->keys_sorted.as<uint64_t>(), n_in, 0, 64, c->stream));
+                                               c->keys_sorted.as<uint64_t>(), n_in, 0, kb.total, c->stream));
   AG_CUDA_CHECK(cub::DeviceSelect::Unique(c->cub_tmp.p, tmp2, c->keys_sorted.as<uint64_t>(),
                                           c->keys_unique.as<uint64_t>(), &st->n_unique, n_in, c->stream));
   c->launches += quirk ? 6 : 4;  // init, [count, scan], classify, keys, emit (CUB kernels not counted)
-  k_emit<<<nb, kBlock, 0, c->stream>>>(c->keys_unique.as<uint64_t>(), n_in, P.voxel_size, st, c->vox.as<float4>());
+  k_emit<<<nb, kBlock, 0, c->stream>>>(c->keys_unique.as<uint64_t>(), n_in, P.voxel_size, st, c->vox.as<float4>(), kb);
   AG_CUDA_CHECK(cudaGetLastError());
   return finish_cloud(c, true);
 }

@@ -24,7 +24,7 @@ namespace ag {
 
 namespace {
 
-constexpr int kWarps = 8;  // warps per CTA
+constexpr int kWarps = 4;  // warps per CTA
 
 // ---- monomial bookkeeping ---------------------------------------------------------------------
 // index of the moment sum x^a y^b z^c, a+b+c <= 4
@@ -36,6 +36,17 @@ __host__ __device__ constexpr int midx(int a, int b, int c) {
        : k == 4 ? 22 : k == 80 ? 23 : k == 76 ? 24 : k == 40 ? 25 : k == 16 ? 26 : k == 28 ? 27 : k == 8 ? 28
        : k == 60 ? 29 : k == 12 ? 30 : k == 52 ? 31 : k == 56 ? 32 : k == 36 ? 33 : k == 32 ? 34 : -1;
 }
+// device-side lookup of the same map (index a*25 + b*5 + c), filled from midx() at compile time
+struct MidxTable {
+  signed char v[125];
+  constexpr MidxTable() : v() {
+    for (int a = 0; a < 5; a++)
+      for (int b = 0; b < 5; b++)
+        for (int c = 0; c < 5; c++) v[a * 25 + b * 5 + c] = (a + b + c <= 4) ? static_cast<signed char>(midx(a, b, c)) : -1;
+  }
+};
+__constant__ MidxTable c_midx = MidxTable();
+__device__ __forceinline__ int midx_d(int a, int b, int c) { return c_midx.v[a * 25 + b * 5 + c]; }
 constexpr int kNumMoments = 35;
 constexpr int kMomentStride = 36;  // + count of camera-1 neighbours
 
@@ -102,7 +113,7 @@ __device__ __forceinline__ void walk_ball(const GPoint* __restrict__ pts, const 
 }
 
 // ---- kernel 1: moments ------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, 4)
 k_taubin_moments(const GPoint* __restrict__ pts, const int* __restrict__ cell_start, GridDesc g,
                  const float4* __restrict__ vox, const int* __restrict__ indices, int n_samples, float r2,
                  double rpad, double inv_r, double* __restrict__ moments, int* __restrict__ nn_counts,
@@ -158,58 +169,100 @@ struct AxesSmem {
   GPoint ring[64];
 };
 
+// Jacobi rotation (c, s) annihilating a_pq, the small-angle root (|angle| <= pi/4), computed without
+// divisions: with h = (a_qq - a_pp)/2, b = a_pq, r = hypot(h, b):  cos 2phi = |h|/r, sin 2phi = b/r,
+// c = sqrt((1 + cos 2phi)/2), s = sign(h) * sin 2phi / (2c)   — two rsqrt, no div/sqrt sequences.
 __device__ __forceinline__ void jacobi_rotate_params(double app, double aqq, double apq, double& c, double& s) {
-  // classic stable formulas (Golub & Van Loan 8.4)
   if (apq == 0.0) {
     c = 1.0;
     s = 0.0;
     return;
   }
-  const double theta = (aqq - app) / (2.0 * apq);
-  const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-  c = 1.0 / sqrt(t * t + 1.0);
-  s = t * c;
+  const double h = 0.5 * (aqq - app);
+  const double rr = h * h + apq * apq;
+  if (!(rr > 1e-300) || !(rr < 1e300)) {  // squares under/overflow: entries this small/large are not rotated
+    c = 1.0;
+    s = 0.0;
+    return;
+  }
+  const double inv_r = rsqrt(rr);
+  const double c2 = fabs(h) * inv_r;        // cos 2phi in [0, 1]
+  const double s2 = apq * inv_r;            // sin 2phi (sign of a_pq)
+  const double y = 0.5 * (1.0 + c2);        // cos^2 phi in [1/2, 1]
+  const double ry = rsqrt(y);
+  c = y * ry;
+  s = (h >= 0.0 ? 0.5 : -0.5) * s2 * ry;
 }
 
-// cyclic Jacobi on the n x n symmetric matrix A (row-major, stride n) with eigenvectors in V;
-// executed by one warp: every lane computes the rotation, lanes 0..n-1 apply it.
-template <int N>
-__device__ void warp_jacobi(double* A, double* V, int lane) {
+// Parallel-ordered cyclic Jacobi on the 9x9 symmetric matrix A (row-major) with eigenvectors in V,
+// executed by one warp.  Round-robin ("circle") ordering over 10 players — index 9 is a bye — gives 9
+// rounds of 4 DISJOINT rotations per sweep; disjoint rotations commute, so each round applies
+// J = J_0 J_1 J_2 J_3 as A <- A J (36 column work items) then A <- J^T A (36 row work items).
+// Rotations are skipped when |a_pq| <= eps*sqrt(a_pp*a_qq) — the scaled criterion that gives
+// positive-definite matrices high RELATIVE accuracy in their small eigenpairs (the one we need is the
+// smallest); a sweep without rotations ends the iteration.
+__device__ void warp_jacobi9(double* A, double* V, int lane) {
+  constexpr int N = 9;
   for (int i = lane; i < N * N; i += 32) V[i] = (i / N == i % N) ? 1.0 : 0.0;
   __syncwarp();
-  // Rotations are skipped when |a_pq| <= eps*sqrt(a_pp*a_qq) (the scaled criterion that gives
-  // positive-definite matrices high RELATIVE accuracy in their small eigenvalues / eigenvectors —
-  // the pair we need is the smallest one); a sweep without rotations ends the iteration.
+  const int t_item0 = lane / N, k_item0 = lane % N;            // work item `lane`      (t in 0..3)
+  const int t_item1 = (lane + 32) / N, k_item1 = (lane + 32) % N;  // work item `lane+32` (lanes 0..3 only)
   for (int sweep = 0; sweep < 30; sweep++) {
     bool rotated = false;
-    for (int p = 0; p < N - 1; p++)
-      for (int q = p + 1; q < N; q++) {
+    for (int r = 0; r < N; r++) {
+      // lanes 0..3 own pair t = lane of this round
+      int p = (r + (lane & 3) + 1) % N, q = (r - (lane & 3) - 1 + 2 * N) % N;
+      if (p > q) { const int tmp = p; p = q; q = tmp; }
+      double c = 1.0, s = 0.0;
+      bool rot = false;
+      if (lane < 4) {
         const double app = A[p * N + p], aqq = A[q * N + q], apq = A[p * N + q];
-        if (!(fabs(apq) > 1.0e-16 * sqrt(fabs(app * aqq)))) continue;  // uniform across the warp
-        rotated = true;
-        double c, s;
-        jacobi_rotate_params(app, aqq, apq, c, s);
-        __syncwarp();
-        if (lane < N) {  // columns p,q of A and V
-          const int k = lane;
-          const double akp = A[k * N + p], akq = A[k * N + q];
-          A[k * N + p] = c * akp - s * akq;
-          A[k * N + q] = s * akp + c * akq;
-          const double vkp = V[k * N + p], vkq = V[k * N + q];
-          V[k * N + p] = c * vkp - s * vkq;
-          V[k * N + q] = s * vkp + c * vkq;
-        }
-        __syncwarp();
-        if (lane < N) {  // rows p,q of A
-          const int k = lane;
-          const double apk = A[p * N + k], aqk = A[q * N + k];
-          A[p * N + k] = c * apk - s * aqk;
-          A[q * N + k] = s * apk + c * aqk;
-        }
-        __syncwarp();
-        if (lane == 0) A[p * N + q] = A[q * N + p] = 0.0;  // annihilated exactly by construction
-        __syncwarp();
+        rot = apq * apq > 1.0e-32 * fabs(app * aqq);
+        if (rot) jacobi_rotate_params(app, aqq, apq, c, s);
       }
+      const unsigned any = __ballot_sync(0xffffffffu, rot);
+      if (any == 0) continue;  // uniform
+      rotated = true;
+      // broadcast the four rotations
+      const int p0 = __shfl_sync(0xffffffffu, p, t_item0), q0 = __shfl_sync(0xffffffffu, q, t_item0);
+      const double c0 = __shfl_sync(0xffffffffu, c, t_item0), s0 = __shfl_sync(0xffffffffu, s, t_item0);
+      const int p1 = __shfl_sync(0xffffffffu, p, t_item1 & 3), q1 = __shfl_sync(0xffffffffu, q, t_item1 & 3);
+      const double c1 = __shfl_sync(0xffffffffu, c, t_item1 & 3), s1 = __shfl_sync(0xffffffffu, s, t_item1 & 3);
+      // columns: A <- A J, V <- V J
+      {
+        const int k = k_item0;
+        const double akp = A[k * N + p0], akq = A[k * N + q0], vkp = V[k * N + p0], vkq = V[k * N + q0];
+        A[k * N + p0] = c0 * akp - s0 * akq;
+        A[k * N + q0] = s0 * akp + c0 * akq;
+        V[k * N + p0] = c0 * vkp - s0 * vkq;
+        V[k * N + q0] = s0 * vkp + c0 * vkq;
+      }
+      if (lane < 4) {
+        const int k = k_item1;
+        const double akp = A[k * N + p1], akq = A[k * N + q1], vkp = V[k * N + p1], vkq = V[k * N + q1];
+        A[k * N + p1] = c1 * akp - s1 * akq;
+        A[k * N + q1] = s1 * akp + c1 * akq;
+        V[k * N + p1] = c1 * vkp - s1 * vkq;
+        V[k * N + q1] = s1 * vkp + c1 * vkq;
+      }
+      __syncwarp();
+      // rows: A <- J^T A
+      {
+        const int k = k_item0;
+        const double apk = A[p0 * N + k], aqk = A[q0 * N + k];
+        A[p0 * N + k] = c0 * apk - s0 * aqk;
+        A[q0 * N + k] = s0 * apk + c0 * aqk;
+      }
+      if (lane < 4) {
+        const int k = k_item1;
+        const double apk = A[p1 * N + k], aqk = A[q1 * N + k];
+        A[p1 * N + k] = c1 * apk - s1 * aqk;
+        A[q1 * N + k] = s1 * apk + c1 * aqk;
+      }
+      __syncwarp();
+      if (lane < 4 && rot) A[p * N + q] = A[q * N + p] = 0.0;  // annihilated by construction
+      __syncwarp();
+    }
     if (!rotated) break;
   }
 }
@@ -293,7 +346,7 @@ __constant__ double c_multinomial6[28] = {
     1, 6, 15, 20, 15, 6, 1};    // a=0
 
 // ---- kernel 2: eigen-solve + local axes -------------------------------------------------------
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, 4)
 k_taubin_axes(const GPoint* __restrict__ pts_c, const int* __restrict__ cell_start, GridDesc g,
               const float4* __restrict__ vox, const int* __restrict__ indices,
               int n_samples, float r2, double rpad, double inv_r, const double* __restrict__ moments,
@@ -320,8 +373,8 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const int* __restrict__ cell_sta
     const int i = e / 9, j = e % 9;
     const int* bi = c_basis[i];
     const int* bj = c_basis[j];
-    const double mij = mom[midx(bi[0] + bj[0], bi[1] + bj[1], bi[2] + bj[2])];
-    const double mi = mom[midx(bi[0], bi[1], bi[2])], mj = mom[midx(bj[0], bj[1], bj[2])];
+    const double mij = mom[midx_d(bi[0] + bj[0], bi[1] + bj[1], bi[2] + bj[2])];
+    const double mi = mom[midx_d(bi[0], bi[1], bi[2])], mj = mom[midx_d(bj[0], bj[1], bj[2])];
     sm.A[e] = mij - mi * mj / n;
     double bsum = 0.0;
 #pragma unroll
@@ -329,24 +382,31 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const int* __restrict__ cell_sta
       if (bi[a] >= 1 && bj[a] >= 1) {
         int ex[3] = {bi[0] + bj[0], bi[1] + bj[1], bi[2] + bj[2]};
         ex[a] -= 2;
-        bsum += double(bi[a] * bj[a]) * mom[midx(ex[0], ex[1], ex[2])];
+        bsum += double(bi[a] * bj[a]) * mom[midx_d(ex[0], ex[1], ex[2])];
       }
     }
     sm.L[e] = bsum;
   }
-  if (lane < 9) sm.m[lane] = mom[midx(c_basis[lane][0], c_basis[lane][1], c_basis[lane][2])];
+  if (lane < 9) sm.m[lane] = mom[midx_d(c_basis[lane][0], c_basis[lane][1], c_basis[lane][2])];
   __syncwarp();
 
-  // --- Cholesky B = L L^T (lane-parallel over rows below the pivot); tiny ridge only if needed
+  // --- Cholesky B = L L^T (lane-parallel over rows below the pivot).  B is singular when the
+  // neighbourhood is degenerate for the gradient form (e.g. voxel corners lying exactly in one lattice
+  // plane); those directions have lambda = infinity (or 0/0) and must be excluded, which the robust
+  // branch below does by working in range(B).
   bool ok = n >= 1.0;
+  bool singular = false;
+  double dmax = 0.0;
+  for (int i = 0; i < 9; i++) dmax = fmax(dmax, sm.L[i * 9 + i]);
+  if (!(dmax > 0.0)) ok = false;
   {
-    double dmax = 0.0;
-    for (int i = 0; i < 9; i++) dmax = fmax(dmax, sm.L[i * 9 + i]);
-    if (!(dmax > 0.0)) ok = false;
-    const double tol = 1e-13 * dmax;
+    const double tol = 1e-10 * dmax;
     for (int k = 0; k < 9 && ok; k++) {
-      double piv = sm.L[k * 9 + k];
-      if (!(piv > tol)) piv = tol > 0 ? tol : 1e-300;  // singular direction (e.g. exactly planar data)
+      const double piv = sm.L[k * 9 + k];
+      if (!(piv > tol)) {  // uniform across the warp (shared memory value)
+        singular = true;
+        break;
+      }
       const double d = sqrt(piv);
       __syncwarp();
       if (lane == 0) sm.L[k * 9 + k] = d;
@@ -360,53 +420,127 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const int* __restrict__ cell_sta
       __syncwarp();
     }
   }
-  // --- C = L^-1 A L^-T : X = L^-1 A (columns in parallel), then C^T = L^-1 X^T
-  if (lane < 9) {
-    const int col = lane;
-    for (int i = 0; i < 9; i++) {
-      double v = sm.A[i * 9 + col];
-      for (int k = 0; k < i; k++) v -= sm.L[i * 9 + k] * sm.A[k * 9 + col];
-      sm.A[i * 9 + col] = v / sm.L[i * 9 + i];
+  if (!singular) {
+    // --- C = L^-1 A L^-T : X = L^-1 A (columns in parallel), then C^T = L^-1 X^T
+    if (lane < 9) {
+      const int col = lane;
+      for (int i = 0; i < 9; i++) {
+        double v = sm.A[i * 9 + col];
+        for (int k = 0; k < i; k++) v -= sm.L[i * 9 + k] * sm.A[k * 9 + col];
+        sm.A[i * 9 + col] = v / sm.L[i * 9 + i];
+      }
+    }
+    __syncwarp();
+    if (lane < 9) {
+      const int row = lane;  // solve L y = (row of X)^T
+      for (int i = 0; i < 9; i++) {
+        double v = sm.A[row * 9 + i];
+        for (int k = 0; k < i; k++) v -= sm.L[i * 9 + k] * sm.A[row * 9 + k];
+        sm.A[row * 9 + i] = v / sm.L[i * 9 + i];
+      }
+    }
+    __syncwarp();
+    // symmetrise (round-off) and diagonalise
+    for (int e = lane; e < 81; e += 32) {
+      const int i = e / 9, j = e % 9;
+      if (i < j) {
+        const double v = 0.5 * (sm.A[i * 9 + j] + sm.A[j * 9 + i]);
+        sm.A[i * 9 + j] = v;
+        sm.A[j * 9 + i] = v;
+      }
+    }
+    __syncwarp();
+    warp_jacobi9(sm.A, sm.V, lane);
+    // smallest eigenvalue (quadric.cpp:149-152), u = L^-T y, j = -m.u/n
+    int mi = 0;
+    for (int k = 1; k < 9; k++)
+      if (sm.A[k * 9 + k] < sm.A[mi * 9 + mi]) mi = k;
+    __syncwarp();
+    if (lane == 0) {
+      double u[9];
+      for (int i = 8; i >= 0; i--) {
+        double v = sm.V[i * 9 + mi];
+        for (int k = i + 1; k < 9; k++) v -= sm.L[k * 9 + i] * u[k];
+        u[i] = v / sm.L[i * 9 + i];
+      }
+      for (int i = 0; i < 9; i++) sm.par[i] = u[i];
+    }
+  } else {
+    // --- robust branch: B = Q D Q^T, W = Q_k D_k^(-1/2) over the directions with D_i > 1e-11 D_max,
+    //     C = W^T A W on range(B), smallest eigenpair y, u = W y
+    for (int e = lane; e < 81; e += 32) {  // rebuild B (the partial Cholesky overwrote it)
+      const int i = e / 9, j = e % 9;
+      const int* bi = c_basis[i];
+      const int* bj = c_basis[j];
+      double bsum = 0.0;
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        if (bi[a] >= 1 && bj[a] >= 1) {
+          int ex[3] = {bi[0] + bj[0], bi[1] + bj[1], bi[2] + bj[2]};
+          ex[a] -= 2;
+          bsum += double(bi[a] * bj[a]) * mom[midx_d(ex[0], ex[1], ex[2])];
+        }
+      }
+      sm.L[e] = bsum;
+    }
+    __syncwarp();
+    warp_jacobi9(sm.L, sm.V, lane);  // eigenvalues on diag(sm.L), eigenvectors in the columns of sm.V
+    double d_max = 0.0;
+    for (int i = 0; i < 9; i++) d_max = fmax(d_max, sm.L[i * 9 + i]);
+    __syncwarp();
+    if (lane < 9) {  // scale column `lane` of Q
+      const double d = sm.L[lane * 9 + lane];
+      const double sc = d > 1e-11 * d_max ? 1.0 / sqrt(d) : 0.0;
+      for (int i = 0; i < 9; i++) sm.V[i * 9 + lane] *= sc;
+    }
+    __syncwarp();
+    for (int e = lane; e < 81; e += 32) {  // T = A W  -> sm.L
+      const int i = e / 9, j = e % 9;
+      double v = 0.0;
+      for (int k = 0; k < 9; k++) v += sm.A[i * 9 + k] * sm.V[k * 9 + j];
+      sm.L[e] = v;
+    }
+    __syncwarp();
+    double cnew[3];
+    for (int e = lane, t = 0; e < 81; e += 32, t++) {  // C = W^T T
+      const int i = e / 9, j = e % 9;
+      double v = 0.0;
+      for (int k = 0; k < 9; k++) v += sm.V[k * 9 + i] * sm.L[k * 9 + j];
+      cnew[t] = v;
+    }
+    __syncwarp();
+    for (int e = lane, t = 0; e < 81; e += 32, t++) sm.A[e] = cnew[t];
+    __syncwarp();
+    for (int e = lane; e < 81; e += 32) {  // symmetrise; excluded directions get a huge diagonal
+      const int i = e / 9, j = e % 9;
+      if (i < j) {
+        const double v = 0.5 * (sm.A[i * 9 + j] + sm.A[j * 9 + i]);
+        sm.A[i * 9 + j] = v;
+        sm.A[j * 9 + i] = v;
+      }
+    }
+    __syncwarp();
+    if (lane < 9) {
+      bool zero_col = true;
+      for (int i = 0; i < 9; i++) zero_col = zero_col && sm.V[i * 9 + lane] == 0.0;
+      if (zero_col) sm.A[lane * 9 + lane] = 1e300;
+    }
+    __syncwarp();
+    warp_jacobi9(sm.A, sm.L, lane);  // eigenvectors Y in sm.L
+    int mi = 0;
+    for (int k = 1; k < 9; k++)
+      if (sm.A[k * 9 + k] < sm.A[mi * 9 + mi]) mi = k;
+    __syncwarp();
+    if (lane < 9) {
+      double v = 0.0;
+      for (int k = 0; k < 9; k++) v += sm.V[lane * 9 + k] * sm.L[k * 9 + mi];
+      sm.par[lane] = v;
     }
   }
-  __syncwarp();
-  if (lane < 9) {
-    const int row = lane;  // solve L y = (row of X)^T
-    for (int i = 0; i < 9; i++) {
-      double v = sm.A[row * 9 + i];
-      for (int k = 0; k < i; k++) v -= sm.L[i * 9 + k] * sm.A[row * 9 + k];
-      sm.A[row * 9 + i] = v / sm.L[i * 9 + i];
-    }
-  }
-  __syncwarp();
-  // symmetrise (round-off) and diagonalise
-  for (int e = lane; e < 81; e += 32) {
-    const int i = e / 9, j = e % 9;
-    if (i < j) {
-      const double v = 0.5 * (sm.A[i * 9 + j] + sm.A[j * 9 + i]);
-      sm.A[i * 9 + j] = v;
-      sm.A[j * 9 + i] = v;
-    }
-  }
-  __syncwarp();
-  warp_jacobi<9>(sm.A, sm.V, lane);
-  // smallest eigenvalue (quadric.cpp:149-152), u = L^-T y, j = -m.u/n
-  int mi = 0;
-  for (int k = 1; k < 9; k++)
-    if (sm.A[k * 9 + k] < sm.A[mi * 9 + mi]) mi = k;
   __syncwarp();
   if (lane == 0) {
-    double u[9];
-    for (int i = 8; i >= 0; i--) {
-      double v = sm.V[i * 9 + mi];
-      for (int k = i + 1; k < 9; k++) v -= sm.L[k * 9 + i] * u[k];
-      u[i] = v / sm.L[i * 9 + i];
-    }
     double mu = 0.0;
-    for (int i = 0; i < 9; i++) {
-      sm.par[i] = u[i];
-      mu += sm.m[i] * u[i];
-    }
+    for (int i = 0; i < 9; i++) mu += sm.m[i] * sm.par[i];
     sm.par[9] = -mu / n;
   }
   __syncwarp();
@@ -548,6 +682,7 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, double radius, ag_f
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_taubin_axes, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cudaFuncSetAttribute(k_taubin_axes, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
     attr_set = true;
   }
   const HandConst& h = c->hand;

@@ -15,6 +15,8 @@
 // binary64 values, evaluated without FMA contraction (this file is compiled with -fmad=false and
 // the products/sums are written in the reference's left-to-right order).
 
+#include <cstdlib>
+
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
@@ -24,8 +26,9 @@ namespace ag {
 
 namespace {
 
-constexpr int kThreads = 256;     // 8 warps = 8 orientations (rotating_hand.cpp:13)
-constexpr int kSlabCap = 6144;    // slab points kept in shared memory (96 KB)
+constexpr int kThreads = 256;       // 8 warps = 8 orientations (rotating_hand.cpp:13)
+constexpr int kSlabCapSmall = 2048; // slab points kept in shared memory by the common kernel (32 KB)
+constexpr int kSlabCapBig = 12032;  // fallback instantiation for dense neighbourhoods (188 KB, 1 CTA/SM)
 
 struct SlabPoint {  // centred neighbour, binary32 exactly as hand_search.cpp:157-158 produces it
   float x, y, z;
@@ -45,7 +48,8 @@ struct SweepArgs {
   int* debug;             // [n_samples * 8] or null
   int* slab_counts;       // [n_samples] or null
   unsigned long long* counters;
-  int* overflow;          // set to 1 if a slab exceeded kSlabCap
+  int* overflow;          // [0] = number of samples whose slab exceeded the capacity, [1..] their slots
+  const int* sample_list; // if non-null: blockIdx.x indexes this list of sample slots (fallback pass)
   int n_samples;
   float r2;
   double rpad;
@@ -57,15 +61,33 @@ __device__ __forceinline__ double dot3e(const double a[3], const double b[3]) {
   return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]);  // Eigen's unrolled 3-vector reduction order
 }
 
-__global__ void __launch_bounds__(kThreads)
+// Exact rank of x in an ascending, (nearly) uniformly spaced threshold table, branch-free.
+// tab is stored with sentinels: tab[0] = -inf, tab[1..n] = thresholds, tab[n+1] = +inf.  The estimate
+// c0 = clamp(floor((x-base)/step) + 1, 0, n) can be off by one only when x is within rounding distance
+// of a threshold, so the true count is (c0-1) + [tab[c0] <cmp> x] + [tab[c0+1] <cmp> x]: two exact
+// binary64 comparisons — the very comparisons the reference evaluates slot by slot.
+__device__ __forceinline__ int rank_est(double x, double base, double inv_step, int n) {
+  return min(max(__double2int_rd((x - base) * inv_step) + 1, 0), n);
+}
+struct SlotTables {    // shared-memory threshold tables with -inf / +inf sentinels (lane-varying indices)
+  double sp[2][12];    // slot lower edges per hand (ascending)
+  double spw[2][12];   // slot upper edges sp[i] + finger_width
+  double bite[14];     // deepening levels d_t (ascending), n_depths <= 12
+};
+
+template <int CAP>
+__global__ void __launch_bounds__(kThreads, CAP <= 2048 ? 3 : 1)
 k_hand_sweep(const SweepArgs A, const GridDesc g, const __grid_constant__ HandConst hc) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   SlabPoint* slab = reinterpret_cast<SlabPoint*>(s_raw);
   __shared__ uint32_t s_img[8][AG_IMAGE_WORDS];
   __shared__ int s_count;
   __shared__ unsigned long long s_cand;
+  __shared__ SlotTables s_tab;
+  __shared__ int s_rs[kThreads], s_pre[kThreads + 1], s_next;
+  __shared__ unsigned long long s_lvl[8][12][32];  // per warp, depth level and lane: (side<<32 | in) slot masks
 
-  const int s = blockIdx.x;
+  const int s = A.sample_list ? A.sample_list[blockIdx.x] : blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
   const int idx = A.indices[s];
@@ -76,6 +98,18 @@ k_hand_sweep(const SweepArgs A, const GridDesc g, const __grid_constant__ HandCo
     s_cand = 0;
   }
   for (int i = lane; i < AG_IMAGE_WORDS; i += 32) s_img[warp][i] = 0u;
+  if (threadIdx.x < 24) {
+    const int hnd = threadIdx.x / 12, j = threadIdx.x % 12;
+    const double inf = __longlong_as_double(0x7FF0000000000000ll);
+    const double lo = j == 0 ? -inf : (j == 11 ? inf : hc.spacing[hnd * 10 + j - 1]);
+    s_tab.sp[hnd][j] = lo;
+    s_tab.spw[hnd][j] = (j == 0 || j == 11) ? lo : lo + hc.finger_width;  // finger_hand.cpp:56-57
+  }
+  if (threadIdx.x < 14) {
+    const double inf = __longlong_as_double(0x7FF0000000000000ll);
+    const int j = threadIdx.x;
+    s_tab.bite[j] = j == 0 ? -inf : (j <= hc.n_depths ? hc.bite[j - 1] : inf);
+  }
 
   // ---- frame = [normal | normal x axis | axis]   (rotating_hand.cpp:25)
   const ag_frame fr = A.frames[s];
@@ -94,49 +128,96 @@ k_hand_sweep(const SweepArgs A, const GridDesc g, const __grid_constant__ HandCo
   __syncthreads();
 
   // ---- phase A: gather the r = 0.08 ball, keep the |z_hand| < hand_height slab -----------------
+  // The <=7x7 cell columns are z-contiguous runs of very different lengths; their candidates are
+  // flattened into one index space (per-column prefix in shared memory) and handed out to the warps in
+  // 64-candidate blocks through a shared counter, two independent 16-byte loads in flight per lane.
   {
     const QueryBox b = query_box(g, q.x, q.y, q.z, A.rpad);
     const int ncy = b.hi[1] - b.lo[1] + 1;
     const int ncol = (b.hi[0] - b.lo[0] + 1) * ncy;
-    unsigned long long cand = 0, nball = 0;
-    for (int col = warp; col < ncol; col += 8) {
-      const int cx = b.lo[0] + col / ncy, cy = b.lo[1] + col % ncy;
-      const int rs = __ldg(A.cell_start + cell_linear(g, cx, cy, b.lo[2]));
-      const int re = __ldg(A.cell_start + cell_linear(g, cx, cy, b.hi[2]) + 1);
-      cand += (unsigned long long)(re - rs);
-      for (int j0 = rs; j0 < re; j0 += 32) {
-        const int j = j0 + lane;
-        bool keep = false;
-        SlabPoint sp;
-        sp.x = sp.y = sp.z = 0.f;
-        sp.tag = 0;
-        bool inball = false;
-        if (j < re) {
-          const GPoint p = A.pts[j];
-          if (dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z) < A.r2) {
+    unsigned long long nball = 0;
+    for (int cbase = 0; cbase < ncol; cbase += kThreads) {  // one batch unless the grid is unusually fine
+      const int nc = min(kThreads, ncol - cbase);
+      if (threadIdx.x < nc) {
+        const int col = cbase + threadIdx.x;
+        const int cx = b.lo[0] + col / ncy, cy = b.lo[1] + col % ncy;
+        const int rs = __ldg(A.cell_start + cell_linear(g, cx, cy, b.lo[2]));
+        const int re = __ldg(A.cell_start + cell_linear(g, cx, cy, b.hi[2]) + 1);
+        s_rs[threadIdx.x] = rs;
+        s_pre[threadIdx.x + 1] = re - rs;
+      }
+      if (threadIdx.x == 0) {
+        s_pre[0] = 0;
+        s_next = 0;
+      }
+      __syncthreads();
+      if (warp == 0) {  // inclusive scan of the <=256 run lengths
+        int carry = 0;
+        for (int base = 0; base < nc; base += 32) {
+          const int i = base + lane;
+          int v = i < nc ? s_pre[i + 1] : 0;
+#pragma unroll
+          for (int o2 = 1; o2 < 32; o2 <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, o2);
+            if (lane >= o2) v += t;
+          }
+          if (i < nc) s_pre[i + 1] = v + carry;
+          carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+      }
+      __syncthreads();
+      const int total = s_pre[nc];
+      if (threadIdx.x == 0) s_cand += (unsigned long long)total;
+      int c = 0;  // column cursor of this lane (blocks come in increasing order per warp)
+      for (;;) {
+        int blk = 0;
+        if (lane == 0) blk = atomicAdd(&s_next, 1);
+        blk = __shfl_sync(0xffffffffu, blk, 0);
+        const int base = blk * 64;
+        if (base >= total) break;
+        GPoint p[2];
+        bool valid[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const int pos = base + u * 32 + lane;
+          valid[u] = pos < total;
+          p[u].x = p[u].y = p[u].z = 0.f;
+          p[u].tag = 0;
+          if (valid[u]) {
+            while (pos >= s_pre[c + 1]) c++;
+            p[u] = A.pts[s_rs[c] + (pos - s_pre[c])];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          bool keep = false, inball = false;
+          SlabPoint sp;
+          sp.x = sp.y = sp.z = 0.f;
+          sp.tag = 0;
+          if (valid[u] && dist2_flann(q.x, q.y, q.z, p[u].x, p[u].y, p[u].z) < A.r2) {
             inball = true;
             // hand_search.cpp:157-158: subtraction in binary32, then cast
-            sp.x = __fsub_rn(p.x, q.x);
-            sp.y = __fsub_rn(p.y, q.y);
-            sp.z = __fsub_rn(p.z, q.z);
-            sp.tag = p.tag;
+            sp.x = __fsub_rn(p[u].x, q.x);
+            sp.y = __fsub_rn(p[u].y, q.y);
+            sp.z = __fsub_rn(p[u].z, q.z);
+            sp.tag = p[u].tag;
             const double hz = (F[0][2] * double(sp.x) + F[1][2] * double(sp.y)) + F[2][2] * double(sp.z);
             keep = hz > -1.0 * hc.hand_height && hz < hc.hand_height;  // rotating_hand.cpp:44
           }
-        }
-        const unsigned mb = __ballot_sync(0xffffffffu, inball);
-        nball += __popc(mb);
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (m) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(&s_count, __popc(m));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          const int pos = base + __popc(m & lt);
-          if (keep && pos < kSlabCap) slab[pos] = sp;
+          nball += __popc(__ballot_sync(0xffffffffu, inball));
+          const unsigned m = __ballot_sync(0xffffffffu, keep);
+          if (m) {
+            int wbase = 0;
+            if (lane == 0) wbase = atomicAdd(&s_count, __popc(m));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            const int pos = wbase + __popc(m & lt);
+            if (keep && pos < CAP) slab[pos] = sp;
+          }
         }
       }
+      __syncthreads();
     }
-    if (lane == 0) atomicAdd(&s_cand, cand | (nball << 32));
+    if (lane == 0) atomicAdd(&s_cand, nball << 32);
   }
   __syncthreads();
   const int k = s_count;
@@ -144,11 +225,14 @@ k_hand_sweep(const SweepArgs A, const GridDesc g, const __grid_constant__ HandCo
     if (A.slab_counts) A.slab_counts[s] = k;
     atomicAdd(&A.counters[2], s_cand >> 32);
     atomicAdd(&A.counters[3], s_cand & 0xFFFFFFFFull);
-    if (k > kSlabCap) atomicExch(A.overflow, 1);
+    if (k > CAP) {  // does not fit: queue the sample for the large-capacity instantiation
+      const int w = atomicAdd(A.overflow, 1);
+      A.overflow[1 + w] = s;
+    }
   }
   const int o = warp;
   const size_t slot = size_t(s) * 8 + o;
-  if (k > kSlabCap) {
+  if (k > CAP) {
     if (lane == 0) A.valid[slot] = 0;
     return;
   }
@@ -182,7 +266,8 @@ k_hand_sweep(const SweepArgs A, const GridDesc g, const __grid_constant__ HandCo
     // pass 1: slot masks per depth level
     unsigned IN[12], SD[12];
 #pragma unroll
-    for (int t = 0; t < 12; t++) IN[t] = SD[t] = 0u;
+    for (int t = 0; t < 12; t++) s_lvl[warp][t][lane] = 0ull;
+#pragma unroll 2
     for (int j = lane; j < k; j += 32) {
       const SlabPoint p = slab[j];
       const double px = double(p.x), py = double(p.y), pz = double(p.z);
@@ -193,20 +278,57 @@ k_hand_sweep(const SweepArgs A, const GridDesc g, const __grid_constant__ HandCo
       minY = fmin(minY, ry);
       maxY = fmax(maxY, ry);
       if (!(ry < hc.bite[hc.n_depths - 1])) continue;  // above the deepest bite: never cropped in
-      unsigned in_mask = 0u, sd_mask = 0u;
+      unsigned in_mask, sd_mask;
+      if (hc.uniform_slots) {
+        // slot i is entered iff sp[i] < rx < spw[i]; both tables ascend within a hand, so the sets
+        // {i: rx > sp[i]}, {i: rx >= spw[i]}, {i: rx > spw[i]} are prefixes given by three exact ranks
+        unsigned gt[2], ge[2], gw[2];
+        int a_rank[2];
 #pragma unroll
-      for (int i = 0; i < 20; i++) {
-        const double lo = hc.spacing[i], hi = hc.spacing[i] + hc.finger_width;  // finger_hand.cpp:56-57
-        if (rx > lo && rx < hi) in_mask |= 1u << i;
-        const bool side = (i <= 10) ? (rx > hi) : (rx < lo);  // finger_hand.cpp:72-82
-        if (side) sd_mask |= 1u << i;
+        for (int hnd = 0; hnd < 2; hnd++) {
+          const double* sp = s_tab.sp[hnd];
+          const double* sw = s_tab.spw[hnd];
+          const int e0 = rank_est(rx, hc.spacing[hnd * 10], hc.inv_slot_step, 10);
+          const int e1 = rank_est(rx, hc.spacing[hnd * 10] + hc.finger_width, hc.inv_slot_step, 10);
+          const double s0 = sp[e0], s1 = sp[e0 + 1], w0 = sw[e1], w1 = sw[e1 + 1];
+          const int a = e0 - 1 + (s0 < rx ? 1 : 0) + (s1 < rx ? 1 : 0);    // #{sp  <  rx}
+          const int bq = e1 - 1 + (w0 <= rx ? 1 : 0) + (w1 <= rx ? 1 : 0); // #{spw <= rx}
+          const int cq = e1 - 1 + (w0 < rx ? 1 : 0) + (w1 < rx ? 1 : 0);   // #{spw <  rx}
+          a_rank[hnd] = a;
+          gt[hnd] = (1u << a) - 1u;
+          ge[hnd] = (1u << bq) - 1u;
+          gw[hnd] = (1u << cq) - 1u;
+        }
+        in_mask = (gt[0] & ~ge[0]) | ((gt[1] & ~ge[1]) << 10);
+        // finger_hand.cpp:72-82: slots 0..10 need a point beyond their upper edge, 11..19 one below their lower edge
+        sd_mask = gw[0] | ((gw[1] & 1u) << 10) | (((~gt[1]) & 0x3FEu) << 10);
+        // rx < sp[i] is NOT(rx > sp[i]) AND NOT(rx == sp[i]); correct the equality case exactly
+        const int aR = a_rank[1];
+        if (aR >= 1 && aR < 10 && rx == s_tab.sp[1][aR + 1]) sd_mask &= ~(1u << (10 + aR));
+      } else {
+        in_mask = 0u;
+        sd_mask = 0u;
+#pragma unroll
+        for (int i = 0; i < 20; i++) {
+          const double lo = hc.spacing[i], hi = hc.spacing[i] + hc.finger_width;  // finger_hand.cpp:56-57
+          if (rx > lo && rx < hi) in_mask |= 1u << i;
+          const bool side = (i <= 10) ? (rx > hi) : (rx < lo);  // finger_hand.cpp:72-82
+          if (side) sd_mask |= 1u << i;
+        }
       }
+      // the point is cropped in at every depth level d_t > ry, i.e. at levels t >= L = #{t : d_t <= ry}
+      // (L < n_depths here); record it at level L only, the prefix-OR below spreads it upwards
+      const int e = rank_est(ry, hc.bite[0], 200.0, hc.n_depths);
+      const int L = e - 1 + (s_tab.bite[e] <= ry ? 1 : 0) + (s_tab.bite[e + 1] <= ry ? 1 : 0);
+      s_lvl[warp][L][lane] |= (static_cast<unsigned long long>(sd_mask) << 32) | in_mask;
+    }
+    {
+      unsigned long long acc = 0ull;
 #pragma unroll
       for (int t = 0; t < 12; t++) {
-        if (t < hc.n_depths && ry < hc.bite[t]) {
-          IN[t] |= in_mask;
-          SD[t] |= sd_mask;
-        }
+        acc |= s_lvl[warp][t][lane];
+        IN[t] = unsigned(acc);
+        SD[t] = unsigned(acc >> 32);
       }
     }
 #pragma unroll
@@ -411,6 +533,14 @@ void compute_hand_const(const ag_params& p, HandConst& h) {
     h.cam[0][a] = p.cam_tf_left[4 * a + 3];
     h.cam[1][a] = p.cam_tf_right[4 * a + 3];
   }
+  // fast slot lookup needs both hands' edge tables strictly ascending with a common step
+  h.inv_slot_step = step > 0 ? 1.0 / step : 0.0;
+  h.uniform_slots = step > 0 && p.finger_width > 0 ? 1 : 0;
+  if (const char* e = getenv("AG_SWEEP_FAST")) h.uniform_slots = h.uniform_slots && atoi(e) != 0;  // diagnostics
+  for (int i = 1; i < 10 && h.uniform_slots; i++)
+    if (!(h.spacing[i] > h.spacing[i - 1]) || !(h.spacing[10 + i] > h.spacing[9 + i]) ||
+        !(h.spacing[i] + p.finger_width > h.spacing[i - 1] + p.finger_width))
+      h.uniform_slots = 0;
   h.img_cell = (0.05 - (-0.05)) / double(AG_IMAGE_COLS);  // learning.cpp:322-324
   h.half_od = p.hand_outer_diameter / 2.0;
 }
@@ -442,22 +572,31 @@ int hand_sweep_device(Ctx* c, const int* d_indices, int n, const ag_frame* d_fra
   A.slab_counts = c->sweep_dbg.as<int>();
   A.debug = c->sweep_dbg.as<int>() + n;
   A.counters = c->counters.as<unsigned long long>();
-  A.overflow = reinterpret_cast<int*>(c->counters.as<unsigned long long>() + 6);
+  if (c->overflow.reserve(size_t(n + 1) * 4)) return AG_ERR_CUDA;
+  A.overflow = c->overflow.as<int>();
   A.n_samples = n;
   const double radius = c->params.nn_radius_hands;
   A.r2 = float(radius * radius);
   A.rpad = sqrt(double(A.r2)) * (1.0 + 1e-5) + 1e-7;
   A.filter_boundaries = (flags & 0x100u) ? 1 : 0;
   for (int i = 0; i < 6; i++) A.workspace[i] = c->params.workspace[i];
-  const size_t smem = size_t(kSlabCap) * sizeof(SlabPoint);
+  A.sample_list = nullptr;
+  const size_t smem_small = size_t(kSlabCapSmall) * sizeof(SlabPoint);
+  const size_t smem_big = size_t(kSlabCapBig) * sizeof(SlabPoint);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_hand_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cudaFuncSetAttribute(k_hand_sweep<kSlabCapSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_small));
+    cudaFuncSetAttribute(k_hand_sweep<kSlabCapSmall>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_hand_sweep<kSlabCapBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_big));
     attr_set = true;
   }
-  AG_CUDA_CHECK(cudaMemsetAsync(A.overflow, 0, 8, c->stream));
-  k_hand_sweep<<<n, kThreads, smem, c->stream>>>(A, c->grid, c->hand);
+  AG_CUDA_CHECK(cudaMemsetAsync(A.overflow, 0, 4, c->stream));
+  k_hand_sweep<kSlabCapSmall><<<n, kThreads, smem_small, c->stream>>>(A, c->grid, c->hand);
   c->launches += 2;  // + k_compact_grasps
+  int n_over = 0;
+  AG_CUDA_CHECK(cudaMemcpyAsync(&n_over, A.overflow, 4, cudaMemcpyDeviceToHost, c->stream));
+  // the overflow count travels with the (already required) hypothesis-count sync below in the common
+  // case; only when it is non-zero do we pay a second pass
   // stable compaction of the valid (sample, orientation) slots
   int* d_slots = c->hyp_slots.as<int>();
   int* d_nsel = d_slots + slots;
@@ -471,10 +610,31 @@ int hand_sweep_device(Ctx* c, const int* d_indices, int n, const ag_frame* d_fra
   AG_CUDA_CHECK(cudaGetLastError());
   int host[4] = {0, 0, 0, 0};
   AG_CUDA_CHECK(cudaMemcpyAsync(&host[0], d_nsel, 4, cudaMemcpyDeviceToHost, c->stream));
-  AG_CUDA_CHECK(cudaMemcpyAsync(&host[1], A.overflow, 4, cudaMemcpyDeviceToHost, c->stream));
   AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (n_over > 0) {
+    // dense neighbourhoods: redo those samples with the 13k-point instantiation, then re-compact
+    A.sample_list = A.overflow + 1;
+    int* d_over2 = A.overflow;  // reuse the counter to detect a second overflow
+    AG_CUDA_CHECK(cudaMemsetAsync(d_over2, 0, 4, c->stream));
+    // the list lives right behind the counter; copy it aside so the kernel can append again safely
+    DevBuf list;
+    if (list.reserve(size_t(n_over) * 4)) return AG_ERR_CUDA;
+    AG_CUDA_CHECK(cudaMemcpyAsync(list.p, A.overflow + 1, size_t(n_over) * 4, cudaMemcpyDeviceToDevice, c->stream));
+    A.sample_list = list.as<int>();
+    k_hand_sweep<kSlabCapBig><<<n_over, kThreads, smem_big, c->stream>>>(A, c->grid, c->hand);
+    AG_CUDA_CHECK(cub::DeviceSelect::Flagged(c->cub_tmp.p, tmp, iota, A.valid, d_slots, d_nsel, int(slots), c->stream));
+    k_compact_grasps<<<int((slots + 255) / 256), 256, 0, c->stream>>>(A.grasps, d_slots, d_nsel,
+                                                                      c->grasps.as<ag_grasp>(), int(slots));
+    c->launches += 2;
+    int over2 = 0;
+    AG_CUDA_CHECK(cudaMemcpyAsync(&over2, d_over2, 4, cudaMemcpyDeviceToHost, c->stream));
+    AG_CUDA_CHECK(cudaMemcpyAsync(&host[0], d_nsel, 4, cudaMemcpyDeviceToHost, c->stream));
+    AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    list.release();
+    host[1] = over2;
+  }
   if (host[1]) {
-    set_error("hand sweep: a sample's slab exceeded the shared-memory capacity (kSlabCap points)");
+    set_error("hand sweep: a sample's slab exceeded the shared-memory capacity (12032 points)");
     return AG_ERR_CAPACITY;
   }
   c->n_hyp = host[0];

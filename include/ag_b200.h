@@ -157,6 +157,11 @@ int ag_localize_device(ag_ctx* ctx, const void* d_points, int stride, int n_in, 
  * hypotheses the reference would return from predictAntipodalHands. */
 int ag_classify(ag_ctx* ctx, const ag_svm* svm, ag_grasp* grasps, int n, uint8_t* keep);
 
+/* Attach an SVM to the context (NULL detaches): every following ag_localize also scores its hypotheses
+ * in the same stream (score/label of the returned records are filled) and a following ag_classify with
+ * the same model just returns those results.  The model must outlive the attachment. */
+int ag_set_svm(ag_ctx* ctx, const ag_svm* svm);
+
 /* Variable-length members of GraspHypothesis for hypothesis `image_id` of the last ag_localize
  * (requires AG_FLAG_KEEP_POINTS): points_for_learning (3 x m, column-major doubles) and the
  * camera source of each column. */

@@ -26,6 +26,7 @@ class Localization {
       : num_threads_(num_threads), filters_boundaries_(filters_boundaries), plotting_mode_(plotting_mode),
         ctx_(nullptr), svm_(nullptr) { init(); }
   ~Localization() {
+    if (ctx_) ag_set_svm(ctx_, nullptr);
     if (svm_) ag_svm_free(svm_);
     if (ctx_) ag_destroy(ctx_);
   }
@@ -74,6 +75,7 @@ class Localization {
     std::vector<GraspHypothesis> antipodal_hands;
     if (!ensure_ctx()) return antipodal_hands;
     if (!svm_ || svm_path_ != svm_filename) {
+      ag_set_svm(ctx_, nullptr);
       if (svm_) ag_svm_free(svm_);
       svm_ = ag_svm_load(svm_filename.c_str());
       svm_path_ = svm_filename;
@@ -81,6 +83,7 @@ class Localization {
         std::cout << " " << ag_last_error() << "\n";
         return antipodal_hands;
       }
+      ag_set_svm(ctx_, svm_);  // later localizeHands calls score their hypotheses in the same pass
     }
     std::vector<ag_grasp> recs(hand_list.size());
     for (size_t i = 0; i < recs.size(); i++) recs[i] = hand_list[i].record();

@@ -523,72 +523,72 @@ static void fit_quadric_exact(const float* xyz, const std::vector<int>& nn, cons
         }
       B[i][j] = bs;
     }
-  // Cholesky B = L L^T
-  ld L[9][9] = {};
-  for (int j = 0; j < 9; j++) {
-    ld d = B[j][j];
-    for (int k = 0; k < j; k++) d -= L[j][k] * L[j][k];
-    if (!(d > 0)) d = 1e-300L;
-    L[j][j] = sqrtl(d);
-    for (int i = j + 1; i < 9; i++) {
-      ld v = B[i][j];
-      for (int k = 0; k < j; k++) v -= L[i][k] * L[j][k];
-      L[i][j] = v / L[j][j];
+  // B = Q D Q^T (Jacobi); W = Q_k D_k^(-1/2) over the directions with D_i > 1e-11 D_max (B is singular
+  // for degenerate neighbourhoods, e.g. voxel corners exactly in one lattice plane: those directions
+  // have infinite or 0/0 eigenvalues and are excluded); C = W^T A W; smallest eigenpair; u = W y.
+  auto jacobi = [](ld Mx[9][9], ld Vx[9][9]) {
+    for (int i = 0; i < 9; i++)
+      for (int j = 0; j < 9; j++) Vx[i][j] = i == j ? 1 : 0;
+    for (int sweep = 0; sweep < 80; sweep++) {
+      bool rotated = false;
+      for (int p = 0; p < 8; p++)
+        for (int q2 = p + 1; q2 < 9; q2++) {
+          const ld apq = Mx[p][q2], app = Mx[p][p], aqq = Mx[q2][q2];
+          if (!(fabsl(apq) > 1e-19L * sqrtl(fabsl(app * aqq)))) continue;
+          rotated = true;
+          const ld theta = (aqq - app) / (2 * apq);
+          const ld tt = (theta >= 0 ? 1 : -1) / (fabsl(theta) + sqrtl(theta * theta + 1));
+          const ld c = 1 / sqrtl(tt * tt + 1), s2 = tt * c;
+          for (int k = 0; k < 9; k++) {
+            const ld akp = Mx[k][p], akq = Mx[k][q2];
+            Mx[k][p] = c * akp - s2 * akq;
+            Mx[k][q2] = s2 * akp + c * akq;
+            const ld vkp = Vx[k][p], vkq = Vx[k][q2];
+            Vx[k][p] = c * vkp - s2 * vkq;
+            Vx[k][q2] = s2 * vkp + c * vkq;
+          }
+          for (int k = 0; k < 9; k++) {
+            const ld apk = Mx[p][k], aqk = Mx[q2][k];
+            Mx[p][k] = c * apk - s2 * aqk;
+            Mx[q2][k] = s2 * apk + c * aqk;
+          }
+          Mx[p][q2] = Mx[q2][p] = 0;
+        }
+      if (!rotated) break;
     }
-  }
-  // C = L^-1 A L^-T
-  ld X[9][9], Cm[9][9];
-  for (int c = 0; c < 9; c++)
-    for (int i = 0; i < 9; i++) {
-      ld v = A[i][c];
-      for (int k = 0; k < i; k++) v -= L[i][k] * X[k][c];
-      X[i][c] = v / L[i][i];
-    }
-  for (int r = 0; r < 9; r++)
-    for (int i = 0; i < 9; i++) {
-      ld v = X[r][i];
-      for (int k = 0; k < i; k++) v -= L[i][k] * Cm[r][k];
-      Cm[r][i] = v / L[i][i];
-    }
+  };
+  ld Bq[9][9], Q[9][9], W[9][9], Cm[9][9], Y[9][9];
   for (int i = 0; i < 9; i++)
-    for (int j = i + 1; j < 9; j++) Cm[i][j] = Cm[j][i] = (Cm[i][j] + Cm[j][i]) / 2;
-  ld V[9][9] = {};
-  for (int i = 0; i < 9; i++) V[i][i] = 1;
-  for (int sweep = 0; sweep < 60; sweep++) {
-    bool rotated = false;
-    for (int p = 0; p < 8; p++)
-      for (int q2 = p + 1; q2 < 9; q2++) {
-        const ld apq = Cm[p][q2], app = Cm[p][p], aqq = Cm[q2][q2];
-        if (!(fabsl(apq) > 1e-19L * sqrtl(fabsl(app * aqq)))) continue;
-        rotated = true;
-        const ld theta = (aqq - app) / (2 * apq);
-        const ld tt = (theta >= 0 ? 1 : -1) / (fabsl(theta) + sqrtl(theta * theta + 1));
-        const ld c = 1 / sqrtl(tt * tt + 1), s2 = tt * c;
-        for (int k = 0; k < 9; k++) {
-          const ld akp = Cm[k][p], akq = Cm[k][q2];
-          Cm[k][p] = c * akp - s2 * akq;
-          Cm[k][q2] = s2 * akp + c * akq;
-          const ld vkp = V[k][p], vkq = V[k][q2];
-          V[k][p] = c * vkp - s2 * vkq;
-          V[k][q2] = s2 * vkp + c * vkq;
-        }
-        for (int k = 0; k < 9; k++) {
-          const ld apk = Cm[p][k], aqk = Cm[q2][k];
-          Cm[p][k] = c * apk - s2 * aqk;
-          Cm[q2][k] = s2 * apk + c * aqk;
-        }
-        Cm[p][q2] = Cm[q2][p] = 0;
-      }
-    if (!rotated) break;
+    for (int j = 0; j < 9; j++) Bq[i][j] = B[i][j];
+  jacobi(Bq, Q);
+  ld dmax = 0;
+  for (int i = 0; i < 9; i++) dmax = std::max(dmax, Bq[i][i]);
+  bool dropped[9];
+  for (int j = 0; j < 9; j++) {
+    dropped[j] = !(Bq[j][j] > 1e-11L * dmax);
+    const ld sc = dropped[j] ? 0 : 1 / sqrtl(Bq[j][j]);
+    for (int i = 0; i < 9; i++) W[i][j] = Q[i][j] * sc;
   }
+  for (int i = 0; i < 9; i++)
+    for (int j = 0; j < 9; j++) {
+      ld v = 0;
+      for (int k = 0; k < 9; k++)
+        for (int l = 0; l < 9; l++) v += W[k][i] * A[k][l] * W[l][j];
+      Cm[i][j] = v;
+    }
+  for (int i = 0; i < 9; i++) {
+    for (int j = i + 1; j < 9; j++) Cm[i][j] = Cm[j][i] = (Cm[i][j] + Cm[j][i]) / 2;
+    if (dropped[i]) Cm[i][i] = 1e300L;
+  }
+  jacobi(Cm, Y);
   int mi = 0;
   for (int k = 1; k < 9; k++)
     if (Cm[k][k] < Cm[mi][mi]) mi = k;
   ld u[9];
-  for (int i = 8; i >= 0; i--) {
-    ld v = V[i][mi];
-    for (int k = i + 1; k < 9; k++) v -= L[k][i] * u[k];
-    u[i] = v / L[i][i];
+  for (int i = 0; i < 9; i++) {
+    ld v = 0;
+    for (int k = 0; k < 9; k++) v += W[i][k] * Y[k][mi];
+    u[i] = v;
   }
   ld mu = 0;
   for (int i = 0; i < 9; i++) { par_out[i] = double(u[i]); mu += mv[i] * u[i]; }
