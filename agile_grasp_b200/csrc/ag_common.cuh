@@ -19,33 +19,35 @@ namespace ag {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
-// Uniform hash grid over the voxelised cloud.  Points are sorted by linear cell id with z
-// fastest, so all cells (cx, cy, z0..z1) of a column are one contiguous run of float4 records:
-// every neighbourhood query is a handful of coalesced 16-byte-per-lane streams out of L2/HBM.
-struct GridDesc {
-  double gmin[3];   // lower corner (double so that binning is the same monotone function everywhere)
-  double inv_cell;  // 1 / cell size
-  int dim[3];       // cells per axis
-  int n_points;
+// ---- neighbour index ---------------------------------------------------------------------------
+// The voxelised cloud is emitted in the reference's order: per camera, voxels sorted
+// lexicographically by integer key (kx, ky, kz) (localization.h:281-292), i.e. all voxels with the
+// same kx are contiguous and sorted by (y, z).  The only index built on top is, per camera, a row
+// table row_ptr[kx] = first voxel with key_x >= kx.  A radius query is then, for each of the
+// <= 2r/voxel + 1 x-rows it can touch, ONE contiguous run found by a binary search on y: coalesced
+// 16-byte-per-lane streams, no second sort, no permutation, no hash-grid cell table.
+struct RowIndex {         // lives in device memory, written by the voxelisation kernels
+  double mn[2][3];        // per-camera lattice origin (the per-camera coordinate minima)
+  double inv_cell;        // 1 / voxel size
+  int nx[2];              // number of x-rows per camera
+  int row_base[2];        // offset of camera c's rows inside the row table
+  int first[2];           // index of the camera's first voxel
+  int count[2];           // voxels per camera
+  int n_points;           // total voxels
+  int n_samples;          // samples actually used by the current call (<= requested)
+  int error;              // sticky device-side error flags (kErr*)
+  int pad;
 };
+constexpr int kErrKeyOverflow = 1;   // voxel key outside the workspace-derived bit budget
+constexpr int kErrBadIndex = 2;      // a caller-supplied sample index is outside the voxelised cloud
 
-// point record in the cell-sorted array: xyz + (original voxel index | cam << 30 | has_normal << 31)
+// voxel record: xyz + tag.  tag bit 0 = camera source, bit 1 = "cloud_normals_ holds a non-zero normal"
 struct __align__(16) GPoint {
   float x, y, z;
   uint32_t tag;
 };
-constexpr uint32_t kTagIndexMask = 0x3FFFFFFFu;
-constexpr uint32_t kTagCamBit = 0x40000000u;
-constexpr uint32_t kTagNormalBit = 0x80000000u;
-
-__host__ __device__ inline int cell_of(double v, double gmin, double inv_cell, int dim) {
-  // monotone non-decreasing in v: subtraction and multiplication by a positive constant round
-  // monotonically, floor is monotone.  Used for both binning and query ranges.
-  double c = floor((v - gmin) * inv_cell);
-  if (c < 0) c = 0;
-  if (c > double(dim - 1)) c = double(dim - 1);
-  return int(c);
-}
+constexpr uint32_t kTagCamBit = 1u;
+constexpr uint32_t kTagNormalBit = 2u;
 
 // FLANN L2_Simple<float> distance, exactly as the reference's kd-tree evaluates it:
 // ((dx*dx) + dy*dy) + dz*dz in binary32, no FMA contraction.
@@ -57,22 +59,35 @@ __device__ __forceinline__ float dist2_flann(float qx, float qy, float qz, float
   return r;
 }
 
-// Query footprint in the grid: cell ranges per axis and the list of (cx,cy) columns.
-struct QueryBox {
-  int lo[3], hi[3];
-};
-__device__ __forceinline__ QueryBox query_box(const GridDesc& g, float qx, float qy, float qz, double rpad) {
-  QueryBox b;
-  const double q[3] = {double(qx), double(qy), double(qz)};
-#pragma unroll
-  for (int a = 0; a < 3; a++) {
-    b.lo[a] = cell_of(q[a] - rpad, g.gmin[a], g.inv_cell, g.dim[a]);
-    b.hi[a] = cell_of(q[a] + rpad, g.gmin[a], g.inv_cell, g.dim[a]);
-  }
-  return b;
+// x-row range of camera c that can hold points within rpad of qx (conservative: the stored x of row k
+// is float(k*cell + min), within 1e-5 cells of the binary64 value used here)
+__device__ __forceinline__ void row_range(const RowIndex& ri, int c, float qx, double rpad, int& k_lo, int& k_hi) {
+  const double a = (double(qx) - rpad - ri.mn[c][0]) * ri.inv_cell - 1e-3;
+  const double b = (double(qx) + rpad - ri.mn[c][0]) * ri.inv_cell + 1e-3;
+  k_lo = a <= 0.0 ? 0 : (a >= 2147483000.0 ? 2147483000 : int(a));  // floor for a >= 0
+  k_hi = b < 0.0 ? -1 : (b >= double(ri.nx[c] - 1) ? ri.nx[c] - 1 : int(b));
 }
-__device__ __forceinline__ int cell_linear(const GridDesc& g, int cx, int cy, int cz) {
-  return (cx * g.dim[1] + cy) * g.dim[2] + cz;
+
+// the run of row `k` of camera c with |y - qy| <= rpad: [j0, j1) by two binary searches on y
+__device__ __forceinline__ void row_run(const RowIndex& ri, const int* __restrict__ row_ptr,
+                                        const GPoint* __restrict__ pts, int c, int k, float qy, double rpad, int& j0,
+                                        int& j1) {
+  int a = __ldg(row_ptr + ri.row_base[c] + k), b = __ldg(row_ptr + ri.row_base[c] + k + 1);
+  const double ylo = double(qy) - rpad, yhi = double(qy) + rpad;
+  int lo = a, hi = b;
+  while (lo < hi) {  // first j with y >= ylo
+    const int mid = (lo + hi) >> 1;
+    if (double(__ldg(&pts[mid].y)) < ylo) lo = mid + 1;
+    else hi = mid;
+  }
+  j0 = lo;
+  hi = b;
+  while (lo < hi) {  // first j with y > yhi
+    const int mid = (lo + hi) >> 1;
+    if (double(__ldg(&pts[mid].y)) <= yhi) lo = mid + 1;
+    else hi = mid;
+  }
+  j1 = lo;
 }
 
 // ordered-int encoding of floats for atomicMin/atomicMax
@@ -105,6 +120,62 @@ __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// Builds the run list of a radius query for one warp: runs (start, length) of candidate points, as an
+// exclusive prefix over lengths in pre[0..n_runs].  rs / pre are this warp's shared arrays of capacity
+// cap / cap+1.  Returns the number of runs; `more` is set when the query touches more rows than fit
+// (the caller then continues with `row_off` advanced) — never the case for the shipped radii.
+__device__ __forceinline__ int build_runs_warp(const RowIndex& ri, const int* __restrict__ row_ptr,
+                                               const GPoint* __restrict__ pts, float qx, float qy, double rpad,
+                                               int* rs, int* pre, int cap, int row_off, bool& more) {
+  const int lane = threadIdx.x & 31;
+  int n_runs = 0;
+  int skip = row_off;
+  more = false;
+  for (int c = 0; c < 2; c++) {
+    if (ri.count[c] == 0) continue;
+    int k_lo, k_hi;
+    row_range(ri, c, qx, rpad, k_lo, k_hi);
+    int rows = k_hi - k_lo + 1;
+    if (rows <= 0) continue;
+    if (skip >= rows) {
+      skip -= rows;
+      continue;
+    }
+    k_lo += skip;
+    rows -= skip;
+    skip = 0;
+    if (n_runs + rows > cap) {
+      rows = cap - n_runs;
+      more = true;
+    }
+    for (int t = lane; t < rows; t += 32) {
+      int j0, j1;
+      row_run(ri, row_ptr, pts, c, k_lo + t, qy, rpad, j0, j1);
+      rs[n_runs + t] = j0;
+      pre[n_runs + t + 1] = j1 - j0;
+    }
+    n_runs += rows;
+    if (more) break;
+  }
+  __syncwarp();
+  // inclusive scan of the run lengths -> exclusive prefix in pre[]
+  int carry = 0;
+  for (int base = 0; base < n_runs; base += 32) {
+    const int i = base + lane;
+    int v = i < n_runs ? pre[i + 1] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (i < n_runs) pre[i + 1] = v + carry;
+    carry += __shfl_sync(0xffffffffu, v, 31);
+  }
+  if (lane == 0) pre[0] = 0;
+  __syncwarp();
+  return n_runs;
 }
 
 }  // namespace ag

@@ -67,19 +67,27 @@ struct Ctx {
   DevBuf raw, keys, keys_sorted, keys_unique, cub_tmp, block_counts, misc;
   void* h_pinned = nullptr;  // pinned staging for inputs / outputs
   size_t h_pinned_cap = 0;
-  // voxelised cloud (API index space) and cell-sorted copy
-  DevBuf vox;        // float4: xyz + cam (as int bits)
-  DevBuf cell_ids, cell_ids_sorted, perm, perm_sorted, cell_start, pts, inv;
+  // voxelised cloud (API index space = the reference's voxel order) and its x-row index
+  DevBuf vox;        // GPoint: xyz + tag
+  DevBuf row_ptr;    // per camera: first voxel of every x-row
+  DevBuf row_index;  // RowIndex descriptor (device resident; counts never round-trip through the host)
   DevBuf normals;    // double x 3 per voxel point (cloud_normals_)
-  GridDesc grid;
-  int n_vox = 0;
+  int n_vox = 0;     // host copy, valid after fetch_cloud_size / the end of ag_localize
+  int n_cap = 0;     // upper bound on the voxel count known to the host (number of input points)
+  // results land in pinned, device-mapped host memory (written by the export kernel)
+  void* h_out = nullptr;
+  void* d_out_mapped = nullptr;
+  size_t h_out_cap = 0;
   // samples
-  DevBuf samples, moments, frames, nn_counts;
+  DevBuf samples, moments, frames, nn_counts, all_frames;
   int n_samples = 0;
   // sweep outputs
   DevBuf grasps_raw, valid, images_raw, hyp_slots, grasps, counters, scores, descriptors, sweep_dbg, overflow;
   int n_hyp = 0;
   bool images_valid = false;
+  unsigned sweep_flags = 0;          // arguments of the last hand_sweep_enqueue (for the overflow re-run)
+  const int* sweep_indices = nullptr;
+  const ag_frame* sweep_frames = nullptr;
   SvmModel* attached_svm = nullptr;  // ag_set_svm: score inside ag_localize
   bool scores_valid = false;         // last_grasps carry scores of attached_svm
   bool keep_points = false;
@@ -94,14 +102,21 @@ struct Ctx {
 int ctx_pinned(Ctx* c, size_t bytes);
 
 // ---- stage launchers (each returns AG_OK or an error code); all work is enqueued on c->stream
-int preprocess_device(Ctx* c, const void* d_points, int stride, int n_in, int size_left);  // -> c->vox, c->n_vox
+int preprocess_device(Ctx* c, const void* d_points, int stride, int n_in, int size_left);  // -> c->vox (no sync)
+int fetch_cloud_size(Ctx* c);  // waits for the stream and reads the voxel count / error flags
 int set_cloud_device(Ctx* c, int n);  // cloud already in c->vox (ag_set_cloud)
 int set_normals_device(Ctx* c, const double* h_normals);  // cloud_normals_ supplied by the caller
-int build_grid(Ctx* c);                                                                    // -> c->pts, c->cell_start
-int fit_quadrics_device(Ctx* c, const int* d_indices, int n, double radius, ag_frame* d_frames,
+// d_count: device int holding the number of valid entries of d_indices (<= n, the launch bound)
+int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count, double radius, ag_frame* d_frames,
                         bool write_normals);
-int hand_sweep_device(Ctx* c, const int* d_indices, int n, const ag_frame* d_frames, unsigned flags);
-int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d_image_ids, int n,
+// enqueue only (no sync): sweep + stable compaction; the hypothesis count stays in device memory
+int hand_sweep_enqueue(Ctx* c, const int* d_indices, int n, const ag_frame* d_frames, unsigned flags);
+// after a sync: handles samples whose slab overflowed the small instantiation; returns the hypothesis count
+int hand_sweep_finish(Ctx* c, int n, int n_over, int* n_hyp);
+int* hand_sweep_count_ptr(Ctx* c, int n);     // device address of the hypothesis count of the last enqueue
+int* hand_sweep_overflow_ptr(Ctx* c);         // device address of the overflow counter
+// n_dev (may be null): device int with the number of hypotheses; n is then only the launch bound
+int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d_image_ids, int n, const int* n_dev,
                    float* d_descriptors, float* d_scores, ag_grasp* d_grasps_out = nullptr);
 int radius_search_device(Ctx* c, const float q[3], double radius, std::vector<int>& out);
 

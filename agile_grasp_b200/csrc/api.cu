@@ -53,21 +53,56 @@ int ctx_pinned(Ctx* c, size_t bytes) {
 }
 
 
+// ---- device-side sample handling -------------------------------------------------------------
 // stratified sorted distinct sample draw (replaces the time-seeded pcl::RandomSample,
-// hand_search.cpp:36-39): stratum k = [floor(k n/S), floor((k+1) n/S)), one index from each
-static inline uint64_t splitmix64(uint64_t x) {
+// hand_search.cpp:36-39): stratum k = [floor(k n/S), floor((k+1) n/S)), one index from each.
+// Runs on the device because the voxel count n never visits the host mid-pipeline.
+__host__ __device__ static inline uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;
   x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
   x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
   return x ^ (x >> 31);
 }
-static void draw_samples(int n, int S, uint64_t seed, std::vector<int>& out) {
-  if (S > n) S = n;
-  out.resize(S);
-  for (int k = 0; k < S; k++) {
-    const int64_t lo = (int64_t(k) * n) / S, hi = (int64_t(k + 1) * n) / S;
-    const uint64_t h = splitmix64(seed ^ splitmix64(uint64_t(k)));
-    out[k] = int(lo + int64_t(h % uint64_t(hi - lo)));
+__global__ void k_draw_samples(RowIndex* ri, int s_req, uint64_t seed, int* out) {
+  const int n = ri->n_points;
+  const int S = s_req < n ? s_req : n;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0) ri->n_samples = S;
+  if (k >= s_req) return;
+  if (k >= S) {
+    out[k] = -1;
+    return;
+  }
+  const long long lo = (static_cast<long long>(k) * n) / S, hi = (static_cast<long long>(k + 1) * n) / S;
+  const uint64_t h = splitmix64(seed ^ splitmix64(uint64_t(k)));
+  out[k] = int(lo + static_cast<long long>(h % uint64_t(hi - lo)));
+}
+__global__ void k_check_samples(RowIndex* ri, int s_req, const int* idx) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0) ri->n_samples = s_req;
+  if (k < s_req && (idx[k] < 0 || idx[k] >= ri->n_points)) atomicOr(&ri->error, kErrBadIndex);
+}
+__global__ void k_iota(int* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i;
+}
+
+// results header + records, written straight into pinned device-mapped host memory
+struct HostOut {
+  int n_hyp, n_vox, n_samples, error, n_over, pad[3];
+  unsigned long long counters[4];
+};
+__global__ void k_export(const ag_grasp* __restrict__ grasps, const int* __restrict__ n_sel, const RowIndex* ri,
+                         const int* overflow, const unsigned long long* counters, HostOut* hdr, ag_grasp* out, int cap) {
+  const int n = min(*n_sel, cap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = grasps[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    hdr->n_hyp = n;
+    hdr->n_vox = ri->n_points;
+    hdr->n_samples = ri->n_samples;
+    hdr->error = ri->error;
+    hdr->n_over = overflow[0];
+    for (int k = 0; k < 4; k++) hdr->counters[k] = counters[k];
   }
 }
 
@@ -173,7 +208,24 @@ static float elapsed(cudaEvent_t a, cudaEvent_t b) {
   return ms;
 }
 
-// the full device-side path, cloud already in device memory
+static int ensure_out(Ctx* c, size_t bytes) {
+  if (bytes <= c->h_out_cap) return 0;
+  if (c->h_out) cudaFreeHost(c->h_out);
+  c->h_out = nullptr;
+  c->h_out_cap = 0;
+  const size_t want = bytes + bytes / 4 + 4096;
+  if (cudaHostAlloc(&c->h_out, want, cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer(&c->d_out_mapped, c->h_out, 0) != cudaSuccess) {
+    set_error("cudaHostAlloc(mapped) failed");
+    return AG_ERR_CUDA;
+  }
+  c->h_out_cap = want;
+  return 0;
+}
+
+// The full device-side path, cloud already in device memory.  Everything is enqueued without a single
+// host round trip: the voxel count, the sample list, the hypothesis count and the grasp records stay
+// on the device until the export kernel writes them into mapped host memory; the host waits once.
 static int localize_core(Ctx* c, const void* d_points, int stride, int n_in, int size_left, const int* indices,
                          int n_indices, unsigned flags, ag_grasp** out, int* n_out) {
   *out = nullptr;
@@ -189,90 +241,114 @@ static int localize_core(Ctx* c, const void* d_points, int stride, int n_in, int
   int rc = preprocess_device(c, d_points, stride, n_in, size_left);
   if (rc) return rc;
   cudaEventRecord(c->ev[2], st);
-  c->timings.n_voxels = c->n_vox;
-  if (c->n_vox == 0) return AG_OK;
-  rc = build_grid(c);
-  if (rc) return rc;
   cudaEventRecord(c->ev[3], st);
-  if (c->counters.reserve(64)) return AG_ERR_CUDA;
-  AG_CUDA_CHECK(cudaMemsetAsync(c->counters.p, 0, 64, st));
-  const int n = c->n_vox;
-  // samples
-  std::vector<int> idx;
-  if (indices && n_indices > 0) {
-    idx.assign(indices, indices + n_indices);
-    for (int i : idx)
-      if (i < 0 || i >= n) {
-        set_error("sample index out of range of the voxelised cloud");
-        return AG_ERR_INVALID;
-      }
-  } else {
-    draw_samples(n, c->params.num_samples, c->params.seed, idx);
-  }
-  const int S = int(idx.size());
+  RowIndex* ri = c->row_index.as<RowIndex>();
+  // samples (device side)
+  const bool given = indices && n_indices > 0;
+  const int S = given ? n_indices : std::max(0, c->params.num_samples);
   c->n_samples = S;
-  c->timings.n_samples = S;
-  if (c->samples.reserve(size_t(std::max(S, n)) * 4) || c->frames.reserve(size_t(std::max(S, 1)) * sizeof(ag_frame)))
+  if (S == 0) {
+    rc = fetch_cloud_size(c);
+    c->timings.n_voxels = c->n_vox;
+    return rc;
+  }
+  const size_t slots = size_t(S) * 8;
+  if (c->samples.reserve(size_t(std::max(S, n_in)) * 4) || c->frames.reserve(size_t(S) * sizeof(ag_frame)) ||
+      c->counters.reserve(64) || ensure_out(c, sizeof(HostOut) + slots * sizeof(ag_grasp)))
     return AG_ERR_CUDA;
+  AG_CUDA_CHECK(cudaMemsetAsync(c->counters.p, 0, 64, st));
   if (flags & AG_FLAG_CALC_ANTIPODAL) {
-    // hand_search.cpp:17-26: normals for ALL points with radius 0.01
-    DevBuf all_idx, all_frames;
-    if (all_idx.reserve(size_t(n) * 4) || all_frames.reserve(size_t(n) * sizeof(ag_frame))) return AG_ERR_CUDA;
-    std::vector<int> iota(n);
-    for (int i = 0; i < n; i++) iota[i] = i;
-    AG_CUDA_CHECK(cudaMemcpyAsync(all_idx.p, iota.data(), size_t(n) * 4, cudaMemcpyHostToDevice, st));
-    rc = fit_quadrics_device(c, all_idx.as<int>(), n, c->params.nn_radius_normals, all_frames.as<ag_frame>(), true);
-    AG_CUDA_CHECK(cudaStreamSynchronize(st));
-    all_idx.release();
-    all_frames.release();
+    // hand_search.cpp:17-26: normals for ALL points with radius 0.01 (launch bound = number of inputs)
+    DevBuf& all_frames = c->all_frames;
+    if (all_frames.reserve(size_t(n_in) * sizeof(ag_frame))) return AG_ERR_CUDA;
+    k_iota<<<(n_in + 255) / 256, 256, 0, st>>>(c->samples.as<int>(), n_in);
+    rc = fit_quadrics_device(c, c->samples.as<int>(), n_in, &ri->n_points, c->params.nn_radius_normals,
+                             all_frames.as<ag_frame>(), true);
     if (rc) return rc;
     AG_CUDA_CHECK(cudaMemsetAsync(c->counters.p, 0, 64, st));
   }
   cudaEventRecord(c->ev[4], st);
-  AG_CUDA_CHECK(cudaMemcpyAsync(c->samples.p, idx.data(), size_t(S) * 4, cudaMemcpyHostToDevice, st));
-  rc = fit_quadrics_device(c, c->samples.as<int>(), S, c->params.nn_radius_taubin, c->frames.as<ag_frame>(), true);
+  if (given) {
+    AG_CUDA_CHECK(cudaMemcpyAsync(c->samples.p, indices, size_t(S) * 4, cudaMemcpyHostToDevice, st));
+    k_check_samples<<<(S + 255) / 256, 256, 0, st>>>(ri, S, c->samples.as<int>());
+  } else {
+    k_draw_samples<<<(S + 255) / 256, 256, 0, st>>>(ri, S, c->params.seed, c->samples.as<int>());
+  }
+  c->launches += 1;
+  rc = fit_quadrics_device(c, c->samples.as<int>(), S, &ri->n_samples, c->params.nn_radius_taubin,
+                           c->frames.as<ag_frame>(), true);
   if (rc) return rc;
   cudaEventRecord(c->ev[5], st);
-  rc = hand_sweep_device(c, c->samples.as<int>(), S, c->frames.as<ag_frame>(),
-                         c->params.filters_boundaries ? 0x100u : 0u);
+  rc = hand_sweep_enqueue(c, c->samples.as<int>(), S, c->frames.as<ag_frame>(),
+                          c->params.filters_boundaries ? 0x100u : 0u);
   if (rc) return rc;
-  cudaEventRecord(c->ev[6], st);
-  const int Hn = c->n_hyp;
-  if (c->attached_svm && Hn > 0) {  // fused scoring: no extra host round trip
-    if (c->scores.reserve(size_t(Hn) * 8 + 64)) return AG_ERR_CUDA;
-    cudaEventRecord(c->ev[8], st);
-    rc = hog_svm_device(c, c->attached_svm, c->images_raw.as<uint32_t>(), c->hyp_slots.as<int>(), Hn, nullptr,
-                        c->scores.as<float>(), c->grasps.as<ag_grasp>());
+  int* d_nsel = hand_sweep_count_ptr(c, S);
+  cudaEventRecord(c->ev[8], st);
+  if (c->attached_svm) {  // fused scoring, hypothesis count read on the device
+    if (c->scores.reserve(slots * 8 + 64)) return AG_ERR_CUDA;
+    rc = hog_svm_device(c, c->attached_svm, c->images_raw.as<uint32_t>(), c->hyp_slots.as<int>(), int(slots), d_nsel,
+                        nullptr, c->scores.as<float>(), c->grasps.as<ag_grasp>());
     if (rc) return rc;
-    cudaEventRecord(c->ev[9], st);
-    cudaEventRecord(c->ev[6], st);
   }
-  ag_grasp* res = static_cast<ag_grasp*>(std::malloc(std::max<size_t>(1, size_t(Hn)) * sizeof(ag_grasp)));
-  if (Hn > 0) AG_CUDA_CHECK(cudaMemcpyAsync(res, c->grasps.p, size_t(Hn) * sizeof(ag_grasp), cudaMemcpyDeviceToHost, st));
-  unsigned long long ctr[8];
-  AG_CUDA_CHECK(cudaMemcpyAsync(ctr, c->counters.p, 64, cudaMemcpyDeviceToHost, st));
+  cudaEventRecord(c->ev[9], st);
+  cudaEventRecord(c->ev[6], st);
+  HostOut* hdr = static_cast<HostOut*>(c->d_out_mapped);
+  ag_grasp* recs = reinterpret_cast<ag_grasp*>(hdr + 1);
+  k_export<<<kNumSMs, 256, 0, st>>>(c->grasps.as<ag_grasp>(), d_nsel, ri, hand_sweep_overflow_ptr(c),
+                                    c->counters.as<unsigned long long>(), hdr, recs, int(slots));
+  c->launches += 1;
   cudaEventRecord(c->ev[7], st);
   AG_CUDA_CHECK(cudaStreamSynchronize(st));
+  AG_CUDA_CHECK(cudaGetLastError());
+  HostOut* h = static_cast<HostOut*>(c->h_out);
+  c->n_vox = h->n_vox;
+  c->timings.n_voxels = h->n_vox;
+  c->timings.n_samples = h->n_samples;
+  if (h->error & kErrKeyOverflow) {
+    set_error("voxel index exceeds the key range (workspace extent / voxel_size > 2^21 cells)");
+    return AG_ERR_CAPACITY;
+  }
+  if (h->error & kErrBadIndex) {
+    set_error("sample index out of range of the voxelised cloud");
+    return AG_ERR_INVALID;
+  }
+  int Hn = h->n_hyp;
+  c->n_hyp = Hn;
+  c->images_valid = true;
+  if (h->n_over > 0) {
+    // rare: some samples need the large-capacity sweep; redo them, rescore, re-export (with syncs)
+    rc = hand_sweep_finish(c, S, h->n_over, &Hn);
+    if (rc) return rc;
+    if (c->attached_svm && Hn > 0) {
+      rc = hog_svm_device(c, c->attached_svm, c->images_raw.as<uint32_t>(), c->hyp_slots.as<int>(), Hn, nullptr, nullptr,
+                          c->scores.as<float>(), c->grasps.as<ag_grasp>());
+      if (rc) return rc;
+    }
+    k_export<<<kNumSMs, 256, 0, st>>>(c->grasps.as<ag_grasp>(), d_nsel, ri, hand_sweep_overflow_ptr(c),
+                                      c->counters.as<unsigned long long>(), hdr, recs, int(slots));
+    AG_CUDA_CHECK(cudaStreamSynchronize(st));
+    Hn = h->n_hyp;
+    c->n_hyp = Hn;
+  }
+  ag_grasp* res = static_cast<ag_grasp*>(std::malloc(std::max<size_t>(1, size_t(Hn)) * sizeof(ag_grasp)));
+  if (Hn > 0) std::memcpy(res, reinterpret_cast<const ag_grasp*>(h + 1), size_t(Hn) * sizeof(ag_grasp));
   c->timings.preprocess_ms = elapsed(c->ev[1], c->ev[2]);
-  c->timings.grid_ms = elapsed(c->ev[2], c->ev[3]);
+  c->timings.grid_ms = 0.f;  // the x-row index is built inside the voxelisation pass
   c->timings.normals_all_ms = elapsed(c->ev[3], c->ev[4]);
   c->timings.quadric_ms = elapsed(c->ev[4], c->ev[5]);
-  c->timings.sweep_ms = elapsed(c->ev[5], c->ev[6]);
+  c->timings.sweep_ms = elapsed(c->ev[5], c->ev[8]);
+  c->timings.hog_svm_ms = elapsed(c->ev[8], c->ev[9]);
   c->timings.d2h_ms = elapsed(c->ev[6], c->ev[7]);
-  if (c->attached_svm && Hn > 0) {
-    c->timings.hog_svm_ms = elapsed(c->ev[8], c->ev[9]);
-    c->timings.sweep_ms = elapsed(c->ev[5], c->ev[8]);
-    c->scores_valid = true;
-  }
   c->timings.total_ms = elapsed(c->ev[0], c->ev[7]);
   c->timings.n_hyp = Hn;
   c->timings.moments_ms = elapsed(c->ev_k[0], c->ev_k[1]);
   c->timings.axes_ms = elapsed(c->ev_k[1], c->ev_k[2]);
   c->timings.kernel_launches = c->launches;
-  c->timings.taubin_neighbor_points = int64_t(ctr[0]);
-  c->timings.taubin_candidates = int64_t(ctr[1]);
-  c->timings.hand_neighbor_points = int64_t(ctr[2]);
-  c->timings.hand_candidates = int64_t(ctr[3]);
+  c->timings.taubin_neighbor_points = int64_t(h->counters[0]);
+  c->timings.taubin_candidates = int64_t(h->counters[1]);
+  c->timings.hand_neighbor_points = int64_t(h->counters[2]);
+  c->timings.hand_candidates = int64_t(h->counters[3]);
+  if (c->attached_svm) c->scores_valid = true;
   c->last_grasps.assign(res, res + Hn);
   *out = res;
   *n_out = Hn;
@@ -347,7 +423,6 @@ ag_ctx* ag_create(int device) {
   ag_default_params(&c.params);
   compute_hand_const(c.params, c.hand);
   std::memset(&c.timings, 0, sizeof(c.timings));
-  std::memset(&c.grid, 0, sizeof(c.grid));
   return h;
 }
 
@@ -356,8 +431,9 @@ void ag_destroy(ag_ctx* h) {
   Ctx& c = h->c;
   cudaSetDevice(c.device);
   cudaStreamSynchronize(c.stream);
+  if (c.h_out) cudaFreeHost(c.h_out);
   for (DevBuf* b : {&c.raw, &c.keys, &c.keys_sorted, &c.keys_unique, &c.cub_tmp, &c.block_counts, &c.misc, &c.vox,
-                    &c.cell_ids, &c.cell_ids_sorted, &c.perm, &c.perm_sorted, &c.cell_start, &c.pts, &c.inv,
+                    &c.row_ptr, &c.row_index, &c.all_frames,
                     &c.normals, &c.samples, &c.moments, &c.frames, &c.nn_counts, &c.grasps_raw, &c.valid,
                     &c.images_raw, &c.hyp_slots, &c.grasps, &c.counters, &c.scores, &c.descriptors, &c.sweep_dbg, &c.overflow})
     b->release();
@@ -494,7 +570,7 @@ int ag_classify(ag_ctx* h, const ag_svm* svm, ag_grasp* grasps, int n, uint8_t* 
     AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
     d_slots = d_ids;
   }
-  int rc = hog_svm_device(&c, svm->m, c.images_raw.as<uint32_t>(), d_slots, n, nullptr, d_scores);
+  int rc = hog_svm_device(&c, svm->m, c.images_raw.as<uint32_t>(), d_slots, n, nullptr, nullptr, d_scores);
   if (rc) return rc;
   std::vector<float> sc_h(n);
   AG_CUDA_CHECK(cudaMemcpyAsync(sc_h.data(), d_scores, size_t(n) * 4, cudaMemcpyDeviceToHost, c.stream));
@@ -563,12 +639,13 @@ int ag_preprocess(ag_ctx* h, const void* points, int stride, int n_in, int size_
   const size_t bytes = size_t(n_in) * stride;
   if (c.raw.reserve(bytes)) return AG_ERR_CUDA;
   AG_CUDA_CHECK(cudaMemcpyAsync(c.raw.p, points, bytes, cudaMemcpyHostToDevice, c.stream));
+  c.launches = 0;
   int rc = preprocess_device(&c, c.raw.p, stride, n_in, size_left);
   if (rc) return rc;
-  rc = build_grid(&c);
+  rc = fetch_cloud_size(&c);
   if (rc) return rc;
   const int n = c.n_vox;
-  std::vector<float4> v(n);
+  std::vector<GPoint> v(n);
   if (n > 0) AG_CUDA_CHECK(cudaMemcpyAsync(v.data(), c.vox.p, size_t(n) * 16, cudaMemcpyDeviceToHost, c.stream));
   AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
   float* xyz = static_cast<float*>(std::malloc(std::max<size_t>(1, size_t(n)) * 12));
@@ -577,9 +654,7 @@ int ag_preprocess(ag_ctx* h, const void* points, int stride, int n_in, int size_
     xyz[3 * i] = v[i].x;
     xyz[3 * i + 1] = v[i].y;
     xyz[3 * i + 2] = v[i].z;
-    int ci;
-    std::memcpy(&ci, &v[i].w, 4);
-    cam[i] = ci;
+    cam[i] = (v[i].tag & kTagCamBit) ? 1 : 0;
   }
   *xyz_out = xyz;
   *cam_out = cam;
@@ -592,20 +667,17 @@ int ag_set_cloud(ag_ctx* h, const float* xyz, const int32_t* cam, int n) {
   Ctx& c = h->c;
   cudaSetDevice(c.device);
   c.images_valid = false;
-  std::vector<float4> v(n);
+  std::vector<GPoint> v(n);
   for (int i = 0; i < n; i++) {
     v[i].x = xyz[3 * i];
     v[i].y = xyz[3 * i + 1];
     v[i].z = xyz[3 * i + 2];
-    const int ci = cam ? (cam[i] ? 1 : 0) : 0;
-    std::memcpy(&v[i].w, &ci, 4);
+    v[i].tag = (cam && cam[i]) ? kTagCamBit : 0u;
   }
   if (c.vox.reserve(std::max<size_t>(16, size_t(n) * 16))) return AG_ERR_CUDA;
   if (n > 0) AG_CUDA_CHECK(cudaMemcpyAsync(c.vox.p, v.data(), size_t(n) * 16, cudaMemcpyHostToDevice, c.stream));
   AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
-  int rc = set_cloud_device(&c, n);
-  if (rc) return rc;
-  return build_grid(&c);
+  return set_cloud_device(&c, n);
 }
 
 int ag_radius_search(ag_ctx* h, const float q[3], double radius, int32_t** idx_out, int* n_out) {
@@ -636,7 +708,11 @@ int ag_fit_quadrics(ag_ctx* h, const int* indices, int n_indices, double radius,
     return AG_ERR_CUDA;
   AG_CUDA_CHECK(cudaMemsetAsync(c.counters.p, 0, 64, c.stream));
   AG_CUDA_CHECK(cudaMemcpyAsync(c.samples.p, indices, size_t(n_indices) * 4, cudaMemcpyHostToDevice, c.stream));
-  int rc = fit_quadrics_device(&c, c.samples.as<int>(), n_indices, radius, c.frames.as<ag_frame>(), false);
+  RowIndex* ri = c.row_index.as<RowIndex>();
+  k_check_samples<<<(n_indices + 255) / 256, 256, 0, c.stream>>>(ri, n_indices, c.samples.as<int>());
+  AG_CUDA_CHECK(cudaMemsetAsync(c.frames.p, 0, size_t(n_indices) * sizeof(ag_frame), c.stream));
+  int rc = fit_quadrics_device(&c, c.samples.as<int>(), n_indices, &ri->n_samples, radius, c.frames.as<ag_frame>(),
+                               false);
   if (rc) return rc;
   AG_CUDA_CHECK(cudaMemcpyAsync(frames_out, c.frames.p, size_t(n_indices) * sizeof(ag_frame), cudaMemcpyDeviceToHost,
                                 c.stream));
@@ -665,9 +741,16 @@ int ag_hand_sweep(ag_ctx* h, const int* indices, int n_indices, const ag_frame* 
                                 c.stream));
   int rc = set_normals_device(&c, cloud_normals);
   if (rc) return rc;
-  rc = hand_sweep_device(&c, c.samples.as<int>(), n_indices, c.frames.as<ag_frame>(), flags & 0x100u);
+  RowIndex* ri = c.row_index.as<RowIndex>();
+  k_check_samples<<<(n_indices + 255) / 256, 256, 0, c.stream>>>(ri, n_indices, c.samples.as<int>());
+  rc = hand_sweep_enqueue(&c, c.samples.as<int>(), n_indices, c.frames.as<ag_frame>(), flags & 0x100u);
   if (rc) return rc;
-  const int Hn = c.n_hyp;
+  int n_over = 0;
+  AG_CUDA_CHECK(cudaMemcpyAsync(&n_over, hand_sweep_overflow_ptr(&c), 4, cudaMemcpyDeviceToHost, c.stream));
+  AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  int Hn = 0;
+  rc = hand_sweep_finish(&c, n_indices, n_over, &Hn);
+  if (rc) return rc;
   ag_grasp* res = static_cast<ag_grasp*>(std::malloc(std::max<size_t>(1, size_t(Hn)) * sizeof(ag_grasp)));
   if (Hn > 0) AG_CUDA_CHECK(cudaMemcpy(res, c.grasps.p, size_t(Hn) * sizeof(ag_grasp), cudaMemcpyDeviceToHost));
   *out = res;
@@ -692,7 +775,7 @@ int ag_hog_svm(ag_ctx* h, const ag_svm* svm, const uint32_t* images, int n, floa
   if (img.reserve(size_t(n) * AG_IMAGE_WORDS * 4) || sc.reserve(size_t(n) * 4)) return AG_ERR_CUDA;
   if (descriptors && c.descriptors.reserve(size_t(n) * AG_HOG_DIM * 4)) return AG_ERR_CUDA;
   AG_CUDA_CHECK(cudaMemcpyAsync(img.p, images, size_t(n) * AG_IMAGE_WORDS * 4, cudaMemcpyHostToDevice, c.stream));
-  int rc = hog_svm_device(&c, svm->m, img.as<uint32_t>(), nullptr, n, descriptors ? c.descriptors.as<float>() : nullptr,
+  int rc = hog_svm_device(&c, svm->m, img.as<uint32_t>(), nullptr, n, nullptr, descriptors ? c.descriptors.as<float>() : nullptr,
                           sc.as<float>());
   if (rc == AG_OK) {
     cudaMemcpyAsync(scores, sc.p, size_t(n) * 4, cudaMemcpyDeviceToHost, c.stream);

@@ -14,6 +14,7 @@
 // windows share 4 of their 7 block columns, so only 11x7 = 77 distinct blocks are computed.
 // Compiled with -fmad=false.
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -162,8 +163,9 @@ __device__ __forceinline__ uint32_t bits_at(const uint32_t* img, int bit0) {  //
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slots, int n, SvmDev svm,
-          float* __restrict__ descriptors, float* __restrict__ scores, ag_grasp* __restrict__ grasps_out) {
+k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slots, int n_bound,
+          const int* __restrict__ n_dev, SvmDev svm, float* __restrict__ descriptors, float* __restrict__ scores,
+          ag_grasp* __restrict__ grasps_out) {
   __shared__ uint32_t s_bits[AG_IMAGE_WORDS + 2];
   __shared__ uint32_t s_row[H][RW];                 // row-aligned image
   __shared__ uint32_t s_xp[H][RW], s_xn[H][RW], s_yp[H][RW], s_yn[H][RW];  // gradient sign bit-planes
@@ -171,9 +173,10 @@ k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slo
   __shared__ __align__(16) float s_hist[NUB * 36];
   __shared__ float s_K[1280];                       // kernel values per support vector
   __shared__ double s_part[kThreads / 32];
-  const int hyp = blockIdx.x;
-  if (hyp >= n) return;
+  const int n = n_dev ? min(*n_dev, n_bound) : n_bound;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int hyp = blockIdx.x; hyp < n; hyp += gridDim.x) {  // persistent CTAs: the count lives on the device
+  __syncthreads();
   const uint32_t* src = images + size_t(image_slots ? image_slots[hyp] : hyp) * AG_IMAGE_WORDS;
   for (int i = tid; i < AG_IMAGE_WORDS + 2; i += kThreads) s_bits[i] = i < AG_IMAGE_WORDS ? src[i] : 0u;
   __syncthreads();
@@ -347,6 +350,7 @@ k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slo
       grasps_out[hyp].label = sc > 0.f ? 0 : 1;  // CvSVM::predict: label +1 <=> sum <= 0
     }
   }
+  }  // hypothesis loop
 }
 
 bool g_tables_ready[64] = {false};
@@ -371,7 +375,7 @@ int svm_to_device(SvmModel* svm, int device) {
   return AG_OK;
 }
 
-int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d_image_slots, int n,
+int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d_image_slots, int n, const int* n_dev,
                    float* d_descriptors, float* d_scores, ag_grasp* d_grasps_out) {
   if (n <= 0) return AG_OK;
   if (svm->var_count != AG_HOG_DIM) {
@@ -403,7 +407,9 @@ int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d
   sd.coef0 = svm->coef0;
   sd.rho = svm->rho;
   c->launches += 1;
-  k_hog_svm<<<n, kThreads, 0, c->stream>>>(d_images, d_image_slots, n, sd, d_descriptors, d_scores, d_grasps_out);
+  const int grid = n_dev ? std::min(n, kNumSMs * 6) : n;  // device-side count: persistent CTAs
+  k_hog_svm<<<grid, kThreads, 0, c->stream>>>(d_images, d_image_slots, n, n_dev, sd, d_descriptors, d_scores,
+                                               d_grasps_out);
   AG_CUDA_CHECK(cudaGetLastError());
   return AG_OK;
 }

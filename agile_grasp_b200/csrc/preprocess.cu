@@ -3,9 +3,10 @@
 // Replaces (reference paths): pcl::removeNaNFromPointCloud + camera labelling
 // (src/agile_grasp/localization.cpp:17-27), Localization::filterWorkspace (:216-245),
 // Localization::voxelizeCloud (:247-355; std::set<Vector3i> -> 64-bit key radix sort + unique) and
-// pcl::KdTreeFLANN::setInputCloud (src/agile_grasp/hand_search.cpp:10-11; kd-tree -> uniform hash
-// grid with z-contiguous cell runs).  All of it is HBM-streaming integer/byte work: one coalesced
-// pass per kernel, CUB only for the device-wide radix sort / scan / select primitives.
+// pcl::KdTreeFLANN::setInputCloud (src/agile_grasp/hand_search.cpp:10-11; kd-tree -> per-camera x-row
+// table over the already sorted voxel list, see ag_common.cuh).  All of it is HBM-streaming
+// integer/byte work: one coalesced pass per kernel, CUB only for the device-wide radix sort and
+// unique primitives.  Nothing here synchronises with the host: counts stay in device memory.
 
 #include <cub/cub.cuh>
 
@@ -27,8 +28,6 @@ struct KeyBits {
 
 struct PreState {
   int cam_min[2][3];  // ordered-int encoded float minima per camera
-  int bb_min[3];      // bounding box of the voxelised cloud (ordered ints)
-  int bb_max[3];
   int n_unique;       // output of DeviceSelect::Unique
   int n_vox;
   int key_overflow;
@@ -51,10 +50,6 @@ __global__ void k_init_state(PreState* st) {
   if (threadIdx.x == 0) {
     for (int c = 0; c < 2; c++)
       for (int a = 0; a < 3; a++) st->cam_min[c][a] = float_to_ordered(10000.0f);  // localization.cpp:251-252
-    for (int a = 0; a < 3; a++) {
-      st->bb_min[a] = 0x7FFFFFFF;
-      st->bb_max[a] = int(0x80000000);
-    }
     st->n_unique = 0;
     st->n_vox = 0;
     st->key_overflow = 0;
@@ -183,151 +178,208 @@ __global__ void k_keys(const char* pts, int stride, int n, const uint8_t* flag, 
             uint64_t(kz);
 }
 
-// voxel corner = (float)(k*cell + min) (localization.cpp:318-351), camera-0 voxels first (key order)
-__global__ void k_emit(const uint64_t* keys_unique, int n_cap, double cell, PreState* st, float4* vox, KeyBits kb) {
-  __shared__ int s_red[6][kBlock / 32];
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int nu = st->n_unique;
-  bool ok = i < nu && i < n_cap;
-  uint64_t key = ok ? keys_unique[i] : kInvalidKey;
-  ok = ok && key != kInvalidKey;
-  if (i == nu - 1) st->n_vox = (key == kInvalidKey) ? nu - 1 : nu;
-  float x = 0, y = 0, z = 0;
-  if (ok) {
-    int c = int((key >> (kb.bx + kb.by + kb.bz)) & 1u);
-    double kx = double((key >> (kb.by + kb.bz)) & ((1ull << kb.bx) - 1)), ky = double((key >> kb.bz) & ((1ull << kb.by) - 1)),
-           kz = double(key & ((1ull << kb.bz) - 1));
-    double mx = double(ordered_to_float(st->cam_min[c][0]));
-    double my = double(ordered_to_float(st->cam_min[c][1]));
-    double mz = double(ordered_to_float(st->cam_min[c][2]));
-    x = float(__dadd_rn(__dmul_rn(kx, cell), mx));  // two roundings, like the reference's SSE2 build
-    y = float(__dadd_rn(__dmul_rn(ky, cell), my));
-    z = float(__dadd_rn(__dmul_rn(kz, cell), mz));
-    vox[i] = make_float4(x, y, z, __int_as_float(c));
-  }
-  // bounding box for the hash grid: warp reduce -> shared -> one atomic per block and bound
-  int v[3] = {float_to_ordered(x), float_to_ordered(y), float_to_ordered(z)};
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-  for (int a = 0; a < 3; a++) {
-    const int lo = __reduce_min_sync(0xffffffffu, ok ? v[a] : 0x7FFFFFFF);
-    const int hi = __reduce_max_sync(0xffffffffu, ok ? v[a] : int(0x80000000));
-    if (lane == 0) {
-      s_red[a][w] = lo;
-      s_red[3 + a][w] = hi;
+// voxel corner = (float)(k*cell + min) (localization.cpp:318-351), camera-0 voxels first (key order);
+// the same pass fills the per-camera x-row table and the RowIndex descriptor.
+__global__ void k_emit(const uint64_t* keys_unique, int n_cap, double cell, PreState* st, GPoint* vox, KeyBits kb,
+                       RowIndex* ri, int* row_ptr, int row_stride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nu = min(st->n_unique, n_cap);
+  if (i >= nu) return;
+  const uint64_t key = keys_unique[i];
+  const int n_vox = (keys_unique[nu - 1] == kInvalidKey) ? nu - 1 : nu;  // the invalid key sorts last
+  if (i == 0) {
+    st->n_vox = n_vox;
+    ri->n_points = n_vox;
+    ri->inv_cell = 1.0 / cell;
+    ri->row_base[0] = 0;
+    ri->row_base[1] = row_stride;
+    for (int c = 0; c < 2; c++)
+      for (int a = 0; a < 3; a++) ri->mn[c][a] = double(ordered_to_float(st->cam_min[c][a]));
+    if (st->key_overflow) atomicOr(&ri->error, kErrKeyOverflow);
+    if (n_vox == 0) {
+      for (int c = 0; c < 2; c++) ri->nx[c] = ri->first[c] = ri->count[c] = 0;
     }
   }
-  __syncthreads();
-  if (threadIdx.x < 6) {
-    const int a = threadIdx.x;
-    int r = s_red[a][0];
-    for (int k = 1; k < kBlock / 32; k++) r = a < 3 ? min(r, s_red[a][k]) : max(r, s_red[a][k]);
-    if (a < 3) {
-      if (r != 0x7FFFFFFF) atomicMin(&st->bb_min[a], r);
-    } else {
-      if (r != int(0x80000000)) atomicMax(&st->bb_max[a - 3], r);
+  if (key == kInvalidKey) return;
+  const int sh_c = kb.bx + kb.by + kb.bz, sh_x = kb.by + kb.bz;
+  const int c = int((key >> sh_c) & 1u);
+  const int kxi = int((key >> sh_x) & ((1ull << kb.bx) - 1));
+  const double kx = double(kxi), ky = double((key >> kb.bz) & ((1ull << kb.by) - 1)),
+               kz = double(key & ((1ull << kb.bz) - 1));
+  const double mx = double(ordered_to_float(st->cam_min[c][0]));
+  const double my = double(ordered_to_float(st->cam_min[c][1]));
+  const double mz = double(ordered_to_float(st->cam_min[c][2]));
+  GPoint p;
+  p.x = float(__dadd_rn(__dmul_rn(kx, cell), mx));  // two roundings, like the reference's SSE2 build
+  p.y = float(__dadd_rn(__dmul_rn(ky, cell), my));
+  p.z = float(__dadd_rn(__dmul_rn(kz, cell), mz));
+  p.tag = c ? kTagCamBit : 0u;
+  vox[i] = p;
+  // x-row table: row_ptr[kx'] = i for every row kx' in (previous row, this row]
+  int prev_c = -1, prev_kx = -1;
+  if (i > 0) {
+    const uint64_t pk = keys_unique[i - 1];
+    prev_c = int((pk >> sh_c) & 1u);
+    prev_kx = int((pk >> sh_x) & ((1ull << kb.bx) - 1));
+  }
+  int* rows = row_ptr + c * row_stride;
+  if (prev_c != c) {
+    for (int k = 0; k <= kxi; k++) rows[k] = i;
+    ri->first[c] = i;
+    if (prev_c == 0) {  // camera 0 ended at i-1
+      ri->nx[0] = prev_kx + 1;
+      ri->count[0] = i;
+      row_ptr[prev_kx + 1] = i;
+    } else if (c == 1) {  // no camera-0 voxels at all
+      ri->nx[0] = 0;
+      ri->count[0] = 0;
+      ri->first[0] = 0;
+    }
+  } else if (prev_kx != kxi) {
+    for (int k = prev_kx + 1; k <= kxi; k++) rows[k] = i;
+  }
+  if (i == n_vox - 1) {  // last voxel closes its camera's table
+    rows[kxi + 1] = n_vox;
+    ri->nx[c] = kxi + 1;
+    int first_c = 0;
+    if (c == 1) {  // first camera-1 key (the boundary thread writes ri->first[1]; do not race on it)
+      int lo = 0, hi = n_vox;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((keys_unique[mid] >> sh_c) & 1u) hi = mid;
+        else lo = mid + 1;
+      }
+      first_c = lo;
+    }
+    ri->count[c] = n_vox - first_c;
+    if (c == 0) {
+      ri->nx[1] = 0;
+      ri->count[1] = 0;
+      ri->first[1] = n_vox;
     }
   }
 }
 
-__global__ void k_bbox(const float4* vox, int n, PreState* st) {  // for ag_set_cloud (cloud given directly)
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool ok = i < n;
-  float4 p = ok ? vox[i] : make_float4(0, 0, 0, 0);
-  int v[3] = {float_to_ordered(p.x), float_to_ordered(p.y), float_to_ordered(p.z)};
-#pragma unroll
-  for (int a = 0; a < 3; a++) {
-    int lo = __reduce_min_sync(0xffffffffu, ok ? v[a] : 0x7FFFFFFF);
-    int hi = __reduce_max_sync(0xffffffffu, ok ? v[a] : int(0x80000000));
-    if ((threadIdx.x & 31) == 0) {
-      atomicMin(&st->bb_min[a], lo);
-      atomicMax(&st->bb_max[a], hi);
-    }
-  }
-}
-
-// ---- hash grid ------------------------------------------------------------------------------
-__global__ void k_cell_ids(const float4* vox, int n, GridDesc g, uint32_t* cell_ids, int* perm, int* cell_count) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+// cloud supplied directly (ag_set_cloud): the caller's order is kept as the API index space, and the
+// x-row table is built over an x-sorted COPY of it?  No — the walkers need rows contiguous in the point
+// array itself, so the supplied cloud must already be in voxel order (it is when it comes from
+// ag_preprocess or from the oracle's preprocess, which is how every caller obtains it).  The kernel
+// below derives the lattice rows from the coordinates and flags a cloud that is not row-sorted.
+__global__ void k_index_cloud(const GPoint* vox, int n, double cell, RowIndex* ri, int* row_ptr, int row_stride,
+                              int* sorted_ok) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float4 p = vox[i];
-  int cx = cell_of(double(p.x), g.gmin[0], g.inv_cell, g.dim[0]);
-  int cy = cell_of(double(p.y), g.gmin[1], g.inv_cell, g.dim[1]);
-  int cz = cell_of(double(p.z), g.gmin[2], g.inv_cell, g.dim[2]);
-  int lin = (cx * g.dim[1] + cy) * g.dim[2] + cz;
-  cell_ids[i] = uint32_t(lin);
-  perm[i] = i;
-  atomicAdd(&cell_count[lin], 1);
+  const GPoint p = vox[i];
+  const int c = (p.tag & kTagCamBit) ? 1 : 0;
+  const double mx = ri->mn[c][0];
+  const int kxi = int(floor((double(p.x) - mx) / cell + 0.5));
+  int prev_c = -1, prev_kx = -1;
+  float prev_y = 0.f;
+  if (i > 0) {
+    const GPoint q = vox[i - 1];
+    prev_c = (q.tag & kTagCamBit) ? 1 : 0;
+    prev_kx = int(floor((double(q.x) - ri->mn[prev_c][0]) / cell + 0.5));
+    prev_y = q.y;
+  }
+  if (prev_c > c || (prev_c == c && (prev_kx > kxi || (prev_kx == kxi && prev_y > p.y)))) *sorted_ok = 0;
+  if (kxi < 0 || kxi >= row_stride - 1) {
+    *sorted_ok = 0;
+    return;
+  }
+  int* rows = row_ptr + c * row_stride;
+  if (prev_c != c) {
+    for (int k = 0; k <= kxi; k++) rows[k] = i;
+    ri->first[c] = i;
+    if (prev_c == 0) {
+      ri->nx[0] = prev_kx + 1;
+      ri->count[0] = i;
+      row_ptr[prev_kx + 1] = i;
+    } else if (c == 1) {
+      ri->nx[0] = 0;
+      ri->count[0] = 0;
+      ri->first[0] = 0;
+    }
+  } else if (prev_kx != kxi) {
+    for (int k = prev_kx + 1; k <= kxi; k++) rows[k] = i;
+  }
+  if (i == n - 1) {
+    rows[kxi + 1] = n;
+    ri->nx[c] = kxi + 1;
+    ri->count[c] = n - ri->first[c];
+    if (c == 0) {
+      ri->nx[1] = 0;
+      ri->count[1] = 0;
+      ri->first[1] = n;
+    }
+  }
 }
 
-__global__ void k_gather(const float4* vox, const int* perm_sorted, int n, GPoint* pts, int* inv) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  int src = perm_sorted[j];
-  float4 p = vox[src];
-  GPoint q;
-  q.x = p.x; q.y = p.y; q.z = p.z;
-  q.tag = uint32_t(src) | (__float_as_int(p.w) ? kTagCamBit : 0u);
-  pts[j] = q;
-  inv[src] = j;
+// per-camera minima of a supplied cloud (lattice origin of each camera)
+__global__ void k_cloud_min(const GPoint* vox, int n, PreState* st) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool ok = i < n;
+  GPoint p;
+  p.x = p.y = p.z = 0.f;
+  p.tag = 0;
+  if (ok) p = vox[i];
+  const int ov[3] = {float_to_ordered(p.x), float_to_ordered(p.y), float_to_ordered(p.z)};
+  for (int c = 0; c < 2; c++) {
+    const bool mine = ok && ((p.tag & kTagCamBit) ? 1 : 0) == c;
+    for (int a = 0; a < 3; a++) {
+      const int r = __reduce_min_sync(0xffffffffu, mine ? ov[a] : 0x7FFFFFFF);
+      if ((threadIdx.x & 31) == 0 && r != 0x7FFFFFFF) atomicMin(&st->cam_min[c][a], r);
+    }
+  }
+}
+__global__ void k_cloud_desc(PreState* st, RowIndex* ri, int n, double cell, int row_stride) {
+  ri->n_points = n;
+  ri->inv_cell = 1.0 / cell;
+  ri->row_base[0] = 0;
+  ri->row_base[1] = row_stride;
+  for (int c = 0; c < 2; c++) {
+    for (int a = 0; a < 3; a++) ri->mn[c][a] = double(ordered_to_float(st->cam_min[c][a]));
+    ri->nx[c] = ri->first[c] = ri->count[c] = 0;
+  }
+  st->n_vox = n;
+}
+
+__global__ void k_radius_search(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr, const RowIndex* rip,
+                                float qx, float qy, float qz, float r2, double rpad, int* out, int* out_count, int cap) {
+  __shared__ int s_rs[256], s_pre[257];
+  const RowIndex ri = *rip;
+  int row_off = 0;
+  bool more = true;
+  while (more) {
+    const int nr = build_runs_warp(ri, row_ptr, pts, qx, qy, rpad, s_rs, s_pre, 256, row_off, more);
+    row_off += nr;
+    for (int r = 0; r < nr; r++)
+      for (int j = s_rs[r] + int(threadIdx.x); j < s_rs[r] + (s_pre[r + 1] - s_pre[r]); j += 32) {
+        const GPoint p = pts[j];
+        if (dist2_flann(qx, qy, qz, p.x, p.y, p.z) < r2) {
+          const int k = atomicAdd(out_count, 1);
+          if (k < cap) out[k] = j;
+        }
+      }
+    __syncwarp();
+  }
 }
 
 }  // namespace
 
 static PreState* state_ptr(Ctx* c) { return c->misc.as<PreState>(); }
 
-static int finish_cloud(Ctx* c, bool have_bbox_on_device) {
-  // read N and the bounding box back (the only host sync of the preprocessing stage)
-  PreState hs;
-  AG_CUDA_CHECK(cudaMemcpyAsync(&hs, state_ptr(c), sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
-  AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  if (hs.key_overflow) {
-    set_error("voxel index exceeds the key range (workspace extent / voxel_size > 2^21 cells, or a point lies "
-              "outside the workspace box it passed)");
-    return AG_ERR_CAPACITY;
-  }
-  (void)have_bbox_on_device;
-  c->n_vox = hs.n_vox;
-  if (c->n_vox <= 0) {
-    c->n_vox = 0;
-    return AG_OK;
-  }
-  GridDesc& g = c->grid;
-  double lo[3], hi[3];
-  for (int a = 0; a < 3; a++) {
-    lo[a] = double(ordered_to_float(hs.bb_min[a]));
-    hi[a] = double(ordered_to_float(hs.bb_max[a]));
-  }
-  // cell edge ~ the Taubin radius: a radius-r query touches <=3 cells per axis, the r=0.08 hand
-  // query <=7.  Grow the cell until the dense cell table stays below 16M entries.
-  double cell = c->params.nn_radius_taubin * 1.001;
-  if (!(cell > 1e-6)) cell = 0.03;
-  for (;;) {
-    double total = 1;
-    for (int a = 0; a < 3; a++) {
-      g.dim[a] = int(floor((hi[a] - lo[a]) / cell)) + 1;
-      total *= double(g.dim[a]);
-    }
-    if (total <= double(1 << 24)) break;
-    cell *= 1.26;
-  }
-  for (int a = 0; a < 3; a++) g.gmin[a] = lo[a];
-  g.inv_cell = 1.0 / cell;
-  g.n_points = c->n_vox;
-  return AG_OK;
+static int row_stride_for(const ag_params& P, int* bx_out) {
+  // rows per camera: workspace extent / voxel (+2), rounded up to the key bit budget
+  const double cells = floor((P.workspace[1] - P.workspace[0]) / P.voxel_size) + 2.0;
+  int bits = 1;
+  while (bits < 21 && double(1u << bits) - 1.0 <= cells) bits++;
+  if (bx_out) *bx_out = bits;
+  return (1 << bits) + 2;
 }
 
 int preprocess_device(Ctx* c, const void* d_points, int stride, int n_in, int size_left) {
   const ag_params& P = c->params;
   const int nb = (n_in + kBlock - 1) / kBlock;
-  if (c->misc.reserve(sizeof(PreState)) || c->keys.reserve(size_t(n_in) * 8) || c->keys_sorted.reserve(size_t(n_in) * 8) ||
-      c->keys_unique.reserve(size_t(n_in) * 8) || c->block_counts.reserve(size_t(nb) * 4 + size_t(n_in)) ||
-      c->vox.reserve(size_t(n_in) * 16))
-    return AG_ERR_CUDA;
-  PreState* st = state_ptr(c);
-  int* d_block = c->block_counts.as<int>();
-  uint8_t* d_flag = reinterpret_cast<uint8_t*>(d_block + nb);
-  const char* pts = static_cast<const char*>(d_points);
   KeyBits kb;
   {
     int* b[3] = {&kb.bx, &kb.by, &kb.bz};
@@ -339,6 +391,18 @@ int preprocess_device(Ctx* c, const void* d_points, int stride, int n_in, int si
     }
     kb.total = 1 + kb.bx + kb.by + kb.bz;
   }
+  const int row_stride = (1 << kb.bx) + 2;
+  if (c->misc.reserve(sizeof(PreState)) || c->keys.reserve(size_t(n_in) * 8) || c->keys_sorted.reserve(size_t(n_in) * 8) ||
+      c->keys_unique.reserve(size_t(n_in) * 8) || c->block_counts.reserve(size_t(nb) * 4 + size_t(n_in)) ||
+      c->vox.reserve(size_t(n_in) * 16) || c->row_ptr.reserve(size_t(row_stride) * 2 * 4) ||
+      c->row_index.reserve(sizeof(RowIndex)) || c->normals.reserve(size_t(n_in) * 24))
+    return AG_ERR_CUDA;
+  c->n_cap = n_in;
+  PreState* st = state_ptr(c);
+  int* d_block = c->block_counts.as<int>();
+  uint8_t* d_flag = reinterpret_cast<uint8_t*>(d_block + nb);
+  const char* pts = static_cast<const char*>(d_points);
+  AG_CUDA_CHECK(cudaMemsetAsync(c->row_index.p, 0, sizeof(RowIndex), c->stream));
   k_init_state<<<1, 32, 0, c->stream>>>(st);
   const bool quirk = !P.fix_cam_source && size_left < n_in;
   if (quirk) {
@@ -354,89 +418,70 @@ int preprocess_device(Ctx* c, const void* d_points, int stride, int n_in, int si
                                  kb.total, c->stream);
   cub::DeviceSelect::Unique(nullptr, tmp2, c->keys_sorted.as<uint64_t>(), c->keys_unique.as<uint64_t>(),
                             &st->n_unique, n_in, c->stream);
-  size_t tmp = tmp1 > tmp2 ? tmp1 : tmp2;
-  if (c->cub_tmp.reserve(tmp)) return AG_ERR_CUDA;
+  if (c->cub_tmp.reserve(tmp1 > tmp2 ? tmp1 : tmp2)) return AG_ERR_CUDA;
   AG_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(c->cub_tmp.p, tmp1, c->keys.as<uint64_t>(),
                                                c->keys_sorted.as<uint64_t>(), n_in, 0, kb.total, c->stream));
   AG_CUDA_CHECK(cub::DeviceSelect::Unique(c->cub_tmp.p, tmp2, c->keys_sorted.as<uint64_t>(),
                                           c->keys_unique.as<uint64_t>(), &st->n_unique, n_in, c->stream));
   c->launches += quirk ? 6 : 4;  // init, [count, scan], classify, keys, emit (CUB kernels not counted)
-  k_emit<<<nb, kBlock, 0, c->stream>>>(c->keys_unique.as<uint64_t>(), n_in, P.voxel_size, st, c->vox.as<float4>(), kb);
-  AG_CUDA_CHECK(cudaGetLastError());
-  return finish_cloud(c, true);
-}
-
-// cloud supplied directly (already voxelised): c->vox holds n float4 records
-int set_cloud_device(Ctx* c, int n) {
-  if (c->misc.reserve(sizeof(PreState))) return AG_ERR_CUDA;
-  PreState* st = state_ptr(c);
-  k_init_state<<<1, 32, 0, c->stream>>>(st);
-  if (n > 0) k_bbox<<<(n + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(c->vox.as<float4>(), n, st);
-  PreState tmp;
-  (void)tmp;
-  // n_vox is known on the host here
-  int* d_nvox = &st->n_vox;
-  AG_CUDA_CHECK(cudaMemcpyAsync(d_nvox, &n, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  AG_CUDA_CHECK(cudaGetLastError());
-  return finish_cloud(c, true);
-}
-
-int build_grid(Ctx* c) {
-  const int n = c->n_vox;
-  if (n <= 0) return AG_OK;
-  GridDesc& g = c->grid;
-  const size_t ncells = size_t(g.dim[0]) * g.dim[1] * g.dim[2];
-  if (c->cell_ids.reserve(size_t(n) * 4) || c->cell_ids_sorted.reserve(size_t(n) * 4) || c->perm.reserve(size_t(n) * 4) ||
-      c->perm_sorted.reserve(size_t(n) * 4) || c->cell_start.reserve((ncells + 1) * 2 * sizeof(int)) ||
-      c->pts.reserve(size_t(n) * sizeof(GPoint)) || c->inv.reserve(size_t(n) * 4))
-    return AG_ERR_CUDA;
-  int* cell_count = c->cell_start.as<int>() + (ncells + 1);
-  int* cell_start = c->cell_start.as<int>();
-  AG_CUDA_CHECK(cudaMemsetAsync(cell_count, 0, (ncells + 1) * sizeof(int), c->stream));
-  const int nb = (n + kBlock - 1) / kBlock;
-  k_cell_ids<<<nb, kBlock, 0, c->stream>>>(c->vox.as<float4>(), n, g, c->cell_ids.as<uint32_t>(), c->perm.as<int>(),
-                                           cell_count);
-  int bits = 1;
-  while ((size_t(1) << bits) < ncells) bits++;
-  size_t tmp1 = 0, tmp2 = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp1, cell_count, cell_start, int(ncells + 1), c->stream);
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp2, c->cell_ids.as<uint32_t>(), c->cell_ids_sorted.as<uint32_t>(),
-                                  c->perm.as<int>(), c->perm_sorted.as<int>(), n, 0, bits, c->stream);
-  if (c->cub_tmp.reserve(tmp1 > tmp2 ? tmp1 : tmp2)) return AG_ERR_CUDA;
-  AG_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp1, cell_count, cell_start, int(ncells + 1), c->stream));
-  AG_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp2, c->cell_ids.as<uint32_t>(),
-                                                c->cell_ids_sorted.as<uint32_t>(), c->perm.as<int>(),
-                                                c->perm_sorted.as<int>(), n, 0, bits, c->stream));
-  c->launches += 2;  // cell_ids, gather
-  k_gather<<<nb, kBlock, 0, c->stream>>>(c->vox.as<float4>(), c->perm_sorted.as<int>(), n, c->pts.as<GPoint>(),
-                                         c->inv.as<int>());
+  k_emit<<<nb, kBlock, 0, c->stream>>>(c->keys_unique.as<uint64_t>(), n_in, P.voxel_size, st, c->vox.as<GPoint>(), kb,
+                                       c->row_index.as<RowIndex>(), c->row_ptr.as<int>(), row_stride);
   // cloud_normals_ is zeroed on every call (hand_search.cpp:13-14)
-  if (c->normals.reserve(size_t(n) * 3 * sizeof(double))) return AG_ERR_CUDA;
-  AG_CUDA_CHECK(cudaMemsetAsync(c->normals.p, 0, size_t(n) * 3 * sizeof(double), c->stream));
+  AG_CUDA_CHECK(cudaMemsetAsync(c->normals.p, 0, size_t(n_in) * 24, c->stream));
   AG_CUDA_CHECK(cudaGetLastError());
   return AG_OK;
 }
 
-// ---- brute radius search through the grid (stage-level API / tests) ---------------------------
-namespace {
-__global__ void k_radius_search(const GPoint* __restrict__ pts, const int* __restrict__ cell_start, GridDesc g,
-                                float qx, float qy, float qz, float r2, double rpad, int* out, int* out_count, int cap) {
-  QueryBox b = query_box(g, qx, qy, qz, rpad);
-  int ncx = b.hi[0] - b.lo[0] + 1, ncy = b.hi[1] - b.lo[1] + 1;
-  for (int col = blockIdx.x; col < ncx * ncy; col += gridDim.x) {
-    int cx = b.lo[0] + col / ncy, cy = b.lo[1] + col % ncy;
-    int s = cell_start[cell_linear(g, cx, cy, b.lo[2])];
-    int e = cell_start[cell_linear(g, cx, cy, b.hi[2]) + 1];
-    for (int j = s + threadIdx.x; j < e; j += blockDim.x) {
-      GPoint p = pts[j];
-      if (dist2_flann(qx, qy, qz, p.x, p.y, p.z) < r2) {
-        int k = atomicAdd(out_count, 1);
-        if (k < cap) out[k] = int(p.tag & kTagIndexMask);
-      }
-    }
+// reads the voxel count (and device-side error flags) back: the one place that waits for the GPU
+int fetch_cloud_size(Ctx* c) {
+  RowIndex hri;
+  AG_CUDA_CHECK(cudaMemcpyAsync(&hri, c->row_index.p, sizeof(hri), cudaMemcpyDeviceToHost, c->stream));
+  AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  c->n_vox = hri.n_points;
+  if (hri.error & kErrKeyOverflow) {
+    set_error("voxel index exceeds the key range (workspace extent / voxel_size > 2^21 cells)");
+    return AG_ERR_CAPACITY;
   }
+  return AG_OK;
 }
-}  // namespace
+
+// cloud supplied directly (already voxelised, in voxel order): c->vox holds n records
+int set_cloud_device(Ctx* c, int n) {
+  const ag_params& P = c->params;
+  int bx = 0;
+  int row_stride = row_stride_for(P, &bx);
+  if (c->misc.reserve(sizeof(PreState) + 16) || c->row_ptr.reserve(size_t(row_stride) * 2 * 4) ||
+      c->row_index.reserve(sizeof(RowIndex)) || c->normals.reserve(std::max<size_t>(24, size_t(n) * 24)))
+    return AG_ERR_CUDA;
+  c->n_cap = n;
+  c->n_vox = n;
+  PreState* st = state_ptr(c);
+  int* d_ok = reinterpret_cast<int*>(st + 1);
+  const int one = 1;
+  AG_CUDA_CHECK(cudaMemsetAsync(c->row_index.p, 0, sizeof(RowIndex), c->stream));
+  AG_CUDA_CHECK(cudaMemcpyAsync(d_ok, &one, 4, cudaMemcpyHostToDevice, c->stream));
+  k_init_state<<<1, 32, 0, c->stream>>>(st);
+  if (n > 0) {
+    const int nb = (n + kBlock - 1) / kBlock;
+    k_cloud_min<<<nb, kBlock, 0, c->stream>>>(c->vox.as<GPoint>(), n, st);
+    k_cloud_desc<<<1, 1, 0, c->stream>>>(st, c->row_index.as<RowIndex>(), n, P.voxel_size, row_stride);
+    k_index_cloud<<<nb, kBlock, 0, c->stream>>>(c->vox.as<GPoint>(), n, P.voxel_size, c->row_index.as<RowIndex>(),
+                                                c->row_ptr.as<int>(), row_stride, d_ok);
+  } else {
+    k_cloud_desc<<<1, 1, 0, c->stream>>>(st, c->row_index.as<RowIndex>(), 0, P.voxel_size, row_stride);
+  }
+  AG_CUDA_CHECK(cudaMemsetAsync(c->normals.p, 0, std::max<size_t>(24, size_t(n) * 24), c->stream));
+  int ok = 1;
+  AG_CUDA_CHECK(cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, c->stream));
+  AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  AG_CUDA_CHECK(cudaGetLastError());
+  if (!ok) {
+    set_error("ag_set_cloud: the cloud is not in voxel order (per camera sorted by x, then y, on the voxel lattice, "
+              "inside the workspace): pass a cloud produced by ag_preprocess");
+    return AG_ERR_INVALID;
+  }
+  return AG_OK;
+}
 
 int radius_search_device(Ctx* c, const float q[3], double radius, std::vector<int>& out) {
   out.clear();
@@ -449,8 +494,8 @@ int radius_search_device(Ctx* c, const float q[3], double radius, std::vector<in
   cudaMemsetAsync(d_cnt, 0, 4, c->stream);
   float r2 = float(radius * radius);
   double rpad = sqrt(double(r2)) * (1.0 + 1e-5) + 1e-7;
-  k_radius_search<<<64, 128, 0, c->stream>>>(c->pts.as<GPoint>(), c->cell_start.as<int>(), c->grid, q[0], q[1], q[2], r2,
-                                             rpad, d_out, d_cnt, cap);
+  k_radius_search<<<1, 32, 0, c->stream>>>(c->vox.as<GPoint>(), c->row_ptr.as<int>(), c->row_index.as<RowIndex>(), q[0],
+                                           q[1], q[2], r2, rpad, d_out, d_cnt, cap);
   int cnt = 0;
   cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, c->stream);
   cudaError_t e = cudaStreamSynchronize(c->stream);

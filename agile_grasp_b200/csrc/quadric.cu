@@ -55,93 +55,104 @@ __constant__ int c_basis[10][3] = {{2, 0, 0}, {0, 2, 0}, {0, 0, 2}, {1, 1, 0}, {
                                    {1, 0, 1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 0, 0}};
 
 // ---- warp-level ball walk with compaction ----------------------------------------------------
-// Calls f(point, active) with all 32 lanes converged; `active` lanes hold distinct accepted
-// neighbours.  Batches are full (32 active) except the last one.
+// The query's candidate runs (one per x-row, see ag_common.cuh) are flattened into one index space
+// and streamed 64 candidates at a time (two independent 16-byte loads in flight per lane); accepted
+// points are compacted through a 64-entry shared ring so that f(point, active) always sees full
+// batches of 32 (except the last).  The ring entry's tag is (point index << 2) | (tag bits).
+constexpr int kRunCap = 128;
+struct RunList {
+  int rs[kRunCap];
+  int pre[kRunCap + 1];
+};
+
 template <typename F>
-__device__ __forceinline__ void walk_ball(const GPoint* __restrict__ pts, const int* __restrict__ cell_start,
-                                          const GridDesc& g, float qx, float qy, float qz, float r2, double rpad,
-                                          GPoint* ring /*64 entries, this warp's*/, int& n_cand, F&& f) {
+__device__ __forceinline__ void walk_runs(const GPoint* __restrict__ pts, const RunList& rl, int n_runs, float qx,
+                                          float qy, float qz, float r2, GPoint* ring, F&& f) {
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
-  const QueryBox b = query_box(g, qx, qy, qz, rpad);
-  const int ncy = b.hi[1] - b.lo[1] + 1;
-  const int ncol = (b.hi[0] - b.lo[0] + 1) * ncy;
-  int head = 0, qn = 0;
+  const int total = rl.pre[n_runs];
+  int head = 0, qn = 0, cur = 0;
   auto push = [&](const GPoint& p, bool ok) {
-    unsigned m = __ballot_sync(0xffffffffu, ok);
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
     if (m == 0) return;
     if (ok) ring[(head + qn + __popc(m & lt)) & 63] = p;
     qn += __popc(m);
     __syncwarp();
     if (qn >= 32) {
-      GPoint v = ring[(head + lane) & 63];
+      const GPoint v = ring[(head + lane) & 63];
       __syncwarp();
       f(v, true);
       head = (head + 32) & 63;
       qn -= 32;
     }
   };
-  for (int cbase = 0; cbase < ncol; cbase += 32) {
-    const int col = cbase + lane;
-    int s = 0, e = 0;
-    if (col < ncol) {
-      const int cx = b.lo[0] + col / ncy, cy = b.lo[1] + col % ncy;
-      s = __ldg(cell_start + cell_linear(g, cx, cy, b.lo[2]));
-      e = __ldg(cell_start + cell_linear(g, cx, cy, b.hi[2]) + 1);
-    }
-    const int ncur = min(32, ncol - cbase);
-    for (int k = 0; k < ncur; k++) {
-      const int rs = __shfl_sync(0xffffffffu, s, k), re = __shfl_sync(0xffffffffu, e, k);
-      n_cand += re - rs;
-      for (int j0 = rs; j0 < re; j0 += 64) {
-        const int ja = j0 + lane, jb = ja + 32;
-        GPoint pa, pb;
-        pa.x = pa.y = pa.z = 0.f; pa.tag = 0;
-        pb = pa;
-        if (ja < re) pa = pts[ja];
-        if (jb < re) pb = pts[jb];
-        push(pa, ja < re && dist2_flann(qx, qy, qz, pa.x, pa.y, pa.z) < r2);
-        if (j0 + 32 < re) push(pb, jb < re && dist2_flann(qx, qy, qz, pb.x, pb.y, pb.z) < r2);
+  for (int base = 0; base < total; base += 64) {
+    GPoint p[2];
+    bool valid[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int pos = base + u * 32 + lane;
+      valid[u] = pos < total;
+      p[u].x = p[u].y = p[u].z = 0.f;
+      p[u].tag = 0;
+      if (valid[u]) {
+        while (pos >= rl.pre[cur + 1]) cur++;
+        const int j = rl.rs[cur] + (pos - rl.pre[cur]);
+        p[u] = pts[j];
+        p[u].tag = (uint32_t(j) << 2) | (p[u].tag & 3u);
       }
     }
+    push(p[0], valid[0] && dist2_flann(qx, qy, qz, p[0].x, p[0].y, p[0].z) < r2);
+    if (base + 32 < total) push(p[1], valid[1] && dist2_flann(qx, qy, qz, p[1].x, p[1].y, p[1].z) < r2);
   }
   if (qn > 0) {
-    GPoint v = ring[(head + lane) & 63];
+    const GPoint v = ring[(head + lane) & 63];
     __syncwarp();
     f(v, lane < qn);
   }
+  __syncwarp();
 }
 
 // ---- kernel 1: moments ------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWarps * 32, 4)
-k_taubin_moments(const GPoint* __restrict__ pts, const int* __restrict__ cell_start, GridDesc g,
-                 const float4* __restrict__ vox, const int* __restrict__ indices, int n_samples, float r2,
-                 double rpad, double inv_r, double* __restrict__ moments, int* __restrict__ nn_counts,
-                 unsigned long long* __restrict__ counters) {
+k_taubin_moments(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr, const RowIndex* __restrict__ rip,
+                 const int* __restrict__ indices, int n_samples_max, const int* __restrict__ d_count, float r2,
+                 double rpad, double inv_r, double* __restrict__ moments, int* __restrict__ nn_counts, unsigned long long* __restrict__ counters) {
   __shared__ GPoint s_ring[kWarps][64];
+  __shared__ RunList s_runs[kWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * kWarps + warp;
-  if (s >= n_samples) return;
-  const float4 q = vox[indices[s]];
+  const RowIndex ri = *rip;
+  if (s >= n_samples_max || s >= *d_count) return;
+  const int idx = indices[s];
+  if (idx < 0 || idx >= ri.n_points) return;
+  const GPoint q = pts[idx];
   const double qx = double(q.x), qy = double(q.y), qz = double(q.z);
   double acc[kNumMoments];
 #pragma unroll
   for (int i = 0; i < kNumMoments; i++) acc[i] = 0.0;
-  int cam1 = 0, n_cand = 0;
-  walk_ball(pts, cell_start, g, q.x, q.y, q.z, r2, rpad, s_ring[warp], n_cand, [&](const GPoint& p, bool active) {
-    if (!active) return;
-    const double x = (double(p.x) - qx) * inv_r, y = (double(p.y) - qy) * inv_r, z = (double(p.z) - qz) * inv_r;
-    const double x2 = x * x, y2 = y * y, z2 = z * z, xy = x * y, yz = y * z, xz = x * z;
-    acc[0] += 1.0;
-    acc[1] += x; acc[2] += y; acc[3] += z;
-    acc[4] += x2; acc[5] += y2; acc[6] += z2; acc[7] += xy; acc[8] += yz; acc[9] += xz;
-    acc[10] += x2 * x; acc[11] += y2 * y; acc[12] += z2 * z; acc[13] += x2 * y; acc[14] += x2 * z;
-    acc[15] += x * y2; acc[16] += y2 * z; acc[17] += x * z2; acc[18] += y * z2; acc[19] += xy * z;
-    acc[20] += x2 * x2; acc[21] += y2 * y2; acc[22] += z2 * z2; acc[23] += x2 * xy; acc[24] += x2 * xz;
-    acc[25] += xy * y2; acc[26] += y2 * yz; acc[27] += xz * z2; acc[28] += yz * z2; acc[29] += x2 * y2;
-    acc[30] += y2 * z2; acc[31] += x2 * z2; acc[32] += x2 * yz; acc[33] += xy * yz; acc[34] += xz * yz;
-    cam1 += (p.tag & kTagCamBit) ? 1 : 0;
-  });
+  int cam1 = 0, n_cand = 0, row_off = 0;
+  bool more = true;
+  while (more) {
+    const int nr = build_runs_warp(ri, row_ptr, pts, q.x, q.y, rpad, s_runs[warp].rs, s_runs[warp].pre, kRunCap,
+                                   row_off, more);
+    row_off += nr;
+    n_cand += s_runs[warp].pre[nr];
+    walk_runs(pts, s_runs[warp], nr, q.x, q.y, q.z, r2, s_ring[warp], [&](const GPoint& p, bool active) {
+      if (!active) return;
+      const double x = (double(p.x) - qx) * inv_r, y = (double(p.y) - qy) * inv_r, z = (double(p.z) - qz) * inv_r;
+      const double x2 = x * x, y2 = y * y, z2 = z * z, xy = x * y, yz = y * z, xz = x * z;
+      acc[0] += 1.0;
+      acc[1] += x; acc[2] += y; acc[3] += z;
+      acc[4] += x2; acc[5] += y2; acc[6] += z2; acc[7] += xy; acc[8] += yz; acc[9] += xz;
+      acc[10] += x2 * x; acc[11] += y2 * y; acc[12] += z2 * z; acc[13] += x2 * y; acc[14] += x2 * z;
+      acc[15] += x * y2; acc[16] += y2 * z; acc[17] += x * z2; acc[18] += y * z2; acc[19] += xy * z;
+      acc[20] += x2 * x2; acc[21] += y2 * y2; acc[22] += z2 * z2; acc[23] += x2 * xy; acc[24] += x2 * xz;
+      acc[25] += xy * y2; acc[26] += y2 * yz; acc[27] += xz * z2; acc[28] += yz * z2; acc[29] += x2 * y2;
+      acc[30] += y2 * z2; acc[31] += x2 * z2; acc[32] += x2 * yz; acc[33] += xy * yz; acc[34] += xz * yz;
+      cam1 += (p.tag & kTagCamBit) ? 1 : 0;
+    });
+  }
 #pragma unroll
   for (int i = 0; i < kNumMoments; i++) acc[i] = warp_sum(acc[i]);
   cam1 = __reduce_add_sync(0xffffffffu, cam1);
@@ -167,6 +178,7 @@ struct AxesSmem {
   double par[10]; // quadric parameters in centred/scaled coordinates
   double T[28];   // weighted order-6 normal tensor
   GPoint ring[64];
+  RunList runs;
 };
 
 // Jacobi rotation (c, s) annihilating a_pq, the small-angle root (|angle| <= pi/4), computed without
@@ -347,19 +359,21 @@ __constant__ double c_multinomial6[28] = {
 
 // ---- kernel 2: eigen-solve + local axes -------------------------------------------------------
 __global__ void __launch_bounds__(kWarps * 32, 4)
-k_taubin_axes(const GPoint* __restrict__ pts_c, const int* __restrict__ cell_start, GridDesc g,
-              const float4* __restrict__ vox, const int* __restrict__ indices,
-              int n_samples, float r2, double rpad, double inv_r, const double* __restrict__ moments,
+k_taubin_axes(const GPoint* __restrict__ pts_c, const int* __restrict__ row_ptr, const RowIndex* __restrict__ rip,
+              const int* __restrict__ indices, int n_samples_max, const int* __restrict__ d_count,
+              float r2, double rpad, double inv_r, const double* __restrict__ moments,
               double cam0x, double cam0y, double cam0z, double cam1x, double cam1y, double cam1z,
               ag_frame* __restrict__ frames, double* normals_out /* may be null */) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   AxesSmem* sm_all = reinterpret_cast<AxesSmem*>(s_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * kWarps + warp;
-  if (s >= n_samples) return;
+  const RowIndex ri = *rip;
+  if (s >= n_samples_max || s >= *d_count) return;
   AxesSmem& sm = sm_all[warp];
   const int idx = indices[s];
-  const float4 q = vox[idx];
+  if (idx < 0 || idx >= ri.n_points) return;
+  const GPoint q = pts_c[idx];
   const double qx = double(q.x), qy = double(q.y), qz = double(q.z);
   const double* mom = moments + size_t(s) * kMomentStride;
   const double n = mom[0];
@@ -552,18 +566,26 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const int* __restrict__ cell_sta
   double acc[34];
 #pragma unroll
   for (int i = 0; i < 34; i++) acc[i] = 0.0;
-  int n_cand = 0;
-  walk_ball(pts_c, cell_start, g, q.x, q.y, q.z, r2, rpad, sm.ring, n_cand, [&](const GPoint& p, bool active) {
-    if (!active) return;
-    const double x = (double(p.x) - qx) * inv_r, y = (double(p.y) - qy) * inv_r, z = (double(p.z) - qz) * inv_r;
-    double gn[3], m6[28];
-    quad_normal(par, x, y, z, gn);
-    acc[0] += gn[0] * gn[0]; acc[1] += gn[1] * gn[1]; acc[2] += gn[2] * gn[2];
-    acc[3] += gn[0] * gn[1]; acc[4] += gn[1] * gn[2]; acc[5] += gn[0] * gn[2];
-    monomials6(gn, m6);
+  // the run list of this ball is built once and reused by both walks (queries touching more than
+  // kRunCap rows are walked in batches)
+  int nr = 0, row_off = 0;
+  bool more = true;
+  while (more) {
+    nr = build_runs_warp(ri, row_ptr, pts_c, q.x, q.y, rpad, sm.runs.rs, sm.runs.pre, kRunCap, row_off, more);
+    row_off += nr;
+    walk_runs(pts_c, sm.runs, nr, q.x, q.y, q.z, r2, sm.ring, [&](const GPoint& p, bool active) {
+      if (!active) return;
+      const double x = (double(p.x) - qx) * inv_r, y = (double(p.y) - qy) * inv_r, z = (double(p.z) - qz) * inv_r;
+      double gn[3], m6[28];
+      quad_normal(par, x, y, z, gn);
+      acc[0] += gn[0] * gn[0]; acc[1] += gn[1] * gn[1]; acc[2] += gn[2] * gn[2];
+      acc[3] += gn[0] * gn[1]; acc[4] += gn[1] * gn[2]; acc[5] += gn[0] * gn[2];
+      monomials6(gn, m6);
 #pragma unroll
-    for (int t = 0; t < 28; t++) acc[6 + t] += m6[t];
-  });
+      for (int t = 0; t < 28; t++) acc[6 + t] += m6[t];
+    });
+  }
+  const bool single_batch = row_off == nr;  // the common case: the list in shared memory is complete
 #pragma unroll
   for (int i = 0; i < 34; i++) acc[i] = warp_sum(acc[i]);
   double w3[3], V3[3][3];
@@ -580,23 +602,32 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const int* __restrict__ cell_sta
   float bestD = 3.0e38f;
   unsigned bestI = 0xFFFFFFFFu;
   double bestG[3] = {0, 0, 0};
-  walk_ball(pts_c, cell_start, g, q.x, q.y, q.z, r2, rpad, sm.ring, n_cand, [&](const GPoint& p, bool active) {
-    if (!active) return;
-    const double x = (double(p.x) - qx) * inv_r, y = (double(p.y) - qy) * inv_r, z = (double(p.z) - qz) * inv_r;
-    double gn[3], m6[28];
-    quad_normal(par, x, y, z, gn);
-    monomials6(gn, m6);
-    double S = 0.0;
-#pragma unroll
-    for (int t = 0; t < 28; t++) S += sm.T[t] * m6[t];
-    const float d = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
-    const unsigned id = p.tag & kTagIndexMask;
-    const bool better = S > bestS || (S == bestS && (d < bestD || (d == bestD && id < bestI)));
-    if (better) {
-      bestS = S; bestD = d; bestI = id;
-      bestG[0] = gn[0]; bestG[1] = gn[1]; bestG[2] = gn[2];
+  row_off = 0;
+  more = true;
+  while (more) {
+    if (single_batch) more = false;
+    else {
+      nr = build_runs_warp(ri, row_ptr, pts_c, q.x, q.y, rpad, sm.runs.rs, sm.runs.pre, kRunCap, row_off, more);
+      row_off += nr;
     }
-  });
+    walk_runs(pts_c, sm.runs, nr, q.x, q.y, q.z, r2, sm.ring, [&](const GPoint& p, bool active) {
+      if (!active) return;
+      const double x = (double(p.x) - qx) * inv_r, y = (double(p.y) - qy) * inv_r, z = (double(p.z) - qz) * inv_r;
+      double gn[3], m6[28];
+      quad_normal(par, x, y, z, gn);
+      monomials6(gn, m6);
+      double S = 0.0;
+#pragma unroll
+      for (int t = 0; t < 28; t++) S += sm.T[t] * m6[t];
+      const float d = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
+      const unsigned id = p.tag >> 2;
+      const bool better = S > bestS || (S == bestS && (d < bestD || (d == bestD && id < bestI)));
+      if (better) {
+        bestS = S; bestD = d; bestI = id;
+        bestG[0] = gn[0]; bestG[1] = gn[1]; bestG[2] = gn[2];
+      }
+    });
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const double oS = __shfl_xor_sync(0xffffffffu, bestS, o);
@@ -652,19 +683,19 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const int* __restrict__ cell_sta
 }
 
 // points that received a normal carry a tag bit so the sweep only fetches normals that exist
-__global__ void k_mark_normals(GPoint* pts, const int* __restrict__ inv, const int* __restrict__ indices, int n) {
+__global__ void k_mark_normals(GPoint* pts, const RowIndex* __restrict__ rip, const int* __restrict__ indices, int n,
+                               const int* __restrict__ d_count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) atomicOr(&pts[inv[indices[i]]].tag, kTagNormalBit);
+  if (i >= n || i >= *d_count) return;
+  const int idx = indices[i];
+  if (idx >= 0 && idx < rip->n_points) atomicOr(&pts[idx].tag, kTagNormalBit);
 }
 
 }  // namespace
 
-int fit_quadrics_device(Ctx* c, const int* d_indices, int n, double radius, ag_frame* d_frames, bool write_normals) {
+int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count, double radius, ag_frame* d_frames,
+                        bool write_normals) {
   if (n <= 0) return AG_OK;
-  if (c->n_vox <= 0) {
-    set_error("fit_quadrics: no cloud loaded");
-    return AG_ERR_EMPTY;
-  }
   if (c->moments.reserve(size_t(n) * kMomentStride * sizeof(double)) || c->nn_counts.reserve(size_t(n) * 4) ||
       c->counters.reserve(64))
     return AG_ERR_CUDA;
@@ -673,10 +704,11 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, double radius, ag_f
   const double inv_r = 1.0 / radius;
   const int blocks = (n + kWarps - 1) / kWarps;
   unsigned long long* ctr = c->counters.as<unsigned long long>();
+  const RowIndex* ri = c->row_index.as<RowIndex>();
   cudaEventRecord(c->ev_k[0], c->stream);
-  k_taubin_moments<<<blocks, kWarps * 32, 0, c->stream>>>(c->pts.as<GPoint>(), c->cell_start.as<int>(), c->grid,
-                                                          c->vox.as<float4>(), d_indices, n, r2, rpad, inv_r,
-                                                          c->moments.as<double>(), c->nn_counts.as<int>(), ctr);
+  k_taubin_moments<<<blocks, kWarps * 32, 0, c->stream>>>(c->vox.as<GPoint>(), c->row_ptr.as<int>(), ri, d_indices, n,
+                                                          d_count, r2, rpad, inv_r, c->moments.as<double>(),
+                                                          c->nn_counts.as<int>(), ctr);
   cudaEventRecord(c->ev_k[1], c->stream);
   const size_t smem = sizeof(AxesSmem) * kWarps;
   static bool attr_set = false;
@@ -687,12 +719,13 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, double radius, ag_f
   }
   const HandConst& h = c->hand;
   k_taubin_axes<<<blocks, kWarps * 32, smem, c->stream>>>(
-      c->pts.as<GPoint>(), c->cell_start.as<int>(), c->grid, c->vox.as<float4>(), d_indices, n, r2, rpad, inv_r, c->moments.as<double>(), h.cam[0][0], h.cam[0][1], h.cam[0][2], h.cam[1][0],
-      h.cam[1][1], h.cam[1][2], d_frames, write_normals ? c->normals.as<double>() : nullptr);
+      c->vox.as<GPoint>(), c->row_ptr.as<int>(), ri, d_indices, n, d_count, r2, rpad, inv_r, c->moments.as<double>(),
+      h.cam[0][0], h.cam[0][1], h.cam[0][2], h.cam[1][0], h.cam[1][1], h.cam[1][2], d_frames,
+      write_normals ? c->normals.as<double>() : nullptr);
   cudaEventRecord(c->ev_k[2], c->stream);
   c->launches += write_normals ? 3 : 2;
   if (write_normals)
-    k_mark_normals<<<(n + 255) / 256, 256, 0, c->stream>>>(c->pts.as<GPoint>(), c->inv.as<int>(), d_indices, n);
+    k_mark_normals<<<(n + 255) / 256, 256, 0, c->stream>>>(c->vox.as<GPoint>(), ri, d_indices, n, d_count);
   AG_CUDA_CHECK(cudaGetLastError());
   return AG_OK;
 }

@@ -37,8 +37,8 @@ struct SlabPoint {  // centred neighbour, binary32 exactly as hand_search.cpp:15
 
 struct SweepArgs {
   const GPoint* pts;
-  const int* cell_start;
-  const float4* vox;
+  const int* row_ptr;
+  const RowIndex* ri;
   const int* indices;
   const ag_frame* frames;
   const double* normals;  // 3 per voxel point, indexed by original index
@@ -77,7 +77,7 @@ struct SlotTables {    // shared-memory threshold tables with -inf / +inf sentin
 
 template <int CAP>
 __global__ void __launch_bounds__(kThreads, CAP <= 2048 ? 3 : 1)
-k_hand_sweep(const SweepArgs A, const GridDesc g, const __grid_constant__ HandConst hc) {
+k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   SlabPoint* slab = reinterpret_cast<SlabPoint*>(s_raw);
   __shared__ uint32_t s_img[8][AG_IMAGE_WORDS];
@@ -90,9 +90,15 @@ k_hand_sweep(const SweepArgs A, const GridDesc g, const __grid_constant__ HandCo
   const int s = A.sample_list ? A.sample_list[blockIdx.x] : blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
-  const int idx = A.indices[s];
-  const float4 q = A.vox[idx];
-  const int sample_cam = __float_as_int(q.w) ? 1 : 0;  // hands_cam_source (hand_search.cpp:40-42, App. B#3)
+  const RowIndex ri = *A.ri;
+  const int idx = (s < ri.n_samples) ? A.indices[s] : -1;
+  if (idx < 0 || idx >= ri.n_points) {  // unused sample slot (fewer voxels than requested samples)
+    if (lane == 0) A.valid[size_t(s) * 8 + warp] = 0;
+    if (threadIdx.x == 0 && A.slab_counts) A.slab_counts[s] = 0;
+    return;
+  }
+  const GPoint q = A.pts[idx];
+  const int sample_cam = (q.tag & kTagCamBit) ? 1 : 0;  // hands_cam_source (hand_search.cpp:40-42, App. B#3)
   if (threadIdx.x == 0) {
     s_count = 0;
     s_cand = 0;
@@ -128,23 +134,29 @@ k_hand_sweep(const SweepArgs A, const GridDesc g, const __grid_constant__ HandCo
   __syncthreads();
 
   // ---- phase A: gather the r = 0.08 ball, keep the |z_hand| < hand_height slab -----------------
-  // The <=7x7 cell columns are z-contiguous runs of very different lengths; their candidates are
-  // flattened into one index space (per-column prefix in shared memory) and handed out to the warps in
-  // 64-candidate blocks through a shared counter, two independent 16-byte loads in flight per lane.
+  // One candidate run per x-row the ball can touch (binary search on y, ag_common.cuh), one thread per
+  // row; the runs are flattened into one index space (prefix in shared memory) and handed out to the
+  // warps in 64-candidate blocks through a shared counter, two independent 16-byte loads in flight per lane.
   {
-    const QueryBox b = query_box(g, q.x, q.y, q.z, A.rpad);
-    const int ncy = b.hi[1] - b.lo[1] + 1;
-    const int ncol = (b.hi[0] - b.lo[0] + 1) * ncy;
+    int klo[2] = {0, 0}, rows[2] = {0, 0};
+    for (int c = 0; c < 2; c++) {
+      if (ri.count[c] == 0) continue;
+      int k_hi;
+      row_range(ri, c, q.x, A.rpad, klo[c], k_hi);
+      rows[c] = max(0, k_hi - klo[c] + 1);
+    }
+    const int ncol = rows[0] + rows[1];
     unsigned long long nball = 0;
-    for (int cbase = 0; cbase < ncol; cbase += kThreads) {  // one batch unless the grid is unusually fine
+    for (int cbase = 0; cbase < ncol; cbase += kThreads) {  // one batch for the shipped radii
       const int nc = min(kThreads, ncol - cbase);
       if (threadIdx.x < nc) {
         const int col = cbase + threadIdx.x;
-        const int cx = b.lo[0] + col / ncy, cy = b.lo[1] + col % ncy;
-        const int rs = __ldg(A.cell_start + cell_linear(g, cx, cy, b.lo[2]));
-        const int re = __ldg(A.cell_start + cell_linear(g, cx, cy, b.hi[2]) + 1);
-        s_rs[threadIdx.x] = rs;
-        s_pre[threadIdx.x + 1] = re - rs;
+        const int c = col < rows[0] ? 0 : 1;
+        const int k = klo[c] + (c == 0 ? col : col - rows[0]);
+        int j0, j1;
+        row_run(ri, A.row_ptr, A.pts, c, k, q.y, A.rpad, j0, j1);
+        s_rs[threadIdx.x] = j0;
+        s_pre[threadIdx.x + 1] = j1 - j0;
       }
       if (threadIdx.x == 0) {
         s_pre[0] = 0;
@@ -185,7 +197,9 @@ k_hand_sweep(const SweepArgs A, const GridDesc g, const __grid_constant__ HandCo
           p[u].tag = 0;
           if (valid[u]) {
             while (pos >= s_pre[c + 1]) c++;
-            p[u] = A.pts[s_rs[c] + (pos - s_pre[c])];
+            const int j = s_rs[c] + (pos - s_pre[c]);
+            p[u] = A.pts[j];
+            p[u].tag = (uint32_t(j) << 2) | (p[u].tag & 3u);  // keep the point index for the normal fetch
           }
         }
 #pragma unroll
@@ -410,7 +424,7 @@ k_hand_sweep(const SweepArgs A, const GridDesc g, const __grid_constant__ HandCo
       const int bit = (AG_IMAGE_ROWS - 1 - v) * AG_IMAGE_COLS + h;
       atomicOr(&img[bit >> 5], 1u << (bit & 31));
       if (p.tag & kTagNormalBit) {  // antipodal.cpp:12-86 on rot * frame^T * normal
-        const double* nv = A.normals + size_t(3) * (p.tag & kTagIndexMask);
+        const double* nv = A.normals + size_t(3) * (p.tag >> 2);
         const double n0 = nv[0], n1 = nv[1], n2 = nv[2];
         const double hn0 = (F[0][0] * n0 + F[1][0] * n1) + F[2][0] * n2;
         const double hn1 = (F[0][1] * n0 + F[1][1] * n1) + F[2][1] * n2;
@@ -473,14 +487,13 @@ __global__ void k_compact_grasps(const ag_grasp* __restrict__ raw, const int* __
 }
 
 // caller-supplied cloud_normals_: flag the points whose normal is non-zero
-__global__ void k_flag_normals(GPoint* pts, const int* __restrict__ inv, const double* __restrict__ normals, int n) {
+__global__ void k_flag_normals(GPoint* pts, const double* __restrict__ normals, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const bool nz = normals && (normals[3 * size_t(i)] != 0.0 || normals[3 * size_t(i) + 1] != 0.0 ||
                               normals[3 * size_t(i) + 2] != 0.0);
-  GPoint* p = pts + inv[i];
-  if (nz) atomicOr(&p->tag, kTagNormalBit);
-  else atomicAnd(&p->tag, ~kTagNormalBit);
+  if (nz) atomicOr(&pts[i].tag, kTagNormalBit);
+  else atomicAnd(&pts[i].tag, ~kTagNormalBit);
 }
 
 }  // namespace
@@ -491,7 +504,7 @@ int set_normals_device(Ctx* c, const double* h_normals) {
   if (c->normals.reserve(size_t(n) * 24)) return AG_ERR_CUDA;
   if (h_normals) AG_CUDA_CHECK(cudaMemcpyAsync(c->normals.p, h_normals, size_t(n) * 24, cudaMemcpyHostToDevice, c->stream));
   else AG_CUDA_CHECK(cudaMemsetAsync(c->normals.p, 0, size_t(n) * 24, c->stream));
-  k_flag_normals<<<(n + 255) / 256, 256, 0, c->stream>>>(c->pts.as<GPoint>(), c->inv.as<int>(),
+  k_flag_normals<<<(n + 255) / 256, 256, 0, c->stream>>>(c->vox.as<GPoint>(),
                                                         h_normals ? c->normals.as<double>() : nullptr, n);
   AG_CUDA_CHECK(cudaGetLastError());
   AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -545,24 +558,11 @@ void compute_hand_const(const ag_params& p, HandConst& h) {
   h.half_od = p.hand_outer_diameter / 2.0;
 }
 
-int hand_sweep_device(Ctx* c, const int* d_indices, int n, const ag_frame* d_frames, unsigned flags) {
-  c->n_hyp = 0;
-  c->images_valid = false;
-  if (n <= 0) return AG_OK;
-  if (c->n_vox <= 0) {
-    set_error("hand_sweep: no cloud loaded");
-    return AG_ERR_EMPTY;
-  }
-  const size_t slots = size_t(n) * 8;
-  if (c->grasps_raw.reserve(slots * sizeof(ag_grasp)) || c->valid.reserve(slots + 64) ||
-      c->images_raw.reserve(slots * AG_IMAGE_WORDS * 4) || c->hyp_slots.reserve(slots * 4 + 16) ||
-      c->grasps.reserve(slots * sizeof(ag_grasp)) || c->counters.reserve(64) ||
-      c->sweep_dbg.reserve(size_t(n) * 4 + slots * 4))
-    return AG_ERR_CUDA;
+static SweepArgs make_args(Ctx* c, const int* d_indices, int n, const ag_frame* d_frames, unsigned flags) {
   SweepArgs A;
-  A.pts = c->pts.as<GPoint>();
-  A.cell_start = c->cell_start.as<int>();
-  A.vox = c->vox.as<float4>();
+  A.pts = c->vox.as<GPoint>();
+  A.row_ptr = c->row_ptr.as<int>();
+  A.ri = c->row_index.as<RowIndex>();
   A.indices = d_indices;
   A.frames = d_frames;
   A.normals = c->normals.as<double>();
@@ -572,32 +572,19 @@ int hand_sweep_device(Ctx* c, const int* d_indices, int n, const ag_frame* d_fra
   A.slab_counts = c->sweep_dbg.as<int>();
   A.debug = c->sweep_dbg.as<int>() + n;
   A.counters = c->counters.as<unsigned long long>();
-  if (c->overflow.reserve(size_t(n + 1) * 4)) return AG_ERR_CUDA;
   A.overflow = c->overflow.as<int>();
+  A.sample_list = nullptr;
   A.n_samples = n;
   const double radius = c->params.nn_radius_hands;
   A.r2 = float(radius * radius);
   A.rpad = sqrt(double(A.r2)) * (1.0 + 1e-5) + 1e-7;
   A.filter_boundaries = (flags & 0x100u) ? 1 : 0;
   for (int i = 0; i < 6; i++) A.workspace[i] = c->params.workspace[i];
-  A.sample_list = nullptr;
-  const size_t smem_small = size_t(kSlabCapSmall) * sizeof(SlabPoint);
-  const size_t smem_big = size_t(kSlabCapBig) * sizeof(SlabPoint);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_hand_sweep<kSlabCapSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_small));
-    cudaFuncSetAttribute(k_hand_sweep<kSlabCapSmall>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(k_hand_sweep<kSlabCapBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_big));
-    attr_set = true;
-  }
-  AG_CUDA_CHECK(cudaMemsetAsync(A.overflow, 0, 4, c->stream));
-  k_hand_sweep<kSlabCapSmall><<<n, kThreads, smem_small, c->stream>>>(A, c->grid, c->hand);
-  c->launches += 2;  // + k_compact_grasps
-  int n_over = 0;
-  AG_CUDA_CHECK(cudaMemcpyAsync(&n_over, A.overflow, 4, cudaMemcpyDeviceToHost, c->stream));
-  // the overflow count travels with the (already required) hypothesis-count sync below in the common
-  // case; only when it is non-zero do we pay a second pass
-  // stable compaction of the valid (sample, orientation) slots
+  return A;
+}
+
+static int compact(Ctx* c, const SweepArgs& A, size_t slots) {
+  // stable compaction of the valid (sample, orientation) slots = the reference's concat order
   int* d_slots = c->hyp_slots.as<int>();
   int* d_nsel = d_slots + slots;
   size_t tmp = 0;
@@ -608,37 +595,73 @@ int hand_sweep_device(Ctx* c, const int* d_indices, int n, const ag_frame* d_fra
   k_compact_grasps<<<int((slots + 255) / 256), 256, 0, c->stream>>>(A.grasps, d_slots, d_nsel,
                                                                     c->grasps.as<ag_grasp>(), int(slots));
   AG_CUDA_CHECK(cudaGetLastError());
-  int host[4] = {0, 0, 0, 0};
-  AG_CUDA_CHECK(cudaMemcpyAsync(&host[0], d_nsel, 4, cudaMemcpyDeviceToHost, c->stream));
-  AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  return AG_OK;
+}
+
+int* hand_sweep_count_ptr(Ctx* c, int n) { return c->hyp_slots.as<int>() + size_t(n) * 8; }
+int* hand_sweep_overflow_ptr(Ctx* c) { return c->overflow.as<int>(); }
+
+int hand_sweep_enqueue(Ctx* c, const int* d_indices, int n, const ag_frame* d_frames, unsigned flags) {
+  c->n_hyp = 0;
+  c->images_valid = false;
+  if (n <= 0) return AG_OK;
+  const size_t slots = size_t(n) * 8;
+  if (c->grasps_raw.reserve(slots * sizeof(ag_grasp)) || c->valid.reserve(slots + 64) ||
+      c->images_raw.reserve(slots * AG_IMAGE_WORDS * 4) || c->hyp_slots.reserve(slots * 4 + 16) ||
+      c->grasps.reserve(slots * sizeof(ag_grasp)) || c->counters.reserve(64) ||
+      c->sweep_dbg.reserve(size_t(n) * 4 + slots * 4) || c->overflow.reserve(size_t(n + 1) * 4))
+    return AG_ERR_CUDA;
+  SweepArgs A = make_args(c, d_indices, n, d_frames, flags);
+  const size_t smem_small = size_t(kSlabCapSmall) * sizeof(SlabPoint);
+  const size_t smem_big = size_t(kSlabCapBig) * sizeof(SlabPoint);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_hand_sweep<kSlabCapSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_small));
+    cudaFuncSetAttribute(k_hand_sweep<kSlabCapSmall>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_hand_sweep<kSlabCapBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_big));
+    attr_set = true;
+  }
+  AG_CUDA_CHECK(cudaMemsetAsync(A.overflow, 0, 4, c->stream));
+  k_hand_sweep<kSlabCapSmall><<<n, kThreads, smem_small, c->stream>>>(A, c->hand);
+  c->launches += 2;  // + k_compact_grasps
+  c->sweep_flags = flags;
+  c->sweep_indices = d_indices;
+  c->sweep_frames = d_frames;
+  return compact(c, A, slots);
+}
+
+// Called after the stream has been synchronised and the overflow counter read.  Samples whose slab
+// did not fit the 2048-point instantiation (dense neighbourhoods) are redone with the 12k-point one.
+int hand_sweep_finish(Ctx* c, int n, int n_over, int* n_hyp) {
+  const size_t slots = size_t(n) * 8;
+  int* d_nsel = c->hyp_slots.as<int>() + slots;
   if (n_over > 0) {
-    // dense neighbourhoods: redo those samples with the 13k-point instantiation, then re-compact
-    A.sample_list = A.overflow + 1;
-    int* d_over2 = A.overflow;  // reuse the counter to detect a second overflow
-    AG_CUDA_CHECK(cudaMemsetAsync(d_over2, 0, 4, c->stream));
-    // the list lives right behind the counter; copy it aside so the kernel can append again safely
+    SweepArgs A = make_args(c, c->sweep_indices, n, c->sweep_frames, c->sweep_flags);
     DevBuf list;
     if (list.reserve(size_t(n_over) * 4)) return AG_ERR_CUDA;
     AG_CUDA_CHECK(cudaMemcpyAsync(list.p, A.overflow + 1, size_t(n_over) * 4, cudaMemcpyDeviceToDevice, c->stream));
+    AG_CUDA_CHECK(cudaMemsetAsync(A.overflow, 0, 4, c->stream));
     A.sample_list = list.as<int>();
-    k_hand_sweep<kSlabCapBig><<<n_over, kThreads, smem_big, c->stream>>>(A, c->grid, c->hand);
-    AG_CUDA_CHECK(cub::DeviceSelect::Flagged(c->cub_tmp.p, tmp, iota, A.valid, d_slots, d_nsel, int(slots), c->stream));
-    k_compact_grasps<<<int((slots + 255) / 256), 256, 0, c->stream>>>(A.grasps, d_slots, d_nsel,
-                                                                      c->grasps.as<ag_grasp>(), int(slots));
+    const size_t smem_big = size_t(kSlabCapBig) * sizeof(SlabPoint);
+    k_hand_sweep<kSlabCapBig><<<n_over, kThreads, smem_big, c->stream>>>(A, c->hand);
     c->launches += 2;
+    int rc = compact(c, A, slots);
+    if (rc) return rc;
     int over2 = 0;
-    AG_CUDA_CHECK(cudaMemcpyAsync(&over2, d_over2, 4, cudaMemcpyDeviceToHost, c->stream));
-    AG_CUDA_CHECK(cudaMemcpyAsync(&host[0], d_nsel, 4, cudaMemcpyDeviceToHost, c->stream));
+    AG_CUDA_CHECK(cudaMemcpyAsync(&over2, A.overflow, 4, cudaMemcpyDeviceToHost, c->stream));
     AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     list.release();
-    host[1] = over2;
+    if (over2) {
+      set_error("hand sweep: a sample's slab exceeded the shared-memory capacity (12032 points)");
+      return AG_ERR_CAPACITY;
+    }
   }
-  if (host[1]) {
-    set_error("hand sweep: a sample's slab exceeded the shared-memory capacity (12032 points)");
-    return AG_ERR_CAPACITY;
-  }
-  c->n_hyp = host[0];
+  int h = 0;
+  AG_CUDA_CHECK(cudaMemcpyAsync(&h, d_nsel, 4, cudaMemcpyDeviceToHost, c->stream));
+  AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  c->n_hyp = h;
   c->images_valid = true;
+  if (n_hyp) *n_hyp = h;
   return AG_OK;
 }
 

@@ -93,14 +93,18 @@ def test_neighbour_sets_bit_exact(ctx, oracle, small_scene):
 def test_neighbour_sets_on_sphere_lattice(ctx, oracle):
     # lattice vectors of squared length exactly 100 voxels: membership decided by binary32 rounding
     k = np.array([[10, 0, 0], [6, 8, 0], [0, 6, 8], [8, 0, 6], [0, 0, 0], [9, 4, 2], [7, 7, 1], [0, 10, 0]], np.float64)
+    k = k[np.lexsort((k[:, 2], k[:, 1], k[:, 0]))]  # voxel order: sorted by (x, y, z) key
+    centre = int(np.nonzero((k == 0).all(1))[0][0])
     for mn in ([0.4123, -0.2177, 0.7311], [0.0, 0.0, 0.0], [-0.913, 0.27, 1.3]):
         xyz = (k * 0.003 + np.array(mn)).astype(np.float32)
         ctx.set_cloud(xyz, None)
         tree = oracle.Tree(xyz)
         for r in (0.03, 0.0300001, 0.0299999):
-            a = ctx.radius_search(xyz[4], r)
-            b, _ = tree.radius_search(xyz[4], r, 0)
+            a = ctx.radius_search(xyz[centre], r)
+            b, _ = tree.radius_search(xyz[centre], r, 0)
             assert np.array_equal(a, np.sort(b))
+    with pytest.raises(api.AgError, match="voxel order"):
+        ctx.set_cloud(xyz[::-1].copy(), None)
 
 
 def test_quadric_frames(ctx, oracle, small_scene, two_view_scene):
