@@ -19,7 +19,7 @@ _LIB = None
 EXPORTS = [
     "ag_last_error", "ag_default_params", "ag_create", "ag_destroy", "ag_set_params", "ag_get_params",
     "ag_get_timings", "ag_free", "ag_svm_load", "ag_svm_free", "ag_svm_info", "ag_localize", "ag_localize_device",
-    "ag_classify", "ag_set_svm", "ag_get_points", "ag_get_images", "ag_preprocess", "ag_set_cloud", "ag_radius_search",
+    "ag_classify", "ag_set_svm", "ag_set_export_buffer", "ag_get_points", "ag_get_images", "ag_preprocess", "ag_set_cloud", "ag_radius_search",
     "ag_fit_quadrics", "ag_hand_sweep", "ag_sweep_debug", "ag_hog_svm",
 ]
 
@@ -50,6 +50,7 @@ def lib():
     L.ag_localize_device.argtypes = loc_args
     L.ag_classify.argtypes = [vp, vp, C.POINTER(AgGrasp), C.c_int, C.POINTER(C.c_uint8)]
     L.ag_set_svm.argtypes = [vp, vp]
+    L.ag_set_export_buffer.argtypes = [vp, vp, C.c_size_t]
     L.ag_get_images.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint32)), ip]
     L.ag_preprocess.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_float)),
                                 C.POINTER(C.POINTER(C.c_int32)), ip]
@@ -168,6 +169,10 @@ class Context:
         """fuse scoring into localize(); pass None to detach"""
         self._svm = svm  # keep the model alive while attached
         _check(lib().ag_set_svm(self.h, None if svm is None else svm.h))
+
+    def set_export_buffer(self, dev_ptr, nbytes):
+        """device buffer that receives [n_hyp, n_vox, n_samples, error][records] on every localize()"""
+        _check(lib().ag_set_export_buffer(self.h, None if not dev_ptr else C.c_void_p(dev_ptr), int(nbytes)))
 
     def images(self):
         bits = C.POINTER(C.c_uint32)()

@@ -74,20 +74,23 @@ __device__ __forceinline__ void row_run(const RowIndex& ri, const int* __restric
                                         int& j1) {
   int a = __ldg(row_ptr + ri.row_base[c] + k), b = __ldg(row_ptr + ri.row_base[c] + k + 1);
   const double ylo = double(qy) - rpad, yhi = double(qy) + rpad;
-  int lo = a, hi = b;
-  while (lo < hi) {  // first j with y >= ylo
-    const int mid = (lo + hi) >> 1;
-    if (double(__ldg(&pts[mid].y)) < ylo) lo = mid + 1;
-    else hi = mid;
+  // two lower-bound searches advanced in lock step (independent load chains -> half the latency)
+  int lo0 = a, hi0 = b, lo1 = a, hi1 = b;
+  while (lo0 < hi0 || lo1 < hi1) {
+    const int m0 = (lo0 + hi0) >> 1, m1 = (lo1 + hi1) >> 1;
+    const float y0 = lo0 < hi0 ? __ldg(&pts[m0].y) : 0.f;
+    const float y1 = lo1 < hi1 ? __ldg(&pts[m1].y) : 0.f;
+    if (lo0 < hi0) {  // first j with y >= ylo
+      if (double(y0) < ylo) lo0 = m0 + 1;
+      else hi0 = m0;
+    }
+    if (lo1 < hi1) {  // first j with y > yhi
+      if (double(y1) <= yhi) lo1 = m1 + 1;
+      else hi1 = m1;
+    }
   }
-  j0 = lo;
-  hi = b;
-  while (lo < hi) {  // first j with y > yhi
-    const int mid = (lo + hi) >> 1;
-    if (double(__ldg(&pts[mid].y)) <= yhi) lo = mid + 1;
-    else hi = mid;
-  }
-  j1 = lo;
+  j0 = lo0;
+  j1 = lo1 < lo0 ? lo0 : lo1;
 }
 
 // ordered-int encoding of floats for atomicMin/atomicMax

@@ -78,6 +78,8 @@ struct Ctx {
   void* h_out = nullptr;
   void* d_out_mapped = nullptr;
   size_t h_out_cap = 0;
+  void* d_export = nullptr;   // caller-registered device buffer (ag_set_export_buffer)
+  size_t d_export_cap = 0;
   // samples
   DevBuf samples, moments, frames, nn_counts, all_frames;
   int n_samples = 0;

@@ -87,15 +87,40 @@ __global__ void k_iota(int* out, int n) {
   if (i < n) out[i] = i;
 }
 
+__global__ void k_gather_grasps(const ag_grasp* __restrict__ raw, const int* __restrict__ slots, int n, ag_grasp* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ag_grasp gr = raw[slots[i]];
+  gr.image_id = i;
+  out[i] = gr;
+}
+
 // results header + records, written straight into pinned device-mapped host memory
 struct HostOut {
   int n_hyp, n_vox, n_samples, error, n_over, pad[3];
   unsigned long long counters[4];
 };
-__global__ void k_export(const ag_grasp* __restrict__ grasps, const int* __restrict__ n_sel, const RowIndex* ri,
-                         const int* overflow, const unsigned long long* counters, HostOut* hdr, ag_grasp* out, int cap) {
+// Gathers the surviving hypotheses in (sample, orientation) order (= the reference's stable concat,
+// hand_search.cpp:194-200) straight from the per-slot records, merges the SVM results and writes the
+// list to mapped host memory, to the device copy used by ag_classify / ag_get_*, and to the optional
+// caller-registered device buffer.
+__global__ void k_export(const ag_grasp* __restrict__ raw, const int* __restrict__ slots, const int* __restrict__ n_sel,
+                         const float* __restrict__ scores, const RowIndex* ri, const int* overflow,
+                         const unsigned long long* counters, HostOut* hdr, ag_grasp* out_host, ag_grasp* out_dev,
+                         int* exp_hdr, ag_grasp* out_exp, int cap, int cap_exp) {
   const int n = min(*n_sel, cap);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = grasps[i];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    ag_grasp gr = raw[slots[i]];
+    gr.image_id = i;
+    if (scores) {
+      const float sc = scores[i];
+      gr.score = sc;
+      gr.label = sc > 0.f ? 0 : 1;  // CvSVM::predict: label +1 <=> sum <= 0
+    }
+    out_host[i] = gr;
+    out_dev[i] = gr;
+    if (out_exp && i < cap_exp) out_exp[i] = gr;
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     hdr->n_hyp = n;
     hdr->n_vox = ri->n_points;
@@ -103,6 +128,12 @@ __global__ void k_export(const ag_grasp* __restrict__ grasps, const int* __restr
     hdr->error = ri->error;
     hdr->n_over = overflow[0];
     for (int k = 0; k < 4; k++) hdr->counters[k] = counters[k];
+    if (exp_hdr) {
+      exp_hdr[0] = min(n, cap_exp);
+      exp_hdr[1] = ri->n_points;
+      exp_hdr[2] = ri->n_samples;
+      exp_hdr[3] = ri->error;
+    }
   }
 }
 
@@ -287,15 +318,23 @@ static int localize_core(Ctx* c, const void* d_points, int stride, int n_in, int
   if (c->attached_svm) {  // fused scoring, hypothesis count read on the device
     if (c->scores.reserve(slots * 8 + 64)) return AG_ERR_CUDA;
     rc = hog_svm_device(c, c->attached_svm, c->images_raw.as<uint32_t>(), c->hyp_slots.as<int>(), int(slots), d_nsel,
-                        nullptr, c->scores.as<float>(), c->grasps.as<ag_grasp>());
+                        nullptr, c->scores.as<float>(), nullptr);
     if (rc) return rc;
   }
   cudaEventRecord(c->ev[9], st);
   cudaEventRecord(c->ev[6], st);
   HostOut* hdr = static_cast<HostOut*>(c->d_out_mapped);
   ag_grasp* recs = reinterpret_cast<ag_grasp*>(hdr + 1);
-  k_export<<<kNumSMs, 256, 0, st>>>(c->grasps.as<ag_grasp>(), d_nsel, ri, hand_sweep_overflow_ptr(c),
-                                    c->counters.as<unsigned long long>(), hdr, recs, int(slots));
+  int* exp_hdr = static_cast<int*>(c->d_export);
+  ag_grasp* exp_recs = c->d_export ? reinterpret_cast<ag_grasp*>(static_cast<char*>(c->d_export) + 16) : nullptr;
+  const int cap_exp = c->d_export ? int((c->d_export_cap - 16) / sizeof(ag_grasp)) : 0;
+  auto do_export = [&]() {
+    k_export<<<kNumSMs, 256, 0, st>>>(c->grasps_raw.as<ag_grasp>(), c->hyp_slots.as<int>(), d_nsel,
+                                      c->attached_svm ? c->scores.as<float>() : nullptr, ri, hand_sweep_overflow_ptr(c),
+                                      c->counters.as<unsigned long long>(), hdr, recs, c->grasps.as<ag_grasp>(),
+                                      exp_hdr, exp_recs, int(slots), cap_exp);
+  };
+  do_export();
   c->launches += 1;
   cudaEventRecord(c->ev[7], st);
   AG_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -321,11 +360,10 @@ static int localize_core(Ctx* c, const void* d_points, int stride, int n_in, int
     if (rc) return rc;
     if (c->attached_svm && Hn > 0) {
       rc = hog_svm_device(c, c->attached_svm, c->images_raw.as<uint32_t>(), c->hyp_slots.as<int>(), Hn, nullptr, nullptr,
-                          c->scores.as<float>(), c->grasps.as<ag_grasp>());
+                          c->scores.as<float>(), nullptr);
       if (rc) return rc;
     }
-    k_export<<<kNumSMs, 256, 0, st>>>(c->grasps.as<ag_grasp>(), d_nsel, ri, hand_sweep_overflow_ptr(c),
-                                      c->counters.as<unsigned long long>(), hdr, recs, int(slots));
+    do_export();
     AG_CUDA_CHECK(cudaStreamSynchronize(st));
     Hn = h->n_hyp;
     c->n_hyp = Hn;
@@ -587,6 +625,17 @@ int ag_classify(ag_ctx* h, const ag_svm* svm, ag_grasp* grasps, int n, uint8_t* 
   return AG_OK;
 }
 
+int ag_set_export_buffer(ag_ctx* h, void* d_buffer, size_t bytes) {
+  if (!h) return AG_ERR_INVALID;
+  if (d_buffer && bytes < 16 + sizeof(ag_grasp)) {
+    set_error("export buffer too small");
+    return AG_ERR_INVALID;
+  }
+  h->c.d_export = d_buffer;
+  h->c.d_export_cap = d_buffer ? bytes : 0;
+  return AG_OK;
+}
+
 int ag_set_svm(ag_ctx* h, const ag_svm* svm) {
   if (!h) return AG_ERR_INVALID;
   h->c.attached_svm = svm ? svm->m : nullptr;
@@ -752,7 +801,12 @@ int ag_hand_sweep(ag_ctx* h, const int* indices, int n_indices, const ag_frame* 
   rc = hand_sweep_finish(&c, n_indices, n_over, &Hn);
   if (rc) return rc;
   ag_grasp* res = static_cast<ag_grasp*>(std::malloc(std::max<size_t>(1, size_t(Hn)) * sizeof(ag_grasp)));
-  if (Hn > 0) AG_CUDA_CHECK(cudaMemcpy(res, c.grasps.p, size_t(Hn) * sizeof(ag_grasp), cudaMemcpyDeviceToHost));
+  if (Hn > 0) {
+    k_gather_grasps<<<(Hn + 127) / 128, 128, 0, c.stream>>>(c.grasps_raw.as<ag_grasp>(), c.hyp_slots.as<int>(), Hn,
+                                                           c.grasps.as<ag_grasp>());
+    AG_CUDA_CHECK(cudaMemcpyAsync(res, c.grasps.p, size_t(Hn) * sizeof(ag_grasp), cudaMemcpyDeviceToHost, c.stream));
+    AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  }
   *out = res;
   *n_out = Hn;
   return AG_OK;

@@ -8,6 +8,8 @@
 // integer/byte work: one coalesced pass per kernel, CUB only for the device-wide radix sort and
 // unique primitives.  Nothing here synchronises with the host: counts stay in device memory.
 
+#include <algorithm>
+
 #include <cub/cub.cuh>
 
 #include "ag_internal.h"
@@ -100,53 +102,58 @@ __global__ void k_scan_blocks(int* block_counts, int nb) {  // single block, exc
   }
 }
 
-// flag[i] = 0 dropped, 1 camera 0, 2 camera 1; per-camera coordinate minima
-__global__ void k_classify(const char* pts, int stride, int n, int size_left, const int* block_offsets,
-                           double w0, double w1, double w2, double w3, double w4, double w5, uint8_t* flag,
-                           PreState* st) {
+// flag[i] = 0 dropped, 1 camera 0, 2 camera 1; per-camera coordinate minima.  Persistent CTAs walk the
+// 256-point chunks with a grid stride and keep the minima in registers, so each CTA issues one atomic
+// per camera and axis at the very end (same-address atomics serialise in L2: one per chunk was the
+// dominant cost of this kernel).
+__global__ void __launch_bounds__(kBlock)
+k_classify(const char* pts, int stride, int n, int size_left, const int* block_offsets, double w0, double w1, double w2,
+           double w3, double w4, double w5, uint8_t* flag, PreState* st) {
   __shared__ int wcount[kBlock / 32];
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  float x = 0, y = 0, z = 0;
-  bool fin = i < n && load_xyz(pts, stride, i, x, y, z);
-  int label;
-  if (block_offsets) {
-    // localization.cpp:19-27: labels are assigned by position BEFORE NaN removal but read AFTER
-    // compaction, i.e. finite point #k gets label (k < size_left ? 0 : 1)   
-    unsigned m = __ballot_sync(0xffffffffu, fin);
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) wcount[w] = __popc(m);
-    __syncthreads();
-    int before = block_offsets[blockIdx.x];
-    for (int k = 0; k < w; k++) before += wcount[k];
-    int rank = before + __popc(m & ((1u << lane) - 1));
-    label = rank < size_left ? 0 : 1;
-  } else {
-    label = i < size_left ? 0 : 1;
-  }
-  // localization.cpp:228-229 inclusive workspace box, float promoted to double
-  bool keep = fin && double(x) >= w0 && double(x) <= w1 && double(y) >= w2 && double(y) <= w3 && double(z) >= w4 &&
-              double(z) <= w5;
-  if (i < n) flag[i] = keep ? uint8_t(1 + label) : uint8_t(0);
-  // minima (localization.cpp:256-277): warp reduce -> shared -> one atomic per block, camera and axis
   __shared__ int s_min[6][kBlock / 32];
-  {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int ov[3] = {float_to_ordered(x), float_to_ordered(y), float_to_ordered(z)};
-#pragma unroll
-    for (int c = 0; c < 2; c++) {
-      const bool mine = keep && label == c;
-#pragma unroll
-      for (int a = 0; a < 3; a++) {
-        const int r = __reduce_min_sync(0xffffffffu, mine ? ov[a] : 0x7FFFFFFF);
-        if (lane == 0) s_min[c * 3 + a][w] = r;
-      }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int mn[6] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF};
+  const int n_chunks = (n + kBlock - 1) / kBlock;
+  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const int i = chunk * kBlock + threadIdx.x;
+    float x = 0, y = 0, z = 0;
+    const bool fin = i < n && load_xyz(pts, stride, i, x, y, z);
+    int label;
+    if (block_offsets) {
+      // localization.cpp:19-27: labels are assigned by position BEFORE NaN removal but read AFTER
+      // compaction, i.e. finite point #k gets label (k < size_left ? 0 : 1)   
+      const unsigned m = __ballot_sync(0xffffffffu, fin);
+      __syncthreads();
+      if (lane == 0) wcount[w] = __popc(m);
+      __syncthreads();
+      int before = block_offsets[chunk];
+      for (int k = 0; k < w; k++) before += wcount[k];
+      const int rank = before + __popc(m & ((1u << lane) - 1));
+      label = rank < size_left ? 0 : 1;
+    } else {
+      label = i < size_left ? 0 : 1;
     }
-    __syncthreads();
-    if (threadIdx.x < 6) {
-      int r = s_min[threadIdx.x][0];
-      for (int k = 1; k < kBlock / 32; k++) r = min(r, s_min[threadIdx.x][k]);
-      if (r != 0x7FFFFFFF) atomicMin(&st->cam_min[threadIdx.x / 3][threadIdx.x % 3], r);
+    // localization.cpp:228-229 inclusive workspace box, float promoted to double
+    const bool keep = fin && double(x) >= w0 && double(x) <= w1 && double(y) >= w2 && double(y) <= w3 &&
+                      double(z) >= w4 && double(z) <= w5;
+    if (i < n) flag[i] = keep ? uint8_t(1 + label) : uint8_t(0);
+    if (keep) {  // localization.cpp:256-277
+      const int o = label * 3;
+      mn[o] = min(mn[o], float_to_ordered(x));
+      mn[o + 1] = min(mn[o + 1], float_to_ordered(y));
+      mn[o + 2] = min(mn[o + 2], float_to_ordered(z));
     }
+  }
+#pragma unroll
+  for (int a = 0; a < 6; a++) {
+    const int r = __reduce_min_sync(0xffffffffu, mn[a]);
+    if (lane == 0) s_min[a][w] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    int r = s_min[threadIdx.x][0];
+    for (int k = 1; k < kBlock / 32; k++) r = min(r, s_min[threadIdx.x][k]);
+    if (r != 0x7FFFFFFF) atomicMin(&st->cam_min[threadIdx.x / 3][threadIdx.x % 3], r);
   }
 }
 
@@ -409,7 +416,7 @@ int preprocess_device(Ctx* c, const void* d_points, int stride, int n_in, int si
     k_count_finite<<<nb, kBlock, 0, c->stream>>>(pts, stride, n_in, d_block);
     k_scan_blocks<<<1, 1024, 0, c->stream>>>(d_block, nb);
   }
-  k_classify<<<nb, kBlock, 0, c->stream>>>(pts, stride, n_in, size_left, quirk ? d_block : nullptr, P.workspace[0],
+  k_classify<<<std::min(nb, kNumSMs * 4), kBlock, 0, c->stream>>>(pts, stride, n_in, size_left, quirk ? d_block : nullptr, P.workspace[0],
                                            P.workspace[1], P.workspace[2], P.workspace[3], P.workspace[4],
                                            P.workspace[5], d_flag, st);
   k_keys<<<nb, kBlock, 0, c->stream>>>(pts, stride, n_in, d_flag, P.voxel_size, st, c->keys.as<uint64_t>(), kb);

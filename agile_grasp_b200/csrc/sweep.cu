@@ -17,8 +17,6 @@
 
 #include <cstdlib>
 
-#include <cub/cub.cuh>
-#include <thrust/iterator/counting_iterator.h>
 
 #include "ag_internal.h"
 
@@ -475,15 +473,56 @@ k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
   for (int i = lane; i < AG_IMAGE_WORDS; i += 32) gimg[i] = img[i];
 }
 
-// gather the surviving hypotheses in (sample, orientation) order = the reference's stable concat
-// (hand_search.cpp:194-200)
-__global__ void k_compact_grasps(const ag_grasp* __restrict__ raw, const int* __restrict__ slots,
-                                 const int* __restrict__ n_sel, ag_grasp* __restrict__ out, int cap) {
-  const int h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= *n_sel || h >= cap) return;
-  ag_grasp gr = raw[slots[h]];
-  gr.image_id = h;
-  out[h] = gr;
+// Stable compaction of the valid (sample, orientation) slots: slots[h] = raw slot of hypothesis h in
+// (sample, orientation) order, *n_sel = number of hypotheses.  One CTA: the flag array is tiny
+// (8 bytes per sample) and a single-block scan needs neither a second launch nor temporary storage.
+__global__ void __launch_bounds__(1024)
+k_compact_slots(const uint8_t* __restrict__ valid, int n_slots, int* __restrict__ slots, int* __restrict__ n_sel) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_slots; base += 1024 * 8) {
+    // each thread owns 8 consecutive flags (= one sample)
+    const int first = base + tid * 8;
+    unsigned bits = 0;
+    if (first + 8 <= n_slots) {
+      const uint2 v = *reinterpret_cast<const uint2*>(valid + first);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        bits |= ((v.x >> (8 * k)) & 0xFFu ? 1u : 0u) << k;
+        bits |= ((v.y >> (8 * k)) & 0xFFu ? 1u : 0u) << (4 + k);
+      }
+    } else {
+      for (int k = 0; k < 8 && first + k < n_slots; k++) bits |= (valid[first + k] ? 1u : 0u) << k;
+    }
+    const int cnt = __popc(bits);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    int pos = s_carry + (warp > 0 ? s_warp[warp - 1] : 0) + incl - cnt;
+    for (unsigned b2 = bits; b2; b2 &= b2 - 1) slots[pos++] = first + (__ffs(b2) - 1);
+    __syncthreads();
+    if (tid == 1023) s_carry = pos;  // thread 1023's end position = total so far
+    __syncthreads();
+  }
+  if (tid == 0) *n_sel = s_carry;
 }
 
 // caller-supplied cloud_normals_: flag the points whose normal is non-zero
@@ -584,16 +623,9 @@ static SweepArgs make_args(Ctx* c, const int* d_indices, int n, const ag_frame* 
 }
 
 static int compact(Ctx* c, const SweepArgs& A, size_t slots) {
-  // stable compaction of the valid (sample, orientation) slots = the reference's concat order
   int* d_slots = c->hyp_slots.as<int>();
   int* d_nsel = d_slots + slots;
-  size_t tmp = 0;
-  thrust::counting_iterator<int> iota(0);
-  cub::DeviceSelect::Flagged(nullptr, tmp, iota, A.valid, d_slots, d_nsel, int(slots), c->stream);
-  if (c->cub_tmp.reserve(tmp)) return AG_ERR_CUDA;
-  AG_CUDA_CHECK(cub::DeviceSelect::Flagged(c->cub_tmp.p, tmp, iota, A.valid, d_slots, d_nsel, int(slots), c->stream));
-  k_compact_grasps<<<int((slots + 255) / 256), 256, 0, c->stream>>>(A.grasps, d_slots, d_nsel,
-                                                                    c->grasps.as<ag_grasp>(), int(slots));
+  k_compact_slots<<<1, 1024, 0, c->stream>>>(A.valid, int(slots), d_slots, d_nsel);
   AG_CUDA_CHECK(cudaGetLastError());
   return AG_OK;
 }

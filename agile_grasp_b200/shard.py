@@ -43,3 +43,29 @@ def all_gather_grasps(local, device=None, group=None):
     out = out.copy()
     out["image_id"] = -1  # images stay on the producing rank
     return out, counts
+
+
+EXPORT_HEADER_BYTES = 16
+
+
+def export_buffer_bytes(num_samples):
+    """size of the per-rank device export buffer of ag_set_export_buffer for `num_samples` samples"""
+    return EXPORT_HEADER_BYTES + 8 * int(num_samples) * GRASP_DTYPE.itemsize
+
+
+def all_gather_export(send, recv, group=None):
+    """ONE fixed-size collective on device memory: every rank contributes its export buffer
+    ([n_hyp, n_vox, n_samples, error][records], written by the library inside ag_localize) and receives
+    all of them; no host copy, no size exchange.  send: uint8 CUDA tensor (export buffer), recv: uint8 CUDA
+    tensor of world * len(send) bytes.  Returns recv viewed as (world, bytes)."""
+    dist.all_gather_into_tensor(recv, send, group=group)
+    return recv.view(dist.get_world_size(group), -1)
+
+
+def parse_export(buf_u8):
+    """host-side decode of one rank's export buffer (numpy uint8 array) -> (header dict, records)"""
+    hdr = np.frombuffer(buf_u8[:EXPORT_HEADER_BYTES].tobytes(), dtype=np.int32)
+    n = int(hdr[0])
+    item = GRASP_DTYPE.itemsize
+    recs = np.frombuffer(buf_u8[EXPORT_HEADER_BYTES:EXPORT_HEADER_BYTES + n * item].tobytes(), dtype=GRASP_DTYPE)
+    return dict(n_hyp=n, n_vox=int(hdr[1]), n_samples=int(hdr[2]), error=int(hdr[3])), recs

@@ -178,12 +178,20 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     item = GRASP_DTYPE.itemsize
 
+    # multi-GPU: the library leaves [header][records] in a device buffer; one fixed-size NCCL all-gather
+    # makes every rank hold every rank's grasp list (device resident)
+    from agile_grasp_b200 import shard
+    if world > 1:
+        nbytes = shard.export_buffer_bytes(pool[0]["P"].num_samples)
+        send = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        recv = torch.zeros(nbytes * world, dtype=torch.uint8, device=dev)
+        ctx.set_export_buffer(send.data_ptr(), nbytes)
+
     def gather(local_g):
         if world == 1:
             return len(local_g)
-        from agile_grasp_b200.shard import all_gather_grasps
-        merged, counts = all_gather_grasps(local_g, device=dev)
-        return len(merged)
+        allbuf = shard.all_gather_export(send, recv)
+        return allbuf  # counts are read after the timed region (no host sync inside the step)
 
     def step_device(c):
         g = ctx.localize_device(c["dev"].data_ptr(), c["stride"], c["n"], c["size_left"])
@@ -254,6 +262,12 @@ def main():
         e2e_h.append(len(g))
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    gathered = None
+    if world > 1:  # decode the last all-gather on the host (outside the timed region): every rank's list is there
+        host = recv.cpu().numpy().reshape(world, -1)
+        parts = [shard.parse_export(host[r]) for r in range(world)]
+        gathered = {"per_rank": [p[0]["n_hyp"] for p in parts], "errors": [p[0]["error"] for p in parts]}
+        assert parts[rank][0]["n_hyp"] == e2e_h[-1], (parts[rank][0], e2e_h[-1])
 
     # ---- reduce over ranks: time = max, hypotheses = sum
     t_dev = torch.tensor([sum(dev_ms), sum(e2e_s) * 1e3], dtype=torch.float64, device=dev)
@@ -296,7 +310,7 @@ def main():
                          "algorithmic_bytes_per_launch": float(np.mean(mom_bytes)),
                          "launch_ms": float(np.mean(mom_ms))},
             "stages_ms": {k: float(np.mean(v)) for k, v in stage.items()},
-            "comm_ms": float(np.mean(comm_ms)),
+            "comm_ms": float(np.mean(comm_ms)), "gathered_last_step": gathered,
             "wall_ms_per_step_incl_flush": float(1e3 * wall_dev / args.steps),
             "clocks": clocks,
         }

@@ -30,6 +30,7 @@
 #ifndef AG_B200_H_
 #define AG_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -161,6 +162,12 @@ int ag_classify(ag_ctx* ctx, const ag_svm* svm, ag_grasp* grasps, int n, uint8_t
  * in the same stream (score/label of the returned records are filled) and a following ag_classify with
  * the same model just returns those results.  The model must outlive the attachment. */
 int ag_set_svm(ag_ctx* ctx, const ag_svm* svm);
+
+/* Multi-GPU plumbing: when a device buffer is registered, every ag_localize also leaves
+ * [int32 n_hyp, int32 n_vox, int32 n_samples, int32 error][n_hyp x ag_grasp] in it (same stream, complete
+ * when ag_localize returns), so the caller can all-gather the grasp list over NCCL without a host copy.
+ * bytes must be >= 16 + 8 * samples * sizeof(ag_grasp); NULL unregisters. */
+int ag_set_export_buffer(ag_ctx* ctx, void* d_buffer, size_t bytes);
 
 /* Variable-length members of GraspHypothesis for hypothesis `image_id` of the last ag_localize
  * (requires AG_FLAG_KEEP_POINTS): points_for_learning (3 x m, column-major doubles) and the
