@@ -51,6 +51,7 @@ def lib():
     L.ag_classify.argtypes = [vp, vp, C.POINTER(AgGrasp), C.c_int, C.POINTER(C.c_uint8)]
     L.ag_set_svm.argtypes = [vp, vp]
     L.ag_set_export_buffer.argtypes = [vp, vp, C.c_size_t]
+    L.ag_get_points.argtypes = [vp, C.c_int, C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.POINTER(C.c_int32)), ip]
     L.ag_get_images.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint32)), ip]
     L.ag_preprocess.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_float)),
                                 C.POINTER(C.POINTER(C.c_int32)), ip]
@@ -169,6 +170,21 @@ class Context:
         """fuse scoring into localize(); pass None to detach"""
         self._svm = svm  # keep the model alive while attached
         _check(lib().ag_set_svm(self.h, None if svm is None else svm.h))
+
+    def points(self, image_id):
+        """points_for_learning (3 x m) and the camera source of every column, reference column order"""
+        pts = C.POINTER(C.c_double)()
+        cam = C.POINTER(C.c_int32)()
+        m = C.c_int()
+        _check(lib().ag_get_points(self.h, int(image_id), C.byref(pts), C.byref(cam), C.byref(m)))
+        if m.value == 0:
+            P3, Cm = np.zeros((3, 0)), np.zeros(0, np.int32)
+        else:
+            P3 = np.ctypeslib.as_array(pts, shape=(m.value, 3)).T.copy()
+            Cm = np.ctypeslib.as_array(cam, shape=(m.value,)).copy()
+        lib().ag_free(pts)
+        lib().ag_free(cam)
+        return P3, Cm
 
     def set_export_buffer(self, dev_ptr, nbytes):
         """device buffer that receives [n_hyp, n_vox, n_samples, error][records] on every localize()"""

@@ -125,6 +125,27 @@ __device__ __forceinline__ double warp_max(double v) {
   return v;
 }
 
+// Sum-reduction of 32 per-lane arrays across the warp by recursive halving: after 5 exchange rounds
+// (16+8+4+2+1 = 31 value exchanges instead of 32 x 5 for 32 independent butterflies) lane i holds the
+// warp-wide sum of element i.  v[] must be indexed with compile-time constants only (registers).
+template <int N>
+__device__ __forceinline__ double warp_reduce_transpose32(double (&v)[N]) {
+  static_assert(N >= 32, "needs at least 32 elements");
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; i++) {
+      // keep elements whose index bit `half` equals this lane's bit; send the other half to the partner
+      const double send = upper ? v[i] : v[i + half];
+      const double keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return v[0];
+}
+
 // Builds the run list of a radius query for one warp: runs (start, length) of candidate points, as an
 // exclusive prefix over lengths in pre[0..n_runs].  rs / pre are this warp's shared arrays of capacity
 // cap / cap+1.  Returns the number of runs; `more` is set when the query touches more rows than fit

@@ -115,6 +115,7 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
 int hand_sweep_enqueue(Ctx* c, const int* d_indices, int n, const ag_frame* d_frames, unsigned flags);
 // after a sync: handles samples whose slab overflowed the small instantiation; returns the hypothesis count
 int hand_sweep_finish(Ctx* c, int n, int n_over, int* n_hyp);
+int box_points_device(Ctx* c, int n_samples, int slot, std::vector<double>& pts, std::vector<int>& cam);
 int* hand_sweep_count_ptr(Ctx* c, int n);     // device address of the hypothesis count of the last enqueue
 int* hand_sweep_overflow_ptr(Ctx* c);         // device address of the overflow counter
 // n_dev (may be null): device int with the number of hypotheses; n is then only the launch bound

@@ -643,9 +643,32 @@ int ag_set_svm(ag_ctx* h, const ag_svm* svm) {
   return AG_OK;
 }
 
-int ag_get_points(ag_ctx*, int, double**, int32_t**, int*) {
-  set_error("ag_get_points: not implemented in this build");
-  return AG_ERR_INVALID;
+int ag_get_points(ag_ctx* h, int image_id, double** pts3xm, int32_t** cam, int* m) {
+  if (!h || !pts3xm || !cam || !m) return AG_ERR_INVALID;
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  *pts3xm = nullptr;
+  *cam = nullptr;
+  *m = 0;
+  if (!c.images_valid || image_id < 0 || image_id >= c.n_hyp) {
+    set_error("ag_get_points: image_id does not belong to the last localize / sweep call");
+    return AG_ERR_INVALID;
+  }
+  int slot = 0;
+  AG_CUDA_CHECK(cudaMemcpy(&slot, c.hyp_slots.as<int>() + image_id, 4, cudaMemcpyDeviceToHost));
+  std::vector<double> p;
+  std::vector<int> cm;
+  int rc = box_points_device(&c, c.n_samples, slot, p, cm);
+  if (rc) return rc;
+  const int n = int(cm.size());
+  double* op = static_cast<double*>(std::malloc(std::max<size_t>(1, p.size()) * sizeof(double)));
+  int32_t* oc = static_cast<int32_t*>(std::malloc(std::max<size_t>(1, cm.size()) * sizeof(int32_t)));
+  std::memcpy(op, p.data(), p.size() * sizeof(double));
+  for (int i = 0; i < n; i++) oc[i] = cm[i];
+  *pts3xm = op;
+  *cam = oc;
+  *m = n;
+  return AG_OK;
 }
 
 int ag_get_images(ag_ctx* h, uint32_t** bits, int* n_images) {
@@ -765,7 +788,15 @@ int ag_fit_quadrics(ag_ctx* h, const int* indices, int n_indices, double radius,
   if (rc) return rc;
   AG_CUDA_CHECK(cudaMemcpyAsync(frames_out, c.frames.p, size_t(n_indices) * sizeof(ag_frame), cudaMemcpyDeviceToHost,
                                 c.stream));
+  unsigned long long ctr[8];
+  AG_CUDA_CHECK(cudaMemcpyAsync(ctr, c.counters.p, 64, cudaMemcpyDeviceToHost, c.stream));
   AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  c.timings.n_samples = n_indices;
+  c.timings.n_voxels = c.n_vox;
+  c.timings.moments_ms = elapsed(c.ev_k[0], c.ev_k[1]);
+  c.timings.axes_ms = elapsed(c.ev_k[1], c.ev_k[2]);
+  c.timings.taubin_neighbor_points = int64_t(ctr[0]);
+  c.timings.taubin_candidates = int64_t(ctr[1]);
   return AG_OK;
 }
 
@@ -792,6 +823,7 @@ int ag_hand_sweep(ag_ctx* h, const int* indices, int n_indices, const ag_frame* 
   if (rc) return rc;
   RowIndex* ri = c.row_index.as<RowIndex>();
   k_check_samples<<<(n_indices + 255) / 256, 256, 0, c.stream>>>(ri, n_indices, c.samples.as<int>());
+  c.n_samples = n_indices;
   rc = hand_sweep_enqueue(&c, c.samples.as<int>(), n_indices, c.frames.as<ag_frame>(), flags & 0x100u);
   if (rc) return rc;
   int n_over = 0;

@@ -153,18 +153,19 @@ k_taubin_moments(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr
       cam1 += (p.tag & kTagCamBit) ? 1 : 0;
     });
   }
-#pragma unroll
-  for (int i = 0; i < kNumMoments; i++) acc[i] = warp_sum(acc[i]);
+  // warp reduction: moments 0..31 by recursive halving (lane i ends up with moment i), 32..34 by butterflies
+  const double r32 = warp_reduce_transpose32(acc);
+  const double m32 = warp_sum(acc[32]), m33 = warp_sum(acc[33]), m34 = warp_sum(acc[34]);
   cam1 = __reduce_add_sync(0xffffffffu, cam1);
   double* out = moments + size_t(s) * kMomentStride;
-  // lane i writes moment i (after the xor-reduction every lane holds every sum)
-#pragma unroll
-  for (int i = 0; i < kNumMoments; i++)
-    if (lane == (i & 31)) out[i] = acc[i];
+  out[lane] = r32;
   if (lane == 0) {
+    out[32] = m32;
+    out[33] = m33;
+    out[34] = m34;
     out[35] = double(cam1);
-    nn_counts[s] = int(acc[0]);
-    atomicAdd(&counters[0], (unsigned long long)(acc[0]));
+    nn_counts[s] = int(r32);
+    atomicAdd(&counters[0], (unsigned long long)(r32));
     atomicAdd(&counters[1], (unsigned long long)(n_cand));
   }
 }
@@ -586,15 +587,24 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const int* __restrict__ row_ptr,
     });
   }
   const bool single_batch = row_off == nr;  // the common case: the list in shared memory is complete
+  // warp reduction by recursive halving: lane i holds sum i (i < 32); sums 32, 33 by butterflies
+  {
+    const double r32 = warp_reduce_transpose32(acc);
+    const double a32 = warp_sum(acc[32]), a33 = warp_sum(acc[33]);
 #pragma unroll
-  for (int i = 0; i < 34; i++) acc[i] = warp_sum(acc[i]);
+    for (int i = 0; i < 6; i++) acc[i] = __shfl_sync(0xffffffffu, r32, i);  // sum g g^T, needed by every lane
+    if (lane >= 6) sm.T[lane - 6] = r32 * c_multinomial6[lane - 6];          // T_0 .. T_25
+    if (lane == 0) {
+      sm.T[26] = a32 * c_multinomial6[26];
+      sm.T[27] = a33 * c_multinomial6[27];
+    }
+  }
   double w3[3], V3[3][3];
   eig3(acc, w3, V3);
   int m3 = 0;
   if (w3[1] < w3[m3]) m3 = 1;
   if (w3[2] < w3[m3]) m3 = 2;  // quadric.cpp:278-280
   double ax[3] = {V3[0][m3], V3[1][m3], V3[2][m3]};
-  if (lane < 28) sm.T[lane] = acc[6 + lane] * c_multinomial6[lane];
   __syncwarp();
 
   // --- walk 3: j* = argmax_j sum_i (g_i.g_j)^6 = argmax_j <T, g_j^(x6)>, first max in (dist, index) order

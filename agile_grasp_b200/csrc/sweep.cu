@@ -15,7 +15,9 @@
 // binary64 values, evaluated without FMA contraction (this file is compiled with -fmad=false and
 // the products/sums are written in the reference's left-to-right order).
 
+#include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 
 #include "ag_internal.h"
@@ -525,6 +527,94 @@ k_compact_slots(const uint8_t* __restrict__ valid, int n_slots, int* __restrict_
   if (tid == 0) *n_sel = s_carry;
 }
 
+// On-demand materialisation of GraspHypothesis::points_for_learning_ for ONE hypothesis (sample s,
+// orientation o): the rotated slab points inside the hand box minus the surface vector
+// (rotating_hand.cpp:125-151), with their camera source, FLANN distance and cloud index (the host sorts
+// them into the reference's (distance, index) neighbour order).  Same arithmetic as k_hand_sweep.
+__global__ void __launch_bounds__(256)
+k_box_points(const SweepArgs A, const __grid_constant__ HandConst hc, int s, int o, double* out_pts, int* out_cam,
+             float* out_d2, int* out_idx, int* out_count, int cap) {
+  __shared__ double s_min[8];
+  __shared__ int s_j0, s_j1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const RowIndex ri = *A.ri;
+  const int idx = A.indices[s];
+  const GPoint q = A.pts[idx];
+  const ag_frame fr = A.frames[s];
+  double F[3][3];
+  {
+    const double* a = fr.normal;
+    const double* b = fr.axis;
+    const double nxa[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    for (int r = 0; r < 3; r++) {
+      F[r][0] = a[r];
+      F[r][1] = nxa[r];
+      F[r][2] = b[r];
+    }
+  }
+  const double cs = hc.cosv[o], sn = hc.sinv[o], msn = -1.0 * sn;
+  const unsigned dbg = unsigned(A.debug[size_t(s) * 8 + o]);
+  const int e_idx = int((dbg >> 4) & 0xFu), last = int((dbg >> 8) & 0xFu);
+  double surface3[3] = {0, 0, 0};
+  for (int pass = 0; pass < 2; pass++) {
+    double minY = 1e300;
+    for (int c = 0; c < 2; c++) {
+      if (ri.count[c] == 0) continue;
+      int k_lo, k_hi;
+      row_range(ri, c, q.x, A.rpad, k_lo, k_hi);
+      for (int k = k_lo; k <= k_hi; k++) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          int j0, j1;
+          row_run(ri, A.row_ptr, A.pts, c, k, q.y, A.rpad, j0, j1);
+          s_j0 = j0;
+          s_j1 = j1;
+        }
+        __syncthreads();
+        for (int j = s_j0 + int(threadIdx.x); j < s_j1; j += blockDim.x) {
+          const GPoint p = A.pts[j];
+          const float d2 = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
+          if (!(d2 < A.r2)) continue;
+          const double px = double(__fsub_rn(p.x, q.x)), py = double(__fsub_rn(p.y, q.y)), pz = double(__fsub_rn(p.z, q.z));
+          const double hz = (F[0][2] * px + F[1][2] * py) + F[2][2] * pz;
+          if (!(hz > -1.0 * hc.hand_height && hz < hc.hand_height)) continue;
+          const double hx = (F[0][0] * px + F[1][0] * py) + F[2][0] * pz;
+          const double hy = (F[0][1] * px + F[1][1] * py) + F[2][1] * pz;
+          const double rx = cs * hx + msn * hy, ry = sn * hx + cs * hy;
+          if (pass == 0) {
+            minY = fmin(minY, ry);
+          } else if (ry < hc.lim[last]) {
+            const int w = atomicAdd(out_count, 1);
+            if (w < cap) {
+              const double rz = (0.0 * hx + 0.0 * hy) + 1.0 * hz;
+              out_pts[3 * size_t(w)] = rx - surface3[0];
+              out_pts[3 * size_t(w) + 1] = ry - surface3[1];
+              out_pts[3 * size_t(w) + 2] = rz - surface3[2];
+              out_cam[w] = (p.tag & kTagCamBit) ? 1 : 0;
+              out_d2[w] = d2;
+              out_idx[w] = j;
+            }
+          }
+        }
+      }
+    }
+    if (pass == 0) {
+      minY = warp_min(minY);
+      if (lane == 0) s_min[warp] = minY;
+      __syncthreads();
+      double m = s_min[0];
+      for (int w2 = 1; w2 < 8; w2++) m = fmin(m, s_min[w2]);
+      const double hor = hc.half_od + hc.spacing[e_idx];
+      for (int r = 0; r < 3; r++) {
+        const double T0 = (F[r][0] * cs + F[r][1] * msn) + F[r][2] * 0.0;
+        const double T1 = (F[r][0] * sn + F[r][1] * cs) + F[r][2] * 0.0;
+        const double T2 = (F[r][0] * 0.0 + F[r][1] * 0.0) + F[r][2] * 1.0;
+        surface3[r] = (T0 * hor + T1 * m) + T2 * 0.0;
+      }
+    }
+  }
+}
+
 // caller-supplied cloud_normals_: flag the points whose normal is non-zero
 __global__ void k_flag_normals(GPoint* pts, const double* __restrict__ normals, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -627,6 +717,48 @@ static int compact(Ctx* c, const SweepArgs& A, size_t slots) {
   int* d_nsel = d_slots + slots;
   k_compact_slots<<<1, 1024, 0, c->stream>>>(A.valid, int(slots), d_slots, d_nsel);
   AG_CUDA_CHECK(cudaGetLastError());
+  return AG_OK;
+}
+
+// points_for_learning of hypothesis `slot` = sample*8 + orientation of the last sweep
+int box_points_device(Ctx* c, int n_samples, int slot, std::vector<double>& pts, std::vector<int>& cam) {
+  pts.clear();
+  cam.clear();
+  const int cap = std::max(c->n_vox, 1);
+  DevBuf buf;
+  if (buf.reserve(size_t(cap) * (24 + 4 + 4 + 4) + 16)) return AG_ERR_CUDA;
+  double* d_pts = buf.as<double>();
+  int* d_cam = reinterpret_cast<int*>(d_pts + size_t(cap) * 3);
+  float* d_d2 = reinterpret_cast<float*>(d_cam + cap);
+  int* d_idx = reinterpret_cast<int*>(d_d2 + cap);
+  int* d_cnt = d_idx + cap;
+  AG_CUDA_CHECK(cudaMemsetAsync(d_cnt, 0, 4, c->stream));
+  SweepArgs A = make_args(c, c->sweep_indices, n_samples, c->sweep_frames, c->sweep_flags);
+  k_box_points<<<1, 256, 0, c->stream>>>(A, c->hand, slot / 8, slot % 8, d_pts, d_cam, d_d2, d_idx, d_cnt, cap);
+  int m = 0;
+  AG_CUDA_CHECK(cudaMemcpyAsync(&m, d_cnt, 4, cudaMemcpyDeviceToHost, c->stream));
+  AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  m = std::min(m, cap);
+  std::vector<double> hp(size_t(m) * 3);
+  std::vector<int> hc2(m), hi(m);
+  std::vector<float> hd(m);
+  if (m > 0) {
+    AG_CUDA_CHECK(cudaMemcpy(hp.data(), d_pts, size_t(m) * 24, cudaMemcpyDeviceToHost));
+    AG_CUDA_CHECK(cudaMemcpy(hc2.data(), d_cam, size_t(m) * 4, cudaMemcpyDeviceToHost));
+    AG_CUDA_CHECK(cudaMemcpy(hd.data(), d_d2, size_t(m) * 4, cudaMemcpyDeviceToHost));
+    AG_CUDA_CHECK(cudaMemcpy(hi.data(), d_idx, size_t(m) * 4, cudaMemcpyDeviceToHost));
+  }
+  buf.release();
+  // the reference's column order is the kd-tree's neighbour order: ascending (distance, index)
+  std::vector<int> order(m);
+  for (int i = 0; i < m; i++) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return hd[a] != hd[b] ? hd[a] < hd[b] : hi[a] < hi[b]; });
+  pts.resize(size_t(m) * 3);
+  cam.resize(m);
+  for (int i = 0; i < m; i++) {
+    for (int d = 0; d < 3; d++) pts[size_t(i) * 3 + d] = hp[size_t(order[i]) * 3 + d];
+    cam[i] = hc2[order[i]];
+  }
   return AG_OK;
 }
 

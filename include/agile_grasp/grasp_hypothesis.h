@@ -56,6 +56,18 @@ class GraspHypothesis {
   void setHalfAntipodal(bool b) { half_antipodal_ = b; rec_.half_antipodal = b; }
   void setGraspWidth(double w) { grasp_width_ = w; rec_.width = w; }
 
+  // B200 addition: fill the variable-length members from ag_get_points (3 x m column-major + camera per column)
+  void setPointsForLearning(const double* pts3xm, const int32_t* cam, int m) {
+    points_for_learning_.resize(3, m);
+    indices_points_for_learning_cam1_.clear();
+    indices_points_for_learning_cam2_.clear();
+    for (int j = 0; j < m; j++) {
+      for (int r = 0; r < 3; r++) points_for_learning_(r, j) = pts3xm[3 * j + r];
+      if (cam[j] == 0) indices_points_for_learning_cam1_.push_back(j);       // rotating_hand.cpp:143-151
+      else if (cam[j] == 1) indices_points_for_learning_cam2_.push_back(j);
+    }
+  }
+
   // B200 additions: the SVM decision value and the underlying record
   float getScore() const { return rec_.score; }
   const ag_grasp& record() const { return rec_; }

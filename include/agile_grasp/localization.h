@@ -62,7 +62,20 @@ class Localization {
       return hand_list;
     }
     hand_list.reserve(n);
-    for (int i = 0; i < n; i++) hand_list.push_back(GraspHypothesis(out[i]));
+    for (int i = 0; i < n; i++) {
+      GraspHypothesis g(out[i]);
+      if (keep_points_) {  // materialise points_for_learning + per-camera index lists (grasp_hypothesis.h:217-220)
+        double* p = nullptr;
+        int32_t* cm = nullptr;
+        int m = 0;
+        if (ag_get_points(ctx_, out[i].image_id, &p, &cm, &m) == AG_OK) {
+          g.setPointsForLearning(p, cm, m);
+          ag_free(p);
+          ag_free(cm);
+        }
+      }
+      hand_list.push_back(g);
+    }
     ag_free(out);
     std::cout << " # hands: " << hand_list.size() << "\n";
     return hand_list;
@@ -127,6 +140,9 @@ class Localization {
   void setInitBite(double v) { params_.init_bite = v; dirty_ = true; }
   void setHandHeight(double v) { params_.hand_height = v; dirty_ = true; }
   void setSampleSeed(uint64_t seed) { params_.seed = seed; dirty_ = true; }  // B200 addition (App. C.2)
+  // B200 addition: the grasp image is rasterised on the device, so the variable-length members of
+  // GraspHypothesis are only copied to the host when asked for
+  void setKeepPointsForLearning(bool keep) { keep_points_ = keep; }
 
   static const int NO_PLOTTING = 0;
   static const int PCL_PLOTTING = 1;
@@ -170,6 +186,7 @@ class Localization {
   double nn_radius_taubin_, nn_radius_hands_;
   ag_params params_;
   bool dirty_;
+  bool keep_points_ = false;
   ag_ctx* ctx_;
   ag_svm* svm_;
   std::string svm_path_;

@@ -192,6 +192,20 @@ def test_sweep_bit_exact_given_frames(ctx, oracle, small_scene, two_view_scene):
             assert np.array_equal(imgs[k], H.image(k, s["P"])), k
 
 
+def test_points_for_learning_bit_exact(ctx, oracle, small_scene):
+    """GraspHypothesis::getPointsForLearning (ag_get_points): same columns, same order, same bits"""
+    s = small_scene
+    frames = oracle.fit_quadrics(s["tree"], s["cam"], s["idx"], 0.03, s["P"])["frames"]
+    normals = np.zeros((len(s["xyz"]), 3))
+    normals[s["idx"]] = frames["normal"]
+    H, g = _sweep_both(ctx, oracle, s, frames, normals)
+    for k in list(range(0, len(g), max(1, len(g) // 12))) + [len(g) - 1]:
+        Po, Co = H.points(k)
+        Pg, Cg = ctx.points(int(g["image_id"][k]))
+        assert Pg.shape == Po.shape == (3, g["num_points"][k])
+        assert (_u64(Pg) == _u64(Po)).all() and np.array_equal(Cg, Co)
+
+
 def test_sweep_antipodal_flags_with_dense_normals(ctx, oracle, small_scene):
     """calculates_antipodal mode: every point carries a normal -> non-trivial half/full flags"""
     s = small_scene
