@@ -108,18 +108,28 @@ __global__ void k_export(const ag_grasp* __restrict__ raw, const int* __restrict
                          const float* __restrict__ scores, const RowIndex* ri, const int* overflow,
                          const unsigned long long* counters, HostOut* hdr, ag_grasp* out_host, ag_grasp* out_dev,
                          int* exp_hdr, ag_grasp* out_exp, int cap, int cap_exp) {
+  // a record is 10 x 16 bytes: three records per warp pass, every lane moves one uint4 (coalesced
+  // 480-byte stores — the mapped host destination is written over PCIe and needs full-width writes)
+  static_assert(sizeof(ag_grasp) == 160, "record layout");
   const int n = min(*n_sel, cap);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    ag_grasp gr = raw[slots[i]];
-    gr.image_id = i;
-    if (scores) {
-      const float sc = scores[i];
-      gr.score = sc;
-      gr.label = sc > 0.f ? 0 : 1;  // CvSVM::predict: label +1 <=> sum <= 0
+  const int lane = threadIdx.x & 31;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int sub = lane / 10, part = lane % 10;
+  for (int base = warp_global * 3; base < n; base += n_warps * 3) {
+    const int i = base + sub;
+    if (lane >= 30 || i >= n) continue;
+    uint4 v = reinterpret_cast<const uint4*>(raw + slots[i])[part];
+    if (part == 8 && scores) v.x = __float_as_uint(scores[i]);            // byte 128: score
+    if (part == 9) {
+      v.z = uint32_t(i);                                                   // byte 152: image_id
+      if (scores) {                                                        // byte 158: label (+1 <=> sum <= 0)
+        const uint32_t label = scores[i] > 0.f ? 0u : 1u;
+        v.w = (v.w & 0xFF00FFFFu) | (label << 16);
+      }
     }
-    out_host[i] = gr;
-    out_dev[i] = gr;
-    if (out_exp && i < cap_exp) out_exp[i] = gr;
+    reinterpret_cast<uint4*>(out_host + i)[part] = v;
+    reinterpret_cast<uint4*>(out_dev + i)[part] = v;
+    if (out_exp && i < cap_exp) reinterpret_cast<uint4*>(out_exp + i)[part] = v;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     hdr->n_hyp = n;
@@ -329,7 +339,7 @@ static int localize_core(Ctx* c, const void* d_points, int stride, int n_in, int
   ag_grasp* exp_recs = c->d_export ? reinterpret_cast<ag_grasp*>(static_cast<char*>(c->d_export) + 16) : nullptr;
   const int cap_exp = c->d_export ? int((c->d_export_cap - 16) / sizeof(ag_grasp)) : 0;
   auto do_export = [&]() {
-    k_export<<<kNumSMs, 256, 0, st>>>(c->grasps_raw.as<ag_grasp>(), c->hyp_slots.as<int>(), d_nsel,
+    k_export<<<32, 256, 0, st>>>(c->grasps_raw.as<ag_grasp>(), c->hyp_slots.as<int>(), d_nsel,
                                       c->attached_svm ? c->scores.as<float>() : nullptr, ri, hand_sweep_overflow_ptr(c),
                                       c->counters.as<unsigned long long>(), hdr, recs, c->grasps.as<ag_grasp>(),
                                       exp_hdr, exp_recs, int(slots), cap_exp);

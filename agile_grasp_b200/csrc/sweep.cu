@@ -135,8 +135,8 @@ k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
 
   // ---- phase A: gather the r = 0.08 ball, keep the |z_hand| < hand_height slab -----------------
   // One candidate run per x-row the ball can touch (binary search on y, ag_common.cuh), one thread per
-  // row; the runs are flattened into one index space (prefix in shared memory) and handed out to the
-  // warps in 64-candidate blocks through a shared counter, two independent 16-byte loads in flight per lane.
+  // row; the warps then pull runs from a shared counter and stream them, two independent 16-byte loads
+  // in flight per lane.
   {
     int klo[2] = {0, 0}, rows[2] = {0, 0};
     for (int c = 0; c < 2; c++) {
@@ -146,7 +146,7 @@ k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
       rows[c] = max(0, k_hi - klo[c] + 1);
     }
     const int ncol = rows[0] + rows[1];
-    unsigned long long nball = 0;
+    unsigned long long nball = 0, ncand = 0;
     for (int cbase = 0; cbase < ncol; cbase += kThreads) {  // one batch for the shipped radii
       const int nc = min(kThreads, ncol - cbase);
       if (threadIdx.x < nc) {
@@ -156,82 +156,63 @@ k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
         int j0, j1;
         row_run(ri, A.row_ptr, A.pts, c, k, q.y, A.rpad, j0, j1);
         s_rs[threadIdx.x] = j0;
-        s_pre[threadIdx.x + 1] = j1 - j0;
+        s_pre[threadIdx.x] = j1;
       }
-      if (threadIdx.x == 0) {
-        s_pre[0] = 0;
-        s_next = 0;
-      }
+      if (threadIdx.x == 0) s_next = 0;
       __syncthreads();
-      if (warp == 0) {  // inclusive scan of the <=256 run lengths
-        int carry = 0;
-        for (int base = 0; base < nc; base += 32) {
-          const int i = base + lane;
-          int v = i < nc ? s_pre[i + 1] : 0;
-#pragma unroll
-          for (int o2 = 1; o2 < 32; o2 <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, v, o2);
-            if (lane >= o2) v += t;
-          }
-          if (i < nc) s_pre[i + 1] = v + carry;
-          carry += __shfl_sync(0xffffffffu, v, 31);
-        }
-      }
-      __syncthreads();
-      const int total = s_pre[nc];
-      if (threadIdx.x == 0) s_cand += (unsigned long long)total;
-      int c = 0;  // column cursor of this lane (blocks come in increasing order per warp)
       for (;;) {
-        int blk = 0;
-        if (lane == 0) blk = atomicAdd(&s_next, 1);
-        blk = __shfl_sync(0xffffffffu, blk, 0);
-        const int base = blk * 64;
-        if (base >= total) break;
-        GPoint p[2];
-        bool valid[2];
+        int run = 0;
+        if (lane == 0) run = atomicAdd(&s_next, 1);
+        run = __shfl_sync(0xffffffffu, run, 0);
+        if (run >= nc) break;
+        const int j0 = s_rs[run], j1 = s_pre[run];
+        ncand += (unsigned long long)(j1 - j0);
+        for (int jb = j0; jb < j1; jb += 64) {
+          GPoint p[2];
+          bool valid[2];
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
-          const int pos = base + u * 32 + lane;
-          valid[u] = pos < total;
-          p[u].x = p[u].y = p[u].z = 0.f;
-          p[u].tag = 0;
-          if (valid[u]) {
-            while (pos >= s_pre[c + 1]) c++;
-            const int j = s_rs[c] + (pos - s_pre[c]);
-            p[u] = A.pts[j];
-            p[u].tag = (uint32_t(j) << 2) | (p[u].tag & 3u);  // keep the point index for the normal fetch
+          for (int u = 0; u < 2; u++) {
+            const int j = jb + u * 32 + lane;
+            valid[u] = j < j1;
+            p[u].x = p[u].y = p[u].z = 0.f;
+            p[u].tag = 0;
+            if (valid[u]) {
+              p[u] = A.pts[j];
+              p[u].tag = (uint32_t(j) << 2) | (p[u].tag & 3u);  // keep the point index for the normal fetch
+            }
           }
-        }
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
-          bool keep = false, inball = false;
-          SlabPoint sp;
-          sp.x = sp.y = sp.z = 0.f;
-          sp.tag = 0;
-          if (valid[u] && dist2_flann(q.x, q.y, q.z, p[u].x, p[u].y, p[u].z) < A.r2) {
-            inball = true;
-            // hand_search.cpp:157-158: subtraction in binary32, then cast
-            sp.x = __fsub_rn(p[u].x, q.x);
-            sp.y = __fsub_rn(p[u].y, q.y);
-            sp.z = __fsub_rn(p[u].z, q.z);
-            sp.tag = p[u].tag;
-            const double hz = (F[0][2] * double(sp.x) + F[1][2] * double(sp.y)) + F[2][2] * double(sp.z);
-            keep = hz > -1.0 * hc.hand_height && hz < hc.hand_height;  // rotating_hand.cpp:44
-          }
-          nball += __popc(__ballot_sync(0xffffffffu, inball));
-          const unsigned m = __ballot_sync(0xffffffffu, keep);
-          if (m) {
-            int wbase = 0;
-            if (lane == 0) wbase = atomicAdd(&s_count, __popc(m));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            const int pos = wbase + __popc(m & lt);
-            if (keep && pos < CAP) slab[pos] = sp;
+          for (int u = 0; u < 2; u++) {
+            if (u == 1 && jb + 32 >= j1) break;  // uniform
+            bool keep = false, inball = false;
+            SlabPoint sp;
+            sp.x = sp.y = sp.z = 0.f;
+            sp.tag = 0;
+            if (valid[u] && dist2_flann(q.x, q.y, q.z, p[u].x, p[u].y, p[u].z) < A.r2) {
+              inball = true;
+              // hand_search.cpp:157-158: subtraction in binary32, then cast
+              sp.x = __fsub_rn(p[u].x, q.x);
+              sp.y = __fsub_rn(p[u].y, q.y);
+              sp.z = __fsub_rn(p[u].z, q.z);
+              sp.tag = p[u].tag;
+              const double hz = (F[0][2] * double(sp.x) + F[1][2] * double(sp.y)) + F[2][2] * double(sp.z);
+              keep = hz > -1.0 * hc.hand_height && hz < hc.hand_height;  // rotating_hand.cpp:44
+            }
+            nball += __popc(__ballot_sync(0xffffffffu, inball));
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (m) {
+              int wbase = 0;
+              if (lane == 0) wbase = atomicAdd(&s_count, __popc(m));
+              wbase = __shfl_sync(0xffffffffu, wbase, 0);
+              const int pos = wbase + __popc(m & lt);
+              if (keep && pos < CAP) slab[pos] = sp;
+            }
           }
         }
       }
       __syncthreads();
     }
-    if (lane == 0) atomicAdd(&s_cand, nball << 32);
+    if (lane == 0) atomicAdd(&s_cand, ncand | (nball << 32));
   }
   __syncthreads();
   const int k = s_count;
