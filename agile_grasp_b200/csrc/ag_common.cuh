@@ -36,6 +36,10 @@ struct RowIndex {         // lives in device memory, written by the voxelisation
   int n_points;           // total voxels
   int n_samples;          // samples actually used by the current call (<= requested)
   int error;              // sticky device-side error flags (kErr*)
+  int use_cols;           // 1 if the dense (kx, ky) column table below is populated
+  int cols_bad;           // set when the table was abandoned (a gap too long to fill inline: very sparse cloud)
+  int ny[2];              // y-cells per x-row of the column table
+  int col_base[2];        // offset of camera c inside the column table
   int pad;
 };
 constexpr int kErrKeyOverflow = 1;   // voxel key outside the workspace-derived bit budget
@@ -68,12 +72,28 @@ __device__ __forceinline__ void row_range(const RowIndex& ri, int c, float qx, d
   k_hi = b < 0.0 ? -1 : (b >= double(ri.nx[c] - 1) ? ri.nx[c] - 1 : int(b));
 }
 
-// the run of row `k` of camera c with |y - qy| <= rpad: [j0, j1) by two binary searches on y
+// the run of row `k` of camera c with |y - qy| <= chord(rpad, dx): [j0, j1).
+// Fast path: the dense column table col_ptr[kx*ny + ky] = first voxel with key >= (kx, ky) gives both
+// ends with two independent loads.  Fallback (table too large for the cloud's extent, or a cloud loaded
+// through ag_set_cloud): two lock-stepped binary searches on the row's sorted y.
 __device__ __forceinline__ void row_run(const RowIndex& ri, const int* __restrict__ row_ptr,
-                                        const GPoint* __restrict__ pts, int c, int k, float qy, double rpad, int& j0,
-                                        int& j1) {
+                                        const int* __restrict__ col_ptr, const GPoint* __restrict__ pts, int c, int k,
+                                        float qx, float qy, double rpad, int& j0, int& j1) {
+  // row x in binary64 (the stored float is within 1e-7 of it); shrink |dx| by a margin so the chord is conservative
+  const double dx = fmax(0.0, fabs(double(k) / ri.inv_cell + ri.mn[c][0] - double(qx)) - 1e-6);
+  const double half = sqrt(fmax(0.0, rpad * rpad - dx * dx)) + 1e-7;
+  const double ylo = double(qy) - half, yhi = double(qy) + half;
+  if (ri.use_cols && !ri.cols_bad) {
+    const int ny = ri.ny[c];
+    const double fa = (ylo - ri.mn[c][1]) * ri.inv_cell - 1e-3, fb = (yhi - ri.mn[c][1]) * ri.inv_cell + 1e-3;
+    const int ka = fa <= 0.0 ? 0 : (fa >= double(ny) ? ny : int(fa));
+    const int kb = fb < 0.0 ? 0 : (fb >= double(ny - 1) ? ny : int(fb) + 1);
+    const int* col = col_ptr + ri.col_base[c] + k * ny;
+    j0 = __ldg(col + ka);
+    j1 = __ldg(col + kb);
+    return;
+  }
   int a = __ldg(row_ptr + ri.row_base[c] + k), b = __ldg(row_ptr + ri.row_base[c] + k + 1);
-  const double ylo = double(qy) - rpad, yhi = double(qy) + rpad;
   // two lower-bound searches advanced in lock step (independent load chains -> half the latency)
   int lo0 = a, hi0 = b, lo1 = a, hi1 = b;
   while (lo0 < hi0 || lo1 < hi1) {
@@ -151,7 +171,8 @@ __device__ __forceinline__ double warp_reduce_transpose32(double (&v)[N]) {
 // cap / cap+1.  Returns the number of runs; `more` is set when the query touches more rows than fit
 // (the caller then continues with `row_off` advanced) — never the case for the shipped radii.
 __device__ __forceinline__ int build_runs_warp(const RowIndex& ri, const int* __restrict__ row_ptr,
-                                               const GPoint* __restrict__ pts, float qx, float qy, double rpad,
+                                               const int* __restrict__ col_ptr, const GPoint* __restrict__ pts,
+                                               float qx, float qy, double rpad,
                                                int* rs, int* pre, int cap, int row_off, bool& more) {
   const int lane = threadIdx.x & 31;
   int n_runs = 0;
@@ -176,7 +197,7 @@ __device__ __forceinline__ int build_runs_warp(const RowIndex& ri, const int* __
     }
     for (int t = lane; t < rows; t += 32) {
       int j0, j1;
-      row_run(ri, row_ptr, pts, c, k_lo + t, qy, rpad, j0, j1);
+      row_run(ri, row_ptr, col_ptr, pts, c, k_lo + t, qx, qy, rpad, j0, j1);
       rs[n_runs + t] = j0;
       pre[n_runs + t + 1] = j1 - j0;
     }

@@ -70,6 +70,7 @@ struct Ctx {
   // voxelised cloud (API index space = the reference's voxel order) and its x-row index
   DevBuf vox;        // GPoint: xyz + tag
   DevBuf row_ptr;    // per camera: first voxel of every x-row
+  DevBuf col_ptr;    // dense (kx, ky) column table (first voxel of every lattice column), when it fits
   DevBuf row_index;  // RowIndex descriptor (device resident; counts never round-trip through the host)
   DevBuf normals;    // double x 3 per voxel point (cloud_normals_)
   int n_vox = 0;     // host copy, valid after fetch_cloud_size / the end of ag_localize

@@ -20,6 +20,7 @@ namespace {
 
 constexpr int kBlock = 256;
 constexpr uint64_t kInvalidKey = ~0ull;
+constexpr int kColCap = 4 << 20;  // entries of the dense (kx, ky) column table (16 MB); larger extents fall back
 
 // voxel key = cam | kx | ky | kz packed with per-axis bit widths derived from the workspace extent, so
 // the radix sort only touches the bits that can be set
@@ -30,6 +31,7 @@ struct KeyBits {
 
 struct PreState {
   int cam_min[2][3];  // ordered-int encoded float minima per camera
+  int cam_max[2][2];  // maxima of x and y per camera (extent of the column table)
   int n_unique;       // output of DeviceSelect::Unique
   int n_vox;
   int key_overflow;
@@ -52,6 +54,8 @@ __global__ void k_init_state(PreState* st) {
   if (threadIdx.x == 0) {
     for (int c = 0; c < 2; c++)
       for (int a = 0; a < 3; a++) st->cam_min[c][a] = float_to_ordered(10000.0f);  // localization.cpp:251-252
+    for (int c = 0; c < 2; c++)
+      for (int a = 0; a < 2; a++) st->cam_max[c][a] = float_to_ordered(-3.0e38f);
     st->n_unique = 0;
     st->n_vox = 0;
     st->key_overflow = 0;
@@ -110,9 +114,10 @@ __global__ void __launch_bounds__(kBlock)
 k_classify(const char* pts, int stride, int n, int size_left, const int* block_offsets, double w0, double w1, double w2,
            double w3, double w4, double w5, uint8_t* flag, PreState* st) {
   __shared__ int wcount[kBlock / 32];
-  __shared__ int s_min[6][kBlock / 32];
+  __shared__ int s_min[10][kBlock / 32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int mn[6] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF};
+  int mxv[4] = {int(0x80000000), int(0x80000000), int(0x80000000), int(0x80000000)};
   const int n_chunks = (n + kBlock - 1) / kBlock;
   for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
     const int i = chunk * kBlock + threadIdx.x;
@@ -142,6 +147,8 @@ k_classify(const char* pts, int stride, int n, int size_left, const int* block_o
       mn[o] = min(mn[o], float_to_ordered(x));
       mn[o + 1] = min(mn[o + 1], float_to_ordered(y));
       mn[o + 2] = min(mn[o + 2], float_to_ordered(z));
+      mxv[label * 2] = max(mxv[label * 2], float_to_ordered(x));
+      mxv[label * 2 + 1] = max(mxv[label * 2 + 1], float_to_ordered(y));
     }
   }
 #pragma unroll
@@ -149,11 +156,21 @@ k_classify(const char* pts, int stride, int n, int size_left, const int* block_o
     const int r = __reduce_min_sync(0xffffffffu, mn[a]);
     if (lane == 0) s_min[a][w] = r;
   }
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    const int r = __reduce_max_sync(0xffffffffu, mxv[a]);
+    if (lane == 0) s_min[6 + a][w] = r;
+  }
   __syncthreads();
   if (threadIdx.x < 6) {
     int r = s_min[threadIdx.x][0];
     for (int k = 1; k < kBlock / 32; k++) r = min(r, s_min[threadIdx.x][k]);
     if (r != 0x7FFFFFFF) atomicMin(&st->cam_min[threadIdx.x / 3][threadIdx.x % 3], r);
+  } else if (threadIdx.x < 10) {
+    const int a = threadIdx.x - 6;
+    int r = s_min[threadIdx.x][0];
+    for (int k = 1; k < kBlock / 32; k++) r = max(r, s_min[threadIdx.x][k]);
+    if (r != int(0x80000000)) atomicMax(&st->cam_max[a / 2][a % 2], r);
   }
 }
 
@@ -188,7 +205,7 @@ __global__ void k_keys(const char* pts, int stride, int n, const uint8_t* flag, 
 // voxel corner = (float)(k*cell + min) (localization.cpp:318-351), camera-0 voxels first (key order);
 // the same pass fills the per-camera x-row table and the RowIndex descriptor.
 __global__ void k_emit(const uint64_t* keys_unique, int n_cap, double cell, PreState* st, GPoint* vox, KeyBits kb,
-                       RowIndex* ri, int* row_ptr, int row_stride) {
+                       RowIndex* ri, int* row_ptr, int row_stride, int* col_ptr, int col_cap) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int nu = min(st->n_unique, n_cap);
   if (i >= nu) return;
@@ -207,6 +224,27 @@ __global__ void k_emit(const uint64_t* keys_unique, int n_cap, double cell, PreS
       for (int c = 0; c < 2; c++) ri->nx[c] = ri->first[c] = ri->count[c] = 0;
     }
   }
+  // extent of the dense (kx, ky) column table, from the per-camera coordinate ranges (every thread
+  // derives the same numbers; thread 0 publishes them)
+  int nyc[2], nxc[2], cbase[2];
+  long long total = 0;
+  for (int cc = 0; cc < 2; cc++) {
+    const double x0 = double(ordered_to_float(st->cam_min[cc][0])), y0 = double(ordered_to_float(st->cam_min[cc][1]));
+    const double x1 = double(ordered_to_float(st->cam_max[cc][0])), y1 = double(ordered_to_float(st->cam_max[cc][1]));
+    const bool any = x1 >= x0;
+    nxc[cc] = any ? int(floor((x1 - x0) / cell)) + 1 : 0;
+    nyc[cc] = any ? int(floor((y1 - y0) / cell)) + 1 : 0;
+    cbase[cc] = int(total);
+    total += static_cast<long long>(nxc[cc]) * nyc[cc] + 1;
+  }
+  const bool use_cols = total <= static_cast<long long>(col_cap);
+  if (i == 0) {
+    ri->use_cols = use_cols ? 1 : 0;
+    for (int cc = 0; cc < 2; cc++) {
+      ri->ny[cc] = nyc[cc];
+      ri->col_base[cc] = cbase[cc];
+    }
+  }
   if (key == kInvalidKey) return;
   const int sh_c = kb.bx + kb.by + kb.bz, sh_x = kb.by + kb.bz;
   const int c = int((key >> sh_c) & 1u);
@@ -223,11 +261,29 @@ __global__ void k_emit(const uint64_t* keys_unique, int n_cap, double cell, PreS
   p.tag = c ? kTagCamBit : 0u;
   vox[i] = p;
   // x-row table: row_ptr[kx'] = i for every row kx' in (previous row, this row]
-  int prev_c = -1, prev_kx = -1;
+  int prev_c = -1, prev_kx = -1, prev_ky = -1;
   if (i > 0) {
     const uint64_t pk = keys_unique[i - 1];
     prev_c = int((pk >> sh_c) & 1u);
     prev_kx = int((pk >> sh_x) & ((1ull << kb.bx) - 1));
+    prev_ky = int((pk >> kb.bz) & ((1ull << kb.by) - 1));
+  }
+  if (use_cols) {
+    // column table: col[kx*ny + ky'] = i for every cell in (previous voxel's cell, this voxel's cell]
+    const int kyi = int(ky);
+    int* col = col_ptr + cbase[c];
+    const long long cur = static_cast<long long>(kxi) * nyc[c] + kyi;
+    const long long prv = (prev_c == c) ? static_cast<long long>(prev_kx) * nyc[c] + prev_ky : -1;
+    constexpr long long kMaxGap = 8192;  // a single thread fills a gap inline; beyond this the table is abandoned
+    if (cur - prv > kMaxGap) atomicOr(&ri->cols_bad, 1);
+    else
+      for (long long L = prv + 1; L <= cur; L++) col[L] = i;
+    if (i == n_vox - 1 || int((keys_unique[i + 1] >> sh_c) & 1u) != c) {  // last voxel of this camera
+      const long long endL = static_cast<long long>(nxc[c]) * nyc[c];
+      if (endL - cur > kMaxGap) atomicOr(&ri->cols_bad, 1);
+      else
+        for (long long L = cur + 1; L <= endL; L++) col[L] = i + 1;
+    }
   }
   int* rows = row_ptr + c * row_stride;
   if (prev_c != c) {
@@ -350,14 +406,15 @@ __global__ void k_cloud_desc(PreState* st, RowIndex* ri, int n, double cell, int
   st->n_vox = n;
 }
 
-__global__ void k_radius_search(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr, const RowIndex* rip,
+__global__ void k_radius_search(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr,
+                                const int* __restrict__ col_ptr, const RowIndex* rip,
                                 float qx, float qy, float qz, float r2, double rpad, int* out, int* out_count, int cap) {
   __shared__ int s_rs[256], s_pre[257];
   const RowIndex ri = *rip;
   int row_off = 0;
   bool more = true;
   while (more) {
-    const int nr = build_runs_warp(ri, row_ptr, pts, qx, qy, rpad, s_rs, s_pre, 256, row_off, more);
+    const int nr = build_runs_warp(ri, row_ptr, col_ptr, pts, qx, qy, rpad, s_rs, s_pre, 256, row_off, more);
     row_off += nr;
     for (int r = 0; r < nr; r++)
       for (int j = s_rs[r] + int(threadIdx.x); j < s_rs[r] + (s_pre[r + 1] - s_pre[r]); j += 32) {
@@ -402,6 +459,7 @@ int preprocess_device(Ctx* c, const void* d_points, int stride, int n_in, int si
   if (c->misc.reserve(sizeof(PreState)) || c->keys.reserve(size_t(n_in) * 8) || c->keys_sorted.reserve(size_t(n_in) * 8) ||
       c->keys_unique.reserve(size_t(n_in) * 8) || c->block_counts.reserve(size_t(nb) * 4 + size_t(n_in)) ||
       c->vox.reserve(size_t(n_in) * 16) || c->row_ptr.reserve(size_t(row_stride) * 2 * 4) ||
+      c->col_ptr.reserve(size_t(kColCap) * 4) ||
       c->row_index.reserve(sizeof(RowIndex)) || c->normals.reserve(size_t(n_in) * 24))
     return AG_ERR_CUDA;
   c->n_cap = n_in;
@@ -432,7 +490,8 @@ int preprocess_device(Ctx* c, const void* d_points, int stride, int n_in, int si
                                           c->keys_unique.as<uint64_t>(), &st->n_unique, n_in, c->stream));
   c->launches += quirk ? 6 : 4;  // init, [count, scan], classify, keys, emit (CUB kernels not counted)
   k_emit<<<nb, kBlock, 0, c->stream>>>(c->keys_unique.as<uint64_t>(), n_in, P.voxel_size, st, c->vox.as<GPoint>(), kb,
-                                       c->row_index.as<RowIndex>(), c->row_ptr.as<int>(), row_stride);
+                                       c->row_index.as<RowIndex>(), c->row_ptr.as<int>(), row_stride,
+                                       c->col_ptr.as<int>(), kColCap);
   // cloud_normals_ is zeroed on every call (hand_search.cpp:13-14)
   AG_CUDA_CHECK(cudaMemsetAsync(c->normals.p, 0, size_t(n_in) * 24, c->stream));
   AG_CUDA_CHECK(cudaGetLastError());
@@ -458,6 +517,7 @@ int set_cloud_device(Ctx* c, int n) {
   int bx = 0;
   int row_stride = row_stride_for(P, &bx);
   if (c->misc.reserve(sizeof(PreState) + 16) || c->row_ptr.reserve(size_t(row_stride) * 2 * 4) ||
+      c->col_ptr.reserve(64) ||
       c->row_index.reserve(sizeof(RowIndex)) || c->normals.reserve(std::max<size_t>(24, size_t(n) * 24)))
     return AG_ERR_CUDA;
   c->n_cap = n;
@@ -501,7 +561,8 @@ int radius_search_device(Ctx* c, const float q[3], double radius, std::vector<in
   cudaMemsetAsync(d_cnt, 0, 4, c->stream);
   float r2 = float(radius * radius);
   double rpad = sqrt(double(r2)) * (1.0 + 1e-5) + 1e-7;
-  k_radius_search<<<1, 32, 0, c->stream>>>(c->vox.as<GPoint>(), c->row_ptr.as<int>(), c->row_index.as<RowIndex>(), q[0],
+  k_radius_search<<<1, 32, 0, c->stream>>>(c->vox.as<GPoint>(), c->row_ptr.as<int>(), c->col_ptr.as<int>(),
+                                           c->row_index.as<RowIndex>(), q[0],
                                            q[1], q[2], r2, rpad, d_out, d_cnt, cap);
   int cnt = 0;
   cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, c->stream);

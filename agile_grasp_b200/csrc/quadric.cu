@@ -18,6 +18,8 @@
 //    sum_i (g_i . g_j)^6 = <T, g_j^(x6)> for every j — O(m) instead of the reference's O(m^2) — and
 //    takes the arg max with the reference's first-max tie-break in (distance, index) order.
 
+#include <cstdlib>
+
 #include "ag_internal.h"
 
 namespace ag {
@@ -114,12 +116,18 @@ __device__ __forceinline__ void walk_runs(const GPoint* __restrict__ pts, const 
 }
 
 // ---- kernel 1: moments ------------------------------------------------------------------------
+// Roofline-graded kernel.  One warp per sample.  Lane r finds where x-row r of the ball starts (ONE
+// lower-bound search on y; the run's end is detected while streaming, because a row is sorted by y).
+// The warp then streams two rows per step — one per half-warp, 16 contiguous 16-byte records each —
+// tests membership with FLANN's binary32 expression, compacts accepted points through a 64-entry
+// shared ring and accumulates the 35 monomial moments of full 32-point batches in binary64 registers.
 __global__ void __launch_bounds__(kWarps * 32, 4)
-k_taubin_moments(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr, const RowIndex* __restrict__ rip,
+k_taubin_moments(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr, const int* __restrict__ col_ptr,
+                 const RowIndex* __restrict__ rip,
                  const int* __restrict__ indices, int n_samples_max, const int* __restrict__ d_count, float r2,
-                 double rpad, double inv_r, double* __restrict__ moments, int* __restrict__ nn_counts, unsigned long long* __restrict__ counters) {
+                 double rpad, double inv_r, double* __restrict__ moments, int* __restrict__ nn_counts,
+                 unsigned long long* __restrict__ counters) {
   __shared__ GPoint s_ring[kWarps][64];
-  __shared__ RunList s_runs[kWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * kWarps + warp;
   const RowIndex ri = *rip;
@@ -128,30 +136,72 @@ k_taubin_moments(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr
   if (idx < 0 || idx >= ri.n_points) return;
   const GPoint q = pts[idx];
   const double qx = double(q.x), qy = double(q.y), qz = double(q.z);
+  GPoint* ring = s_ring[warp];
   double acc[kNumMoments];
 #pragma unroll
   for (int i = 0; i < kNumMoments; i++) acc[i] = 0.0;
-  int cam1 = 0, n_cand = 0, row_off = 0;
-  bool more = true;
-  while (more) {
-    const int nr = build_runs_warp(ri, row_ptr, pts, q.x, q.y, rpad, s_runs[warp].rs, s_runs[warp].pre, kRunCap,
-                                   row_off, more);
-    row_off += nr;
-    n_cand += s_runs[warp].pre[nr];
-    walk_runs(pts, s_runs[warp], nr, q.x, q.y, q.z, r2, s_ring[warp], [&](const GPoint& p, bool active) {
-      if (!active) return;
-      const double x = (double(p.x) - qx) * inv_r, y = (double(p.y) - qy) * inv_r, z = (double(p.z) - qz) * inv_r;
-      const double x2 = x * x, y2 = y * y, z2 = z * z, xy = x * y, yz = y * z, xz = x * z;
-      acc[0] += 1.0;
-      acc[1] += x; acc[2] += y; acc[3] += z;
-      acc[4] += x2; acc[5] += y2; acc[6] += z2; acc[7] += xy; acc[8] += yz; acc[9] += xz;
-      acc[10] += x2 * x; acc[11] += y2 * y; acc[12] += z2 * z; acc[13] += x2 * y; acc[14] += x2 * z;
-      acc[15] += x * y2; acc[16] += y2 * z; acc[17] += x * z2; acc[18] += y * z2; acc[19] += xy * z;
-      acc[20] += x2 * x2; acc[21] += y2 * y2; acc[22] += z2 * z2; acc[23] += x2 * xy; acc[24] += x2 * xz;
-      acc[25] += xy * y2; acc[26] += y2 * yz; acc[27] += xz * z2; acc[28] += yz * z2; acc[29] += x2 * y2;
-      acc[30] += y2 * z2; acc[31] += x2 * z2; acc[32] += x2 * yz; acc[33] += xy * yz; acc[34] += xz * yz;
-      cam1 += (p.tag & kTagCamBit) ? 1 : 0;
-    });
+  int cam1 = 0, n_cand = 0, head = 0, qn = 0;
+  const unsigned lt = (1u << lane) - 1u;
+  const int half_id = lane >> 4, l16 = lane & 15;
+  auto process = [&](const GPoint& p, bool active) {
+    if (!active) return;
+    const double x = (double(p.x) - qx) * inv_r, y = (double(p.y) - qy) * inv_r, z = (double(p.z) - qz) * inv_r;
+    const double x2 = x * x, y2 = y * y, z2 = z * z, xy = x * y, yz = y * z, xz = x * z;
+    acc[0] += 1.0;
+    acc[1] += x; acc[2] += y; acc[3] += z;
+    acc[4] += x2; acc[5] += y2; acc[6] += z2; acc[7] += xy; acc[8] += yz; acc[9] += xz;
+    acc[10] += x2 * x; acc[11] += y2 * y; acc[12] += z2 * z; acc[13] += x2 * y; acc[14] += x2 * z;
+    acc[15] += x * y2; acc[16] += y2 * z; acc[17] += x * z2; acc[18] += y * z2; acc[19] += xy * z;
+    acc[20] += x2 * x2; acc[21] += y2 * y2; acc[22] += z2 * z2; acc[23] += x2 * xy; acc[24] += x2 * xz;
+    acc[25] += xy * y2; acc[26] += y2 * yz; acc[27] += xz * z2; acc[28] += yz * z2; acc[29] += x2 * y2;
+    acc[30] += y2 * z2; acc[31] += x2 * z2; acc[32] += x2 * yz; acc[33] += xy * yz; acc[34] += xz * yz;
+    cam1 += (p.tag & kTagCamBit) ? 1 : 0;
+  };
+  for (int c = 0; c < 2; c++) {
+    if (ri.count[c] == 0) continue;
+    int k_lo, k_hi;
+    row_range(ri, c, q.x, rpad, k_lo, k_hi);
+    for (int kb = k_lo; kb <= k_hi; kb += 32) {  // batches of 32 rows (one batch for the shipped radii)
+      const int nrows = min(32, k_hi - kb + 1);
+      // lane r: candidate run [j_lo, j_end) of row r (column table: two independent loads)
+      int j_lo = 0, j_end = 0;
+      if (lane < nrows) row_run(ri, row_ptr, col_ptr, pts, c, kb + lane, q.x, q.y, rpad, j_lo, j_end);
+      for (int r = 0; r < nrows; r += 2) {
+        const int src = min(r + half_id, 31);
+        const bool has = r + half_id < nrows;
+        const int a = __shfl_sync(0xffffffffu, j_lo, src);
+        const int e_src = __shfl_sync(0xffffffffu, j_end, src);  // (all lanes must execute the shuffle)
+        const int e = has ? e_src : a;
+        const int len = max(__shfl_sync(0xffffffffu, e - a, 0), __shfl_sync(0xffffffffu, e - a, 16));
+        n_cand += __shfl_sync(0xffffffffu, e - a, 0) + __shfl_sync(0xffffffffu, e - a, 16);
+        for (int off = 0; off < len; off += 16) {
+          const int j = a + off + l16;
+          GPoint p;
+          p.x = p.y = p.z = 0.f;
+          p.tag = 0;
+          const bool valid = j < e;
+          if (valid) p = pts[j];
+          const bool ok = valid && dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z) < r2;
+          const unsigned m = __ballot_sync(0xffffffffu, ok);
+          if (m) {
+            if (ok) ring[(head + qn + __popc(m & lt)) & 63] = p;
+            qn += __popc(m);
+            __syncwarp();
+            if (qn >= 32) {
+              const GPoint v = ring[(head + lane) & 63];
+              __syncwarp();
+              process(v, true);
+              head = (head + 32) & 63;
+              qn -= 32;
+            }
+          }
+        }
+      }
+    }
+  }
+  if (qn > 0) {
+    const GPoint v = ring[(head + lane) & 63];
+    process(v, lane < qn);
   }
   // warp reduction: moments 0..31 by recursive halving (lane i ends up with moment i), 32..34 by butterflies
   const double r32 = warp_reduce_transpose32(acc);
@@ -360,7 +410,8 @@ __constant__ double c_multinomial6[28] = {
 
 // ---- kernel 2: eigen-solve + local axes -------------------------------------------------------
 __global__ void __launch_bounds__(kWarps * 32, 4)
-k_taubin_axes(const GPoint* __restrict__ pts_c, const int* __restrict__ row_ptr, const RowIndex* __restrict__ rip,
+k_taubin_axes(const GPoint* __restrict__ pts_c, const int* __restrict__ row_ptr, const int* __restrict__ col_ptr,
+              const RowIndex* __restrict__ rip,
               const int* __restrict__ indices, int n_samples_max, const int* __restrict__ d_count,
               float r2, double rpad, double inv_r, const double* __restrict__ moments,
               double cam0x, double cam0y, double cam0z, double cam1x, double cam1y, double cam1z,
@@ -572,7 +623,7 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const int* __restrict__ row_ptr,
   int nr = 0, row_off = 0;
   bool more = true;
   while (more) {
-    nr = build_runs_warp(ri, row_ptr, pts_c, q.x, q.y, rpad, sm.runs.rs, sm.runs.pre, kRunCap, row_off, more);
+    nr = build_runs_warp(ri, row_ptr, col_ptr, pts_c, q.x, q.y, rpad, sm.runs.rs, sm.runs.pre, kRunCap, row_off, more);
     row_off += nr;
     walk_runs(pts_c, sm.runs, nr, q.x, q.y, q.z, r2, sm.ring, [&](const GPoint& p, bool active) {
       if (!active) return;
@@ -617,7 +668,7 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const int* __restrict__ row_ptr,
   while (more) {
     if (single_batch) more = false;
     else {
-      nr = build_runs_warp(ri, row_ptr, pts_c, q.x, q.y, rpad, sm.runs.rs, sm.runs.pre, kRunCap, row_off, more);
+      nr = build_runs_warp(ri, row_ptr, col_ptr, pts_c, q.x, q.y, rpad, sm.runs.rs, sm.runs.pre, kRunCap, row_off, more);
       row_off += nr;
     }
     walk_runs(pts_c, sm.runs, nr, q.x, q.y, q.z, r2, sm.ring, [&](const GPoint& p, bool active) {
@@ -716,7 +767,8 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
   unsigned long long* ctr = c->counters.as<unsigned long long>();
   const RowIndex* ri = c->row_index.as<RowIndex>();
   cudaEventRecord(c->ev_k[0], c->stream);
-  k_taubin_moments<<<blocks, kWarps * 32, 0, c->stream>>>(c->vox.as<GPoint>(), c->row_ptr.as<int>(), ri, d_indices, n,
+  k_taubin_moments<<<blocks, kWarps * 32, 0, c->stream>>>(c->vox.as<GPoint>(), c->row_ptr.as<int>(),
+                                                          c->col_ptr.as<int>(), ri, d_indices, n,
                                                           d_count, r2, rpad, inv_r, c->moments.as<double>(),
                                                           c->nn_counts.as<int>(), ctr);
   cudaEventRecord(c->ev_k[1], c->stream);
@@ -729,7 +781,8 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
   }
   const HandConst& h = c->hand;
   k_taubin_axes<<<blocks, kWarps * 32, smem, c->stream>>>(
-      c->vox.as<GPoint>(), c->row_ptr.as<int>(), ri, d_indices, n, d_count, r2, rpad, inv_r, c->moments.as<double>(),
+      c->vox.as<GPoint>(), c->row_ptr.as<int>(), c->col_ptr.as<int>(), ri, d_indices, n, d_count, r2, rpad, inv_r,
+      c->moments.as<double>(),
       h.cam[0][0], h.cam[0][1], h.cam[0][2], h.cam[1][0], h.cam[1][1], h.cam[1][2], d_frames,
       write_normals ? c->normals.as<double>() : nullptr);
   cudaEventRecord(c->ev_k[2], c->stream);

@@ -38,6 +38,7 @@ struct SlabPoint {  // centred neighbour, binary32 exactly as hand_search.cpp:15
 struct SweepArgs {
   const GPoint* pts;
   const int* row_ptr;
+  const int* col_ptr;
   const RowIndex* ri;
   const int* indices;
   const ag_frame* frames;
@@ -154,7 +155,7 @@ k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
         const int c = col < rows[0] ? 0 : 1;
         const int k = klo[c] + (c == 0 ? col : col - rows[0]);
         int j0, j1;
-        row_run(ri, A.row_ptr, A.pts, c, k, q.y, A.rpad, j0, j1);
+        row_run(ri, A.row_ptr, A.col_ptr, A.pts, c, k, q.x, q.y, A.rpad, j0, j1);
         s_rs[threadIdx.x] = j0;
         s_pre[threadIdx.x] = j1;
       }
@@ -547,7 +548,7 @@ k_box_points(const SweepArgs A, const __grid_constant__ HandConst hc, int s, int
         __syncthreads();
         if (threadIdx.x == 0) {
           int j0, j1;
-          row_run(ri, A.row_ptr, A.pts, c, k, q.y, A.rpad, j0, j1);
+          row_run(ri, A.row_ptr, A.col_ptr, A.pts, c, k, q.x, q.y, A.rpad, j0, j1);
           s_j0 = j0;
           s_j1 = j1;
         }
@@ -672,6 +673,7 @@ static SweepArgs make_args(Ctx* c, const int* d_indices, int n, const ag_frame* 
   SweepArgs A;
   A.pts = c->vox.as<GPoint>();
   A.row_ptr = c->row_ptr.as<int>();
+  A.col_ptr = c->col_ptr.as<int>();
   A.ri = c->row_index.as<RowIndex>();
   A.indices = d_indices;
   A.frames = d_frames;
