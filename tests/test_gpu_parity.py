@@ -391,3 +391,53 @@ def test_cpp_localization_shim_end_to_end(tmp_path, linear_svm_path):
     gg, keep = ctx.classify(api.Svm(linear_svm_path), g)
     assert f"{len(g)} hands, {int(keep.sum())} antipodal" in out.stdout, out.stdout[-400:]
     ctx.close()
+
+
+@pytest.mark.parametrize("config", [1, 3, 5])
+def test_other_baseline_configs_full_size(ctx, config, linear_svm_path):
+    """BASELINE.json configs 1 (tabletop, 400 samples, boundary filter), 3 (two registered views,
+    4000 samples) and 5 (fused 7-view scene, 20000 samples) at full size: voxelisation bit-identical to the
+    oracle, sampled frames tight against the extended-precision solve, and the size-independent properties."""
+    from oracle import oracle as O
+    pts, size_left, P, S = scenes.config_cloud(config)
+    ctx.set_params(P)
+    ctx.set_svm(None)
+    xyz, cam = ctx.preprocess(pts, size_left)
+    xo, co = O.preprocess(pts, size_left, P, False)
+    assert (_u32(xyz) == _u32(xo)).all() and (cam == co).all()
+    if config == 3:
+        assert set(np.unique(cam)) == {0, 1}
+    g = ctx.localize(pts, size_left)
+    t = ctx.timings()
+    assert t["n_voxels"] == len(xo) and t["n_samples"] == min(S, len(xo)) and len(g) > 50
+    key = g["sample_slot"].astype(np.int64) * 8 + g["orientation"]
+    assert (np.diff(key) > 0).all()
+    idx_all = O.draw_samples(len(xo), S, P.seed)
+    assert np.array_equal(np.unique(g["sample_index"]), np.intersect1d(idx_all, g["sample_index"]))  # bit-exact sample indices
+    assert np.allclose(np.einsum("ij,ij->i", g["approach"], g["binormal"]), 0, atol=1e-12)
+    if P.filters_boundaries:  # config 1: localization.cpp:364-388
+        ws = np.array(list(P.workspace))
+        d = np.abs(g["surface"][:, [0, 0, 1, 1, 2, 2]] - ws[None, :])
+        assert (d >= 0.02).all()
+    # frames of a subset of the samples against the extended-precision oracle
+    tree = O.Tree(xo)
+    sub = idx_all[:: max(1, len(idx_all) // 64)]
+    fg = ctx.fit_quadrics(sub, 0.03)
+    ex = O.fit_quadrics(tree, co, sub, 0.03, P, sum_perm=-1)["frames"]
+    assert np.array_equal(fg["num_neighbors"], ex["num_neighbors"])
+    det = ex["num_neighbors"] >= 10
+    assert np.linalg.norm(fg["normal"] - ex["normal"], axis=1)[det].max() <= 1e-9
+    # hypotheses of those samples against the oracle sweep on identical frames (bit-exact)
+    normals = np.zeros((len(xo), 3))
+    normals[sub] = fg["normal"]
+    H = O.find_hands(tree, co, sub, fg, co[sub], normals, P)
+    gs = ctx.hand_sweep(sub, fg, normals)
+    go = H.grasps
+    assert len(gs) == len(go)
+    for nm in ("sample_index", "orientation", "cam_source", "num_points", "half_antipodal", "full_antipodal"):
+        assert np.array_equal(gs[nm], go[nm]), nm
+    for nm in ("approach", "binormal", "bottom", "surface", "width"):
+        assert (_u64(gs[nm]) == _u64(go[nm])).all(), nm
+    gg, keep = ctx.classify(api.Svm(linear_svm_path), gs)
+    keep_o = H.classify(O.Svm(linear_svm_path), P)
+    assert (_u32(gg["score"]) == _u32(H.grasps["score"])).all() and np.array_equal(keep, keep_o)
