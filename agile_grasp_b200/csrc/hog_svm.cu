@@ -162,7 +162,7 @@ __device__ __forceinline__ uint32_t bits_at(const uint32_t* img, int bit0) {  //
   return __funnelshift_r(img[w], img[w + 1], sh);
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slots, int n_bound,
           const int* __restrict__ n_dev, SvmDev svm, float* __restrict__ descriptors, float* __restrict__ scores,
           ag_grasp* __restrict__ grasps_out) {
@@ -205,19 +205,16 @@ k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slo
     s_yn[r][w] = U & ~D & valid;
   }
   __syncthreads();
-  // 3. column masks of pixels with a non-zero gradient
-  if (tid < W) {
-    const int x = tid, w = x >> 5, sh = x & 31;
-    uint32_t m0 = 0, m1 = 0, m2 = 0;
-    for (int r = 0; r < H; r++) {
+  // 3. column masks of pixels with a non-zero gradient: one thread per (column, 32-row segment)
+  if (tid < W * 3) {
+    const int x = tid % W, seg = tid / W, w = x >> 5, sh = x & 31;
+    const int r0 = seg * 32, r1 = min(H, r0 + 32);
+    uint32_t m = 0;
+    for (int r = r0; r < r1; r++) {
       const uint32_t nz = ((s_xp[r][w] | s_xn[r][w] | s_yp[r][w] | s_yn[r][w]) >> sh) & 1u;
-      if (r < 32) m0 |= nz << r;
-      else if (r < 64) m1 |= nz << (r - 32);
-      else m2 |= nz << (r - 64);
+      m |= nz << (r - r0);
     }
-    s_col[x][0] = m0;
-    s_col[x][1] = m1;
-    s_col[x][2] = m2;
+    s_col[x][seg] = m;
   }
   __syncthreads();
   // 4. block histograms: one thread per (distinct block, cell); only pixels with a gradient are visited,
@@ -257,26 +254,40 @@ k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slo
     for (int b = 0; b < 9; b++) s_hist[ub * 36 + cell * 9 + b] = h[b];
   }
   __syncthreads();
-  // 5. L2-Hys normalisation per block (HOGCache::normalizeBlockHistogram), 4 interleaved partial sums
-  if (tid < NUB) {
-    float* hist = s_hist + tid * 36;
-    float part[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int i = 0; i < 36; i += 4)
+  // 5. L2-Hys normalisation per block (HOGCache::normalizeBlockHistogram).  OpenCV keeps 4 interleaved
+  //    partial sums (element i goes to partial i mod 4) and combines them as (p0+p1)+(p2+p3): thread l of
+  //    a 4-thread group owns partial l, so the binary32 rounding sequence is identical.
+  {
+    const bool act = tid < NUB * 4;
+    float* hist = s_hist + (act ? (tid >> 2) : 0) * 36;
+    const int l = tid & 3, gbase = lane & ~3;
+    float v[9];
+    float part = 0.f;
 #pragma unroll
-      for (int l = 0; l < 4; l++) part[l] = __fadd_rn(part[l], __fmul_rn(hist[i + l], hist[i + l]));
-    float sum = __fadd_rn(__fadd_rn(part[0], part[1]), __fadd_rn(part[2], part[3]));
+    for (int k = 0; k < 9; k++) {
+      v[k] = hist[l + 4 * k];
+      part = __fadd_rn(part, __fmul_rn(v[k], v[k]));
+    }
+    float p0 = __shfl_sync(0xffffffffu, part, gbase), p1 = __shfl_sync(0xffffffffu, part, gbase + 1);
+    float p2 = __shfl_sync(0xffffffffu, part, gbase + 2), p3 = __shfl_sync(0xffffffffu, part, gbase + 3);
+    float sum = __fadd_rn(__fadd_rn(p0, p1), __fadd_rn(p2, p3));
     float scale = __fdiv_rn(1.f, __fadd_rn(__fsqrt_rn(sum), __fmul_rn(36.f, 0.1f)));
-    part[0] = part[1] = part[2] = part[3] = 0.f;
-    for (int i = 0; i < 36; i += 4)
+    part = 0.f;
 #pragma unroll
-      for (int l = 0; l < 4; l++) {
-        const float p = fminf(__fmul_rn(hist[i + l], scale), 0.2f);
-        hist[i + l] = p;
-        part[l] = __fadd_rn(part[l], __fmul_rn(p, p));
-      }
-    sum = __fadd_rn(__fadd_rn(part[0], part[1]), __fadd_rn(part[2], part[3]));
+    for (int k = 0; k < 9; k++) {
+      v[k] = fminf(__fmul_rn(v[k], scale), 0.2f);
+      part = __fadd_rn(part, __fmul_rn(v[k], v[k]));
+    }
+    p0 = __shfl_sync(0xffffffffu, part, gbase);
+    p1 = __shfl_sync(0xffffffffu, part, gbase + 1);
+    p2 = __shfl_sync(0xffffffffu, part, gbase + 2);
+    p3 = __shfl_sync(0xffffffffu, part, gbase + 3);
+    sum = __fadd_rn(__fadd_rn(p0, p1), __fadd_rn(p2, p3));
     scale = __fdiv_rn(1.f, __fadd_rn(__fsqrt_rn(sum), 1e-3f));
-    for (int i = 0; i < 36; i++) hist[i] = __fmul_rn(hist[i], scale);
+    if (act) {
+#pragma unroll
+      for (int k = 0; k < 9; k++) hist[l + 4 * k] = __fmul_rn(v[k], scale);
+    }
   }
   __syncthreads();
   // descriptor group k4 (4 consecutive floats) -> histogram entry: k = ((w*7 + bx)*7 + by)*36 + e
