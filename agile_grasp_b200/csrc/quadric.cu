@@ -116,38 +116,104 @@ __device__ __forceinline__ void walk_runs(const GPoint* __restrict__ pts, const 
 }
 
 // ---- kernel 1: moments ------------------------------------------------------------------------
-// Roofline-graded kernel.  One warp per sample.  Lane r finds where x-row r of the ball starts (ONE
-// lower-bound search on y; the run's end is detected while streaming, because a row is sorted by y).
-// The warp then streams two rows per step — one per half-warp, 16 contiguous 16-byte records each —
-// tests membership with FLANN's binary32 expression, compacts accepted points through a 64-entry
-// shared ring and accumulates the 35 monomial moments of full 32-point batches in binary64 registers.
-__global__ void __launch_bounds__(kWarps * 32, 4)
+// Roofline-graded kernel.  One warp per sample, four independent warps per CTA.  Per sample:
+//   1. lane r finds the candidate run of x-row r of the ball (two independent loads from the column table);
+//      a run is contiguous in the voxel list, so
+//   2. each row lane issues ONE bulk async copy (TMA, cp.async.bulk) of its run into the warp's shared
+//      staging buffer at the run's prefix offset; one mbarrier transaction count tracks all of them — every
+//      load of the ball is in flight at once, no registers are held for them;
+//   3. the staged candidates are tested 32 per step with FLANN's exact binary32 expression and compacted
+//      IN PLACE (the write cursor never passes the read cursor);
+//   4. full 32-point batches of accepted points are accumulated into the 35 monomial moments in binary64
+//      registers, in coordinates centred on the sample (exact: differences of binary32 values); a remainder
+//      of < 32 points is carried to the front of the buffer for the next pass (balls with more candidates
+//      than the buffer holds, or more than 32 rows, take several passes);
+//   5. the 32 x 35 partial sums are transposed through the same buffer (lane i sums moment i), the
+//      power-of-two coordinate scale is applied exactly (moment of degree d times scale^d), 36 doubles out.
+constexpr int kCandCap = 560;               // staging buffer entries per warp (8960 B = 35 x 32 doubles)
+constexpr int kCandNew = kCandCap - 32;     // new candidates per pass (the rest holds the carried remainder)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done)
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy (16-byte aligned, size a multiple of 16), completion counted on the mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// explicit shared-space 16-byte accesses (one 32-bit address register, immediate offsets)
+__device__ __forceinline__ GPoint lds_point(uint32_t addr) {
+  GPoint p;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(p.x), "=f"(p.y), "=f"(p.z), "=r"(p.tag)
+               : "r"(addr)
+               : "memory");
+  return p;
+}
+__device__ __forceinline__ void sts_point(uint32_t addr, const GPoint& p) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(p.x), "f"(p.y), "f"(p.z), "r"(p.tag)
+               : "memory");
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+#ifndef AG_MOM_MINB
+#define AG_MOM_MINB 4
+#endif
+__global__ void __launch_bounds__(kWarps * 32, AG_MOM_MINB)
 k_taubin_moments(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr, const int* __restrict__ col_ptr,
                  const RowIndex* __restrict__ rip,
                  const int* __restrict__ indices, int n_samples_max, const int* __restrict__ d_count, float r2,
-                 double rpad, double inv_r, double* __restrict__ moments, int* __restrict__ nn_counts,
-                 unsigned long long* __restrict__ counters) {
-  __shared__ GPoint s_ring[kWarps][64];
+                 double rpad, double scale, double* __restrict__ moments, int2* __restrict__ nn_counts) {
+  __shared__ __align__(16) GPoint s_cand[kWarps][kCandCap];
+  static_assert(kCandCap * sizeof(GPoint) >= 32 * 33 * sizeof(double), "the reduction reuses the staging buffer");
+  __shared__ __align__(8) unsigned long long s_bar[kWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * kWarps + warp;
-  const RowIndex ri = *rip;
+  // the index descriptor is read in place (L1 hits) instead of being held in ~30 registers per thread
+  const RowIndex& ri = *rip;
   if (s >= n_samples_max || s >= *d_count) return;
   const int idx = indices[s];
   if (idx < 0 || idx >= ri.n_points) return;
   const GPoint q = pts[idx];
   const double qx = double(q.x), qy = double(q.y), qz = double(q.z);
-  GPoint* ring = s_ring[warp];
-  double acc[kNumMoments];
+  uint32_t cand_s, bar;  // opaque to the compiler so the addresses stay in registers instead of being rebuilt
+  asm volatile("mov.u32 %0, %1;" : "=r"(cand_s) : "r"(smem_u32(s_cand[warp])));
+  asm volatile("mov.u32 %0, %1;" : "=r"(bar) : "r"(smem_u32(&s_bar[warp])));
+  const uint32_t lane_s = cand_s + uint32_t(lane) * 16u;  // this lane's slot of a 32-point batch
+  if (lane == 0) mbar_init(bar, 1);
+  fence_proxy_async_smem();  // the initialised barrier must be visible to the async proxy
+  __syncwarp();
+  uint32_t parity = 0;
+  double acc[kNumMoments];  // acc[0] (the count) is filled from the integer counter at the end
 #pragma unroll
   for (int i = 0; i < kNumMoments; i++) acc[i] = 0.0;
-  int cam1 = 0, n_cand = 0, head = 0, qn = 0;
+  int cam1 = 0, n_cand = 0, n_acc = 0, carry = 0;
   const unsigned lt = (1u << lane) - 1u;
-  const int half_id = lane >> 4, l16 = lane & 15;
-  auto process = [&](const GPoint& p, bool active) {
-    if (!active) return;
-    const double x = (double(p.x) - qx) * inv_r, y = (double(p.y) - qy) * inv_r, z = (double(p.z) - qz) * inv_r;
+  auto process = [&](const GPoint& p) {
+    const double x = double(p.x) - qx, y = double(p.y) - qy, z = double(p.z) - qz;
     const double x2 = x * x, y2 = y * y, z2 = z * z, xy = x * y, yz = y * z, xz = x * z;
-    acc[0] += 1.0;
     acc[1] += x; acc[2] += y; acc[3] += z;
     acc[4] += x2; acc[5] += y2; acc[6] += z2; acc[7] += xy; acc[8] += yz; acc[9] += xz;
     acc[10] += x2 * x; acc[11] += y2 * y; acc[12] += z2 * z; acc[13] += x2 * y; acc[14] += x2 * z;
@@ -155,68 +221,120 @@ k_taubin_moments(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr
     acc[20] += x2 * x2; acc[21] += y2 * y2; acc[22] += z2 * z2; acc[23] += x2 * xy; acc[24] += x2 * xz;
     acc[25] += xy * y2; acc[26] += y2 * yz; acc[27] += xz * z2; acc[28] += yz * z2; acc[29] += x2 * y2;
     acc[30] += y2 * z2; acc[31] += x2 * z2; acc[32] += x2 * yz; acc[33] += xy * yz; acc[34] += xz * yz;
-    cam1 += (p.tag & kTagCamBit) ? 1 : 0;
+    cam1 += int(p.tag & kTagCamBit);
   };
-  for (int c = 0; c < 2; c++) {
-    if (ri.count[c] == 0) continue;
-    int k_lo, k_hi;
-    row_range(ri, c, q.x, rpad, k_lo, k_hi);
-    for (int kb = k_lo; kb <= k_hi; kb += 32) {  // batches of 32 rows (one batch for the shipped radii)
+  // a point that fails the radius test and contributes zero to every sum
+  GPoint far_pt;
+  far_pt.x = 1e30f;
+  far_pt.y = far_pt.z = 0.f;
+  far_pt.tag = 0;
+  // one loop over (camera, batch of 32 x-rows): one batch per camera for the shipped radii
+  int k_lo0 = 0, k_hi0 = -1, k_lo1 = 0, k_hi1 = -1;
+  if (ri.count[0] > 0) row_range(ri, 0, q.x, rpad, k_lo0, k_hi0);
+  if (ri.count[1] > 0) row_range(ri, 1, q.x, rpad, k_lo1, k_hi1);
+  const int nb0 = k_hi0 >= k_lo0 ? (k_hi0 - k_lo0) / 32 + 1 : 0;
+  const int nb1 = k_hi1 >= k_lo1 ? (k_hi1 - k_lo1) / 32 + 1 : 0;
+  for (int t = 0; t < nb0 + nb1; t++) {
+    {
+      const int c = t < nb0 ? 0 : 1;
+      const int kb = c ? k_lo1 + (t - nb0) * 32 : k_lo0 + t * 32;
+      const int k_hi = c ? k_hi1 : k_hi0;
       const int nrows = min(32, k_hi - kb + 1);
-      // lane r: candidate run [j_lo, j_end) of row r (column table: two independent loads)
       int j_lo = 0, j_end = 0;
       if (lane < nrows) row_run(ri, row_ptr, col_ptr, pts, c, kb + lane, q.x, q.y, rpad, j_lo, j_end);
-      for (int r = 0; r < nrows; r += 2) {
-        const int src = min(r + half_id, 31);
-        const bool has = r + half_id < nrows;
-        const int a = __shfl_sync(0xffffffffu, j_lo, src);
-        const int e_src = __shfl_sync(0xffffffffu, j_end, src);  // (all lanes must execute the shuffle)
-        const int e = has ? e_src : a;
-        const int len = max(__shfl_sync(0xffffffffu, e - a, 0), __shfl_sync(0xffffffffu, e - a, 16));
-        n_cand += __shfl_sync(0xffffffffu, e - a, 0) + __shfl_sync(0xffffffffu, e - a, 16);
-        for (int off = 0; off < len; off += 16) {
-          const int j = a + off + l16;
-          GPoint p;
-          p.x = p.y = p.z = 0.f;
-          p.tag = 0;
-          const bool valid = j < e;
-          if (valid) p = pts[j];
-          const bool ok = valid && dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z) < r2;
-          const unsigned m = __ballot_sync(0xffffffffu, ok);
-          if (m) {
-            if (ok) ring[(head + qn + __popc(m & lt)) & 63] = p;
-            qn += __popc(m);
-            __syncwarp();
-            if (qn >= 32) {
-              const GPoint v = ring[(head + lane) & 63];
-              __syncwarp();
-              process(v, true);
-              head = (head + 32) & 63;
-              qn -= 32;
-            }
-          }
+      int rem = max(0, j_end - j_lo);
+      n_cand += rem;
+      while (true) {
+        int incl = rem;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
         }
+        const int total_rem = __shfl_sync(0xffffffffu, incl, 31);
+        if (total_rem == 0) break;
+        const int excl = incl - rem;
+        const int take = min(rem, max(0, kCandNew - excl));
+        const int total = min(total_rem, kCandNew);
+        fence_proxy_async_smem();  // earlier generic-proxy accesses of the buffer precede the async writes
+        __syncwarp();
+        if (lane == 0) mbar_expect_tx(bar, uint32_t(total) * 16u);
+        __syncwarp();
+        if (take > 0) bulk_g2s(cand_s + uint32_t(carry + excl) * 16u, pts + j_lo, uint32_t(take) * 16u, bar);
+        j_lo += take;
+        rem -= take;
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        // membership test + in-place compaction, 64 candidates per step (two independent chains)
+        const int end = carry + total;
+        int w = carry;
+        for (int base = carry; base < end; base += 64) {
+          const int i0 = base + lane, i1 = i0 + 32;
+          GPoint p0 = far_pt, p1 = far_pt;
+          if (i0 < end) p0 = lds_point(lane_s + uint32_t(base) * 16u);
+          if (i1 < end) p1 = lds_point(lane_s + uint32_t(base) * 16u + 512u);
+          const bool ok0 = dist2_flann(q.x, q.y, q.z, p0.x, p0.y, p0.z) < r2;
+          const bool ok1 = dist2_flann(q.x, q.y, q.z, p1.x, p1.y, p1.z) < r2;
+          const unsigned m0 = __ballot_sync(0xffffffffu, ok0), m1 = __ballot_sync(0xffffffffu, ok1);
+          const int w1 = w + __popc(m0);
+          if (ok0) sts_point(cand_s + uint32_t(w + __popc(m0 & lt)) * 16u, p0);
+          if (ok1) sts_point(cand_s + uint32_t(w1 + __popc(m1 & lt)) * 16u, p1);
+          w = w1 + __popc(m1);
+        }
+        __syncwarp();
+        n_acc += w - carry;
+        const int nfull = w & ~31;
+        for (int b = 0; b < nfull; b += 32) process(lds_point(lane_s + uint32_t(b) * 16u));
+        carry = w - nfull;
+        if (nfull > 0 && carry > 0) {  // move the remainder to the front
+          GPoint v = far_pt;
+          if (lane < carry) v = lds_point(lane_s + uint32_t(nfull) * 16u);
+          __syncwarp();
+          if (lane < carry) sts_point(lane_s, v);
+        }
+        __syncwarp();
       }
     }
   }
-  if (qn > 0) {
-    const GPoint v = ring[(head + lane) & 63];
-    process(v, lane < qn);
+  if (carry > 0) {  // inactive lanes process the sample itself: every term is exactly zero
+    GPoint v = q;
+    v.tag = 0;
+    if (lane < carry) v = lds_point(lane_s);
+    process(v);
   }
-  // warp reduction: moments 0..31 by recursive halving (lane i ends up with moment i), 32..34 by butterflies
-  const double r32 = warp_reduce_transpose32(acc);
-  const double m32 = warp_sum(acc[32]), m33 = warp_sum(acc[33]), m34 = warp_sum(acc[34]);
+  // warp reduction: moments 1..32 transposed through shared memory with a 33-double row pitch (lane i
+  // sums moment i + 1 with immediate offsets, bank-conflict free), 33..34 by butterflies
+  __syncwarp();
+#pragma unroll
+  for (int m = 0; m < 32; m++) sts_f64(cand_s + uint32_t(m * 33 + 0) * 8u + uint32_t(lane) * 8u, acc[m + 1]);
+  const double m33 = warp_sum(acc[33]), m34 = warp_sum(acc[34]);
   cam1 = __reduce_add_sync(0xffffffffu, cam1);
+  n_cand = __reduce_add_sync(0xffffffffu, n_cand);
+  __syncwarp();
+  double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+  const uint32_t row_s = cand_s + uint32_t(lane) * (33u * 8u);
+#pragma unroll
+  for (int k = 0; k < 32; k += 4) {
+    t0 += lds_f64(row_s + uint32_t(k) * 8u);
+    t1 += lds_f64(row_s + uint32_t(k + 1) * 8u);
+    t2 += lds_f64(row_s + uint32_t(k + 2) * 8u);
+    t3 += lds_f64(row_s + uint32_t(k + 3) * 8u);
+  }
+  const double rsum = (t0 + t1) + (t2 + t3);                       // moment lane + 1
+  double r32 = __shfl_up_sync(0xffffffffu, rsum, 1);               // lane i (i >= 1): moment i
+  const double m32 = __shfl_sync(0xffffffffu, rsum, 31);           // moment 32
+  if (lane == 0) r32 = double(n_acc);                              // moment 0: the neighbour count
+  // coordinate scale (a power of two, so this equals accumulating scaled coordinates bit for bit)
+  const double s2 = scale * scale, s4 = s2 * s2;
+  const double scl = lane == 0 ? 1.0 : lane <= 3 ? scale : lane <= 9 ? s2 : lane <= 19 ? s2 * scale : s4;
   double* out = moments + size_t(s) * kMomentStride;
-  out[lane] = r32;
+  out[lane] = r32 * scl;
   if (lane == 0) {
-    out[32] = m32;
-    out[33] = m33;
-    out[34] = m34;
+    out[32] = m32 * s4;
+    out[33] = m33 * s4;
+    out[34] = m34 * s4;
     out[35] = double(cam1);
-    nn_counts[s] = int(r32);
-    atomicAdd(&counters[0], (unsigned long long)(r32));
-    atomicAdd(&counters[1], (unsigned long long)(n_cand));
+    nn_counts[s] = make_int2(int(r32), n_cand);
   }
 }
 
@@ -743,13 +861,34 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const int* __restrict__ row_ptr,
   }
 }
 
-// points that received a normal carry a tag bit so the sweep only fetches normals that exist
-__global__ void k_mark_normals(GPoint* pts, const RowIndex* __restrict__ rip, const int* __restrict__ indices, int n,
-                               const int* __restrict__ d_count) {
+// one thread per sample after the fit: totals of the per-sample neighbour / candidate counts (one atomic
+// pair per CTA, reported through ag_timings) and, when the normals were written to cloud_normals_, the
+// tag bit that lets the sweep fetch only normals that exist
+__global__ void k_quadric_finish(GPoint* pts, const RowIndex* __restrict__ rip, const int* __restrict__ indices, int n,
+                                 const int* __restrict__ d_count, const int2* __restrict__ nn_counts,
+                                 unsigned long long* __restrict__ counters, int mark) {
+  __shared__ unsigned long long s_sum[2];
+  if (threadIdx.x < 2) s_sum[threadIdx.x] = 0ull;
+  __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || i >= *d_count) return;
-  const int idx = indices[i];
-  if (idx >= 0 && idx < rip->n_points) atomicOr(&pts[idx].tag, kTagNormalBit);
+  int nn = 0, nc = 0;
+  if (i < n && i < *d_count) {
+    const int idx = indices[i];
+    if (idx >= 0 && idx < rip->n_points) {
+      if (mark) atomicOr(&pts[idx].tag, kTagNormalBit);
+      const int2 v = nn_counts[i];
+      nn = v.x;
+      nc = v.y;
+    }
+  }
+  nn = __reduce_add_sync(0xffffffffu, nn);
+  nc = __reduce_add_sync(0xffffffffu, nc);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&s_sum[0], (unsigned long long)nn);
+    atomicAdd(&s_sum[1], (unsigned long long)nc);
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 && s_sum[threadIdx.x]) atomicAdd(&counters[threadIdx.x], s_sum[threadIdx.x]);
 }
 
 }  // namespace
@@ -757,20 +896,21 @@ __global__ void k_mark_normals(GPoint* pts, const RowIndex* __restrict__ rip, co
 int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count, double radius, ag_frame* d_frames,
                         bool write_normals) {
   if (n <= 0) return AG_OK;
-  if (c->moments.reserve(size_t(n) * kMomentStride * sizeof(double)) || c->nn_counts.reserve(size_t(n) * 4) ||
+  if (c->moments.reserve(size_t(n) * kMomentStride * sizeof(double)) || c->nn_counts.reserve(size_t(n) * 8) ||
       c->counters.reserve(64))
     return AG_ERR_CUDA;
   const float r2 = float(radius * radius);  // PCL hands radius*radius to FLANN as float
   const double rpad = sqrt(double(r2)) * (1.0 + 1e-5) + 1e-7;
-  const double inv_r = 1.0 / radius;
+  // coordinates are centred on the sample and scaled by the power of two nearest to 1/r (the fit is
+  // invariant under translation and uniform scale; a power of two makes the scaling exact)
+  const double inv_r = ldexp(1.0, int(lrint(log2(1.0 / radius))));
   const int blocks = (n + kWarps - 1) / kWarps;
   unsigned long long* ctr = c->counters.as<unsigned long long>();
   const RowIndex* ri = c->row_index.as<RowIndex>();
   cudaEventRecord(c->ev_k[0], c->stream);
   k_taubin_moments<<<blocks, kWarps * 32, 0, c->stream>>>(c->vox.as<GPoint>(), c->row_ptr.as<int>(),
-                                                          c->col_ptr.as<int>(), ri, d_indices, n,
-                                                          d_count, r2, rpad, inv_r, c->moments.as<double>(),
-                                                          c->nn_counts.as<int>(), ctr);
+                                                          c->col_ptr.as<int>(), ri, d_indices, n, d_count, r2, rpad,
+                                                          inv_r, c->moments.as<double>(), c->nn_counts.as<int2>());
   cudaEventRecord(c->ev_k[1], c->stream);
   const size_t smem = sizeof(AxesSmem) * kWarps;
   static bool attr_set = false;
@@ -786,9 +926,9 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
       h.cam[0][0], h.cam[0][1], h.cam[0][2], h.cam[1][0], h.cam[1][1], h.cam[1][2], d_frames,
       write_normals ? c->normals.as<double>() : nullptr);
   cudaEventRecord(c->ev_k[2], c->stream);
-  c->launches += write_normals ? 3 : 2;
-  if (write_normals)
-    k_mark_normals<<<(n + 255) / 256, 256, 0, c->stream>>>(c->vox.as<GPoint>(), ri, d_indices, n, d_count);
+  c->launches += 3;
+  k_quadric_finish<<<(n + 255) / 256, 256, 0, c->stream>>>(c->vox.as<GPoint>(), ri, d_indices, n, d_count,
+                                                          c->nn_counts.as<int2>(), ctr, write_normals ? 1 : 0);
   AG_CUDA_CHECK(cudaGetLastError());
   return AG_OK;
 }
