@@ -44,6 +44,7 @@ struct RowIndex {         // lives in device memory, written by the voxelisation
 };
 constexpr int kErrKeyOverflow = 1;   // voxel key outside the workspace-derived bit budget
 constexpr int kErrBadIndex = 2;      // a caller-supplied sample index is outside the voxelised cloud
+constexpr int kErrBallOverflow = 4;  // a radius ball held more points than a neighbour-pool slot
 
 // voxel record: xyz + tag.  tag bit 0 = camera source, bit 1 = "cloud_normals_ holds a non-zero normal"
 struct __align__(16) GPoint {

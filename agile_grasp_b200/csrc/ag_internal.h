@@ -83,6 +83,9 @@ struct Ctx {
   size_t d_export_cap = 0;
   // samples
   DevBuf samples, moments, frames, nn_counts, all_frames;
+  DevBuf nbr_heads;  // per sample of the chunk: sample xyz + neighbour count (float4)
+  DevBuf nbr_pool;   // neighbour lists of the current chunk of samples: stride x 16-byte records per sample
+  bool two_cams = false;  // the last cloud had points of both cameras (sizes the neighbour pool)
   int n_samples = 0;
   // sweep outputs
   DevBuf grasps_raw, valid, images_raw, hyp_slots, grasps, counters, scores, descriptors, sweep_dbg, overflow;
@@ -98,7 +101,7 @@ struct Ctx {
   std::vector<ag_grasp> last_grasps;
   ag_timings timings;
   cudaEvent_t ev[10];
-  cudaEvent_t ev_k[3];   // around k_taubin_moments / k_taubin_axes
+  cudaEvent_t ev_k[4];   // around k_ball_search / k_taubin_moments / k_taubin_axes
   int launches = 0;      // own-kernel launch counter (reset per localize call)
 };
 

@@ -279,6 +279,7 @@ static int localize_core(Ctx* c, const void* d_points, int stride, int n_in, int
   c->launches = 0;
   cudaStream_t st = c->stream;
   cudaEventRecord(c->ev[1], st);
+  c->two_cams = size_left < n_in;
   int rc = preprocess_device(c, d_points, stride, n_in, size_left);
   if (rc) return rc;
   cudaEventRecord(c->ev[2], st);
@@ -361,6 +362,10 @@ static int localize_core(Ctx* c, const void* d_points, int stride, int n_in, int
     set_error("sample index out of range of the voxelised cloud");
     return AG_ERR_INVALID;
   }
+  if (h->error & kErrBallOverflow) {
+    set_error("a radius ball holds more points than a neighbour-pool slot (cloud far denser than a voxelised surface)");
+    return AG_ERR_CAPACITY;
+  }
   int Hn = h->n_hyp;
   c->n_hyp = Hn;
   c->images_valid = true;
@@ -389,8 +394,9 @@ static int localize_core(Ctx* c, const void* d_points, int stride, int n_in, int
   c->timings.d2h_ms = elapsed(c->ev[6], c->ev[7]);
   c->timings.total_ms = elapsed(c->ev[0], c->ev[7]);
   c->timings.n_hyp = Hn;
-  c->timings.moments_ms = elapsed(c->ev_k[0], c->ev_k[1]);
-  c->timings.axes_ms = elapsed(c->ev_k[1], c->ev_k[2]);
+  c->timings.search_ms = elapsed(c->ev_k[0], c->ev_k[1]);
+  c->timings.moments_ms = elapsed(c->ev_k[1], c->ev_k[2]);
+  c->timings.axes_ms = elapsed(c->ev_k[2], c->ev_k[3]);
   c->timings.kernel_launches = c->launches;
   c->timings.taubin_neighbor_points = int64_t(h->counters[0]);
   c->timings.taubin_candidates = int64_t(h->counters[1]);
@@ -482,7 +488,7 @@ void ag_destroy(ag_ctx* h) {
   if (c.h_out) cudaFreeHost(c.h_out);
   for (DevBuf* b : {&c.raw, &c.keys, &c.keys_sorted, &c.keys_unique, &c.cub_tmp, &c.block_counts, &c.misc, &c.vox,
                     &c.row_ptr, &c.col_ptr, &c.row_index, &c.all_frames,
-                    &c.normals, &c.samples, &c.moments, &c.frames, &c.nn_counts, &c.grasps_raw, &c.valid,
+                    &c.normals, &c.samples, &c.moments, &c.frames, &c.nn_counts, &c.nbr_pool, &c.nbr_heads, &c.grasps_raw, &c.valid,
                     &c.images_raw, &c.hyp_slots, &c.grasps, &c.counters, &c.scores, &c.descriptors, &c.sweep_dbg, &c.overflow})
     b->release();
   if (c.h_pinned) cudaFreeHost(c.h_pinned);
@@ -722,6 +728,7 @@ int ag_preprocess(ag_ctx* h, const void* points, int stride, int n_in, int size_
   if (c.raw.reserve(bytes)) return AG_ERR_CUDA;
   AG_CUDA_CHECK(cudaMemcpyAsync(c.raw.p, points, bytes, cudaMemcpyHostToDevice, c.stream));
   c.launches = 0;
+  c.two_cams = size_left < n_in;
   int rc = preprocess_device(&c, c.raw.p, stride, n_in, size_left);
   if (rc) return rc;
   rc = fetch_cloud_size(&c);
@@ -749,12 +756,14 @@ int ag_set_cloud(ag_ctx* h, const float* xyz, const int32_t* cam, int n) {
   Ctx& c = h->c;
   cudaSetDevice(c.device);
   c.images_valid = false;
+  c.two_cams = false;
   std::vector<GPoint> v(n);
   for (int i = 0; i < n; i++) {
     v[i].x = xyz[3 * i];
     v[i].y = xyz[3 * i + 1];
     v[i].z = xyz[3 * i + 2];
     v[i].tag = (cam && cam[i]) ? kTagCamBit : 0u;
+    if (cam && cam[i]) c.two_cams = true;
   }
   if (c.vox.reserve(std::max<size_t>(16, size_t(n) * 16))) return AG_ERR_CUDA;
   if (n > 0) AG_CUDA_CHECK(cudaMemcpyAsync(c.vox.p, v.data(), size_t(n) * 16, cudaMemcpyHostToDevice, c.stream));
@@ -799,12 +808,21 @@ int ag_fit_quadrics(ag_ctx* h, const int* indices, int n_indices, double radius,
   AG_CUDA_CHECK(cudaMemcpyAsync(frames_out, c.frames.p, size_t(n_indices) * sizeof(ag_frame), cudaMemcpyDeviceToHost,
                                 c.stream));
   unsigned long long ctr[8];
+  int dev_err = 0;
   AG_CUDA_CHECK(cudaMemcpyAsync(ctr, c.counters.p, 64, cudaMemcpyDeviceToHost, c.stream));
+  AG_CUDA_CHECK(cudaMemcpyAsync(&dev_err, &ri->error, 4, cudaMemcpyDeviceToHost, c.stream));
   AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  if (dev_err & kErrBallOverflow) {
+    dev_err &= ~kErrBallOverflow;
+    AG_CUDA_CHECK(cudaMemcpy(&ri->error, &dev_err, 4, cudaMemcpyHostToDevice));
+    set_error("a radius ball holds more points than a neighbour-pool slot (cloud far denser than a voxelised surface)");
+    return AG_ERR_CAPACITY;
+  }
   c.timings.n_samples = n_indices;
   c.timings.n_voxels = c.n_vox;
-  c.timings.moments_ms = elapsed(c.ev_k[0], c.ev_k[1]);
-  c.timings.axes_ms = elapsed(c.ev_k[1], c.ev_k[2]);
+  c.timings.search_ms = elapsed(c.ev_k[0], c.ev_k[1]);
+  c.timings.moments_ms = elapsed(c.ev_k[1], c.ev_k[2]);
+  c.timings.axes_ms = elapsed(c.ev_k[2], c.ev_k[3]);
   c.timings.taubin_neighbor_points = int64_t(ctr[0]);
   c.timings.taubin_candidates = int64_t(ctr[1]);
   return AG_OK;

@@ -56,83 +56,7 @@ constexpr int kMomentStride = 36;  // + count of camera-1 neighbours
 __constant__ int c_basis[10][3] = {{2, 0, 0}, {0, 2, 0}, {0, 0, 2}, {1, 1, 0}, {0, 1, 1},
                                    {1, 0, 1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 0, 0}};
 
-// ---- warp-level ball walk with compaction ----------------------------------------------------
-// The query's candidate runs (one per x-row, see ag_common.cuh) are flattened into one index space
-// and streamed 64 candidates at a time (two independent 16-byte loads in flight per lane); accepted
-// points are compacted through a 64-entry shared ring so that f(point, active) always sees full
-// batches of 32 (except the last).  The ring entry's tag is (point index << 2) | (tag bits).
-constexpr int kRunCap = 128;
-struct RunList {
-  int rs[kRunCap];
-  int pre[kRunCap + 1];
-};
-
-template <typename F>
-__device__ __forceinline__ void walk_runs(const GPoint* __restrict__ pts, const RunList& rl, int n_runs, float qx,
-                                          float qy, float qz, float r2, GPoint* ring, F&& f) {
-  const int lane = threadIdx.x & 31;
-  const unsigned lt = (1u << lane) - 1u;
-  const int total = rl.pre[n_runs];
-  int head = 0, qn = 0, cur = 0;
-  auto push = [&](const GPoint& p, bool ok) {
-    const unsigned m = __ballot_sync(0xffffffffu, ok);
-    if (m == 0) return;
-    if (ok) ring[(head + qn + __popc(m & lt)) & 63] = p;
-    qn += __popc(m);
-    __syncwarp();
-    if (qn >= 32) {
-      const GPoint v = ring[(head + lane) & 63];
-      __syncwarp();
-      f(v, true);
-      head = (head + 32) & 63;
-      qn -= 32;
-    }
-  };
-  for (int base = 0; base < total; base += 64) {
-    GPoint p[2];
-    bool valid[2];
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const int pos = base + u * 32 + lane;
-      valid[u] = pos < total;
-      p[u].x = p[u].y = p[u].z = 0.f;
-      p[u].tag = 0;
-      if (valid[u]) {
-        while (pos >= rl.pre[cur + 1]) cur++;
-        const int j = rl.rs[cur] + (pos - rl.pre[cur]);
-        p[u] = pts[j];
-        p[u].tag = (uint32_t(j) << 2) | (p[u].tag & 3u);
-      }
-    }
-    push(p[0], valid[0] && dist2_flann(qx, qy, qz, p[0].x, p[0].y, p[0].z) < r2);
-    if (base + 32 < total) push(p[1], valid[1] && dist2_flann(qx, qy, qz, p[1].x, p[1].y, p[1].z) < r2);
-  }
-  if (qn > 0) {
-    const GPoint v = ring[(head + lane) & 63];
-    __syncwarp();
-    f(v, lane < qn);
-  }
-  __syncwarp();
-}
-
-// ---- kernel 1: moments ------------------------------------------------------------------------
-// Roofline-graded kernel.  One warp per sample, four independent warps per CTA.  Per sample:
-//   1. lane r finds the candidate run of x-row r of the ball (two independent loads from the column table);
-//      a run is contiguous in the voxel list, so
-//   2. each row lane issues ONE bulk async copy (TMA, cp.async.bulk) of its run into the warp's shared
-//      staging buffer at the run's prefix offset; one mbarrier transaction count tracks all of them — every
-//      load of the ball is in flight at once, no registers are held for them;
-//   3. the staged candidates are tested 32 per step with FLANN's exact binary32 expression and compacted
-//      IN PLACE (the write cursor never passes the read cursor);
-//   4. full 32-point batches of accepted points are accumulated into the 35 monomial moments in binary64
-//      registers, in coordinates centred on the sample (exact: differences of binary32 values); a remainder
-//      of < 32 points is carried to the front of the buffer for the next pass (balls with more candidates
-//      than the buffer holds, or more than 32 rows, take several passes);
-//   5. the 32 x 35 partial sums are transposed through the same buffer (lane i sums moment i), the
-//      power-of-two coordinate scale is applied exactly (moment of degree d times scale^d), 36 doubles out.
-constexpr int kCandCap = 560;               // staging buffer entries per warp (8960 B = 35 x 32 doubles)
-constexpr int kCandNew = kCandCap - 32;     // new candidates per pass (the rest holds the carried remainder)
-
+// ---- PTX helpers: shared-space accesses, mbarrier, TMA bulk copy ---------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -155,7 +79,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-// explicit shared-space 16-byte accesses (one 32-bit address register, immediate offsets)
+// explicit shared-space accesses (one 32-bit address register, immediate offsets)
 __device__ __forceinline__ GPoint lds_point(uint32_t addr) {
   GPoint p;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
@@ -163,10 +87,6 @@ __device__ __forceinline__ GPoint lds_point(uint32_t addr) {
                : "r"(addr)
                : "memory");
   return p;
-}
-__device__ __forceinline__ void sts_point(uint32_t addr, const GPoint& p) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(p.x), "f"(p.y), "f"(p.z), "r"(p.tag)
-               : "memory");
 }
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
   double v;
@@ -177,164 +97,248 @@ __device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
   asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// the result is opaque to the compiler, so the address stays in a register instead of being rebuilt
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
 
-#ifndef AG_MOM_MINB
-#define AG_MOM_MINB 4
-#endif
-__global__ void __launch_bounds__(kWarps * 32, AG_MOM_MINB)
-k_taubin_moments(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr, const int* __restrict__ col_ptr,
-                 const RowIndex* __restrict__ rip,
-                 const int* __restrict__ indices, int n_samples_max, const int* __restrict__ d_count, float r2,
-                 double rpad, double scale, double* __restrict__ moments, int2* __restrict__ nn_counts) {
-  __shared__ __align__(16) GPoint s_cand[kWarps][kCandCap];
-  static_assert(kCandCap * sizeof(GPoint) >= 32 * 33 * sizeof(double), "the reduction reuses the staging buffer");
+// ---- kernel 0: radius search -> neighbour lists -------------------------------------------------
+// Replaces pcl::KdTreeFLANN::radiusSearch (hand_search.cpp:85).  One warp per sample, four independent
+// warps per CTA.  Per sample:
+//   1. lane r finds the candidate run of x-row r of the ball (two independent loads from the column table);
+//      a run is contiguous in the voxel list, so
+//   2. each row lane issues ONE bulk async copy (TMA, cp.async.bulk) of its run into the warp's shared
+//      staging buffer at the run's prefix offset; one mbarrier transaction count tracks all of them — every
+//      load of the ball is in flight at once and no registers are held for them;
+//   3. the staged candidates are tested 64 per step with FLANN's exact binary32 expression and the
+//      accepted records are written, compacted (ballot + popc), to this sample's slot of the neighbour
+//      pool: `stride` 16-byte records per sample, consumed as one contiguous stream by the moments kernel
+//      and by the two normal walks of the axes kernel.
+// List order = (camera, x-row, y, z) = ascending point index; no consumer depends on FLANN's
+// (distance, index) order except through explicit tie-breaks.
+constexpr int kStageCap = 384;  // candidates staged per pass and warp (6 KB); bigger balls take more passes
+
+__global__ void __launch_bounds__(kWarps * 32, 8)
+k_ball_search(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr, const int* __restrict__ col_ptr,
+              RowIndex* __restrict__ rip, const int* __restrict__ indices, int s0, int n_samples_max,
+              const int* __restrict__ d_count, float r2, double rpad, GPoint* __restrict__ pool, int stride,
+              int2* __restrict__ nn_counts, float4* __restrict__ heads) {
+  __shared__ __align__(16) GPoint s_cand[kWarps][kStageCap];
   __shared__ __align__(8) unsigned long long s_bar[kWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int s = blockIdx.x * kWarps + warp;
-  // the index descriptor is read in place (L1 hits) instead of being held in ~30 registers per thread
-  const RowIndex& ri = *rip;
-  if (s >= n_samples_max || s >= *d_count) return;
-  const int idx = indices[s];
-  if (idx < 0 || idx >= ri.n_points) return;
+  const int sl = blockIdx.x * kWarps + warp;  // slot of this launch
+  const int s = s0 + sl;
+  const RowIndex& ri = *rip;  // read in place (L1 hits), not held in registers
+  if (s >= n_samples_max) return;
+  const int idx = s < *d_count ? indices[s] : -1;
+  if (idx < 0 || idx >= ri.n_points) {  // not a sample: an empty list
+    if (lane == 0) {
+      nn_counts[s] = make_int2(0, 0);
+      heads[sl] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+    }
+    return;
+  }
   const GPoint q = pts[idx];
-  const double qx = double(q.x), qy = double(q.y), qz = double(q.z);
-  uint32_t cand_s, bar;  // opaque to the compiler so the addresses stay in registers instead of being rebuilt
-  asm volatile("mov.u32 %0, %1;" : "=r"(cand_s) : "r"(smem_u32(s_cand[warp])));
-  asm volatile("mov.u32 %0, %1;" : "=r"(bar) : "r"(smem_u32(&s_bar[warp])));
-  const uint32_t lane_s = cand_s + uint32_t(lane) * 16u;  // this lane's slot of a 32-point batch
+  const uint32_t cand_s = pin_u32(smem_u32(s_cand[warp])), bar = pin_u32(smem_u32(&s_bar[warp]));
+  const uint32_t lane_s = cand_s + uint32_t(lane) * 16u;
   if (lane == 0) mbar_init(bar, 1);
   fence_proxy_async_smem();  // the initialised barrier must be visible to the async proxy
   __syncwarp();
   uint32_t parity = 0;
-  double acc[kNumMoments];  // acc[0] (the count) is filled from the integer counter at the end
-#pragma unroll
-  for (int i = 0; i < kNumMoments; i++) acc[i] = 0.0;
-  int cam1 = 0, n_cand = 0, n_acc = 0, carry = 0;
+  GPoint* out = pool + size_t(sl) * size_t(stride);
+  int n_cand = 0, n_out = 0;
   const unsigned lt = (1u << lane) - 1u;
-  auto process = [&](const GPoint& p) {
-    const double x = double(p.x) - qx, y = double(p.y) - qy, z = double(p.z) - qz;
-    const double x2 = x * x, y2 = y * y, z2 = z * z, xy = x * y, yz = y * z, xz = x * z;
-    acc[1] += x; acc[2] += y; acc[3] += z;
-    acc[4] += x2; acc[5] += y2; acc[6] += z2; acc[7] += xy; acc[8] += yz; acc[9] += xz;
-    acc[10] += x2 * x; acc[11] += y2 * y; acc[12] += z2 * z; acc[13] += x2 * y; acc[14] += x2 * z;
-    acc[15] += x * y2; acc[16] += y2 * z; acc[17] += x * z2; acc[18] += y * z2; acc[19] += xy * z;
-    acc[20] += x2 * x2; acc[21] += y2 * y2; acc[22] += z2 * z2; acc[23] += x2 * xy; acc[24] += x2 * xz;
-    acc[25] += xy * y2; acc[26] += y2 * yz; acc[27] += xz * z2; acc[28] += yz * z2; acc[29] += x2 * y2;
-    acc[30] += y2 * z2; acc[31] += x2 * z2; acc[32] += x2 * yz; acc[33] += xy * yz; acc[34] += xz * yz;
-    cam1 += int(p.tag & kTagCamBit);
-  };
-  // a point that fails the radius test and contributes zero to every sum
-  GPoint far_pt;
+  GPoint far_pt;  // fails the radius test
   far_pt.x = 1e30f;
   far_pt.y = far_pt.z = 0.f;
   far_pt.tag = 0;
-  // one loop over (camera, batch of 32 x-rows): one batch per camera for the shipped radii
+  // one loop over (camera, batch of 32 x-rows): one batch per camera for the shipped Taubin radii
   int k_lo0 = 0, k_hi0 = -1, k_lo1 = 0, k_hi1 = -1;
   if (ri.count[0] > 0) row_range(ri, 0, q.x, rpad, k_lo0, k_hi0);
   if (ri.count[1] > 0) row_range(ri, 1, q.x, rpad, k_lo1, k_hi1);
   const int nb0 = k_hi0 >= k_lo0 ? (k_hi0 - k_lo0) / 32 + 1 : 0;
   const int nb1 = k_hi1 >= k_lo1 ? (k_hi1 - k_lo1) / 32 + 1 : 0;
   for (int t = 0; t < nb0 + nb1; t++) {
-    {
-      const int c = t < nb0 ? 0 : 1;
-      const int kb = c ? k_lo1 + (t - nb0) * 32 : k_lo0 + t * 32;
-      const int k_hi = c ? k_hi1 : k_hi0;
-      const int nrows = min(32, k_hi - kb + 1);
-      int j_lo = 0, j_end = 0;
-      if (lane < nrows) row_run(ri, row_ptr, col_ptr, pts, c, kb + lane, q.x, q.y, rpad, j_lo, j_end);
-      int rem = max(0, j_end - j_lo);
-      n_cand += rem;
-      while (true) {
-        int incl = rem;
+    const int c = t < nb0 ? 0 : 1;
+    const int kb = c ? k_lo1 + (t - nb0) * 32 : k_lo0 + t * 32;
+    const int k_hi = c ? k_hi1 : k_hi0;
+    const int nrows = min(32, k_hi - kb + 1);
+    int j_lo = 0, j_end = 0;
+    if (lane < nrows) row_run(ri, row_ptr, col_ptr, pts, c, kb + lane, q.x, q.y, rpad, j_lo, j_end);
+    int rem = max(0, j_end - j_lo);
+    n_cand += rem;
+    while (true) {
+      int incl = rem;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += t;
-        }
-        const int total_rem = __shfl_sync(0xffffffffu, incl, 31);
-        if (total_rem == 0) break;
-        const int excl = incl - rem;
-        const int take = min(rem, max(0, kCandNew - excl));
-        const int total = min(total_rem, kCandNew);
-        fence_proxy_async_smem();  // earlier generic-proxy accesses of the buffer precede the async writes
-        __syncwarp();
-        if (lane == 0) mbar_expect_tx(bar, uint32_t(total) * 16u);
-        __syncwarp();
-        if (take > 0) bulk_g2s(cand_s + uint32_t(carry + excl) * 16u, pts + j_lo, uint32_t(take) * 16u, bar);
-        j_lo += take;
-        rem -= take;
-        mbar_wait(bar, parity);
-        parity ^= 1u;
-        // membership test + in-place compaction, 64 candidates per step (two independent chains)
-        const int end = carry + total;
-        int w = carry;
-        for (int base = carry; base < end; base += 64) {
-          const int i0 = base + lane, i1 = i0 + 32;
-          GPoint p0 = far_pt, p1 = far_pt;
-          if (i0 < end) p0 = lds_point(lane_s + uint32_t(base) * 16u);
-          if (i1 < end) p1 = lds_point(lane_s + uint32_t(base) * 16u + 512u);
-          const bool ok0 = dist2_flann(q.x, q.y, q.z, p0.x, p0.y, p0.z) < r2;
-          const bool ok1 = dist2_flann(q.x, q.y, q.z, p1.x, p1.y, p1.z) < r2;
-          const unsigned m0 = __ballot_sync(0xffffffffu, ok0), m1 = __ballot_sync(0xffffffffu, ok1);
-          const int w1 = w + __popc(m0);
-          if (ok0) sts_point(cand_s + uint32_t(w + __popc(m0 & lt)) * 16u, p0);
-          if (ok1) sts_point(cand_s + uint32_t(w1 + __popc(m1 & lt)) * 16u, p1);
-          w = w1 + __popc(m1);
-        }
-        __syncwarp();
-        n_acc += w - carry;
-        const int nfull = w & ~31;
-        for (int b = 0; b < nfull; b += 32) process(lds_point(lane_s + uint32_t(b) * 16u));
-        carry = w - nfull;
-        if (nfull > 0 && carry > 0) {  // move the remainder to the front
-          GPoint v = far_pt;
-          if (lane < carry) v = lds_point(lane_s + uint32_t(nfull) * 16u);
-          __syncwarp();
-          if (lane < carry) sts_point(lane_s, v);
-        }
-        __syncwarp();
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
       }
+      const int total_rem = __shfl_sync(0xffffffffu, incl, 31);
+      if (total_rem == 0) break;
+      const int excl = incl - rem;
+      const int take = min(rem, max(0, kStageCap - excl));
+      const int total = min(total_rem, kStageCap);
+      fence_proxy_async_smem();  // earlier generic-proxy reads of the buffer precede the async writes
+      __syncwarp();
+      if (lane == 0) mbar_expect_tx(bar, uint32_t(total) * 16u);
+      __syncwarp();
+      if (take > 0) bulk_g2s(cand_s + uint32_t(excl) * 16u, pts + j_lo, uint32_t(take) * 16u, bar);
+      j_lo += take;
+      rem -= take;
+      mbar_wait(bar, parity);
+      parity ^= 1u;
+      // membership test, 64 candidates per step (two independent chains), compacted store to the pool
+      for (int base = 0; base < total; base += 64) {
+        GPoint p0 = far_pt, p1 = far_pt;
+        if (base + lane < total) p0 = lds_point(lane_s + uint32_t(base) * 16u);
+        if (base + lane + 32 < total) p1 = lds_point(lane_s + uint32_t(base) * 16u + 512u);
+        const bool ok0 = dist2_flann(q.x, q.y, q.z, p0.x, p0.y, p0.z) < r2;
+        const bool ok1 = dist2_flann(q.x, q.y, q.z, p1.x, p1.y, p1.z) < r2;
+        const unsigned m0 = __ballot_sync(0xffffffffu, ok0), m1 = __ballot_sync(0xffffffffu, ok1);
+        const int w0 = n_out + __popc(m0 & lt), w1 = n_out + __popc(m0) + __popc(m1 & lt);
+        if (ok0 && w0 < stride) out[w0] = p0;
+        if (ok1 && w1 < stride) out[w1] = p1;
+        n_out += __popc(m0) + __popc(m1);
+      }
+      __syncwarp();
     }
   }
-  if (carry > 0) {  // inactive lanes process the sample itself: every term is exactly zero
-    GPoint v = q;
-    v.tag = 0;
-    if (lane < carry) v = lds_point(lane_s);
-    process(v);
-  }
-  // warp reduction: moments 1..32 transposed through shared memory with a 33-double row pitch (lane i
-  // sums moment i + 1 with immediate offsets, bank-conflict free), 33..34 by butterflies
-  __syncwarp();
-#pragma unroll
-  for (int m = 0; m < 32; m++) sts_f64(cand_s + uint32_t(m * 33 + 0) * 8u + uint32_t(lane) * 8u, acc[m + 1]);
-  const double m33 = warp_sum(acc[33]), m34 = warp_sum(acc[34]);
-  cam1 = __reduce_add_sync(0xffffffffu, cam1);
   n_cand = __reduce_add_sync(0xffffffffu, n_cand);
-  __syncwarp();
-  double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
-  const uint32_t row_s = cand_s + uint32_t(lane) * (33u * 8u);
-#pragma unroll
-  for (int k = 0; k < 32; k += 4) {
-    t0 += lds_f64(row_s + uint32_t(k) * 8u);
-    t1 += lds_f64(row_s + uint32_t(k + 1) * 8u);
-    t2 += lds_f64(row_s + uint32_t(k + 2) * 8u);
-    t3 += lds_f64(row_s + uint32_t(k + 3) * 8u);
-  }
-  const double rsum = (t0 + t1) + (t2 + t3);                       // moment lane + 1
-  double r32 = __shfl_up_sync(0xffffffffu, rsum, 1);               // lane i (i >= 1): moment i
-  const double m32 = __shfl_sync(0xffffffffu, rsum, 31);           // moment 32
-  if (lane == 0) r32 = double(n_acc);                              // moment 0: the neighbour count
-  // coordinate scale (a power of two, so this equals accumulating scaled coordinates bit for bit)
-  const double s2 = scale * scale, s4 = s2 * s2;
-  const double scl = lane == 0 ? 1.0 : lane <= 3 ? scale : lane <= 9 ? s2 : lane <= 19 ? s2 * scale : s4;
-  double* out = moments + size_t(s) * kMomentStride;
-  out[lane] = r32 * scl;
   if (lane == 0) {
-    out[32] = m32 * s4;
-    out[33] = m33 * s4;
-    out[34] = m34 * s4;
-    out[35] = double(cam1);
-    nn_counts[s] = make_int2(int(r32), n_cand);
+    nn_counts[s] = make_int2(min(n_out, stride), n_cand);
+    heads[sl] = make_float4(q.x, q.y, q.z, __int_as_float(min(n_out, stride)));  // what the moments kernel needs
+    if (n_out > stride) atomicOr(&rip->error, kErrBallOverflow);
+  }
+}
+
+// ---- kernel 1: moments ------------------------------------------------------------------------
+// Roofline-graded kernel: streams each sample's neighbour list (16 B per neighbour, contiguous) and
+// accumulates the 34 monomial moments of degree 1..4 in binary64.  Persistent warps (one CTA slot per SM
+// and register budget), each walking samples gw, gw + G, ...; the stream is cut into segments of kSeg
+// records that ping-pong between two shared buffers per warp:
+//   1. one elected lane issues the bulk async copy (TMA) of the NEXT segment — the rest of this list or,
+//      speculatively at full size, the head of the next sample's list — before the warp touches the
+//      current one, so a copy is always in flight behind the arithmetic and no registers are held for it;
+//   2. 32 points per step: coordinates centred on the sample (exact: differences of binary32 values),
+//      6 products, 34 fused multiply-adds per lane;
+//   3. the 32 x 34 partial sums are transposed through the just-consumed buffer in two rounds of 16
+//      moments (both half-warps sum half a row each, immediate offsets, conflict free), the power-of-two
+//      coordinate scale is applied exactly (moment of degree d times scale^d), 36 doubles out.
+constexpr int kSeg = 272;  // records per segment (4352 B >= the 16 x 33 doubles of a reduction round)
+static_assert(kSeg * sizeof(GPoint) >= 16 * 33 * sizeof(double), "the reduction reuses a segment buffer");
+
+__global__ void __launch_bounds__(kWarps * 32, 4)
+k_taubin_moments(int s0, int m, const float4* __restrict__ heads, const GPoint* __restrict__ pool, int stride,
+                 double scale, double* __restrict__ moments) {
+  __shared__ __align__(16) GPoint s_seg[kWarps][2][kSeg];
+  __shared__ __align__(8) unsigned long long s_bar[kWarps][2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x * kWarps;
+  int sl = blockIdx.x * kWarps + warp;
+  if (sl >= m) return;
+  const uint32_t buf0 = pin_u32(smem_u32(s_seg[warp][0])), bar0 = pin_u32(smem_u32(&s_bar[warp][0]));
+  constexpr uint32_t kBufBytes = kSeg * sizeof(GPoint);
+  const uint32_t seg_bytes = uint32_t(min(kSeg, stride)) * 16u;  // speculative first segment of a list
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8u, 1);
+    fence_proxy_async_smem();
+    mbar_expect_tx(bar0, seg_bytes);
+    bulk_g2s(buf0, pool + size_t(sl) * size_t(stride), seg_bytes, bar0);
+  }
+  __syncwarp();
+  float4 head = heads[sl];
+  const double s2 = scale * scale, s4 = s2 * s2;
+  const int mj = lane + 1;  // the moment this lane writes
+  const double scl = mj <= 3 ? scale : mj <= 9 ? s2 : mj <= 19 ? s2 * scale : s4;
+  int g = 0;  // segments consumed so far: buffer g & 1, barrier phase (g >> 1) & 1
+  while (sl < m) {
+    const int n = __float_as_int(head.w);
+    const int sl_next = sl + G;
+    float4 head_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sl_next < m) head_next = heads[sl_next];
+    const double qx = double(head.x), qy = double(head.y), qz = double(head.z);
+    GPoint self;  // padding of the last batch: every term of the sample itself is exactly zero
+    self.x = head.x;
+    self.y = head.y;
+    self.z = head.z;
+    self.tag = 0;
+    const GPoint* src = pool + size_t(sl) * size_t(stride);
+    double acc[kNumMoments];  // acc[0] is unused: the count is known
+#pragma unroll
+    for (int i = 0; i < kNumMoments; i++) acc[i] = 0.0;
+    int cam1 = 0;
+    const int nseg = max(1, (n + kSeg - 1) / kSeg);
+    for (int k = 0; k < nseg; k++, g++) {
+      const uint32_t cur = buf0 + uint32_t(g & 1) * kBufBytes, cur_bar = bar0 + uint32_t(g & 1) * 8u;
+      const uint32_t oth = buf0 + uint32_t((g + 1) & 1) * kBufBytes, oth_bar = bar0 + uint32_t((g + 1) & 1) * 8u;
+      __syncwarp();  // every lane is done with the other buffer (segment g - 1 or the reduction scratch)
+      if (lane == 0) {
+        fence_proxy_async_smem();
+        if (k + 1 < nseg) {
+          const uint32_t bytes = uint32_t(min(kSeg, n - (k + 1) * kSeg)) * 16u;
+          mbar_expect_tx(oth_bar, bytes);
+          bulk_g2s(oth, src + (k + 1) * kSeg, bytes, oth_bar);
+        } else if (sl_next < m) {
+          mbar_expect_tx(oth_bar, seg_bytes);
+          bulk_g2s(oth, pool + size_t(sl_next) * size_t(stride), seg_bytes, oth_bar);
+        }
+      }
+      mbar_wait(cur_bar, uint32_t(g >> 1) & 1u);
+      const int cnt = min(kSeg, n - k * kSeg);
+      const uint32_t lane_s = cur + uint32_t(lane) * 16u;
+      for (int b = 0; b < cnt; b += 32) {
+        GPoint p = self;
+        if (b + lane < cnt) p = lds_point(lane_s + uint32_t(b) * 16u);
+        const double x = double(p.x) - qx, y = double(p.y) - qy, z = double(p.z) - qz;
+        const double x2 = x * x, y2 = y * y, z2 = z * z, xy = x * y, yz = y * z, xz = x * z;
+        acc[1] += x; acc[2] += y; acc[3] += z;
+        acc[4] += x2; acc[5] += y2; acc[6] += z2; acc[7] += xy; acc[8] += yz; acc[9] += xz;
+        acc[10] += x2 * x; acc[11] += y2 * y; acc[12] += z2 * z; acc[13] += x2 * y; acc[14] += x2 * z;
+        acc[15] += x * y2; acc[16] += y2 * z; acc[17] += x * z2; acc[18] += y * z2; acc[19] += xy * z;
+        acc[20] += x2 * x2; acc[21] += y2 * y2; acc[22] += z2 * z2; acc[23] += x2 * xy; acc[24] += x2 * xz;
+        acc[25] += xy * y2; acc[26] += y2 * yz; acc[27] += xz * z2; acc[28] += yz * z2; acc[29] += x2 * y2;
+        acc[30] += y2 * z2; acc[31] += x2 * z2; acc[32] += x2 * yz; acc[33] += xy * yz; acc[34] += xz * yz;
+        cam1 += int(p.tag & kTagCamBit);
+      }
+    }
+    // warp reduction through the buffer consumed last: two rounds of 16 moments with a 33-double row
+    // pitch; lane i sums half (i >> 4) of row (i & 15), the halves meet by one exchange
+    const uint32_t scr = buf0 + uint32_t((g - 1) & 1) * kBufBytes;
+    const uint32_t row_s = scr + uint32_t(lane & 15) * (33u * 8u) + uint32_t(lane >> 4) * (16u * 8u);
+    double r01[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 16; j++) sts_f64(scr + uint32_t(j * 33) * 8u + uint32_t(lane) * 8u, acc[1 + 16 * r + j]);
+      __syncwarp();
+      double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 16; k += 2) {
+        t0 += lds_f64(row_s + uint32_t(k) * 8u);
+        t1 += lds_f64(row_s + uint32_t(k + 1) * 8u);
+      }
+      const double t = t0 + t1;
+      r01[r] = t + __shfl_xor_sync(0xffffffffu, t, 16);
+    }
+    const double m33 = warp_sum(acc[33]), m34 = warp_sum(acc[34]);
+    cam1 = __reduce_add_sync(0xffffffffu, cam1);
+    if (n > 0) {
+      double* out = moments + size_t(s0 + sl) * kMomentStride;
+      out[mj] = (lane < 16 ? r01[0] : r01[1]) * scl;  // moments 1..32
+      if (lane == 0) {
+        out[0] = double(n);
+        out[33] = m33 * s4;
+        out[34] = m34 * s4;
+        out[35] = double(cam1);
+      }
+    }
+    sl = sl_next;
+    head = head_next;
   }
 }
 
@@ -346,9 +350,23 @@ struct AxesSmem {
   double m[10];   // last column of M (9 entries) and n
   double par[10]; // quadric parameters in centred/scaled coordinates
   double T[28];   // weighted order-6 normal tensor
-  GPoint ring[64];
-  RunList runs;
 };
+
+// streams a sample's neighbour list (written by k_ball_search) 32 records per step, the next step's load
+// already in flight; f(point, active)
+template <typename F>
+__device__ __forceinline__ void walk_list(const GPoint* __restrict__ list, int n, F&& f) {
+  const int lane = threadIdx.x & 31;
+  GPoint nxt;
+  nxt.x = nxt.y = nxt.z = 0.f;
+  nxt.tag = 0;
+  if (lane < n) nxt = list[lane];
+  for (int b = 0; b < n; b += 32) {
+    const GPoint p = nxt;
+    if (b + 32 + lane < n) nxt = list[b + 32 + lane];
+    f(p, b + lane < n);
+  }
+}
 
 // Jacobi rotation (c, s) annihilating a_pq, the small-angle root (|angle| <= pi/4), computed without
 // divisions: with h = (a_qq - a_pp)/2, b = a_pq, r = hypot(h, b):  cos 2phi = |h|/r, sin 2phi = b/r,
@@ -528,21 +546,23 @@ __constant__ double c_multinomial6[28] = {
 
 // ---- kernel 2: eigen-solve + local axes -------------------------------------------------------
 __global__ void __launch_bounds__(kWarps * 32, 4)
-k_taubin_axes(const GPoint* __restrict__ pts_c, const int* __restrict__ row_ptr, const int* __restrict__ col_ptr,
-              const RowIndex* __restrict__ rip,
-              const int* __restrict__ indices, int n_samples_max, const int* __restrict__ d_count,
-              float r2, double rpad, double inv_r, const double* __restrict__ moments,
+k_taubin_axes(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip,
+              const int* __restrict__ indices, int s0, int n_samples_max, const int* __restrict__ d_count,
+              const GPoint* __restrict__ pool, int stride, const int2* __restrict__ nn_counts, double inv_r,
+              const double* __restrict__ moments,
               double cam0x, double cam0y, double cam0z, double cam1x, double cam1y, double cam1z,
               ag_frame* __restrict__ frames, double* normals_out /* may be null */) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   AxesSmem* sm_all = reinterpret_cast<AxesSmem*>(s_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int s = blockIdx.x * kWarps + warp;
-  const RowIndex ri = *rip;
+  const int sl = blockIdx.x * kWarps + warp;
+  const int s = s0 + sl;
   if (s >= n_samples_max || s >= *d_count) return;
   AxesSmem& sm = sm_all[warp];
   const int idx = indices[s];
-  if (idx < 0 || idx >= ri.n_points) return;
+  if (idx < 0 || idx >= rip->n_points) return;
+  const GPoint* list = pool + size_t(sl) * size_t(stride);
+  const int n_list = nn_counts[s].x;
   const GPoint q = pts_c[idx];
   const double qx = double(q.x), qy = double(q.y), qz = double(q.z);
   const double* mom = moments + size_t(s) * kMomentStride;
@@ -736,26 +756,17 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const int* __restrict__ row_ptr,
   double acc[34];
 #pragma unroll
   for (int i = 0; i < 34; i++) acc[i] = 0.0;
-  // the run list of this ball is built once and reused by both walks (queries touching more than
-  // kRunCap rows are walked in batches)
-  int nr = 0, row_off = 0;
-  bool more = true;
-  while (more) {
-    nr = build_runs_warp(ri, row_ptr, col_ptr, pts_c, q.x, q.y, rpad, sm.runs.rs, sm.runs.pre, kRunCap, row_off, more);
-    row_off += nr;
-    walk_runs(pts_c, sm.runs, nr, q.x, q.y, q.z, r2, sm.ring, [&](const GPoint& p, bool active) {
-      if (!active) return;
-      const double x = (double(p.x) - qx) * inv_r, y = (double(p.y) - qy) * inv_r, z = (double(p.z) - qz) * inv_r;
-      double gn[3], m6[28];
-      quad_normal(par, x, y, z, gn);
-      acc[0] += gn[0] * gn[0]; acc[1] += gn[1] * gn[1]; acc[2] += gn[2] * gn[2];
-      acc[3] += gn[0] * gn[1]; acc[4] += gn[1] * gn[2]; acc[5] += gn[0] * gn[2];
-      monomials6(gn, m6);
+  walk_list(list, n_list, [&](const GPoint& p, bool active) {
+    if (!active) return;
+    const double x = (double(p.x) - qx) * inv_r, y = (double(p.y) - qy) * inv_r, z = (double(p.z) - qz) * inv_r;
+    double gn[3], m6[28];
+    quad_normal(par, x, y, z, gn);
+    acc[0] += gn[0] * gn[0]; acc[1] += gn[1] * gn[1]; acc[2] += gn[2] * gn[2];
+    acc[3] += gn[0] * gn[1]; acc[4] += gn[1] * gn[2]; acc[5] += gn[0] * gn[2];
+    monomials6(gn, m6);
 #pragma unroll
-      for (int t = 0; t < 28; t++) acc[6 + t] += m6[t];
-    });
-  }
-  const bool single_batch = row_off == nr;  // the common case: the list in shared memory is complete
+    for (int t = 0; t < 28; t++) acc[6 + t] += m6[t];
+  });
   // warp reduction by recursive halving: lane i holds sum i (i < 32); sums 32, 33 by butterflies
   {
     const double r32 = warp_reduce_transpose32(acc);
@@ -776,48 +787,52 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const int* __restrict__ row_ptr,
   double ax[3] = {V3[0][m3], V3[1][m3], V3[2][m3]};
   __syncwarp();
 
-  // --- walk 3: j* = argmax_j sum_i (g_i.g_j)^6 = argmax_j <T, g_j^(x6)>, first max in (dist, index) order
+  // --- walk 3: j* = argmax_j sum_i (g_i.g_j)^6 = argmax_j <T, g_j^(x6)>, first max in the reference's
+  // (distance, index) order; index order == (camera, x, y, z) order of the voxel list
   double bestS = -1.0;
   float bestD = 3.0e38f;
-  unsigned bestI = 0xFFFFFFFFu;
+  GPoint bestP;
+  bestP.x = bestP.y = bestP.z = 3.0e38f;
+  bestP.tag = 1u;
   double bestG[3] = {0, 0, 0};
-  row_off = 0;
-  more = true;
-  while (more) {
-    if (single_batch) more = false;
-    else {
-      nr = build_runs_warp(ri, row_ptr, col_ptr, pts_c, q.x, q.y, rpad, sm.runs.rs, sm.runs.pre, kRunCap, row_off, more);
-      row_off += nr;
-    }
-    walk_runs(pts_c, sm.runs, nr, q.x, q.y, q.z, r2, sm.ring, [&](const GPoint& p, bool active) {
-      if (!active) return;
-      const double x = (double(p.x) - qx) * inv_r, y = (double(p.y) - qy) * inv_r, z = (double(p.z) - qz) * inv_r;
-      double gn[3], m6[28];
-      quad_normal(par, x, y, z, gn);
-      monomials6(gn, m6);
-      double S = 0.0;
+  auto before = [](const GPoint& a, const GPoint& b) {  // a precedes b in the voxel list
+    const unsigned ca = a.tag & kTagCamBit, cb = b.tag & kTagCamBit;
+    if (ca != cb) return ca < cb;
+    if (a.x != b.x) return a.x < b.x;
+    if (a.y != b.y) return a.y < b.y;
+    return a.z < b.z;
+  };
+  walk_list(list, n_list, [&](const GPoint& p, bool active) {
+    if (!active) return;
+    const double x = (double(p.x) - qx) * inv_r, y = (double(p.y) - qy) * inv_r, z = (double(p.z) - qz) * inv_r;
+    double gn[3], m6[28];
+    quad_normal(par, x, y, z, gn);
+    monomials6(gn, m6);
+    double S = 0.0;
 #pragma unroll
-      for (int t = 0; t < 28; t++) S += sm.T[t] * m6[t];
-      const float d = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
-      const unsigned id = p.tag >> 2;
-      const bool better = S > bestS || (S == bestS && (d < bestD || (d == bestD && id < bestI)));
-      if (better) {
-        bestS = S; bestD = d; bestI = id;
-        bestG[0] = gn[0]; bestG[1] = gn[1]; bestG[2] = gn[2];
-      }
-    });
-  }
+    for (int t = 0; t < 28; t++) S += sm.T[t] * m6[t];
+    const float d = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
+    const bool better = S > bestS || (S == bestS && (d < bestD || (d == bestD && before(p, bestP))));
+    if (better) {
+      bestS = S; bestD = d; bestP = p;
+      bestG[0] = gn[0]; bestG[1] = gn[1]; bestG[2] = gn[2];
+    }
+  });
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const double oS = __shfl_xor_sync(0xffffffffu, bestS, o);
     const float oD = __shfl_xor_sync(0xffffffffu, bestD, o);
-    const unsigned oI = __shfl_xor_sync(0xffffffffu, bestI, o);
+    GPoint oP;
+    oP.x = __shfl_xor_sync(0xffffffffu, bestP.x, o);
+    oP.y = __shfl_xor_sync(0xffffffffu, bestP.y, o);
+    oP.z = __shfl_xor_sync(0xffffffffu, bestP.z, o);
+    oP.tag = __shfl_xor_sync(0xffffffffu, bestP.tag, o);
     const double g0 = __shfl_xor_sync(0xffffffffu, bestG[0], o);
     const double g1 = __shfl_xor_sync(0xffffffffu, bestG[1], o);
     const double g2 = __shfl_xor_sync(0xffffffffu, bestG[2], o);
-    const bool better = oS > bestS || (oS == bestS && (oD < bestD || (oD == bestD && oI < bestI)));
+    const bool better = oS > bestS || (oS == bestS && (oD < bestD || (oD == bestD && before(oP, bestP))));
     if (better) {
-      bestS = oS; bestD = oD; bestI = oI;
+      bestS = oS; bestD = oD; bestP = oP;
       bestG[0] = g0; bestG[1] = g1; bestG[2] = g2;
     }
   }
@@ -893,42 +908,67 @@ __global__ void k_quadric_finish(GPoint* pts, const RowIndex* __restrict__ rip, 
 
 }  // namespace
 
+// neighbour-pool records per sample for a radius: the lattice-ball bound, capped at four times what a
+// surface sampled by the voxel lattice puts into the ball (a ball holding more sets kErrBallOverflow)
+static int ball_stride(double radius, double voxel, bool two_cams) {
+  const double cells = radius / (voxel > 0 ? voxel : 0.003);
+  const double ball = 4.18879 * (cells + 0.87) * (cells + 0.87) * (cells + 0.87) + 32.0;
+  const double surf = std::max(288.0, 1024.0 * (cells / 10.0) * (cells / 10.0));
+  const double v = std::min(ball, surf) * (two_cams ? 2.0 : 1.0);
+  return int((std::min(v, 1.0e6) + 31.0) / 32.0) * 32;
+}
+
 int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count, double radius, ag_frame* d_frames,
                         bool write_normals) {
   if (n <= 0) return AG_OK;
+  const int stride = ball_stride(radius, c->params.voxel_size, c->two_cams);
+  // samples are processed in chunks whose neighbour pool stays below kPoolBytes (one chunk for every
+  // BASELINE config; only all-points passes over multi-million-point inputs take more)
+  constexpr size_t kPoolBytes = size_t(4) << 30;
+  const int chunk = int(std::min<size_t>(size_t(n), std::max<size_t>(kWarps, kPoolBytes / (size_t(stride) * sizeof(GPoint)))));
   if (c->moments.reserve(size_t(n) * kMomentStride * sizeof(double)) || c->nn_counts.reserve(size_t(n) * 8) ||
-      c->counters.reserve(64))
+      c->counters.reserve(64) || c->nbr_pool.reserve(size_t(chunk) * size_t(stride) * sizeof(GPoint)) ||
+      c->nbr_heads.reserve(size_t(chunk) * sizeof(float4)))
     return AG_ERR_CUDA;
   const float r2 = float(radius * radius);  // PCL hands radius*radius to FLANN as float
   const double rpad = sqrt(double(r2)) * (1.0 + 1e-5) + 1e-7;
   // coordinates are centred on the sample and scaled by the power of two nearest to 1/r (the fit is
   // invariant under translation and uniform scale; a power of two makes the scaling exact)
   const double inv_r = ldexp(1.0, int(lrint(log2(1.0 / radius))));
-  const int blocks = (n + kWarps - 1) / kWarps;
   unsigned long long* ctr = c->counters.as<unsigned long long>();
-  const RowIndex* ri = c->row_index.as<RowIndex>();
-  cudaEventRecord(c->ev_k[0], c->stream);
-  k_taubin_moments<<<blocks, kWarps * 32, 0, c->stream>>>(c->vox.as<GPoint>(), c->row_ptr.as<int>(),
-                                                          c->col_ptr.as<int>(), ri, d_indices, n, d_count, r2, rpad,
-                                                          inv_r, c->moments.as<double>(), c->nn_counts.as<int2>());
-  cudaEventRecord(c->ev_k[1], c->stream);
+  RowIndex* ri = c->row_index.as<RowIndex>();
   const size_t smem = sizeof(AxesSmem) * kWarps;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_taubin_axes, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     cudaFuncSetAttribute(k_taubin_axes, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    cudaFuncSetAttribute(k_ball_search, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     attr_set = true;
   }
   const HandConst& h = c->hand;
-  k_taubin_axes<<<blocks, kWarps * 32, smem, c->stream>>>(
-      c->vox.as<GPoint>(), c->row_ptr.as<int>(), c->col_ptr.as<int>(), ri, d_indices, n, d_count, r2, rpad, inv_r,
-      c->moments.as<double>(),
-      h.cam[0][0], h.cam[0][1], h.cam[0][2], h.cam[1][0], h.cam[1][1], h.cam[1][2], d_frames,
-      write_normals ? c->normals.as<double>() : nullptr);
-  cudaEventRecord(c->ev_k[2], c->stream);
-  c->launches += 3;
+  for (int s0 = 0; s0 < n; s0 += chunk) {
+    const int m = std::min(chunk, n - s0);
+    const int blocks = (m + kWarps - 1) / kWarps;
+    const bool timed = s0 == 0;  // ag_timings reports the kernels of the first chunk
+    if (timed) cudaEventRecord(c->ev_k[0], c->stream);
+    k_ball_search<<<blocks, kWarps * 32, 0, c->stream>>>(c->vox.as<GPoint>(), c->row_ptr.as<int>(),
+                                                         c->col_ptr.as<int>(), ri, d_indices, s0, s0 + m, d_count, r2,
+                                                         rpad, c->nbr_pool.as<GPoint>(), stride,
+                                                         c->nn_counts.as<int2>(), c->nbr_heads.as<float4>());
+    if (timed) cudaEventRecord(c->ev_k[1], c->stream);
+    k_taubin_moments<<<std::min(blocks, kNumSMs * 4), kWarps * 32, 0, c->stream>>>(
+        s0, m, c->nbr_heads.as<float4>(), c->nbr_pool.as<GPoint>(), stride, inv_r, c->moments.as<double>());
+    if (timed) cudaEventRecord(c->ev_k[2], c->stream);
+    k_taubin_axes<<<blocks, kWarps * 32, smem, c->stream>>>(
+        c->vox.as<GPoint>(), ri, d_indices, s0, s0 + m, d_count, c->nbr_pool.as<GPoint>(), stride,
+        c->nn_counts.as<int2>(), inv_r, c->moments.as<double>(), h.cam[0][0], h.cam[0][1], h.cam[0][2], h.cam[1][0],
+        h.cam[1][1], h.cam[1][2], d_frames, write_normals ? c->normals.as<double>() : nullptr);
+    if (timed) cudaEventRecord(c->ev_k[3], c->stream);
+    c->launches += 3;
+  }
   k_quadric_finish<<<(n + 255) / 256, 256, 0, c->stream>>>(c->vox.as<GPoint>(), ri, d_indices, n, d_count,
                                                           c->nn_counts.as<int2>(), ctr, write_normals ? 1 : 0);
+  c->launches += 1;
   AG_CUDA_CHECK(cudaGetLastError());
   return AG_OK;
 }

@@ -73,7 +73,7 @@ class AgTimings(C.Structure):
         "d2h_ms", "total_ms")] + [(n, C.c_int32) for n in ("n_in", "n_voxels", "n_samples", "n_hyp")] + [
         (n, C.c_int64) for n in ("taubin_neighbor_points", "hand_neighbor_points", "taubin_candidates",
                                  "hand_candidates")] + [("moments_ms", C.c_float), ("axes_ms", C.c_float),
-                                                        ("kernel_launches", C.c_int32), ("reserved", C.c_int32)]
+                                                        ("kernel_launches", C.c_int32), ("search_ms", C.c_float)]
 
 
 GRASP_DTYPE = np.dtype([

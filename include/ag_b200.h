@@ -120,7 +120,7 @@ typedef struct ag_timings {
   float moments_ms;                 /* k_taubin_moments alone (the roofline-graded kernel), last call */
   float axes_ms;                    /* k_taubin_axes alone */
   int32_t kernel_launches;          /* launches of this library's own kernels in the last localize(+classify) */
-  int32_t reserved;
+  float search_ms;                  /* k_ball_search alone (radius search -> neighbour lists of the Taubin fit) */
 } ag_timings;
 
 typedef struct ag_ctx ag_ctx;

@@ -13,4 +13,4 @@ for mode in ("samples", "all"):
         ctx.fit_quadrics(idx, 0.03); t = ctx.timings()
         if best is None or t["moments_ms"] < best["moments_ms"]: best = t
     b = 16 * best["taubin_neighbor_points"] + 292 * len(idx)
-    print("WPS", os.environ.get("AG_MOM_WPS"), mode, "moments_ms", round(best["moments_ms"], 4), "GB/s", round(b / best["moments_ms"] / 1e6, 1), "axes_ms", round(best["axes_ms"], 4))
+    print(mode, "search_ms", round(best["search_ms"], 4), "moments_ms", round(best["moments_ms"], 4), "moments GB/s", round(b / best["moments_ms"] / 1e6, 1), "search+moments GB/s", round(b / (best["moments_ms"] + best["search_ms"]) / 1e6, 1), "axes_ms", round(best["axes_ms"], 4))
