@@ -88,7 +88,7 @@ struct Ctx {
   bool two_cams = false;  // the last cloud had points of both cameras (sizes the neighbour pool)
   int n_samples = 0;
   // sweep outputs
-  DevBuf grasps_raw, valid, images_raw, hyp_slots, grasps, counters, scores, descriptors, sweep_dbg, overflow;
+  DevBuf grasps_raw, valid, images_raw, hyp_slots, grasps, counters, scores, descriptors, kvals, sweep_dbg, overflow;
   int n_hyp = 0;
   bool images_valid = false;
   unsigned sweep_flags = 0;          // arguments of the last hand_sweep_enqueue (for the overflow re-run)

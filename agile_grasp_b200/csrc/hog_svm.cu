@@ -323,6 +323,7 @@ k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slo
     }
     return __fmul_rn(a, b);
   };
+  if (svm.sv_total == 0) continue;  // descriptors only: the batched kernels below score them (CTA uniform)
   if (svm.sv_total == 1) {
     double acc = 0.0;
     for (int k4 = tid; k4 < AG_HOG_DIM / 4; k4 += kThreads) acc += group_term(svm.sv, k4);
@@ -364,6 +365,118 @@ k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slo
   }  // hypothesis loop
 }
 
+// ---- batched scoring for models with many support vectors (POLY: 588 / 1190 x 3528) -------------------
+// CvSVM::predict evaluates, per hypothesis, sv_total dot products of length 3528.  Batched over the H
+// hypotheses of a cloud that is a [H x 3528] . [3528 x sv_total] product; it is NOT routed to tensor cores:
+// OpenCV's calc_non_rbf_base rounds every product to binary32, sums groups of four in binary32 and
+// accumulates the groups in binary64, and the scores must match that bit for bit.  So this is a classic
+// shared-memory tiled SIMT kernel in which every thread keeps the reference's order for its 4 x 4 outputs:
+// 32 hypotheses x 64 support vectors per CTA (128 threads), K tiles of 24 (3528 = 147 x 24) double-buffered with
+// cp.async, row pitch 28 floats so the 16-byte reads of a quarter warp hit distinct banks.  The support
+// vector matrix is read H/64 times instead of H times.
+constexpr int GM = 32, GN = 64, GK = 24, GP = 28, kGemmThreads = 128;
+static_assert(AG_HOG_DIM % GK == 0, "K tiles must divide the descriptor length");
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, bool valid) {
+  const uint32_t d = uint32_t(__cvta_generic_to_shared(dst_smem));
+  const int sz = valid ? 16 : 0;  // 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+
+__device__ __forceinline__ float svm_kernel_value(double acc, int kernel, double gamma, double coef0, int degree) {
+  if (kernel == 0) return float(acc * 1.0 + 0.0);
+  float kv = float(acc * gamma + coef0);
+  float b = kv, a = 1.f;  // cv::pow with an integer exponent: repeated binary32 multiplication
+  int p = degree;
+  while (p > 1) {
+    if (p & 1) a = __fmul_rn(a, b);
+    b = __fmul_rn(b, b);
+    p >>= 1;
+  }
+  return __fmul_rn(a, b);
+}
+
+__global__ void __launch_bounds__(kGemmThreads)
+k_svm_gemm(const float* __restrict__ desc, const float* __restrict__ sv, int n_bound, const int* __restrict__ n_dev,
+           int nsv, int kernel, double gamma, double coef0, int degree, float* __restrict__ kvals) {
+  __shared__ __align__(16) float sA[2][GM][GP];
+  __shared__ __align__(16) float sB[2][GN][GP];
+  const int n = n_dev ? min(*n_dev, n_bound) : n_bound;
+  const int h0 = blockIdx.x * GM, k0 = blockIdx.y * GN;
+  if (h0 >= n) return;
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  auto load_tiles = [&](int kt, int st) {
+    for (int e = t; e < (GM + GN) * (GK / 4); e += kGemmThreads) {
+      const bool isB = e >= GM * (GK / 4);
+      const int f = isB ? e - GM * (GK / 4) : e;
+      const int r = f / (GK / 4), c4 = f % (GK / 4);
+      const int row = (isB ? k0 : h0) + r;
+      const bool valid = row < (isB ? nsv : n);
+      const float* src = (isB ? sv : desc) + size_t(valid ? row : 0) * AG_HOG_DIM + kt * GK + c4 * 4;
+      cp_async16(isB ? &sB[st][r][c4 * 4] : &sA[st][r][c4 * 4], src, valid);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+  load_tiles(0, 0);
+  constexpr int NT = AG_HOG_DIM / GK;
+  for (int kt = 0; kt < NT; kt++) {
+    const int st = kt & 1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // tile kt has landed; every thread is done with tile kt - 1
+    if (kt + 1 < NT) load_tiles(kt + 1, st ^ 1);
+#pragma unroll
+    for (int g = 0; g < GK / 4; g++) {
+      float4 a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const float4*>(&sA[st][ty * 4 + i][g * 4]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) b[j] = *reinterpret_cast<const float4*>(&sB[st][tx + 16 * j][g * 4]);
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          float p = __fmul_rn(b[j].x, a[i].x);
+          p = __fadd_rn(p, __fmul_rn(b[j].y, a[i].y));
+          p = __fadd_rn(p, __fmul_rn(b[j].z, a[i].z));
+          p = __fadd_rn(p, __fmul_rn(b[j].w, a[i].w));
+          acc[i][j] += double(p);
+        }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int h = h0 + ty * 4 + i;
+    if (h >= n) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int k = k0 + tx + 16 * j;
+      if (k < nsv) kvals[size_t(h) * nsv + k] = svm_kernel_value(acc[i][j], kernel, gamma, coef0, degree);
+    }
+  }
+}
+
+// decision value per hypothesis, in CvSVM::predict's order: sum = -rho; sum += alpha_k * K[index_k], k ascending
+__global__ void k_svm_decide(const float* __restrict__ kvals, int n_bound, const int* __restrict__ n_dev, SvmDev svm,
+                             float* __restrict__ scores, ag_grasp* __restrict__ grasps_out) {
+  const int n = n_dev ? min(*n_dev, n_bound) : n_bound;
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n) return;
+  const float* K = kvals + size_t(h) * svm.sv_total;
+  double sum = -svm.rho;
+  for (int k = 0; k < svm.sv_count; k++) sum += svm.alpha[k] * double(K[svm.index[k]]);
+  const float sc = float(sum);
+  scores[h] = sc;
+  if (grasps_out) {
+    grasps_out[h].score = sc;
+    grasps_out[h].label = sc > 0.f ? 0 : 1;  // CvSVM::predict: label +1 <=> sum <= 0
+  }
+}
+
 bool g_tables_ready[64] = {false};
 
 }  // namespace
@@ -393,10 +506,6 @@ int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d
     set_error("SVM var_count != 3528");
     return AG_ERR_INVALID;
   }
-  if (svm->sv_total > 1280) {
-    set_error("SVM has more than 1280 support vectors");
-    return AG_ERR_CAPACITY;
-  }
   if (!g_tables_ready[c->device & 63]) {
     HogTables T;
     std::memset(&T, 0, sizeof(T));
@@ -417,10 +526,28 @@ int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d
   sd.gamma = svm->gamma;
   sd.coef0 = svm->coef0;
   sd.rho = svm->rho;
-  c->launches += 1;
   const int grid = n_dev ? std::min(n, kNumSMs * 6) : n;  // device-side count: persistent CTAs
-  k_hog_svm<<<grid, kThreads, 0, c->stream>>>(d_images, d_image_slots, n, n_dev, sd, d_descriptors, d_scores,
-                                               d_grasps_out);
+  if (svm->sv_total > 1) {
+    // many support vectors: descriptors -> [H x 3528] . [3528 x sv_total] tiled product -> decision values
+    float* desc = d_descriptors;
+    if (!desc) {
+      if (c->descriptors.reserve(size_t(n) * AG_HOG_DIM * sizeof(float))) return AG_ERR_CUDA;
+      desc = c->descriptors.as<float>();
+    }
+    if (c->kvals.reserve(size_t(n) * svm->sv_total * sizeof(float))) return AG_ERR_CUDA;
+    SvmDev none = sd;
+    none.sv_total = 0;
+    k_hog_svm<<<grid, kThreads, 0, c->stream>>>(d_images, d_image_slots, n, n_dev, none, desc, d_scores, nullptr);
+    const dim3 gg((n + GM - 1) / GM, (svm->sv_total + GN - 1) / GN);
+    k_svm_gemm<<<gg, kGemmThreads, 0, c->stream>>>(desc, svm->d_sv, n, n_dev, svm->sv_total, svm->kernel, svm->gamma,
+                                                  svm->coef0, svm->degree, c->kvals.as<float>());
+    k_svm_decide<<<(n + 127) / 128, 128, 0, c->stream>>>(c->kvals.as<float>(), n, n_dev, sd, d_scores, d_grasps_out);
+    c->launches += 3;
+  } else {
+    k_hog_svm<<<grid, kThreads, 0, c->stream>>>(d_images, d_image_slots, n, n_dev, sd, d_descriptors, d_scores,
+                                                 d_grasps_out);
+    c->launches += 1;
+  }
   AG_CUDA_CHECK(cudaGetLastError());
   return AG_OK;
 }

@@ -261,6 +261,27 @@ def test_poly_svm_scores(ctx, oracle, tmp_path):
         assert abs(scores[t] - ref) <= 1e-5 * max(1.0, abs(ref))  # tolerance: 1e-5 relative (north_star)
 
 
+def test_poly_svm_batched_bit_exact(ctx, oracle, tmp_path):
+    """The batched [H x 3528].[3528 x nSV] path (models with many support vectors, learning.cpp:225 with the
+    launch-file POLY models) keeps calc_non_rbf_base's rounding order: decision values equal the oracle's
+    bit for bit; H and nSV deliberately not multiples of the 64 x 64 tile."""
+    from test_oracle_hog_svm import write_opencv_svm
+    rng = np.random.default_rng(11)
+    nsv, H = 131, 70
+    sv = (rng.random((nsv, 3528)) * (rng.random((nsv, 3528)) < 0.2)).astype(np.float32)
+    path = tmp_path / "poly131"
+    write_opencv_svm(path, sv, rng.normal(size=nsv), rho=0.31, kernel="POLY", degree=2, gamma=1.0, coef0=0.0)
+    svm, osvm = api.Svm(path), oracle.Svm(path)
+    imgs = np.zeros((H, 80, 100), np.uint8)
+    for t in range(H):
+        imgs[t][rng.random((80, 100)) < 0.05 + 0.3 * rng.random()] = 255
+    scores, desc = ctx.hog_svm(svm, api.pack_images(imgs), want_descriptors=True)
+    ref = np.array([osvm.decision(desc[t]) for t in range(H)], np.float32)
+    assert (_u32(scores) == _u32(ref)).all()
+    scores2, _ = ctx.hog_svm(svm, api.pack_images(imgs))  # internal descriptor buffer
+    assert (_u32(scores2) == _u32(ref)).all()
+
+
 def test_golden_pipeline_without_oracle(ctx, linear_svm_path):
     """CUDA path against the committed fixture (frames supplied -> everything bit exact)."""
     z = np.load(os.path.join(GOLD, "pipeline_small.npz"), allow_pickle=True)
