@@ -21,6 +21,7 @@ EXPORTS = [
     "ag_get_timings", "ag_free", "ag_svm_load", "ag_svm_free", "ag_svm_info", "ag_localize", "ag_localize_device",
     "ag_classify", "ag_set_svm", "ag_set_export_buffer", "ag_get_points", "ag_get_images", "ag_preprocess", "ag_set_cloud", "ag_radius_search",
     "ag_fit_quadrics", "ag_hand_sweep", "ag_sweep_debug", "ag_hog_svm",
+    "ag_gather_slot_bytes", "ag_gather_create", "ag_gather_connect", "ag_gather_wait", "ag_gather_destroy",
 ]
 
 
@@ -61,6 +62,12 @@ def lib():
     L.ag_hand_sweep.argtypes = [vp, ip, C.c_int, C.POINTER(AgFrame), dp, C.c_uint, C.POINTER(C.POINTER(AgGrasp)), ip]
     L.ag_sweep_debug.argtypes = [vp, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.ag_hog_svm.argtypes = [vp, vp, C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.ag_gather_slot_bytes.restype = C.c_size_t
+    L.ag_gather_slot_bytes.argtypes = [C.c_int]
+    L.ag_gather_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_char_p]
+    L.ag_gather_connect.argtypes = [vp, C.c_char_p]
+    L.ag_gather_wait.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.ag_gather_destroy.argtypes = [vp]
     _LIB = L
     return L
 
@@ -185,6 +192,26 @@ class Context:
         lib().ag_free(pts)
         lib().ag_free(cam)
         return P3, Cm
+
+    # ---- peer gather: the grasp-list all-gather fused into the export kernel (include/ag_b200.h)
+    def gather_create(self, num_samples, world, rank):
+        """allocates this rank's gather buffer; returns its 64-byte CUDA IPC handle"""
+        hd = C.create_string_buffer(64)
+        _check(lib().ag_gather_create(self.h, int(num_samples), int(world), int(rank), hd))
+        self._gather_world = int(world)
+        return hd.raw
+
+    def gather_connect(self, handles):
+        """handles: list of every rank's 64-byte IPC handle, in rank order"""
+        _check(lib().ag_gather_connect(self.h, b"".join(handles)))
+
+    def gather_wait(self):
+        """waits until every rank's list of the last localize() has landed in this rank's buffer;
+        returns (n_hyp per rank, device address of slot 0, slot bytes)"""
+        n = (C.c_int32 * self._gather_world)()
+        ptr, sb = C.c_void_p(), C.c_size_t()
+        _check(lib().ag_gather_wait(self.h, n, C.byref(ptr), C.byref(sb)))
+        return list(n), ptr.value, sb.value
 
     def set_export_buffer(self, dev_ptr, nbytes):
         """device buffer that receives [n_hyp, n_vox, n_samples, error][records] on every localize()"""

@@ -81,6 +81,16 @@ struct Ctx {
   size_t h_out_cap = 0;
   void* d_export = nullptr;   // caller-registered device buffer (ag_set_export_buffer)
   size_t d_export_cap = 0;
+  // peer gather (ag_gather_*): this rank's buffer, every rank's buffer as mapped through CUDA IPC
+  void* gather_buf = nullptr;
+  void* gather_peer[AG_MAX_GATHER_RANKS] = {nullptr};
+  void* gather_done = nullptr;
+  void* gather_host_hdr = nullptr;
+  void* gather_host_hdr_dev = nullptr;
+  size_t gather_slot_bytes = 0;
+  int gather_world = 0, gather_rank = 0;
+  unsigned gather_epoch = 0;
+  bool gather_connected = false;
   // samples
   DevBuf samples, moments, frames, nn_counts, all_frames;
   DevBuf nbr_heads;  // per sample of the chunk: sample xyz + neighbour count (float4)

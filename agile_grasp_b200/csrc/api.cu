@@ -104,10 +104,22 @@ struct HostOut {
 // hand_search.cpp:194-200) straight from the per-slot records, merges the SVM results and writes the
 // list to mapped host memory, to the device copy used by ag_classify / ag_get_*, and to the optional
 // caller-registered device buffer.
+// Peer gather (ag_gather_*): slot `rank` of every rank's gather buffer, reached over NVLink through CUDA IPC
+// mappings.  Slot layout: [uint32 epoch flag, 12 pad][int32 n_hyp, n_vox, n_samples, error][records].
+struct PeerOut {
+  char* slot[AG_MAX_GATHER_RANKS];
+  int world;         // 0 = peer gather not configured
+  int cap;           // records per slot
+  unsigned epoch;
+  unsigned* done;    // CTA completion counter of this launch (device, zeroed by the last CTA)
+  int final_pass;    // 0: first export of a call (publishes only if no sample needs the large-slab re-run)
+};
+constexpr int kSlotHeaderBytes = 32;
+
 __global__ void k_export(const ag_grasp* __restrict__ raw, const int* __restrict__ slots, const int* __restrict__ n_sel,
                          const float* __restrict__ scores, const RowIndex* ri, const int* overflow,
                          const unsigned long long* counters, HostOut* hdr, ag_grasp* out_host, ag_grasp* out_dev,
-                         int* exp_hdr, ag_grasp* out_exp, int cap, int cap_exp) {
+                         int* exp_hdr, ag_grasp* out_exp, int cap, int cap_exp, PeerOut peer) {
   // a record is 10 x 16 bytes: three records per warp pass, every lane moves one uint4 (coalesced
   // 480-byte stores — the mapped host destination is written over PCIe and needs full-width writes)
   static_assert(sizeof(ag_grasp) == 160, "record layout");
@@ -130,6 +142,30 @@ __global__ void k_export(const ag_grasp* __restrict__ raw, const int* __restrict
     reinterpret_cast<uint4*>(out_host + i)[part] = v;
     reinterpret_cast<uint4*>(out_dev + i)[part] = v;
     if (out_exp && i < cap_exp) reinterpret_cast<uint4*>(out_exp + i)[part] = v;
+    if (i < peer.cap)  // fused all-gather: the record goes straight into every rank's buffer over NVLink
+      for (int r = 0; r < peer.world; r++)
+        reinterpret_cast<uint4*>(peer.slot[r] + kSlotHeaderBytes + size_t(i) * sizeof(ag_grasp))[part] = v;
+  }
+  if (peer.world > 0) {
+    // publish: every CTA fences its peer stores; the last one to finish writes the headers, fences again and
+    // raises the epoch flags the consumers (k_gather_wait on each rank) spin on
+    __shared__ bool s_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(peer.done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+      if (threadIdx.x < peer.world && (peer.final_pass || overflow[0] == 0)) {
+        int* h4 = reinterpret_cast<int*>(peer.slot[threadIdx.x] + 16);
+        h4[0] = min(n, peer.cap);
+        h4[1] = ri->n_points;
+        h4[2] = ri->n_samples;
+        h4[3] = ri->error | (n > peer.cap ? 0x100 : 0);
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned*>(peer.slot[threadIdx.x]) = peer.epoch;
+      }
+      if (threadIdx.x == 0) *peer.done = 0u;
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     hdr->n_hyp = n;
@@ -145,6 +181,34 @@ __global__ void k_export(const ag_grasp* __restrict__ raw, const int* __restrict
       exp_hdr[3] = ri->error;
     }
   }
+}
+
+// one thread per rank: spins until slot r of this rank's gather buffer carries `epoch` (the producer's
+// export kernel wrote it after a system-scope fence), then copies the slot header to mapped host memory.
+// A producer that never arrives (a failed peer) ends the wait after ~2 s with status 1.
+__global__ void k_gather_wait(const char* buf, size_t slot_bytes, int world, unsigned epoch, int* host_hdr /* world x 4 + 1 */) {
+  const int r = threadIdx.x;
+  __shared__ int s_bad;
+  if (r == 0) s_bad = 0;
+  __syncthreads();
+  if (r < world) {
+    const volatile unsigned* flag = reinterpret_cast<const volatile unsigned*>(buf + size_t(r) * slot_bytes);
+    const long long t0 = clock64();
+    bool ok = true;
+    while (int(*flag - epoch) < 0) {  // (a producer that ran ahead carries a later epoch: never a deadlock)
+      if (clock64() - t0 > 4000000000ll) {
+        ok = false;
+        break;
+      }
+      __nanosleep(200);
+    }
+    __threadfence_system();
+    const volatile int* h4 = reinterpret_cast<const volatile int*>(buf + size_t(r) * slot_bytes + 16);
+    for (int k = 0; k < 4; k++) host_hdr[r * 4 + k] = h4[k];
+    if (!ok) atomicOr(&s_bad, 1);
+  }
+  __syncthreads();
+  if (r == 0) host_hdr[world * 4] = s_bad;
 }
 
 // ---- SVM model file (OpenCV 2.4 YAML, svm_032015_linear_20_20_same:1-16,780-789) -------------
@@ -339,11 +403,24 @@ static int localize_core(Ctx* c, const void* d_points, int stride, int n_in, int
   int* exp_hdr = static_cast<int*>(c->d_export);
   ag_grasp* exp_recs = c->d_export ? reinterpret_cast<ag_grasp*>(static_cast<char*>(c->d_export) + 16) : nullptr;
   const int cap_exp = c->d_export ? int((c->d_export_cap - 16) / sizeof(ag_grasp)) : 0;
+  PeerOut peer;
+  std::memset(&peer, 0, sizeof(peer));
+  if (c->gather_world > 0 && c->gather_connected) {
+    c->gather_epoch++;
+    const size_t half = size_t(c->gather_world) * c->gather_slot_bytes;
+    for (int r = 0; r < c->gather_world; r++)
+      peer.slot[r] = static_cast<char*>(c->gather_peer[r]) + (c->gather_epoch & 1u) * half +
+                     size_t(c->gather_rank) * c->gather_slot_bytes;
+    peer.world = c->gather_world;
+    peer.cap = int((c->gather_slot_bytes - kSlotHeaderBytes) / sizeof(ag_grasp));
+    peer.epoch = c->gather_epoch;
+    peer.done = static_cast<unsigned*>(c->gather_done);
+  }
   auto do_export = [&]() {
     k_export<<<32, 256, 0, st>>>(c->grasps_raw.as<ag_grasp>(), c->hyp_slots.as<int>(), d_nsel,
                                       c->attached_svm ? c->scores.as<float>() : nullptr, ri, hand_sweep_overflow_ptr(c),
                                       c->counters.as<unsigned long long>(), hdr, recs, c->grasps.as<ag_grasp>(),
-                                      exp_hdr, exp_recs, int(slots), cap_exp);
+                                      exp_hdr, exp_recs, int(slots), cap_exp, peer);
   };
   do_export();
   c->launches += 1;
@@ -378,6 +455,7 @@ static int localize_core(Ctx* c, const void* d_points, int stride, int n_in, int
                           c->scores.as<float>(), nullptr);
       if (rc) return rc;
     }
+    peer.final_pass = 1;
     do_export();
     AG_CUDA_CHECK(cudaStreamSynchronize(st));
     Hn = h->n_hyp;
@@ -485,6 +563,7 @@ void ag_destroy(ag_ctx* h) {
   Ctx& c = h->c;
   cudaSetDevice(c.device);
   cudaStreamSynchronize(c.stream);
+  ag_gather_destroy(h);
   if (c.h_out) cudaFreeHost(c.h_out);
   for (DevBuf* b : {&c.raw, &c.keys, &c.keys_sorted, &c.keys_unique, &c.cub_tmp, &c.block_counts, &c.misc, &c.vox,
                     &c.row_ptr, &c.col_ptr, &c.row_index, &c.all_frames,
@@ -649,6 +728,106 @@ int ag_set_export_buffer(ag_ctx* h, void* d_buffer, size_t bytes) {
   }
   h->c.d_export = d_buffer;
   h->c.d_export_cap = d_buffer ? bytes : 0;
+  return AG_OK;
+}
+
+// ---- peer gather: the grasp-list all-gather fused into the export kernel (NVLink peer stores) ----------
+size_t ag_gather_slot_bytes(int num_samples) { return size_t(kSlotHeaderBytes) + size_t(8) * size_t(num_samples) * sizeof(ag_grasp); }
+
+int ag_gather_create(ag_ctx* h, int num_samples, int world, int rank, unsigned char* ipc_handle_out) {
+  if (!h || world < 1 || world > AG_MAX_GATHER_RANKS || rank < 0 || rank >= world || num_samples < 1 || !ipc_handle_out) {
+    set_error("ag_gather_create: bad arguments");
+    return AG_ERR_INVALID;
+  }
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  if (c.gather_buf) {
+    set_error("ag_gather_create: already created for this context");
+    return AG_ERR_INVALID;
+  }
+  c.gather_slot_bytes = ag_gather_slot_bytes(num_samples);
+  const size_t bytes = 2 * size_t(world) * c.gather_slot_bytes;  // two epochs (parity) x world slots
+  AG_CUDA_CHECK(cudaMalloc(&c.gather_buf, bytes));
+  AG_CUDA_CHECK(cudaMemset(c.gather_buf, 0, bytes));
+  AG_CUDA_CHECK(cudaMalloc(&c.gather_done, 64));
+  AG_CUDA_CHECK(cudaMemset(c.gather_done, 0, 64));
+  AG_CUDA_CHECK(cudaHostAlloc(&c.gather_host_hdr, (world * 4 + 4) * sizeof(int), cudaHostAllocMapped));
+  AG_CUDA_CHECK(cudaHostGetDevicePointer(&c.gather_host_hdr_dev, c.gather_host_hdr, 0));
+  cudaIpcMemHandle_t hd;
+  AG_CUDA_CHECK(cudaIpcGetMemHandle(&hd, c.gather_buf));
+  static_assert(sizeof(hd) == AG_IPC_HANDLE_BYTES, "IPC handle size");
+  std::memcpy(ipc_handle_out, &hd, sizeof(hd));
+  c.gather_world = world;
+  c.gather_rank = rank;
+  c.gather_epoch = 0;
+  c.gather_connected = false;
+  AG_CUDA_CHECK(cudaDeviceSynchronize());
+  return AG_OK;
+}
+
+int ag_gather_connect(ag_ctx* h, const unsigned char* handles) {
+  if (!h || !handles || h->c.gather_world < 1 || !h->c.gather_buf) {
+    set_error("ag_gather_connect: ag_gather_create first");
+    return AG_ERR_INVALID;
+  }
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  for (int r = 0; r < c.gather_world; r++) {
+    if (r == c.gather_rank) {
+      c.gather_peer[r] = c.gather_buf;
+      continue;
+    }
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, handles + size_t(r) * AG_IPC_HANDLE_BYTES, sizeof(hd));
+    AG_CUDA_CHECK(cudaIpcOpenMemHandle(&c.gather_peer[r], hd, cudaIpcMemLazyEnablePeerAccess));
+  }
+  c.gather_connected = true;
+  return AG_OK;
+}
+
+int ag_gather_wait(ag_ctx* h, int32_t* n_hyp_per_rank, const void** d_slots, size_t* slot_bytes) {
+  if (!h || !h->c.gather_connected || h->c.gather_epoch == 0) {
+    set_error("ag_gather_wait: no connected peer gather / no ag_localize yet");
+    return AG_ERR_INVALID;
+  }
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  const char* cur = static_cast<const char*>(c.gather_buf) + (c.gather_epoch & 1u) * size_t(c.gather_world) * c.gather_slot_bytes;
+  k_gather_wait<<<1, 32, 0, c.stream>>>(cur, c.gather_slot_bytes, c.gather_world, c.gather_epoch,
+                                       static_cast<int*>(c.gather_host_hdr_dev));
+  AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  const int* hh = static_cast<const int*>(c.gather_host_hdr);
+  if (hh[c.gather_world * 4]) {
+    set_error("ag_gather_wait: a peer did not publish its grasp list (timeout)");
+    return AG_ERR_CUDA;
+  }
+  int err = 0;
+  for (int r = 0; r < c.gather_world; r++) {
+    if (n_hyp_per_rank) n_hyp_per_rank[r] = hh[r * 4];
+    err |= hh[r * 4 + 3];
+  }
+  if (d_slots) *d_slots = cur;
+  if (slot_bytes) *slot_bytes = c.gather_slot_bytes;
+  if (err & 0x100) {
+    set_error("ag_gather_wait: a rank produced more hypotheses than a gather slot holds");
+    return AG_ERR_CAPACITY;
+  }
+  return AG_OK;
+}
+
+int ag_gather_destroy(ag_ctx* h) {
+  if (!h) return AG_ERR_INVALID;
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  cudaStreamSynchronize(c.stream);
+  for (int r = 0; r < c.gather_world; r++)
+    if (c.gather_connected && r != c.gather_rank && c.gather_peer[r]) cudaIpcCloseMemHandle(c.gather_peer[r]);
+  if (c.gather_buf) cudaFree(c.gather_buf);
+  if (c.gather_done) cudaFree(c.gather_done);
+  if (c.gather_host_hdr) cudaFreeHost(c.gather_host_hdr);
+  c.gather_buf = c.gather_done = c.gather_host_hdr = c.gather_host_hdr_dev = nullptr;
+  c.gather_world = 0;
+  c.gather_connected = false;
   return AG_OK;
 }
 

@@ -69,3 +69,35 @@ def parse_export(buf_u8):
     item = GRASP_DTYPE.itemsize
     recs = np.frombuffer(buf_u8[EXPORT_HEADER_BYTES:EXPORT_HEADER_BYTES + n * item].tobytes(), dtype=GRASP_DTYPE)
     return dict(n_hyp=n, n_vox=int(hdr[1]), n_samples=int(hdr[2]), error=int(hdr[3])), recs
+
+
+GATHER_SLOT_HEADER = 32
+
+
+def setup_peer_gather(ctx, num_samples, group=None):
+    """Fused export + all-gather over NVLink peer memory (include/ag_b200.h, ag_gather_*): every rank creates
+    its gather buffer, the CUDA IPC handles are exchanged once through torch.distributed, every rank maps
+    every buffer.  After this, ctx.localize*() stores the rank's grasp list into all ranks' buffers and
+    ctx.gather_wait() returns once all lists have arrived - no collective call per step."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    handle = ctx.gather_create(num_samples, world, rank)
+    handles = [None] * world
+    dist.all_gather_object(handles, handle, group=group)
+    ctx.gather_connect(handles)
+    dist.barrier(group=group)
+
+
+def read_gathered(n_hyp, slots_ptr, slot_bytes):
+    """host copy of the gathered lists (debug / verification): list of GRASP_DTYPE arrays, one per rank"""
+    import ctypes as C
+    rt = C.CDLL("libcudart.so")
+    out = []
+    item = GRASP_DTYPE.itemsize
+    for r, n in enumerate(n_hyp):
+        buf = np.zeros(max(n, 0) * item, np.uint8)
+        if n > 0:
+            rc = rt.cudaMemcpy(C.c_void_p(buf.ctypes.data), C.c_void_p(slots_ptr + r * slot_bytes + GATHER_SLOT_HEADER),
+                               C.c_size_t(n * item), C.c_int(2))
+            assert rc == 0, rc
+        out.append(np.frombuffer(buf.tobytes(), dtype=GRASP_DTYPE))
+    return out

@@ -143,6 +143,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU grasp-list exchange: NVLink peer stores fused into the export kernel, or NCCL")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -181,15 +183,22 @@ def main():
     # multi-GPU: the library leaves [header][records] in a device buffer; one fixed-size NCCL all-gather
     # makes every rank hold every rank's grasp list (device resident)
     from agile_grasp_b200 import shard
-    if world > 1:
+    peer_gather = world > 1 and args.gather == "peer"
+    if peer_gather:
+        shard.setup_peer_gather(ctx, pool[0]["P"].num_samples)
+    elif world > 1:
         nbytes = shard.export_buffer_bytes(pool[0]["P"].num_samples)
         send = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
         recv = torch.zeros(nbytes * world, dtype=torch.uint8, device=dev)
         ctx.set_export_buffer(send.data_ptr(), nbytes)
+    last_gather = [None]
 
     def gather(local_g):
         if world == 1:
             return len(local_g)
+        if peer_gather:  # the export kernel already stored this rank's list into every rank's buffer
+            last_gather[0] = ctx.gather_wait()
+            return last_gather[0]
         allbuf = shard.all_gather_export(send, recv)
         return allbuf  # counts are read after the timed region (no host sync inside the step)
 
@@ -215,7 +224,7 @@ def main():
     for w in range(args.warmup):
         g, _, _ = step_device(pool[w % len(pool)])
         gather(g)
-        step_host(pool[w % len(pool)])
+        gather(step_host(pool[w % len(pool)]))
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -231,11 +240,14 @@ def main():
         torch.cuda.synchronize()
         g, t1, t2 = step_device(c)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tg0 = time.perf_counter()
         e0.record()
         total = gather(g)
         e1.record()
         torch.cuda.synchronize()
-        cm = e0.elapsed_time(e1) if world > 1 else 0.0
+        # peer gather: the stores ride inside ag_localize's export kernel (already in total_ms); what is left
+        # is the wait for the slowest peer, on the library stream -> wall clock of ag_gather_wait
+        cm = 0.0 if world == 1 else ((time.perf_counter() - tg0) * 1e3 if peer_gather else e0.elapsed_time(e1))
         dev_ms.append(t1["total_ms"] + cm)  # scoring is fused into ag_localize (ag_set_svm): already inside total_ms
         comm_ms.append(cm)
         hyps.append(len(g))
@@ -263,10 +275,20 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     gathered = None
-    if world > 1:  # decode the last all-gather on the host (outside the timed region): every rank's list is there
+    if peer_gather:  # verify the last exchange on the host (outside the timed region): every rank's list is there
+        n_per, slots_ptr, slot_bytes = last_gather[0]
+        lists = shard.read_gathered(n_per, slots_ptr, slot_bytes)
+        assert n_per[rank] == e2e_h[-1], (n_per, e2e_h[-1])
+        for nm in ("sample_index", "orientation", "score", "label", "width", "surface", "bottom"):
+            assert np.array_equal(lists[rank][nm], g[nm]), "own slot differs from the returned list: " + nm
+        for r in range(world):  # every rank's list is well formed (sample-major order)
+            assert np.all(np.diff(lists[r]["sample_index"]) >= 0)
+        gathered = {"per_rank": n_per, "mode": "peer stores over NVLink (ag_gather_*), no collective per step"}
+    elif world > 1:  # decode the last all-gather on the host (outside the timed region)
         host = recv.cpu().numpy().reshape(world, -1)
         parts = [shard.parse_export(host[r]) for r in range(world)]
-        gathered = {"per_rank": [p[0]["n_hyp"] for p in parts], "errors": [p[0]["error"] for p in parts]}
+        gathered = {"per_rank": [p[0]["n_hyp"] for p in parts], "errors": [p[0]["error"] for p in parts],
+                    "mode": "NCCL all_gather_into_tensor of the fixed-size export buffer"}
         assert parts[rank][0]["n_hyp"] == e2e_h[-1], (parts[rank][0], e2e_h[-1])
 
     # ---- reduce over ranks: time = max, hypotheses = sum
@@ -298,7 +320,9 @@ def main():
                                    "per step, 2000 samples, linear SVM svm_032015_linear_20_20_same",
                        "l2": "flushed between timed iterations (256 MiB write)",
                        "hypotheses_per_step": float(n_h[0] / args.steps),
-                       "multi_gpu": "one cloud per rank per step + NCCL all-gather of grasp records" if world > 1
+                       "multi_gpu": ("one cloud per rank per step; grasp lists exchanged by " +
+                                     ("NVLink peer stores fused into the export kernel" if peer_gather else
+                                      "an NCCL all-gather")) if world > 1
                        else "single GPU", "timer": "CUDA events on the library stream (ag_timings), max over ranks"},
             "e2e": {"value": float(e2e), "unit": "hyp/s", "ms_per_cloud": float(t_dev[1] / args.steps),
                     "h2d_bytes_per_step": int(c0["n"] * c0["stride"]),

@@ -169,6 +169,26 @@ int ag_set_svm(ag_ctx* ctx, const ag_svm* svm);
  * bytes must be >= 16 + 8 * samples * sizeof(ag_grasp); NULL unregisters. */
 int ag_set_export_buffer(ag_ctx* ctx, void* d_buffer, size_t bytes);
 
+/* Multi-GPU grasp-list exchange WITHOUT a collective call (one process per GPU, all GPUs of one NVLink/
+ * NVSwitch box).  Every rank creates a gather buffer (two epochs x world slots), publishes its CUDA IPC
+ * handle, and connects to the handles of all ranks (rank order, its own included).  From then on the export
+ * kernel of every ag_localize stores this rank's [header][records] directly into slot `rank` of EVERY rank's
+ * buffer over NVLink and raises an epoch flag; ag_gather_wait() waits (on the device) until all `world`
+ * slots of this rank's buffer carry the current epoch and returns the per-rank hypothesis counts plus the
+ * device address of the slots: slot r = d_slots + r * slot_bytes, records start AG_GATHER_SLOT_HEADER bytes
+ * into a slot, in the reference's sample-major order (hand_search.cpp:194-200).  All ranks must call
+ * ag_localize the same number of times; a slot's contents stay valid until the second following
+ * ag_localize.  This replaces the NCCL all-gather of ag_set_export_buffer (kept for other backends). */
+#define AG_MAX_GATHER_RANKS 8
+#define AG_IPC_HANDLE_BYTES 64
+#define AG_GATHER_SLOT_HEADER 32
+size_t ag_gather_slot_bytes(int num_samples);
+int ag_gather_create(ag_ctx* ctx, int num_samples, int world, int rank, unsigned char* ipc_handle_out /* 64 B */);
+int ag_gather_connect(ag_ctx* ctx, const unsigned char* handles /* world x 64 B, rank order */);
+int ag_gather_wait(ag_ctx* ctx, int32_t* n_hyp_per_rank /* world, may be NULL */, const void** d_slots,
+                   size_t* slot_bytes);
+int ag_gather_destroy(ag_ctx* ctx);
+
 /* Variable-length members of GraspHypothesis for hypothesis `image_id` of the last ag_localize
  * (requires AG_FLAG_KEEP_POINTS): points_for_learning (3 x m, column-major doubles) and the
  * camera source of each column. */
