@@ -21,7 +21,7 @@ EXPORTS = [
     "ag_get_timings", "ag_free", "ag_svm_load", "ag_svm_free", "ag_svm_info", "ag_localize", "ag_localize_device",
     "ag_classify", "ag_set_svm", "ag_set_export_buffer", "ag_get_points", "ag_get_images", "ag_preprocess", "ag_set_cloud", "ag_radius_search",
     "ag_fit_quadrics", "ag_hand_sweep", "ag_sweep_debug", "ag_hog_svm",
-    "ag_gather_slot_bytes", "ag_gather_create", "ag_gather_connect", "ag_gather_wait", "ag_gather_destroy",
+    "ag_find_handles", "ag_load_pcd", "ag_gather_slot_bytes", "ag_gather_create", "ag_gather_connect", "ag_gather_wait", "ag_gather_destroy",
 ]
 
 
@@ -62,6 +62,9 @@ def lib():
     L.ag_hand_sweep.argtypes = [vp, ip, C.c_int, C.POINTER(AgFrame), dp, C.c_uint, C.POINTER(C.POINTER(AgGrasp)), ip]
     L.ag_sweep_debug.argtypes = [vp, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.ag_hog_svm.argtypes = [vp, vp, C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.ag_find_handles.argtypes = [vp, C.POINTER(AgGrasp), C.c_int, C.c_int, C.c_double, C.POINTER(C.c_void_p), ip,
+                                  C.POINTER(C.POINTER(C.c_int32)), ip]
+    L.ag_load_pcd.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), ip, ip, ip]
     L.ag_gather_slot_bytes.restype = C.c_size_t
     L.ag_gather_slot_bytes.argtypes = [C.c_int]
     L.ag_gather_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_char_p]
@@ -117,6 +120,15 @@ class Svm:
         if getattr(self, "h", None):
             lib().ag_svm_free(self.h)
             self.h = None
+
+
+def load_pcd(path):
+    """ag_load_pcd: PCD file -> (n, 8) float32 view of pcl::PointXYZRGBA records (x y z _ rgba-bits _ _ _), width, height"""
+    p, n, w, h = C.c_void_p(), C.c_int(), C.c_int(), C.c_int()
+    _check(lib().ag_load_pcd(str(path).encode(), C.byref(p), C.byref(n), C.byref(w), C.byref(h)))
+    arr = np.frombuffer(C.string_at(p, n.value * 32), dtype=np.float32).reshape(n.value, 8).copy()
+    lib().ag_free(p)
+    return arr, w.value, h.value
 
 
 class Context:
@@ -192,6 +204,19 @@ class Context:
         lib().ag_free(pts)
         lib().ag_free(cam)
         return P3, Cm
+
+    def find_handles(self, grasps, min_inliers, min_length):
+        """HandleSearch::findHandles on grasp records -> (handles: HANDLE_DTYPE array, list of inlier index arrays)"""
+        from .ctypes_defs import HANDLE_DTYPE
+        g = np.ascontiguousarray(grasps)
+        hp, ip_, nh, ni = C.c_void_p(), C.POINTER(C.c_int32)(), C.c_int(), C.c_int()
+        _check(lib().ag_find_handles(self.h, g.ctypes.data_as(C.POINTER(AgGrasp)), g.shape[0], int(min_inliers),
+                                     float(min_length), C.byref(hp), C.byref(nh), C.byref(ip_), C.byref(ni)))
+        H = np.frombuffer(C.string_at(hp, nh.value * HANDLE_DTYPE.itemsize), dtype=HANDLE_DTYPE).copy()
+        flat = np.ctypeslib.as_array(ip_, shape=(max(ni.value, 1),))[:ni.value].copy()
+        lib().ag_free(hp)
+        lib().ag_free(ip_)
+        return H, [flat[h["inlier_offset"]:h["inlier_offset"] + h["n_inliers"]] for h in H]
 
     # ---- peer gather: the grasp-list all-gather fused into the export kernel (include/ag_b200.h)
     def gather_create(self, num_samples, world, rank):

@@ -99,6 +99,7 @@ struct Ctx {
   int n_samples = 0;
   // sweep outputs
   DevBuf grasps_raw, valid, images_raw, hyp_slots, grasps, counters, scores, descriptors, kvals, sweep_dbg, overflow;
+  DevBuf handle_in, handle_bits;  // ag_find_handles: grasp records and the n x n inlier bit matrix
   int n_hyp = 0;
   bool images_valid = false;
   unsigned sweep_flags = 0;          // arguments of the last hand_sweep_enqueue (for the overflow re-run)
@@ -140,4 +141,12 @@ int radius_search_device(Ctx* c, const float q[3], double radius, std::vector<in
 void compute_hand_const(const ag_params& p, HandConst& h);
 int svm_to_device(SvmModel* svm, int device);
 
+}  // namespace ag
+
+// the opaque handle of the C ABI
+struct ag_ctx {
+  ag::Ctx c;
+};
+namespace ag {
+inline Ctx& ctx_of(ag_ctx* h) { return h->c; }
 }  // namespace ag

@@ -491,9 +491,6 @@ static int localize_core(Ctx* c, const void* d_points, int stride, int n_in, int
 
 using namespace ag;
 
-struct ag_ctx {
-  Ctx c;
-};
 struct ag_svm {
   SvmModel* m;
 };
@@ -568,7 +565,7 @@ void ag_destroy(ag_ctx* h) {
   for (DevBuf* b : {&c.raw, &c.keys, &c.keys_sorted, &c.keys_unique, &c.cub_tmp, &c.block_counts, &c.misc, &c.vox,
                     &c.row_ptr, &c.col_ptr, &c.row_index, &c.all_frames,
                     &c.normals, &c.samples, &c.moments, &c.frames, &c.nn_counts, &c.nbr_pool, &c.nbr_heads, &c.grasps_raw, &c.valid,
-                    &c.images_raw, &c.hyp_slots, &c.grasps, &c.counters, &c.scores, &c.descriptors, &c.kvals, &c.sweep_dbg, &c.overflow})
+                    &c.images_raw, &c.hyp_slots, &c.grasps, &c.counters, &c.scores, &c.descriptors, &c.kvals, &c.handle_in, &c.handle_bits, &c.sweep_dbg, &c.overflow})
     b->release();
   if (c.h_pinned) cudaFreeHost(c.h_pinned);
   for (auto& ev : c.ev) cudaEventDestroy(ev);

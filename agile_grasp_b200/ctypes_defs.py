@@ -82,6 +82,10 @@ GRASP_DTYPE = np.dtype([
     ("sample_slot", "<i4"), ("orientation", "<i4"), ("cam_source", "<i4"), ("num_points", "<i4"),
     ("image_id", "<i4"), ("half_antipodal", "u1"), ("full_antipodal", "u1"), ("label", "u1"),
     ("reserved", "u1")], align=True)
+HANDLE_DTYPE = np.dtype([("axis", "<f8", 3), ("center", "<f8", 3), ("approach", "<f8", 3), ("binormal", "<f8", 3),
+                         ("hands_center", "<f8", 3), ("width", "<f8"), ("n_inliers", "<i4"),
+                         ("inlier_offset", "<i4")], align=True)
+assert HANDLE_DTYPE.itemsize == 136
 FRAME_DTYPE = np.dtype([("normal", "<f8", 3), ("axis", "<f8", 3), ("binormal", "<f8", 3),
                         ("num_neighbors", "<i4"), ("majority_cam", "<i4")], align=True)
 assert GRASP_DTYPE.itemsize == C.sizeof(AgGrasp) == 160, (GRASP_DTYPE.itemsize, C.sizeof(AgGrasp))

@@ -110,6 +110,18 @@ typedef struct ag_frame {
   int32_t majority_cam;
 } ag_frame;
 
+/* "Average grasp" of a handle = collinear cluster of grasp hypotheses: class Handle, handle.h / handle.cpp:3-73 */
+typedef struct ag_handle {
+  double axis[3];          /* Handle::getAxis: principal direction of the inliers' axes */
+  double center[3];        /* getCenter: grasp bottom of the inlier nearest the middle of the handle */
+  double approach[3];      /* getApproach of that inlier */
+  double binormal[3];      /* approach x axis */
+  double hands_center[3];  /* getHandsCenter: grasp surface of that inlier */
+  double width;            /* mean grasp width of the inliers */
+  int32_t n_inliers;       /* inliers of this handle: inlier list [inlier_offset, inlier_offset + n_inliers) */
+  int32_t inlier_offset;
+} ag_handle;
+
 typedef struct ag_timings {
   float h2d_ms, preprocess_ms, grid_ms, normals_all_ms, quadric_ms, sweep_ms, hog_svm_ms, d2h_ms, total_ms;
   int32_t n_in, n_voxels, n_samples, n_hyp;
@@ -188,6 +200,21 @@ int ag_gather_connect(ag_ctx* ctx, const unsigned char* handles /* world x 64 B,
 int ag_gather_wait(ag_ctx* ctx, int32_t* n_hyp_per_rank /* world, may be NULL */, const void** d_slots,
                    size_t* slot_bytes);
 int ag_gather_destroy(ag_ctx* ctx);
+
+/* pcl::io::loadPCDFile<pcl::PointXYZRGBA> (localization.cpp:184,198; file overloads :169-214): reads a PCD
+ * v0.7 file (DATA ascii | binary | binary_compressed) into malloc'ed pcl::PointXYZRGBA records (32 bytes
+ * each, x y z float32 at bytes 0/4/8, rgba uint32 at byte 16) — the layout ag_localize takes with
+ * stride 32.  Host only (no device needed).  width/height may be NULL. */
+int ag_load_pcd(const char* path, void** points_out, int* n_out, int* width_out, int* height_out);
+
+/* HandleSearch::findHandles (handle_search.cpp:4-89) + Handle (handle.cpp:3-73): the step that follows
+ * predictAntipodalHands in every caller (grasp_localizer.cpp:103, src/nodes/test.cpp:97).  The O(n^2) pair
+ * predicate (distance from the axis line < 0.01, axis angle and approach angle < 0.34 rad: three acos per
+ * pair) is evaluated on the GPU into an n x n bit matrix; the greedy, order-dependent clustering walks the
+ * set bits on the host.  hands: n records (host).  Outputs malloc'ed (ag_free): handles and the flat inlier
+ * index list.  Deviations from the reference are listed in INTEGRATION.md (eigenvector sign, sort ties). */
+int ag_find_handles(ag_ctx* ctx, const ag_grasp* hands, int n, int min_inliers, double min_length,
+                    ag_handle** handles_out, int* n_handles, int32_t** inliers_out, int* n_inliers_total);
 
 /* Variable-length members of GraspHypothesis for hypothesis `image_id` of the last ag_localize
  * (requires AG_FLAG_KEEP_POINTS): points_for_learning (3 x m, column-major doubles) and the

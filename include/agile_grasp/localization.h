@@ -3,7 +3,7 @@
 // Same method names, argument meaning and error behaviour: errors print to stdout and return an empty
 // vector (localization.cpp:9-15,184-189; learning.cpp:172-191).  Differences, all documented in
 // num_threads is accepted and ignored (the GPU path has no thread knob); only
-// NO_PLOTTING is honoured; findHandles / createVisualsPub are outside the hot path and not provided;
+// NO_PLOTTING is honoured; createVisualsPub needs ROS and is not provided;
 // points_for_learning stay on the device unless requested.
 #ifndef AGILE_GRASP_LOCALIZATION_H_
 #define AGILE_GRASP_LOCALIZATION_H_
@@ -16,6 +16,7 @@
 #include "../ag_b200.h"
 #include "compat_types.h"
 #include "grasp_hypothesis.h"
+#include "handle.h"
 
 typedef pcl::PointCloud<pcl::PointXYZRGBA> PointCloud;
 
@@ -79,6 +80,74 @@ class Localization {
     ag_free(out);
     std::cout << " # hands: " << hand_list.size() << "\n";
     return hand_list;
+  }
+
+  /** Localize hands given two point cloud files (reference: localization.cpp:169-214; the right file name may be
+   *  empty).  PCD v0.7 files, DATA ascii / binary / binary_compressed. */
+  std::vector<GraspHypothesis> localizeHands(const std::string& pcd_filename_left, const std::string& pcd_filename_right,
+                                             bool calculates_antipodal = false, bool uses_clustering = false) {
+    std::vector<int> indices(0);
+    return localizeHands(pcd_filename_left, pcd_filename_right, indices, calculates_antipodal, uses_clustering);
+  }
+  std::vector<GraspHypothesis> localizeHands(const std::string& pcd_filename_left, const std::string& pcd_filename_right,
+                                             const std::vector<int>& indices, bool calculates_antipodal = false,
+                                             bool uses_clustering = false) {
+    std::vector<GraspHypothesis> none;
+    PointCloud::Ptr cloud(new PointCloud);
+    size_t size_left = 0;
+    for (int side = 0; side < 2; side++) {
+      const std::string& name = side == 0 ? pcd_filename_left : pcd_filename_right;
+      if (side == 1 && name.empty()) break;
+      void* pts = nullptr;
+      int n = 0, w = 0, h = 0;
+      if (ag_load_pcd(name.c_str(), &pts, &n, &w, &h) != AG_OK) {
+        std::cout << "Couldn't read pcd_filename_left file: " << name << " \n";  // (sic, localization.cpp:186,200)
+        return none;
+      }
+      if (side == 0 && !pcd_filename_right.empty()) std::cout << "Loaded left point cloud with " << w * h << " data points.\n";
+      else if (side == 0) std::cout << "Loaded point cloud with " << w * h << " data points.\n";
+      else std::cout << "Loaded right point cloud with " << w * h << " data points.\n";
+      const pcl::PointXYZRGBA* p = static_cast<const pcl::PointXYZRGBA*>(pts);
+      cloud->points.insert(cloud->points.end(), p, p + n);
+      ag_free(pts);
+      if (side == 0) size_left = cloud->points.size();
+    }
+    std::cout << "Concatenating point clouds ...\n";
+    return localizeHands(cloud, int(size_left), indices, calculates_antipodal, uses_clustering);
+  }
+
+  /** Find handles = collinear clusters of grasps (reference: localization.cpp:390-408 -> HandleSearch::findHandles,
+   *  handle_search.cpp:4-89).  Plotting modes are not honoured. */
+  std::vector<Handle> findHandles(const std::vector<GraspHypothesis>& hand_list, int min_inliers, double min_length) {
+    std::vector<Handle> handles;
+    if (!ensure_ctx()) return handles;
+    std::vector<ag_grasp> recs(hand_list.size());
+    for (size_t i = 0; i < recs.size(); i++) {
+      recs[i] = hand_list[i].record();
+      for (int k = 0; k < 3; k++) {  // (hypotheses built through the reference's own constructor carry no record)
+        recs[i].axis[k] = hand_list[i].getAxis()(k);
+        recs[i].approach[k] = hand_list[i].getApproach()(k);
+        recs[i].bottom[k] = hand_list[i].getGraspBottom()(k);
+        recs[i].surface[k] = hand_list[i].getGraspSurface()(k);
+      }
+      recs[i].width = hand_list[i].getGraspWidth();
+    }
+    ag_handle* hs = nullptr;
+    int32_t* inl = nullptr;
+    int nh = 0, ni = 0;
+    if (ag_find_handles(ctx_, recs.data(), int(recs.size()), min_inliers, min_length, &hs, &nh, &inl, &ni) != AG_OK) {
+      std::cout << ag_last_error() << "\n";
+      return handles;
+    }
+    for (int k = 0; k < nh; k++) {
+      std::vector<int> in(inl + hs[k].inlier_offset, inl + hs[k].inlier_offset + hs[k].n_inliers);
+      handles.push_back(Handle(hand_list, in, hs[k]));
+      std::cout << "handle found with " << in.size() << " inliers\n";
+    }
+    ag_free(hs);
+    ag_free(inl);
+    std::cout << "Handle Search\n " << handles.size() << " handles found\n";
+    return handles;
   }
 
   /** Predict antipodal hands with the SVM stored in svm_filename (reference: localization.cpp:142-167,

@@ -104,6 +104,11 @@ ago_hands* ago_localize(const void* points, int stride, int n_in, int size_left,
                         const int* indices, int n_indices, unsigned flags, const ago_svm* svm,
                         int use_std_set, double* times_ms, int* n_voxels_out);
 
+/* HandleSearch::findHandles + Handle (handle_search.cpp:4-118, handle.cpp:3-73) on grasp records; outputs
+ * malloc'ed: handles, flat inlier index list (handle k owns [inlier_offset, inlier_offset + n_inliers)). */
+int ago_find_handles(const ag_grasp* hands, int n, int min_inliers, double min_length, ag_handle** handles_out,
+                     int* n_handles, int32_t** inliers_out, int* n_inliers_total);
+
 /* deterministic sample draw shared with the product: sorted distinct indices in [0,n) */
 int ago_draw_samples(int n, int num_samples, uint64_t seed, int32_t* out);
 

@@ -313,6 +313,22 @@ def localize(points32, size_left, params: AgParams, indices=None, flags=0, svm=N
     return Hands(h), dict(zip(names, tm.tolist())), nv.value
 
 
+def find_handles(grasps, min_inliers, min_length):
+    """HandleSearch::findHandles + Handle on grasp records -> (handles: HANDLE_DTYPE array, inlier index arrays)"""
+    from agile_grasp_b200.ctypes_defs import HANDLE_DTYPE
+    g = np.ascontiguousarray(grasps)
+    hp, ip_, nh, ni = C.c_void_p(), C.POINTER(C.c_int32)(), C.c_int(), C.c_int()
+    rc = lib().ago_find_handles(g.ctypes.data_as(C.POINTER(AgGrasp)), g.shape[0], int(min_inliers), C.c_double(min_length),
+                                C.byref(hp), C.byref(nh), C.byref(ip_), C.byref(ni))
+    if rc:
+        raise RuntimeError(_err())
+    H = np.frombuffer(C.string_at(hp, nh.value * HANDLE_DTYPE.itemsize), dtype=HANDLE_DTYPE).copy()
+    flat = np.ctypeslib.as_array(ip_, shape=(max(ni.value, 1),))[:ni.value].copy()
+    lib().ago_free(hp)
+    lib().ago_free(ip_)
+    return H, [flat[h["inlier_offset"]:h["inlier_offset"] + h["n_inliers"]] for h in H]
+
+
 def draw_samples(n, num_samples, seed):
     out = np.zeros(min(n, num_samples), np.int32)
     k = lib().ago_draw_samples(int(n), int(num_samples), C.c_uint64(seed), _p(out, C.c_int32))

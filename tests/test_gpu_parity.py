@@ -462,3 +462,39 @@ def test_other_baseline_configs_full_size(ctx, config, linear_svm_path):
     gg, keep = ctx.classify(api.Svm(linear_svm_path), gs)
     keep_o = H.classify(O.Svm(linear_svm_path), P)
     assert (_u32(gg["score"]) == _u32(H.grasps["score"])).all() and np.array_equal(keep, keep_o)
+
+
+@pytest.mark.parametrize("seed,min_inliers,min_length", [(0, 3, 0.005), (1, 5, 0.02), (5, 2, 0.0)])
+def test_find_handles_matches_oracle(ctx, oracle, seed, min_inliers, min_length):
+    """ag_find_handles (GPU pair predicate + host greedy) vs the oracle's literal double loop
+    (handle_search.cpp:4-118, handle.cpp:3-73): identical inlier lists, identical copied fields, axis 1e-12."""
+    from test_oracle_handles import synthetic_grasps
+    g = synthetic_grasps(seed, clutter=300)
+    H, inl = ctx.find_handles(g, min_inliers, min_length)
+    Ho, inlo = oracle.find_handles(g, min_inliers, min_length)
+    assert len(H) == len(Ho) and len(H) >= 2
+    for k in range(len(H)):
+        assert np.array_equal(inl[k], inlo[k])
+        for nm in ("center", "approach", "hands_center"):
+            assert (_u64(H[k][nm]) == _u64(Ho[k][nm])).all(), nm
+        assert np.allclose(H[k]["axis"], Ho[k]["axis"], atol=1e-12)
+        assert np.allclose(H[k]["binormal"], Ho[k]["binormal"], atol=1e-12)
+        assert abs(H[k]["width"] - Ho[k]["width"]) <= 1e-15
+
+
+def test_find_handles_on_pipeline_output(ctx, oracle, small_scene, linear_svm_path):
+    """handles of the positives of a real localize + classify run (the caller sequence of
+    grasp_localizer.cpp:95-103 with min_inliers = 3, min_length = 0.005)"""
+    s = small_scene
+    ctx.set_params(s["P"])
+    g = ctx.localize(s["pts"], s["size_left"], s["idx"])
+    gg, keep = ctx.classify(api.Svm(linear_svm_path), g)
+    pos = gg[keep.astype(bool)]
+    H, inl = ctx.find_handles(pos, 3, 0.005)
+    Ho, inlo = oracle.find_handles(pos, 3, 0.005)
+    assert len(H) == len(Ho)
+    for k in range(len(H)):
+        assert np.array_equal(inl[k], inlo[k])
+        assert np.allclose(H[k]["axis"], Ho[k]["axis"], atol=1e-12)
+    H0, inl0 = ctx.find_handles(pos[:0], 3, 0.005)
+    assert len(H0) == 0
