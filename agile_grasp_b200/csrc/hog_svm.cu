@@ -460,15 +460,34 @@ k_svm_gemm(const float* __restrict__ desc, const float* __restrict__ sv, int n_b
   }
 }
 
-// decision value per hypothesis, in CvSVM::predict's order: sum = -rho; sum += alpha_k * K[index_k], k ascending
-__global__ void k_svm_decide(const float* __restrict__ kvals, int n_bound, const int* __restrict__ n_dev, SvmDev svm,
-                             float* __restrict__ scores, ag_grasp* __restrict__ grasps_out) {
+// decision value per hypothesis, in CvSVM::predict's order: sum = -rho; sum += alpha_k * K[index_k], k ascending.
+// One warp per 32 hypotheses: tiles of 32 x 32 kernel values are loaded coalesced into shared memory, then
+// lane r walks row r sequentially (binary64 multiply, then add — no contraction).  `identity` = index[k] == k
+// for all k (what CvSVM writes for two-class models); otherwise the row is read directly.
+__global__ void __launch_bounds__(32)
+k_svm_decide(const float* __restrict__ kvals, int n_bound, const int* __restrict__ n_dev, SvmDev svm, int identity,
+             float* __restrict__ scores, ag_grasp* __restrict__ grasps_out) {
+  __shared__ float s_tile[32][33];
   const int n = n_dev ? min(*n_dev, n_bound) : n_bound;
-  const int h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= n) return;
-  const float* K = kvals + size_t(h) * svm.sv_total;
+  const int h0 = blockIdx.x * 32, lane = threadIdx.x;
+  if (h0 >= n) return;
+  const int h = h0 + lane;
+  const int nsv = svm.sv_total;
   double sum = -svm.rho;
-  for (int k = 0; k < svm.sv_count; k++) sum += svm.alpha[k] * double(K[svm.index[k]]);
+  if (identity) {
+    for (int k0 = 0; k0 < svm.sv_count; k0 += 32) {
+      __syncwarp();
+      for (int r = 0; r < 32; r++)
+        s_tile[r][lane] = (h0 + r < n && k0 + lane < svm.sv_count) ? kvals[size_t(h0 + r) * nsv + k0 + lane] : 0.f;
+      __syncwarp();
+      const int kn = min(32, svm.sv_count - k0);
+      for (int kk = 0; kk < kn; kk++) sum += svm.alpha[k0 + kk] * double(s_tile[lane][kk]);
+    }
+  } else if (h < n) {
+    const float* K = kvals + size_t(h) * nsv;
+    for (int k = 0; k < svm.sv_count; k++) sum += svm.alpha[k] * double(K[svm.index[k]]);
+  }
+  if (h >= n) return;
   const float sc = float(sum);
   scores[h] = sc;
   if (grasps_out) {
@@ -541,7 +560,10 @@ int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d
     const dim3 gg((n + GM - 1) / GM, (svm->sv_total + GN - 1) / GN);
     k_svm_gemm<<<gg, kGemmThreads, 0, c->stream>>>(desc, svm->d_sv, n, n_dev, svm->sv_total, svm->kernel, svm->gamma,
                                                   svm->coef0, svm->degree, c->kvals.as<float>());
-    k_svm_decide<<<(n + 127) / 128, 128, 0, c->stream>>>(c->kvals.as<float>(), n, n_dev, sd, d_scores, d_grasps_out);
+    bool identity = svm->sv_count <= svm->sv_total;
+    for (int k = 0; k < svm->sv_count && identity; k++) identity = svm->index[k] == k;
+    k_svm_decide<<<(n + 31) / 32, 32, 0, c->stream>>>(c->kvals.as<float>(), n, n_dev, sd, identity ? 1 : 0, d_scores,
+                                                     d_grasps_out);
     c->launches += 3;
   } else {
     k_hog_svm<<<grid, kThreads, 0, c->stream>>>(d_images, d_image_slots, n, n_dev, sd, d_descriptors, d_scores,
