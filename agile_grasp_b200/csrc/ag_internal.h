@@ -58,6 +58,23 @@ struct SvmModel {
 };
 
 
+// what a captured localize graph depends on besides buffer addresses (tracked by g_alloc_gen)
+struct GraphKey {
+  const void* d_points;
+  const void* svm;
+  unsigned long long state_gen;
+  int stride, n_in, size_left, S, given;
+  unsigned flags;
+};
+extern unsigned long long g_alloc_gen;
+struct GraphSlot {
+  GraphKey key;
+  bool valid = false;
+  unsigned long long allocgen = 0, last_use = 0;
+  cudaGraphExec_t exec = nullptr;
+  int launches = 0;
+};
+
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -92,7 +109,12 @@ struct Ctx {
   unsigned gather_epoch = 0;
   bool gather_connected = false;
   // samples
-  DevBuf samples, moments, frames, nn_counts, all_frames;
+  DevBuf samples, sample_stage, moments, frames, nn_counts, all_frames;
+  // CUDA graph of the localize pipeline (second call with the same shapes captures, later calls replay)
+  GraphSlot gslots[4];
+  unsigned long long g_tick = 0, state_gen = 0;
+  int n_graph_replays = 0;
+  bool capturing = false;  // the stream is being captured: timing events must be recorded as external events
   DevBuf nbr_heads;  // per sample of the chunk: sample xyz + neighbour count (float4)
   DevBuf nbr_pool;   // neighbour lists of the current chunk of samples: stride x 16-byte records per sample
   bool two_cams = false;  // the last cloud had points of both cameras (sizes the neighbour pool)
@@ -117,6 +139,13 @@ struct Ctx {
 };
 
 int ctx_pinned(Ctx* c, size_t bytes);
+
+// timing events: inside a stream capture a plain cudaEventRecord only marks a dependency; the external flavour
+// becomes an event-record node that is executed (and can be timed) at every graph launch
+inline void record_event(Ctx* c, cudaEvent_t ev) {
+  if (c->capturing) cudaEventRecordWithFlags(ev, c->stream, cudaEventRecordExternal);
+  else cudaEventRecord(ev, c->stream);
+}
 
 // ---- stage launchers (each returns AG_OK or an error code); all work is enqueued on c->stream
 int preprocess_device(Ctx* c, const void* d_points, int stride, int n_in, int size_left);  // -> c->vox (no sync)

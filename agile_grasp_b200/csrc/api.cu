@@ -16,8 +16,13 @@ namespace ag {
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 
+// bumped whenever any buffer a captured graph may point to is (re)allocated: a cached graph is only replayed
+// while the generation it was captured under is current
+unsigned long long g_alloc_gen = 0;
+
 int DevBuf::reserve(size_t bytes) {
   if (bytes <= cap) return 0;
+  g_alloc_gen++;
   if (p) cudaFree(p);
   p = nullptr;
   cap = 0;
@@ -315,6 +320,7 @@ static float elapsed(cudaEvent_t a, cudaEvent_t b) {
 
 static int ensure_out(Ctx* c, size_t bytes) {
   if (bytes <= c->h_out_cap) return 0;
+  g_alloc_gen++;
   if (c->h_out) cudaFreeHost(c->h_out);
   c->h_out = nullptr;
   c->h_out_cap = 0;
@@ -342,62 +348,141 @@ static int localize_core(Ctx* c, const void* d_points, int stride, int n_in, int
   c->n_hyp = 0;
   c->launches = 0;
   cudaStream_t st = c->stream;
-  cudaEventRecord(c->ev[1], st);
   c->two_cams = size_left < n_in;
-  int rc = preprocess_device(c, d_points, stride, n_in, size_left);
-  if (rc) return rc;
-  cudaEventRecord(c->ev[2], st);
-  cudaEventRecord(c->ev[3], st);
-  RowIndex* ri = c->row_index.as<RowIndex>();
-  // samples (device side)
   const bool given = indices && n_indices > 0;
   const int S = given ? n_indices : std::max(0, c->params.num_samples);
   c->n_samples = S;
+  const size_t slots = size_t(S) * 8;
+  RowIndex* ri = c->row_index.as<RowIndex>();
+  if (given) {  // caller's indices go to a staging buffer first: the (graph-captured) body only copies device to device
+    if (c->sample_stage.reserve(size_t(S) * 4)) return AG_ERR_CUDA;
+    AG_CUDA_CHECK(cudaMemcpyAsync(c->sample_stage.p, indices, size_t(S) * 4, cudaMemcpyHostToDevice, st));
+  }
+  int* d_nsel = nullptr;
+  // Everything from the voxelisation to the scoring: ~25 launches without a host dependency.  The second call
+  // with the same shapes captures it into a CUDA graph, later calls replay the graph (one launch call, no
+  // per-kernel launch gaps); any change of shape, parameters or buffers falls back to the eager path.
+  auto body = [&]() -> int {
+    record_event(c, c->ev[1]);
+    int rc = preprocess_device(c, d_points, stride, n_in, size_left);
+    if (rc) return rc;
+    record_event(c, c->ev[2]);
+    record_event(c, c->ev[3]);
+    ri = c->row_index.as<RowIndex>();
+    if (S == 0) return AG_OK;
+    if (c->samples.reserve(size_t(std::max(S, n_in)) * 4) || c->frames.reserve(size_t(S) * sizeof(ag_frame)) ||
+        c->counters.reserve(64) || ensure_out(c, sizeof(HostOut) + slots * sizeof(ag_grasp)))
+      return AG_ERR_CUDA;
+    AG_CUDA_CHECK(cudaMemsetAsync(c->counters.p, 0, 64, st));
+    if (flags & AG_FLAG_CALC_ANTIPODAL) {
+      // hand_search.cpp:17-26: normals for ALL points with radius 0.01 (launch bound = number of inputs)
+      DevBuf& all_frames = c->all_frames;
+      if (all_frames.reserve(size_t(n_in) * sizeof(ag_frame))) return AG_ERR_CUDA;
+      k_iota<<<(n_in + 255) / 256, 256, 0, st>>>(c->samples.as<int>(), n_in);
+      rc = fit_quadrics_device(c, c->samples.as<int>(), n_in, &ri->n_points, c->params.nn_radius_normals,
+                               all_frames.as<ag_frame>(), true);
+      if (rc) return rc;
+      AG_CUDA_CHECK(cudaMemsetAsync(c->counters.p, 0, 64, st));
+    }
+    record_event(c, c->ev[4]);
+    if (given) {
+      AG_CUDA_CHECK(cudaMemcpyAsync(c->samples.p, c->sample_stage.p, size_t(S) * 4, cudaMemcpyDeviceToDevice, st));
+      k_check_samples<<<(S + 255) / 256, 256, 0, st>>>(ri, S, c->samples.as<int>());
+    } else {
+      k_draw_samples<<<(S + 255) / 256, 256, 0, st>>>(ri, S, c->params.seed, c->samples.as<int>());
+    }
+    c->launches += 1;
+    rc = fit_quadrics_device(c, c->samples.as<int>(), S, &ri->n_samples, c->params.nn_radius_taubin,
+                             c->frames.as<ag_frame>(), true);
+    if (rc) return rc;
+    record_event(c, c->ev[5]);
+    rc = hand_sweep_enqueue(c, c->samples.as<int>(), S, c->frames.as<ag_frame>(),
+                            c->params.filters_boundaries ? 0x100u : 0u);
+    if (rc) return rc;
+    d_nsel = hand_sweep_count_ptr(c, S);
+    record_event(c, c->ev[8]);
+    if (c->attached_svm) {  // fused scoring, hypothesis count read on the device
+      if (c->scores.reserve(slots * 8 + 64)) return AG_ERR_CUDA;
+      rc = hog_svm_device(c, c->attached_svm, c->images_raw.as<uint32_t>(), c->hyp_slots.as<int>(), int(slots), d_nsel,
+                          nullptr, c->scores.as<float>(), nullptr);
+      if (rc) return rc;
+    }
+    record_event(c, c->ev[9]);
+    record_event(c, c->ev[6]);
+    return AG_OK;
+  };
+  GraphKey key;
+  std::memset(&key, 0, sizeof(key));
+  key.d_points = d_points;
+  key.stride = stride;
+  key.n_in = n_in;
+  key.size_left = size_left;
+  key.S = S;
+  key.given = given ? 1 : 0;
+  key.flags = flags;
+  key.state_gen = c->state_gen;
+  key.svm = c->attached_svm;
+  static const bool graphs_off = getenv("AG_NO_GRAPH") != nullptr;
+  const bool can_graph = !graphs_off && S > 0 && !(flags & AG_FLAG_CALC_ANTIPODAL);
+  // small cache of captured pipelines (callers typically alternate between a few input buffers)
+  GraphSlot* slot = nullptr;
+  for (GraphSlot& g : c->gslots)
+    if (g.valid && std::memcmp(&key, &g.key, sizeof(key)) == 0 && g.allocgen == g_alloc_gen) slot = &g;
+  c->g_tick++;
+  int rc = AG_OK;
+  if (can_graph && slot && slot->exec) {  // replay
+    AG_CUDA_CHECK(cudaGraphLaunch(slot->exec, st));
+    c->launches = slot->launches;
+    slot->last_use = c->g_tick;
+    d_nsel = hand_sweep_count_ptr(c, S);
+    c->n_graph_replays++;
+  } else if (can_graph && slot) {  // second call with these shapes: capture, instantiate, launch
+    const int launches0 = c->launches;
+    cudaGraph_t graph = nullptr;
+    AG_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    c->capturing = true;
+    rc = body();
+    c->capturing = false;
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    const bool moved = slot->allocgen != g_alloc_gen;
+    if (rc == AG_OK && ce == cudaSuccess && !moved && cudaGraphInstantiate(&slot->exec, graph, 0) == cudaSuccess) {
+      slot->launches = c->launches;
+      slot->last_use = c->g_tick;
+      AG_CUDA_CHECK(cudaGraphLaunch(slot->exec, st));
+    } else {  // could not capture (a buffer moved, an error): run it eagerly
+      cudaGetLastError();
+      slot->exec = nullptr;
+      slot->valid = false;
+      c->launches = launches0;
+      rc = body();
+    }
+    if (graph) cudaGraphDestroy(graph);
+    if (rc) return rc;
+  } else {  // first call with these shapes (or graphs not applicable): eager, remember the shapes
+    rc = body();
+    if (rc) return rc;
+    if (can_graph) {
+      GraphSlot* victim = &c->gslots[0];
+      for (GraphSlot& g : c->gslots) {
+        if (!g.valid || g.allocgen != g_alloc_gen) {
+          victim = &g;
+          break;
+        }
+        if (g.last_use < victim->last_use) victim = &g;
+      }
+      if (victim->exec) cudaGraphExecDestroy(victim->exec);
+      victim->exec = nullptr;
+      victim->key = key;
+      victim->valid = true;
+      victim->allocgen = g_alloc_gen;
+      victim->last_use = c->g_tick;
+    }
+  }
   if (S == 0) {
     rc = fetch_cloud_size(c);
     c->timings.n_voxels = c->n_vox;
     return rc;
   }
-  const size_t slots = size_t(S) * 8;
-  if (c->samples.reserve(size_t(std::max(S, n_in)) * 4) || c->frames.reserve(size_t(S) * sizeof(ag_frame)) ||
-      c->counters.reserve(64) || ensure_out(c, sizeof(HostOut) + slots * sizeof(ag_grasp)))
-    return AG_ERR_CUDA;
-  AG_CUDA_CHECK(cudaMemsetAsync(c->counters.p, 0, 64, st));
-  if (flags & AG_FLAG_CALC_ANTIPODAL) {
-    // hand_search.cpp:17-26: normals for ALL points with radius 0.01 (launch bound = number of inputs)
-    DevBuf& all_frames = c->all_frames;
-    if (all_frames.reserve(size_t(n_in) * sizeof(ag_frame))) return AG_ERR_CUDA;
-    k_iota<<<(n_in + 255) / 256, 256, 0, st>>>(c->samples.as<int>(), n_in);
-    rc = fit_quadrics_device(c, c->samples.as<int>(), n_in, &ri->n_points, c->params.nn_radius_normals,
-                             all_frames.as<ag_frame>(), true);
-    if (rc) return rc;
-    AG_CUDA_CHECK(cudaMemsetAsync(c->counters.p, 0, 64, st));
-  }
-  cudaEventRecord(c->ev[4], st);
-  if (given) {
-    AG_CUDA_CHECK(cudaMemcpyAsync(c->samples.p, indices, size_t(S) * 4, cudaMemcpyHostToDevice, st));
-    k_check_samples<<<(S + 255) / 256, 256, 0, st>>>(ri, S, c->samples.as<int>());
-  } else {
-    k_draw_samples<<<(S + 255) / 256, 256, 0, st>>>(ri, S, c->params.seed, c->samples.as<int>());
-  }
-  c->launches += 1;
-  rc = fit_quadrics_device(c, c->samples.as<int>(), S, &ri->n_samples, c->params.nn_radius_taubin,
-                           c->frames.as<ag_frame>(), true);
-  if (rc) return rc;
-  cudaEventRecord(c->ev[5], st);
-  rc = hand_sweep_enqueue(c, c->samples.as<int>(), S, c->frames.as<ag_frame>(),
-                          c->params.filters_boundaries ? 0x100u : 0u);
-  if (rc) return rc;
-  int* d_nsel = hand_sweep_count_ptr(c, S);
-  cudaEventRecord(c->ev[8], st);
-  if (c->attached_svm) {  // fused scoring, hypothesis count read on the device
-    if (c->scores.reserve(slots * 8 + 64)) return AG_ERR_CUDA;
-    rc = hog_svm_device(c, c->attached_svm, c->images_raw.as<uint32_t>(), c->hyp_slots.as<int>(), int(slots), d_nsel,
-                        nullptr, c->scores.as<float>(), nullptr);
-    if (rc) return rc;
-  }
-  cudaEventRecord(c->ev[9], st);
-  cudaEventRecord(c->ev[6], st);
   HostOut* hdr = static_cast<HostOut*>(c->d_out_mapped);
   ag_grasp* recs = reinterpret_cast<ag_grasp*>(hdr + 1);
   int* exp_hdr = static_cast<int*>(c->d_export);
@@ -561,10 +646,12 @@ void ag_destroy(ag_ctx* h) {
   cudaSetDevice(c.device);
   cudaStreamSynchronize(c.stream);
   ag_gather_destroy(h);
+  for (GraphSlot& g : c.gslots)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   if (c.h_out) cudaFreeHost(c.h_out);
   for (DevBuf* b : {&c.raw, &c.keys, &c.keys_sorted, &c.keys_unique, &c.cub_tmp, &c.block_counts, &c.misc, &c.vox,
                     &c.row_ptr, &c.col_ptr, &c.row_index, &c.all_frames,
-                    &c.normals, &c.samples, &c.moments, &c.frames, &c.nn_counts, &c.nbr_pool, &c.nbr_heads, &c.grasps_raw, &c.valid,
+                    &c.normals, &c.samples, &c.sample_stage, &c.moments, &c.frames, &c.nn_counts, &c.nbr_pool, &c.nbr_heads, &c.grasps_raw, &c.valid,
                     &c.images_raw, &c.hyp_slots, &c.grasps, &c.counters, &c.scores, &c.descriptors, &c.kvals, &c.handle_in, &c.handle_bits, &c.sweep_dbg, &c.overflow})
     b->release();
   if (c.h_pinned) cudaFreeHost(c.h_pinned);
@@ -582,6 +669,7 @@ int ag_set_params(ag_ctx* h, const ag_params* p) {
   }
   h->c.params = *p;
   compute_hand_const(h->c.params, h->c.hand);
+  h->c.state_gen++;
   return AG_OK;
 }
 int ag_get_params(ag_ctx* h, ag_params* p) {
@@ -725,6 +813,7 @@ int ag_set_export_buffer(ag_ctx* h, void* d_buffer, size_t bytes) {
   }
   h->c.d_export = d_buffer;
   h->c.d_export_cap = d_buffer ? bytes : 0;
+  h->c.state_gen++;
   return AG_OK;
 }
 
@@ -779,6 +868,7 @@ int ag_gather_connect(ag_ctx* h, const unsigned char* handles) {
     AG_CUDA_CHECK(cudaIpcOpenMemHandle(&c.gather_peer[r], hd, cudaIpcMemLazyEnablePeerAccess));
   }
   c.gather_connected = true;
+  c.state_gen++;
   return AG_OK;
 }
 
@@ -825,6 +915,7 @@ int ag_gather_destroy(ag_ctx* h) {
   c.gather_buf = c.gather_done = c.gather_host_hdr = c.gather_host_hdr_dev = nullptr;
   c.gather_world = 0;
   c.gather_connected = false;
+  c.state_gen++;
   return AG_OK;
 }
 
@@ -832,6 +923,7 @@ int ag_set_svm(ag_ctx* h, const ag_svm* svm) {
   if (!h) return AG_ERR_INVALID;
   h->c.attached_svm = svm ? svm->m : nullptr;
   h->c.scores_valid = false;
+  h->c.state_gen++;
   return AG_OK;
 }
 

@@ -950,20 +950,20 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
     const int m = std::min(chunk, n - s0);
     const int blocks = (m + kWarps - 1) / kWarps;
     const bool timed = s0 == 0;  // ag_timings reports the kernels of the first chunk
-    if (timed) cudaEventRecord(c->ev_k[0], c->stream);
+    if (timed) record_event(c, c->ev_k[0]);
     k_ball_search<<<blocks, kWarps * 32, 0, c->stream>>>(c->vox.as<GPoint>(), c->row_ptr.as<int>(),
                                                          c->col_ptr.as<int>(), ri, d_indices, s0, s0 + m, d_count, r2,
                                                          rpad, c->nbr_pool.as<GPoint>(), stride,
                                                          c->nn_counts.as<int2>(), c->nbr_heads.as<float4>());
-    if (timed) cudaEventRecord(c->ev_k[1], c->stream);
+    if (timed) record_event(c, c->ev_k[1]);
     k_taubin_moments<<<std::min(blocks, kNumSMs * 4), kWarps * 32, 0, c->stream>>>(
         s0, m, c->nbr_heads.as<float4>(), c->nbr_pool.as<GPoint>(), stride, inv_r, c->moments.as<double>());
-    if (timed) cudaEventRecord(c->ev_k[2], c->stream);
+    if (timed) record_event(c, c->ev_k[2]);
     k_taubin_axes<<<blocks, kWarps * 32, smem, c->stream>>>(
         c->vox.as<GPoint>(), ri, d_indices, s0, s0 + m, d_count, c->nbr_pool.as<GPoint>(), stride,
         c->nn_counts.as<int2>(), inv_r, c->moments.as<double>(), h.cam[0][0], h.cam[0][1], h.cam[0][2], h.cam[1][0],
         h.cam[1][1], h.cam[1][2], d_frames, write_normals ? c->normals.as<double>() : nullptr);
-    if (timed) cudaEventRecord(c->ev_k[3], c->stream);
+    if (timed) record_event(c, c->ev_k[3]);
     c->launches += 3;
   }
   k_quadric_finish<<<(n + 255) / 256, 256, 0, c->stream>>>(c->vox.as<GPoint>(), ri, d_indices, n, d_count,
