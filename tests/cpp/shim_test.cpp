@@ -2,6 +2,7 @@
 // reference's would be used, the Grasps message helpers follow grasp_localizer.cpp:123-188, the ROS 1 wire
 // format round-trips, and the file overloads report unreadable files the way localization.cpp:184-189 does.
 #include <agile_grasp/Grasp.h>
+#include <agile_grasp/cloud_msgs.h>
 #include <agile_grasp/localization.h>
 
 #include <cstdio>
@@ -61,6 +62,43 @@ int main(int argc, char** argv) {
     CHECK(ag_load_pcd(argv[1], &pts, &n, &w, &hh) == AG_OK);
     CHECK(n == std::atoi(argv[2]) && w * hh == n);
     ag_free(pts);
+  }
+  {  // CloudSized / PointCloud2 wire format -> PointXYZRGBA cloud (grasp_localizer.cpp:40-77), written here byte by byte
+    std::vector<uint8_t> w;
+    auto put = [&w](const void* p, size_t n) { const uint8_t* b = static_cast<const uint8_t*>(p); w.insert(w.end(), b, b + n); };
+    auto put32 = [&](uint32_t v) { put(&v, 4); };
+    auto puts = [&](const std::string& s) { put32(uint32_t(s.size())); put(s.data(), s.size()); };
+    put32(3); put32(100); put32(5); puts("camera_rgb_optical_frame");   // header
+    const uint32_t H = 2, W = 3, step = 32;
+    put32(H); put32(W);
+    put32(4);                                                            // fields
+    const char* names[4] = {"x", "y", "z", "rgb"};
+    const uint32_t offs[4] = {0, 4, 8, 16};
+    for (int k = 0; k < 4; k++) { puts(names[k]); put32(offs[k]); uint8_t dt = 7; put(&dt, 1); put32(1); }
+    uint8_t z8 = 0; put(&z8, 1);                                         // is_bigendian
+    put32(step); put32(step * W);
+    put32(step * W * H);                                                 // data length
+    for (uint32_t i = 0; i < H * W; i++) {
+      float rec[8] = {float(i), float(i) + 0.5f, 1.0f + i, 0, 0, 0, 0, 0};
+      uint32_t rgb = 0x00102030u + i;
+      std::memcpy(&rec[4], &rgb, 4);
+      put(rec, 32);
+    }
+    uint8_t dense = 1; put(&dense, 1);
+    int64_t size_left = 4; put(&size_left, 8);
+    agile_grasp::CloudSized cs;
+    CHECK(agile_grasp::deserialize(w, cs));
+    CHECK(cs.size_left == 4 && cs.cloud.frame_id == "camera_rgb_optical_frame" && cs.cloud.fields.size() == 4);
+    PointCloud cloud;
+    CHECK(agile_grasp::fromROSMsg(cs.cloud, cloud));
+    CHECK(cloud.size() == 6 && cloud.points[5].x == 5.0f && cloud.points[5].y == 5.5f && cloud.points[2].z == 3.0f);
+    CHECK(cloud.points[4].rgba == 0x00102034u && cloud.width == 3 && cloud.height == 2);
+    w.resize(w.size() - 9);  // a bare PointCloud2 ends after is_dense... and a truncated one is rejected
+    agile_grasp::PointCloud2 pc2;
+    w.push_back(1);
+    CHECK(agile_grasp::deserialize(w, pc2) && pc2.width == 3);
+    w.pop_back();
+    CHECK(!agile_grasp::deserialize(w, pc2));
   }
   std::printf("shim ok\n");
   return 0;
