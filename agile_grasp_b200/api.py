@@ -21,7 +21,7 @@ EXPORTS = [
     "ag_get_timings", "ag_free", "ag_svm_load", "ag_svm_free", "ag_svm_info", "ag_localize", "ag_localize_device",
     "ag_classify", "ag_set_svm", "ag_set_export_buffer", "ag_get_points", "ag_get_images", "ag_preprocess", "ag_set_cloud", "ag_radius_search",
     "ag_fit_quadrics", "ag_hand_sweep", "ag_sweep_debug", "ag_hog_svm",
-    "ag_find_handles", "ag_load_pcd", "ag_gather_slot_bytes", "ag_gather_create", "ag_gather_connect", "ag_gather_wait", "ag_gather_destroy",
+    "ag_find_handles", "ag_load_pcd", "ag_localize_batch", "ag_gather_slot_bytes", "ag_gather_create", "ag_gather_connect", "ag_gather_wait", "ag_gather_destroy",
 ]
 
 
@@ -64,6 +64,8 @@ def lib():
     L.ag_hog_svm.argtypes = [vp, vp, C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.ag_find_handles.argtypes = [vp, C.POINTER(AgGrasp), C.c_int, C.c_int, C.c_double, C.POINTER(C.c_void_p), ip,
                                   C.POINTER(C.POINTER(C.c_int32)), ip]
+    L.ag_localize_batch.argtypes = [vp, C.c_int, C.POINTER(C.c_void_p), ip, ip, ip, C.c_uint,
+                                    C.POINTER(C.POINTER(AgGrasp)), ip]
     L.ag_load_pcd.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), ip, ip, ip]
     L.ag_gather_slot_bytes.restype = C.c_size_t
     L.ag_gather_slot_bytes.argtypes = [C.c_int]
@@ -168,6 +170,19 @@ class Context:
                                  None if idx is None else idx.ctypes.data_as(C.POINTER(C.c_int)),
                                  0 if idx is None else idx.shape[0], int(flags), C.byref(out), C.byref(n)))
         return _grasps_from(out, n.value)
+
+    def localize_batch(self, clouds, size_lefts, flags=0):
+        """ag_localize_batch: list of (n, 8) float32 clouds -> list of grasp arrays (samples drawn from params.seed)"""
+        k = len(clouds)
+        arrs = [np.ascontiguousarray(p) for p in clouds]
+        ptrs = (C.c_void_p * k)(*[a.ctypes.data for a in arrs])
+        strides = (C.c_int * k)(*[a.strides[0] for a in arrs])
+        n_in = (C.c_int * k)(*[a.shape[0] for a in arrs])
+        sl = (C.c_int * k)(*[int(v) for v in size_lefts])
+        outs = (C.POINTER(AgGrasp) * k)()
+        n_out = (C.c_int * k)()
+        _check(lib().ag_localize_batch(self.h, k, ptrs, strides, n_in, sl, int(flags), outs, n_out))
+        return [_grasps_from(outs[i], n_out[i]) for i in range(k)]
 
     def localize_device(self, dev_ptr, stride, n_in, size_left, indices=None, flags=0):
         idx = None if indices is None else np.ascontiguousarray(indices, dtype=np.int32)

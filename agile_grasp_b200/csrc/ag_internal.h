@@ -111,6 +111,12 @@ struct Ctx {
   // samples
   DevBuf samples, sample_stage, moments, frames, nn_counts, all_frames;
   // CUDA graph of the localize pipeline (second call with the same shapes captures, later calls replay)
+  // state between localize_begin and localize_end
+  bool pend_active = false;
+  int pend_S = 0;
+  int* pend_nsel = nullptr;
+  alignas(8) unsigned char pend_peer[128];
+  unsigned long long batch_parent_gen = ~0ull;  // child lane of ag_localize_batch: parent state it mirrors
   GraphSlot gslots[4];
   unsigned long long g_tick = 0, state_gen = 0;
   int n_graph_replays = 0;
@@ -175,6 +181,7 @@ int svm_to_device(SvmModel* svm, int device);
 // the opaque handle of the C ABI
 struct ag_ctx {
   ag::Ctx c;
+  std::vector<ag_ctx*> children;  // extra lanes of ag_localize_batch (same device, own stream and buffers)
 };
 namespace ag {
 inline Ctx& ctx_of(ag_ctx* h) { return h->c; }

@@ -337,10 +337,22 @@ static int ensure_out(Ctx* c, size_t bytes) {
 // The full device-side path, cloud already in device memory.  Everything is enqueued without a single
 // host round trip: the voxel count, the sample list, the hypothesis count and the grasp records stay
 // on the device until the export kernel writes them into mapped host memory; the host waits once.
-static int localize_core(Ctx* c, const void* d_points, int stride, int n_in, int size_left, const int* indices,
-                         int n_indices, unsigned flags, ag_grasp** out, int* n_out) {
-  *out = nullptr;
-  *n_out = 0;
+static void launch_export(Ctx* c, const PeerOut& peer) {
+  HostOut* hdr = static_cast<HostOut*>(c->d_out_mapped);
+  ag_grasp* recs = reinterpret_cast<ag_grasp*>(hdr + 1);
+  int* exp_hdr = static_cast<int*>(c->d_export);
+  ag_grasp* exp_recs = c->d_export ? reinterpret_cast<ag_grasp*>(static_cast<char*>(c->d_export) + 16) : nullptr;
+  const int cap_exp = c->d_export ? int((c->d_export_cap - 16) / sizeof(ag_grasp)) : 0;
+  k_export<<<32, 256, 0, c->stream>>>(c->grasps_raw.as<ag_grasp>(), c->hyp_slots.as<int>(), c->pend_nsel,
+                                      c->attached_svm ? c->scores.as<float>() : nullptr, c->row_index.as<RowIndex>(),
+                                      hand_sweep_overflow_ptr(c), c->counters.as<unsigned long long>(), hdr, recs,
+                                      c->grasps.as<ag_grasp>(), exp_hdr, exp_recs, int(size_t(c->pend_S) * 8), cap_exp, peer);
+}
+
+// First half of a localize call: everything is enqueued on the context's stream, nothing is waited for.
+static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, int size_left, const int* indices,
+                          int n_indices, unsigned flags) {
+  c->pend_active = false;
   std::memset(&c->timings, 0, sizeof(c->timings));
   c->timings.n_in = n_in;
   c->images_valid = false;
@@ -478,16 +490,7 @@ static int localize_core(Ctx* c, const void* d_points, int stride, int n_in, int
       victim->last_use = c->g_tick;
     }
   }
-  if (S == 0) {
-    rc = fetch_cloud_size(c);
-    c->timings.n_voxels = c->n_vox;
-    return rc;
-  }
-  HostOut* hdr = static_cast<HostOut*>(c->d_out_mapped);
-  ag_grasp* recs = reinterpret_cast<ag_grasp*>(hdr + 1);
-  int* exp_hdr = static_cast<int*>(c->d_export);
-  ag_grasp* exp_recs = c->d_export ? reinterpret_cast<ag_grasp*>(static_cast<char*>(c->d_export) + 16) : nullptr;
-  const int cap_exp = c->d_export ? int((c->d_export_cap - 16) / sizeof(ag_grasp)) : 0;
+  if (S == 0) return AG_OK;  // (localize_end reads the cloud size back)
   PeerOut peer;
   std::memset(&peer, 0, sizeof(peer));
   if (c->gather_world > 0 && c->gather_connected) {
@@ -501,15 +504,32 @@ static int localize_core(Ctx* c, const void* d_points, int stride, int n_in, int
     peer.epoch = c->gather_epoch;
     peer.done = static_cast<unsigned*>(c->gather_done);
   }
-  auto do_export = [&]() {
-    k_export<<<32, 256, 0, st>>>(c->grasps_raw.as<ag_grasp>(), c->hyp_slots.as<int>(), d_nsel,
-                                      c->attached_svm ? c->scores.as<float>() : nullptr, ri, hand_sweep_overflow_ptr(c),
-                                      c->counters.as<unsigned long long>(), hdr, recs, c->grasps.as<ag_grasp>(),
-                                      exp_hdr, exp_recs, int(slots), cap_exp, peer);
-  };
-  do_export();
+  c->pend_S = S;
+  c->pend_nsel = d_nsel;
+  static_assert(sizeof(PeerOut) <= sizeof(c->pend_peer), "pending export arguments");
+  std::memcpy(c->pend_peer, &peer, sizeof(peer));
+  launch_export(c, peer);
   c->launches += 1;
   cudaEventRecord(c->ev[7], st);
+  c->pend_active = true;
+  return AG_OK;
+}
+
+// Second half: the one wait of the call, error flags, the rare large-slab re-run, the host copy of the list.
+static int localize_end(Ctx* c, ag_grasp** out, int* n_out) {
+  *out = nullptr;
+  *n_out = 0;
+  cudaStream_t st = c->stream;
+  if (!c->pend_active) {  // no samples requested: only the voxelised cloud exists
+    int rc = fetch_cloud_size(c);
+    c->timings.n_voxels = c->n_vox;
+    return rc;
+  }
+  c->pend_active = false;
+  const int S = c->pend_S;
+  PeerOut peer;
+  std::memcpy(&peer, c->pend_peer, sizeof(peer));
+  int rc = AG_OK;
   AG_CUDA_CHECK(cudaStreamSynchronize(st));
   AG_CUDA_CHECK(cudaGetLastError());
   HostOut* h = static_cast<HostOut*>(c->h_out);
@@ -541,7 +561,7 @@ static int localize_core(Ctx* c, const void* d_points, int stride, int n_in, int
       if (rc) return rc;
     }
     peer.final_pass = 1;
-    do_export();
+    launch_export(c, peer);
     AG_CUDA_CHECK(cudaStreamSynchronize(st));
     Hn = h->n_hyp;
     c->n_hyp = Hn;
@@ -646,6 +666,8 @@ void ag_destroy(ag_ctx* h) {
   cudaSetDevice(c.device);
   cudaStreamSynchronize(c.stream);
   ag_gather_destroy(h);
+  for (ag_ctx* ch : h->children) ag_destroy(ch);
+  h->children.clear();
   for (GraphSlot& g : c.gslots)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (c.h_out) cudaFreeHost(c.h_out);
@@ -726,7 +748,8 @@ int ag_localize(ag_ctx* h, const void* points, int stride, int n_in, int size_le
   if (c.raw.reserve(bytes)) return AG_ERR_CUDA;
   cudaEventRecord(c.ev[0], c.stream);
   AG_CUDA_CHECK(cudaMemcpyAsync(c.raw.p, points, bytes, cudaMemcpyHostToDevice, c.stream));
-  int rc = localize_core(&c, c.raw.p, stride, n_in, size_left, indices, n_indices, flags, out, n_out);
+  int rc = localize_begin(&c, c.raw.p, stride, n_in, size_left, indices, n_indices, flags);
+  if (rc == AG_OK) rc = localize_end(&c, out, n_out);
   c.timings.h2d_ms = elapsed(c.ev[0], c.ev[1]);
   return rc;
 }
@@ -741,7 +764,9 @@ int ag_localize_device(ag_ctx* h, const void* d_points, int stride, int n_in, in
   Ctx& c = h->c;
   cudaSetDevice(c.device);
   cudaEventRecord(c.ev[0], c.stream);
-  return localize_core(&c, d_points, stride, n_in, size_left, indices, n_indices, flags, out, n_out);
+  int rc = localize_begin(&c, d_points, stride, n_in, size_left, indices, n_indices, flags);
+  if (rc == AG_OK) rc = localize_end(&c, out, n_out);
+  return rc;
 }
 
 int ag_classify(ag_ctx* h, const ag_svm* svm, ag_grasp* grasps, int n, uint8_t* keep) {
@@ -803,6 +828,79 @@ int ag_classify(ag_ctx* h, const ag_svm* svm, ag_grasp* grasps, int n, uint8_t* 
     if (keep) keep[i] = grasps[i].label;
   }
   return AG_OK;
+}
+
+// ---- batches of clouds (BASELINE config 4): up to kBatchLanes clouds in flight on one GPU -------------------
+// Every stage of one cloud is a few hundred warps of latency-bound work, so one cloud leaves most of the GPU
+// idle; clouds are independent, so a batch is spread over lanes — the context itself plus lazily created
+// children with the same parameters and SVM, each with its own stream, buffers and cached CUDA graph — and the
+// lanes' pipelines overlap on the device.  Results are identical to calling ag_localize cloud by cloud.
+int ag_localize_batch(ag_ctx* h, int n_clouds, const void* const* points, const int* strides, const int* n_in,
+                      const int* size_left, unsigned flags, ag_grasp** out, int* n_out) {
+  if (!h || n_clouds < 0 || (n_clouds > 0 && (!points || !strides || !n_in || !size_left || !out || !n_out))) return AG_ERR_INVALID;
+  Ctx& c0 = h->c;
+  cudaSetDevice(c0.device);
+  for (int i = 0; i < n_clouds; i++) {
+    out[i] = nullptr;
+    n_out[i] = 0;
+  }
+  static const int max_lanes = [] {  // AG_BATCH_LANES overrides the default (tuning), 1..16
+    const char* e = getenv("AG_BATCH_LANES");
+    const int v = e ? atoi(e) : AG_BATCH_LANES;
+    return std::min(16, std::max(1, v));
+  }();
+  const int lanes = std::min(n_clouds, max_lanes);
+  while (int(h->children.size()) < lanes - 1) {
+    ag_ctx* ch = ag_create(c0.device);
+    if (!ch) return AG_ERR_CUDA;
+    h->children.push_back(ch);
+  }
+  std::vector<Ctx*> lane(lanes);
+  for (int l = 0; l < lanes; l++) {
+    lane[l] = l == 0 ? &c0 : &h->children[l - 1]->c;
+    if (l > 0 && (lane[l]->batch_parent_gen != c0.state_gen)) {  // mirror parameters / SVM of the parent
+      int rc = ag_set_params(h->children[l - 1], &c0.params);
+      if (rc) return rc;
+      lane[l]->attached_svm = c0.attached_svm;
+      lane[l]->state_gen++;
+      lane[l]->batch_parent_gen = c0.state_gen;
+    }
+  }
+  // rolling pipeline: cloud i goes to lane i % lanes; before a lane is reused its previous cloud is collected,
+  // so every lane always has a cloud in flight while the host collects / enqueues on the others
+  int first_err = AG_OK;
+  std::vector<int> pending(lanes, -1), rcs(n_clouds, AG_OK);
+  auto collect = [&](int l) {
+    const int i = pending[l];
+    if (i < 0) return;
+    pending[l] = -1;
+    if (rcs[i] == AG_OK) rcs[i] = localize_end(lane[l], &out[i], &n_out[i]);
+    if (rcs[i] == AG_ERR_EMPTY) rcs[i] = AG_OK;  // an empty cloud yields an empty list (localization.cpp:9-15)
+    if (rcs[i] != AG_OK && first_err == AG_OK) first_err = rcs[i];
+  };
+  for (int i = 0; i < n_clouds; i++) {
+    const int l = i % lanes;
+    collect(l);
+    Ctx& c = *lane[l];
+    pending[l] = i;
+    if (n_in[i] <= 0 || size_left[i] == 0 || !points[i] || strides[i] < 12) {
+      rcs[i] = AG_ERR_EMPTY;
+      continue;
+    }
+    const size_t bytes = size_t(n_in[i]) * strides[i];
+    if (c.raw.reserve(bytes)) {
+      rcs[i] = AG_ERR_CUDA;
+      continue;
+    }
+    cudaEventRecord(c.ev[0], c.stream);
+    if (cudaMemcpyAsync(c.raw.p, points[i], bytes, cudaMemcpyHostToDevice, c.stream) != cudaSuccess) {
+      rcs[i] = AG_ERR_CUDA;
+      continue;
+    }
+    rcs[i] = localize_begin(&c, c.raw.p, strides[i], n_in[i], size_left[i], nullptr, 0, flags);
+  }
+  for (int l = 0; l < lanes; l++) collect(l);
+  return first_err;
 }
 
 int ag_set_export_buffer(ag_ctx* h, void* d_buffer, size_t bytes) {

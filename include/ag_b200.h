@@ -170,6 +170,14 @@ int ag_localize_device(ag_ctx* ctx, const void* d_points, int stride, int n_in, 
  * hypotheses the reference would return from predictAntipodalHands. */
 int ag_classify(ag_ctx* ctx, const ag_svm* svm, ag_grasp* grasps, int n, uint8_t* keep);
 
+/* A batch of clouds on one GPU (BASELINE config 4; the reference has no batch call — its node handles one
+ * cloud per second, grasp_localizer.cpp:82).  Up to AG_BATCH_LANES clouds are in flight at a time on separate
+ * streams (the context plus internal child contexts mirroring its parameters and attached SVM); out[i] / n_out[i]
+ * are exactly what ag_localize(points[i], ...) with sampled indices returns.  Returns the first error. */
+#define AG_BATCH_LANES 4
+int ag_localize_batch(ag_ctx* ctx, int n_clouds, const void* const* points, const int* strides, const int* n_in,
+                      const int* size_left, unsigned flags, ag_grasp** out, int* n_out);
+
 /* Attach an SVM to the context (NULL detaches): every following ag_localize also scores its hypotheses
  * in the same stream (score/label of the returned records are filled) and a following ag_classify with
  * the same model just returns those results.  The model must outlive the attachment. */

@@ -498,3 +498,27 @@ def test_find_handles_on_pipeline_output(ctx, oracle, small_scene, linear_svm_pa
         assert np.allclose(H[k]["axis"], Ho[k]["axis"], atol=1e-12)
     H0, inl0 = ctx.find_handles(pos[:0], 3, 0.005)
     assert len(H0) == 0
+
+
+def test_localize_batch_equals_sequential(ctx, linear_svm_path):
+    """ag_localize_batch (BASELINE config 4: clouds in flight on several streams / child contexts) returns,
+    cloud by cloud, exactly the bytes of sequential ag_localize calls; 5 clouds = two waves over the 4 lanes."""
+    svm = api.Svm(linear_svm_path)
+    clouds, sls = [], []
+    for k in range(5):
+        pts, size_left, P, S = scenes.config_cloud(2, small=(200 + 8 * k, 150, 80), scene_offset=k)
+        clouds.append(pts)
+        sls.append(size_left)
+    ctx.set_params(P)
+    ctx.set_svm(svm)
+    try:
+        seq = [ctx.localize(p, s) for p, s in zip(clouds, sls)]
+        for rep in range(3):  # eager, graph capture, graph replay on every lane
+            bat = ctx.localize_batch(clouds, sls)
+            assert len(bat) == 5
+            for a, b in zip(seq, bat):
+                assert len(a) > 0 and a.tobytes() == b.tobytes()
+        empty = ctx.localize_batch([], [])
+        assert empty == []
+    finally:
+        ctx.set_svm(None)
