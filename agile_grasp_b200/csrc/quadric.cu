@@ -230,26 +230,40 @@ k_ball_search(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr, c
 constexpr int kSeg = 272;  // records per segment (4352 B >= the 16 x 33 doubles of a reduction round)
 static_assert(kSeg * sizeof(GPoint) >= 16 * 33 * sizeof(double), "the reduction reuses a segment buffer");
 
+// WPS = warps per sample: 1 when the launch fills the machine; 2 / 4 for small launches, where a sample's
+// list is shared by a team of warps (the team leader issues the copies, warp `sub` takes every WPS-th batch of
+// 32 records, the partial sums meet in shared memory in a fixed order) so that a 2000-sample launch is not
+// bounded by the latency of one warp walking a whole list.
+template <int WPS>
 __global__ void __launch_bounds__(kWarps * 32, 4)
 k_taubin_moments(int s0, int m, const float4* __restrict__ heads, const GPoint* __restrict__ pool, int stride,
                  double scale, double* __restrict__ moments) {
   __shared__ __align__(16) GPoint s_seg[kWarps][2][kSeg];
   __shared__ __align__(8) unsigned long long s_bar[kWarps][2];
+  __shared__ double s_part[WPS > 1 ? kWarps : 1][kMomentStride];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int G = gridDim.x * kWarps;
-  int sl = blockIdx.x * kWarps + warp;
-  if (sl >= m) return;
-  const uint32_t buf0 = pin_u32(smem_u32(s_seg[warp][0])), bar0 = pin_u32(smem_u32(&s_bar[warp][0]));
+  constexpr int kTeams = kWarps / WPS;           // teams per CTA
+  const int team = warp / WPS, sub = warp % WPS;  // sub == 0: the team leader
+  const int lead = team * WPS;                    // leader's warp index: its buffers stage the team's lists
+  const int G = gridDim.x * kTeams;
+  int sl = blockIdx.x * kTeams + team;
+  if (sl >= m) return;  // (the whole team leaves together)
+  auto team_sync = [&]() {
+    if (WPS == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(WPS * 32) : "memory");
+  };
+  const uint32_t buf0 = pin_u32(smem_u32(s_seg[lead][0])), bar0 = pin_u32(smem_u32(&s_bar[lead][0]));
+  const uint32_t own0 = pin_u32(smem_u32(s_seg[warp][0]));  // non-leaders: private reduction scratch
   constexpr uint32_t kBufBytes = kSeg * sizeof(GPoint);
   const uint32_t seg_bytes = uint32_t(min(kSeg, stride)) * 16u;  // speculative first segment of a list
-  if (lane == 0) {
+  if (sub == 0 && lane == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8u, 1);
     fence_proxy_async_smem();
     mbar_expect_tx(bar0, seg_bytes);
     bulk_g2s(buf0, pool + size_t(sl) * size_t(stride), seg_bytes, bar0);
   }
-  __syncwarp();
+  team_sync();  // the barriers are initialised before anyone waits on them
   float4 head = heads[sl];
   const double s2 = scale * scale, s4 = s2 * s2;
   const int mj = lane + 1;  // the moment this lane writes
@@ -275,8 +289,8 @@ k_taubin_moments(int s0, int m, const float4* __restrict__ heads, const GPoint* 
     for (int k = 0; k < nseg; k++, g++) {
       const uint32_t cur = buf0 + uint32_t(g & 1) * kBufBytes, cur_bar = bar0 + uint32_t(g & 1) * 8u;
       const uint32_t oth = buf0 + uint32_t((g + 1) & 1) * kBufBytes, oth_bar = bar0 + uint32_t((g + 1) & 1) * 8u;
-      __syncwarp();  // every lane is done with the other buffer (segment g - 1 or the reduction scratch)
-      if (lane == 0) {
+      team_sync();  // everyone is done with the other buffer (segment g - 1 or the leader's reduction scratch)
+      if (sub == 0 && lane == 0) {
         fence_proxy_async_smem();
         if (k + 1 < nseg) {
           const uint32_t bytes = uint32_t(min(kSeg, n - (k + 1) * kSeg)) * 16u;
@@ -290,7 +304,7 @@ k_taubin_moments(int s0, int m, const float4* __restrict__ heads, const GPoint* 
       mbar_wait(cur_bar, uint32_t(g >> 1) & 1u);
       const int cnt = min(kSeg, n - k * kSeg);
       const uint32_t lane_s = cur + uint32_t(lane) * 16u;
-      for (int b = 0; b < cnt; b += 32) {
+      for (int b = sub * 32; b < cnt; b += WPS * 32) {
         GPoint p = self;
         if (b + lane < cnt) p = lds_point(lane_s + uint32_t(b) * 16u);
         const double x = double(p.x) - qx, y = double(p.y) - qy, z = double(p.z) - qz;
@@ -305,9 +319,11 @@ k_taubin_moments(int s0, int m, const float4* __restrict__ heads, const GPoint* 
         cam1 += int(p.tag & kTagCamBit);
       }
     }
-    // warp reduction through the buffer consumed last: two rounds of 16 moments with a 33-double row
-    // pitch; lane i sums half (i >> 4) of row (i & 15), the halves meet by one exchange
-    const uint32_t scr = buf0 + uint32_t((g - 1) & 1) * kBufBytes;
+    // warp reduction through shared memory: two rounds of 16 moments with a 33-double row pitch; lane i sums
+    // half (i >> 4) of row (i & 15), the halves meet by one exchange.  Scratch = the buffer consumed last
+    // (leader, once the team is done reading it) or the warp's own, otherwise unused, buffer.
+    if (WPS > 1) team_sync();
+    const uint32_t scr = sub == 0 ? buf0 + uint32_t((g - 1) & 1) * kBufBytes : own0;
     const uint32_t row_s = scr + uint32_t(lane & 15) * (33u * 8u) + uint32_t(lane >> 4) * (16u * 8u);
     double r01[2];
 #pragma unroll
@@ -325,11 +341,33 @@ k_taubin_moments(int s0, int m, const float4* __restrict__ heads, const GPoint* 
       const double t = t0 + t1;
       r01[r] = t + __shfl_xor_sync(0xffffffffu, t, 16);
     }
-    const double m33 = warp_sum(acc[33]), m34 = warp_sum(acc[34]);
+    double mom = lane < 16 ? r01[0] : r01[1];  // moment lane + 1 (this warp's share)
+    double m33 = warp_sum(acc[33]), m34 = warp_sum(acc[34]);
     cam1 = __reduce_add_sync(0xffffffffu, cam1);
-    if (n > 0) {
+    if (WPS > 1) {  // the team's shares meet in shared memory, summed by the leader in warp order
+      s_part[warp][mj] = mom;
+      if (lane == 0) {
+        s_part[warp][33] = m33;
+        s_part[warp][34] = m34;
+        s_part[warp][35] = double(cam1);
+      }
+      team_sync();
+      if (sub == 0) {
+        mom = 0.0;
+        double e = 0.0;
+#pragma unroll
+        for (int w = 0; w < WPS; w++) {
+          mom += s_part[lead + w][mj];
+          if (lane < 3) e += s_part[lead + w][33 + lane];
+        }
+        m33 = __shfl_sync(0xffffffffu, e, 0);
+        m34 = __shfl_sync(0xffffffffu, e, 1);
+        cam1 = int(__shfl_sync(0xffffffffu, e, 2));
+      }
+    }
+    if (n > 0 && sub == 0) {
       double* out = moments + size_t(s0 + sl) * kMomentStride;
-      out[mj] = (lane < 16 ? r01[0] : r01[1]) * scl;  // moments 1..32
+      out[mj] = mom * scl;  // moments 1..32
       if (lane == 0) {
         out[0] = double(n);
         out[33] = m33 * s4;
@@ -956,8 +994,24 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
                                                          rpad, c->nbr_pool.as<GPoint>(), stride,
                                                          c->nn_counts.as<int2>(), c->nbr_heads.as<float4>());
     if (timed) record_event(c, c->ev_k[1]);
-    k_taubin_moments<<<std::min(blocks, kNumSMs * 4), kWarps * 32, 0, c->stream>>>(
-        s0, m, c->nbr_heads.as<float4>(), c->nbr_pool.as<GPoint>(), stride, inv_r, c->moments.as<double>());
+    {
+      // warps per sample.  Measured on B200: a 2000-sample launch takes 10.2 / 11.3 / 14.3 us with 1 / 2 / 4 warps
+      // per sample — it is bounded by fixed costs (launch, first-touch latencies, reduction), not by one warp
+      // walking a whole list — so teams are only used when asked for (AG_MOM_WPS = 2 | 4, a tuning knob).
+      static const int forced = [] {
+        const char* e = getenv("AG_MOM_WPS");
+        return e ? atoi(e) : 0;
+      }();
+      const int wps = (forced == 2 || forced == 4) ? forced : 1;
+      const float4* hd = c->nbr_heads.as<float4>();
+      const GPoint* pl = c->nbr_pool.as<GPoint>();
+      double* mo = c->moments.as<double>();
+      const int teams_per_cta = kWarps / wps;
+      const int grid = std::min((m + teams_per_cta - 1) / teams_per_cta, kNumSMs * 4);
+      if (wps == 4) k_taubin_moments<4><<<grid, kWarps * 32, 0, c->stream>>>(s0, m, hd, pl, stride, inv_r, mo);
+      else if (wps == 2) k_taubin_moments<2><<<grid, kWarps * 32, 0, c->stream>>>(s0, m, hd, pl, stride, inv_r, mo);
+      else k_taubin_moments<1><<<grid, kWarps * 32, 0, c->stream>>>(s0, m, hd, pl, stride, inv_r, mo);
+    }
     if (timed) record_event(c, c->ev_k[2]);
     k_taubin_axes<<<blocks, kWarps * 32, smem, c->stream>>>(
         c->vox.as<GPoint>(), ri, d_indices, s0, s0 + m, d_count, c->nbr_pool.as<GPoint>(), stride,
