@@ -265,7 +265,7 @@ k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slo
     float part = 0.f;
 #pragma unroll
     for (int k = 0; k < 9; k++) {
-      v[k] = hist[l + 4 * k];
+      v[k] = act ? hist[l + 4 * k] : 0.f;  // (idle threads must not read block 0 while its owners rewrite it)
       part = __fadd_rn(part, __fmul_rn(v[k], v[k]));
     }
     float p0 = __shfl_sync(0xffffffffu, part, gbase), p1 = __shfl_sync(0xffffffffu, part, gbase + 1);
