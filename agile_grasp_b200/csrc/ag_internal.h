@@ -121,6 +121,11 @@ struct Ctx {
   unsigned long long g_tick = 0, state_gen = 0;
   int n_graph_replays = 0;
   bool capturing = false;  // the stream is being captured: timing events must be recorded as external events
+  // non-deterministic normal mode: glibc rand() stream, per-sample stream offsets ([0] = carry), bound on the
+  // number of samples that may already have consumed draws in the current call
+  DevBuf rand_raw, rand_off;
+  size_t rand_count = 0;
+  int rand_consumed_bound = 0;
   DevBuf nbr_heads;  // per sample of the chunk: sample xyz + neighbour count (float4)
   DevBuf nbr_pool;   // neighbour lists of the current chunk of samples: stride x 16-byte records per sample
   bool two_cams = false;  // the last cloud had points of both cameras (sizes the neighbour pool)
@@ -161,6 +166,8 @@ int set_normals_device(Ctx* c, const double* h_normals);  // cloud_normals_ supp
 // d_count: device int holding the number of valid entries of d_indices (<= n, the launch bound)
 int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count, double radius, ag_frame* d_frames,
                         bool write_normals);
+// restarts the rand() stream of the non-deterministic normal mode (start of every ag_localize / ag_fit_quadrics)
+int quadric_rand_reset(Ctx* c);
 // enqueue only (no sync): sweep + stable compaction; the hypothesis count stays in device memory
 int hand_sweep_enqueue(Ctx* c, const int* d_indices, int n, const ag_frame* d_frames, unsigned flags);
 // after a sync: handles samples whose slab overflowed the small instantiation; returns the hypothesis count

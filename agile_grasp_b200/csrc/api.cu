@@ -376,7 +376,9 @@ static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, in
   // per-kernel launch gaps); any change of shape, parameters or buffers falls back to the eager path.
   auto body = [&]() -> int {
     record_event(c, c->ev[1]);
-    int rc = preprocess_device(c, d_points, stride, n_in, size_left);
+    int rc = quadric_rand_reset(c);
+    if (rc) return rc;
+    rc = preprocess_device(c, d_points, stride, n_in, size_left);
     if (rc) return rc;
     record_event(c, c->ev[2]);
     record_event(c, c->ev[3]);
@@ -673,7 +675,7 @@ void ag_destroy(ag_ctx* h) {
   if (c.h_out) cudaFreeHost(c.h_out);
   for (DevBuf* b : {&c.raw, &c.keys, &c.keys_sorted, &c.keys_unique, &c.cub_tmp, &c.block_counts, &c.misc, &c.vox,
                     &c.row_ptr, &c.col_ptr, &c.row_index, &c.all_frames,
-                    &c.normals, &c.samples, &c.sample_stage, &c.moments, &c.frames, &c.nn_counts, &c.nbr_pool, &c.nbr_heads, &c.grasps_raw, &c.valid,
+                    &c.normals, &c.samples, &c.sample_stage, &c.moments, &c.frames, &c.nn_counts, &c.nbr_pool, &c.nbr_heads, &c.rand_raw, &c.rand_off, &c.grasps_raw, &c.valid,
                     &c.images_raw, &c.hyp_slots, &c.grasps, &c.counters, &c.scores, &c.descriptors, &c.kvals, &c.handle_in, &c.handle_bits, &c.sweep_dbg, &c.overflow})
     b->release();
   if (c.h_pinned) cudaFreeHost(c.h_pinned);
@@ -1168,8 +1170,10 @@ int ag_fit_quadrics(ag_ctx* h, const int* indices, int n_indices, double radius,
   RowIndex* ri = c.row_index.as<RowIndex>();
   k_check_samples<<<(n_indices + 255) / 256, 256, 0, c.stream>>>(ri, n_indices, c.samples.as<int>());
   AG_CUDA_CHECK(cudaMemsetAsync(c.frames.p, 0, size_t(n_indices) * sizeof(ag_frame), c.stream));
-  int rc = fit_quadrics_device(&c, c.samples.as<int>(), n_indices, &ri->n_samples, radius, c.frames.as<ag_frame>(),
-                               false);
+  int rc = quadric_rand_reset(&c);
+  if (rc) return rc;
+  rc = fit_quadrics_device(&c, c.samples.as<int>(), n_indices, &ri->n_samples, radius, c.frames.as<ag_frame>(),
+                           false);
   if (rc) return rc;
   AG_CUDA_CHECK(cudaMemcpyAsync(frames_out, c.frames.p, size_t(n_indices) * sizeof(ag_frame), cudaMemcpyDeviceToHost,
                                 c.stream));

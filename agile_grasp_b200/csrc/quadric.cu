@@ -381,6 +381,7 @@ k_taubin_moments(int s0, int m, const float4* __restrict__ heads, const GPoint* 
 }
 
 // ---- small dense helpers (per warp, shared memory, lane-parallel where it is cheap) -----------
+constexpr int kRankCap = 2048;  // neighbours per sample the rand() % n mode can rank (larger balls fall back)
 struct AxesSmem {
   double A[81];   // Schur complement, later C = L^-1 A L^-T, diagonalised in place
   double L[81];   // B, then its Cholesky factor
@@ -388,6 +389,12 @@ struct AxesSmem {
   double m[10];   // last column of M (9 entries) and n
   double par[10]; // quadric parameters in centred/scaled coordinates
   double T[28];   // weighted order-6 normal tensor
+};
+// non-deterministic normal mode only (extra dynamic shared memory behind the kWarps AxesSmem blocks): squared
+// distances of the neighbours and their (distance, index) order
+struct RankSmem {
+  float d2[kRankCap];
+  unsigned short order[kRankCap];
 };
 
 // streams a sample's neighbour list (written by k_ball_search) 32 records per step, the next step's load
@@ -589,7 +596,9 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip
               const GPoint* __restrict__ pool, int stride, const int2* __restrict__ nn_counts, double inv_r,
               const double* __restrict__ moments,
               double cam0x, double cam0y, double cam0z, double cam1x, double cam1y, double cam1z,
-              ag_frame* __restrict__ frames, double* normals_out /* may be null */) {
+              ag_frame* __restrict__ frames, double* normals_out /* may be null */,
+              const uint32_t* __restrict__ rand_raw /* null = deterministic normals */,
+              const int* __restrict__ rand_off) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   AxesSmem* sm_all = reinterpret_cast<AxesSmem*>(s_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -607,8 +616,11 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip
   const double n = mom[0];
   ag_frame F;
   F.num_neighbors = int(n);
-  const int major = (mom[35] > n - mom[35]) ? 1 : 0;  // quadric.cpp:217-226 (tie -> camera 0)
-  F.majority_cam = major;
+  int major = (mom[35] > n - mom[35]) ? 1 : 0;  // quadric.cpp:217-226 (tie -> camera 0)
+  // the reference's production mode (is_deterministic = false, quadric.cpp:177-192): with more than 50
+  // neighbours the normals are evaluated at 50 picks rand() % n of the (distance, index)-sorted neighbour list
+  const bool picks = rand_raw != nullptr && n_list > 50 && n_list <= kRankCap;
+  RankSmem& rk = reinterpret_cast<RankSmem*>(s_raw + sizeof(AxesSmem) * kWarps)[warp];  // only touched if picks
 
   // --- build the reduced pencil: A = M[0:9,0:9] - m m^T / n, B = N[0:9,0:9]
   for (int e = lane; e < 81; e += 32) {
@@ -794,8 +806,7 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip
   double acc[34];
 #pragma unroll
   for (int i = 0; i < 34; i++) acc[i] = 0.0;
-  walk_list(list, n_list, [&](const GPoint& p, bool active) {
-    if (!active) return;
+  auto accumulate = [&](const GPoint& p) {
     const double x = (double(p.x) - qx) * inv_r, y = (double(p.y) - qy) * inv_r, z = (double(p.z) - qz) * inv_r;
     double gn[3], m6[28];
     quad_normal(par, x, y, z, gn);
@@ -804,7 +815,46 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip
     monomials6(gn, m6);
 #pragma unroll
     for (int t = 0; t < 28; t++) acc[6 + t] += m6[t];
-  });
+  };
+  GPoint pick[2];  // picks t = lane and t = lane + 32 (t < 50)
+  pick[0] = pick[1] = q;
+  if (picks) {
+    // (distance, index) rank of every neighbour: the list is in index order, so position breaks distance ties
+    for (int i = lane; i < n_list; i += 32) {
+      const GPoint p = list[i];
+      rk.d2[i] = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
+    }
+    __syncwarp();
+    for (int i0 = 0; i0 < n_list; i0 += 32) {
+      const int i = i0 + lane;
+      const float di = i < n_list ? rk.d2[i] : 0.f;
+      int rank = 0;
+      for (int j = 0; j < n_list; j++) {
+        const float dj = rk.d2[j];
+        rank += (dj < di || (dj == di && j < i)) ? 1 : 0;
+      }
+      if (i < n_list) rk.order[rank] = (unsigned short)i;
+    }
+    __syncwarp();
+    const uint32_t* raw = rand_raw + size_t(50) * size_t(rand_off[s]);
+    int cam1 = 0;
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int t = lane + 32 * u;
+      if (t < 50) {
+        pick[u] = list[rk.order[raw[t] % uint32_t(n_list)]];
+        cam1 += int(pick[u].tag & kTagCamBit);
+        accumulate(pick[u]);
+      }
+    }
+    cam1 = __reduce_add_sync(0xffffffffu, cam1);
+    major = cam1 > 50 - cam1 ? 1 : 0;  // majority over the picks (quadric.cpp:217-226)
+  } else {
+    walk_list(list, n_list, [&](const GPoint& p, bool active) {
+      if (active) accumulate(p);
+    });
+  }
+  F.majority_cam = major;
   // warp reduction by recursive halving: lane i holds sum i (i < 32); sums 32, 33 by butterflies
   {
     const double r32 = warp_reduce_transpose32(acc);
@@ -826,7 +876,8 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip
   __syncwarp();
 
   // --- walk 3: j* = argmax_j sum_i (g_i.g_j)^6 = argmax_j <T, g_j^(x6)>, first max in the reference's
-  // (distance, index) order; index order == (camera, x, y, z) order of the voxel list
+  // (distance, index) order; index order == (camera, x, y, z) order of the voxel list.  In the picks mode the
+  // first max is in pick order t.
   double bestS = -1.0;
   float bestD = 3.0e38f;
   GPoint bestP;
@@ -840,8 +891,7 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip
     if (a.y != b.y) return a.y < b.y;
     return a.z < b.z;
   };
-  walk_list(list, n_list, [&](const GPoint& p, bool active) {
-    if (!active) return;
+  auto score = [&](const GPoint& p, float d, const GPoint& key) {
     const double x = (double(p.x) - qx) * inv_r, y = (double(p.y) - qy) * inv_r, z = (double(p.z) - qz) * inv_r;
     double gn[3], m6[28];
     quad_normal(par, x, y, z, gn);
@@ -849,13 +899,29 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip
     double S = 0.0;
 #pragma unroll
     for (int t = 0; t < 28; t++) S += sm.T[t] * m6[t];
-    const float d = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
-    const bool better = S > bestS || (S == bestS && (d < bestD || (d == bestD && before(p, bestP))));
+    const bool better = S > bestS || (S == bestS && (d < bestD || (d == bestD && before(key, bestP))));
     if (better) {
-      bestS = S; bestD = d; bestP = p;
+      bestS = S; bestD = d; bestP = key;
       bestG[0] = gn[0]; bestG[1] = gn[1]; bestG[2] = gn[2];
     }
-  });
+  };
+  if (picks) {
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int t = lane + 32 * u;
+      if (t < 50) {  // order key = pick number t (encoded so that `before` compares t)
+        GPoint key;
+        key.x = float(t);
+        key.y = key.z = 0.f;
+        key.tag = 0u;
+        score(pick[u], 0.f, key);
+      }
+    }
+  } else {
+    walk_list(list, n_list, [&](const GPoint& p, bool active) {
+      if (active) score(p, dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z), p);
+    });
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const double oS = __shfl_xor_sync(0xffffffffu, bestS, o);
@@ -946,6 +1012,64 @@ __global__ void k_quadric_finish(GPoint* pts, const RowIndex* __restrict__ rip, 
 
 }  // namespace
 
+// non-deterministic normal mode: sample s consumes rand() draws [50 k_s, 50 k_s + 50), k_s = number of earlier
+// samples (in sample order, continuing across the launches of one call) with more than 50 neighbours
+__global__ void __launch_bounds__(1024)
+k_rand_offsets(const int2* __restrict__ nn_counts, int s0, int m, const int* __restrict__ d_count, int* __restrict__ rand_off,
+               int* __restrict__ carry) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_base = *carry;
+  __syncthreads();
+  for (int base = 0; base < m; base += 1024) {
+    const int s = s0 + base + tid;
+    const int f = (base + tid < m && s < *d_count && nn_counts[s].x > 50) ? 1 : 0;
+    int v = f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (lane == 31) s_warp[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int excl = v - f + (warp > 0 ? s_warp[warp - 1] : 0);
+    if (base + tid < m) rand_off[s] = s_base + excl;
+    __syncthreads();
+    if (tid == 0) s_base += s_warp[31];
+    __syncthreads();
+  }
+  if (tid == 0) *carry = s_base;
+}
+
+// glibc rand() outputs after srand(1) — what a process that never seeds gets from the reference's
+// `rand() % indices.size()` (quadric.cpp:184): random_r TYPE_3, word_k = word_(k-31) + word_(k-3), output >> 1
+static void glibc_rand_stream(size_t count, std::vector<uint32_t>& out) {
+  std::vector<uint32_t> w(34);
+  int64_t x = 1;
+  w[0] = 1u;
+  for (int i = 1; i < 31; i++) {
+    x = (16807 * x) % 2147483647;
+    if (x < 0) x += 2147483647;
+    w[i] = uint32_t(x);
+  }
+  for (int i = 31; i < 34; i++) w[i] = w[i - 31];
+  w.resize(344 + count);
+  for (size_t i = 34; i < w.size(); i++) w[i] = w[i - 31] + w[i - 3];
+  out.resize(count);
+  for (size_t k = 0; k < count; k++) out[k] = w[344 + k] >> 1;
+}
+
 // neighbour-pool records per sample for a radius: the lattice-ball bound, capped at four times what a
 // surface sampled by the voxel lattice puts into the ball (a ball holding more sets kErrBallOverflow)
 static int ball_stride(double radius, double voxel, bool two_cams) {
@@ -954,6 +1078,14 @@ static int ball_stride(double radius, double voxel, bool two_cams) {
   const double surf = std::max(288.0, 1024.0 * (cells / 10.0) * (cells / 10.0));
   const double v = std::min(ball, surf) * (two_cams ? 2.0 : 1.0);
   return int((std::min(v, 1.0e6) + 31.0) / 32.0) * 32;
+}
+
+int quadric_rand_reset(Ctx* c) {
+  c->rand_consumed_bound = 0;
+  if (c->params.deterministic_normals != 0) return AG_OK;
+  if (c->rand_off.reserve(64)) return AG_ERR_CUDA;
+  AG_CUDA_CHECK(cudaMemsetAsync(c->rand_off.p, 0, 16, c->stream));
+  return AG_OK;
 }
 
 int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count, double radius, ag_frame* d_frames,
@@ -975,15 +1107,36 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
   const double inv_r = ldexp(1.0, int(lrint(log2(1.0 / radius))));
   unsigned long long* ctr = c->counters.as<unsigned long long>();
   RowIndex* ri = c->row_index.as<RowIndex>();
-  const size_t smem = sizeof(AxesSmem) * kWarps;
+  const size_t smem = sizeof(AxesSmem) * kWarps + (c->params.deterministic_normals == 0 ? sizeof(RankSmem) * kWarps : 0);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_taubin_axes, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cudaFuncSetAttribute(k_taubin_axes, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         int(sizeof(AxesSmem) * kWarps + sizeof(RankSmem) * kWarps));
     cudaFuncSetAttribute(k_taubin_axes, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
     cudaFuncSetAttribute(k_ball_search, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     attr_set = true;
   }
   const HandConst& h = c->hand;
+  // non-deterministic normal mode (ag_params.deterministic_normals = 0): the rand() stream of an unseeded process,
+  // 50 draws per sample with more than 50 neighbours; the stream restarts with every ag_localize / ag_fit_quadrics
+  const bool rand_mode = c->params.deterministic_normals == 0;
+  const uint32_t* d_rand = nullptr;
+  int* d_rand_off = nullptr;
+  if (rand_mode) {
+    const size_t need = size_t(50) * (size_t(c->rand_consumed_bound) + size_t(n));
+    if (c->rand_count < need) {
+      std::vector<uint32_t> hs;
+      glibc_rand_stream(need + need / 2, hs);
+      if (c->rand_raw.reserve(hs.size() * 4)) return AG_ERR_CUDA;
+      AG_CUDA_CHECK(cudaMemcpyAsync(c->rand_raw.p, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice, c->stream));
+      AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      c->rand_count = hs.size();
+    }
+    if (c->rand_off.reserve(size_t(n) * 4 + 16)) return AG_ERR_CUDA;
+    d_rand = c->rand_raw.as<uint32_t>();
+    d_rand_off = c->rand_off.as<int>() + 4;  // [0] = carry across launches, offsets from [4]
+    c->rand_consumed_bound += n;
+  }
   for (int s0 = 0; s0 < n; s0 += chunk) {
     const int m = std::min(chunk, n - s0);
     const int blocks = (m + kWarps - 1) / kWarps;
@@ -1013,10 +1166,14 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
       else k_taubin_moments<1><<<grid, kWarps * 32, 0, c->stream>>>(s0, m, hd, pl, stride, inv_r, mo);
     }
     if (timed) record_event(c, c->ev_k[2]);
+    if (rand_mode) {
+      k_rand_offsets<<<1, 1024, 0, c->stream>>>(c->nn_counts.as<int2>(), s0, m, d_count, d_rand_off, c->rand_off.as<int>());
+      c->launches += 1;
+    }
     k_taubin_axes<<<blocks, kWarps * 32, smem, c->stream>>>(
         c->vox.as<GPoint>(), ri, d_indices, s0, s0 + m, d_count, c->nbr_pool.as<GPoint>(), stride,
         c->nn_counts.as<int2>(), inv_r, c->moments.as<double>(), h.cam[0][0], h.cam[0][1], h.cam[0][2], h.cam[1][0],
-        h.cam[1][1], h.cam[1][2], d_frames, write_normals ? c->normals.as<double>() : nullptr);
+        h.cam[1][1], h.cam[1][2], d_frames, write_normals ? c->normals.as<double>() : nullptr, d_rand, d_rand_off);
     if (timed) record_event(c, c->ev_k[3]);
     c->launches += 3;
   }

@@ -109,6 +109,9 @@ ago_hands* ago_localize(const void* points, int stride, int n_in, int size_left,
 int ago_find_handles(const ag_grasp* hands, int n, int min_inliers, double min_length, ag_handle** handles_out,
                      int* n_handles, int32_t** inliers_out, int* n_inliers_total);
 
+/* the first n outputs of glibc rand() after srand(seed) (restatement used by the non-deterministic normal mode) */
+int ago_glibc_rand(uint32_t seed, int n, int32_t* out);
+
 /* deterministic sample draw shared with the product: sorted distinct indices in [0,n) */
 int ago_draw_samples(int n, int num_samples, uint64_t seed, int32_t* out);
 

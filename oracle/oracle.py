@@ -329,6 +329,12 @@ def find_handles(grasps, min_inliers, min_length):
     return H, [flat[h["inlier_offset"]:h["inlier_offset"] + h["n_inliers"]] for h in H]
 
 
+def glibc_rand(seed, n):
+    out = np.zeros(n, np.int32)
+    lib().ago_glibc_rand(C.c_uint32(seed), int(n), _p(out, C.c_int32))
+    return out
+
+
 def draw_samples(n, num_samples, seed):
     out = np.zeros(min(n, num_samples), np.int32)
     k = lib().ago_draw_samples(int(n), int(num_samples), C.c_uint64(seed), _p(out, C.c_int32))

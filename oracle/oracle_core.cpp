@@ -606,12 +606,45 @@ static void permute(std::vector<int>& v, int k) {
   }
 }
 
+// glibc rand(): random_r TYPE_3 (additive feedback, degree 31, separation 3), the generator behind the
+// reference's unseeded `rand() % indices.size()` (quadric.cpp:184).  Seed 1 = a process that never called
+// srand.  Pinned against the C library itself in tests/test_oracle_quadric.py.
+struct GlibcRand {
+  uint32_t r[34];
+  int pos = 0;  // next output is built at ring position pos
+  explicit GlibcRand(uint32_t seed) {
+    int32_t w[34];
+    w[0] = int32_t(seed ? seed : 1u);
+    for (int i = 1; i < 31; i++) {
+      int64_t v = (16807LL * int64_t(w[i - 1])) % 2147483647LL;
+      if (v < 0) v += 2147483647LL;
+      w[i] = int32_t(v);
+    }
+    for (int i = 31; i < 34; i++) w[i] = w[i - 31];
+    std::vector<uint32_t> u(w, w + 34);
+    for (int i = 34; i < 344; i++) u.push_back(u[i - 31] + u[i - 3]);
+    for (int i = 0; i < 34; i++) r[i] = u[344 - 34 + i];  // the last 34 words, r[33] = word 343
+    pos = 0;
+  }
+  uint32_t next() {  // word k = word(k - 31) + word(k - 3); the ring holds the last 34 words, oldest at pos
+    const uint32_t v = r[(pos + 3) % 34] + r[(pos + 31) % 34];
+    r[pos] = v;
+    pos = (pos + 1) % 34;
+    return v >> 1;
+  }
+};
+
 int fit_quadrics(const float* xyz, const int32_t* cam, int n, const Tree* tree, const int* indices, int S,
                  double radius, const ag_params& P, int sum_perm, ag_frame* frames, double* params_out,
                  double* MN_out, double* eig_out) {
   const double cam_origin[2][3] = {{P.cam_tf_left[3], P.cam_tf_left[7], P.cam_tf_left[11]},
                                    {P.cam_tf_right[3], P.cam_tf_right[7], P.cam_tf_right[11]}};
   int threads = std::max(1, P.num_threads);
+  // production mode of the reference (is_deterministic = false, hand_search.h:84): normals from 50 neighbours
+  // drawn with rand() % n; reproducible only single-threaded, in sample order, from the unseeded state
+  const bool rand_mode = P.deterministic_normals == 0;
+  GlibcRand rng(1);
+  if (rand_mode) threads = 1;
   int err = 0;
   std::string errmsg;
   // hand_search.cpp:77-80 omp parallel for over samples
@@ -645,7 +678,19 @@ int fit_quadrics(const float* xyz, const int32_t* cam, int n, const Tree* tree, 
         for (size_t t = 0; t < nn.size(); t++)
           for (int d = 0; d < 3; d++) coords[3 * t + d] = double(xyz[3 * nn[t] + d]);
       }
-      local_axes(coords, cam, nn, Q.params, sample, cam_origin, F);
+      if (rand_mode && nn.size() > 50) {  // quadric.cpp:177-192: 50 picks (repeats allowed) in FLANN order
+        std::vector<int> pick_nn(50);
+        std::vector<double> pick_xyz(150);
+        for (int t = 0; t < 50; t++) {
+          const int r = int(rng.next() % uint32_t(nn.size()));
+          pick_nn[t] = nn[r];
+          for (int d = 0; d < 3; d++) pick_xyz[3 * t + d] = coords[3 * r + d];
+        }
+        local_axes(pick_xyz, cam, pick_nn, Q.params, sample, cam_origin, F);
+        F.num_neighbors = int(nn.size());
+      } else {
+        local_axes(coords, cam, nn, Q.params, sample, cam_origin, F);
+      }
       if (params_out) std::memcpy(params_out + size_t(10) * s, Q.params, sizeof(Q.params));
       if (MN_out) {
         std::memcpy(MN_out + size_t(200) * s, Q.M, sizeof(Q.M));
@@ -1113,6 +1158,11 @@ int ago_hands_debug(const ago_hands* h, const int32_t** status, const int32_t** 
 }
 int ago_filter_hands(const ag_grasp* grasps, int n, const ag_params* P, uint8_t* keep) {
   filter_hands(grasps, n, *P, keep);
+  return 0;
+}
+int ago_glibc_rand(uint32_t seed, int n, int32_t* out) {
+  GlibcRand g(seed);
+  for (int i = 0; i < n; i++) out[i] = int32_t(g.next());
   return 0;
 }
 int ago_draw_samples(int n, int num_samples, uint64_t seed, int32_t* out) {

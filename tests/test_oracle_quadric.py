@@ -91,3 +91,33 @@ def test_two_lapack_builds_disagree_within_the_same_envelope(oracle, small_scene
     d = np.linalg.norm(res[0]["normal"] - res[1]["normal"], axis=1)
     assert np.median(d) < 1e-6  # they agree in the bulk ...
     assert d.max() > 0  # ... but not bit for bit: the reference is LAPACK-build dependent
+
+
+def test_glibc_rand_restatement_matches_libc(oracle):
+    """the generator behind the reference's unseeded rand() % n (quadric.cpp:184), pinned against the C library"""
+    import ctypes
+    libc = ctypes.CDLL("libc.so.6")
+    for seed in (1, 12345):
+        libc.srand(seed)
+        ref = np.array([libc.rand() for _ in range(3000)], np.int32)
+        assert np.array_equal(oracle.glibc_rand(seed, 3000), ref)
+
+
+def test_rand_mode_normals(oracle, small_scene):
+    """is_deterministic = false (the reference's production default, hand_search.h:84): 50 picks rand() % n per
+    sample with more than 50 neighbours, consumed in sample order from the unseeded state.  Reproducible, differs
+    from the all-neighbour mode by the sampling noise only, and samples with <= 50 neighbours are untouched."""
+    import copy
+    s = small_scene
+    P = copy.copy(s["P"])
+    det = oracle.fit_quadrics(s["tree"], s["cam"], s["idx"], 0.03, P)["frames"]
+    P.deterministic_normals = 0
+    r1 = oracle.fit_quadrics(s["tree"], s["cam"], s["idx"], 0.03, P)["frames"]
+    r2 = oracle.fit_quadrics(s["tree"], s["cam"], s["idx"], 0.03, P)["frames"]
+    assert r1.tobytes() == r2.tobytes()
+    assert np.array_equal(r1["num_neighbors"], det["num_neighbors"])
+    small = det["num_neighbors"] <= 50
+    assert np.array_equal(r1["normal"][small], det["normal"][small])
+    big = det["num_neighbors"] > 50
+    cosang = np.abs(np.einsum("ij,ij->i", r1["normal"][big], det["normal"][big]))
+    assert big.sum() > 50 and np.median(cosang) > 0.99 and (r1["normal"][big] != det["normal"][big]).any()
