@@ -68,19 +68,22 @@ __host__ __device__ static inline uint64_t splitmix64(uint64_t x) {
   x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
   return x ^ (x >> 31);
 }
-__global__ void k_draw_samples(RowIndex* ri, int s_req, uint64_t seed, int* out) {
+// seeded stratified draw: sample k of S lies in [k n / S, (k + 1) n / S).  A shard handles the samples
+// k = k_lo + j, j < count (count = launch bound; k_lo = 0 and count = s_req without sharding).
+__global__ void k_draw_samples(RowIndex* ri, int s_req, uint64_t seed, int* out, int k_lo, int count) {
   const int n = ri->n_points;
   const int S = s_req < n ? s_req : n;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k == 0) ri->n_samples = S;
-  if (k >= s_req) return;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0) ri->n_samples = min(max(S - k_lo, 0), count);
+  if (j >= count) return;
+  const int k = k_lo + j;
   if (k >= S) {
-    out[k] = -1;
+    out[j] = -1;
     return;
   }
   const long long lo = (static_cast<long long>(k) * n) / S, hi = (static_cast<long long>(k + 1) * n) / S;
   const uint64_t h = splitmix64(seed ^ splitmix64(uint64_t(k)));
-  out[k] = int(lo + static_cast<long long>(h % uint64_t(hi - lo)));
+  out[j] = int(lo + static_cast<long long>(h % uint64_t(hi - lo)));
 }
 __global__ void k_check_samples(RowIndex* ri, int s_req, const int* idx) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -362,7 +365,12 @@ static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, in
   cudaStream_t st = c->stream;
   c->two_cams = size_left < n_in;
   const bool given = indices && n_indices > 0;
-  const int S = given ? n_indices : std::max(0, c->params.num_samples);
+  const int S_total = given ? n_indices : std::max(0, c->params.num_samples);
+  // sample sharding (ag_params.shard_index / shard_count): this context's contiguous share of the samples
+  const int sh_n = std::max(1, c->params.shard_count), sh_i = std::min(std::max(0, c->params.shard_index), sh_n - 1);
+  const int k_lo = int((long long)S_total * sh_i / sh_n), k_hi = int((long long)S_total * (sh_i + 1) / sh_n);
+  const int S = k_hi - k_lo;
+  if (given) indices += k_lo;
   c->n_samples = S;
   const size_t slots = size_t(S) * 8;
   RowIndex* ri = c->row_index.as<RowIndex>();
@@ -403,7 +411,7 @@ static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, in
       AG_CUDA_CHECK(cudaMemcpyAsync(c->samples.p, c->sample_stage.p, size_t(S) * 4, cudaMemcpyDeviceToDevice, st));
       k_check_samples<<<(S + 255) / 256, 256, 0, st>>>(ri, S, c->samples.as<int>());
     } else {
-      k_draw_samples<<<(S + 255) / 256, 256, 0, st>>>(ri, S, c->params.seed, c->samples.as<int>());
+      k_draw_samples<<<(S + 255) / 256, 256, 0, st>>>(ri, S_total, c->params.seed, c->samples.as<int>(), k_lo, S);
     }
     c->launches += 1;
     rc = fit_quadrics_device(c, c->samples.as<int>(), S, &ri->n_samples, c->params.nn_radius_taubin,
@@ -625,6 +633,8 @@ void ag_default_params(ag_params* p) {
   p->num_samples = 2000;        // find_grasps.cpp:11
   p->num_threads = 1;
   p->deterministic_normals = 1;
+  p->shard_index = 0;
+  p->shard_count = 1;
   p->filters_boundaries = 0;
   p->fix_cam_source = 0;
   p->seed = 20150320;
@@ -687,7 +697,8 @@ void ag_destroy(ag_ctx* h) {
 
 int ag_set_params(ag_ctx* h, const ag_params* p) {
   if (!h || !p) return AG_ERR_INVALID;
-  if (!(p->voxel_size > 0) || !(p->nn_radius_taubin > 0) || !(p->nn_radius_hands > 0) || !(p->hand_depth > 0)) {
+  if (!(p->voxel_size > 0) || !(p->nn_radius_taubin > 0) || !(p->nn_radius_hands > 0) || !(p->hand_depth > 0) ||
+      p->shard_count < 0 || p->shard_index < 0 || (p->shard_count > 0 && p->shard_index >= p->shard_count)) {
     set_error("invalid parameters");
     return AG_ERR_INVALID;
   }

@@ -32,6 +32,8 @@ class AgParams(C.Structure):
         ("fix_cam_source", C.c_int32),
         ("reserved", C.c_int32),
         ("seed", C.c_uint64),
+        ("shard_index", C.c_int32),
+        ("shard_count", C.c_int32),
     ]
 
 

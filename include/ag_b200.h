@@ -76,6 +76,11 @@ typedef struct ag_params {
   int32_t fix_cam_source;      /* 0 reproduces the reference's pre-NaN camera labelling quirk */
   int32_t reserved;
   uint64_t seed;               /* sample-index RNG seed when indices are not supplied */
+  /* Sample sharding of ONE cloud over several GPUs: this context handles the contiguous share
+   * shard_index of shard_count of the samples (drawn or explicit); the cloud itself is voxelised on every
+   * rank.  Concatenating the shards' lists in shard order gives the unsharded list.  0 / 1 = no sharding. */
+  int32_t shard_index;
+  int32_t shard_count;
 } ag_params;
 
 /* One grasp hypothesis = GraspHypothesis (grasp_hypothesis.h:46-231) minus the variable-length

@@ -42,7 +42,7 @@ def test_no_gpu_means_loud_failure_not_a_fallback():
 def test_struct_layouts_match_header():
     from agile_grasp_b200.ctypes_defs import AgFrame, AgGrasp, AgParams
     assert ctypes.sizeof(AgGrasp) == 160 and ctypes.sizeof(AgFrame) == 80
-    assert ctypes.sizeof(AgParams) == 5 * 8 + 6 * 8 + 32 * 8 + 4 * 8 + 6 * 4 + 8
+    assert ctypes.sizeof(AgParams) == 5 * 8 + 6 * 8 + 32 * 8 + 4 * 8 + 6 * 4 + 8 + 2 * 4  # + shard_index, shard_count
     p = AgParams()
     api.lib().ag_default_params(ctypes.byref(p))
     assert (p.finger_width, p.hand_outer_diameter, p.hand_depth, p.hand_height, p.init_bite) == (0.01, 0.09, 0.06, 0.02, 0.01)

@@ -25,6 +25,10 @@ def ctx():
     c.close()
 
 
+GRASP_FIELDS = ("axis", "approach", "binormal", "bottom", "surface", "width", "score", "sample_index", "sample_slot",
+                "orientation", "cam_source", "num_points", "image_id", "half_antipodal", "full_antipodal", "label")
+
+
 def _u32(a):
     return np.ascontiguousarray(a).view(np.uint32)
 
@@ -557,3 +561,32 @@ def test_rand_mode_normals_match_oracle(ctx, oracle, small_scene):
         assert np.array_equal(fd["normal"][~big], fg["normal"][~big])
     finally:
         ctx.set_params(s["P"])
+
+
+def test_sample_sharding_concatenates_to_the_unsharded_list(ctx, small_scene, linear_svm_path):
+    """one cloud, the samples split into contiguous shares (ag_params.shard_index / shard_count, the
+    cloud voxelised by every shard): the shards' lists concatenated in shard order are the unsharded list
+    (drawn samples and explicit indices; sample_slot / image_id are shard-local bookkeeping)."""
+    import copy
+    s = small_scene
+    svm = api.Svm(linear_svm_path)
+    ctx.set_svm(svm)
+    fields = [f for f in GRASP_FIELDS if f not in ("sample_slot", "image_id")]
+    try:
+        for idx in (None, s["idx"]):
+            ctx.set_params(s["P"])
+            full = ctx.localize(s["pts"], s["size_left"], idx)
+            for world in (2, 3):
+                parts = []
+                for r in range(world):
+                    P = copy.copy(s["P"])
+                    P.shard_index, P.shard_count = r, world
+                    ctx.set_params(P)
+                    parts.append(ctx.localize(s["pts"], s["size_left"], idx))
+                cat = np.concatenate(parts)
+                assert len(cat) == len(full) and all(len(p) > 0 for p in parts)
+                for f in fields:
+                    assert np.ascontiguousarray(cat[f]).tobytes() == np.ascontiguousarray(full[f]).tobytes(), (world, f)
+    finally:
+        ctx.set_params(s["P"])
+        ctx.set_svm(None)
