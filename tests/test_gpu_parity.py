@@ -590,3 +590,42 @@ def test_sample_sharding_concatenates_to_the_unsharded_list(ctx, small_scene, li
     finally:
         ctx.set_params(s["P"])
         ctx.set_svm(None)
+
+
+def test_localize_edge_cases(ctx, oracle, small_scene, linear_svm_path):
+    """ragged / degenerate calls of the boundary: more samples than voxels, repeated explicit
+    indices (hand_search.cpp:29-46 uses them verbatim), an out-of-range index, zero samples, a one-point cloud,
+    an empty cloud inside a batch."""
+    import copy
+    s = small_scene
+    tiny = s["pts"][:2000].copy()
+    P = copy.copy(s["P"])
+    P.num_samples = 5000  # far more than the voxels of the tiny cloud
+    ctx.set_params(P)
+    try:
+        g = ctx.localize(tiny, len(tiny))
+        t = ctx.timings()
+        assert t["n_samples"] == t["n_voxels"] <= 2000  # clamped: one stratum per voxel
+        assert len(np.unique(g["sample_index"])) <= t["n_voxels"]
+        ctx.set_params(s["P"])
+        rep = np.array([s["idx"][3], s["idx"][3], s["idx"][7]], np.int32)
+        g2 = ctx.localize(s["pts"], s["size_left"], rep)
+        H, _, _ = oracle.localize(s["pts"], s["size_left"], s["P"], rep, 0, None, False)
+        assert len(g2) == len(H.grasps) and np.array_equal(g2["sample_index"], H.grasps["sample_index"])
+        a, b = g2[g2["sample_slot"] == 0], g2[g2["sample_slot"] == 1]
+        assert len(a) == len(b) and np.array_equal(a["approach"], b["approach"])  # the repeated sample, twice
+        with pytest.raises(api.AgError, match="out of range"):
+            ctx.localize(s["pts"], s["size_left"], np.array([10**8], np.int32))
+        P0 = copy.copy(s["P"])
+        P0.num_samples = 0
+        ctx.set_params(P0)
+        assert len(ctx.localize(s["pts"], s["size_left"])) == 0 and ctx.timings()["n_voxels"] == len(s["xyz"])
+        ctx.set_params(s["P"])
+        one = np.zeros((1, 8), np.float32)
+        one[0, :3] = [0.1, 0.0, 0.7]
+        ctx.localize(one, 1)  # (a rank-deficient neighbourhood: the frame is arbitrary in the reference too)
+        assert ctx.timings()["n_voxels"] == 1 and ctx.timings()["n_samples"] == 1
+        outs = ctx.localize_batch([s["pts"], np.zeros((0, 8), np.float32), s["pts"]], [s["size_left"], 1, s["size_left"]])
+        assert len(outs[1]) == 0 and len(outs[0]) > 0 and outs[0].tobytes() == outs[2].tobytes()
+    finally:
+        ctx.set_params(s["P"])
