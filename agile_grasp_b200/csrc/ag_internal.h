@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -66,7 +67,7 @@ struct GraphKey {
   int stride, n_in, size_left, S, given;
   unsigned flags;
 };
-extern unsigned long long g_alloc_gen;
+extern std::atomic<unsigned long long> g_alloc_gen;  // process-wide: any (re)allocation retires every cached graph
 struct GraphSlot {
   GraphKey key;
   bool valid = false;

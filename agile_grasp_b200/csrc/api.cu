@@ -2,6 +2,7 @@
 // loader, the full localize/classify path and the stage-level entry points.
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -18,7 +19,7 @@ void set_error(const std::string& msg) { g_error = msg; }
 
 // bumped whenever any buffer a captured graph may point to is (re)allocated: a cached graph is only replayed
 // while the generation it was captured under is current
-unsigned long long g_alloc_gen = 0;
+std::atomic<unsigned long long> g_alloc_gen{0};
 
 int DevBuf::reserve(size_t bytes) {
   if (bytes <= cap) return 0;
