@@ -124,7 +124,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "hyp/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"config{args.config}: 640x480 organised cloud (307200 pts), 2000 samples, linear SVM",
+        "config": {"workload": f"config{args.config}: organised cloud of {pts.shape[0]} pts, {S} samples, linear SVM",
                    "hypotheses_per_step": float(np.mean(hyps))},
         "cpu_baseline": {"value": value, "unit": "hyp/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} full clouds of the bench workload, OpenMP over samples on all "
@@ -316,8 +316,9 @@ def main():
             "metric": METRIC, "value": float(value), "unit": "hyp/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": float(t_dev[0] / args.steps), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"config{args.config}: one 640x480 organised cloud (307200 pts, 32 B/pt) per rank "
-                                   "per step, 2000 samples, linear SVM svm_032015_linear_20_20_same",
+            "config": {"workload": f"config{args.config}: one organised cloud ({c0['n']} pts, {c0['stride']} B/pt; 640x480 "
+                                   f"per view) per rank per step, {c0['P'].num_samples} samples, linear SVM "
+                                   "svm_032015_linear_20_20_same",
                        "l2": "flushed between timed iterations (256 MiB write)",
                        "hypotheses_per_step": float(n_h[0] / args.steps),
                        "multi_gpu": ("one cloud per rank per step; grasp lists exchanged by " +
