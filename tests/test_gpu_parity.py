@@ -415,6 +415,18 @@ def test_cpp_localization_shim_end_to_end(tmp_path, linear_svm_path):
     g = ctx.localize(pts, size_left)
     gg, keep = ctx.classify(api.Svm(linear_svm_path), g)
     assert f"{len(g)} hands, {int(keep.sum())} antipodal" in out.stdout, out.stdout[-400:]
+    # the same cloud as a binary PCD file: the file overload (localization.cpp:169-214) + findHandles (test.cpp:95-97)
+    rec = np.zeros(len(pts), dtype=[("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("rgba", "<u4")])
+    rec["x"], rec["y"], rec["z"] = pts[:, 0], pts[:, 1], pts[:, 2]
+    pcd = tmp_path / "cloud.pcd"
+    hdr = ("VERSION 0.7\nFIELDS x y z rgba\nSIZE 4 4 4 4\nTYPE F F F U\nCOUNT 1 1 1 1\nWIDTH %d\nHEIGHT 1\n"
+           "VIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA binary\n" % (len(pts), len(pts))).encode()
+    pcd.write_bytes(hdr + rec.tobytes())
+    out2 = subprocess.run([str(exe), str(pcd), linear_svm_path, "400", "1"], capture_output=True, text=True)
+    assert out2.returncode == 0, out2.stdout + out2.stderr
+    assert f"{len(g)} hands, {int(keep.sum())} antipodal" in out2.stdout, out2.stdout[-400:]
+    H, inl = ctx.find_handles(gg[keep.astype(bool)], 3, 0.005)
+    assert f"{len(H)} handles; serialized Grasps message of the handles: {16 + 4 + 100 * len(H)} bytes" in out2.stdout, out2.stdout[-400:]
     ctx.close()
 
 
