@@ -50,9 +50,15 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
     def __init__(self, index):
-        self.rows = []
+        self.rows = []   # (host time the line arrived, fields)
         self.proc = None
         self.index = index
+        self.t_mark = None
+
+    def mark(self):
+        """start of the timed region: only samples from here on are reported (the sampler itself is started
+        earlier, nvidia-smi needs a few hundred ms to deliver its first line)"""
+        self.t_mark = time.perf_counter()
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -60,7 +66,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -69,7 +75,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if not self.proc:
@@ -81,7 +87,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for t, r in self.rows if self.t_mark is None or t >= self.t_mark]
+        window = "timed region"
+        if not rows:  # the timed region was shorter than one sampling period: report the warm-up samples
+            rows, window = [r for t, r in self.rows], "warm-up (timed region shorter than the 20 ms sampling period)"
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -91,7 +101,7 @@ class ClockSampler:
             except Exception:
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def make_cloud(config, scene_offset):
@@ -220,6 +230,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     # ---- priming (untimed, before the W warm-up steps): every input buffer goes through the eager call and the
     # CUDA-graph capture once, so that warm-up and timed steps all run the steady-state (replay) path
     for c in pool:
@@ -231,9 +244,7 @@ def main():
         g, _, _ = step_device(pool[w % len(pool)])
         gather(g)
         gather(step_host(pool[w % len(pool)]))
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
 
     # ---- timed: device-resident input (value)
     dev_ms, hyps, mom_ms, mom_bytes, launches, comm_ms = [], [], [], [], [], []
