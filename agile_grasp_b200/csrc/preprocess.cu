@@ -1,4 +1,4 @@
-// preprocess.cu — NaN removal, workspace filter, voxelisation and hash-grid build on the GPU.
+// preprocess.cu — NaN removal, workspace filter, voxelisation and the x-row / column index build on the GPU.
 //
 // Replaces (reference paths): pcl::removeNaNFromPointCloud + camera labelling
 // (src/agile_grasp/localization.cpp:17-27), Localization::filterWorkspace (:216-245),

@@ -2,7 +2,7 @@
 
 Every sample's work is independent (the reference's two hot loops are plain `omp parallel for`,
 hand_search.cpp:77-80,135-138, followed by a stable concatenation, :194-200), so samples are split
-into contiguous ranges, one per rank; the voxelised cloud and the hash grid are replicated (each rank
+into contiguous ranges, one per rank; the voxelised cloud and its row index are replicated (each rank
 runs the deterministic preprocessing itself).  The only exchange step is one all-gather of the
 fixed-stride grasp records, after which every rank holds the reference's sample-major ordering.
 Works with any torch.distributed backend: NCCL on device tensors (bench.py), gloo on CPU (tests).

@@ -20,6 +20,11 @@
  *                             hand_search.cpp:116-206, rotating_hand.cpp:19-177, finger_hand.cpp, antipodal.cpp
  *   ag_hog_svm             <- Learning::convertToImage + cv::HOGDescriptor::compute + CvSVM::predict,
  *                             learning.cpp:194-226,320-365
+ *   ag_find_handles        <- Localization::findHandles -> HandleSearch::findHandles + Handle,
+ *                             localization.cpp:390-408, handle_search.cpp:4-118, handle.cpp:3-73
+ *   ag_load_pcd            <- pcl::io::loadPCDFile<pcl::PointXYZRGBA> in the file overloads, localization.cpp:169-214
+ *   ag_localize_batch, ag_gather_*, ag_set_export_buffer, ag_params.shard_*  (no reference counterpart:
+ *                             batches of clouds, multi-GPU exchange of the grasp list, sample sharding)
  *
  * Error model: every function returns 0 on success, <0 on error; ag_last_error() gives the
  * message (thread-local).  The reference's "print and return an empty vector" behaviour
@@ -132,7 +137,7 @@ typedef struct ag_timings {
   int32_t n_in, n_voxels, n_samples, n_hyp;
   int64_t taubin_neighbor_points;   /* sum over samples of n_T(s): algorithmic bytes = 16 * this */
   int64_t hand_neighbor_points;     /* sum over samples of n_H(s) */
-  int64_t taubin_candidates;        /* points actually scanned by the hash-grid walk */
+  int64_t taubin_candidates;        /* candidate points staged by the radius search (rows x chord) */
   int64_t hand_candidates;
   float moments_ms;                 /* k_taubin_moments alone (the roofline-graded kernel), last call */
   float axes_ms;                    /* k_taubin_axes alone */
@@ -241,7 +246,7 @@ int ag_get_images(ag_ctx* ctx, uint32_t** bits, int* n_images);   /* AG_IMAGE_WO
 int ag_preprocess(ag_ctx* ctx, const void* points, int stride, int n_in, int size_left,
                   float** xyz_out, int32_t** cam_out, int* n_out);
 
-/* Load an already-voxelised cloud (skips preprocessing) and build the hash grid. */
+/* Load an already-voxelised cloud (skips preprocessing; must be in voxel order) and build the row index. */
 int ag_set_cloud(ag_ctx* ctx, const float* xyz, const int32_t* cam, int n);
 
 /* Radius search on the current cloud; returns neighbour indices in ascending index order. */
