@@ -52,3 +52,20 @@ def test_all_gather_grasps_gloo(tmp_path):
         assert len(m) == len(e)
         for nm in ("sample_slot", "orientation", "width"):
             assert np.array_equal(m[nm], e[nm])
+
+
+def test_shard_range_matches_the_library_partition():
+    """shard_range (python helper) and ag_params.shard_index / shard_count (api.cu: k_lo = S * i / n) cut the same
+    contiguous shares: they tile [0, S) in order, sizes differ by at most one."""
+    from agile_grasp_b200.shard import shard_range
+    for S in (0, 1, 7, 2000, 20000):
+        for world in (1, 2, 3, 8):
+            edges = [shard_range(S, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == S
+            for r in range(world):
+                lo, hi = edges[r]
+                assert lo == (S * r) // world and hi == (S * (r + 1)) // world
+                if r:
+                    assert lo == edges[r - 1][1]
+            sizes = [hi - lo for lo, hi in edges]
+            assert max(sizes) - min(sizes) <= 1
