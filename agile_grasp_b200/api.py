@@ -19,7 +19,7 @@ _LIB = None
 EXPORTS = [
     "ag_last_error", "ag_default_params", "ag_create", "ag_destroy", "ag_set_params", "ag_get_params",
     "ag_get_timings", "ag_free", "ag_svm_load", "ag_svm_free", "ag_svm_info", "ag_localize", "ag_localize_device",
-    "ag_classify", "ag_set_svm", "ag_set_export_buffer", "ag_get_points", "ag_get_images", "ag_preprocess", "ag_set_cloud", "ag_radius_search",
+    "ag_classify", "ag_set_svm", "ag_set_export_buffer", "ag_get_points", "ag_get_images", "ag_get_normals", "ag_preprocess", "ag_set_cloud", "ag_radius_search",
     "ag_fit_quadrics", "ag_hand_sweep", "ag_sweep_debug", "ag_hog_svm",
     "ag_find_handles", "ag_load_pcd", "ag_localize_batch", "ag_gather_slot_bytes", "ag_gather_create", "ag_gather_connect", "ag_gather_wait", "ag_gather_destroy",
 ]
@@ -54,6 +54,7 @@ def lib():
     L.ag_set_export_buffer.argtypes = [vp, vp, C.c_size_t]
     L.ag_get_points.argtypes = [vp, C.c_int, C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.POINTER(C.c_int32)), ip]
     L.ag_get_images.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint32)), ip]
+    L.ag_get_normals.argtypes = [vp, dp, C.c_int]
     L.ag_preprocess.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_float)),
                                 C.POINTER(C.POINTER(C.c_int32)), ip]
     L.ag_set_cloud.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int]
@@ -266,6 +267,12 @@ class Context:
         else:
             out = np.ctypeslib.as_array(bits, shape=(n.value, AG_IMAGE_WORDS)).copy()
         lib().ag_free(bits)
+        return out
+
+    def normals(self, n):
+        """cloud_normals_ of the last localize / sweep call: (n, 3) float64, zero where no normal was computed"""
+        out = np.zeros((int(n), 3), np.float64)
+        _check(lib().ag_get_normals(self.h, out.ctypes.data_as(C.POINTER(C.c_double)), int(n)))
         return out
 
     # ---- stages

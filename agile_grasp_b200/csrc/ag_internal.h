@@ -122,9 +122,9 @@ struct Ctx {
   unsigned long long g_tick = 0, state_gen = 0;
   int n_graph_replays = 0;
   bool capturing = false;  // the stream is being captured: timing events must be recorded as external events
-  // non-deterministic normal mode: glibc rand() stream, per-sample stream offsets ([0] = carry), bound on the
+  // non-deterministic normal mode: glibc rand() stream, per-sample stream offsets, the carry across launches, bound on the
   // number of samples that may already have consumed draws in the current call
-  DevBuf rand_raw, rand_off;
+  DevBuf rand_raw, rand_off, rand_carry;
   size_t rand_count = 0;
   int rand_consumed_bound = 0;
   DevBuf nbr_heads;  // per sample of the chunk: sample xyz + neighbour count (float4)
@@ -136,6 +136,8 @@ struct Ctx {
   DevBuf handle_in, handle_bits;  // ag_find_handles: grasp records and the n x n inlier bit matrix
   int n_hyp = 0;
   bool images_valid = false;
+  unsigned serial = 0, call_gen = 0;  // context number and call counter behind the record stamp
+  uint8_t stamp = 0;                  // ag_grasp.reserved of every record of the last localize / sweep call
   unsigned sweep_flags = 0;          // arguments of the last hand_sweep_enqueue (for the overflow re-run)
   const int* sweep_indices = nullptr;
   const ag_frame* sweep_frames = nullptr;

@@ -21,6 +21,16 @@ void set_error(const std::string& msg) { g_error = msg; }
 // while the generation it was captured under is current
 std::atomic<unsigned long long> g_alloc_gen{0};
 
+// Every list of hypotheses is stamped (ag_grasp.reserved) with a non-zero byte derived from the context and its
+// call counter, so that ag_classify can tell records of the resident grasp images from records of an earlier
+// call, another context or a batch lane (their image_id would silently address unrelated images).
+static std::atomic<unsigned> g_ctx_serial{0};
+uint8_t next_stamp(Ctx* c) {
+  c->call_gen++;
+  c->stamp = uint8_t(1u + (c->serial * 151u + c->call_gen) % 255u);
+  return c->stamp;
+}
+
 int DevBuf::reserve(size_t bytes) {
   if (bytes <= cap) return 0;
   g_alloc_gen++;
@@ -96,11 +106,13 @@ __global__ void k_iota(int* out, int n) {
   if (i < n) out[i] = i;
 }
 
-__global__ void k_gather_grasps(const ag_grasp* __restrict__ raw, const int* __restrict__ slots, int n, ag_grasp* out) {
+__global__ void k_gather_grasps(const ag_grasp* __restrict__ raw, const int* __restrict__ slots, int n, ag_grasp* out,
+                                uint8_t stamp) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   ag_grasp gr = raw[slots[i]];
   gr.image_id = i;
+  gr.reserved = stamp;
   out[i] = gr;
 }
 
@@ -128,7 +140,7 @@ constexpr int kSlotHeaderBytes = 32;
 __global__ void k_export(const ag_grasp* __restrict__ raw, const int* __restrict__ slots, const int* __restrict__ n_sel,
                          const float* __restrict__ scores, const RowIndex* ri, const int* overflow,
                          const unsigned long long* counters, HostOut* hdr, ag_grasp* out_host, ag_grasp* out_dev,
-                         int* exp_hdr, ag_grasp* out_exp, int cap, int cap_exp, PeerOut peer) {
+                         int* exp_hdr, ag_grasp* out_exp, int cap, int cap_exp, PeerOut peer, unsigned stamp) {
   // a record is 10 x 16 bytes: three records per warp pass, every lane moves one uint4 (coalesced
   // 480-byte stores — the mapped host destination is written over PCIe and needs full-width writes)
   static_assert(sizeof(ag_grasp) == 160, "record layout");
@@ -143,6 +155,7 @@ __global__ void k_export(const ag_grasp* __restrict__ raw, const int* __restrict
     if (part == 8 && scores) v.x = __float_as_uint(scores[i]);            // byte 128: score
     if (part == 9) {
       v.z = uint32_t(i);                                                   // byte 152: image_id
+      v.w = (v.w & 0x00FFFFFFu) | (stamp << 24);                           // byte 159: call stamp
       if (scores) {                                                        // byte 158: label (+1 <=> sum <= 0)
         const uint32_t label = scores[i] > 0.f ? 0u : 1u;
         v.w = (v.w & 0xFF00FFFFu) | (label << 16);
@@ -350,13 +363,14 @@ static void launch_export(Ctx* c, const PeerOut& peer) {
   k_export<<<32, 256, 0, c->stream>>>(c->grasps_raw.as<ag_grasp>(), c->hyp_slots.as<int>(), c->pend_nsel,
                                       c->attached_svm ? c->scores.as<float>() : nullptr, c->row_index.as<RowIndex>(),
                                       hand_sweep_overflow_ptr(c), c->counters.as<unsigned long long>(), hdr, recs,
-                                      c->grasps.as<ag_grasp>(), exp_hdr, exp_recs, int(size_t(c->pend_S) * 8), cap_exp, peer);
+                                      c->grasps.as<ag_grasp>(), exp_hdr, exp_recs, int(size_t(c->pend_S) * 8), cap_exp, peer, c->stamp);
 }
 
 // First half of a localize call: everything is enqueued on the context's stream, nothing is waited for.
 static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, int size_left, const int* indices,
                           int n_indices, unsigned flags) {
   c->pend_active = false;
+  next_stamp(c);
   std::memset(&c->timings, 0, sizeof(c->timings));
   c->timings.n_in = n_in;
   c->images_valid = false;
@@ -660,6 +674,7 @@ ag_ctx* ag_create(int device) {
   ag_ctx* h = new ag_ctx;
   Ctx& c = h->c;
   c.device = device;
+  c.serial = ++g_ctx_serial;
   if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess) {
     set_error("cudaStreamCreate failed");
     delete h;
@@ -686,7 +701,7 @@ void ag_destroy(ag_ctx* h) {
   if (c.h_out) cudaFreeHost(c.h_out);
   for (DevBuf* b : {&c.raw, &c.keys, &c.keys_sorted, &c.keys_unique, &c.cub_tmp, &c.block_counts, &c.misc, &c.vox,
                     &c.row_ptr, &c.col_ptr, &c.row_index, &c.all_frames,
-                    &c.normals, &c.samples, &c.sample_stage, &c.moments, &c.frames, &c.nn_counts, &c.nbr_pool, &c.nbr_heads, &c.rand_raw, &c.rand_off, &c.grasps_raw, &c.valid,
+                    &c.normals, &c.samples, &c.sample_stage, &c.moments, &c.frames, &c.nn_counts, &c.nbr_pool, &c.nbr_heads, &c.rand_raw, &c.rand_off, &c.rand_carry, &c.grasps_raw, &c.valid,
                     &c.images_raw, &c.hyp_slots, &c.grasps, &c.counters, &c.scores, &c.descriptors, &c.kvals, &c.handle_in, &c.handle_bits, &c.sweep_dbg, &c.overflow})
     b->release();
   if (c.h_pinned) cudaFreeHost(c.h_pinned);
@@ -795,8 +810,10 @@ int ag_classify(ag_ctx* h, const ag_svm* svm, ag_grasp* grasps, int n, uint8_t* 
   bool identity = n == c.n_hyp;
   for (int i = 0; i < n; i++) {
     const int id = grasps[i].image_id;
-    if (id < 0 || id >= c.n_hyp) {
-      set_error("ag_classify: image_id does not belong to the last localize call");
+    if (id < 0 || id >= c.n_hyp || grasps[i].reserved != c.stamp) {
+      set_error("ag_classify: hypothesis does not belong to the last ag_localize / ag_hand_sweep call on this context "
+                "(records of an earlier call, another context or a batch lane cannot be scored: their grasp images "
+                "are no longer resident)");
       return AG_ERR_INVALID;
     }
     identity = identity && id == i;
@@ -1067,6 +1084,19 @@ int ag_get_points(ag_ctx* h, int image_id, double** pts3xm, int32_t** cam, int* 
   return AG_OK;
 }
 
+int ag_get_normals(ag_ctx* h, double* normals3n, int n) {
+  if (!h || !normals3n || n < 0) return AG_ERR_INVALID;
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  if (n > c.n_vox || c.normals.cap < size_t(n) * 24) {
+    set_error("ag_get_normals: n exceeds the voxelised cloud of the last call");
+    return AG_ERR_INVALID;
+  }
+  if (n > 0) AG_CUDA_CHECK(cudaMemcpyAsync(normals3n, c.normals.p, size_t(n) * 24, cudaMemcpyDeviceToHost, c.stream));
+  AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  return AG_OK;
+}
+
 int ag_get_images(ag_ctx* h, uint32_t** bits, int* n_images) {
   Ctx& c = h->c;
   cudaSetDevice(c.device);
@@ -1222,6 +1252,7 @@ int ag_hand_sweep(ag_ctx* h, const int* indices, int n_indices, const ag_frame* 
       set_error("sample index out of range");
       return AG_ERR_INVALID;
     }
+  next_stamp(&c);
   if (c.samples.reserve(size_t(n_indices) * 4) || c.frames.reserve(size_t(n_indices) * sizeof(ag_frame)) ||
       c.counters.reserve(64))
     return AG_ERR_CUDA;
@@ -1245,7 +1276,7 @@ int ag_hand_sweep(ag_ctx* h, const int* indices, int n_indices, const ag_frame* 
   ag_grasp* res = static_cast<ag_grasp*>(std::malloc(std::max<size_t>(1, size_t(Hn)) * sizeof(ag_grasp)));
   if (Hn > 0) {
     k_gather_grasps<<<(Hn + 127) / 128, 128, 0, c.stream>>>(c.grasps_raw.as<ag_grasp>(), c.hyp_slots.as<int>(), Hn,
-                                                           c.grasps.as<ag_grasp>());
+                                                           c.grasps.as<ag_grasp>(), c.stamp);
     AG_CUDA_CHECK(cudaMemcpyAsync(res, c.grasps.p, size_t(Hn) * sizeof(ag_grasp), cudaMemcpyDeviceToHost, c.stream));
     AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
   }

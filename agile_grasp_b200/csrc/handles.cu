@@ -181,6 +181,9 @@ int ag_find_handles(ag_ctx* h, const ag_grasp* hands, int n, int min_inliers, do
           break;
         }
       if (int(inl.size()) < min_inliers) continue;
+      // an empty list (cut at position 0, or a NaN axis that is not its own inlier) yields max - min < 0 in the
+      // reference and no handle; it must not reach back() / front() when min_inliers <= 0
+      if (inl.empty()) continue;
       if (!(inl.back().d - inl.front().d > min_length)) continue;  // sorted: max - min (:58-72)
       // Handle (handle.cpp:3-73)
       ag_handle H;

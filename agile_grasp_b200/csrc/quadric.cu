@@ -1083,8 +1083,9 @@ static int ball_stride(double radius, double voxel, bool two_cams) {
 int quadric_rand_reset(Ctx* c) {
   c->rand_consumed_bound = 0;
   if (c->params.deterministic_normals != 0) return AG_OK;
-  if (c->rand_off.reserve(64)) return AG_ERR_CUDA;
-  AG_CUDA_CHECK(cudaMemsetAsync(c->rand_off.p, 0, 16, c->stream));
+  // the carry lives in its own buffer: rand_off is re-sized per launch (DevBuf::reserve does not keep contents)
+  if (c->rand_carry.reserve(16)) return AG_ERR_CUDA;
+  AG_CUDA_CHECK(cudaMemsetAsync(c->rand_carry.p, 0, 16, c->stream));
   return AG_OK;
 }
 
@@ -1132,9 +1133,9 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
       AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
       c->rand_count = hs.size();
     }
-    if (c->rand_off.reserve(size_t(n) * 4 + 16)) return AG_ERR_CUDA;
+    if (c->rand_off.reserve(size_t(n) * 4 + 16) || c->rand_carry.reserve(16)) return AG_ERR_CUDA;
     d_rand = c->rand_raw.as<uint32_t>();
-    d_rand_off = c->rand_off.as<int>() + 4;  // [0] = carry across launches, offsets from [4]
+    d_rand_off = c->rand_off.as<int>();
     c->rand_consumed_bound += n;
   }
   for (int s0 = 0; s0 < n; s0 += chunk) {
@@ -1167,7 +1168,7 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
     }
     if (timed) record_event(c, c->ev_k[2]);
     if (rand_mode) {
-      k_rand_offsets<<<1, 1024, 0, c->stream>>>(c->nn_counts.as<int2>(), s0, m, d_count, d_rand_off, c->rand_off.as<int>());
+      k_rand_offsets<<<1, 1024, 0, c->stream>>>(c->nn_counts.as<int2>(), s0, m, d_count, d_rand_off, c->rand_carry.as<int>());
       c->launches += 1;
     }
     k_taubin_axes<<<blocks, kWarps * 32, smem, c->stream>>>(

@@ -108,7 +108,8 @@ typedef struct ag_grasp {
   uint8_t half_antipodal;
   uint8_t full_antipodal;
   uint8_t label;          /* 1 if the SVM says antipodal (kept by classify) */
-  uint8_t reserved;
+  uint8_t reserved;       /* call stamp (non-zero): ties the record to the ag_localize / ag_hand_sweep call whose
+                             grasp images image_id addresses; ag_classify rejects records of any other call */
 } ag_grasp;
 
 /* Per-sample local frame = the outputs of Quadric that are used downstream. */
@@ -239,6 +240,9 @@ int ag_find_handles(ag_ctx* ctx, const ag_grasp* hands, int n, int min_inliers, 
  * camera source of each column. */
 int ag_get_points(ag_ctx* ctx, int image_id, double** pts3xm, int32_t** cam, int* m);
 int ag_get_images(ag_ctx* ctx, uint32_t** bits, int* n_images);   /* AG_IMAGE_WORDS per image */
+/* cloud_normals_ (hand_search.cpp:13-26,102) as the last ag_localize / ag_hand_sweep left it: 3 doubles for each
+ * of the first n voxels (n <= voxel count); zero where no normal was computed. */
+int ag_get_normals(ag_ctx* ctx, double* normals3n, int n);
 
 /* ---- stage-level entry points (used by the parity tests and by callers that want one stage) */
 

@@ -62,12 +62,12 @@ struct Reader {
 inline bool read_cloud(Reader& r, PointCloud2& m) {
   uint32_t nf = 0, nd = 0;
   if (!r.get(&m.seq, 4) || !r.get(&m.stamp_sec, 4) || !r.get(&m.stamp_nsec, 4) || !r.str(m.frame_id)) return false;
-  if (!r.get(&m.height, 4) || !r.get(&m.width, 4) || !r.get(&nf, 4) || nf > 1024) return false;
+  if (!r.get(&m.height, 4) || !r.get(&m.width, 4) || !r.get(&nf, 4) || nf > 1024 || size_t(nf) * 13 > r.n - r.pos) return false;
   m.fields.resize(nf);
   for (PointField& f : m.fields)
     if (!r.str(f.name) || !r.get(&f.offset, 4) || !r.get(&f.datatype, 1) || !r.get(&f.count, 4)) return false;
   if (!r.get(&m.is_bigendian, 1) || !r.get(&m.point_step, 4) || !r.get(&m.row_step, 4) || !r.get(&nd, 4)) return false;
-  if (r.pos + nd > r.n) return false;
+  if (nd > r.n - r.pos) return false;
   m.data.assign(r.p + r.pos, r.p + r.pos + nd);
   r.pos += nd;
   return r.get(&m.is_dense, 1);
@@ -98,7 +98,8 @@ inline bool deserialize(const std::vector<uint8_t>& wire, CloudSized& msg) {
 
 /** pcl::fromROSMsg for PointXYZRGBA (grasp_localizer.cpp:55-58,73): x, y, z by field name (any numeric
  *  datatype), rgb / rgba as the packed 32-bit word; missing colour stays 0.  Returns false if x/y/z are
- *  missing, the message is big endian or data is shorter than height * row_step. */
+ *  missing, the message is big endian, a used field does not fit inside point_step (offset / datatype), row_step is
+ *  shorter than width * point_step, or data is shorter than height * row_step. */
 inline bool fromROSMsg(const PointCloud2& msg, pcl::PointCloud<pcl::PointXYZRGBA>& cloud) {
   const PointField *fx = nullptr, *fy = nullptr, *fz = nullptr, *fc = nullptr;
   for (const PointField& f : msg.fields) {
@@ -109,8 +110,17 @@ inline bool fromROSMsg(const PointCloud2& msg, pcl::PointCloud<pcl::PointXYZRGBA
   }
   const size_t n = size_t(msg.width) * msg.height;
   if (!fx || !fy || !fz || msg.is_bigendian || msg.point_step == 0) return false;
+  // the message is external input: every field that is read must lie inside a point record, every record inside
+  // its row, every row inside data (a hostile offset / row_step must not turn into an out-of-bounds read)
+  static const uint32_t kTypeSize[9] = {0, 1, 1, 2, 2, 4, 4, 4, 8};
+  for (const PointField* f : {fx, fy, fz}) {
+    if (f->datatype < 1 || f->datatype > 8) return false;
+    if (uint64_t(f->offset) + kTypeSize[f->datatype] > msg.point_step) return false;
+  }
+  if (fc && uint64_t(fc->offset) + 4 > msg.point_step) return false;
   const size_t row_step = msg.row_step ? msg.row_step : size_t(msg.point_step) * msg.width;
-  if (msg.data.size() < size_t(msg.height) * row_step) return false;
+  if (row_step < size_t(msg.point_step) * msg.width) return false;
+  if (msg.height != 0 && row_step > msg.data.size() / msg.height) return false;  // height * row_step <= size, no overflow
   cloud.points.resize(n);
   cloud.width = msg.width;
   cloud.height = msg.height;

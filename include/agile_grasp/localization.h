@@ -176,8 +176,10 @@ class Localization {
     }
     for (size_t i = 0; i < recs.size(); i++)
       if (keep[i]) {
-        GraspHypothesis g(recs[i]);
-        g.setFullAntipodal(true);  // learning.cpp:236-243
+        GraspHypothesis g(hand_list[i]);  // the caller's hypothesis (points_for_learning included) ...
+        g.record().score = recs[i].score;
+        g.record().label = recs[i].label;
+        g.setFullAntipodal(true);  // ... marked as learning.cpp:236-243 does
         antipodal_hands.push_back(g);
       }
     std::cout << " " << antipodal_hands.size() << " antipodal grasps found.\n";

@@ -636,15 +636,39 @@ struct GlibcRand {
 
 int fit_quadrics(const float* xyz, const int32_t* cam, int n, const Tree* tree, const int* indices, int S,
                  double radius, const ag_params& P, int sum_perm, ag_frame* frames, double* params_out,
-                 double* MN_out, double* eig_out) {
+                 double* MN_out, double* eig_out, size_t* rand_consumed) {
   const double cam_origin[2][3] = {{P.cam_tf_left[3], P.cam_tf_left[7], P.cam_tf_left[11]},
                                    {P.cam_tf_right[3], P.cam_tf_right[7], P.cam_tf_right[11]}};
-  int threads = std::max(1, P.num_threads);
+  const int threads = std::max(1, P.num_threads);
   // production mode of the reference (is_deterministic = false, hand_search.h:84): normals from 50 neighbours
-  // drawn with rand() % n; reproducible only single-threaded, in sample order, from the unseeded state
+  // drawn with rand() % n (quadric.cpp:177-192).  The pinned stream is the one a single-threaded, never-seeded
+  // process sees: 50 draws per sample with more than 50 neighbours, consumed in sample order.  The draws do not
+  // depend on the fit, so the stream is laid out up front — a first parallel pass finds the
+  // neighbour lists, a prefix count gives every sample its slice of the stream — and the samples are then
+  // fitted on all threads with results identical to the serial walk.
   const bool rand_mode = P.deterministic_normals == 0;
-  GlibcRand rng(1);
-  if (rand_mode) threads = 1;
+  std::vector<std::vector<std::pair<float, int>>> res_all;
+  std::vector<uint32_t> stream;
+  std::vector<size_t> stream_off;
+  if (rand_mode) {
+    res_all.resize(S);
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 8)
+    for (int s = 0; s < S; s++) radius_search(tree, xyz, n, xyz + 3 * indices[s], radius, tree ? 1 : 0, res_all[s]);
+    stream_off.resize(S);
+    size_t used = 0;
+    for (int s = 0; s < S; s++) {
+      stream_off[s] = used;
+      if (res_all[s].size() > 50) used += 50;
+    }
+    // rand() is process state: a second fit of the same localizeHands call (all-points pass, then the samples:
+    // hand_search.cpp:17-26 then :77) continues where the first one stopped
+    GlibcRand rng(1);
+    const size_t skip = rand_consumed ? *rand_consumed : 0;
+    for (size_t k = 0; k < skip; k++) rng.next();
+    stream.resize(used);
+    for (size_t k = 0; k < used; k++) stream[k] = rng.next();
+    if (rand_consumed) *rand_consumed = skip + used;
+  }
   int err = 0;
   std::string errmsg;
   // hand_search.cpp:77-80 omp parallel for over samples
@@ -652,7 +676,8 @@ int fit_quadrics(const float* xyz, const int32_t* cam, int n, const Tree* tree, 
   for (int s = 0; s < S; s++) {
     std::vector<std::pair<float, int>> res;
     const float* q = xyz + 3 * indices[s];
-    radius_search(tree, xyz, n, q, radius, tree ? 1 : 0, res);  // hand_search.cpp:85
+    if (rand_mode) res.swap(res_all[s]);
+    else radius_search(tree, xyz, n, q, radius, tree ? 1 : 0, res);  // hand_search.cpp:85
     std::vector<int> nn(res.size());
     for (size_t t = 0; t < res.size(); t++) nn[t] = res[t].second;
     ag_frame F;
@@ -682,7 +707,7 @@ int fit_quadrics(const float* xyz, const int32_t* cam, int n, const Tree* tree, 
         std::vector<int> pick_nn(50);
         std::vector<double> pick_xyz(150);
         for (int t = 0; t < 50; t++) {
-          const int r = int(rng.next() % uint32_t(nn.size()));
+          const int r = int(stream[stream_off[s] + t] % uint32_t(nn.size()));
           pick_nn[t] = nn[r];
           for (int d = 0; d < 3; d++) pick_xyz[3 * t + d] = coords[3 * r + d];
         }

@@ -27,7 +27,7 @@ Hands* find_hands(const float* xyz, const int32_t* cam, int n, const Tree* tree,
                   const ag_frame* frames, const int32_t* sample_cam, const double* cloud_normals, const ag_params& P);
 int fit_quadrics(const float* xyz, const int32_t* cam, int n, const Tree* tree, const int* indices, int S,
                  double radius, const ag_params& P, int sum_perm, ag_frame* frames, double* params_out,
-                 double* MN_out, double* eig_out);
+                 double* MN_out, double* eig_out, size_t* rand_consumed = nullptr);
 void filter_hands(const ag_grasp* g, int n, const ag_params& P, uint8_t* keep);
 int draw_samples(int n, int S, uint64_t seed, int32_t* out);
 const Tree* tree_of(const ago_tree* t);

@@ -519,12 +519,13 @@ ago_hands* ago_localize(const void* points, int stride, int n_in, int size_left,
   tm[1] = ms(t1, t2);
   const Tree* T = tree_of(tree);
   std::vector<double> normals(size_t(3) * n, 0.0);       // hand_search.cpp:13-14
+  size_t rand_consumed = 0;  // rand() draws of the production normal mode so far in this call
   if (flags & AG_FLAG_CALC_ANTIPODAL) {                  // hand_search.cpp:17-26
     std::vector<int> all(n);
     for (int i = 0; i < n; i++) all[i] = i;
     std::vector<ag_frame> fr(n);
     if (fit_quadrics(xyz.data(), cam.data(), n, T, all.data(), n, P->nn_radius_normals, *P, 0, fr.data(), nullptr,
-                     nullptr, nullptr) != 0) {
+                     nullptr, nullptr, &rand_consumed) != 0) {
       ago_tree_free(tree);
       return nullptr;
     }
@@ -551,7 +552,7 @@ ago_hands* ago_localize(const void* points, int stride, int n_in, int size_left,
   for (int i = 0; i < S; i++) scam[i] = cam[idx[i]];  // hand_search.cpp:40-42 (+ App. B#3)
   std::vector<ag_frame> frames(S);
   if (fit_quadrics(xyz.data(), cam.data(), n, T, idx.data(), S, P->nn_radius_taubin, *P, 0, frames.data(), nullptr,
-                   nullptr, nullptr) != 0) {
+                   nullptr, nullptr, &rand_consumed) != 0) {
     ago_tree_free(tree);
     return nullptr;
   }

@@ -44,3 +44,16 @@ def two_view_scene(oracle):
     tree = oracle.Tree(xyz)
     idx = oracle.draw_samples(len(xyz), S, P.seed)
     return dict(pts=pts, size_left=size_left, P=P, xyz=xyz, cam=cam, tree=tree, idx=idx)
+
+
+@pytest.fixture(scope="session")
+def poly_svm_paths(tmp_path_factory):
+    """the reference's two shipped POLY-kernel model files (committed xz-compressed: 11 / 25 MB of YAML text)"""
+    import lzma
+    d = tmp_path_factory.mktemp("poly_svm")
+    out = {}
+    for name in ("svm_032015_20_20_same", "svm_032015_20_20"):
+        p = d / name
+        p.write_bytes(lzma.open(os.path.join(ROOT, "tests", "golden", name + ".xz")).read())
+        out[name] = str(p)
+    return out

@@ -93,6 +93,30 @@ int main(int argc, char** argv) {
     CHECK(agile_grasp::fromROSMsg(cs.cloud, cloud));
     CHECK(cloud.size() == 6 && cloud.points[5].x == 5.0f && cloud.points[5].y == 5.5f && cloud.points[2].z == 3.0f);
     CHECK(cloud.points[4].rgba == 0x00102034u && cloud.width == 3 && cloud.height == 2);
+    {  // malformed / hostile messages are rejected instead of read out of bounds
+      agile_grasp::PointCloud2 bad = cs.cloud;
+      bad.fields[0].offset = 30;  // x would straddle the end of the 32-byte record
+      CHECK(!agile_grasp::fromROSMsg(bad, cloud));
+      bad = cs.cloud;
+      bad.fields[1].offset = 0xFFFFFFF0u;
+      CHECK(!agile_grasp::fromROSMsg(bad, cloud));
+      bad = cs.cloud;
+      bad.fields[2].datatype = 9;
+      CHECK(!agile_grasp::fromROSMsg(bad, cloud));
+      bad = cs.cloud;
+      bad.fields[3].offset = 29;  // rgb word past the record
+      CHECK(!agile_grasp::fromROSMsg(bad, cloud));
+      bad = cs.cloud;
+      bad.row_step = 16;  // shorter than width * point_step
+      CHECK(!agile_grasp::fromROSMsg(bad, cloud));
+      bad = cs.cloud;
+      bad.height = 3;  // more rows than data
+      CHECK(!agile_grasp::fromROSMsg(bad, cloud));
+      bad = cs.cloud;
+      bad.row_step = 0xFFFFFFFFu;
+      CHECK(!agile_grasp::fromROSMsg(bad, cloud));
+      CHECK(agile_grasp::fromROSMsg(cs.cloud, cloud));
+    }
     w.resize(w.size() - 9);  // a bare PointCloud2 ends after is_dense... and a truncated one is rejected
     agile_grasp::PointCloud2 pc2;
     w.push_back(1);

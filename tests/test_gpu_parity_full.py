@@ -1,0 +1,309 @@
+"""Full-size parity of the CUDA path against the CPU oracle (-m gpu; run on the B200 box).
+
+tests/test_gpu_parity.py checks every stage bit-exactly on shared inputs at small sizes.  This file checks the
+WHOLE call — ag_localize + ag_classify on its own frames — at the BASELINE.json sizes (configs 1, 2, 3 and a
+2000-sample share of config 5) in both normal modes, the calculates_antipodal path end to end, the boundary
+filter against the oracle's filterHands, and the reference's shipped POLY models against cv2.
+
+Two oracles are used for the end-to-end comparison:
+  (a) the reference arithmetic (uncentred 10x10 pencil through LAPACK dggev_): the only non-bit-exact stage.
+      dggev_'s own noise flips a few borderline slab / slot decisions, so the comparison is
+      statistical, with thresholds just under what is measured;
+  (b) the same oracle with the eigen-solve replaced by its extended-precision solve (sum_perm = -1): the CUDA
+      path solves the same fit to <= 1e-9 of that, so there the lists must agree essentially everywhere.
+"""
+import copy
+import os
+
+import numpy as np
+import pytest
+
+from agile_grasp_b200 import api, scenes
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def _u32(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def _u64(a):
+    return np.ascontiguousarray(a).view(np.uint64)
+
+
+def _match(ga, gb):
+    ka = {(a, b): i for i, (a, b) in enumerate(zip(ga["sample_index"].tolist(), ga["orientation"].tolist()))}
+    kb = {(a, b): i for i, (a, b) in enumerate(zip(gb["sample_index"].tolist(), gb["orientation"].tolist()))}
+    common = sorted(set(ka) & set(kb))
+    return np.array([ka[k] for k in common], dtype=int), np.array([kb[k] for k in common], dtype=int)
+
+
+# config, deterministic_normals, stride through the drawn samples
+CASES = [(1, 1, 1), (2, 1, 1), (2, 0, 1), (3, 1, 1), (3, 0, 1), (5, 1, 10)]
+
+
+@pytest.mark.parametrize("config,det,stride", CASES)
+def test_full_size_end_to_end_vs_oracle(ctx, oracle, config, det, stride, linear_svm_path):
+    O = oracle
+    pts, size_left, P, S = scenes.config_cloud(config)
+    P.deterministic_normals = det
+    P.num_threads = os.cpu_count() or 1
+    xo, co = O.preprocess(pts, size_left, P, False)
+    idx = O.draw_samples(len(xo), S, P.seed)[::stride]
+    ctx.set_params(P)
+    ctx.set_svm(None)
+    try:
+        xyz, cam = ctx.preprocess(pts, size_left)
+        assert (_u32(xyz) == _u32(xo)).all() and (cam == co).all()  # voxelised cloud: bit identical
+        g = ctx.localize(pts, size_left, idx)
+        gg, keep = ctx.classify(api.Svm(linear_svm_path), g)
+        assert ctx.timings()["n_voxels"] == len(xo)
+        # ---- frames
+        tree = O.Tree(xo)
+        fo = O.fit_quadrics(tree, co, idx, 0.03, P)["frames"]
+        fx = O.fit_quadrics(tree, co, idx, 0.03, P, sum_perm=-1)["frames"]
+        fg = ctx.fit_quadrics(idx, 0.03)
+        assert np.array_equal(fg["num_neighbors"], fo["num_neighbors"])  # neighbour counts: identical
+        assert np.array_equal(fg["majority_cam"], fo["majority_cam"])
+        det10 = fo["num_neighbors"] >= 10
+        d_ex = np.linalg.norm(fg["normal"] - fx["normal"], axis=1)
+        assert d_ex[det10].max() <= 1e-9, d_ex[det10].max()
+        d_ref = np.linalg.norm(fg["normal"] - fo["normal"], axis=1)
+        d_own = np.linalg.norm(fo["normal"] - fx["normal"], axis=1)  # dggev's own distance from exact
+        assert (d_ref[det10] <= 1e-5).mean() >= 0.96, (d_ref[det10] <= 1e-5).mean()
+        far = (d_ref > 1e-5) & det10
+        assert (d_own[far] > 0.5e-5).all()  # wherever the CUDA path is off the reference, the reference is off exact
+        # ---- (a) end to end against the reference arithmetic
+        H, tm, nv = O.localize(pts, size_left, P, idx, 0, O.Svm(linear_svm_path), False)
+        go = H.grasps
+        ig, io = _match(gg, go)
+        assert len(ig) >= 0.995 * max(len(gg), len(go)), (len(ig), len(gg), len(go))
+        assert np.array_equal(gg["half_antipodal"][ig], go["half_antipodal"][io])
+        assert np.array_equal(gg["full_antipodal"][ig], go["full_antipodal"][io])
+        assert np.array_equal(gg["cam_source"][ig], go["cam_source"][io])
+        assert (gg["label"][ig] == go["label"][io]).mean() >= 0.995
+        assert (gg["num_points"][ig] == go["num_points"][io]).mean() >= 0.975
+        rel = np.abs(gg["score"][ig] - go["score"][io]) / np.maximum(1.0, np.abs(go["score"][io]))
+        assert (rel <= 1e-5).mean() >= 0.95, (rel <= 1e-5).mean()
+        assert np.median(np.linalg.norm(gg["approach"][ig] - go["approach"][io], axis=1)) <= 1e-5
+        if P.filters_boundaries:  # config 1: the filtered list is the oracle's filtered list
+            assert O.filter_hands(gg, P).all()
+        # ---- (b) against the oracle with the extended-precision eigen-solve: the same lists
+        normals = np.zeros((len(xo), 3))
+        normals[idx] = fx["normal"]  # hand_search.cpp:102 (App. B#11)
+        Hx = O.find_hands(tree, co, idx, fx, co[idx], normals, P)
+        keep_x = Hx.classify(O.Svm(linear_svm_path), P)
+        gx = Hx.grasps
+        if P.filters_boundaries:
+            kf = O.filter_hands(gx, P).astype(bool)
+            gx, keep_x = gx[kf], keep_x[kf]
+        ig, ix = _match(gg, gx)
+        assert len(ig) >= 0.999 * max(len(gg), len(gx)), (len(ig), len(gg), len(gx))
+        same = gg["num_points"][ig] == gx["num_points"][ix]
+        assert same.mean() >= 0.998, same.mean()
+        assert (keep[ig] == keep_x[ix]).mean() >= 0.999
+        for nm in ("bottom", "surface", "approach", "binormal"):
+            assert np.abs(gg[nm][ig] - gx[nm][ix]).max() <= 1e-8, nm
+        assert np.array_equal(gg["width"][ig][same], gx["width"][ix][same]) or \
+            np.abs(gg["width"][ig] - gx["width"][ix])[same].max() <= 1e-9
+        rel = np.abs(gg["score"][ig] - gx["score"][ix]) / np.maximum(1.0, np.abs(gx["score"][ix]))
+        assert (rel <= 1e-5).mean() >= 0.998, (rel <= 1e-5).mean()
+    finally:
+        P.deterministic_normals = 1
+        ctx.set_params(P)
+
+
+@pytest.mark.parametrize("which", ["small", "config1"])
+def test_calculates_antipodal_end_to_end(ctx, oracle, small_scene, which, linear_svm_path):
+    """ag_localize(..., AG_FLAG_CALC_ANTIPODAL) = localizeHands(calculates_antipodal = true): normals for ALL points
+    with r = 0.01 (hand_search.cpp:17-26), the sampled points' normals then OVERWRITTEN by their r = 0.03 normals
+    (:102) before the hand loop reads them (:159) — SURVEY App. B#11."""
+    O = oracle
+    if which == "small":
+        s = small_scene
+        pts, size_left, P, idx = s["pts"], s["size_left"], copy.copy(s["P"]), s["idx"]
+        xo, co = s["xyz"], s["cam"]
+        tree = s["tree"]
+    else:
+        pts, size_left, P, S = scenes.config_cloud(1)
+        xo, co = O.preprocess(pts, size_left, P, False)
+        idx = O.draw_samples(len(xo), S, P.seed)
+        tree = O.Tree(xo)
+    P.num_threads = os.cpu_count() or 1
+    ctx.set_params(P)
+    ctx.set_svm(None)
+    g = ctx.localize(pts, size_left, idx, flags=1)
+    t = ctx.timings()
+    assert t["n_voxels"] == len(xo) and t["normals_all_ms"] > 0
+    Ng = ctx.normals(len(xo))
+    # a run without the flag differs: there only the sampled points carry normals
+    g0 = ctx.localize(pts, size_left, idx, flags=0)
+    N0 = ctx.normals(len(xo))
+    is_sample = np.zeros(len(xo), bool)
+    is_sample[idx] = True
+    assert (N0[~is_sample] == 0).all() and (N0[is_sample] != 0).any(1).mean() > 0.99
+    # (1) overwrite order: sampled points hold their r = 0.03 normal, bit for bit
+    assert (_u64(Ng[is_sample]) == _u64(N0[is_sample])).all()
+    fg = ctx.fit_quadrics(idx, 0.03)
+    assert (_u64(Ng[idx]) == _u64(fg["normal"])).all()
+    # (2) every other point holds its r = 0.01 normal: the stage-level call gives the same bits, and the
+    #     well-determined ones agree with the extended-precision oracle
+    rest = np.nonzero(~is_sample)[0][:: max(1, (len(xo) - len(idx)) // 3000)].astype(np.int32)
+    fa = ctx.fit_quadrics(rest, 0.01)
+    assert (_u64(Ng[rest]) == _u64(fa["normal"])).all()
+    ex = O.fit_quadrics(tree, co, rest, 0.01, P, sum_perm=-1)["frames"]
+    assert np.array_equal(fa["num_neighbors"], ex["num_neighbors"])
+    ok = (ex["num_neighbors"] >= 12) & np.isfinite(ex["normal"]).all(1) & np.isfinite(fa["normal"]).all(1)
+    assert np.median(np.linalg.norm(fa["normal"][ok] - ex["normal"][ok], axis=1)) <= 1e-6
+    # (3) the hand loop on exactly these frames and normals: the oracle gives the same list, flags included
+    H = O.find_hands(tree, co, idx, fg, co[idx], np.nan_to_num(Ng), P)
+    go = H.grasps
+    if P.filters_boundaries:
+        go = go[O.filter_hands(go, P).astype(bool)]
+    assert len(g) == len(go) and len(g) > 0
+    for nm in ("sample_index", "orientation", "cam_source", "num_points", "half_antipodal", "full_antipodal"):
+        assert np.array_equal(g[nm], go[nm]), nm
+    for nm in ("approach", "binormal", "bottom", "surface", "width"):
+        assert (_u64(g[nm]) == _u64(go[nm])).all(), nm
+    assert g["half_antipodal"].sum() > 0 and g["full_antipodal"].sum() > 0  # the flags are exercised
+    assert g["half_antipodal"].sum() > g0["half_antipodal"].sum()
+    # (4) against the reference arithmetic end to end (all-points normals through dggev_, which is a median 3e-3
+    #     off the exact solve on the tiny r = 0.01 neighbourhoods): same hypotheses, flags equal on nearly all
+    Hr, tm, nv = O.localize(pts, size_left, P, idx, 1, None, False)
+    gr = Hr.grasps
+    ig, ir = _match(g, gr)
+    assert len(ig) >= 0.99 * max(len(g), len(gr))
+    eq = (g["half_antipodal"][ig] == gr["half_antipodal"][ir]) & (g["full_antipodal"][ig] == gr["full_antipodal"][ir])
+    assert eq.mean() >= 0.97, eq.mean()
+
+
+def test_boundary_filter_matches_oracle_filter_hands(ctx, oracle, small_scene):
+    """Localization::filterHands (localization.cpp:364-388) inside the sweep (flags = 0x100) against the oracle's
+    ago_filter_hands on the unfiltered oracle list: a workspace whose faces cut through the scene."""
+    O = oracle
+    s = small_scene
+    frames = O.fit_quadrics(s["tree"], s["cam"], s["idx"], 0.03, s["P"])["frames"]
+    normals = np.zeros((len(s["xyz"]), 3))
+    normals[s["idx"]] = frames["normal"]
+    lo, hi = s["xyz"].min(0), s["xyz"].max(0)
+    mid = 0.5 * (lo + hi)
+    tried = 0
+    for ws in ([lo[0] - 1, mid[0], lo[1] - 1, hi[1] + 1, lo[2] - 1, hi[2] + 1],
+               [lo[0] - 1, hi[0] + 1, mid[1] - 0.05, hi[1] + 1, lo[2] - 1, hi[2] + 1],
+               [lo[0] + 0.05, hi[0] - 0.05, lo[1] + 0.05, hi[1] - 0.05, lo[2] + 0.01, hi[2] + 1]):
+        P = copy.copy(s["P"])
+        P.workspace[:] = [float(v) for v in ws]
+        P.filters_boundaries = 1
+        ctx.set_params(P)
+        ctx.set_cloud(s["xyz"], s["cam"])
+        H = O.find_hands(s["tree"], s["cam"], s["idx"], frames, s["cam"][s["idx"]], normals, P)
+        go = H.grasps
+        keep = O.filter_hands(go, P).astype(bool)
+        g_all = ctx.hand_sweep(s["idx"], frames, normals, flags=0)
+        g_f = ctx.hand_sweep(s["idx"], frames, normals, flags=0x100)
+        assert len(g_all) == len(go)
+        assert 0 < keep.sum() < len(go), (keep.sum(), len(go))  # the filter both keeps and drops
+        assert len(g_f) == keep.sum()
+        for nm in ("sample_index", "orientation", "num_points"):
+            assert np.array_equal(g_f[nm], go[nm][keep]), nm
+        for nm in ("approach", "bottom", "surface", "width"):
+            assert (_u64(g_f[nm]) == _u64(go[nm][keep])).all(), nm
+        tried += 1
+    assert tried == 3
+    ctx.set_params(s["P"])
+
+
+@pytest.mark.parametrize("name", ["svm_032015_20_20_same", "svm_032015_20_20"])
+def test_shipped_poly_models_bit_exact_vs_cv2(ctx, poly_svm_paths, name):
+    """The reference's shipped POLY models (588 / 1190 support vectors; the launch default,
+    launch/single_camera_grasps.launch:6) through ag_svm_load + the batched product: decision values equal
+    cv2.ml.SVM_load(model).predict(RAW_OUTPUT) (CvSVM::predict, learning.cpp:225) bit for bit on the cv2-made fixture."""
+    z = np.load(os.path.join(GOLD, "poly_svm_cv2.npz"))
+    svm = api.Svm(poly_svm_paths[name])
+    assert svm.kernel == 1 and svm.var_count == 3528 and svm.sv_total == (588 if name.endswith("same") else 1190)
+    scores, desc = ctx.hog_svm(svm, z["images_bits"], want_descriptors=True)
+    assert (_u32(desc) == _u32(z["descriptors"])).all()
+    assert (_u32(scores) == _u32(z["raw_" + name])).all()
+    scores2, _ = ctx.hog_svm(svm, z["images_bits"][:5])  # a partial tile, internal descriptor buffer
+    assert (_u32(scores2) == _u32(z["raw_" + name][:5])).all()
+
+
+def test_poly_model_through_localize_and_classify(ctx, oracle, small_scene, poly_svm_paths):
+    """predictAntipodalHands with the launch-file default model: fused into ag_localize (ag_set_svm) and as a
+    separate ag_classify, against the oracle's classify on the same hypotheses (given frames -> bit exact)."""
+    O = oracle
+    s = small_scene
+    path = poly_svm_paths["svm_032015_20_20_same"]
+    svm, osvm = api.Svm(path), O.Svm(path)
+    frames = O.fit_quadrics(s["tree"], s["cam"], s["idx"], 0.03, s["P"])["frames"]
+    normals = np.zeros((len(s["xyz"]), 3))
+    normals[s["idx"]] = frames["normal"]
+    ctx.set_params(s["P"])
+    ctx.set_svm(None)
+    ctx.set_cloud(s["xyz"], s["cam"])
+    g = ctx.hand_sweep(s["idx"], frames, normals)
+    gg, keep = ctx.classify(svm, g)
+    H = O.find_hands(s["tree"], s["cam"], s["idx"], frames, s["cam"][s["idx"]], normals, s["P"])
+    keep_o = H.classify(osvm, s["P"])
+    assert (_u32(gg["score"]) == _u32(H.grasps["score"])).all() and np.array_equal(keep, keep_o)
+    assert 0 < keep.sum() < len(keep)
+    ctx.set_svm(svm)
+    try:
+        g1 = ctx.localize(s["pts"], s["size_left"], s["idx"])
+        ctx.set_svm(None)
+        g2 = ctx.localize(s["pts"], s["size_left"], s["idx"])
+        g2, keep2 = ctx.classify(svm, g2)
+        assert (_u32(g1["score"]) == _u32(g2["score"])).all() and np.array_equal(g1["label"], keep2)
+    finally:
+        ctx.set_svm(None)
+
+
+def test_rand_mode_survives_growing_calls(ctx, oracle, small_scene):
+    """the rand() carry of the production normal mode must not live in a buffer that is re-allocated when
+    a later call has more samples.  A small call, then a larger one on the same context (fresh context too)."""
+    O = oracle
+    s = small_scene
+    P = copy.copy(s["P"])
+    P.deterministic_normals = 0
+    for c in (ctx, api.Context(0)):
+        c.set_params(P)
+        c.set_cloud(s["xyz"], s["cam"])
+        for idx in (s["idx"][:7], s["idx"], np.arange(0, len(s["xyz"]), 3, dtype=np.int32)):
+            fg = c.fit_quadrics(idx, 0.03)
+            ex = O.fit_quadrics(s["tree"], s["cam"], idx, 0.03, P, sum_perm=-1)["frames"]
+            assert np.array_equal(fg["num_neighbors"], ex["num_neighbors"])
+            assert np.array_equal(fg["majority_cam"], ex["majority_cam"])
+            ok = fg["num_neighbors"] >= 10
+            assert np.linalg.norm(fg["normal"] - ex["normal"], axis=1)[ok].max() <= 1e-9
+        if c is not ctx:
+            c.close()
+    ctx.set_params(s["P"])
+
+
+def test_classify_rejects_records_of_another_call(ctx, small_scene, linear_svm_path):
+    """predictAntipodalHands keeps the reference signature (any hand_list), but the grasp images live on the
+    device: records of an earlier call / another context are rejected instead of being scored against
+    unrelated images."""
+    s = small_scene
+    svm = api.Svm(linear_svm_path)
+    ctx.set_params(s["P"])
+    ctx.set_svm(None)
+    g_old = ctx.localize(s["pts"], s["size_left"], s["idx"])
+    g_new = ctx.localize(s["pts"], s["size_left"], s["idx"][:50])
+    with pytest.raises(api.AgError, match="does not belong"):
+        ctx.classify(svm, g_old)
+    other = api.Context(0, s["P"])
+    g_other = other.localize(s["pts"], s["size_left"], s["idx"][:50])
+    with pytest.raises(api.AgError, match="does not belong"):
+        ctx.classify(svm, g_other)
+    other.close()
+    gg, keep = ctx.classify(svm, g_new)
+    assert np.isfinite(gg["score"]).all()

@@ -108,3 +108,21 @@ my_svm: !!opencv-ml-svm
 """
     with open(path, "w") as f:
         f.write(txt)
+
+
+@pytest.mark.parametrize("name", ["svm_032015_20_20_same", "svm_032015_20_20"])
+def test_shipped_poly_models_match_cv2_fixture(oracle, poly_svm_paths, name):
+    """The reference's shipped POLY models (588 / 1190 support vectors; svm_032015_20_20_same is the launch-file
+    default, launch/single_camera_grasps.launch:6): descriptors and raw decision values of the committed
+    cv2-made fixture (tools/make_golden_poly.py), bit for bit."""
+    z = np.load(os.path.join(GOLD, "poly_svm_cv2.npz"))
+    svm = oracle.Svm(poly_svm_paths[name])
+    assert svm.kernel == 1 and svm.degree == 2 and svm.var_count == 3528
+    assert svm.sv_total == (588 if name.endswith("same") else 1190)
+    imgs = api.unpack_images(z["images_bits"])
+    raw = z["raw_" + name]
+    for t in range(len(imgs)):
+        d = oracle.hog(imgs[t])
+        assert (d.view(np.uint32) == z["descriptors"][t].view(np.uint32)).all()
+        assert np.float32(svm.decision(d)).view(np.uint32) == raw[t].view(np.uint32), t
+    assert ((raw <= 0) == (z["label_" + name] == 1)).all()  # CvSVM::predict: label +1 <=> sum <= 0

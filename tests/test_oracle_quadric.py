@@ -121,3 +121,9 @@ def test_rand_mode_normals(oracle, small_scene):
     big = det["num_neighbors"] > 50
     cosang = np.abs(np.einsum("ij,ij->i", r1["normal"][big], det["normal"][big]))
     assert big.sum() > 50 and np.median(cosang) > 0.99 and (r1["normal"][big] != det["normal"][big]).any()
+    # the stream is laid out per sample up front, so the result does not depend on the thread count
+    P.num_threads = 1
+    r3 = oracle.fit_quadrics(s["tree"], s["cam"], s["idx"], 0.03, P)["frames"]
+    P.num_threads = 7
+    r4 = oracle.fit_quadrics(s["tree"], s["cam"], s["idx"], 0.03, P)["frames"]
+    assert r3.tobytes() == r4.tobytes() == r1.tobytes()
