@@ -2,21 +2,28 @@
 """bench.py — grasp hypotheses/sec on the BASELINE.json configuration (307,200-point organised cloud,
 2000 samples, linear SVM), through the C ABI of libag_b200.so.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 2]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 2] [--normals rand|det]
 
 A step = one pass of the hot path (ag_localize + ag_classify = Localization::localizeHands +
 predictAntipodalHands) over one synthetic cloud per rank.  N>1 is launched by torchrun, one rank per
-GPU: every rank processes its own cloud (weak scaling) and the step ends with one NCCL all-gather of
-the fixed-stride grasp records, so every rank holds the whole grasp list.
+GPU: every rank processes one cloud per step (weak scaling; the same two scenes alternate on every rank and
+in the CPU arm, so hyp/s ratios are time ratios) and the grasp lists are exchanged by peer stores fused into
+the export kernel, so every rank holds the whole grasp list.
+
+Normal mode: the reference's PRODUCTION default (hand_search.h:84 is_deterministic = false: normals from 50
+picks rand() % n, quadric.cpp:177-192) in both arms (--normals rand); the deterministic all-neighbour mode of
+the reference's component tests is reported next to it (`other_mode` sub-objects; --normals det makes it
+the headline instead).
 
   value : hyp/s with the cloud already resident in HBM (ag_localize_device), timed with CUDA events on
           the library's own stream (ag_timings), max over ranks.
   e2e   : hyp/s through the host-buffer entry points (pinned host cloud in, host grasp list out),
           wall clock around the calls; H2D of the cloud and D2H of the records are inside.
-  roofline : the Taubin-moments kernel: algorithmic bytes (16 B per neighbour + 292 B out per sample)
-          over its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
+  roofline : the Taubin stage (radius search + moment accumulation): algorithmic bytes (16 B per neighbour +
+          292 B out per sample) over the CUDA-event duration of its kernel(s), against MEASURED_PEAKS.json.
+  roofline_step : the same for the kernel with the largest share of the step (k_hand_sweep).
   cpu_baseline : the CPU oracle (a port of the reference path, OpenMP over samples like the reference)
-          on this box's host cores.
+          on this box's host cores, both normal modes.
 --impl reference runs only that CPU arm.
 """
 import argparse
@@ -34,6 +41,10 @@ sys.path.insert(0, ROOT)
 
 METRIC = "grasp hypotheses/sec on 307k-pt cloud, 2000 samples; ms/cloud end-to-end"
 SVM_PATH = os.path.join(ROOT, "tests", "golden", "svm_032015_linear_20_20_same")
+POLY_XZ = os.path.join(ROOT, "tests", "golden", "svm_032015_20_20_same.xz")
+SCENES = (0, 1)  # scene offsets of the pool: the same in both arms and on every rank
+MODE_NAME = {0: "production (50 picks rand() % n, hand_search.h:84 is_deterministic = false)",
+             1: "deterministic (all neighbours, as src/tests/test_taubin.cpp:58)"}
 
 
 def measured_peak():
@@ -110,36 +121,62 @@ def make_cloud(config, scene_offset):
     return np.ascontiguousarray(pts), size_left, P, S
 
 
-def run_reference(args, rank, world):
-    """CPU arm: the oracle port of the reference path on all host threads."""
-    if rank != 0:
-        return
+def poly_model_path():
+    """the launch-file default model (launch/single_camera_grasps.launch:6), committed xz-compressed"""
+    import lzma
+    import tempfile
+    d = tempfile.mkdtemp(prefix="ag_poly_")
+    p = os.path.join(d, "svm_032015_20_20_same")
+    with open(p, "wb") as f:
+        f.write(lzma.open(POLY_XZ).read())
+    return p
+
+
+def cpu_arm(clouds, det, steps, warmup, svm_path=SVM_PATH):
+    """The oracle port of the reference path on all host threads over the scene pool; one cloud per step.
+    Returns (hyp/s, ms per cloud, mean hypotheses per cloud, cores)."""
     from oracle import oracle as O
-    pts, size_left, P, S = make_cloud(args.config, 0)
     cores = os.cpu_count() or 1
-    P.num_threads = cores
-    svm = O.Svm(SVM_PATH)
+    svm = O.Svm(svm_path)
     times, hyps = [], []
-    for it in range(args.warmup + args.steps):
+    for it in range(warmup + steps):
+        pts, size_left, P = clouds[it % len(clouds)]
+        P.num_threads = cores
+        P.deterministic_normals = det
         t0 = time.perf_counter()
         H, tm, nv = O.localize(pts, size_left, P, None, 0, svm, True)
         dt = time.perf_counter() - t0
-        if it >= args.warmup:
+        if it >= warmup:
             times.append(dt)
             hyps.append(len(H))
         del H
-    ms = 1e3 * float(np.mean(times))
-    value = float(np.sum(hyps) / np.sum(times))
+    return float(np.sum(hyps) / np.sum(times)), 1e3 * float(np.mean(times)), float(np.mean(hyps)), cores
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of the reference path on all host threads (same scene pool as the GPU arm)."""
+    if rank != 0:
+        return
+    det = 1 if args.normals == "det" else 0
+    clouds = []
+    for k in SCENES:
+        pts, size_left, P, S = make_cloud(args.config, k)
+        clouds.append((pts, size_left, P))
+    value, ms, hyp, cores = cpu_arm(clouds, det, args.steps, args.warmup)
+    o_value, o_ms, o_hyp, _ = cpu_arm(clouds, 1 - det, max(1, min(args.steps, 2)), 0)
+    n_pts = clouds[0][0].shape[0]
+    sample = (f"{args.steps} full clouds of the bench workload (scenes {list(SCENES)} alternating, as the GPU arm), "
+              f"OpenMP over samples on all {cores} host threads; std::set voxelisation and kd-tree as the reference; "
+              "SVM parsed once")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "hyp/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"config{args.config}: organised cloud of {pts.shape[0]} pts, {S} samples, linear SVM",
-                   "hypotheses_per_step": float(np.mean(hyps))},
-        "cpu_baseline": {"value": value, "unit": "hyp/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} full clouds of the bench workload, OpenMP over samples on all "
-                                   f"{cores} host threads; std::set voxelisation and kd-tree as the reference; "
-                                   "SVM parsed once"},
+        "config": {"workload": f"config{args.config}: organised cloud of {n_pts} pts, {S} samples, linear SVM",
+                   "normal_mode": MODE_NAME[det], "scenes": list(SCENES), "hypotheses_per_step": hyp},
+        "cpu_baseline": {"value": value, "unit": "hyp/s", "cores": cores, "kind": "port", "normal_mode": MODE_NAME[det],
+                         "ms_per_cloud": ms, "sample": sample,
+                         "other_mode": {"normal_mode": MODE_NAME[1 - det], "value": o_value, "ms_per_cloud": o_ms}},
         "e2e": {"value": value, "unit": "hyp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -152,7 +189,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--normals", default="rand", choices=["rand", "det"],
+                    help="normal mode of the headline numbers: rand = the reference's production default")
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (profiling runs)")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU grasp-list exchange: NVLink peer stores fused into the export kernel, or NCCL")
     args = ap.parse_args()
@@ -167,7 +207,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from agile_grasp_b200 import api
+    from agile_grasp_b200 import api, shard
     from agile_grasp_b200.ctypes_defs import GRASP_DTYPE
 
     if not torch.cuda.is_available():
@@ -176,11 +216,13 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    det = 1 if args.normals == "det" else 0
 
-    # a small pool of different scenes per rank so successive steps do not see identical inputs
+    # the scene pool: successive steps do not see identical inputs; every rank (and the CPU arm) uses the same set
     pool = []
-    for k in range(2):
-        pts, size_left, P, S = make_cloud(args.config, scene_offset=rank * 2 + k)
+    for k in SCENES:
+        pts, size_left, P, S = make_cloud(args.config, scene_offset=k)
+        P.deterministic_normals = det
         pinned = torch.from_numpy(pts).pin_memory()
         pool.append(dict(host=pinned, dev=pinned.to(dev), size_left=size_left, P=P, n=pts.shape[0],
                          stride=pts.strides[0]))
@@ -190,9 +232,6 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     item = GRASP_DTYPE.itemsize
 
-    # multi-GPU: the library leaves [header][records] in a device buffer; one fixed-size NCCL all-gather
-    # makes every rank hold every rank's grasp list (device resident)
-    from agile_grasp_b200 import shard
     peer_gather = world > 1 and args.gather == "peer"
     if peer_gather:
         shard.setup_peer_gather(ctx, pool[0]["P"].num_samples)
@@ -209,8 +248,7 @@ def main():
         if peer_gather:  # the export kernel already stored this rank's list into every rank's buffer
             last_gather[0] = ctx.gather_wait()
             return last_gather[0]
-        allbuf = shard.all_gather_export(send, recv)
-        return allbuf  # counts are read after the timed region (no host sync inside the step)
+        return shard.all_gather_export(send, recv)  # counts are read after the timed region
 
     def step_device(c):
         g = ctx.localize_device(c["dev"].data_ptr(), c["stride"], c["n"], c["size_left"])
@@ -230,67 +268,69 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def prime():
+        # every input buffer goes through the eager call and the CUDA-graph capture once (untimed), so that
+        # warm-up and timed steps all run the steady-state (replay) path
+        for c in pool:
+            for _ in range(2):
+                gather(step_device(c)[0])
+                gather(step_host(c))
+
+    def timed_device(steps):
+        dev_ms, hyps, comm_ms, launches, recs = [], [], [], [], []
+        barrier()
+        wall0 = time.perf_counter()
+        for k in range(steps):
+            c = pool[k % len(pool)]
+            flush.fill_(k & 0xFF)  # L2 flush between timed iterations (outside the per-step event brackets)
+            torch.cuda.synchronize()
+            g, t1, t2 = step_device(c)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tg0 = time.perf_counter()
+            e0.record()
+            gather(g)
+            e1.record()
+            torch.cuda.synchronize()
+            # peer gather: the stores ride inside ag_localize's export kernel (already in total_ms); what is left
+            # is the wait for the slowest peer, on the library stream -> wall clock of ag_gather_wait
+            cm = 0.0 if world == 1 else ((time.perf_counter() - tg0) * 1e3 if peer_gather else e0.elapsed_time(e1))
+            dev_ms.append(t1["total_ms"] + cm)  # scoring is fused into ag_localize (ag_set_svm): inside total_ms
+            comm_ms.append(cm)
+            hyps.append(len(g))
+            launches.append(t2["kernel_launches"])
+            recs.append(t1)
+        barrier()
+        return dict(dev_ms=dev_ms, hyps=hyps, comm_ms=comm_ms, launches=launches, t=recs,
+                    wall=time.perf_counter() - wall0)
+
+    def timed_host(steps):
+        e2e_s, e2e_h = [], []
+        g = None
+        barrier()
+        for k in range(steps):
+            c = pool[k % len(pool)]
+            flush.fill_(k & 0xFF)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            g = step_host(c)
+            gather(g)
+            e2e_s.append(time.perf_counter() - t0)
+            e2e_h.append(len(g))
+        barrier()
+        return e2e_s, e2e_h, g
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # ---- priming (untimed, before the W warm-up steps): every input buffer goes through the eager call and the
-    # CUDA-graph capture once, so that warm-up and timed steps all run the steady-state (replay) path
-    for c in pool:
-        for _ in range(2):
-            gather(step_device(c)[0])
-            gather(step_host(c))
-    # ---- warm-up
+    prime()
     for w in range(args.warmup):
-        g, _, _ = step_device(pool[w % len(pool)])
-        gather(g)
+        gather(step_device(pool[w % len(pool)])[0])
         gather(step_host(pool[w % len(pool)]))
     sampler.mark()
-
-    # ---- timed: device-resident input (value)
-    dev_ms, hyps, mom_ms, mom_bytes, launches, comm_ms = [], [], [], [], [], []
-    stage = {}
-    barrier()
-    wall0 = time.perf_counter()
-    for k in range(args.steps):
-        c = pool[k % len(pool)]
-        flush.fill_(k & 0xFF)  # L2 flush between timed iterations (outside the per-step event brackets)
-        torch.cuda.synchronize()
-        g, t1, t2 = step_device(c)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tg0 = time.perf_counter()
-        e0.record()
-        total = gather(g)
-        e1.record()
-        torch.cuda.synchronize()
-        # peer gather: the stores ride inside ag_localize's export kernel (already in total_ms); what is left
-        # is the wait for the slowest peer, on the library stream -> wall clock of ag_gather_wait
-        cm = 0.0 if world == 1 else ((time.perf_counter() - tg0) * 1e3 if peer_gather else e0.elapsed_time(e1))
-        dev_ms.append(t1["total_ms"] + cm)  # scoring is fused into ag_localize (ag_set_svm): already inside total_ms
-        comm_ms.append(cm)
-        hyps.append(len(g))
-        mom_ms.append(t1["moments_ms"])
-        mom_bytes.append(16 * t1["taubin_neighbor_points"] + 292 * t1["n_samples"])
-        launches.append(t2["kernel_launches"])
-        for nm in ("preprocess_ms", "grid_ms", "quadric_ms", "sweep_ms", "d2h_ms", "search_ms", "moments_ms", "axes_ms"):
-            stage.setdefault(nm, []).append(t1[nm])
-        stage.setdefault("hog_svm_ms", []).append(t1["hog_svm_ms"])
-    barrier()
-    wall_dev = time.perf_counter() - wall0
-
-    # ---- timed: host buffers through the reference-facing entry points (e2e)
-    e2e_s, e2e_h = [], []
-    barrier()
-    for k in range(args.steps):
-        c = pool[k % len(pool)]
-        flush.fill_(k & 0xFF)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        g = step_host(c)
-        gather(g)
-        e2e_s.append(time.perf_counter() - t0)
-        e2e_h.append(len(g))
-    barrier()
+    D = timed_device(args.steps)
+    e2e_s, e2e_h, g = timed_host(args.steps)
     clocks = sampler.stop() if rank == 0 else None
+
     gathered = None
     if peer_gather:  # verify the last exchange on the host (outside the timed region): every rank's list is there
         n_per, slots_ptr, slot_bytes = last_gather[0]
@@ -309,26 +349,40 @@ def main():
         assert parts[rank][0]["n_hyp"] == e2e_h[-1], (parts[rank][0], e2e_h[-1])
 
     # ---- reduce over ranks: time = max, hypotheses = sum
-    t_dev = torch.tensor([sum(dev_ms), sum(e2e_s) * 1e3], dtype=torch.float64, device=dev)
-    n_h = torch.tensor([sum(hyps), sum(e2e_h)], dtype=torch.float64, device=dev)
+    t_dev = torch.tensor([sum(D["dev_ms"]), sum(e2e_s) * 1e3], dtype=torch.float64, device=dev)
+    n_h = torch.tensor([sum(D["hyps"]), sum(e2e_h)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
         dist.all_reduce(n_h, op=dist.ReduceOp.SUM)
     t_dev, n_h = t_dev.cpu().numpy(), n_h.cpu().numpy()
 
+    line = None
     if rank == 0:
+        T = D["t"]
+        mean = lambda nm: float(np.mean([t[nm] for t in T]))  # noqa: E731
         value = n_h[0] / (t_dev[0] * 1e-3)
         e2e = n_h[1] / (t_dev[1] * 1e-3)
         peak, peak_src = measured_peak()
-        achieved = float(np.sum(mom_bytes) / (np.sum(mom_ms) * 1e-3) / 1e9) if np.sum(mom_ms) > 0 else 0.0
+        # graded stage: radius search + moment accumulation of the Taubin fit (one fused kernel when moments_ms == 0)
+        tb_bytes = [16 * t["taubin_neighbor_points"] + 292 * t["n_samples"] for t in T]
+        tb_ms = [t["search_ms"] + t["moments_ms"] for t in T]
+        achieved = float(np.sum(tb_bytes) / (np.sum(tb_ms) * 1e-3) / 1e9) if np.sum(tb_ms) > 0 else 0.0
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "taubin_moments_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "taubin_traffic.json")
         if os.path.exists(tp):
             try:
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        # the kernel with the largest share of the step: the hand sweep (16 B per point of the r = 0.08 ball in,
+        # 160 B record + 1000 B grasp image out per hypothesis)
+        sw_bytes = [16 * t["hand_neighbor_points"] + 1160 * t["n_hyp"] for t in T]
+        sw_ms = [t["sweep_ms"] for t in T]
+        sw_ach = float(np.sum(sw_bytes) / (np.sum(sw_ms) * 1e-3) / 1e9) if np.sum(sw_ms) > 0 else 0.0
         c0 = pool[0]
+        stages = {nm: mean(nm) for nm in ("preprocess_ms", "normals_all_ms", "quadric_ms", "search_ms", "moments_ms",
+                                          "axes_ms", "sweep_ms", "hog_svm_ms", "d2h_ms")}
+        fused = float(np.sum([t["moments_ms"] for t in T])) == 0.0
         line = {
             "metric": METRIC, "value": float(value), "unit": "hyp/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": float(t_dev[0] / args.steps), "higher_is_better": True,
@@ -336,96 +390,157 @@ def main():
             "config": {"workload": f"config{args.config}: one organised cloud ({c0['n']} pts, {c0['stride']} B/pt; 640x480 "
                                    f"per view) per rank per step, {c0['P'].num_samples} samples, linear SVM "
                                    "svm_032015_linear_20_20_same",
+                       "normal_mode": MODE_NAME[det], "scenes": list(SCENES),
                        "l2": "flushed between timed iterations (256 MiB write)",
                        "launch": "CUDA graph replay (captured during untimed priming calls)",
-                       "hypotheses_per_step": float(n_h[0] / args.steps),
-                       "multi_gpu": ("one cloud per rank per step; grasp lists exchanged by " +
-                                     ("NVLink peer stores fused into the export kernel" if peer_gather else
-                                      "an NCCL all-gather")) if world > 1
-                       else "single GPU", "timer": "CUDA events on the library stream (ag_timings), max over ranks"},
+                       "hypotheses_per_step": float(n_h[0] / args.steps / world),
+                       "multi_gpu": ("one cloud per rank per step (the same scene pool on every rank); grasp lists "
+                                     "exchanged by " + ("NVLink peer stores fused into the export kernel" if peer_gather
+                                                        else "an NCCL all-gather")) if world > 1 else "single GPU",
+                       "timer": "CUDA events on the library stream (ag_timings), max over ranks"},
             "e2e": {"value": float(e2e), "unit": "hyp/s", "ms_per_cloud": float(t_dev[1] / args.steps),
                     "h2d_bytes_per_step": int(c0["n"] * c0["stride"]),
-                    "d2h_bytes_per_step": int(np.mean(e2e_h) * (item + 4)),
-                    "timer": "wall clock around ag_localize + ag_classify (+ all-gather), pinned host cloud"},
-            "gpu_launches": int(np.sum(launches)),
-            "roofline": {"bound": "hbm", "kernel": "k_taubin_moments", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": float(np.mean(mom_bytes)),
-                         "launch_ms": float(np.mean(mom_ms)),
-                         "search_launch_ms": float(np.mean(stage["search_ms"])),
-                         "achieved_incl_search": float(np.sum(mom_bytes) / ((np.sum(mom_ms) + np.sum(stage["search_ms"]))
-                                                                            * 1e-3) / 1e9),
-                         "note": "k_taubin_moments streams the neighbour lists k_ball_search wrote (16 B per "
-                                 "neighbour); a 2000-sample launch is latency bound, profiles/ holds the at-scale runs"},
-            "stages_ms": {k: float(np.mean(v)) for k, v in stage.items()},
-            "comm_ms": float(np.mean(comm_ms)), "gathered_last_step": gathered,
-            "wall_ms_per_step_incl_flush": float(1e3 * wall_dev / args.steps),
+                    "d2h_bytes_per_step": int(np.mean(e2e_h) * item + 64),
+                    "timer": "wall clock around ag_localize + ag_classify (+ gather wait), pinned host cloud"},
+            "gpu_launches": int(np.sum(D["launches"])),
+            "roofline": {"bound": "hbm",
+                         "kernel": "k_ball_moments (radius search + Taubin moments, one kernel)" if fused
+                         else "k_ball_search + k_taubin_moments",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": float(np.mean(tb_bytes)), "launch_ms": float(np.mean(tb_ms)),
+                         "note": "16 B per neighbour of the r = 0.03 ball + 292 B of moments per sample; a 2000-sample "
+                                 "launch is latency bound, roofline_at_scale is the same stage on a launch that fills "
+                                 "the machine"},
+            "roofline_step": {"bound": "hbm", "kernel": "k_hand_sweep",
+                              "share_of_step": float(np.sum(sw_ms) / np.sum([t["total_ms"] for t in T])),
+                              "achieved": sw_ach, "peak": peak, "unit": "GB/s", "frac": sw_ach / peak,
+                              "algorithmic_bytes_per_launch": float(np.mean(sw_bytes)), "launch_ms": float(np.mean(sw_ms)),
+                              "note": "16 B per point of the r = 0.08 ball + 1160 B per hypothesis out; the ball is "
+                                      "L2 resident (1.3 MB cloud), the kernel is issue / latency bound"},
+            "stages_ms": stages,
+            "comm_ms": float(np.mean(D["comm_ms"])), "gathered_last_step": gathered,
+            "wall_ms_per_step_incl_flush": float(1e3 * D["wall"] / args.steps),
             "clocks": clocks,
         }
-        if world == 1:
-            # the same kernel on a launch that fills the machine (outside the timed region): every voxel of the
-            # bench cloud as a sample, r = 0.03 — the size of the reference's all-points pass (hand_search.cpp:17-26)
-            try:
-                n_vox = ctx.timings()["n_voxels"]
-                all_idx = np.arange(n_vox, dtype=np.int32)
-                best = None
-                for _ in range(4):
-                    flush.fill_(1)
-                    torch.cuda.synchronize()
-                    ctx.fit_quadrics(all_idx, c0["P"].nn_radius_taubin)
-                    t = ctx.timings()
-                    if best is None or t["moments_ms"] < best["moments_ms"]:
-                        best = t
-                b_alg = 16 * best["taubin_neighbor_points"] + 292 * n_vox
-                a_sc = b_alg / (best["moments_ms"] * 1e-3) / 1e9
-                line["roofline_at_scale"] = {
-                    "kernel": "k_taubin_moments", "samples": int(n_vox), "algorithmic_bytes_per_launch": float(b_alg),
-                    "launch_ms": float(best["moments_ms"]), "achieved": float(a_sc), "peak": peak, "unit": "GB/s",
-                    "frac": float(a_sc / peak), "search_launch_ms": float(best["search_ms"]),
-                    "achieved_incl_search": float(b_alg / ((best["moments_ms"] + best["search_ms"]) * 1e-3) / 1e9),
-                    "note": "all voxels of the bench cloud as samples (L2 flushed before each of 4 launches, best taken)"}
-            except Exception as e:  # never lose the bench line over the extra measurement
-                line["roofline_at_scale"] = {"error": str(e)}
-            # throughput mode (BASELINE config 4 on one GPU): 16 clouds through ag_localize_batch, pinned host
-            # buffers in, host grasp lists out (wall clock, best of 3); the headline above stays one cloud per call
-            try:
-                bc = [pool[i % len(pool)]["host"].numpy() for i in range(16)]
-                bs = [pool[i % len(pool)]["size_left"] for i in range(16)]
-                ctx.localize_batch(bc[:8], bs[:8])
-                ctx.localize_batch(bc[:8], bs[:8])
-                best_dt, nh = None, 0
+
+    extras = world == 1 and not args.no_extras
+    if extras:
+        # ---- the other normal mode, same steps (outside the headline's timed region)
+        try:
+            for c in pool:
+                c["P"].deterministic_normals = 1 - det
+            ctx.set_params(pool[0]["P"])
+            prime()
+            k2 = max(4, min(args.steps, 10))
+            D2 = timed_device(k2)
+            s2, h2, _ = timed_host(k2)
+            line["other_mode"] = {"normal_mode": MODE_NAME[1 - det],
+                                  "value": float(np.sum(D2["hyps"]) / (np.sum(D2["dev_ms"]) * 1e-3)),
+                                  "ms_per_step": float(np.mean(D2["dev_ms"])),
+                                  "e2e": {"value": float(np.sum(h2) / np.sum(s2)), "ms_per_cloud": float(1e3 * np.mean(s2))},
+                                  "stages_ms": {nm: float(np.mean([t[nm] for t in D2["t"]])) for nm in
+                                                ("preprocess_ms", "quadric_ms", "search_ms", "moments_ms", "axes_ms",
+                                                 "sweep_ms", "hog_svm_ms")}, "steps": k2}
+        except Exception as e:
+            line["other_mode"] = {"error": str(e)}
+        finally:
+            for c in pool:
+                c["P"].deterministic_normals = det
+            ctx.set_params(pool[0]["P"])
+        # ---- the Taubin stage on a launch that fills the machine: every voxel of the bench cloud as a sample,
+        # r = 0.03 — the size of the reference's all-points pass (hand_search.cpp:17-26)
+        try:
+            c0 = pool[0]
+            step_device(c0)
+            n_vox = ctx.timings()["n_voxels"]
+            all_idx = np.arange(n_vox, dtype=np.int32)
+            best = None
+            for _ in range(4):
+                flush.fill_(1)
+                torch.cuda.synchronize()
+                ctx.fit_quadrics(all_idx, c0["P"].nn_radius_taubin)
+                t = ctx.timings()
+                if best is None or t["moments_ms"] + t["search_ms"] < best["moments_ms"] + best["search_ms"]:
+                    best = t
+            b_alg = 16 * best["taubin_neighbor_points"] + 292 * n_vox
+            ms = best["moments_ms"] + best["search_ms"]
+            a_sc = b_alg / (ms * 1e-3) / 1e9
+            peak, _ = measured_peak()
+            line["roofline_at_scale"] = {
+                "kernel": line["roofline"]["kernel"], "samples": int(n_vox), "algorithmic_bytes_per_launch": float(b_alg),
+                "launch_ms": float(ms), "achieved": float(a_sc), "peak": peak, "unit": "GB/s", "frac": float(a_sc / peak),
+                "axes_ms": float(best["axes_ms"]),
+                "note": "all voxels of the bench cloud as samples (L2 flushed before each of 4 launches, best taken)"}
+        except Exception as e:  # never lose the bench line over the extra measurement
+            line["roofline_at_scale"] = {"error": str(e)}
+        # ---- throughput mode (BASELINE config 4 on one GPU): 16 clouds through ag_localize_batch, pinned host
+        # buffers in, host grasp lists out (wall clock, best of 3); the headline above stays one cloud per call
+        try:
+            bc = [pool[i % len(pool)]["host"].numpy() for i in range(16)]
+            bs = [pool[i % len(pool)]["size_left"] for i in range(16)]
+            ctx.localize_batch(bc[:8], bs[:8])
+            ctx.localize_batch(bc[:8], bs[:8])
+            best_dt, nh = None, 0
+            for _ in range(3):
+                t0 = time.perf_counter()
+                outs = ctx.localize_batch(bc, bs)
+                dt = time.perf_counter() - t0
+                if best_dt is None or dt < best_dt:
+                    best_dt, nh = dt, sum(len(o) for o in outs)
+            line["batched_e2e"] = {"clouds": 16, "lanes": 4, "value": float(nh / best_dt), "unit": "hyp/s",
+                                   "ms_per_cloud": float(best_dt * 1e3 / 16),
+                                   "note": "ag_localize_batch: 4 clouds in flight on separate streams, each lane "
+                                           "replaying its CUDA graph; results identical to sequential calls"}
+        except Exception as e:
+            line["batched_e2e"] = {"error": str(e)}
+        # ---- the launch-file default model (POLY, 588 support vectors): same step with that model attached
+        try:
+            poly = api.Svm(poly_model_path())
+            ctx.set_svm(poly)
+            for c in pool:
                 for _ in range(3):
-                    t0 = time.perf_counter()
-                    outs = ctx.localize_batch(bc, bs)
-                    dt = time.perf_counter() - t0
-                    if best_dt is None or dt < best_dt:
-                        best_dt, nh = dt, sum(len(o) for o in outs)
-                line["batched_e2e"] = {"clouds": 16, "lanes": 4, "value": float(nh / best_dt), "unit": "hyp/s",
-                                       "ms_per_cloud": float(best_dt * 1e3 / 16),
-                                       "note": "ag_localize_batch: 4 clouds in flight on separate streams, each lane "
-                                               "replaying its CUDA graph; results identical to sequential calls"}
-            except Exception as e:
-                line["batched_e2e"] = {"error": str(e)}
-            try:
-                from oracle import oracle as O
-                P = c0["P"]
-                cores = os.cpu_count() or 1
-                P.num_threads = cores
-                osvm = O.Svm(SVM_PATH)
-                ts, hs = [], []
-                for _ in range(args.cpu_steps):
-                    t0 = time.perf_counter()
-                    H, tm, nv = O.localize(c0["host"].numpy(), c0["size_left"], P, None, 0, osvm, True)
-                    ts.append(time.perf_counter() - t0)
-                    hs.append(len(H))
-                    del H
-                line["cpu_baseline"] = {"value": float(np.sum(hs) / np.sum(ts)), "unit": "hyp/s", "cores": cores,
-                                        "kind": "port", "ms_per_cloud": float(1e3 * np.mean(ts)),
-                                        "sample": f"{args.cpu_steps} full clouds of the same workload, all {cores} "
-                                                  "host threads (OpenMP over samples, as the reference)"}
-            except Exception as e:  # the oracle is test infrastructure; never let it break the GPU number
-                line["cpu_baseline"] = {"value": None, "unit": "hyp/s", "cores": 0, "kind": "port",
-                                        "sample": f"unavailable: {e}"}
+                    ctx.localize(c["host"].numpy(), c["size_left"])
+            ts, hs, hg = [], [], []
+            for k in range(max(4, min(args.steps, 10))):
+                c = pool[k % len(pool)]
+                flush.fill_(k & 0xFF)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                gp = ctx.localize(c["host"].numpy(), c["size_left"])
+                gp, keep = ctx.classify(poly, gp)
+                ts.append(time.perf_counter() - t0)
+                hs.append(len(gp))
+                hg.append(ctx.timings()["hog_svm_ms"])
+            line["poly_svm"] = {"model": "svm_032015_20_20_same (POLY degree 2, 588 support vectors; "
+                                         "launch/single_camera_grasps.launch:6)",
+                                "e2e": {"value": float(np.sum(hs) / np.sum(ts)), "unit": "hyp/s",
+                                        "ms_per_cloud": float(1e3 * np.mean(ts))},
+                                "hog_svm_ms": float(np.mean(hg)), "positives_last_step": int(keep.sum())}
+        except Exception as e:
+            line["poly_svm"] = {"error": str(e)}
+        finally:
+            ctx.set_svm(svm)
+        # ---- CPU baseline: the oracle port on this box's host cores, both normal modes, same scene pool
+        try:
+            clouds = [(c["host"].numpy(), c["size_left"], c["P"]) for c in pool]
+            v, ms, hyp, cores = cpu_arm(clouds, det, args.cpu_steps, 0)
+            ov, oms, _, _ = cpu_arm(clouds, 1 - det, max(1, args.cpu_steps // 2), 0)
+            line["cpu_baseline"] = {"value": v, "unit": "hyp/s", "cores": cores, "kind": "port", "ms_per_cloud": ms,
+                                    "normal_mode": MODE_NAME[det],
+                                    "sample": f"{args.cpu_steps} full clouds of the same workload and scene pool, all "
+                                              f"{cores} host threads (OpenMP over samples, as the reference)",
+                                    "other_mode": {"normal_mode": MODE_NAME[1 - det], "value": ov, "ms_per_cloud": oms}}
+            if "poly_svm" in line and "e2e" in line["poly_svm"]:
+                pv, pms, _, _ = cpu_arm(clouds[:1], det, 1, 0, svm_path=poly_model_path())
+                line["poly_svm"]["cpu_baseline"] = {"value": pv, "ms_per_cloud": pms, "cores": cores}
+        except Exception as e:  # the oracle is test infrastructure; never let it break the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": "hyp/s", "cores": 0, "kind": "port",
+                                    "sample": f"unavailable: {e}"}
+        finally:
+            for c in pool:
+                c["P"].deterministic_normals = det
+    if rank == 0:
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

@@ -37,6 +37,13 @@ def _u64(a):
     return np.ascontiguousarray(a).view(np.uint64)
 
 
+def _rec_bytes(g):
+    """grasp records as bytes, without the per-call stamp (ag_grasp.reserved differs from call to call by design)"""
+    h = g.copy()
+    h["reserved"] = 0
+    return h.tobytes()
+
+
 # ---------------------------------------------------------------------------------------------
 def test_preprocess_bit_exact(ctx, oracle, small_scene, two_view_scene):
     for s in (small_scene, two_view_scene):
@@ -135,7 +142,7 @@ def test_quadric_frames(ctx, oracle, small_scene, two_view_scene):
         dr = np.linalg.norm(fg["normal"] - ref["normal"], axis=1)
         de = np.linalg.norm(ref["normal"] - exact["normal"], axis=1)  # dggev's own distance from exact
         assert np.median(dr) <= 1e-6
-        assert (dr <= 1e-5).mean() >= 0.93, (dr <= 1e-5).mean()
+        assert (dr <= 1e-5).mean() >= 0.955, (dr <= 1e-5).mean()  # measured 0.98 / 0.967
         # where the GPU is farther than tolerance from dggev, dggev is equally far from exact
         far = dr > 1e-5
         assert (de[far & det] > 0.5e-5).all()
@@ -323,15 +330,15 @@ def test_end_to_end_own_frames(ctx, oracle, small_scene, linear_svm_path):
     kg = {(a, b): i for i, (a, b) in enumerate(zip(gg["sample_index"].tolist(), gg["orientation"].tolist()))}
     common = sorted(set(ko) & set(kg))
     # the two frame solvers differ at the reference's noise level, which can flip a borderline slot
-    assert len(common) >= 0.97 * max(len(ko), len(kg))
+    assert len(common) >= 0.985 * max(len(ko), len(kg))  # measured: 78 of 78
     io = np.array([ko[k] for k in common])
     ig = np.array([kg[k] for k in common])
     d = np.linalg.norm(gg["approach"][ig] - go["approach"][io], axis=1)
     assert np.median(d) <= 1e-4
     same_img = gg["num_points"][ig] == go["num_points"][io]
     # identical box contents -> identical images up to a borderline pixel -> (nearly) identical scores
-    assert same_img.mean() >= 0.9
-    assert (gg["label"][ig] == go["label"][io]).mean() >= 0.97
+    assert same_img.mean() >= 0.96  # measured 0.974 (76 of 78)
+    assert (gg["label"][ig] == go["label"][io]).mean() >= 0.98  # measured 0.987 (77 of 78)
 
 
 def test_fused_scoring_equals_separate_classify(ctx, small_scene, linear_svm_path):
@@ -374,7 +381,7 @@ def test_size_independent_properties_full_config(ctx, linear_svm_path):
     assert np.allclose(np.einsum("ij,ij->i", g["approach"], g["binormal"]), 0, atol=1e-12)
     assert np.allclose(np.einsum("ij,ij->i", g["approach"], g["axis"]), 0, atol=1e-9)
     g2 = ctx.localize(pts, size_left)
-    assert g.tobytes() == g2.tobytes()
+    assert _rec_bytes(g) == _rec_bytes(g2)
     # permuting the input points does not change the voxelised cloud (sorted unique voxels)
     xyz, cam = ctx.preprocess(pts, size_left)
     perm = np.random.default_rng(0).permutation(len(pts))
@@ -390,7 +397,7 @@ def test_size_independent_properties_full_config(ctx, linear_svm_path):
     xyz_2, _ = ctx.preprocess(rec, len(rec))
     xo2, _ = O.preprocess(rec, len(rec), P, False)
     assert len(xyz_2) <= len(xyz) and (_u32(xyz_2) == _u32(xo2)).all()
-    gg, keep = ctx.classify(api.Svm(linear_svm_path), g)
+    gg, keep = ctx.classify(api.Svm(linear_svm_path), g2)  # (the records of the LAST localize call)
     assert np.isfinite(gg["score"]).all() and ((gg["score"] <= 0) == (keep == 1)).all()
 
 
@@ -533,7 +540,7 @@ def test_localize_batch_equals_sequential(ctx, linear_svm_path):
             bat = ctx.localize_batch(clouds, sls)
             assert len(bat) == 5
             for a, b in zip(seq, bat):
-                assert len(a) > 0 and a.tobytes() == b.tobytes()
+                assert len(a) > 0 and _rec_bytes(a) == _rec_bytes(b)
         empty = ctx.localize_batch([], [])
         assert empty == []
     finally:
@@ -563,7 +570,7 @@ def test_rand_mode_normals_match_oracle(ctx, oracle, small_scene):
         assert dn[det].max() <= 1e-9, dn[det].max()
         # the whole pipeline in this mode: eager, graph capture and graph replay give the same list
         runs = [ctx.localize(s["pts"], s["size_left"], s["idx"]) for _ in range(3)]
-        assert len(runs[0]) > 0 and runs[0].tobytes() == runs[1].tobytes() == runs[2].tobytes()
+        assert len(runs[0]) > 0 and _rec_bytes(runs[0]) == _rec_bytes(runs[1]) == _rec_bytes(runs[2])
         ctx.set_cloud(s["xyz"], s["cam"])
         Pd = copy.copy(s["P"])
         ctx.set_params(Pd)
@@ -638,6 +645,6 @@ def test_localize_edge_cases(ctx, oracle, small_scene, linear_svm_path):
         ctx.localize(one, 1)  # (a rank-deficient neighbourhood: the frame is arbitrary in the reference too)
         assert ctx.timings()["n_voxels"] == 1 and ctx.timings()["n_samples"] == 1
         outs = ctx.localize_batch([s["pts"], np.zeros((0, 8), np.float32), s["pts"]], [s["size_left"], 1, s["size_left"]])
-        assert len(outs[1]) == 0 and len(outs[0]) > 0 and outs[0].tobytes() == outs[2].tobytes()
+        assert len(outs[1]) == 0 and len(outs[0]) > 0 and _rec_bytes(outs[0]) == _rec_bytes(outs[2])
     finally:
         ctx.set_params(s["P"])
