@@ -25,6 +25,8 @@ struct DevBuf {
   }
 };
 
+#define AG_SWEEP_LUT 44  // zones k = -1 .. 20, two per slot step
+
 // constants of the hand model, evaluated on the host with the same libm as the reference
 // (finger_hand.cpp:8-15, rotating_hand.cpp:12-15,90, finger_hand.cpp:199-204, antipodal.cpp:14)
 struct HandConst {
@@ -39,8 +41,15 @@ struct HandConst {
   double cam[2][3];        // camera origins
   double img_cell;         // (0.05 - -0.05) / 100
   double half_od;          // outer_diameter / 2.0
-  double inv_slot_step;    // 1 / spacing step (index estimate for the slot lookup)
-  int uniform_slots;       // 1 if the slot edge tables are strictly ascending (fast lookup valid)
+  double inv_slot_step;    // 1 / spacing step (zone estimate for the slot-mask table)
+  double inv_bite_step;    // 1 / 0.005 (depth-level estimate)
+  double inv_img_cell;     // 1 / img_cell (cell estimate, exact division near cell borders)
+  // slot masks (side << 32 | in) of a point per zone between two consecutive slot edges: the 40 edges are two
+  // interleaved uniform grids (lower edges at integer slot steps from spacing[0], upper edges lut_phi further),
+  // so zone (k, a|b) = floor and fraction of (x - spacing[0]) / step; entry 2 (k + 1) + (fraction > lut_phi)
+  unsigned long long lut[AG_SWEEP_LUT];
+  float lut_phi;
+  int lut_ok;              // 0: hand geometry without the table (every point takes the exact comparisons)
 };
 
 struct SvmModel {

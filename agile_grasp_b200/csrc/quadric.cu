@@ -382,19 +382,23 @@ k_taubin_moments(int s0, int m, const float4* __restrict__ heads, const GPoint* 
 
 // ---- small dense helpers (per warp, shared memory, lane-parallel where it is cheap) -----------
 constexpr int kRankCap = 2048;  // neighbours per sample the rand() % n mode can rank (larger balls fall back)
+__device__ int g_force_jacobi = 0;  // diagnostics (AG_FORCE_JACOBI): always diagonalise with the cyclic Jacobi
 struct AxesSmem {
-  double A[81];   // Schur complement, later C = L^-1 A L^-T, diagonalised in place
+  double A[81];   // Schur complement, later C = L^-1 A L^-T (diagonalised in place only on the Jacobi fallback)
   double L[81];   // B, then its Cholesky factor
-  double V[81];   // Jacobi eigenvectors
+  double V[96];   // scratch of the eigen-solve: L D L^T factors (81 + 9), or the Jacobi eigenvectors
   double m[10];   // last column of M (9 entries) and n
   double par[10]; // quadric parameters in centred/scaled coordinates
   double T[28];   // weighted order-6 normal tensor
 };
-// non-deterministic normal mode only (extra dynamic shared memory behind the kWarps AxesSmem blocks): squared
-// distances of the neighbours and their (distance, index) order
+// non-deterministic normal mode only (extra dynamic shared memory behind the kWarps AxesSmem blocks): the
+// (distance, index) order of the neighbours (distances are recomputed from the list: 5 KB per warp keep the
+// kernel at 4 CTAs per SM)
+constexpr int kRankBuckets = 256;
 struct RankSmem {
-  float d2[kRankCap];
-  unsigned short order[kRankCap];
+  unsigned short order[kRankCap];  // neighbour positions grouped by distance bucket
+  unsigned char bucket[kRankCap];  // distance bucket of every neighbour
+  int cur[kRankBuckets];           // fill cursors of the counting sort: afterwards the END of every bucket
 };
 
 // streams a sample's neighbour list (written by k_ball_search) 32 records per step, the next step's load
@@ -511,6 +515,125 @@ __device__ void warp_jacobi9(double* A, double* V, int lane) {
   }
 }
 
+
+// ---- smallest eigenpair of the reduced 9x9 pencil without diagonalising it ------------------------
+// C (symmetric, positive semi-definite up to round-off) is only needed for its SMALLEST eigenpair
+// (quadric.cpp:149-152).  lambda_1 is bracketed by multisection on the predicate "C - sigma I is positive
+// definite": every lane factorises C - sigma_lane I = L D L^T in registers (fully unrolled, no communication)
+// and reports whether all nine pivots stayed positive — a Cholesky test, stable exactly where it says yes — so
+// one ballot narrows the bracket 33 times.  Eight rounds pin lambda_1 to ~1e-12 of the smallest diagonal
+// entry from below; inverse iteration with that (positive definite) shift then converges in 3-4 solves.
+// ~2.5k warp instructions instead of ~10k for the cyclic Jacobi, and almost no dependent shared-memory traffic.
+__device__ __forceinline__ double fast_rcp(double x) {  // reciprocal to ~1 ulp: approximation + 2 Newton steps
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(fma(-x, r, 1.0), r, r);
+  r = fma(fma(-x, r, 1.0), r, r);
+  return r;
+}
+// L D L^T of C - sigma I from the row-major 9x9 in shared memory (lower triangle read).  Returns whether all
+// pivots were positive.  STORE: lane 0 also leaves L (strict lower part, row-major 9x9) and 1/D in `fac`.
+template <bool STORE>
+__device__ __forceinline__ bool ldl9_shifted(const double* __restrict__ C, double sigma, double* fac, int lane) {
+  double a[9][9];  // lower triangle, compile-time indices only (registers)
+#pragma unroll
+  for (int i = 0; i < 9; i++)
+#pragma unroll
+    for (int j = 0; j <= i; j++) a[i][j] = C[i * 9 + j] - (i == j ? sigma : 0.0);
+  bool pd = true;
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    const double d = a[k][k];
+    pd = pd && (d > 0.0);
+    const double inv = fast_rcp(d);
+    if (STORE && lane == 0) fac[81 + k] = inv;
+    double l[9];
+#pragma unroll
+    for (int i = k + 1; i < 9; i++) {
+      l[i] = a[i][k] * inv;
+      if (STORE && lane == 0) fac[i * 9 + k] = l[i];
+    }
+#pragma unroll
+    for (int i = k + 1; i < 9; i++)
+#pragma unroll
+      for (int j = k + 1; j <= i; j++) a[i][j] = fma(-l[i], a[j][k], a[i][j]);
+  }
+  return pd;
+}
+// Returns true and the unit eigenvector y[9] of the smallest eigenvalue of C (row-major 9x9 in shared memory,
+// symmetric); false if the bracket or the iteration did not behave (the caller then diagonalises C with the
+// cyclic Jacobi).  `fac` = 90 doubles of shared scratch.  Every lane ends up with the same y.
+__device__ bool smallest_eigvec9(const double* __restrict__ C, double* fac, int lane, double y[9]) {
+  double dmin = C[0], dmax = C[0];
+#pragma unroll
+  for (int k = 1; k < 9; k++) {
+    dmin = fmin(dmin, C[k * 9 + k]);
+    dmax = fmax(dmax, C[k * 9 + k]);
+  }
+  if (!(dmax > 0.0) || !(dmax < 1e300)) return false;
+  // lambda_1 <= every diagonal entry (Rayleigh quotient of a unit vector); >= -round-off
+  double lo = -1e-9 * dmax, hi = dmin + 1e-9 * dmax;
+  if (!__all_sync(0xffffffffu, ldl9_shifted<false>(C, lo, fac, lane))) return false;  // not PSD: leave it to Jacobi
+#pragma unroll 1
+  for (int round = 0; round < 8; round++) {
+    const double step = (hi - lo) * (1.0 / 33.0);
+    const double sigma = lo + step * double(lane + 1);
+    const unsigned ok = __ballot_sync(0xffffffffu, ldl9_shifted<false>(C, sigma, fac, lane));
+    const int j = __ffs(~ok) - 1;  // first shift that is not below lambda_1 (-1: all 32 are)
+    const double lo_new = j == 0 ? lo : lo + step * double(j < 0 ? 32 : j);
+    if (j >= 0) hi = lo + step * double(j + 1);
+    lo = lo_new;
+    if (!(hi - lo > 1e-15 * dmax)) break;
+  }
+  // inverse iteration with the shift at the lower end of the bracket (C - lo I is positive definite)
+  __syncwarp();
+  if (!__all_sync(0xffffffffu, ldl9_shifted<true>(C, lo, fac, lane))) return false;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 9; i++) y[i] = 1.0 + 0.0625 * double((i * 5) % 9);  // a fixed vector with no symmetry
+  bool converged = false;
+#pragma unroll 1
+  for (int it = 0; it < 10 && !converged; it++) {
+    double z[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) {  // L z = y
+      double v = y[i];
+#pragma unroll
+      for (int j = 0; j < i; j++) v = fma(-fac[i * 9 + j], z[j], v);
+      z[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) z[i] *= fac[81 + i];  // D
+#pragma unroll
+    for (int i = 8; i >= 0; i--) {  // L^T w = z
+      double v = z[i];
+#pragma unroll
+      for (int j = i + 1; j < 9; j++) v = fma(-fac[j * 9 + i], z[j], v);
+      z[i] = v;
+    }
+    double nn = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) nn = fma(z[i], z[i], nn);
+    if (!(nn > 0.0) || !(nn < 1e300)) return false;
+    const double inv = rsqrt(nn);
+    // fix the sign by the largest component so successive iterates are comparable
+    double big = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; i++)
+      if (fabs(z[i]) > fabs(big)) big = z[i];
+    const double sc = big < 0.0 ? -inv : inv;
+    double diff = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+      const double v = z[i] * sc;
+      diff = fmax(diff, fabs(v - y[i]));
+      y[i] = v;
+    }
+    converged = it > 0 && diff < 4e-15;
+  }
+  return converged;
+}
+
 // symmetric 3x3 eigen-decomposition in registers (every lane redundantly)
 __device__ void eig3(const double Cm[6] /*xx yy zz xy yz xz*/, double w[3], double V[3][3]) {
   double a[3][3] = {{Cm[0], Cm[3], Cm[5]}, {Cm[3], Cm[1], Cm[4]}, {Cm[5], Cm[4], Cm[2]}};
@@ -594,7 +717,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4)
 k_taubin_axes(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip,
               const int* __restrict__ indices, int s0, int n_samples_max, const int* __restrict__ d_count,
               const GPoint* __restrict__ pool, int stride, const int2* __restrict__ nn_counts, double inv_r,
-              const double* __restrict__ moments,
+              float r2_f, const double* __restrict__ moments,
               double cam0x, double cam0y, double cam0z, double cam1x, double cam1y, double cam1z,
               ag_frame* __restrict__ frames, double* normals_out /* may be null */,
               const uint32_t* __restrict__ rand_raw /* null = deterministic normals */,
@@ -704,19 +827,29 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip
       }
     }
     __syncwarp();
-    warp_jacobi9(sm.A, sm.V, lane);
-    // smallest eigenvalue (quadric.cpp:149-152), u = L^-T y, j = -m.u/n
-    int mi = 0;
-    for (int k = 1; k < 9; k++)
-      if (sm.A[k * 9 + k] < sm.A[mi * 9 + mi]) mi = k;
+    // smallest eigenvalue (quadric.cpp:149-152): bracket + inverse iteration; the cyclic Jacobi is the fallback
+    double yv[9];
+    const bool fast = g_force_jacobi ? false : smallest_eigvec9(sm.A, sm.V, lane, yv);
+    if (!fast) {
+      __syncwarp();
+      warp_jacobi9(sm.A, sm.V, lane);
+      int mi = 0;
+      for (int k = 1; k < 9; k++)
+        if (sm.A[k * 9 + k] < sm.A[mi * 9 + mi]) mi = k;
+#pragma unroll
+      for (int i = 0; i < 9; i++) yv[i] = sm.V[i * 9 + mi];
+    }
     __syncwarp();
-    if (lane == 0) {
+    if (lane == 0) {  // u = L^-T y, j = -m.u/n
       double u[9];
+#pragma unroll
       for (int i = 8; i >= 0; i--) {
-        double v = sm.V[i * 9 + mi];
+        double v = yv[i];
+#pragma unroll
         for (int k = i + 1; k < 9; k++) v -= sm.L[k * 9 + i] * u[k];
         u[i] = v / sm.L[i * 9 + i];
       }
+#pragma unroll
       for (int i = 0; i < 9; i++) sm.par[i] = u[i];
     }
   } else {
@@ -819,30 +952,99 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip
   GPoint pick[2];  // picks t = lane and t = lane + 32 (t < 50)
   pick[0] = pick[1] = q;
   if (picks) {
-    // (distance, index) rank of every neighbour: the list is in index order, so position breaks distance ties
-    for (int i = lane; i < n_list; i += 32) {
+    // The picks index the kd-tree's result order = ascending (distance, index).  Only 50 of the n order
+    // statistics are needed, so the list is not sorted: a counting sort groups the neighbours into distance
+    // buckets (a monotone function of the binary32 distance, ~3 neighbours per bucket), and every pick then
+    // selects its element inside one bucket by exact (distance, position) comparisons — the list is in index
+    // order, so the position breaks distance ties.  O(n) + O(50 m^2) instead of ranking all n against all n.
+    constexpr int nb = kRankBuckets;
+    const float bscale = float(nb) / r2_f;
+    auto dist_of = [&](int i) {
       const GPoint p = list[i];
-      rk.d2[i] = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
+      return dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
+    };
+    for (int i = lane; i < kRankBuckets; i += 32) rk.cur[i] = 0;
+    __syncwarp();
+    for (int i = lane; i < n_list; i += 32) {
+      const int b = min(nb - 1, int(dist_of(i) * bscale));
+      rk.bucket[i] = (unsigned char)b;
+      atomicAdd(&rk.cur[b], 1);
     }
     __syncwarp();
-    for (int i0 = 0; i0 < n_list; i0 += 32) {
-      const int i = i0 + lane;
-      const float di = i < n_list ? rk.d2[i] : 0.f;
-      int rank = 0;
-      for (int j = 0; j < n_list; j++) {
-        const float dj = rk.d2[j];
-        rank += (dj < di || (dj == di && j < i)) ? 1 : 0;
+    {  // exclusive prefix over the bucket counts: 8 consecutive buckets per lane
+      int c[8], tot = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        c[k] = rk.cur[8 * lane + k];
+        tot += c[k];
       }
-      if (i < n_list) rk.order[rank] = (unsigned short)i;
+      int incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      int run = incl - tot;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        rk.cur[8 * lane + k] = run;
+        run += c[k];
+      }
     }
     __syncwarp();
+    for (int i = lane; i < n_list; i += 32) rk.order[atomicAdd(&rk.cur[rk.bucket[i]], 1)] = (unsigned short)i;
+    __syncwarp();
+    // cur[b] is now the end of bucket b (= the start of bucket b + 1)
+    auto select_rank = [&](int r) {
+      int lo_b = 0, hi_b = nb - 1;  // first bucket whose end exceeds r
+      while (lo_b < hi_b) {
+        const int mid = (lo_b + hi_b) >> 1;
+        if (rk.cur[mid] > r) hi_b = mid;
+        else lo_b = mid + 1;
+      }
+      const int lo = lo_b > 0 ? rk.cur[lo_b - 1] : 0, hi = rk.cur[lo_b];
+      const int k = r - lo;
+      int found = rk.order[lo];
+      if (hi - lo <= 8) {  // the bucket's members once into registers, ranked against each other without branches
+        float d[8];
+        int id[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+          id[t] = lo + t < hi ? int(rk.order[lo + t]) : 0x7fffffff;
+          d[t] = lo + t < hi ? dist_of(id[t]) : 3.0e38f;
+        }
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+          int cnt = 0;
+#pragma unroll
+          for (int u = 0; u < 8; u++) cnt += (d[u] < d[t] || (d[u] == d[t] && id[u] < id[t])) ? 1 : 0;
+          if (cnt == k && lo + t < hi) found = id[t];
+        }
+        return found;
+      }
+      for (int a = lo; a < hi; a++) {
+        const int e = rk.order[a];
+        const float de = dist_of(e);
+        int cnt = 0;
+        for (int b2 = lo; b2 < hi; b2++) {
+          const int f = rk.order[b2];
+          const float df = dist_of(f);
+          cnt += (df < de || (df == de && f < e)) ? 1 : 0;
+        }
+        if (cnt == k) {
+          found = e;
+          break;
+        }
+      }
+      return found;
+    };
     const uint32_t* raw = rand_raw + size_t(50) * size_t(rand_off[s]);
     int cam1 = 0;
 #pragma unroll
     for (int u = 0; u < 2; u++) {
       const int t = lane + 32 * u;
       if (t < 50) {
-        pick[u] = list[rk.order[raw[t] % uint32_t(n_list)]];
+        pick[u] = list[select_rank(int(raw[t] % uint32_t(n_list)))];
         cam1 += int(pick[u].tag & kTagCamBit);
         accumulate(pick[u]);
       }
@@ -1113,7 +1315,11 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
   if (!attr_set) {
     cudaFuncSetAttribute(k_taubin_axes, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          int(sizeof(AxesSmem) * kWarps + sizeof(RankSmem) * kWarps));
-    cudaFuncSetAttribute(k_taubin_axes, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    cudaFuncSetAttribute(k_taubin_axes, cudaFuncAttributePreferredSharedMemoryCarveout, 75);  // 4 CTAs/SM in either mode
+    if (getenv("AG_FORCE_JACOBI")) {
+      const int one = 1;
+      cudaMemcpyToSymbol(g_force_jacobi, &one, sizeof(one));
+    }
     cudaFuncSetAttribute(k_ball_search, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     attr_set = true;
   }
@@ -1173,7 +1379,7 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
     }
     k_taubin_axes<<<blocks, kWarps * 32, smem, c->stream>>>(
         c->vox.as<GPoint>(), ri, d_indices, s0, s0 + m, d_count, c->nbr_pool.as<GPoint>(), stride,
-        c->nn_counts.as<int2>(), inv_r, c->moments.as<double>(), h.cam[0][0], h.cam[0][1], h.cam[0][2], h.cam[1][0],
+        c->nn_counts.as<int2>(), inv_r, r2, c->moments.as<double>(), h.cam[0][0], h.cam[0][1], h.cam[0][2], h.cam[1][0],
         h.cam[1][1], h.cam[1][2], d_frames, write_normals ? c->normals.as<double>() : nullptr, d_rand, d_rand_off);
     if (timed) record_event(c, c->ev_k[3]);
     c->launches += 3;

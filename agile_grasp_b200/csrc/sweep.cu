@@ -27,13 +27,9 @@ namespace ag {
 namespace {
 
 constexpr int kThreads = 256;       // 8 warps = 8 orientations (rotating_hand.cpp:13)
-constexpr int kSlabCapSmall = 2048; // slab points kept in shared memory by the common kernel (32 KB)
-constexpr int kSlabCapBig = 12032;  // fallback instantiation for dense neighbourhoods (188 KB, 1 CTA/SM)
-
-struct SlabPoint {  // centred neighbour, binary32 exactly as hand_search.cpp:157-158 produces it
-  float x, y, z;
-  uint32_t tag;
-};
+constexpr int kSlabCapSmall = 1920; // slab points kept in shared memory by the common kernel (37.5 KB, 3 CTAs / SM)
+constexpr int kSlabCapBig = 9600;   // fallback instantiation for dense neighbourhoods (187.5 KB, 1 CTA / SM)
+constexpr int kStage = 2048;        // candidates staged per pass of the ball gather (32 KB, reused by phase B)
 
 struct SweepArgs {
   const GPoint* pts;
@@ -62,36 +58,78 @@ __device__ __forceinline__ double dot3e(const double a[3], const double b[3]) {
   return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]);  // Eigen's unrolled 3-vector reduction order
 }
 
-// Exact rank of x in an ascending, (nearly) uniformly spaced threshold table, branch-free.
-// tab is stored with sentinels: tab[0] = -inf, tab[1..n] = thresholds, tab[n+1] = +inf.  The estimate
-// c0 = clamp(floor((x-base)/step) + 1, 0, n) can be off by one only when x is within rounding distance
-// of a threshold, so the true count is (c0-1) + [tab[c0] <cmp> x] + [tab[c0+1] <cmp> x]: two exact
-// binary64 comparisons — the very comparisons the reference evaluates slot by slot.
-__device__ __forceinline__ int rank_est(double x, double base, double inv_step, int n) {
-  return min(max(__double2int_rd((x - base) * inv_step) + 1, 0), n);
+// ---- PTX helpers: mbarrier + TMA bulk copy (global -> shared) -------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-struct SlotTables {    // shared-memory threshold tables with -inf / +inf sentinels (lane-varying indices)
-  double sp[2][12];    // slot lower edges per hand (ascending)
-  double spw[2][12];   // slot upper edges sp[i] + finger_width
-  double bite[14];     // deepening levels d_t (ascending), n_depths <= 12
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done)
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- the finger-slot predicates of one slab point, literally (finger_hand.cpp:54-95) ---------------
+// in bit i  : the point lies strictly inside slot i,            sp[i] < x < sp[i] + finger_width
+// side bit i: the point lies beyond slot i on the object side,  x > sp[i] + w (i <= 10)  |  x < sp[i] (i > 10)
+__host__ __device__ inline unsigned long long slot_masks_exact(const double* spacing, double fw, double x) {
+  unsigned in_mask = 0u, sd_mask = 0u;
+  for (int i = 0; i < 20; i++) {
+    const double lo = spacing[i], hi = spacing[i] + fw;  // finger_hand.cpp:56-57
+    if (x > lo && x < hi) in_mask |= 1u << i;
+    const bool side = (i <= 10) ? (x > hi) : (x < lo);  // finger_hand.cpp:72-82
+    if (side) sd_mask |= 1u << i;
+  }
+  return (static_cast<unsigned long long>(sd_mask) << 32) | in_mask;
+}
+
+constexpr float kLutMargin = 1e-4f;  // distance (in slot steps / depth steps) from a threshold below which the
+                                     // exact comparisons decide instead of the table
+
+// Shared memory of one CTA.  The 32 KB `u` block is the TMA staging buffer of the ball gather (phase A) and
+// then, per orientation, the depth-level slot masks and the grasp image (phase B).
+struct SweepShared {
+  union {
+    GPoint stage[kStage];
+    struct {
+      unsigned long long lvl[8][12][32];  // per warp, depth level and lane: (side << 32 | in) slot masks
+      uint32_t img[8][AG_IMAGE_WORDS];
+    } b;
+  } u;
+  unsigned long long lut[AG_SWEEP_LUT];  // slot masks per zone between two slot edges
+  double bite[12];
+  int run_start[128], run_pre[129];      // candidate run of every x-row of the ball, exclusive prefix of the lengths
+  int warp_tot[8];
+  unsigned long long bar;
+  unsigned long long cand;
+  int count;
 };
 
 template <int CAP>
 __global__ void __launch_bounds__(kThreads, CAP <= 2048 ? 3 : 1)
 k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  SlabPoint* slab = reinterpret_cast<SlabPoint*>(s_raw);
-  __shared__ uint32_t s_img[8][AG_IMAGE_WORDS];
-  __shared__ int s_count;
-  __shared__ unsigned long long s_cand;
-  __shared__ SlotTables s_tab;
-  __shared__ int s_rs[kThreads], s_pre[kThreads + 1], s_next;
-  __shared__ unsigned long long s_lvl[8][12][32];  // per warp, depth level and lane: (side<<32 | in) slot masks
+  SweepShared& sh = *reinterpret_cast<SweepShared*>(s_raw);
+  double2* slab_xy = reinterpret_cast<double2*>(s_raw + sizeof(SweepShared));  // hand-frame x, y of every slab point
+  uint32_t* slab_tag = reinterpret_cast<uint32_t*>(slab_xy + CAP);             // point index << 2 | tag bits
 
   const int s = A.sample_list ? A.sample_list[blockIdx.x] : blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
-  const RowIndex ri = *A.ri;
+  const RowIndex& ri = *A.ri;
   const int idx = (s < ri.n_samples) ? A.indices[s] : -1;
   if (idx < 0 || idx >= ri.n_points) {  // unused sample slot (fewer voxels than requested samples)
     if (lane == 0) A.valid[size_t(s) * 8 + warp] = 0;
@@ -100,23 +138,15 @@ k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
   }
   const GPoint q = A.pts[idx];
   const int sample_cam = (q.tag & kTagCamBit) ? 1 : 0;  // hands_cam_source (hand_search.cpp:40-42, App. B#3)
+  const uint32_t bar = smem_u32(&sh.bar);
   if (threadIdx.x == 0) {
-    s_count = 0;
-    s_cand = 0;
+    sh.count = 0;
+    sh.cand = 0;
+    mbar_init(bar, 1);
+    fence_proxy_async_smem();
   }
-  for (int i = lane; i < AG_IMAGE_WORDS; i += 32) s_img[warp][i] = 0u;
-  if (threadIdx.x < 24) {
-    const int hnd = threadIdx.x / 12, j = threadIdx.x % 12;
-    const double inf = __longlong_as_double(0x7FF0000000000000ll);
-    const double lo = j == 0 ? -inf : (j == 11 ? inf : hc.spacing[hnd * 10 + j - 1]);
-    s_tab.sp[hnd][j] = lo;
-    s_tab.spw[hnd][j] = (j == 0 || j == 11) ? lo : lo + hc.finger_width;  // finger_hand.cpp:56-57
-  }
-  if (threadIdx.x < 14) {
-    const double inf = __longlong_as_double(0x7FF0000000000000ll);
-    const int j = threadIdx.x;
-    s_tab.bite[j] = j == 0 ? -inf : (j <= hc.n_depths ? hc.bite[j - 1] : inf);
-  }
+  if (threadIdx.x < AG_SWEEP_LUT) sh.lut[threadIdx.x] = hc.lut[threadIdx.x];
+  if (threadIdx.x < 12) sh.bite[threadIdx.x] = hc.bite[threadIdx.x];
 
   // ---- frame = [normal | normal x axis | axis]   (rotating_hand.cpp:25)
   const ag_frame fr = A.frames[s];
@@ -132,95 +162,130 @@ k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
       F[r][2] = b[r];
     }
   }
-  __syncthreads();
 
   // ---- phase A: gather the r = 0.08 ball, keep the |z_hand| < hand_height slab -----------------
-  // One candidate run per x-row the ball can touch (binary search on y, ag_common.cuh), one thread per
-  // row; the warps then pull runs from a shared counter and stream them, two independent 16-byte loads
-  // in flight per lane.
-  {
-    int klo[2] = {0, 0}, rows[2] = {0, 0};
-    for (int c = 0; c < 2; c++) {
-      if (ri.count[c] == 0) continue;
-      int k_hi;
-      row_range(ri, c, q.x, A.rpad, klo[c], k_hi);
-      rows[c] = max(0, k_hi - klo[c] + 1);
+  // One candidate run per x-row the ball can touch (two loads from the column table, ag_common.cuh), one thread
+  // per row.  A run is contiguous in the voxel list, so every row thread moves its run with ONE TMA bulk copy
+  // (cp.async.bulk) into the CTA's staging buffer at the run's prefix offset; one mbarrier transaction count
+  // tracks them all: the whole ball is in flight at once and no registers are held for it.  The 256 threads then
+  // test the staged candidates (FLANN's binary32 distance, then the slab) and append the survivors — already
+  // rotated into the hand frame — to the slab.
+  int klo[2] = {0, 0}, rows[2] = {0, 0};
+  for (int c = 0; c < 2; c++) {
+    if (ri.count[c] == 0) continue;
+    int k_hi;
+    row_range(ri, c, q.x, A.rpad, klo[c], k_hi);
+    rows[c] = max(0, k_hi - klo[c] + 1);
+  }
+  const int ncol = rows[0] + rows[1];
+  const float fzx = float(F[0][2]), fzy = float(F[1][2]), fzz = float(F[2][2]), hh = float(hc.hand_height);
+  unsigned n_ball = 0;
+  unsigned long long n_cand = 0;
+  uint32_t parity = 0;
+  for (int cbase = 0; cbase < ncol; cbase += 128) {  // one batch for the shipped radii (55 rows per camera)
+    const int nc = min(128, ncol - cbase);
+    int j0 = 0, len = 0;
+    if (threadIdx.x < nc) {
+      const int col = cbase + threadIdx.x;
+      const int c = col < rows[0] ? 0 : 1;
+      const int k = klo[c] + (c == 0 ? col : col - rows[0]);
+      int j1;
+      row_run(ri, A.row_ptr, A.col_ptr, A.pts, c, k, q.x, q.y, A.rpad, j0, j1);
+      len = max(0, j1 - j0);
     }
-    const int ncol = rows[0] + rows[1];
-    unsigned long long nball = 0, ncand = 0;
-    for (int cbase = 0; cbase < ncol; cbase += kThreads) {  // one batch for the shipped radii
-      const int nc = min(kThreads, ncol - cbase);
-      if (threadIdx.x < nc) {
-        const int col = cbase + threadIdx.x;
-        const int c = col < rows[0] ? 0 : 1;
-        const int k = klo[c] + (c == 0 ? col : col - rows[0]);
-        int j0, j1;
-        row_run(ri, A.row_ptr, A.col_ptr, A.pts, c, k, q.x, q.y, A.rpad, j0, j1);
-        s_rs[threadIdx.x] = j0;
-        s_pre[threadIdx.x] = j1;
-      }
-      if (threadIdx.x == 0) s_next = 0;
+    // exclusive prefix of the run lengths over the (<= 128) row threads
+    int incl = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) sh.warp_tot[warp] = incl;
+    __syncthreads();
+    int pre = incl - len;
+    for (int w = 0; w < warp && w < 4; w++) pre += sh.warp_tot[w];
+    const int total = sh.warp_tot[0] + sh.warp_tot[1] + sh.warp_tot[2] + sh.warp_tot[3];
+    if (threadIdx.x < nc) {
+      sh.run_start[threadIdx.x] = j0;
+      sh.run_pre[threadIdx.x] = pre;
+    }
+    if (threadIdx.x == 0) sh.run_pre[nc] = total;
+    n_cand += threadIdx.x == 0 ? (unsigned long long)total : 0ull;
+    for (int base = 0; base < total; base += kStage) {
+      const int cnt = min(kStage, total - base);
+      fence_proxy_async_smem();  // earlier generic-proxy accesses of the staging buffer precede the async writes
       __syncthreads();
-      for (;;) {
-        int run = 0;
-        if (lane == 0) run = atomicAdd(&s_next, 1);
-        run = __shfl_sync(0xffffffffu, run, 0);
-        if (run >= nc) break;
-        const int j0 = s_rs[run], j1 = s_pre[run];
-        ncand += (unsigned long long)(j1 - j0);
-        for (int jb = j0; jb < j1; jb += 64) {
-          GPoint p[2];
-          bool valid[2];
-#pragma unroll
-          for (int u = 0; u < 2; u++) {
-            const int j = jb + u * 32 + lane;
-            valid[u] = j < j1;
-            p[u].x = p[u].y = p[u].z = 0.f;
-            p[u].tag = 0;
-            if (valid[u]) {
-              p[u] = A.pts[j];
-              p[u].tag = (uint32_t(j) << 2) | (p[u].tag & 3u);  // keep the point index for the normal fetch
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 2; u++) {
-            if (u == 1 && jb + 32 >= j1) break;  // uniform
-            bool keep = false, inball = false;
-            SlabPoint sp;
-            sp.x = sp.y = sp.z = 0.f;
-            sp.tag = 0;
-            if (valid[u] && dist2_flann(q.x, q.y, q.z, p[u].x, p[u].y, p[u].z) < A.r2) {
-              inball = true;
-              // hand_search.cpp:157-158: subtraction in binary32, then cast
-              sp.x = __fsub_rn(p[u].x, q.x);
-              sp.y = __fsub_rn(p[u].y, q.y);
-              sp.z = __fsub_rn(p[u].z, q.z);
-              sp.tag = p[u].tag;
-              const double hz = (F[0][2] * double(sp.x) + F[1][2] * double(sp.y)) + F[2][2] * double(sp.z);
-              keep = hz > -1.0 * hc.hand_height && hz < hc.hand_height;  // rotating_hand.cpp:44
-            }
-            nball += __popc(__ballot_sync(0xffffffffu, inball));
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (m) {
-              int wbase = 0;
-              if (lane == 0) wbase = atomicAdd(&s_count, __popc(m));
-              wbase = __shfl_sync(0xffffffffu, wbase, 0);
-              const int pos = wbase + __popc(m & lt);
-              if (keep && pos < CAP) slab[pos] = sp;
+      if (threadIdx.x == 0) mbar_expect_tx(bar, uint32_t(cnt) * 16u);
+      __syncthreads();
+      {  // this row's share of the pass: [pre, pre + len) clipped to [base, base + cnt)
+        const int a = max(pre, base), b = min(pre + len, base + cnt);
+        if (threadIdx.x < nc && b > a)
+          bulk_g2s(smem_u32(&sh.u.stage[a - base]), A.pts + j0 + (a - pre), uint32_t(b - a) * 16u, bar);
+      }
+      mbar_wait(bar, parity);
+      parity ^= 1u;
+      for (int i0 = 0; i0 < cnt; i0 += kThreads) {
+        const int i = i0 + threadIdx.x;
+        bool keep = false, inball = false;
+        GPoint p;
+        float cx = 0.f, cy = 0.f, cz = 0.f;
+        if (i < cnt) {
+          p = sh.u.stage[i];
+          if (dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z) < A.r2) {
+            inball = true;
+            // hand_search.cpp:157-158: subtraction in binary32, then cast
+            cx = __fsub_rn(p.x, q.x);
+            cy = __fsub_rn(p.y, q.y);
+            cz = __fsub_rn(p.z, q.z);
+            // slab test -h < z_hand < h (rotating_hand.cpp:44): decided in binary32 when the point is clearly
+            // inside or outside (the binary32 value is within 1e-7 of the binary64 one), exactly otherwise
+            const float hzf = fmaf(fzx, cx, fmaf(fzy, cy, fzz * cz));
+            const float az = fabsf(hzf);
+            if (az < hh - 1e-5f) keep = true;
+            else if (az <= hh + 1e-5f) {
+              const double hz = (F[0][2] * double(cx) + F[1][2] * double(cy)) + F[2][2] * double(cz);
+              keep = hz > -1.0 * hc.hand_height && hz < hc.hand_height;
             }
           }
         }
+        n_ball += __popc(__ballot_sync(0xffffffffu, inball));
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m) {
+          int wbase = 0;
+          if (lane == 0) wbase = atomicAdd(&sh.count, __popc(m));
+          wbase = __shfl_sync(0xffffffffu, wbase, 0);
+          const int pos = wbase + __popc(m & lt);
+          if (keep && pos < CAP) {
+            const double px = double(cx), py = double(cy), pz = double(cz);
+            double2 h;  // frame^T * p (rotating_hand.cpp:26)
+            h.x = (F[0][0] * px + F[1][0] * py) + F[2][0] * pz;
+            h.y = (F[0][1] * px + F[1][1] * py) + F[2][1] * pz;
+            slab_xy[pos] = h;
+            uint32_t tag = p.tag & 3u;
+            if (tag & kTagNormalBit) {  // the point index is only needed to fetch its normal: row of position base + i
+              const int g = base + i;
+              int lo_r = 0, hi_r = nc - 1;
+              while (lo_r < hi_r) {
+                const int mid = (lo_r + hi_r + 1) >> 1;
+                if (sh.run_pre[mid] <= g) lo_r = mid;
+                else hi_r = mid - 1;
+              }
+              tag |= uint32_t(sh.run_start[lo_r] + (g - sh.run_pre[lo_r])) << 2;
+            }
+            slab_tag[pos] = tag;
+          }
+        }
       }
-      __syncthreads();
     }
-    if (lane == 0) atomicAdd(&s_cand, ncand | (nball << 32));
+    __syncthreads();
   }
+  if (lane == 0) atomicAdd(&sh.cand, (unsigned long long)n_ball << 32);
   __syncthreads();
-  const int k = s_count;
+  const int k = sh.count;
   if (threadIdx.x == 0) {
     if (A.slab_counts) A.slab_counts[s] = k;
-    atomicAdd(&A.counters[2], s_cand >> 32);
-    atomicAdd(&A.counters[3], s_cand & 0xFFFFFFFFull);
+    atomicAdd(&A.counters[2], sh.cand >> 32);
+    atomicAdd(&A.counters[3], n_cand);
     if (k > CAP) {  // does not fit: queue the sample for the large-capacity instantiation
       const int w = atomicAdd(A.overflow, 1);
       A.overflow[1 + w] = s;
@@ -257,72 +322,58 @@ k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
   unsigned fingers_last = 0;
   bool have = false;
   double minY = 1e300, maxY = -1e300;
+  uint32_t* img = sh.u.b.img[warp];
+  for (int i = lane; i < AG_IMAGE_WORDS; i += 32) img[i] = 0u;
   const bool cam_ok = !(dot3e(approach, camv0) > 0 && dot3e(approach, camv1) > 0);  // rotating_hand.cpp:99
   if (cam_ok) {
-    // pass 1: slot masks per depth level
-    unsigned IN[12], SD[12];
+    // pass 1: slot masks per depth level.  Every boolean of FingerHand is "is there a point with y < d_t whose x
+    // lies in some interval", so each point ORs its 20 + 20 slot bits into the first depth level that crops it
+    // in.  Between two consecutive slot edges the bits are constant: they come from a 44-entry table indexed
+    // by the zone of x (slot edges are two interleaved uniform grids, so the zone is a floor and a fraction
+    // test); a point closer than kLutMargin steps to an edge — or a hand geometry without the table — takes the
+    // reference's own comparisons slot by slot.  Same for the depth level of y.
+    unsigned long long(*lvl)[32] = sh.u.b.lvl[warp];
 #pragma unroll
-    for (int t = 0; t < 12; t++) s_lvl[warp][t][lane] = 0ull;
+    for (int t = 0; t < 12; t++) lvl[t][lane] = 0ull;
+    const double deepest = hc.bite[hc.n_depths - 1];
+    const float phi = hc.lut_phi;
 #pragma unroll 2
     for (int j = lane; j < k; j += 32) {
-      const SlabPoint p = slab[j];
-      const double px = double(p.x), py = double(p.y), pz = double(p.z);
-      const double hx = (F[0][0] * px + F[1][0] * py) + F[2][0] * pz;  // frame^T * p (rotating_hand.cpp:26)
-      const double hy = (F[0][1] * px + F[1][1] * py) + F[2][1] * pz;
-      const double rx = cs * hx + msn * hy;  // rot * p (rotating_hand.cpp:91); the 0*z term is exact
-      const double ry = sn * hx + cs * hy;
+      const double2 h = slab_xy[j];
+      const double rx = cs * h.x + msn * h.y;  // rot * p (rotating_hand.cpp:91); the 0*z term is exact
+      const double ry = sn * h.x + cs * h.y;
       minY = fmin(minY, ry);
       maxY = fmax(maxY, ry);
-      if (!(ry < hc.bite[hc.n_depths - 1])) continue;  // above the deepest bite: never cropped in
-      unsigned in_mask, sd_mask;
-      if (hc.uniform_slots) {
-        // slot i is entered iff sp[i] < rx < spw[i]; both tables ascend within a hand, so the sets
-        // {i: rx > sp[i]}, {i: rx >= spw[i]}, {i: rx > spw[i]} are prefixes given by three exact ranks
-        unsigned gt[2], ge[2], gw[2];
-        int a_rank[2];
-#pragma unroll
-        for (int hnd = 0; hnd < 2; hnd++) {
-          const double* sp = s_tab.sp[hnd];
-          const double* sw = s_tab.spw[hnd];
-          const int e0 = rank_est(rx, hc.spacing[hnd * 10], hc.inv_slot_step, 10);
-          const int e1 = rank_est(rx, hc.spacing[hnd * 10] + hc.finger_width, hc.inv_slot_step, 10);
-          const double s0 = sp[e0], s1 = sp[e0 + 1], w0 = sw[e1], w1 = sw[e1 + 1];
-          const int a = e0 - 1 + (s0 < rx ? 1 : 0) + (s1 < rx ? 1 : 0);    // #{sp  <  rx}
-          const int bq = e1 - 1 + (w0 <= rx ? 1 : 0) + (w1 <= rx ? 1 : 0); // #{spw <= rx}
-          const int cq = e1 - 1 + (w0 < rx ? 1 : 0) + (w1 < rx ? 1 : 0);   // #{spw <  rx}
-          a_rank[hnd] = a;
-          gt[hnd] = (1u << a) - 1u;
-          ge[hnd] = (1u << bq) - 1u;
-          gw[hnd] = (1u << cq) - 1u;
-        }
-        in_mask = (gt[0] & ~ge[0]) | ((gt[1] & ~ge[1]) << 10);
-        // finger_hand.cpp:72-82: slots 0..10 need a point beyond their upper edge, 11..19 one below their lower edge
-        sd_mask = gw[0] | ((gw[1] & 1u) << 10) | (((~gt[1]) & 0x3FEu) << 10);
-        // rx < sp[i] is NOT(rx > sp[i]) AND NOT(rx == sp[i]); correct the equality case exactly
-        const int aR = a_rank[1];
-        if (aR >= 1 && aR < 10 && rx == s_tab.sp[1][aR + 1]) sd_mask &= ~(1u << (10 + aR));
+      if (!(ry < deepest)) continue;  // above the deepest bite: never cropped in
+      const double tx = (rx - hc.spacing[0]) * hc.inv_slot_step;
+      const double ty = (ry - hc.bite[0]) * hc.inv_bite_step;
+      const int kx = __double2int_rd(tx), ky = __double2int_rd(ty);
+      const float fx = float(tx - double(kx)), fy = float(ty - double(ky));
+      const bool zone_a = fx > kLutMargin && fx < phi - kLutMargin;
+      const bool zone_b = fx > phi + kLutMargin && fx < 1.0f - kLutMargin;
+      const bool far_x = kx < -1 || kx > AG_SWEEP_LUT / 2 - 2;
+      const bool y_ok = fy > kLutMargin && fy < 1.0f - kLutMargin;
+      unsigned long long m;
+      int L;
+      if (hc.lut_ok && (zone_a || zone_b || far_x) && y_ok) {
+        const int kc = min(max(kx, -1), AG_SWEEP_LUT / 2 - 2) + 1;
+        m = sh.lut[2 * kc + (zone_a && !far_x ? 0 : 1)];
+        L = min(max(ky + 1, 0), hc.n_depths - 1);
       } else {
-        in_mask = 0u;
-        sd_mask = 0u;
-#pragma unroll
-        for (int i = 0; i < 20; i++) {
-          const double lo = hc.spacing[i], hi = hc.spacing[i] + hc.finger_width;  // finger_hand.cpp:56-57
-          if (rx > lo && rx < hi) in_mask |= 1u << i;
-          const bool side = (i <= 10) ? (rx > hi) : (rx < lo);  // finger_hand.cpp:72-82
-          if (side) sd_mask |= 1u << i;
-        }
+        m = slot_masks_exact(hc.spacing, hc.finger_width, rx);
+        L = 0;
+        for (int t = 0; t < hc.n_depths; t++) L += (sh.bite[t] <= ry) ? 1 : 0;
       }
       // the point is cropped in at every depth level d_t > ry, i.e. at levels t >= L = #{t : d_t <= ry}
       // (L < n_depths here); record it at level L only, the prefix-OR below spreads it upwards
-      const int e = rank_est(ry, hc.bite[0], 200.0, hc.n_depths);
-      const int L = e - 1 + (s_tab.bite[e] <= ry ? 1 : 0) + (s_tab.bite[e + 1] <= ry ? 1 : 0);
-      s_lvl[warp][L][lane] |= (static_cast<unsigned long long>(sd_mask) << 32) | in_mask;
+      lvl[L][lane] |= m;
     }
+    unsigned IN[12], SD[12];
     {
       unsigned long long acc = 0ull;
 #pragma unroll
       for (int t = 0; t < 12; t++) {
-        acc |= s_lvl[warp][t][lane];
+        acc |= lvl[t][lane];
         IN[t] = unsigned(acc);
         SD[t] = unsigned(acc >> 32);
       }
@@ -383,14 +434,18 @@ k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
   const double left = hc.spacing[e_idx], right = hc.spacing[10 + e_idx];
   double wmin = 100000.0, wmax = -100000.0;
   int m_box = 0, numl = 0, numr = 0;
-  uint32_t* img = s_img[warp];
+  // floor(v / img_cell) (learning.cpp:330-335): a product with the reciprocal, unless that lands within 1e-6 of
+  // an integer — then the reference's own division decides
+  auto cell_of = [&](double v) {
+    const double qf = v * hc.inv_img_cell;
+    const double fl = floor(qf);
+    const double fr2 = qf - fl;
+    return (fr2 > 1e-6 && fr2 < 1.0 - 1e-6) ? fl : floor(v / hc.img_cell);
+  };
   for (int j = lane; j < k; j += 32) {
-    const SlabPoint p = slab[j];
-    const double px = double(p.x), py = double(p.y), pz = double(p.z);
-    const double hx = (F[0][0] * px + F[1][0] * py) + F[2][0] * pz;
-    const double hy = (F[0][1] * px + F[1][1] * py) + F[2][1] * pz;
-    const double rx = cs * hx + msn * hy;
-    const double ry = sn * hx + cs * hy;
+    const double2 h = slab_xy[j];
+    const double rx = cs * h.x + msn * h.y;
+    const double ry = sn * h.x + cs * h.y;
     if (ry < hc.bite[0] && rx > left && rx < right) {  // finger_hand.cpp:159-167
       wmin = fmin(wmin, rx);
       wmax = fmax(wmax, rx);
@@ -399,14 +454,15 @@ k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
       m_box++;
       // learning.cpp:320-365 on points_for_learning = rotated point - surface (frame mix-up kept)
       const double bx = rx - surface3[0], by = ry - surface3[1];
-      const double hcell = floor(((keep_sign ? bx : -bx) - (-0.05)) / hc.img_cell);
-      const double vcell = floor((by - 0.0) / hc.img_cell);
-      const int h = int(fmin(99.0, fmax(0.0, hcell)));
-      const int v = int(fmin(79.0, fmax(0.0, vcell)));
-      const int bit = (AG_IMAGE_ROWS - 1 - v) * AG_IMAGE_COLS + h;
+      const double hcell = cell_of((keep_sign ? bx : -bx) - (-0.05));
+      const double vcell = cell_of(by - 0.0);
+      const int hpx = int(fmin(99.0, fmax(0.0, hcell)));
+      const int vpx = int(fmin(79.0, fmax(0.0, vcell)));
+      const int bit = (AG_IMAGE_ROWS - 1 - vpx) * AG_IMAGE_COLS + hpx;
       atomicOr(&img[bit >> 5], 1u << (bit & 31));
-      if (p.tag & kTagNormalBit) {  // antipodal.cpp:12-86 on rot * frame^T * normal
-        const double* nv = A.normals + size_t(3) * (p.tag >> 2);
+      const uint32_t tag = slab_tag[j];
+      if (tag & kTagNormalBit) {  // antipodal.cpp:12-86 on rot * frame^T * normal
+        const double* nv = A.normals + size_t(3) * (tag >> 2);
         const double n0 = nv[0], n1 = nv[1], n2 = nv[2];
         const double hn0 = (F[0][0] * n0 + F[1][0] * n1) + F[2][0] * n2;
         const double hn1 = (F[0][1] * n0 + F[1][1] * n1) + F[2][1] * n2;
@@ -657,15 +713,45 @@ void compute_hand_const(const ag_params& p, HandConst& h) {
     h.cam[0][a] = p.cam_tf_left[4 * a + 3];
     h.cam[1][a] = p.cam_tf_right[4 * a + 3];
   }
-  // fast slot lookup needs both hands' edge tables strictly ascending with a common step
+  // slot-mask table: valid when the 40 slot edges are where the uniform model puts them (lower edges at integer
+  // multiples of the step from spacing[0], upper edges a fraction phi further) — checked by evaluating the exact
+  // predicates at three probes of every zone; any disagreement (odd geometry) disables the table
   h.inv_slot_step = step > 0 ? 1.0 / step : 0.0;
-  h.uniform_slots = step > 0 && p.finger_width > 0 ? 1 : 0;
-  if (const char* e = getenv("AG_SWEEP_FAST")) h.uniform_slots = h.uniform_slots && atoi(e) != 0;  // diagnostics
-  for (int i = 1; i < 10 && h.uniform_slots; i++)
-    if (!(h.spacing[i] > h.spacing[i - 1]) || !(h.spacing[10 + i] > h.spacing[9 + i]) ||
-        !(h.spacing[i] + p.finger_width > h.spacing[i - 1] + p.finger_width))
-      h.uniform_slots = 0;
+  h.inv_bite_step = 1.0 / 0.005;
+  h.lut_ok = 0;
+  h.lut_phi = 0.5f;
+  for (int z = 0; z < AG_SWEEP_LUT; z++) h.lut[z] = 0ull;
+  if (step > 0 && p.finger_width > 0) {
+    const double w = p.finger_width / step;
+    const double phi = w - floor(w);
+    const int k_last = 18 + int(floor(w)) + 1;  // zone index of the last upper edge, plus one
+    bool ok = phi > 0.01 && phi < 0.99 && k_last <= AG_SWEEP_LUT / 2 - 2;
+    for (int k = -1; k <= AG_SWEEP_LUT / 2 - 2 && ok; k++)
+      for (int zb = 0; zb < 2 && ok; zb++) {
+        const double f_lo = zb ? phi : 0.0, f_hi = zb ? 1.0 : phi;
+        const double probes[3] = {f_lo + 0.5e-4, 0.5 * (f_lo + f_hi), f_hi - 0.5e-4};
+        unsigned long long m[3];
+        for (int t = 0; t < 3; t++) m[t] = slot_masks_exact(h.spacing, p.finger_width, h.spacing[0] + (double(k) + probes[t]) * step);
+        ok = m[0] == m[1] && m[1] == m[2];
+        h.lut[2 * (k + 1) + zb] = m[1];
+      }
+    // beyond the table on either side nothing changes any more
+    ok = ok && slot_masks_exact(h.spacing, p.finger_width, h.spacing[0] - 1e3) == h.lut[0] &&
+         slot_masks_exact(h.spacing, p.finger_width, h.spacing[0] + 1e3) == h.lut[AG_SWEEP_LUT - 1];
+    // the depth levels must sit at integer multiples of 0.005 from the first one (to 1e-9)
+    for (int t = 0; t < 12 && ok; t++) {
+      const double d = p.init_bite + 0.005 * double(t);
+      // (h.bite is filled below; recompute the accumulation here)
+      double acc = p.init_bite;
+      for (int u = 0; u < t; u++) acc += 0.005;
+      ok = fabs(acc - d) < 1e-12;
+    }
+    if (const char* e = getenv("AG_SWEEP_FAST")) ok = ok && atoi(e) != 0;  // diagnostics: force the exact comparisons
+    h.lut_ok = ok ? 1 : 0;
+    h.lut_phi = float(phi);
+  }
   h.img_cell = (0.05 - (-0.05)) / double(AG_IMAGE_COLS);  // learning.cpp:322-324
+  h.inv_img_cell = 1.0 / h.img_cell;
   h.half_od = p.hand_outer_diameter / 2.0;
 }
 
@@ -759,8 +845,8 @@ int hand_sweep_enqueue(Ctx* c, const int* d_indices, int n, const ag_frame* d_fr
       c->sweep_dbg.reserve(size_t(n) * 4 + slots * 4) || c->overflow.reserve(size_t(n + 1) * 4))
     return AG_ERR_CUDA;
   SweepArgs A = make_args(c, d_indices, n, d_frames, flags);
-  const size_t smem_small = size_t(kSlabCapSmall) * sizeof(SlabPoint);
-  const size_t smem_big = size_t(kSlabCapBig) * sizeof(SlabPoint);
+  const size_t smem_small = sizeof(SweepShared) + size_t(kSlabCapSmall) * 20;
+  const size_t smem_big = sizeof(SweepShared) + size_t(kSlabCapBig) * 20;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_hand_sweep<kSlabCapSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_small));
@@ -789,7 +875,7 @@ int hand_sweep_finish(Ctx* c, int n, int n_over, int* n_hyp) {
     AG_CUDA_CHECK(cudaMemcpyAsync(list.p, A.overflow + 1, size_t(n_over) * 4, cudaMemcpyDeviceToDevice, c->stream));
     AG_CUDA_CHECK(cudaMemsetAsync(A.overflow, 0, 4, c->stream));
     A.sample_list = list.as<int>();
-    const size_t smem_big = size_t(kSlabCapBig) * sizeof(SlabPoint);
+    const size_t smem_big = sizeof(SweepShared) + size_t(kSlabCapBig) * 20;
     k_hand_sweep<kSlabCapBig><<<n_over, kThreads, smem_big, c->stream>>>(A, c->hand);
     c->launches += 2;
     int rc = compact(c, A, slots);
@@ -799,7 +885,7 @@ int hand_sweep_finish(Ctx* c, int n, int n_over, int* n_hyp) {
     AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     list.release();
     if (over2) {
-      set_error("hand sweep: a sample's slab exceeded the shared-memory capacity (12032 points)");
+      set_error("hand sweep: a sample's slab exceeded the shared-memory capacity (9600 points)");
       return AG_ERR_CAPACITY;
     }
   }

@@ -6,9 +6,11 @@ from agile_grasp_b200 import api, scenes
 cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 warm = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 pts, size_left, P, S = scenes.config_cloud(cfg)
+P.deterministic_normals = int(sys.argv[3]) if len(sys.argv) > 3 else 0  # 0 = the reference's production mode
 ctx = api.Context(0, P)
 svm = api.Svm(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests/golden/svm_032015_linear_20_20_same"))
 rt = ctypes.CDLL("libcudart.so")
+ctx.set_svm(svm)
 for _ in range(warm):
     g = ctx.localize(pts, size_left); ctx.classify(svm, g)
 rt.cudaProfilerStart()
