@@ -45,6 +45,8 @@ struct RowIndex {         // lives in device memory, written by the voxelisation
 constexpr int kErrKeyOverflow = 1;   // voxel key outside the workspace-derived bit budget
 constexpr int kErrBadIndex = 2;      // a caller-supplied sample index is outside the voxelised cloud
 constexpr int kErrBallOverflow = 4;  // a radius ball held more points than a neighbour-pool slot
+constexpr int kErrBitmapRetry = 8;   // the voxel lattice does not fit the occupancy bitmap: re-run on the key-sort path
+constexpr int AG_RETRY_KEYSORT = 1;  // internal status (> 0): the caller switches the context to the key-sort path and re-runs
 
 // voxel record: xyz + tag.  tag bit 0 = camera source, bit 1 = "cloud_normals_ holds a non-zero normal"
 struct __align__(16) GPoint {

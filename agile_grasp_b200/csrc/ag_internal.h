@@ -92,6 +92,8 @@ struct Ctx {
   HandConst hand;
   // raw input + preprocessing
   DevBuf raw, keys, keys_sorted, keys_unique, cub_tmp, block_counts, misc;
+  DevBuf bitmap, tile_state;  // occupancy-bitmap voxelisation: one bit per lattice cell, tile states of its scan
+  bool bitmap_ok = true;      // false once a cloud's lattice did not fit: the context stays on the key-sort path
   void* h_pinned = nullptr;  // pinned staging for inputs / outputs
   size_t h_pinned_cap = 0;
   // voxelised cloud (API index space = the reference's voxel order) and its x-row index

@@ -561,6 +561,7 @@ static int localize_end(Ctx* c, ag_grasp** out, int* n_out) {
   c->n_vox = h->n_vox;
   c->timings.n_voxels = h->n_vox;
   c->timings.n_samples = h->n_samples;
+  if (h->error & kErrBitmapRetry) return AG_RETRY_KEYSORT;  // (the caller re-runs the call on the key-sort path)
   if (h->error & kErrKeyOverflow) {
     set_error("voxel index exceeds the key range (workspace extent / voxel_size > 2^21 cells)");
     return AG_ERR_CAPACITY;
@@ -615,6 +616,21 @@ static int localize_end(Ctx* c, ag_grasp** out, int* n_out) {
   *out = res;
   *n_out = Hn;
   return AG_OK;
+}
+
+// localize_begin + localize_end; a cloud whose voxel lattice does not fit the occupancy bitmap is re-run once on the
+// key-sort path, and the context stays on that path (the scene extents of a camera setup do not change per frame)
+static int localize_run(Ctx* c, const void* d_points, int stride, int n_in, int size_left, const int* indices,
+                        int n_indices, unsigned flags, ag_grasp** out, int* n_out) {
+  int rc = localize_begin(c, d_points, stride, n_in, size_left, indices, n_indices, flags);
+  if (rc == AG_OK) rc = localize_end(c, out, n_out);
+  if (rc == AG_RETRY_KEYSORT) {
+    c->bitmap_ok = false;
+    c->state_gen++;
+    rc = localize_begin(c, d_points, stride, n_in, size_left, indices, n_indices, flags);
+    if (rc == AG_OK) rc = localize_end(c, out, n_out);
+  }
+  return rc;
 }
 
 }  // namespace ag
@@ -699,7 +715,7 @@ void ag_destroy(ag_ctx* h) {
   for (GraphSlot& g : c.gslots)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (c.h_out) cudaFreeHost(c.h_out);
-  for (DevBuf* b : {&c.raw, &c.keys, &c.keys_sorted, &c.keys_unique, &c.cub_tmp, &c.block_counts, &c.misc, &c.vox,
+  for (DevBuf* b : {&c.raw, &c.keys, &c.keys_sorted, &c.keys_unique, &c.cub_tmp, &c.block_counts, &c.misc, &c.bitmap, &c.tile_state, &c.vox,
                     &c.row_ptr, &c.col_ptr, &c.row_index, &c.all_frames,
                     &c.normals, &c.samples, &c.sample_stage, &c.moments, &c.frames, &c.nn_counts, &c.nbr_pool, &c.nbr_heads, &c.rand_raw, &c.rand_off, &c.rand_carry, &c.grasps_raw, &c.valid,
                     &c.images_raw, &c.hyp_slots, &c.grasps, &c.counters, &c.scores, &c.descriptors, &c.kvals, &c.handle_in, &c.handle_bits, &c.sweep_dbg, &c.overflow})
@@ -777,8 +793,7 @@ int ag_localize(ag_ctx* h, const void* points, int stride, int n_in, int size_le
   if (c.raw.reserve(bytes)) return AG_ERR_CUDA;
   cudaEventRecord(c.ev[0], c.stream);
   AG_CUDA_CHECK(cudaMemcpyAsync(c.raw.p, points, bytes, cudaMemcpyHostToDevice, c.stream));
-  int rc = localize_begin(&c, c.raw.p, stride, n_in, size_left, indices, n_indices, flags);
-  if (rc == AG_OK) rc = localize_end(&c, out, n_out);
+  int rc = localize_run(&c, c.raw.p, stride, n_in, size_left, indices, n_indices, flags, out, n_out);
   c.timings.h2d_ms = elapsed(c.ev[0], c.ev[1]);
   return rc;
 }
@@ -793,9 +808,7 @@ int ag_localize_device(ag_ctx* h, const void* d_points, int stride, int n_in, in
   Ctx& c = h->c;
   cudaSetDevice(c.device);
   cudaEventRecord(c.ev[0], c.stream);
-  int rc = localize_begin(&c, d_points, stride, n_in, size_left, indices, n_indices, flags);
-  if (rc == AG_OK) rc = localize_end(&c, out, n_out);
-  return rc;
+  return localize_run(&c, d_points, stride, n_in, size_left, indices, n_indices, flags, out, n_out);
 }
 
 int ag_classify(ag_ctx* h, const ag_svm* svm, ag_grasp* grasps, int n, uint8_t* keep) {
@@ -906,6 +919,11 @@ int ag_localize_batch(ag_ctx* h, int n_clouds, const void* const* points, const 
     if (i < 0) return;
     pending[l] = -1;
     if (rcs[i] == AG_OK) rcs[i] = localize_end(lane[l], &out[i], &n_out[i]);
+    if (rcs[i] == AG_RETRY_KEYSORT) {  // lattice too large for the occupancy bitmap: this lane moves to the key-sort path
+      lane[l]->bitmap_ok = false;
+      lane[l]->state_gen++;
+      rcs[i] = localize_run(lane[l], lane[l]->raw.p, strides[i], n_in[i], size_left[i], nullptr, 0, flags, &out[i], &n_out[i]);
+    }
     if (rcs[i] == AG_ERR_EMPTY) rcs[i] = AG_OK;  // an empty cloud yields an empty list (localization.cpp:9-15)
     if (rcs[i] != AG_OK && first_err == AG_OK) first_err = rcs[i];
   };
@@ -1142,6 +1160,13 @@ int ag_preprocess(ag_ctx* h, const void* points, int stride, int n_in, int size_
   int rc = preprocess_device(&c, c.raw.p, stride, n_in, size_left);
   if (rc) return rc;
   rc = fetch_cloud_size(&c);
+  if (rc == AG_RETRY_KEYSORT) {  // lattice too large for the occupancy bitmap: key-sort path from now on
+    c.bitmap_ok = false;
+    c.state_gen++;
+    rc = preprocess_device(&c, c.raw.p, stride, n_in, size_left);
+    if (rc) return rc;
+    rc = fetch_cloud_size(&c);
+  }
   if (rc) return rc;
   const int n = c.n_vox;
   std::vector<GPoint> v(n);

@@ -5,8 +5,18 @@
 // Localization::voxelizeCloud (:247-355; std::set<Vector3i> -> 64-bit key radix sort + unique) and
 // pcl::KdTreeFLANN::setInputCloud (src/agile_grasp/hand_search.cpp:10-11; kd-tree -> per-camera x-row
 // table over the already sorted voxel list, see ag_common.cuh).  All of it is HBM-streaming
-// integer/byte work: one coalesced pass per kernel, CUB only for the device-wide radix sort and
-// unique primitives.  Nothing here synchronises with the host: counts stay in device memory.
+// integer/byte work.  Nothing here synchronises with the host: counts stay in device memory.
+//
+// Two voxelisation paths produce the same bits:
+//  * occupancy bitmap (the common case: the voxel lattice of the cropped scene fits kBitmapBytes): one bit per
+//    lattice cell, laid out (camera, x, y, z) so that the set bits in address order ARE the reference's
+//    std::set order (localization.h:281-292).  k_classify (flags, per-camera extents, lattice dimensions by its
+//    last CTA) -> k_mark (one atomic OR per kept point: duplicates collapse for free) -> k_emit_bitmap (one pass:
+//    popcount, single-pass decoupled look-back scan across tiles, voxel records, the dense (kx, ky) column table
+//    and the x-row table as by-products of the scan, cloud_normals_ zeroed per voxel; every word is cleared
+//    again as it is read, so the bitmap is clean for the next call).  Three launches, no sort, no library call.
+//  * key sort (any extent): 64-bit keys, CUB radix sort + unique.  Taken when the lattice does not fit the
+//    bitmap; the device reports that (kErrBitmapRetry) and the host re-runs the call on this path.
 
 #include <algorithm>
 
@@ -21,6 +31,7 @@ namespace {
 constexpr int kBlock = 256;
 constexpr uint64_t kInvalidKey = ~0ull;
 constexpr int kColCap = 4 << 20;  // entries of the dense (kx, ky) column table (16 MB); larger extents fall back
+constexpr size_t kBitmapBytes = size_t(64) << 20;  // occupancy bitmap: 512 M lattice cells (e.g. 2.4 m x 2.4 m x 0.8 m at 3 mm)
 
 // voxel key = cam | kx | ky | kz packed with per-axis bit widths derived from the workspace extent, so
 // the radix sort only touches the bits that can be set
@@ -31,11 +42,22 @@ struct KeyBits {
 
 struct PreState {
   int cam_min[2][3];  // ordered-int encoded float minima per camera
-  int cam_max[2][2];  // maxima of x and y per camera (extent of the column table)
+  int cam_max[2][3];  // maxima per camera (extent of the column table / of the occupancy bitmap)
   int n_unique;       // output of DeviceSelect::Unique
   int n_vox;
   int key_overflow;
+  // occupancy-bitmap path: lattice dimensions per camera (published by the last CTA of k_classify)
+  int bnx[2], bny[2], bnzw[2];       // x cells, y cells, 32-bit words per (x, y) column
+  unsigned long long bword0[2];      // first bitmap word of each camera
+  unsigned long long bwords;         // words in use (both cameras)
+  int bcol0[2];                      // offset of each camera inside the column table
+  int bitmap_fail;                   // the lattice does not fit: the host re-runs the call on the key-sort path
+  unsigned classify_done;            // CTA completion counter of k_classify
+  unsigned tile_ticket;              // next tile of k_emit_bitmap
+  unsigned emit_done;                // CTA completion counter of k_emit_bitmap
+  unsigned epoch;                    // call counter tagging the tile states of the scan (never reset)
 };
+constexpr int kTileWords = 2048;     // bitmap words per scan tile (256 threads x 8 words)
 
 __device__ __forceinline__ bool load_xyz(const char* base, int stride, int i, float& x, float& y, float& z) {
   const char* p = base + size_t(i) * stride;
@@ -55,10 +77,15 @@ __global__ void k_init_state(PreState* st) {
     for (int c = 0; c < 2; c++)
       for (int a = 0; a < 3; a++) st->cam_min[c][a] = float_to_ordered(10000.0f);  // localization.cpp:251-252
     for (int c = 0; c < 2; c++)
-      for (int a = 0; a < 2; a++) st->cam_max[c][a] = float_to_ordered(-3.0e38f);
+      for (int a = 0; a < 3; a++) st->cam_max[c][a] = float_to_ordered(-3.0e38f);
     st->n_unique = 0;
     st->n_vox = 0;
     st->key_overflow = 0;
+    st->bitmap_fail = 0;
+    st->classify_done = 0;
+    st->tile_ticket = 0;
+    st->emit_done = 0;
+    st->epoch++;
   }
 }
 
@@ -112,12 +139,14 @@ __global__ void k_scan_blocks(int* block_counts, int nb) {  // single block, exc
 // dominant cost of this kernel).
 __global__ void __launch_bounds__(kBlock)
 k_classify(const char* pts, int stride, int n, int size_left, const int* block_offsets, double w0, double w1, double w2,
-           double w3, double w4, double w5, uint8_t* flag, PreState* st) {
+           double w3, double w4, double w5, uint8_t* flag, PreState* st, double cell, unsigned long long bitmap_words,
+           int col_cap, KeyBits kb) {
   __shared__ int wcount[kBlock / 32];
-  __shared__ int s_min[10][kBlock / 32];
+  __shared__ int s_min[12][kBlock / 32];
+  __shared__ bool s_last;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int mn[6] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF};
-  int mxv[4] = {int(0x80000000), int(0x80000000), int(0x80000000), int(0x80000000)};
+  int mxv[6] = {int(0x80000000), int(0x80000000), int(0x80000000), int(0x80000000), int(0x80000000), int(0x80000000)};
   const int n_chunks = (n + kBlock - 1) / kBlock;
   for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
     const int i = chunk * kBlock + threadIdx.x;
@@ -147,8 +176,9 @@ k_classify(const char* pts, int stride, int n, int size_left, const int* block_o
       mn[o] = min(mn[o], float_to_ordered(x));
       mn[o + 1] = min(mn[o + 1], float_to_ordered(y));
       mn[o + 2] = min(mn[o + 2], float_to_ordered(z));
-      mxv[label * 2] = max(mxv[label * 2], float_to_ordered(x));
-      mxv[label * 2 + 1] = max(mxv[label * 2 + 1], float_to_ordered(y));
+      mxv[o] = max(mxv[o], float_to_ordered(x));
+      mxv[o + 1] = max(mxv[o + 1], float_to_ordered(y));
+      mxv[o + 2] = max(mxv[o + 2], float_to_ordered(z));
     }
   }
 #pragma unroll
@@ -157,7 +187,7 @@ k_classify(const char* pts, int stride, int n, int size_left, const int* block_o
     if (lane == 0) s_min[a][w] = r;
   }
 #pragma unroll
-  for (int a = 0; a < 4; a++) {
+  for (int a = 0; a < 6; a++) {
     const int r = __reduce_max_sync(0xffffffffu, mxv[a]);
     if (lane == 0) s_min[6 + a][w] = r;
   }
@@ -166,11 +196,254 @@ k_classify(const char* pts, int stride, int n, int size_left, const int* block_o
     int r = s_min[threadIdx.x][0];
     for (int k = 1; k < kBlock / 32; k++) r = min(r, s_min[threadIdx.x][k]);
     if (r != 0x7FFFFFFF) atomicMin(&st->cam_min[threadIdx.x / 3][threadIdx.x % 3], r);
-  } else if (threadIdx.x < 10) {
+  } else if (threadIdx.x < 12) {
     const int a = threadIdx.x - 6;
     int r = s_min[threadIdx.x][0];
     for (int k = 1; k < kBlock / 32; k++) r = max(r, s_min[threadIdx.x][k]);
-    if (r != int(0x80000000)) atomicMax(&st->cam_max[a / 2][a % 2], r);
+    if (r != int(0x80000000)) atomicMax(&st->cam_max[a / 3][a % 3], r);
+  }
+  if (bitmap_words == 0) return;  // key-sort path: no lattice to lay out
+  // the last CTA to finish sees every minimum / maximum and lays out the occupancy bitmap
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&st->classify_done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  unsigned long long words = 0;
+  long long cols = 0;
+  bool fail = false;
+  for (int c = 0; c < 2; c++) {
+    int dim[3] = {0, 0, 0};
+    const volatile int* vmin = st->cam_min[c];
+    const volatile int* vmax = st->cam_max[c];
+    for (int a = 0; a < 3; a++) {
+      const double lo = double(ordered_to_float(vmin[a])), hi = double(ordered_to_float(vmax[a]));
+      if (hi >= lo) {  // largest key of this axis, the very expression k_mark evaluates (localization.cpp:289,357-362)
+        const double kmax = floor(__ddiv_rn(__dsub_rn(hi, lo), cell));
+        const int bits = a == 0 ? kb.bx : a == 1 ? kb.by : kb.bz;
+        if (kmax >= double((1u << bits) - 1u)) fail = true;  // outside the key range: the key-sort path reports it
+        dim[a] = kmax < 2.0e9 ? int(kmax) + 1 : 0x7FFFFFF0;
+      }
+    }
+    const int nzw = (dim[2] + 31) / 32;
+    st->bnx[c] = dim[0];
+    st->bny[c] = dim[1];
+    st->bnzw[c] = nzw;
+    st->bword0[c] = words;
+    st->bcol0[c] = int(cols);
+    const double wc = double(dim[0]) * double(dim[1]) * double(nzw);
+    if (wc > 4.0e18) fail = true;
+    else words += (unsigned long long)(dim[0]) * (unsigned long long)(dim[1]) * (unsigned long long)(nzw);
+    cols += static_cast<long long>(dim[0]) * dim[1] + 1;
+    if (words > bitmap_words || cols > static_cast<long long>(col_cap)) fail = true;
+  }
+  st->bwords = fail ? 0ull : words;
+  st->bitmap_fail = fail ? 1 : 0;
+}
+
+// one atomic OR per kept point: bit (camera, kx, ky, kz) of the occupancy bitmap, k = floor((p - min)/cell) in
+// binary64 exactly as the reference computes its voxel keys (localization.cpp:289,357-362)
+__global__ void __launch_bounds__(kBlock)
+k_mark(const char* pts, int stride, int n, const uint8_t* flag, double cell, const PreState* st, uint32_t* bitmap) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || st->bitmap_fail) return;
+  const uint8_t f = flag[i];
+  if (f == 0) return;
+  float x, y, z;
+  load_xyz(pts, stride, i, x, y, z);
+  const int c = f - 1;
+  const double mx = double(ordered_to_float(st->cam_min[c][0]));
+  const double my = double(ordered_to_float(st->cam_min[c][1]));
+  const double mz = double(ordered_to_float(st->cam_min[c][2]));
+  const unsigned long long kx = (unsigned long long)(floor(__ddiv_rn(__dsub_rn(double(x), mx), cell)));
+  const unsigned long long ky = (unsigned long long)(floor(__ddiv_rn(__dsub_rn(double(y), my), cell)));
+  const unsigned kz = unsigned(floor(__ddiv_rn(__dsub_rn(double(z), mz), cell)));
+  const unsigned long long word = st->bword0[c] + (kx * (unsigned long long)(st->bny[c]) + ky) * (unsigned long long)(st->bnzw[c]) + (kz >> 5);
+  atomicOr(bitmap + word, 1u << (kz & 31u));
+}
+
+// tile states of the single-pass scan: epoch << 34 | status << 32 | value.  The epoch (one per call) makes
+// entries of earlier calls read as "not yet published", so the array is never cleared.
+constexpr unsigned long long kTileAggregate = 1ull, kTilePrefix = 2ull;
+__device__ __forceinline__ unsigned long long tile_pack(unsigned epoch, unsigned long long status, unsigned value) {
+  return ((unsigned long long)(epoch & 0x3FFFFFFFu) << 34) | (status << 32) | value;
+}
+
+// Set bits in address order -> voxel list.  Persistent CTAs take tiles of kTileWords words by ticket; per tile:
+// 8 words per thread (read, then cleared for the next call), popcount, block scan, the tile's exclusive prefix by
+// decoupled look-back over the published tile states, then every set bit becomes the voxel record at its rank.
+// The prefix at the first word of a lattice column / x-row is that column's / row's first voxel: the (kx, ky)
+// column table and the x-row table fall out of the same scan.  voxel corner = (float)(k*cell + min)
+// (localization.cpp:318-351); cloud_normals_ of the voxel is zeroed (hand_search.cpp:13-14).
+__global__ void __launch_bounds__(kBlock)
+k_emit_bitmap(uint32_t* bitmap, unsigned long long* tile_state, double cell, PreState* st, GPoint* vox,
+              double* normals, RowIndex* ri, int* row_ptr, int row_stride, int* col_ptr) {
+  __shared__ int s_warp[kBlock / 32];
+  __shared__ unsigned s_tile;
+  __shared__ unsigned s_base;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned epoch = st->epoch;  // advanced on the device by k_init_state: a replayed CUDA graph gets a new one
+  if (st->bitmap_fail) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      atomicOr(&ri->error, kErrBitmapRetry);
+      ri->n_points = 0;
+    }
+    return;
+  }
+  const unsigned long long words = st->bwords;
+  const unsigned n_tiles = unsigned((words + kTileWords - 1) / kTileWords);
+  const unsigned long long w0c[2] = {st->bword0[0], st->bword0[1]};
+  const int nx[2] = {st->bnx[0], st->bnx[1]}, ny[2] = {st->bny[0], st->bny[1]}, nzw[2] = {st->bnzw[0], st->bnzw[1]};
+  const int col0[2] = {st->bcol0[0], st->bcol0[1]};
+  double mn[2][3];
+  for (int c = 0; c < 2; c++)
+    for (int a = 0; a < 3; a++) mn[c][a] = double(ordered_to_float(st->cam_min[c][a]));
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // the descriptor fields that do not depend on the scan
+    ri->inv_cell = 1.0 / cell;
+    ri->row_base[0] = 0;
+    ri->row_base[1] = row_stride;
+    ri->use_cols = 1;
+    ri->cols_bad = 0;
+    for (int c = 0; c < 2; c++) {
+      for (int a = 0; a < 3; a++) ri->mn[c][a] = mn[c][a];
+      ri->nx[c] = nx[c];
+      ri->ny[c] = ny[c];
+      ri->col_base[c] = col0[c];
+    }
+    if (st->key_overflow) atomicOr(&ri->error, kErrKeyOverflow);
+    if (words == 0) {  // nothing survived the filters
+      ri->n_points = 0;
+      st->n_vox = 0;
+      for (int c = 0; c < 2; c++) ri->first[c] = ri->count[c] = 0;
+    }
+  }
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_tile = atomicAdd(&st->tile_ticket, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    if (tile >= n_tiles) {
+      // the last CTA to leave closes the descriptor from the sentinels of the column table
+      __threadfence();
+      if (threadIdx.x == 0 && atomicAdd(&st->emit_done, 1u) == gridDim.x - 1 && words > 0) {
+        __threadfence();
+        const volatile int* cp = col_ptr;
+        const bool has0 = nx[0] > 0 && ny[0] > 0 && nzw[0] > 0, has1 = nx[1] > 0 && ny[1] > 0 && nzw[1] > 0;
+        const int end0 = has0 ? cp[col0[0] + nx[0] * ny[0]] : 0;
+        const int end1 = has1 ? cp[col0[1] + nx[1] * ny[1]] : end0;
+        ri->first[0] = 0;
+        ri->count[0] = end0;
+        ri->first[1] = end0;
+        ri->count[1] = end1 - end0;
+        ri->n_points = end1;
+        st->n_vox = end1;
+      }
+      return;
+    }
+    const unsigned long long wbase = (unsigned long long)(tile) * kTileWords + (unsigned long long)(threadIdx.x) * 8ull;
+    uint32_t wd[8];
+    if (wbase + 8 <= words) {
+      const uint4 a = *reinterpret_cast<const uint4*>(bitmap + wbase), b = *reinterpret_cast<const uint4*>(bitmap + wbase + 4);
+      wd[0] = a.x; wd[1] = a.y; wd[2] = a.z; wd[3] = a.w; wd[4] = b.x; wd[5] = b.y; wd[6] = b.z; wd[7] = b.w;
+      *reinterpret_cast<uint4*>(bitmap + wbase) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(bitmap + wbase + 4) = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        wd[k] = wbase + k < words ? bitmap[wbase + k] : 0u;
+        if (wbase + k < words) bitmap[wbase + k] = 0u;
+      }
+    }
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) cnt += __popc(wd[k]);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    int before = 0, tile_total = 0;
+#pragma unroll
+    for (int k = 0; k < kBlock / 32; k++) {
+      before += k < w ? s_warp[k] : 0;
+      tile_total += s_warp[k];
+    }
+    // decoupled look-back (one warp): publish the aggregate, walk the predecessors until an inclusive prefix
+    if (w == 0) {
+      unsigned base = 0;
+      if (tile == 0) {
+        if (lane == 0) atomicExch(&tile_state[0], tile_pack(epoch, kTilePrefix, unsigned(tile_total)));
+      } else {
+        if (lane == 0) atomicExch(&tile_state[tile], tile_pack(epoch, kTileAggregate, unsigned(tile_total)));
+        int look = int(tile) - 1;
+        for (;;) {  // lanes inspect tiles look, look - 1, ..., look - 31 (nearest first)
+          const int t = look - lane;
+          unsigned long long sv = 0ull;
+          bool ready;
+          do {
+            ready = true;
+            if (t >= 0) {
+              sv = *reinterpret_cast<volatile unsigned long long*>(&tile_state[t]);
+              ready = (sv >> 34) == (unsigned long long)(epoch & 0x3FFFFFFFu) && ((sv >> 32) & 3ull) != 0ull;
+            }
+          } while (!__all_sync(0xffffffffu, ready));
+          const bool is_prefix = t >= 0 && ((sv >> 32) & 3ull) == kTilePrefix;
+          const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
+          // aggregates of the tiles in front of the nearest inclusive prefix, plus that prefix
+          const int stop = pm ? __ffs(pm) - 1 : 31;
+          const unsigned v = (t >= 0 && lane <= stop) ? unsigned(sv & 0xFFFFFFFFull) : 0u;
+          base += __reduce_add_sync(0xffffffffu, v);
+          if (pm) break;  // (tile 0 always publishes a prefix, so the walk ends)
+          look -= 32;
+        }
+        if (lane == 0) atomicExch(&tile_state[tile], tile_pack(epoch, kTilePrefix, base + unsigned(tile_total)));
+      }
+      if (lane == 0) s_base = base;
+    }
+    __syncthreads();
+    int run = int(s_base) + before + incl - cnt;  // rank of this thread's first set bit
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) {
+      const unsigned long long wi = wbase + k;
+      if (wi >= words) break;
+      const int c = (wi >= w0c[1] && nx[1] > 0 && ny[1] > 0 && nzw[1] > 0) ? 1 : 0;
+      const unsigned long long rel = wi - w0c[c];
+      const unsigned long long column = rel / (unsigned long long)(nzw[c]);
+      const int zw = int(rel - column * (unsigned long long)(nzw[c]));
+      const int kx = int(column / (unsigned long long)(ny[c])), ky = int(column - (unsigned long long)(kx) * ny[c]);
+      if (zw == 0) {  // first word of a lattice column: the scan value is the column's first voxel
+        col_ptr[col0[c] + int(column)] = run;
+        if (ky == 0) row_ptr[c * row_stride + kx] = run;
+      }
+      uint32_t bits = wd[k];
+      if (bits) {
+        const double px = __dadd_rn(__dmul_rn(double(kx), cell), mn[c][0]);  // two roundings, like the reference's SSE2 build
+        const double py = __dadd_rn(__dmul_rn(double(ky), cell), mn[c][1]);
+        while (bits) {
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          GPoint p;
+          p.x = float(px);
+          p.y = float(py);
+          p.z = float(__dadd_rn(__dmul_rn(double(zw * 32 + b), cell), mn[c][2]));
+          p.tag = c ? kTagCamBit : 0u;
+          vox[run] = p;
+          normals[3 * size_t(run)] = 0.0;
+          normals[3 * size_t(run) + 1] = 0.0;
+          normals[3 * size_t(run) + 2] = 0.0;
+          run++;
+        }
+      }
+      // last word of a camera: close its tables
+      if (rel + 1 == (unsigned long long)(nx[c]) * ny[c] * nzw[c]) {
+        col_ptr[col0[c] + nx[c] * ny[c]] = run;
+        row_ptr[c * row_stride + nx[c]] = run;
+      }
+    }
   }
 }
 
@@ -456,11 +729,21 @@ int preprocess_device(Ctx* c, const void* d_points, int stride, int n_in, int si
     kb.total = 1 + kb.bx + kb.by + kb.bz;
   }
   const int row_stride = (1 << kb.bx) + 2;
-  if (c->misc.reserve(sizeof(PreState)) || c->keys.reserve(size_t(n_in) * 8) || c->keys_sorted.reserve(size_t(n_in) * 8) ||
-      c->keys_unique.reserve(size_t(n_in) * 8) || c->block_counts.reserve(size_t(nb) * 4 + size_t(n_in)) ||
+  const bool fresh_state = c->misc.cap < sizeof(PreState);
+  if (c->misc.reserve(sizeof(PreState)) || c->block_counts.reserve(size_t(nb) * 4 + size_t(n_in)) ||
       c->vox.reserve(size_t(n_in) * 16) || c->row_ptr.reserve(size_t(row_stride) * 2 * 4) ||
       c->col_ptr.reserve(size_t(kColCap) * 4) ||
       c->row_index.reserve(sizeof(RowIndex)) || c->normals.reserve(size_t(n_in) * 24))
+    return AG_ERR_CUDA;
+  if (fresh_state) AG_CUDA_CHECK(cudaMemsetAsync(c->misc.p, 0, sizeof(PreState), c->stream));  // (the scan epoch starts at 0)
+  const bool bitmap = c->bitmap_ok;
+  if (bitmap && !c->bitmap.p) {  // once per context: the occupancy bitmap (kept clean by its reader) and the tile states
+    if (c->bitmap.reserve(kBitmapBytes) || c->tile_state.reserve((kBitmapBytes / 4 / kTileWords + 1) * 8)) return AG_ERR_CUDA;
+    AG_CUDA_CHECK(cudaMemsetAsync(c->bitmap.p, 0, c->bitmap.cap, c->stream));
+    AG_CUDA_CHECK(cudaMemsetAsync(c->tile_state.p, 0, c->tile_state.cap, c->stream));
+  }
+  if (!bitmap && (c->keys.reserve(size_t(n_in) * 8) || c->keys_sorted.reserve(size_t(n_in) * 8) ||
+                  c->keys_unique.reserve(size_t(n_in) * 8)))
     return AG_ERR_CUDA;
   c->n_cap = n_in;
   PreState* st = state_ptr(c);
@@ -474,9 +757,20 @@ int preprocess_device(Ctx* c, const void* d_points, int stride, int n_in, int si
     k_count_finite<<<nb, kBlock, 0, c->stream>>>(pts, stride, n_in, d_block);
     k_scan_blocks<<<1, 1024, 0, c->stream>>>(d_block, nb);
   }
-  k_classify<<<std::min(nb, kNumSMs * 4), kBlock, 0, c->stream>>>(pts, stride, n_in, size_left, quirk ? d_block : nullptr, P.workspace[0],
-                                           P.workspace[1], P.workspace[2], P.workspace[3], P.workspace[4],
-                                           P.workspace[5], d_flag, st);
+  k_classify<<<std::min(nb, kNumSMs * 4), kBlock, 0, c->stream>>>(
+      pts, stride, n_in, size_left, quirk ? d_block : nullptr, P.workspace[0], P.workspace[1], P.workspace[2],
+      P.workspace[3], P.workspace[4], P.workspace[5], d_flag, st, P.voxel_size,
+      bitmap ? (unsigned long long)(kBitmapBytes / 4) : 0ull, kColCap, kb);
+  if (bitmap) {
+    k_mark<<<nb, kBlock, 0, c->stream>>>(pts, stride, n_in, d_flag, P.voxel_size, st, c->bitmap.as<uint32_t>());
+    k_emit_bitmap<<<kNumSMs * 4, kBlock, 0, c->stream>>>(c->bitmap.as<uint32_t>(), c->tile_state.as<unsigned long long>(),
+                                                         P.voxel_size, st, c->vox.as<GPoint>(), c->normals.as<double>(),
+                                                         c->row_index.as<RowIndex>(), c->row_ptr.as<int>(), row_stride,
+                                                         c->col_ptr.as<int>());
+    c->launches += quirk ? 6 : 4;  // init, [count, scan], classify, mark, emit
+    AG_CUDA_CHECK(cudaGetLastError());
+    return AG_OK;
+  }
   k_keys<<<nb, kBlock, 0, c->stream>>>(pts, stride, n_in, d_flag, P.voxel_size, st, c->keys.as<uint64_t>(), kb);
   size_t tmp1 = 0, tmp2 = 0;
   cub::DeviceRadixSort::SortKeys(nullptr, tmp1, c->keys.as<uint64_t>(), c->keys_sorted.as<uint64_t>(), n_in, 0,
@@ -504,6 +798,7 @@ int fetch_cloud_size(Ctx* c) {
   AG_CUDA_CHECK(cudaMemcpyAsync(&hri, c->row_index.p, sizeof(hri), cudaMemcpyDeviceToHost, c->stream));
   AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   c->n_vox = hri.n_points;
+  if (hri.error & kErrBitmapRetry) return AG_RETRY_KEYSORT;
   if (hri.error & kErrKeyOverflow) {
     set_error("voxel index exceeds the key range (workspace extent / voxel_size > 2^21 cells)");
     return AG_ERR_CAPACITY;

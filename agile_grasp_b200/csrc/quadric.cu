@@ -1005,23 +1005,7 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip
       const int lo = lo_b > 0 ? rk.cur[lo_b - 1] : 0, hi = rk.cur[lo_b];
       const int k = r - lo;
       int found = rk.order[lo];
-      if (hi - lo <= 8) {  // the bucket's members once into registers, ranked against each other without branches
-        float d[8];
-        int id[8];
-#pragma unroll
-        for (int t = 0; t < 8; t++) {
-          id[t] = lo + t < hi ? int(rk.order[lo + t]) : 0x7fffffff;
-          d[t] = lo + t < hi ? dist_of(id[t]) : 3.0e38f;
-        }
-#pragma unroll
-        for (int t = 0; t < 8; t++) {
-          int cnt = 0;
-#pragma unroll
-          for (int u = 0; u < 8; u++) cnt += (d[u] < d[t] || (d[u] == d[t] && id[u] < id[t])) ? 1 : 0;
-          if (cnt == k && lo + t < hi) found = id[t];
-        }
-        return found;
-      }
+      if (hi - lo == 1) return found;  // (the common case at ~1.6 neighbours per bucket)
       for (int a = lo; a < hi; a++) {
         const int e = rk.order[a];
         const float de = dist_of(e);

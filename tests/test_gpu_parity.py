@@ -648,3 +648,36 @@ def test_localize_edge_cases(ctx, oracle, small_scene, linear_svm_path):
         assert len(outs[1]) == 0 and len(outs[0]) > 0 and _rec_bytes(outs[0]) == _rec_bytes(outs[2])
     finally:
         ctx.set_params(s["P"])
+
+
+def test_voxelisation_paths_agree(oracle, small_scene, two_view_scene):
+    """The voxelised cloud comes from the occupancy-bitmap path when the scene's voxel lattice fits the bitmap and
+    from the key-sort path otherwise (the device reports the misfit, the call is re-run, the context stays on the
+    key-sort path): both are bit-identical to the oracle's std::set order (localization.cpp:247-355), for one and
+    two cameras, and the whole call gives the same hypotheses on either path."""
+    for s in (small_scene, two_view_scene):
+        c = api.Context(0, s["P"])
+        xyz, cam = c.preprocess(s["pts"], s["size_left"])  # bitmap path
+        assert (_u32(xyz) == _u32(s["xyz"])).all() and (cam == s["cam"]).all()
+        g_bitmap = c.localize(s["pts"], s["size_left"], s["idx"])
+        # two far outliers inside the workspace blow the lattice up to ~6000^3 cells: key-sort path
+        far = s["pts"].copy()
+        n0 = s["size_left"] - 1
+        far[0, :3] = [-9.0, -9.0, -9.0]
+        far[n0, :3] = [9.0, 9.0, 9.0]
+        xo, co = oracle.preprocess(far, s["size_left"], s["P"], False)
+        xf, cf = c.preprocess(far, s["size_left"])
+        assert (_u32(xf) == _u32(xo)).all() and (cf == co).all()
+        # the context now stays on the key-sort path: same bits as before on the original cloud
+        xyz2, cam2 = c.preprocess(s["pts"], s["size_left"])
+        assert (_u32(xyz2) == _u32(s["xyz"])).all() and (cam2 == s["cam"]).all()
+        g_sort = c.localize(s["pts"], s["size_left"], s["idx"])
+        assert len(g_sort) > 0 and _rec_bytes(g_sort) == _rec_bytes(g_bitmap)
+        # a fresh context meets the oversized lattice inside a full call (retry inside ag_localize)
+        c2 = api.Context(0, s["P"])
+        idx_f = oracle.draw_samples(len(xo), 50, s["P"].seed)
+        g_far = c2.localize(far, s["size_left"], idx_f)
+        g_far2 = c.localize(far, s["size_left"], idx_f)
+        assert c2.timings()["n_voxels"] == len(xo) and _rec_bytes(g_far) == _rec_bytes(g_far2)
+        c.close()
+        c2.close()

