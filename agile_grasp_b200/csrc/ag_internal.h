@@ -135,7 +135,10 @@ struct Ctx {
   bool capturing = false;  // the stream is being captured: timing events must be recorded as external events
   // non-deterministic normal mode: glibc rand() stream, per-sample stream offsets, the carry across launches, bound on the
   // number of samples that may already have consumed draws in the current call
-  DevBuf rand_raw, rand_off, rand_carry;
+  DevBuf rand_raw, rand_off, rand_carry, picks;
+  DevBuf quad_par;             // quadric parameters per sample (k_taubin_solve -> k_axes_finish)
+  cudaStream_t stream2 = nullptr;  // side branch of the pipeline (rank selection next to the eigen-solve)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   size_t rand_count = 0;
   int rand_consumed_bound = 0;
   DevBuf nbr_heads;  // per sample of the chunk: sample xyz + neighbour count (float4)

@@ -696,6 +696,9 @@ ag_ctx* ag_create(int device) {
     delete h;
     return nullptr;
   }
+  cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming);
   for (auto& ev : c.ev) cudaEventCreate(&ev);
   for (auto& ev : c.ev_k) cudaEventCreate(&ev);
   ag_default_params(&c.params);
@@ -717,12 +720,15 @@ void ag_destroy(ag_ctx* h) {
   if (c.h_out) cudaFreeHost(c.h_out);
   for (DevBuf* b : {&c.raw, &c.keys, &c.keys_sorted, &c.keys_unique, &c.cub_tmp, &c.block_counts, &c.misc, &c.bitmap, &c.tile_state, &c.vox,
                     &c.row_ptr, &c.col_ptr, &c.row_index, &c.all_frames,
-                    &c.normals, &c.samples, &c.sample_stage, &c.moments, &c.frames, &c.nn_counts, &c.nbr_pool, &c.nbr_heads, &c.rand_raw, &c.rand_off, &c.rand_carry, &c.grasps_raw, &c.valid,
+                    &c.normals, &c.samples, &c.sample_stage, &c.moments, &c.frames, &c.nn_counts, &c.nbr_pool, &c.nbr_heads, &c.rand_raw, &c.rand_off, &c.rand_carry, &c.picks, &c.quad_par, &c.grasps_raw, &c.valid,
                     &c.images_raw, &c.hyp_slots, &c.grasps, &c.counters, &c.scores, &c.descriptors, &c.kvals, &c.handle_in, &c.handle_bits, &c.sweep_dbg, &c.overflow})
     b->release();
   if (c.h_pinned) cudaFreeHost(c.h_pinned);
   for (auto& ev : c.ev) cudaEventDestroy(ev);
   for (auto& ev : c.ev_k) cudaEventDestroy(ev);
+  cudaEventDestroy(c.ev_fork);
+  cudaEventDestroy(c.ev_join);
+  cudaStreamDestroy(c.stream2);
   cudaStreamDestroy(c.stream);
   delete h;
 }

@@ -38,23 +38,46 @@ __host__ __device__ constexpr int midx(int a, int b, int c) {
        : k == 4 ? 22 : k == 80 ? 23 : k == 76 ? 24 : k == 40 ? 25 : k == 16 ? 26 : k == 28 ? 27 : k == 8 ? 28
        : k == 60 ? 29 : k == 12 ? 30 : k == 52 ? 31 : k == 56 ? 32 : k == 36 ? 33 : k == 32 ? 34 : -1;
 }
-// device-side lookup of the same map (index a*25 + b*5 + c), filled from midx() at compile time
-struct MidxTable {
-  signed char v[125];
-  constexpr MidxTable() : v() {
-    for (int a = 0; a < 5; a++)
-      for (int b = 0; b < 5; b++)
-        for (int c = 0; c < 5; c++) v[a * 25 + b * 5 + c] = (a + b + c <= 4) ? static_cast<signed char>(midx(a, b, c)) : -1;
-  }
-};
-__constant__ MidxTable c_midx = MidxTable();
-__device__ __forceinline__ int midx_d(int a, int b, int c) { return c_midx.v[a * 25 + b * 5 + c]; }
 constexpr int kNumMoments = 35;
 constexpr int kMomentStride = 36;  // + count of camera-1 neighbours
 
-// exponents of the quadric basis [x2 y2 z2 xy yz xz x y z 1] (quadric.cpp:40-73)
-__constant__ int c_basis[10][3] = {{2, 0, 0}, {0, 2, 0}, {0, 0, 2}, {1, 1, 0}, {0, 1, 1},
-                                   {1, 0, 1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 0, 0}};
+// exponents of the quadric basis [x2 y2 z2 xy yz xz x y z] (quadric.cpp:40-73)
+constexpr int kBasis[9][3] = {{2, 0, 0}, {0, 2, 0}, {0, 0, 2}, {1, 1, 0}, {0, 1, 1}, {1, 0, 1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+// where entry (i, j) of the reduced pencil comes from: A_ij = mom[a_ij] - mom[a_i] mom[a_j] / n and
+// B_ij = sum_t b_coef[t] mom[b_idx[t]] (N = sum grad phi^T grad phi, quadric.cpp:103-131), as moment indices —
+// a per-entry table read with one coalesced load instead of chains of lane-divergent constant-memory lookups
+struct PencilEntry {
+  unsigned char a_ij, a_i, a_j, nb, b_idx[3], b_coef[3], pad[2];
+};
+struct PencilTable {
+  PencilEntry e[81];
+  constexpr PencilTable() : e() {
+    for (int i = 0; i < 9; i++)
+      for (int j = 0; j < 9; j++) {
+        PencilEntry& t = e[i * 9 + j];
+        const int* bi = kBasis[i];
+        const int* bj = kBasis[j];
+        t.a_ij = static_cast<unsigned char>(midx(bi[0] + bj[0], bi[1] + bj[1], bi[2] + bj[2]));
+        t.a_i = static_cast<unsigned char>(midx(bi[0], bi[1], bi[2]));
+        t.a_j = static_cast<unsigned char>(midx(bj[0], bj[1], bj[2]));
+        t.nb = 0;
+        for (int a = 0; a < 3; a++)
+          if (bi[a] >= 1 && bj[a] >= 1) {
+            int ex[3] = {bi[0] + bj[0], bi[1] + bj[1], bi[2] + bj[2]};
+            ex[a] -= 2;
+            t.b_idx[t.nb] = static_cast<unsigned char>(midx(ex[0], ex[1], ex[2]));
+            t.b_coef[t.nb] = static_cast<unsigned char>(bi[a] * bj[a]);
+            t.nb++;
+          }
+        for (int k = t.nb; k < 3; k++) {
+          t.b_idx[k] = 0;
+          t.b_coef[k] = 0;
+        }
+        t.pad[0] = t.pad[1] = 0;
+      }
+  }
+};
+__device__ const PencilTable g_pencil = PencilTable();
 
 // ---- PTX helpers: shared-space accesses, mbarrier, TMA bulk copy ---------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -387,19 +410,12 @@ struct AxesSmem {
   double A[81];   // Schur complement, later C = L^-1 A L^-T (diagonalised in place only on the Jacobi fallback)
   double L[81];   // B, then its Cholesky factor
   double V[96];   // scratch of the eigen-solve: L D L^T factors (81 + 9), or the Jacobi eigenvectors
-  double m[10];   // last column of M (9 entries) and n
+  double m[20];   // last column of M (9 entries); from [10]: the scaling S = D^(-1/2) of the reduction
   double par[10]; // quadric parameters in centred/scaled coordinates
   double T[28];   // weighted order-6 normal tensor
 };
-// non-deterministic normal mode only (extra dynamic shared memory behind the kWarps AxesSmem blocks): the
-// (distance, index) order of the neighbours (distances are recomputed from the list: 5 KB per warp keep the
-// kernel at 4 CTAs per SM)
+// non-deterministic normal mode: neighbours per sample the rank kernel can order, distance buckets of its counting sort
 constexpr int kRankBuckets = 256;
-struct RankSmem {
-  unsigned short order[kRankCap];  // neighbour positions grouped by distance bucket
-  unsigned char bucket[kRankCap];  // distance bucket of every neighbour
-  int cur[kRankBuckets];           // fill cursors of the counting sort: afterwards the END of every bucket
-};
 
 // streams a sample's neighbour list (written by k_ball_search) 32 records per step, the next step's load
 // already in flight; f(point, active)
@@ -534,7 +550,8 @@ __device__ __forceinline__ double fast_rcp(double x) {  // reciprocal to ~1 ulp:
 // L D L^T of C - sigma I from the row-major 9x9 in shared memory (lower triangle read).  Returns whether all
 // pivots were positive.  STORE: lane 0 also leaves L (strict lower part, row-major 9x9) and 1/D in `fac`.
 template <bool STORE>
-__device__ __forceinline__ bool ldl9_shifted(const double* __restrict__ C, double sigma, double* fac, int lane) {
+__device__ __forceinline__ bool ldl9_shifted(const double* __restrict__ C, double sigma, double* fac, int lane,
+                                             double tol = 0.0) {
   double a[9][9];  // lower triangle, compile-time indices only (registers)
 #pragma unroll
   for (int i = 0; i < 9; i++)
@@ -544,7 +561,7 @@ __device__ __forceinline__ bool ldl9_shifted(const double* __restrict__ C, doubl
 #pragma unroll
   for (int k = 0; k < 9; k++) {
     const double d = a[k][k];
-    pd = pd && (d > 0.0);
+    pd = pd && (d > tol);
     const double inv = fast_rcp(d);
     if (STORE && lane == 0) fac[81 + k] = inv;
     double l[9];
@@ -712,120 +729,93 @@ __constant__ double c_multinomial6[28] = {
     6, 30, 60, 60, 30, 6,       // a=1
     1, 6, 15, 20, 15, 6, 1};    // a=0
 
-// ---- kernel 2: eigen-solve + local axes -------------------------------------------------------
+// ---- kernel 2: the 9x9 pencil and its smallest eigenpair -> quadric parameters -----------------------
+// One warp per sample; needs only the 36 moments.  Output: 10 quadric parameters in centred / scaled
+// coordinates + a validity flag, 12 doubles per sample.
 __global__ void __launch_bounds__(kWarps * 32, 4)
-k_taubin_axes(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip,
-              const int* __restrict__ indices, int s0, int n_samples_max, const int* __restrict__ d_count,
-              const GPoint* __restrict__ pool, int stride, const int2* __restrict__ nn_counts, double inv_r,
-              float r2_f, const double* __restrict__ moments,
-              double cam0x, double cam0y, double cam0z, double cam1x, double cam1y, double cam1z,
-              ag_frame* __restrict__ frames, double* normals_out /* may be null */,
-              const uint32_t* __restrict__ rand_raw /* null = deterministic normals */,
-              const int* __restrict__ rand_off) {
-  extern __shared__ __align__(16) unsigned char s_raw[];
-  AxesSmem* sm_all = reinterpret_cast<AxesSmem*>(s_raw);
+k_taubin_solve(const RowIndex* __restrict__ rip, const int* __restrict__ indices, int s0, int n_samples_max,
+               const int* __restrict__ d_count, const double* __restrict__ moments, double* __restrict__ par_out) {
+  __shared__ AxesSmem sm_all[kWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int sl = blockIdx.x * kWarps + warp;
-  const int s = s0 + sl;
+  const int s = s0 + blockIdx.x * kWarps + warp;
   if (s >= n_samples_max || s >= *d_count) return;
   AxesSmem& sm = sm_all[warp];
   const int idx = indices[s];
   if (idx < 0 || idx >= rip->n_points) return;
-  const GPoint* list = pool + size_t(sl) * size_t(stride);
-  const int n_list = nn_counts[s].x;
-  const GPoint q = pts_c[idx];
-  const double qx = double(q.x), qy = double(q.y), qz = double(q.z);
   const double* mom = moments + size_t(s) * kMomentStride;
   const double n = mom[0];
-  ag_frame F;
-  F.num_neighbors = int(n);
-  int major = (mom[35] > n - mom[35]) ? 1 : 0;  // quadric.cpp:217-226 (tie -> camera 0)
-  // the reference's production mode (is_deterministic = false, quadric.cpp:177-192): with more than 50
-  // neighbours the normals are evaluated at 50 picks rand() % n of the (distance, index)-sorted neighbour list
-  const bool picks = rand_raw != nullptr && n_list > 50 && n_list <= kRankCap;
-  RankSmem& rk = reinterpret_cast<RankSmem*>(s_raw + sizeof(AxesSmem) * kWarps)[warp];  // only touched if picks
 
   // --- build the reduced pencil: A = M[0:9,0:9] - m m^T / n, B = N[0:9,0:9]
+  const double inv_n = 1.0 / n;
   for (int e = lane; e < 81; e += 32) {
-    const int i = e / 9, j = e % 9;
-    const int* bi = c_basis[i];
-    const int* bj = c_basis[j];
-    const double mij = mom[midx_d(bi[0] + bj[0], bi[1] + bj[1], bi[2] + bj[2])];
-    const double mi = mom[midx_d(bi[0], bi[1], bi[2])], mj = mom[midx_d(bj[0], bj[1], bj[2])];
-    sm.A[e] = mij - mi * mj / n;
+    const PencilEntry t = g_pencil.e[e];
+    sm.A[e] = mom[t.a_ij] - mom[t.a_i] * mom[t.a_j] * inv_n;
     double bsum = 0.0;
 #pragma unroll
-    for (int a = 0; a < 3; a++) {
-      if (bi[a] >= 1 && bj[a] >= 1) {
-        int ex[3] = {bi[0] + bj[0], bi[1] + bj[1], bi[2] + bj[2]};
-        ex[a] -= 2;
-        bsum += double(bi[a] * bj[a]) * mom[midx_d(ex[0], ex[1], ex[2])];
-      }
-    }
+    for (int k = 0; k < 3; k++)
+      if (k < t.nb) bsum += double(t.b_coef[k]) * mom[t.b_idx[k]];
     sm.L[e] = bsum;
   }
-  if (lane < 9) sm.m[lane] = mom[midx_d(c_basis[lane][0], c_basis[lane][1], c_basis[lane][2])];
+  if (lane < 9) sm.m[lane] = mom[g_pencil.e[lane * 9 + lane].a_i];
   __syncwarp();
 
-  // --- Cholesky B = L L^T (lane-parallel over rows below the pivot).  B is singular when the
-  // neighbourhood is degenerate for the gradient form (e.g. voxel corners lying exactly in one lattice
-  // plane); those directions have lambda = infinity (or 0/0) and must be excluded, which the robust
-  // branch below does by working in range(B).
+  // --- B = G G^T with G = L sqrt(D): every lane factorises B = L D L^T redundantly in registers (no
+  // communication, no divisions beyond nine reciprocals); lane 0 leaves L and 1/D in sm.V.  B is singular when
+  // the neighbourhood is degenerate for the gradient form (e.g. voxel corners lying exactly in one lattice
+  // plane); those directions have lambda = infinity (or 0/0) and must be excluded, which the robust branch
+  // below does by working in range(B).
   bool ok = n >= 1.0;
-  bool singular = false;
   double dmax = 0.0;
   for (int i = 0; i < 9; i++) dmax = fmax(dmax, sm.L[i * 9 + i]);
   if (!(dmax > 0.0)) ok = false;
-  {
-    const double tol = 1e-10 * dmax;
-    for (int k = 0; k < 9 && ok; k++) {
-      const double piv = sm.L[k * 9 + k];
-      if (!(piv > tol)) {  // uniform across the warp (shared memory value)
-        singular = true;
-        break;
-      }
-      const double d = sqrt(piv);
-      __syncwarp();
-      if (lane == 0) sm.L[k * 9 + k] = d;
-      if (lane > k && lane < 9) sm.L[lane * 9 + k] /= d;
-      __syncwarp();
-      // trailing update: entries (i,j), k < j <= i < 9
-      for (int e = lane; e < 81; e += 32) {
-        const int i = e / 9, j = e % 9;
-        if (j > k && i >= j) sm.L[i * 9 + j] -= sm.L[i * 9 + k] * sm.L[j * 9 + k];
-      }
-      __syncwarp();
-    }
-  }
+  const bool singular = ok && !__all_sync(0xffffffffu, ldl9_shifted<true>(sm.L, 0.0, sm.V, lane, 1e-10 * dmax));
+  __syncwarp();
   if (!singular) {
-    // --- C = L^-1 A L^-T : X = L^-1 A (columns in parallel), then C^T = L^-1 X^T
+    // --- C = G^-1 A G^-T = S (L^-1 A L^-T) S, S = D^(-1/2): unit-triangular solves (columns, then rows, in
+    // parallel over nine lanes), then the diagonal scaling
+    double rs = 0.0;  // lane i < 9: 1 / sqrt(D_i)
     if (lane < 9) {
+      rs = sqrt(sm.V[81 + lane]);
       const int col = lane;
+      double x[9];
+#pragma unroll
       for (int i = 0; i < 9; i++) {
         double v = sm.A[i * 9 + col];
-        for (int k = 0; k < i; k++) v -= sm.L[i * 9 + k] * sm.A[k * 9 + col];
-        sm.A[i * 9 + col] = v / sm.L[i * 9 + i];
+#pragma unroll
+        for (int k = 0; k < i; k++) v = fma(-sm.V[i * 9 + k], x[k], v);
+        x[i] = v;
       }
+#pragma unroll
+      for (int i = 0; i < 9; i++) sm.A[i * 9 + col] = x[i];
     }
     __syncwarp();
     if (lane < 9) {
       const int row = lane;  // solve L y = (row of X)^T
+      double x[9];
+#pragma unroll
       for (int i = 0; i < 9; i++) {
         double v = sm.A[row * 9 + i];
-        for (int k = 0; k < i; k++) v -= sm.L[i * 9 + k] * sm.A[row * 9 + k];
-        sm.A[row * 9 + i] = v / sm.L[i * 9 + i];
+#pragma unroll
+        for (int k = 0; k < i; k++) v = fma(-sm.V[i * 9 + k], x[k], v);
+        x[i] = v;
       }
+#pragma unroll
+      for (int i = 0; i < 9; i++) sm.A[row * 9 + i] = x[i];
     }
     __syncwarp();
-    // symmetrise (round-off) and diagonalise
-    for (int e = lane; e < 81; e += 32) {
+    if (lane < 9) sm.m[10 + lane] = rs;  // (sm.m has 10 + 10 entries: last column of M, then S)
+    __syncwarp();
+    // scale, symmetrise (round-off)
+    double cnew[3];
+    for (int e = lane, t = 0; e < 81; e += 32, t++) {
       const int i = e / 9, j = e % 9;
-      if (i < j) {
-        const double v = 0.5 * (sm.A[i * 9 + j] + sm.A[j * 9 + i]);
-        sm.A[i * 9 + j] = v;
-        sm.A[j * 9 + i] = v;
-      }
+      cnew[t] = 0.5 * (sm.A[i * 9 + j] + sm.A[j * 9 + i]) * (sm.m[10 + i] * sm.m[10 + j]);
     }
+    __syncwarp();
+    for (int e = lane, t = 0; e < 81; e += 32, t++) sm.A[e] = cnew[t];
+    __syncwarp();
+    // keep L and S for the back-transformation: the eigen-solve below overwrites sm.V, so move L into sm.L
+    for (int e = lane; e < 81; e += 32) sm.L[e] = sm.V[e];
     __syncwarp();
     // smallest eigenvalue (quadric.cpp:149-152): bracket + inverse iteration; the cyclic Jacobi is the fallback
     double yv[9];
@@ -840,14 +830,14 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip
       for (int i = 0; i < 9; i++) yv[i] = sm.V[i * 9 + mi];
     }
     __syncwarp();
-    if (lane == 0) {  // u = L^-T y, j = -m.u/n
+    if (lane == 0) {  // u = G^-T y = L^-T (S y), j = -m.u/n
       double u[9];
 #pragma unroll
       for (int i = 8; i >= 0; i--) {
-        double v = yv[i];
+        double v = yv[i] * sm.m[10 + i];
 #pragma unroll
-        for (int k = i + 1; k < 9; k++) v -= sm.L[k * 9 + i] * u[k];
-        u[i] = v / sm.L[i * 9 + i];
+        for (int k = i + 1; k < 9; k++) v = fma(-sm.L[k * 9 + i], u[k], v);
+        u[i] = v;
       }
 #pragma unroll
       for (int i = 0; i < 9; i++) sm.par[i] = u[i];
@@ -855,21 +845,7 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip
   } else {
     // --- robust branch: B = Q D Q^T, W = Q_k D_k^(-1/2) over the directions with D_i > 1e-11 D_max,
     //     C = W^T A W on range(B), smallest eigenpair y, u = W y
-    for (int e = lane; e < 81; e += 32) {  // rebuild B (the partial Cholesky overwrote it)
-      const int i = e / 9, j = e % 9;
-      const int* bi = c_basis[i];
-      const int* bj = c_basis[j];
-      double bsum = 0.0;
-#pragma unroll
-      for (int a = 0; a < 3; a++) {
-        if (bi[a] >= 1 && bj[a] >= 1) {
-          int ex[3] = {bi[0] + bj[0], bi[1] + bj[1], bi[2] + bj[2]};
-          ex[a] -= 2;
-          bsum += double(bi[a] * bj[a]) * mom[midx_d(ex[0], ex[1], ex[2])];
-        }
-      }
-      sm.L[e] = bsum;
-    }
+    // (sm.L still holds B: the factorisation above works in registers)
     __syncwarp();
     warp_jacobi9(sm.L, sm.V, lane);  // eigenvalues on diag(sm.L), eigenvectors in the columns of sm.V
     double d_max = 0.0;
@@ -931,9 +907,143 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip
     sm.par[9] = -mu / n;
   }
   __syncwarp();
+  if (lane < 10) par_out[size_t(s) * 12 + lane] = sm.par[lane];
+  if (lane == 0) par_out[size_t(s) * 12 + 10] = ok ? 1.0 : 0.0;
+
+}
+
+// ---- kernel 2b (production normal mode only): which 50 neighbours the reference's rand() % n picks -------
+// The picks index the kd-tree's result order = ascending (distance, index).  Independent of the fit, so this
+// runs on a second stream next to the moments / solve kernels.  One warp per sample, everything in shared
+// memory: binary32 distances of the neighbours, a counting sort into 256 distance buckets (a monotone function of
+// the distance), then every lane finishes its buckets by insertion on (distance, position) — the list is in
+// index order, so the position breaks distance ties.  Voxel corners sit on a lattice, so whole groups of
+// neighbours share a distance up to rounding noise; sorting each group once is cheaper than ranking inside it
+// for every pick.  Output: 50 list positions per sample (samples with at most 50 neighbours evaluate all of
+// them and get no picks).
+template <int CAP>
+__global__ void __launch_bounds__(kWarps * 32, 8)
+k_rank_picks(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip, const int* __restrict__ indices,
+             int s0, int n_samples_max, const int* __restrict__ d_count, const GPoint* __restrict__ pool, int stride,
+             const int2* __restrict__ nn_counts, float r2_f, const uint32_t* __restrict__ rand_raw,
+             const int* __restrict__ rand_off, unsigned short* __restrict__ picks_out) {
+  extern __shared__ __align__(16) unsigned char s_rank[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sl = blockIdx.x * kWarps + warp;
+  const int s = s0 + sl;
+  if (s >= n_samples_max || s >= *d_count) return;
+  const int idx = indices[s];
+  if (idx < 0 || idx >= rip->n_points) return;
+  const GPoint* list = pool + size_t(sl) * size_t(stride);
+  const int n_list = nn_counts[s].x;
+  if (!(n_list > 50 && n_list <= CAP)) return;
+  const GPoint q = pts_c[idx];
+  float* d2 = reinterpret_cast<float*>(s_rank) + size_t(warp) * CAP;
+  int* cur = reinterpret_cast<int*>(s_rank + size_t(kWarps) * CAP * 4) + warp * kRankBuckets;
+  unsigned short* order = reinterpret_cast<unsigned short*>(s_rank + size_t(kWarps) * (CAP * 4 + kRankBuckets * 4)) + size_t(warp) * CAP;
+  constexpr int nb = kRankBuckets;
+  const float bscale = float(nb) / r2_f;
+  for (int i = lane; i < nb; i += 32) cur[i] = 0;
+  __syncwarp();
+  for (int i0 = lane; i0 < n_list; i0 += 128) {  // four independent loads in flight per lane
+    GPoint p[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (i0 + 32 * u < n_list) p[u] = list[i0 + 32 * u];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (i0 + 32 * u < n_list) {
+        const float d = dist2_flann(q.x, q.y, q.z, p[u].x, p[u].y, p[u].z);
+        d2[i0 + 32 * u] = d;
+        atomicAdd(&cur[min(nb - 1, int(d * bscale))], 1);
+      }
+  }
+  __syncwarp();
+  int first[8];  // start of this lane's 8 consecutive buckets, kept for the insertion pass
+  {
+    int c[8], tot = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      c[k] = cur[8 * lane + k];
+      tot += c[k];
+    }
+    int incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    int run = incl - tot;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      first[k] = run;
+      cur[8 * lane + k] = run;
+      run += c[k];
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < n_list; i += 32) order[atomicAdd(&cur[min(nb - 1, int(d2[i] * bscale))], 1)] = (unsigned short)i;
+  __syncwarp();
+  // cur[b] is now the end of bucket b; this lane owns buckets 8 lane .. 8 lane + 7 = one contiguous range
+  {
+    const int lo = first[0], hi = cur[8 * lane + 7];
+    // insertion sort of the whole range: elements only ever move inside their bucket (bucket = monotone in d)
+    for (int a = lo + 1; a < hi; a++) {
+      const unsigned short e = order[a];
+      const float de = d2[e];
+      int t = a - 1;
+      while (t >= lo) {
+        const unsigned short f = order[t];
+        const float df = d2[f];
+        if (df < de || (df == de && f < e)) break;
+        order[t + 1] = f;
+        t--;
+      }
+      order[t + 1] = e;
+    }
+  }
+  __syncwarp();
+  const uint32_t* raw = rand_raw + size_t(50) * size_t(rand_off[s]);
+#pragma unroll
+  for (int u = 0; u < 2; u++) {
+    const int t = lane + 32 * u;
+    if (t < 50) picks_out[size_t(s) * 50 + t] = order[raw[t] % uint32_t(n_list)];
+  }
+}
+
+// ---- kernel 3: gradient normals at the evaluation points, curvature axis, frame ---------------------------
+__global__ void __launch_bounds__(kWarps * 32, 4)
+k_axes_finish(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip,
+              const int* __restrict__ indices, int s0, int n_samples_max, const int* __restrict__ d_count,
+              const GPoint* __restrict__ pool, int stride, const int2* __restrict__ nn_counts, double inv_r,
+              const double* __restrict__ moments, const double* __restrict__ par_in,
+              double cam0x, double cam0y, double cam0z, double cam1x, double cam1y, double cam1z,
+              ag_frame* __restrict__ frames, double* normals_out /* may be null */,
+              const unsigned short* __restrict__ picks_in /* null = deterministic normals */) {
+  __shared__ double s_T[kWarps][28];  // weighted order-6 normal tensor
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sl = blockIdx.x * kWarps + warp;
+  const int s = s0 + sl;
+  if (s >= n_samples_max || s >= *d_count) return;
+  double* sT = s_T[warp];
+  const int idx = indices[s];
+  if (idx < 0 || idx >= rip->n_points) return;
+  const GPoint* list = pool + size_t(sl) * size_t(stride);
+  const int n_list = nn_counts[s].x;
+  const GPoint q = pts_c[idx];
+  const double qx = double(q.x), qy = double(q.y), qz = double(q.z);
+  const double* mom = moments + size_t(s) * kMomentStride;
+  const double n = mom[0];
+  ag_frame F;
+  F.num_neighbors = int(n);
+  int major = (mom[35] > n - mom[35]) ? 1 : 0;  // quadric.cpp:217-226 (tie -> camera 0)
+  // the reference's production mode (is_deterministic = false, quadric.cpp:177-192): with more than 50
+  // neighbours the normals are evaluated at 50 picks rand() % n of the (distance, index)-sorted neighbour list
+  const bool picks = picks_in != nullptr && n_list > 50 && n_list <= kRankCap;
   double par[9];
 #pragma unroll
-  for (int i = 0; i < 9; i++) par[i] = sm.par[i];
+  for (int i = 0; i < 9; i++) par[i] = par_in[size_t(s) * 12 + i];
+  const bool ok = par_in[size_t(s) * 12 + 10] != 0.0;
 
   // --- walk 2: C = sum g g^T and T = sum g^(x6)
   double acc[34];
@@ -952,83 +1062,12 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip
   GPoint pick[2];  // picks t = lane and t = lane + 32 (t < 50)
   pick[0] = pick[1] = q;
   if (picks) {
-    // The picks index the kd-tree's result order = ascending (distance, index).  Only 50 of the n order
-    // statistics are needed, so the list is not sorted: a counting sort groups the neighbours into distance
-    // buckets (a monotone function of the binary32 distance, ~3 neighbours per bucket), and every pick then
-    // selects its element inside one bucket by exact (distance, position) comparisons — the list is in index
-    // order, so the position breaks distance ties.  O(n) + O(50 m^2) instead of ranking all n against all n.
-    constexpr int nb = kRankBuckets;
-    const float bscale = float(nb) / r2_f;
-    auto dist_of = [&](int i) {
-      const GPoint p = list[i];
-      return dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
-    };
-    for (int i = lane; i < kRankBuckets; i += 32) rk.cur[i] = 0;
-    __syncwarp();
-    for (int i = lane; i < n_list; i += 32) {
-      const int b = min(nb - 1, int(dist_of(i) * bscale));
-      rk.bucket[i] = (unsigned char)b;
-      atomicAdd(&rk.cur[b], 1);
-    }
-    __syncwarp();
-    {  // exclusive prefix over the bucket counts: 8 consecutive buckets per lane
-      int c[8], tot = 0;
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        c[k] = rk.cur[8 * lane + k];
-        tot += c[k];
-      }
-      int incl = tot;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-      }
-      int run = incl - tot;
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        rk.cur[8 * lane + k] = run;
-        run += c[k];
-      }
-    }
-    __syncwarp();
-    for (int i = lane; i < n_list; i += 32) rk.order[atomicAdd(&rk.cur[rk.bucket[i]], 1)] = (unsigned short)i;
-    __syncwarp();
-    // cur[b] is now the end of bucket b (= the start of bucket b + 1)
-    auto select_rank = [&](int r) {
-      int lo_b = 0, hi_b = nb - 1;  // first bucket whose end exceeds r
-      while (lo_b < hi_b) {
-        const int mid = (lo_b + hi_b) >> 1;
-        if (rk.cur[mid] > r) hi_b = mid;
-        else lo_b = mid + 1;
-      }
-      const int lo = lo_b > 0 ? rk.cur[lo_b - 1] : 0, hi = rk.cur[lo_b];
-      const int k = r - lo;
-      int found = rk.order[lo];
-      if (hi - lo == 1) return found;  // (the common case at ~1.6 neighbours per bucket)
-      for (int a = lo; a < hi; a++) {
-        const int e = rk.order[a];
-        const float de = dist_of(e);
-        int cnt = 0;
-        for (int b2 = lo; b2 < hi; b2++) {
-          const int f = rk.order[b2];
-          const float df = dist_of(f);
-          cnt += (df < de || (df == de && f < e)) ? 1 : 0;
-        }
-        if (cnt == k) {
-          found = e;
-          break;
-        }
-      }
-      return found;
-    };
-    const uint32_t* raw = rand_raw + size_t(50) * size_t(rand_off[s]);
     int cam1 = 0;
 #pragma unroll
     for (int u = 0; u < 2; u++) {
       const int t = lane + 32 * u;
       if (t < 50) {
-        pick[u] = list[select_rank(int(raw[t] % uint32_t(n_list)))];
+        pick[u] = list[picks_in[size_t(s) * 50 + t]];
         cam1 += int(pick[u].tag & kTagCamBit);
         accumulate(pick[u]);
       }
@@ -1047,10 +1086,10 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip
     const double a32 = warp_sum(acc[32]), a33 = warp_sum(acc[33]);
 #pragma unroll
     for (int i = 0; i < 6; i++) acc[i] = __shfl_sync(0xffffffffu, r32, i);  // sum g g^T, needed by every lane
-    if (lane >= 6) sm.T[lane - 6] = r32 * c_multinomial6[lane - 6];          // T_0 .. T_25
+    if (lane >= 6) sT[lane - 6] = r32 * c_multinomial6[lane - 6];          // T_0 .. T_25
     if (lane == 0) {
-      sm.T[26] = a32 * c_multinomial6[26];
-      sm.T[27] = a33 * c_multinomial6[27];
+      sT[26] = a32 * c_multinomial6[26];
+      sT[27] = a33 * c_multinomial6[27];
     }
   }
   double w3[3], V3[3][3];
@@ -1084,7 +1123,7 @@ k_taubin_axes(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip
     monomials6(gn, m6);
     double S = 0.0;
 #pragma unroll
-    for (int t = 0; t < 28; t++) S += sm.T[t] * m6[t];
+    for (int t = 0; t < 28; t++) S += sT[t] * m6[t];
     const bool better = S > bestS || (S == bestS && (d < bestD || (d == bestD && before(key, bestP))));
     if (better) {
       bestS = S; bestD = d; bestP = key;
@@ -1284,6 +1323,7 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
   constexpr size_t kPoolBytes = size_t(4) << 30;
   const int chunk = int(std::min<size_t>(size_t(n), std::max<size_t>(kWarps, kPoolBytes / (size_t(stride) * sizeof(GPoint)))));
   if (c->moments.reserve(size_t(n) * kMomentStride * sizeof(double)) || c->nn_counts.reserve(size_t(n) * 8) ||
+      c->quad_par.reserve(size_t(n) * 12 * sizeof(double)) ||
       c->counters.reserve(64) || c->nbr_pool.reserve(size_t(chunk) * size_t(stride) * sizeof(GPoint)) ||
       c->nbr_heads.reserve(size_t(chunk) * sizeof(float4)))
     return AG_ERR_CUDA;
@@ -1294,17 +1334,17 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
   const double inv_r = ldexp(1.0, int(lrint(log2(1.0 / radius))));
   unsigned long long* ctr = c->counters.as<unsigned long long>();
   RowIndex* ri = c->row_index.as<RowIndex>();
-  const size_t smem = sizeof(AxesSmem) * kWarps + (c->params.deterministic_normals == 0 ? sizeof(RankSmem) * kWarps : 0);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_taubin_axes, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         int(sizeof(AxesSmem) * kWarps + sizeof(RankSmem) * kWarps));
-    cudaFuncSetAttribute(k_taubin_axes, cudaFuncAttributePreferredSharedMemoryCarveout, 75);  // 4 CTAs/SM in either mode
+    cudaFuncSetAttribute(k_ball_search, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_rank_picks<kRankCap>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         int(kWarps * (kRankCap * 6 + kRankBuckets * 4)));
+    cudaFuncSetAttribute(k_rank_picks<1024>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_rank_picks<kRankCap>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (getenv("AG_FORCE_JACOBI")) {
       const int one = 1;
       cudaMemcpyToSymbol(g_force_jacobi, &one, sizeof(one));
     }
-    cudaFuncSetAttribute(k_ball_search, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     attr_set = true;
   }
   const HandConst& h = c->hand;
@@ -1323,7 +1363,8 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
       AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
       c->rand_count = hs.size();
     }
-    if (c->rand_off.reserve(size_t(n) * 4 + 16) || c->rand_carry.reserve(16)) return AG_ERR_CUDA;
+    if (c->rand_off.reserve(size_t(n) * 4 + 16) || c->rand_carry.reserve(16) || c->picks.reserve(size_t(n) * 100))
+      return AG_ERR_CUDA;
     d_rand = c->rand_raw.as<uint32_t>();
     d_rand_off = c->rand_off.as<int>();
     c->rand_consumed_bound += n;
@@ -1338,6 +1379,24 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
                                                          rpad, c->nbr_pool.as<GPoint>(), stride,
                                                          c->nn_counts.as<int2>(), c->nbr_heads.as<float4>());
     if (timed) record_event(c, c->ev_k[1]);
+    if (rand_mode) {
+      // the reference's rand() % n picks depend on the neighbour lists only: ranked on a second stream while
+      // this one accumulates the moments and solves the eigenproblem (fork / join by events, also under capture)
+      AG_CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
+      AG_CUDA_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+      k_rand_offsets<<<1, 1024, 0, c->stream2>>>(c->nn_counts.as<int2>(), s0, m, d_count, d_rand_off, c->rand_carry.as<int>());
+      const size_t rank_smem = size_t(kWarps) * (size_t(stride <= 1024 ? 1024 : kRankCap) * 6 + kRankBuckets * 4);
+      if (stride <= 1024)
+        k_rank_picks<1024><<<blocks, kWarps * 32, rank_smem, c->stream2>>>(
+            c->vox.as<GPoint>(), ri, d_indices, s0, s0 + m, d_count, c->nbr_pool.as<GPoint>(), stride,
+            c->nn_counts.as<int2>(), r2, d_rand, d_rand_off, c->picks.as<unsigned short>());
+      else
+        k_rank_picks<kRankCap><<<blocks, kWarps * 32, rank_smem, c->stream2>>>(
+            c->vox.as<GPoint>(), ri, d_indices, s0, s0 + m, d_count, c->nbr_pool.as<GPoint>(), stride,
+            c->nn_counts.as<int2>(), r2, d_rand, d_rand_off, c->picks.as<unsigned short>());
+      AG_CUDA_CHECK(cudaEventRecord(c->ev_join, c->stream2));
+      c->launches += 2;
+    }
     {
       // warps per sample.  Measured on B200: a 2000-sample launch takes 10.2 / 11.3 / 14.3 us with 1 / 2 / 4 warps
       // per sample — it is bounded by fixed costs (launch, first-touch latencies, reduction), not by one warp
@@ -1357,16 +1416,16 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
       else k_taubin_moments<1><<<grid, kWarps * 32, 0, c->stream>>>(s0, m, hd, pl, stride, inv_r, mo);
     }
     if (timed) record_event(c, c->ev_k[2]);
-    if (rand_mode) {
-      k_rand_offsets<<<1, 1024, 0, c->stream>>>(c->nn_counts.as<int2>(), s0, m, d_count, d_rand_off, c->rand_carry.as<int>());
-      c->launches += 1;
-    }
-    k_taubin_axes<<<blocks, kWarps * 32, smem, c->stream>>>(
+    k_taubin_solve<<<blocks, kWarps * 32, 0, c->stream>>>(ri, d_indices, s0, s0 + m, d_count, c->moments.as<double>(),
+                                                           c->quad_par.as<double>());
+    if (rand_mode) AG_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));  // the picks are ready
+    k_axes_finish<<<blocks, kWarps * 32, 0, c->stream>>>(
         c->vox.as<GPoint>(), ri, d_indices, s0, s0 + m, d_count, c->nbr_pool.as<GPoint>(), stride,
-        c->nn_counts.as<int2>(), inv_r, r2, c->moments.as<double>(), h.cam[0][0], h.cam[0][1], h.cam[0][2], h.cam[1][0],
-        h.cam[1][1], h.cam[1][2], d_frames, write_normals ? c->normals.as<double>() : nullptr, d_rand, d_rand_off);
+        c->nn_counts.as<int2>(), inv_r, c->moments.as<double>(), c->quad_par.as<double>(), h.cam[0][0], h.cam[0][1],
+        h.cam[0][2], h.cam[1][0], h.cam[1][1], h.cam[1][2], d_frames, write_normals ? c->normals.as<double>() : nullptr,
+        rand_mode ? c->picks.as<unsigned short>() : nullptr);
     if (timed) record_event(c, c->ev_k[3]);
-    c->launches += 3;
+    c->launches += 4;
   }
   k_quadric_finish<<<(n + 255) / 256, 256, 0, c->stream>>>(c->vox.as<GPoint>(), ri, d_indices, n, d_count,
                                                           c->nn_counts.as<int2>(), ctr, write_normals ? 1 : 0);

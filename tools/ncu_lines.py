@@ -6,7 +6,10 @@ import csv, re, subprocess, sys, tempfile, os
 src_csv, obj, kname = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 rows = list(csv.reader(open(src_csv)))
-hdr = rows[1]; data = rows[2:]
+# the export holds one table per profiled launch ("Kernel Name" row, header row, SASS rows): take the first whose name matches
+starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name'] + [len(rows)]
+tab = next((a, b) for a, b in zip(starts, starts[1:]) if kname in rows[a][1])
+hdr = rows[tab[0] + 1]; data = rows[tab[0] + 2:tab[1]]
 ia, ie, ism = hdr.index('Address'), hdr.index('Instructions Executed'), hdr.index('# Samples')
 with tempfile.TemporaryDirectory() as d:
     subprocess.check_call(['cuobjdump', '-xelf', 'all', os.path.abspath(obj)], cwd=d, stdout=subprocess.DEVNULL)
