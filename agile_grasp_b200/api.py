@@ -21,7 +21,7 @@ EXPORTS = [
     "ag_get_timings", "ag_free", "ag_svm_load", "ag_svm_free", "ag_svm_info", "ag_localize", "ag_localize_device",
     "ag_classify", "ag_set_svm", "ag_set_export_buffer", "ag_get_points", "ag_get_images", "ag_get_normals", "ag_preprocess", "ag_set_cloud", "ag_radius_search",
     "ag_fit_quadrics", "ag_hand_sweep", "ag_sweep_debug", "ag_hog_svm",
-    "ag_find_handles", "ag_load_pcd", "ag_localize_batch", "ag_gather_slot_bytes", "ag_gather_create", "ag_gather_connect", "ag_gather_wait", "ag_gather_destroy",
+    "ag_find_handles", "ag_load_pcd", "ag_localize_batch", "ag_gather_slot_bytes", "ag_gather_create", "ag_gather_connect", "ag_gather_wait", "ag_gather_result", "ag_gather_destroy",
 ]
 
 
@@ -73,6 +73,7 @@ def lib():
     L.ag_gather_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_char_p]
     L.ag_gather_connect.argtypes = [vp, C.c_char_p]
     L.ag_gather_wait.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.ag_gather_result.argtypes = [vp, C.POINTER(C.c_int32), ip, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     L.ag_gather_destroy.argtypes = [vp]
     _LIB = L
     return L
@@ -246,9 +247,22 @@ class Context:
         """handles: list of every rank's 64-byte IPC handle, in rank order"""
         _check(lib().ag_gather_connect(self.h, b"".join(handles)))
 
+    def gather_result(self, copy=True):
+        """the merged grasp list of the last localize() over all ranks (sample-major, as one unsharded call would
+        return it): (n_hyp per rank, merged records from the mapped host copy, device address of the merged list)"""
+        n = (C.c_int32 * self._gather_world)()
+        tot, dptr, hptr = C.c_int(), C.c_void_p(), C.c_void_p()
+        _check(lib().ag_gather_result(self.h, n, C.byref(tot), C.byref(dptr), C.byref(hptr)))
+        recs = None
+        if copy:
+            if tot.value == 0:
+                recs = np.zeros(0, GRASP_DTYPE)
+            else:
+                recs = np.frombuffer(C.string_at(hptr.value, tot.value * C.sizeof(AgGrasp)), dtype=GRASP_DTYPE).copy()
+        return list(n), recs, dptr.value
+
     def gather_wait(self):
-        """waits until every rank's list of the last localize() has landed in this rank's buffer;
-        returns (n_hyp per rank, device address of slot 0, slot bytes)"""
+        """the exchange completes inside localize(); reports it: (n_hyp per rank, device address of slot 0, slot bytes)"""
         n = (C.c_int32 * self._gather_world)()
         ptr, sb = C.c_void_p(), C.c_size_t()
         _check(lib().ag_gather_wait(self.h, n, C.byref(ptr), C.byref(sb)))

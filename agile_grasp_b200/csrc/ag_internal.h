@@ -114,8 +114,15 @@ struct Ctx {
   void* gather_buf = nullptr;
   void* gather_peer[AG_MAX_GATHER_RANKS] = {nullptr};
   void* gather_done = nullptr;
-  void* gather_host_hdr = nullptr;
-  void* gather_host_hdr_dev = nullptr;
+  void* gather_zero = nullptr;        // device int that stays 0
+  void* gather_merged = nullptr;      // merged list of all ranks (device), in the reference's sample-major order
+  void* gather_host = nullptr;        // mapped host copy: GatherHost header + merged records
+  void* gather_host_dev = nullptr;
+  int gather_cap_total = 0;
+  bool gather_pending = false;        // a merge of this call is in the stream
+  bool gather_valid = false;          // gather_host describes the last completed call
+  int pend_slot_first = 0, pend_slot_step = 1;  // position of this context's samples in the full sample list
+  std::vector<int> sample_host;       // interleaved share of caller-supplied indices
   size_t gather_slot_bytes = 0;
   int gather_world = 0, gather_rank = 0;
   unsigned gather_epoch = 0;

@@ -80,14 +80,14 @@ __host__ __device__ static inline uint64_t splitmix64(uint64_t x) {
   return x ^ (x >> 31);
 }
 // seeded stratified draw: sample k of S lies in [k n / S, (k + 1) n / S).  A shard handles the samples
-// k = k_lo + j, j < count (count = launch bound; k_lo = 0 and count = s_req without sharding).
-__global__ void k_draw_samples(RowIndex* ri, int s_req, uint64_t seed, int* out, int k_lo, int count) {
+// k = k_first + j k_step, j < count (count = launch bound; k_first = 0, k_step = 1 and count = s_req without sharding).
+__global__ void k_draw_samples(RowIndex* ri, int s_req, uint64_t seed, int* out, int k_first, int k_step, int count) {
   const int n = ri->n_points;
   const int S = s_req < n ? s_req : n;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j == 0) ri->n_samples = min(max(S - k_lo, 0), count);
+  if (j == 0) ri->n_samples = S > k_first ? min((S - k_first + k_step - 1) / k_step, count) : 0;
   if (j >= count) return;
-  const int k = k_lo + j;
+  const int k = k_first + j * k_step;
   if (k >= S) {
     out[j] = -1;
     return;
@@ -129,30 +129,48 @@ struct HostOut {
 // mappings.  Slot layout: [uint32 epoch flag, 12 pad][int32 n_hyp, n_vox, n_samples, error][records].
 struct PeerOut {
   char* slot[AG_MAX_GATHER_RANKS];
+  const unsigned* ack;  // this rank's ack words (one per consumer, kAckStride bytes apart): last epoch it has consumed
   int world;         // 0 = peer gather not configured
   int cap;           // records per slot
   unsigned epoch;
   unsigned* done;    // CTA completion counter of this launch (device, zeroed by the last CTA)
   int final_pass;    // 0: first export of a call (publishes only if no sample needs the large-slab re-run)
 };
+constexpr int kAckStride = 64;                                    // bytes between the ack words of two consumers
+constexpr int kAckBytes = AG_MAX_GATHER_RANKS * kAckStride;       // ack area in front of the slots of a gather buffer
 constexpr int kSlotHeaderBytes = 32;
 
 __global__ void k_export(const ag_grasp* __restrict__ raw, const int* __restrict__ slots, const int* __restrict__ n_sel,
                          const float* __restrict__ scores, const RowIndex* ri, const int* overflow,
                          const unsigned long long* counters, HostOut* hdr, ag_grasp* out_host, ag_grasp* out_dev,
-                         int* exp_hdr, ag_grasp* out_exp, int cap, int cap_exp, PeerOut peer, unsigned stamp) {
+                         int* exp_hdr, ag_grasp* out_exp, int cap, int cap_exp, PeerOut peer, unsigned stamp,
+                         int slot_first, int slot_step) {
   // a record is 10 x 16 bytes: three records per warp pass, every lane moves one uint4 (coalesced
   // 480-byte stores — the mapped host destination is written over PCIe and needs full-width writes)
   static_assert(sizeof(ag_grasp) == 160, "record layout");
   const int n = min(*n_sel, cap);
   const int lane = threadIdx.x & 31;
+  if (peer.world > 0) {
+    // back-pressure: the slot about to be written held epoch - 2; every consumer must have acknowledged it
+    // (k_gather_merge stores the epoch it has finished reading into this rank's ack words)
+    if (threadIdx.x < peer.world && peer.epoch > 2u) {
+      const volatile unsigned* a = reinterpret_cast<const volatile unsigned*>(
+          reinterpret_cast<const char*>(peer.ack) + size_t(threadIdx.x) * kAckStride);
+      const long long t0 = clock64();
+      while (int(*a - (peer.epoch - 2u)) < 0 && clock64() - t0 < 4000000000ll) __nanosleep(100);
+    }
+    __syncthreads();
+  }
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   const int sub = lane / 10, part = lane % 10;
   for (int base = warp_global * 3; base < n; base += n_warps * 3) {
     const int i = base + sub;
     if (lane >= 30 || i >= n) continue;
     uint4 v = reinterpret_cast<const uint4*>(raw + slots[i])[part];
-    if (part == 8 && scores) v.x = __float_as_uint(scores[i]);            // byte 128: score
+    if (part == 8) {
+      if (scores) v.x = __float_as_uint(scores[i]);                        // byte 128: score
+      v.z = uint32_t(slot_first + int(v.z) * slot_step);                   // byte 136: sample_slot, position in the FULL sample list
+    }
     if (part == 9) {
       v.z = uint32_t(i);                                                   // byte 152: image_id
       v.w = (v.w & 0x00FFFFFFu) | (stamp << 24);                           // byte 159: call stamp
@@ -170,7 +188,7 @@ __global__ void k_export(const ag_grasp* __restrict__ raw, const int* __restrict
   }
   if (peer.world > 0) {
     // publish: every CTA fences its peer stores; the last one to finish writes the headers, fences again and
-    // raises the epoch flags the consumers (k_gather_wait on each rank) spin on
+    // raises the epoch flags the consumers (k_gather_merge on each rank) spin on
     __shared__ bool s_last;
     __threadfence_system();
     __syncthreads();
@@ -205,32 +223,134 @@ __global__ void k_export(const ag_grasp* __restrict__ raw, const int* __restrict
   }
 }
 
-// one thread per rank: spins until slot r of this rank's gather buffer carries `epoch` (the producer's
-// export kernel wrote it after a system-scope fence), then copies the slot header to mapped host memory.
-// A producer that never arrives (a failed peer) ends the wait after ~2 s with status 1.
-__global__ void k_gather_wait(const char* buf, size_t slot_bytes, int world, unsigned epoch, int* host_hdr /* world x 4 + 1 */) {
-  const int r = threadIdx.x;
-  __shared__ int s_bad;
-  if (r == 0) s_bad = 0;
+// Consumer side of the peer gather, enqueued right behind the export kernel of the same call: waits until every
+// rank's list of this epoch has landed in this rank's buffer, merges the lists into ONE list in the reference's
+// order (sample-major, orientation-minor: hand_search.cpp:194-200) — whatever the sample assignment was,
+// contiguous or interleaved: the position of a record is the number of records with a smaller
+// (sample position, orientation) key over all lists, found by one binary search per list — writes it to device
+// and mapped host memory, and acknowledges the epoch to every producer (its slot may then be overwritten).
+struct GatherHost {  // mapped host header of the merged list
+  int n_total, status, world, pad;
+  int n_per_rank[AG_MAX_GATHER_RANKS];
+  int err_per_rank[AG_MAX_GATHER_RANKS];
+};
+struct MergeArgs {
+  const char* buf;         // this epoch's slots of this rank's gather buffer
+  size_t slot_bytes;
+  unsigned* ack_peer[AG_MAX_GATHER_RANKS];  // producer p's ack word for this consumer
+  int world;
+  unsigned epoch;
+  const int* overflow;     // [0] != 0: this rank's own list is re-exported after a host-side re-run -> skip this pass
+  int final_pass;
+  ag_grasp* merged_dev;
+  ag_grasp* merged_host;
+  GatherHost* host;
+  int cap_total;
+  unsigned* done;
+};
+__device__ __forceinline__ long long grasp_key(const ag_grasp* g) {
+  return (static_cast<long long>(g->sample_slot) << 3) | static_cast<long long>(g->orientation & 7);
+}
+__global__ void __launch_bounds__(256)
+k_gather_merge(const MergeArgs A) {
+  __shared__ int s_n[AG_MAX_GATHER_RANKS], s_err[AG_MAX_GATHER_RANKS], s_bad;
+  __shared__ bool s_last;
+  if (!A.final_pass && A.overflow[0] != 0) return;
+  if (threadIdx.x == 0) s_bad = 0;
   __syncthreads();
-  if (r < world) {
-    const volatile unsigned* flag = reinterpret_cast<const volatile unsigned*>(buf + size_t(r) * slot_bytes);
+  if (threadIdx.x < A.world) {
+    const int r = threadIdx.x;
+    const volatile unsigned* flag = reinterpret_cast<const volatile unsigned*>(A.buf + size_t(r) * A.slot_bytes);
     const long long t0 = clock64();
     bool ok = true;
-    while (int(*flag - epoch) < 0) {  // (a producer that ran ahead carries a later epoch: never a deadlock)
+    while (*flag != A.epoch) {  // (a producer cannot run ahead: it waits for this consumer's acknowledgement)
       if (clock64() - t0 > 4000000000ll) {
         ok = false;
         break;
       }
-      __nanosleep(200);
+      __nanosleep(100);
     }
     __threadfence_system();
-    const volatile int* h4 = reinterpret_cast<const volatile int*>(buf + size_t(r) * slot_bytes + 16);
-    for (int k = 0; k < 4; k++) host_hdr[r * 4 + k] = h4[k];
+    const volatile int* h4 = reinterpret_cast<const volatile int*>(A.buf + size_t(r) * A.slot_bytes + 16);
+    s_n[r] = ok ? h4[0] : 0;
+    s_err[r] = ok ? h4[3] : 0x200;
     if (!ok) atomicOr(&s_bad, 1);
   }
   __syncthreads();
-  if (r == 0) host_hdr[world * 4] = s_bad;
+  int total = 0;
+  for (int r = 0; r < A.world; r++) total += s_n[r];
+  // one record per 10 lanes (16 bytes each), three records per warp pass
+  const int lane = threadIdx.x & 31, sub = lane / 10, part = lane % 10;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int base = warp_global * 3; base < total; base += n_warps * 3) {
+    const int item = base + sub;
+    if (lane >= 30 || item >= total) continue;
+    int r = 0, i = item;
+    while (i >= s_n[r]) {
+      i -= s_n[r];
+      r++;
+    }
+    const ag_grasp* mine = reinterpret_cast<const ag_grasp*>(A.buf + size_t(r) * A.slot_bytes + kSlotHeaderBytes) + i;
+    const long long key = grasp_key(mine);
+    int pos = 0;
+    for (int q = 0; q < A.world; q++) {
+      if (q == r) {
+        pos += i;
+        continue;
+      }
+      // records of list q in front of mine: smaller key, or the same key from a lower rank (ranks that are not
+      // shards of one call produce equal keys: the merge is then stable in rank order)
+      const ag_grasp* lst = reinterpret_cast<const ag_grasp*>(A.buf + size_t(q) * A.slot_bytes + kSlotHeaderBytes);
+      int lo = 0, hi = s_n[q];
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const long long km = grasp_key(lst + mid);
+        if (km < key || (km == key && q < r)) lo = mid + 1;
+        else hi = mid;
+      }
+      pos += lo;
+    }
+    if (pos < A.cap_total) {
+      uint4 v = reinterpret_cast<const uint4*>(mine)[part];
+      if (part == 9) v.z = uint32_t(-1);  // image_id: the grasp images stay on the producing rank
+      reinterpret_cast<uint4*>(A.merged_dev + pos)[part] = v;
+      reinterpret_cast<uint4*>(A.merged_host + pos)[part] = v;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(A.done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x < A.world) {  // every list of this epoch has been read: the producers may reuse the slots
+    A.host->n_per_rank[threadIdx.x] = s_n[threadIdx.x];
+    A.host->err_per_rank[threadIdx.x] = s_err[threadIdx.x];
+    *reinterpret_cast<volatile unsigned*>(A.ack_peer[threadIdx.x]) = A.epoch;
+  }
+  if (threadIdx.x == 0) {
+    A.host->n_total = min(total, A.cap_total);
+    A.host->world = A.world;
+    A.host->status = s_bad | (total > A.cap_total ? 2 : 0);
+    *A.done = 0u;
+  }
+}
+// publishes an empty list (a call without samples still takes part in the exchange)
+__global__ void k_publish_empty(PeerOut peer, const RowIndex* ri) {
+  if (threadIdx.x < peer.world) {
+    if (peer.epoch > 2u) {
+      const volatile unsigned* a = reinterpret_cast<const volatile unsigned*>(
+          reinterpret_cast<const char*>(peer.ack) + size_t(threadIdx.x) * kAckStride);
+      const long long t0 = clock64();
+      while (int(*a - (peer.epoch - 2u)) < 0 && clock64() - t0 < 4000000000ll) __nanosleep(100);
+    }
+    int* h4 = reinterpret_cast<int*>(peer.slot[threadIdx.x] + 16);
+    h4[0] = 0;
+    h4[1] = ri->n_points;
+    h4[2] = 0;
+    h4[3] = ri->error;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned*>(peer.slot[threadIdx.x]) = peer.epoch;
+  }
 }
 
 // ---- SVM model file (OpenCV 2.4 YAML, svm_032015_linear_20_20_same:1-16,780-789) -------------
@@ -363,7 +483,31 @@ static void launch_export(Ctx* c, const PeerOut& peer) {
   k_export<<<32, 256, 0, c->stream>>>(c->grasps_raw.as<ag_grasp>(), c->hyp_slots.as<int>(), c->pend_nsel,
                                       c->attached_svm ? c->scores.as<float>() : nullptr, c->row_index.as<RowIndex>(),
                                       hand_sweep_overflow_ptr(c), c->counters.as<unsigned long long>(), hdr, recs,
-                                      c->grasps.as<ag_grasp>(), exp_hdr, exp_recs, int(size_t(c->pend_S) * 8), cap_exp, peer, c->stamp);
+                                      c->grasps.as<ag_grasp>(), exp_hdr, exp_recs, int(size_t(c->pend_S) * 8), cap_exp, peer,
+                                      c->stamp, c->pend_slot_first, c->pend_slot_step);
+}
+
+// consumer side of the peer gather for the current epoch (right behind the export of the same call)
+static void launch_merge(Ctx* c, const PeerOut& peer) {
+  if (peer.world <= 0) return;
+  MergeArgs A;
+  std::memset(&A, 0, sizeof(A));
+  const size_t half = size_t(c->gather_world) * c->gather_slot_bytes;
+  A.buf = static_cast<const char*>(c->gather_buf) + kAckBytes + (peer.epoch & 1u) * half;
+  A.slot_bytes = c->gather_slot_bytes;
+  for (int r = 0; r < c->gather_world; r++)
+    A.ack_peer[r] = reinterpret_cast<unsigned*>(static_cast<char*>(c->gather_peer[r]) + size_t(c->gather_rank) * kAckStride);
+  A.world = c->gather_world;
+  A.epoch = peer.epoch;
+  A.overflow = c->overflow.p ? hand_sweep_overflow_ptr(c) : static_cast<const int*>(c->gather_zero);
+  A.final_pass = peer.final_pass;
+  A.merged_dev = static_cast<ag_grasp*>(c->gather_merged);
+  A.host = static_cast<GatherHost*>(c->gather_host_dev);
+  A.merged_host = reinterpret_cast<ag_grasp*>(static_cast<char*>(c->gather_host_dev) + sizeof(GatherHost));
+  A.cap_total = c->gather_cap_total;
+  A.done = static_cast<unsigned*>(c->gather_done) + 4;
+  k_gather_merge<<<64, 256, 0, c->stream>>>(A);
+  c->launches += 1;
 }
 
 // First half of a localize call: everything is enqueued on the context's stream, nothing is waited for.
@@ -381,17 +525,28 @@ static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, in
   c->two_cams = size_left < n_in;
   const bool given = indices && n_indices > 0;
   const int S_total = given ? n_indices : std::max(0, c->params.num_samples);
-  // sample sharding (ag_params.shard_index / shard_count): this context's contiguous share of the samples
+  // sample sharding (ag_params.shard_index / shard_count): this context's share of the samples — a contiguous
+  // range, or (shard_interleave) every shard_count-th sample, which balances scenes whose hypotheses cluster
   const int sh_n = std::max(1, c->params.shard_count), sh_i = std::min(std::max(0, c->params.shard_index), sh_n - 1);
+  const bool interleave = sh_n > 1 && c->params.shard_interleave != 0;
   const int k_lo = int((long long)S_total * sh_i / sh_n), k_hi = int((long long)S_total * (sh_i + 1) / sh_n);
-  const int S = k_hi - k_lo;
-  if (given) indices += k_lo;
+  const int k_first = interleave ? sh_i : k_lo, k_step = interleave ? sh_n : 1;
+  const int S = interleave ? (S_total > sh_i ? (S_total - sh_i + sh_n - 1) / sh_n : 0) : k_hi - k_lo;
   c->n_samples = S;
+  c->pend_slot_first = k_first;
+  c->pend_slot_step = k_step;
   const size_t slots = size_t(S) * 8;
   RowIndex* ri = c->row_index.as<RowIndex>();
   if (given) {  // caller's indices go to a staging buffer first: the (graph-captured) body only copies device to device
-    if (c->sample_stage.reserve(size_t(S) * 4)) return AG_ERR_CUDA;
-    AG_CUDA_CHECK(cudaMemcpyAsync(c->sample_stage.p, indices, size_t(S) * 4, cudaMemcpyHostToDevice, st));
+    if (c->sample_stage.reserve(size_t(std::max(S, 1)) * 4)) return AG_ERR_CUDA;
+    if (interleave) {
+      c->sample_host.resize(S);
+      for (int j = 0; j < S; j++) c->sample_host[j] = indices[k_first + j * k_step];
+      indices = c->sample_host.data();
+    } else {
+      indices += k_lo;
+    }
+    if (S > 0) AG_CUDA_CHECK(cudaMemcpyAsync(c->sample_stage.p, indices, size_t(S) * 4, cudaMemcpyHostToDevice, st));
   }
   int* d_nsel = nullptr;
   // Everything from the voxelisation to the scoring: ~25 launches without a host dependency.  The second call
@@ -426,7 +581,7 @@ static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, in
       AG_CUDA_CHECK(cudaMemcpyAsync(c->samples.p, c->sample_stage.p, size_t(S) * 4, cudaMemcpyDeviceToDevice, st));
       k_check_samples<<<(S + 255) / 256, 256, 0, st>>>(ri, S, c->samples.as<int>());
     } else {
-      k_draw_samples<<<(S + 255) / 256, 256, 0, st>>>(ri, S_total, c->params.seed, c->samples.as<int>(), k_lo, S);
+      k_draw_samples<<<(S + 255) / 256, 256, 0, st>>>(ri, S_total, c->params.seed, c->samples.as<int>(), k_first, k_step, S);
     }
     c->launches += 1;
     rc = fit_quadrics_device(c, c->samples.as<int>(), S, &ri->n_samples, c->params.nn_radius_taubin,
@@ -515,28 +670,60 @@ static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, in
       victim->last_use = c->g_tick;
     }
   }
-  if (S == 0) return AG_OK;  // (localize_end reads the cloud size back)
   PeerOut peer;
   std::memset(&peer, 0, sizeof(peer));
   if (c->gather_world > 0 && c->gather_connected) {
     c->gather_epoch++;
     const size_t half = size_t(c->gather_world) * c->gather_slot_bytes;
     for (int r = 0; r < c->gather_world; r++)
-      peer.slot[r] = static_cast<char*>(c->gather_peer[r]) + (c->gather_epoch & 1u) * half +
+      peer.slot[r] = static_cast<char*>(c->gather_peer[r]) + kAckBytes + (c->gather_epoch & 1u) * half +
                      size_t(c->gather_rank) * c->gather_slot_bytes;
+    peer.ack = static_cast<const unsigned*>(c->gather_buf);
     peer.world = c->gather_world;
     peer.cap = int((c->gather_slot_bytes - kSlotHeaderBytes) / sizeof(ag_grasp));
     peer.epoch = c->gather_epoch;
     peer.done = static_cast<unsigned*>(c->gather_done);
   }
-  c->pend_S = S;
-  c->pend_nsel = d_nsel;
   static_assert(sizeof(PeerOut) <= sizeof(c->pend_peer), "pending export arguments");
   std::memcpy(c->pend_peer, &peer, sizeof(peer));
+  if (S == 0) {  // (localize_end reads the cloud size back); a connected gather still gets this rank's (empty) list
+    if (peer.world > 0) {
+      k_publish_empty<<<1, 32, 0, st>>>(peer, ri);
+      peer.final_pass = 1;
+      launch_merge(c, peer);
+      c->gather_pending = true;
+    }
+    return AG_OK;
+  }
+  c->pend_S = S;
+  c->pend_nsel = d_nsel;
   launch_export(c, peer);
+  launch_merge(c, peer);
+  c->gather_pending = peer.world > 0;
   c->launches += 1;
   cudaEventRecord(c->ev[7], st);
   c->pend_active = true;
+  return AG_OK;
+}
+
+// after the stream has been waited for: status of the merged list of the peer gather
+static int gather_collect(Ctx* c) {
+  c->gather_pending = false;
+  const GatherHost* gh = static_cast<const GatherHost*>(c->gather_host);
+  c->gather_valid = true;
+  if (gh->status & 1) {
+    set_error("peer gather: a rank did not publish its grasp list (timeout)");
+    return AG_ERR_CUDA;
+  }
+  if (gh->status & 2) {
+    set_error("peer gather: the merged list exceeds the gather capacity (ag_gather_create num_samples too small)");
+    return AG_ERR_CAPACITY;
+  }
+  for (int r = 0; r < c->gather_world; r++)
+    if (gh->err_per_rank[r] & 0x100) {
+      set_error("peer gather: a rank produced more hypotheses than a gather slot holds");
+      return AG_ERR_CAPACITY;
+    }
   return AG_OK;
 }
 
@@ -548,6 +735,7 @@ static int localize_end(Ctx* c, ag_grasp** out, int* n_out) {
   if (!c->pend_active) {  // no samples requested: only the voxelised cloud exists
     int rc = fetch_cloud_size(c);
     c->timings.n_voxels = c->n_vox;
+    if (rc == AG_OK && c->gather_pending) rc = gather_collect(c);
     return rc;
   }
   c->pend_active = false;
@@ -588,6 +776,7 @@ static int localize_end(Ctx* c, ag_grasp** out, int* n_out) {
     }
     peer.final_pass = 1;
     launch_export(c, peer);
+    launch_merge(c, peer);
     AG_CUDA_CHECK(cudaStreamSynchronize(st));
     Hn = h->n_hyp;
     c->n_hyp = Hn;
@@ -615,6 +804,7 @@ static int localize_end(Ctx* c, ag_grasp** out, int* n_out) {
   c->last_grasps.assign(res, res + Hn);
   *out = res;
   *n_out = Hn;
+  if (c->gather_pending) return gather_collect(c);
   return AG_OK;
 }
 
@@ -985,13 +1175,20 @@ int ag_gather_create(ag_ctx* h, int num_samples, int world, int rank, unsigned c
     return AG_ERR_INVALID;
   }
   c.gather_slot_bytes = ag_gather_slot_bytes(num_samples);
-  const size_t bytes = 2 * size_t(world) * c.gather_slot_bytes;  // two epochs (parity) x world slots
+  // [ack words of the consumers][two epochs (parity) x world slots]
+  const size_t bytes = kAckBytes + 2 * size_t(world) * c.gather_slot_bytes;
   AG_CUDA_CHECK(cudaMalloc(&c.gather_buf, bytes));
   AG_CUDA_CHECK(cudaMemset(c.gather_buf, 0, bytes));
   AG_CUDA_CHECK(cudaMalloc(&c.gather_done, 64));
   AG_CUDA_CHECK(cudaMemset(c.gather_done, 0, 64));
-  AG_CUDA_CHECK(cudaHostAlloc(&c.gather_host_hdr, (world * 4 + 4) * sizeof(int), cudaHostAllocMapped));
-  AG_CUDA_CHECK(cudaHostGetDevicePointer(&c.gather_host_hdr_dev, c.gather_host_hdr, 0));
+  c.gather_zero = static_cast<char*>(c.gather_done) + 32;  // a device int that stays 0
+  // the merged list: every rank's share of up to 8 hypotheses per sample of the whole call
+  c.gather_cap_total = int(std::min<size_t>(size_t(8) * size_t(num_samples) * size_t(world), size_t(1) << 24));
+  const size_t mbytes = size_t(c.gather_cap_total) * sizeof(ag_grasp);
+  AG_CUDA_CHECK(cudaMalloc(&c.gather_merged, mbytes));
+  AG_CUDA_CHECK(cudaHostAlloc(&c.gather_host, sizeof(GatherHost) + mbytes, cudaHostAllocMapped));
+  std::memset(c.gather_host, 0, sizeof(GatherHost));
+  AG_CUDA_CHECK(cudaHostGetDevicePointer(&c.gather_host_dev, c.gather_host, 0));
   cudaIpcMemHandle_t hd;
   AG_CUDA_CHECK(cudaIpcGetMemHandle(&hd, c.gather_buf));
   static_assert(sizeof(hd) == AG_IPC_HANDLE_BYTES, "IPC handle size");
@@ -1000,6 +1197,7 @@ int ag_gather_create(ag_ctx* h, int num_samples, int world, int rank, unsigned c
   c.gather_rank = rank;
   c.gather_epoch = 0;
   c.gather_connected = false;
+  c.gather_valid = false;
   AG_CUDA_CHECK(cudaDeviceSynchronize());
   return AG_OK;
 }
@@ -1025,33 +1223,32 @@ int ag_gather_connect(ag_ctx* h, const unsigned char* handles) {
   return AG_OK;
 }
 
-int ag_gather_wait(ag_ctx* h, int32_t* n_hyp_per_rank, const void** d_slots, size_t* slot_bytes) {
-  if (!h || !h->c.gather_connected || h->c.gather_epoch == 0) {
-    set_error("ag_gather_wait: no connected peer gather / no ag_localize yet");
+int ag_gather_result(ag_ctx* h, int32_t* n_hyp_per_rank, int* n_total, const ag_grasp** d_merged, const ag_grasp** h_merged) {
+  if (!h || !h->c.gather_connected || !h->c.gather_valid) {
+    set_error("ag_gather_result: no connected peer gather / no completed ag_localize yet");
     return AG_ERR_INVALID;
   }
   Ctx& c = h->c;
-  cudaSetDevice(c.device);
-  const char* cur = static_cast<const char*>(c.gather_buf) + (c.gather_epoch & 1u) * size_t(c.gather_world) * c.gather_slot_bytes;
-  k_gather_wait<<<1, 32, 0, c.stream>>>(cur, c.gather_slot_bytes, c.gather_world, c.gather_epoch,
-                                       static_cast<int*>(c.gather_host_hdr_dev));
-  AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
-  const int* hh = static_cast<const int*>(c.gather_host_hdr);
-  if (hh[c.gather_world * 4]) {
-    set_error("ag_gather_wait: a peer did not publish its grasp list (timeout)");
-    return AG_ERR_CUDA;
+  const GatherHost* gh = static_cast<const GatherHost*>(c.gather_host);
+  for (int r = 0; r < c.gather_world && n_hyp_per_rank; r++) n_hyp_per_rank[r] = gh->n_per_rank[r];
+  if (n_total) *n_total = gh->n_total;
+  if (d_merged) *d_merged = static_cast<const ag_grasp*>(c.gather_merged);
+  if (h_merged) *h_merged = reinterpret_cast<const ag_grasp*>(static_cast<const char*>(c.gather_host) + sizeof(GatherHost));
+  return AG_OK;
+}
+
+int ag_gather_wait(ag_ctx* h, int32_t* n_hyp_per_rank, const void** d_slots, size_t* slot_bytes) {
+  if (!h || !h->c.gather_connected || !h->c.gather_valid) {
+    set_error("ag_gather_wait: no connected peer gather / no completed ag_localize yet");
+    return AG_ERR_INVALID;
   }
-  int err = 0;
-  for (int r = 0; r < c.gather_world; r++) {
-    if (n_hyp_per_rank) n_hyp_per_rank[r] = hh[r * 4];
-    err |= hh[r * 4 + 3];
-  }
-  if (d_slots) *d_slots = cur;
+  Ctx& c = h->c;
+  // the exchange completed inside ag_localize (export -> merge in the same stream): this only reports it
+  const GatherHost* gh = static_cast<const GatherHost*>(c.gather_host);
+  for (int r = 0; r < c.gather_world && n_hyp_per_rank; r++) n_hyp_per_rank[r] = gh->n_per_rank[r];
+  if (d_slots)
+    *d_slots = static_cast<const char*>(c.gather_buf) + kAckBytes + (c.gather_epoch & 1u) * size_t(c.gather_world) * c.gather_slot_bytes;
   if (slot_bytes) *slot_bytes = c.gather_slot_bytes;
-  if (err & 0x100) {
-    set_error("ag_gather_wait: a rank produced more hypotheses than a gather slot holds");
-    return AG_ERR_CAPACITY;
-  }
   return AG_OK;
 }
 
@@ -1064,10 +1261,12 @@ int ag_gather_destroy(ag_ctx* h) {
     if (c.gather_connected && r != c.gather_rank && c.gather_peer[r]) cudaIpcCloseMemHandle(c.gather_peer[r]);
   if (c.gather_buf) cudaFree(c.gather_buf);
   if (c.gather_done) cudaFree(c.gather_done);
-  if (c.gather_host_hdr) cudaFreeHost(c.gather_host_hdr);
-  c.gather_buf = c.gather_done = c.gather_host_hdr = c.gather_host_hdr_dev = nullptr;
+  if (c.gather_merged) cudaFree(c.gather_merged);
+  if (c.gather_host) cudaFreeHost(c.gather_host);
+  c.gather_buf = c.gather_done = c.gather_merged = c.gather_host = c.gather_host_dev = c.gather_zero = nullptr;
   c.gather_world = 0;
   c.gather_connected = false;
+  c.gather_valid = false;
   c.state_gen++;
   return AG_OK;
 }

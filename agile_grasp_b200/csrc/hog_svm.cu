@@ -171,10 +171,25 @@ k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slo
   __shared__ uint32_t s_xp[H][RW], s_xn[H][RW], s_yp[H][RW], s_yn[H][RW];  // gradient sign bit-planes
   __shared__ uint32_t s_col[W][3];                  // per column: 80-bit mask of non-zero-gradient pixels
   __shared__ __align__(16) float s_hist[NUB * 36];
-  __shared__ float s_K[1280];                       // kernel values per support vector
+  __shared__ float s_acc[NB][kThreads];             // step 4: the 9 bins of every (block, cell) thread, [bin][thread]
+  __shared__ float s_K[1];                          // kernel value of the (single) support vector
   __shared__ double s_part[kThreads / 32];
+  // the lookup tables of step 4 are indexed per lane: shared memory (constant memory would serialise the warp)
+  __shared__ float s_w[4][CELL_LIST + 1];
+  __shared__ CellRun s_runs[4][kMaxRuns];
+  __shared__ float s_g0[9], s_g1[9];
+  __shared__ int s_h0[9], s_h1[9], s_nruns[4];
   const int n = n_dev ? min(*n_dev, n_bound) : n_bound;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 4 * (CELL_LIST + 1); i += kThreads) (&s_w[0][0])[i] = (&c_hog.w[0][0])[i];
+  for (int i = tid; i < 4 * kMaxRuns; i += kThreads) (&s_runs[0][0])[i] = (&c_hog.runs[0][0])[i];
+  if (tid < 9) {
+    s_g0[tid] = c_hog.g0[tid];
+    s_g1[tid] = c_hog.g1[tid];
+    s_h0[tid] = c_hog.h0[tid];
+    s_h1[tid] = c_hog.h1[tid];
+  }
+  if (tid < 4) s_nruns[tid] = c_hog.n_runs[tid];
   for (int hyp = blockIdx.x; hyp < n; hyp += gridDim.x) {  // persistent CTAs: the count lives on the device
   __syncthreads();
   const uint32_t* src = images + size_t(image_slots ? image_slots[hyp] : hyp) * AG_IMAGE_WORDS;
@@ -222,36 +237,34 @@ k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slo
   if (tid < NUB * 4) {
     const int ub = tid >> 2, cell = tid & 3;
     const int ox = (ub / UBY) * 8, oy = (ub % UBY) * 8;
-    float h[9];
 #pragma unroll
-    for (int b = 0; b < 9; b++) h[b] = 0.f;
-    const int nr = c_hog.n_runs[cell];
+    for (int b = 0; b < 9; b++) s_acc[b][tid] = 0.f;
+    const int nr = s_nruns[cell];
     for (int rI = 0; rI < nr; rI++) {
-      const CellRun run = c_hog.runs[cell][rI];
+      const CellRun run = s_runs[cell][rI];
       const int x = ox + run.j, y0 = oy + run.i0;
       // bits y0 .. y0+len-1 of the 80-bit column mask
       const int wq = y0 >> 5, sh = y0 & 31;
       const uint32_t lo = s_col[x][wq], hi = wq < 2 ? s_col[x][wq + 1] : 0u;
       uint32_t m = __funnelshift_r(lo, hi, sh) & ((1u << run.len) - 1u);
+      const int wx = x >> 5, bx = x & 31;
       while (m) {
         const int i = __ffs(m) - 1;
         m &= m - 1;
-        const int y = y0 + i, wx = x >> 5, bx = x & 31;
+        const int y = y0 + i;
         const int sx = int((s_xp[y][wx] >> bx) & 1u) - int((s_xn[y][wx] >> bx) & 1u);
         const int sy = int((s_yp[y][wx] >> bx) & 1u) - int((s_yn[y][wx] >> bx) & 1u);
         const int c = (sy + 1) * 3 + (sx + 1);
-        const float wgt = c_hog.w[cell][run.first + i];
-        const float a0 = __fmul_rn(c_hog.g0[c], wgt), a1 = __fmul_rn(c_hog.g1[c], wgt);
-        const int b0 = c_hog.h0[c], b1 = c_hog.h1[c];
-#pragma unroll
-        for (int b = 0; b < 9; b++) {
-          if (b == b0) h[b] = __fadd_rn(h[b], a0);
-          if (b == b1) h[b] = __fadd_rn(h[b], a1);
-        }
+        const float wgt = s_w[cell][run.first + i];
+        const float a0 = __fmul_rn(s_g0[c], wgt), a1 = __fmul_rn(s_g1[c], wgt);
+        float* h0 = &s_acc[s_h0[c]][tid];
+        *h0 = __fadd_rn(*h0, a0);
+        float* h1 = &s_acc[s_h1[c]][tid];  // (h1 != h0: the two bins of a gradient are adjacent, never equal)
+        *h1 = __fadd_rn(*h1, a1);
       }
     }
 #pragma unroll
-    for (int b = 0; b < 9; b++) s_hist[ub * 36 + cell * 9 + b] = h[b];
+    for (int b = 0; b < 9; b++) s_hist[ub * 36 + cell * 9 + b] = s_acc[b][tid];
   }
   __syncthreads();
   // 5. L2-Hys normalisation per block (HOGCache::normalizeBlockHistogram).  OpenCV keeps 4 interleaved
@@ -335,19 +348,11 @@ k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slo
       for (int w2 = 0; w2 < kThreads / 32; w2++) t += s_part[w2];
       s_K[0] = kernel_value(t);
     }
-  } else {
-    for (int j = warp; j < svm.sv_total; j += kThreads / 32) {
-      const float* sv = svm.sv + size_t(j) * AG_HOG_DIM;
-      double acc = 0.0;
-      for (int k4 = lane; k4 < AG_HOG_DIM / 4; k4 += 32) acc += group_term(sv, k4);
-      acc = warp_sum(acc);
-      if (lane == 0 && j < 1280) s_K[j] = kernel_value(acc);
-    }
   }
   __syncthreads();
   // decision value: sum = -rho + sum_k alpha_k * K[index_k]   (CvSVM::predict)
-  double part = 0.0;
-  for (int kk = tid; kk < svm.sv_count; kk += kThreads) part += svm.alpha[kk] * double(s_K[svm.index[kk]]);
+  double part = 0.0;  // (one support vector here: models with more go through k_svm_gemm / k_svm_decide)
+  for (int kk = tid; kk < svm.sv_count && kk < 1; kk += kThreads) part += svm.alpha[kk] * double(s_K[0]);
   part = warp_sum(part);
   __syncthreads();
   if (lane == 0) s_part[warp] = part;

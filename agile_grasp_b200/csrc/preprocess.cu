@@ -318,6 +318,9 @@ k_emit_bitmap(uint32_t* bitmap, unsigned long long* tile_state, double cell, Pre
       for (int c = 0; c < 2; c++) ri->first[c] = ri->count[c] = 0;
     }
   }
+  // tiles are taken by ticket, so a tile only exists once a RUNNING CTA owns it: every tile a look-back waits for is
+  // being worked on, whatever else shares the GPU (other lanes of a batch, the side stream) — a static
+  // assignment would need all CTAs of the launch to be co-resident
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) s_tile = atomicAdd(&st->tile_ticket, 1u);
@@ -406,18 +409,28 @@ k_emit_bitmap(uint32_t* bitmap, unsigned long long* tile_state, double cell, Pre
     }
     __syncthreads();
     int run = int(s_base) + before + incl - cnt;  // rank of this thread's first set bit
+    // lattice position of this thread's first word, then stepped word by word (no divisions in the loop)
+    int c = 0;
+    unsigned column = 0, kx = 0, ky = 0;
+    int zw = 0;
+    bool have = false;
 #pragma unroll 1
     for (int k = 0; k < 8; k++) {
       const unsigned long long wi = wbase + k;
       if (wi >= words) break;
-      const int c = (wi >= w0c[1] && nx[1] > 0 && ny[1] > 0 && nzw[1] > 0) ? 1 : 0;
-      const unsigned long long rel = wi - w0c[c];
-      const unsigned long long column = rel / (unsigned long long)(nzw[c]);
-      const int zw = int(rel - column * (unsigned long long)(nzw[c]));
-      const int kx = int(column / (unsigned long long)(ny[c])), ky = int(column - (unsigned long long)(kx) * ny[c]);
+      const int c_now = (wi >= w0c[1] && nx[1] > 0 && ny[1] > 0 && nzw[1] > 0) ? 1 : 0;
+      if (!have || c_now != c) {
+        c = c_now;
+        const unsigned rel0 = unsigned(wi - w0c[c]);  // (the bitmap has < 2^32 words)
+        column = rel0 / unsigned(nzw[c]);
+        zw = int(rel0 - column * unsigned(nzw[c]));
+        kx = column / unsigned(ny[c]);
+        ky = column - kx * unsigned(ny[c]);
+        have = true;
+      }
       if (zw == 0) {  // first word of a lattice column: the scan value is the column's first voxel
         col_ptr[col0[c] + int(column)] = run;
-        if (ky == 0) row_ptr[c * row_stride + kx] = run;
+        if (ky == 0) row_ptr[c * row_stride + int(kx)] = run;
       }
       uint32_t bits = wd[k];
       if (bits) {
@@ -438,10 +451,19 @@ k_emit_bitmap(uint32_t* bitmap, unsigned long long* tile_state, double cell, Pre
           run++;
         }
       }
-      // last word of a camera: close its tables
-      if (rel + 1 == (unsigned long long)(nx[c]) * ny[c] * nzw[c]) {
-        col_ptr[col0[c] + nx[c] * ny[c]] = run;
-        row_ptr[c * row_stride + nx[c]] = run;
+      // step to the next word of the lattice; the last word of a camera closes its tables
+      if (++zw == nzw[c]) {
+        zw = 0;
+        column++;
+        if (++ky == unsigned(ny[c])) {
+          ky = 0;
+          kx++;
+          if (kx == unsigned(nx[c])) {
+            col_ptr[col0[c] + nx[c] * ny[c]] = run;
+            row_ptr[c * row_stride + nx[c]] = run;
+            have = false;
+          }
+        }
       }
     }
   }

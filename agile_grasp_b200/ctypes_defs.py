@@ -30,7 +30,7 @@ class AgParams(C.Structure):
         ("deterministic_normals", C.c_int32),
         ("filters_boundaries", C.c_int32),
         ("fix_cam_source", C.c_int32),
-        ("reserved", C.c_int32),
+        ("shard_interleave", C.c_int32),
         ("seed", C.c_uint64),
         ("shard_index", C.c_int32),
         ("shard_count", C.c_int32),

@@ -14,6 +14,26 @@ import torch.distributed as dist
 from .ctypes_defs import GRASP_DTYPE
 
 
+def shard_positions(n_items, rank, world, interleave=False):
+    """positions (in the full sample list) of rank's share: a contiguous range (ag_params.shard_interleave = 0) or
+    every world-th sample starting at rank (= 1) — the same partition api.cu applies"""
+    if interleave:
+        return np.arange(rank, n_items, world)
+    lo, hi = shard_range(n_items, rank, world)
+    return np.arange(lo, hi)
+
+
+def merge_by_sample(parts):
+    """host statement of the gather's merge: lists whose sample_slot is the position in the full sample list ->
+    one list ordered by (sample_slot, orientation) = the reference's stable concat (hand_search.cpp:194-200)"""
+    parts = [p for p in parts if len(p)]
+    if not parts:
+        return np.zeros(0, GRASP_DTYPE)
+    cat = np.concatenate(parts)
+    order = np.lexsort((cat["orientation"], cat["sample_slot"]))
+    return cat[order]
+
+
 def shard_range(n_items, rank, world):
     """contiguous [lo, hi) of rank's share; sizes differ by at most one, order preserved"""
     lo = (n_items * rank) // world
@@ -77,8 +97,9 @@ GATHER_SLOT_HEADER = 32
 def setup_peer_gather(ctx, num_samples, group=None):
     """Fused export + all-gather over NVLink peer memory (include/ag_b200.h, ag_gather_*): every rank creates
     its gather buffer, the CUDA IPC handles are exchanged once through torch.distributed, every rank maps
-    every buffer.  After this, ctx.localize*() stores the rank's grasp list into all ranks' buffers and
-    ctx.gather_wait() returns once all lists have arrived - no collective call per step."""
+    every buffer.  After this, every ctx.localize*() is a collective step: it stores the rank's grasp list into
+    all ranks' buffers, waits (on the device) for the other ranks' lists and merges them;
+    ctx.gather_result() returns the merged list - no collective call per step."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     handle = ctx.gather_create(num_samples, world, rank)
     handles = [None] * world

@@ -22,6 +22,9 @@ the headline instead).
   roofline : the Taubin stage (radius search + moment accumulation): algorithmic bytes (16 B per neighbour +
           292 B out per sample) over the CUDA-event duration of its kernel(s), against MEASURED_PEAKS.json.
   roofline_step : the same for the kernel with the largest share of the step (k_hand_sweep).
+  strong_scaling : ONE cloud per step, its samples sharded over the N ranks (ag_params.shard_index / shard_count,
+          interleaved shares), every rank ending up with the whole merged grasp list (peer stores + merge inside
+          ag_localize): BASELINE configs 5 (2 M points, 20,000 samples) and 4 (VGA clouds, 2000 samples), ms/cloud.
   cpu_baseline : the CPU oracle (a port of the reference path, OpenMP over samples like the reference)
           on this box's host cores, both normal modes.
 --impl reference runs only that CPU arm.
@@ -340,7 +343,11 @@ def main():
             assert np.array_equal(lists[rank][nm], g[nm]), "own slot differs from the returned list: " + nm
         for r in range(world):  # every rank's list is well formed (sample-major order)
             assert np.all(np.diff(lists[r]["sample_index"]) >= 0)
-        gathered = {"per_rank": n_per, "mode": "peer stores over NVLink (ag_gather_*), no collective per step"}
+        n_per2, merged, _ = ctx.gather_result()
+        assert n_per2 == n_per and len(merged) == sum(n_per)
+        assert np.all(np.diff(merged["sample_slot"].astype(np.int64) * 8 + merged["orientation"]) >= 0)
+        gathered = {"per_rank": n_per, "merged": int(len(merged)),
+                    "mode": "peer stores over NVLink + on-device merge inside ag_localize (ag_gather_*), no collective per step"}
     elif world > 1:  # decode the last all-gather on the host (outside the timed region)
         host = recv.cpu().numpy().reshape(world, -1)
         parts = [shard.parse_export(host[r]) for r in range(world)]
@@ -423,6 +430,69 @@ def main():
             "wall_ms_per_step_incl_flush": float(1e3 * D["wall"] / args.steps),
             "clocks": clocks,
         }
+
+    # ---- strong scaling: the samples of ONE cloud sharded over the ranks (north_star: "samples shard naturally
+    # across the 8 GPUs"), every rank ending with the whole merged list; runs at every N (N = 1: the unsharded call)
+    if not args.no_extras:
+        strong = {}
+        for cfg, n_clouds, k_steps in ((5, 1, 5), (4, 8, 2)):
+            try:
+                clouds = []
+                for k in range(n_clouds if cfg == 4 else 1):
+                    pts, size_left, Ps, S = make_cloud(5 if cfg == 5 else 2, scene_offset=k % 4)
+                    Ps.deterministic_normals = det
+                    Ps.shard_index, Ps.shard_count, Ps.shard_interleave = rank, world, 1
+                    pin = torch.from_numpy(pts).pin_memory()
+                    clouds.append(dict(host=pin, dev=pin.to(dev), size_left=size_left, P=Ps, n=pts.shape[0],
+                                       stride=pts.strides[0]))
+                c2 = api.Context(local_rank, clouds[0]["P"])
+                c2.set_svm(svm)
+                if world > 1:
+                    shard.setup_peer_gather(c2, clouds[0]["P"].num_samples)
+                for _ in range(3):
+                    for c in clouds:
+                        c2.localize_device(c["dev"].data_ptr(), c["stride"], c["n"], c["size_left"])
+                        c2.localize(c["host"].numpy(), c["size_left"])
+                dms, ems, hyp = [], [], []
+                barrier()
+                for k in range(k_steps):
+                    for c in clouds:
+                        flush.fill_(k & 0xFF)
+                        barrier()
+                        g = c2.localize_device(c["dev"].data_ptr(), c["stride"], c["n"], c["size_left"])
+                        dms.append(c2.timings()["total_ms"])
+                        hyp.append(sum(c2.gather_result(copy=False)[0]) if world > 1 else len(g))
+                for k in range(k_steps):
+                    for c in clouds:
+                        flush.fill_(k & 0xFF)
+                        barrier()
+                        t0 = time.perf_counter()
+                        g = c2.localize(c["host"].numpy(), c["size_left"])
+                        ems.append((time.perf_counter() - t0) * 1e3)
+                t2 = torch.tensor([float(np.mean(dms)), float(np.mean(ems))], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+                t2 = t2.cpu().numpy()
+                tm = c2.timings()
+                strong[f"config{cfg}"] = {
+                    "workload": ("one fused 7-view cloud (%d pts), 20000 samples" % clouds[0]["n"]) if cfg == 5 else
+                                ("%d VGA clouds, 2000 samples each, every cloud sharded over the ranks" % n_clouds),
+                    "ms_per_cloud": float(t2[0]), "e2e_ms_per_cloud": float(t2[1]),
+                    "hypotheses_per_cloud": float(np.mean(hyp)), "hyp_per_s": float(np.mean(hyp) / (t2[0] * 1e-3)),
+                    "rank0_stages_ms": {nm: round(tm[nm], 4) for nm in ("preprocess_ms", "quadric_ms", "sweep_ms",
+                                                                         "hog_svm_ms", "total_ms")},
+                    "timer": "ms_per_cloud: CUDA events around the whole call incl. the exchange + merge (device-resident "
+                             "cloud), e2e: wall clock from the pinned host cloud; max over ranks"}
+                c2.set_svm(None)
+                c2.close()
+                del c2, clouds
+            except Exception as e:
+                strong[f"config{cfg}"] = {"error": str(e)}
+        if rank == 0:
+            strong["sharding"] = ("samples interleaved over %d ranks (ag_params.shard_interleave), cloud voxelised on every "
+                                  "rank, lists exchanged by peer stores and merged on the device" % world) if world > 1 \
+                else "single GPU (the unsharded call)"
+            line["strong_scaling"] = strong
 
     extras = world == 1 and not args.no_extras
     if extras:

@@ -79,11 +79,14 @@ typedef struct ag_params {
   int32_t deterministic_normals; /* 1 = Quadric(is_deterministic=true) (parity mode) */
   int32_t filters_boundaries;  /* Localization ctor arg, localization.h:84 */
   int32_t fix_cam_source;      /* 0 reproduces the reference's pre-NaN camera labelling quirk */
-  int32_t reserved;
+  int32_t shard_interleave;    /* sample sharding: 0 = contiguous ranges, 1 = shard i takes samples i, i + n, i + 2n ... */
   uint64_t seed;               /* sample-index RNG seed when indices are not supplied */
-  /* Sample sharding of ONE cloud over several GPUs: this context handles the contiguous share
-   * shard_index of shard_count of the samples (drawn or explicit); the cloud itself is voxelised on every
-   * rank.  Concatenating the shards' lists in shard order gives the unsharded list.  0 / 1 = no sharding. */
+  /* Sample sharding of ONE cloud over several GPUs: this context handles share shard_index of
+   * shard_count of the samples (drawn or explicit) — a contiguous range, or with shard_interleave every
+   * shard_count-th sample (hypotheses cluster on objects, so interleaving balances the shards); the cloud
+   * itself is voxelised on every rank.  ag_grasp.sample_slot is the position in the FULL sample list, so the
+   * shards' lists merge into the unsharded list by (sample_slot, orientation) — which is what the peer gather
+   * (ag_gather_*) does; for contiguous ranges that is plain concatenation in shard order.  0 / 1 = no sharding. */
   int32_t shard_index;
   int32_t shard_count;
 } ag_params;
@@ -201,15 +204,19 @@ int ag_set_svm(ag_ctx* ctx, const ag_svm* svm);
 int ag_set_export_buffer(ag_ctx* ctx, void* d_buffer, size_t bytes);
 
 /* Multi-GPU grasp-list exchange WITHOUT a collective call (one process per GPU, all GPUs of one NVLink/
- * NVSwitch box).  Every rank creates a gather buffer (two epochs x world slots), publishes its CUDA IPC
- * handle, and connects to the handles of all ranks (rank order, its own included).  From then on the export
- * kernel of every ag_localize stores this rank's [header][records] directly into slot `rank` of EVERY rank's
- * buffer over NVLink and raises an epoch flag; ag_gather_wait() waits (on the device) until all `world`
- * slots of this rank's buffer carry the current epoch and returns the per-rank hypothesis counts plus the
- * device address of the slots: slot r = d_slots + r * slot_bytes, records start AG_GATHER_SLOT_HEADER bytes
- * into a slot, in the reference's sample-major order (hand_search.cpp:194-200).  All ranks must call
- * ag_localize the same number of times; a slot's contents stay valid until the second following
- * ag_localize.  This replaces the NCCL all-gather of ag_set_export_buffer (kept for other backends). */
+ * NVSwitch box).  Every rank creates a gather buffer (consumer acknowledgements + two epochs x world slots),
+ * publishes its CUDA IPC handle, and connects to the handles of all ranks (rank order, its own included).  From
+ * then on every ag_localize is a collective step: its export kernel stores this rank's [header][records]
+ * directly into slot `rank` of EVERY rank's buffer over NVLink and raises an epoch flag; a merge kernel in the
+ * same stream waits (on the device) for all `world` lists of the epoch, merges them by (sample_slot,
+ * orientation) into ONE list in the reference's sample-major order (hand_search.cpp:194-200) in device and
+ * mapped host memory, and acknowledges the epoch to every producer — a producer never overwrites a slot whose
+ * epoch a consumer has not acknowledged (back-pressure instead of "hope the consumer was fast enough").  The one
+ * host wait of ag_localize covers the whole exchange.  ag_gather_result returns the merged list of the last
+ * call (valid until the next ag_localize); ag_gather_wait (kept for callers that want the per-rank slots)
+ * returns the per-rank counts and slot addresses: slot r = d_slots + r * slot_bytes, records start
+ * AG_GATHER_SLOT_HEADER bytes into a slot.  All ranks must call ag_localize the same number of times.  This
+ * replaces the NCCL all-gather of ag_set_export_buffer (kept for other backends). */
 #define AG_MAX_GATHER_RANKS 8
 #define AG_IPC_HANDLE_BYTES 64
 #define AG_GATHER_SLOT_HEADER 32
@@ -218,6 +225,8 @@ int ag_gather_create(ag_ctx* ctx, int num_samples, int world, int rank, unsigned
 int ag_gather_connect(ag_ctx* ctx, const unsigned char* handles /* world x 64 B, rank order */);
 int ag_gather_wait(ag_ctx* ctx, int32_t* n_hyp_per_rank /* world, may be NULL */, const void** d_slots,
                    size_t* slot_bytes);
+int ag_gather_result(ag_ctx* ctx, int32_t* n_hyp_per_rank /* world, may be NULL */, int* n_total,
+                     const ag_grasp** d_merged, const ag_grasp** h_merged);
 int ag_gather_destroy(ag_ctx* ctx);
 
 /* pcl::io::loadPCDFile<pcl::PointXYZRGBA> (localization.cpp:184,198; file overloads :169-214): reads a PCD

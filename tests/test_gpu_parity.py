@@ -583,32 +583,103 @@ def test_rand_mode_normals_match_oracle(ctx, oracle, small_scene):
 
 
 def test_sample_sharding_concatenates_to_the_unsharded_list(ctx, small_scene, linear_svm_path):
-    """one cloud, the samples split into contiguous shares (ag_params.shard_index / shard_count, the
-    cloud voxelised by every shard): the shards' lists concatenated in shard order are the unsharded list
-    (drawn samples and explicit indices; sample_slot / image_id are shard-local bookkeeping)."""
+    """one cloud, the samples split into shares (ag_params.shard_index / shard_count, the cloud voxelised
+    by every shard) — contiguous ranges or, with shard_interleave, every n-th sample: the shards' lists merged by
+    (sample_slot, orientation) are the unsharded list, bit for bit (drawn samples and explicit indices; only
+    image_id is shard-local bookkeeping); for contiguous ranges the merge is plain concatenation."""
     import copy
+    from agile_grasp_b200 import shard
     s = small_scene
     svm = api.Svm(linear_svm_path)
     ctx.set_svm(svm)
-    fields = [f for f in GRASP_FIELDS if f not in ("sample_slot", "image_id")]
+    fields = [f for f in GRASP_FIELDS if f != "image_id"]
     try:
         for idx in (None, s["idx"]):
             ctx.set_params(s["P"])
             full = ctx.localize(s["pts"], s["size_left"], idx)
+            assert (np.diff(full["sample_slot"]) >= 0).all()
             for world in (2, 3):
-                parts = []
-                for r in range(world):
-                    P = copy.copy(s["P"])
-                    P.shard_index, P.shard_count = r, world
-                    ctx.set_params(P)
-                    parts.append(ctx.localize(s["pts"], s["size_left"], idx))
-                cat = np.concatenate(parts)
-                assert len(cat) == len(full) and all(len(p) > 0 for p in parts)
-                for f in fields:
-                    assert np.ascontiguousarray(cat[f]).tobytes() == np.ascontiguousarray(full[f]).tobytes(), (world, f)
+                for interleave in (0, 1):
+                    parts = []
+                    for r in range(world):
+                        P = copy.copy(s["P"])
+                        P.shard_index, P.shard_count, P.shard_interleave = r, world, interleave
+                        ctx.set_params(P)
+                        parts.append(ctx.localize(s["pts"], s["size_left"], idx))
+                        n_s = len(s["idx"]) if idx is not None else ctx.timings()["n_samples"]
+                        pos = shard.shard_positions(len(s["idx"]), r, world, bool(interleave))
+                        assert set(np.unique(parts[-1]["sample_slot"])) <= set(pos.tolist())
+                    cat = shard.merge_by_sample(parts)
+                    if not interleave:
+                        assert _rec_bytes(cat) == _rec_bytes(np.concatenate(parts))
+                    assert len(cat) == len(full) and all(len(p) > 0 for p in parts)
+                    for f in fields:
+                        assert np.ascontiguousarray(cat[f]).tobytes() == np.ascontiguousarray(full[f]).tobytes(), (world, interleave, f)
     finally:
         ctx.set_params(s["P"])
         ctx.set_svm(None)
+
+
+def _gather_worker(rank, world, port, out_dir, interleave):
+    """one rank of the peer-gather test: both ranks share cuda:0 (the exchange goes through CUDA IPC mappings of
+    each other's gather buffers, exactly as between two GPUs of a box)"""
+    import copy
+    import torch.distributed as dist
+    from agile_grasp_b200 import shard
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pts, size_left, P, S = scenes.config_cloud(2, small=(320, 240, 150))
+    svm = api.Svm(os.path.join(GOLD, "svm_032015_linear_20_20_same"))
+    c = api.Context(0, P)
+    c.set_svm(svm)
+    full = c.localize(pts, size_left) if rank == 0 else None
+    Ps = copy.copy(P)
+    Ps.shard_index, Ps.shard_count, Ps.shard_interleave = rank, world, interleave
+    c.set_params(Ps)
+    shard.setup_peer_gather(c, P.num_samples)
+    ok = True
+    for it in range(5):  # epochs 1..5: the slot parity is reused and the acknowledgements are exercised
+        local = c.localize(pts, size_left)
+        n_per, merged, dptr = c.gather_result()
+        ok = ok and n_per[rank] == len(local) and sum(n_per) == len(merged)
+        if rank == 0:
+            h = merged.copy()
+            f = full.copy()
+            for a in (h, f):
+                a["image_id"] = 0
+                a["reserved"] = 0
+            ok = ok and h.tobytes() == f.tobytes()
+    # a call without samples still takes part in the exchange
+    P0 = copy.copy(Ps)
+    P0.num_samples = 0 if rank == 1 else P.num_samples
+    c.set_params(P0)
+    local = c.localize(pts, size_left)
+    n_per, merged, _ = c.gather_result()
+    ok = ok and n_per[1] == 0 and n_per[0] == len(merged) and (rank == 1 or len(local) == n_per[0])
+    np.save(os.path.join(out_dir, f"ok_{rank}_{interleave}.npy"), np.array([ok, len(merged)]))
+    dist.barrier()
+    c.set_svm(None)
+    c.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("interleave", [0, 1])
+def test_peer_gather_two_ranks_merge_to_the_unsharded_list(tmp_path, interleave):
+    """ag_gather_*: two processes (one per rank, both on cuda:0) shard the samples of one cloud; the export kernel of
+    each stores its list into the other's buffer, the merge kernel gives every rank the whole list in the
+    reference's order — equal to the list of one unsharded call, for contiguous and interleaved shares, over more
+    calls than the two slot parities (acknowledgement / back-pressure path) and with an empty share."""
+    import socket
+    import torch.multiprocessing as mp
+    sck = socket.socket()
+    sck.bind(("127.0.0.1", 0))
+    port = sck.getsockname()[1]
+    sck.close()
+    mp.spawn(_gather_worker, args=(2, port, str(tmp_path), interleave), nprocs=2, join=True)
+    for r in range(2):
+        ok, n = np.load(tmp_path / f"ok_{r}_{interleave}.npy")
+        assert ok and n > 0
 
 
 def test_localize_edge_cases(ctx, oracle, small_scene, linear_svm_path):

@@ -69,3 +69,28 @@ def test_shard_range_matches_the_library_partition():
                     assert lo == edges[r - 1][1]
             sizes = [hi - lo for lo, hi in edges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_interleaved_shares_merge_back():
+    """shard_positions / merge_by_sample (host statement of the library's partition and of the gather's merge):
+    contiguous and interleaved shares tile the sample list; lists keyed by the position in the full list merge back
+    into sample-major order whatever the partition was."""
+    from agile_grasp_b200.shard import merge_by_sample, shard_positions
+    rng = np.random.default_rng(3)
+    for S in (1, 7, 2000):
+        allg = np.zeros(0, GRASP_DTYPE)
+        per_sample = rng.integers(0, 4, S)
+        recs = []
+        for k in range(S):
+            for o in sorted(rng.choice(8, per_sample[k], replace=False)):
+                g = np.zeros(1, GRASP_DTYPE)
+                g["sample_slot"], g["orientation"], g["width"] = k, o, k + 0.1 * o
+                recs.append(g)
+        allg = np.concatenate(recs) if recs else allg
+        for world in (1, 2, 3, 8):
+            for il in (False, True):
+                pos = [shard_positions(S, r, world, il) for r in range(world)]
+                assert sorted(np.concatenate(pos).tolist()) == list(range(S))
+                parts = [allg[np.isin(allg["sample_slot"], p)] for p in pos]
+                m = merge_by_sample(parts)
+                assert m.tobytes() == allg.tobytes()
