@@ -19,7 +19,7 @@ _LIB = None
 EXPORTS = [
     "ag_last_error", "ag_default_params", "ag_create", "ag_destroy", "ag_set_params", "ag_get_params",
     "ag_get_timings", "ag_free", "ag_svm_load", "ag_svm_free", "ag_svm_info", "ag_localize", "ag_localize_device",
-    "ag_classify", "ag_set_svm", "ag_set_export_buffer", "ag_get_points", "ag_get_images", "ag_get_normals", "ag_preprocess", "ag_set_cloud", "ag_radius_search",
+    "ag_classify", "ag_set_svm", "ag_set_export_buffer", "ag_get_points", "ag_get_images", "ag_get_normals", "ag_train_features", "ag_remove_plane", "ag_preprocess", "ag_set_cloud", "ag_radius_search",
     "ag_fit_quadrics", "ag_hand_sweep", "ag_sweep_debug", "ag_hog_svm",
     "ag_find_handles", "ag_load_pcd", "ag_localize_batch", "ag_gather_slot_bytes", "ag_gather_create", "ag_gather_connect", "ag_gather_wait", "ag_gather_result", "ag_gather_destroy",
 ]
@@ -55,9 +55,11 @@ def lib():
     L.ag_get_points.argtypes = [vp, C.c_int, C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.POINTER(C.c_int32)), ip]
     L.ag_get_images.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint32)), ip]
     L.ag_get_normals.argtypes = [vp, dp, C.c_int]
+    L.ag_train_features.argtypes = [vp, C.POINTER(AgGrasp), C.c_int, C.POINTER(C.c_float)]
     L.ag_preprocess.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_float)),
                                 C.POINTER(C.POINTER(C.c_int32)), ip]
     L.ag_set_cloud.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int]
+    L.ag_remove_plane.argtypes = [vp, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.POINTER(C.c_int32)), ip]
     L.ag_radius_search.argtypes = [vp, C.POINTER(C.c_float), C.c_double, C.POINTER(C.POINTER(C.c_int32)), ip]
     L.ag_fit_quadrics.argtypes = [vp, ip, C.c_int, C.c_double, C.POINTER(AgFrame)]
     L.ag_hand_sweep.argtypes = [vp, ip, C.c_int, C.POINTER(AgFrame), dp, C.c_uint, C.POINTER(C.POINTER(AgGrasp)), ip]
@@ -89,10 +91,10 @@ def _check(rc):
 
 
 def _grasps_from(ptr, n):
-    if n == 0:
-        out = np.zeros(0, GRASP_DTYPE)
-    else:
-        out = np.frombuffer(C.string_at(ptr, n * C.sizeof(AgGrasp)), dtype=GRASP_DTYPE).copy()
+    # one flat copy out of the malloc'ed list (a field-wise copy of the structured dtype costs ten times as much)
+    out = np.empty(n, GRASP_DTYPE)
+    if n:
+        C.memmove(out.ctypes.data, ptr, n * C.sizeof(AgGrasp))
     lib().ag_free(ptr)
     return out
 
@@ -283,6 +285,15 @@ class Context:
         lib().ag_free(bits)
         return out
 
+    def train_features(self, grasps):
+        """HOG descriptors of the three training instances of each hypothesis (own image, camera 1 only, camera 2
+        only): (n, 3, 3528) float32"""
+        g = np.ascontiguousarray(grasps)
+        out = np.zeros((g.shape[0], 3, AG_HOG_DIM), np.float32)
+        _check(lib().ag_train_features(self.h, g.ctypes.data_as(C.POINTER(AgGrasp)), g.shape[0],
+                                       out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
     def normals(self, n):
         """cloud_normals_ of the last localize / sweep call: (n, 3) float64, zero where no normal was computed"""
         out = np.zeros((int(n), 3), np.float64)
@@ -297,6 +308,21 @@ class Context:
         n = C.c_int()
         _check(lib().ag_preprocess(self.h, pts.ctypes.data_as(C.c_void_p), pts.strides[0], pts.shape[0],
                                    int(size_left), C.byref(xyz), C.byref(cam), C.byref(n)))
+        if n.value == 0:
+            X, Cm = np.zeros((0, 3), np.float32), np.zeros(0, np.int32)
+        else:
+            X = np.ctypeslib.as_array(xyz, shape=(n.value, 3)).copy()
+            Cm = np.ctypeslib.as_array(cam, shape=(n.value,)).copy()
+        lib().ag_free(xyz)
+        lib().ag_free(cam)
+        return X, Cm
+
+    def remove_plane(self):
+        """uses_clustering as a stage: the current voxelised cloud without its dominant plane -> (xyz, cam)"""
+        xyz = C.POINTER(C.c_float)()
+        cam = C.POINTER(C.c_int32)()
+        n = C.c_int()
+        _check(lib().ag_remove_plane(self.h, C.byref(xyz), C.byref(cam), C.byref(n)))
         if n.value == 0:
             X, Cm = np.zeros((0, 3), np.float32), np.zeros(0, np.int32)
         else:

@@ -165,9 +165,11 @@ struct Ctx {
   SvmModel* attached_svm = nullptr;  // ag_set_svm: score inside ag_localize
   bool scores_valid = false;         // last_grasps carry scores of attached_svm
   bool keep_points = false;
-  // host copies for ag_get_points
-  std::vector<ag_grasp> last_grasps;
+  // results of the fused scoring of the last ag_localize (what ag_classify returns for the attached model)
+  std::vector<float> last_scores;
+  std::vector<uint8_t> last_labels;
   ag_timings timings;
+  bool timings_pending = false, timings_h2d = false;  // stage times are read from the events on demand
   cudaEvent_t ev[10];
   cudaEvent_t ev_k[4];   // around k_ball_search / k_taubin_moments / k_taubin_axes
   int launches = 0;      // own-kernel launch counter (reset per localize call)
@@ -203,6 +205,12 @@ int* hand_sweep_overflow_ptr(Ctx* c);         // device address of the overflow 
 int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d_image_ids, int n, const int* n_dev,
                    float* d_descriptors, float* d_scores, ag_grasp* d_grasps_out = nullptr);
 int radius_search_device(Ctx* c, const float q[3], double radius, std::vector<int>& out);
+// training-data path
+int hog_descriptors_device(Ctx* c, const uint32_t* d_images, const int* d_image_slots, int n, float* d_descriptors);
+int camera_images_device(Ctx* c, int n_samples, const int* d_slots, int n, uint32_t* d_images);
+// uses_clustering: removes the dominant RANSAC plane from the voxelised cloud (waits for the stream; the cloud is
+// re-indexed).  Returns AG_RETRY_KEYSORT if the voxelisation asked for the key-sort path.
+int remove_plane_device(Ctx* c);
 
 void compute_hand_const(const ag_params& p, HandConst& h);
 int svm_to_device(SvmModel* svm, int device);

@@ -392,7 +392,8 @@ static SvmModel* load_svm(const char* path) {
   std::stringstream ss;
   ss << f.rdbuf();
   const std::string text = ss.str();
-  if (text.find("opencv-ml-svm") == std::string::npos) {
+  // OpenCV 2.4 (the reference's files): "my_svm: !!opencv-ml-svm"; OpenCV 3 / 4 write "opencv_ml_svm:" with the same keys
+  if (text.find("opencv-ml-svm") == std::string::npos && text.find("opencv_ml_svm") == std::string::npos) {
     set_error("not an !!opencv-ml-svm file");
     return nullptr;
   }
@@ -558,6 +559,10 @@ static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, in
     if (rc) return rc;
     rc = preprocess_device(c, d_points, stride, n_in, size_left);
     if (rc) return rc;
+    if (flags & AG_FLAG_USE_CLUSTERING) {  // localization.cpp:51-98 (training-time path: waits for the stream)
+      rc = remove_plane_device(c);
+      if (rc) return rc;
+    }
     record_event(c, c->ev[2]);
     record_event(c, c->ev[3]);
     ri = c->row_index.as<RowIndex>();
@@ -615,7 +620,7 @@ static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, in
   key.state_gen = c->state_gen;
   key.svm = c->attached_svm;
   static const bool graphs_off = getenv("AG_NO_GRAPH") != nullptr;
-  const bool can_graph = !graphs_off && S > 0 && !(flags & AG_FLAG_CALC_ANTIPODAL);
+  const bool can_graph = !graphs_off && S > 0 && !(flags & (AG_FLAG_CALC_ANTIPODAL | AG_FLAG_USE_CLUSTERING));
   // small cache of captured pipelines (callers typically alternate between a few input buffers)
   GraphSlot* slot = nullptr;
   for (GraphSlot& g : c->gslots)
@@ -783,25 +788,22 @@ static int localize_end(Ctx* c, ag_grasp** out, int* n_out) {
   }
   ag_grasp* res = static_cast<ag_grasp*>(std::malloc(std::max<size_t>(1, size_t(Hn)) * sizeof(ag_grasp)));
   if (Hn > 0) std::memcpy(res, reinterpret_cast<const ag_grasp*>(h + 1), size_t(Hn) * sizeof(ag_grasp));
-  c->timings.preprocess_ms = elapsed(c->ev[1], c->ev[2]);
-  c->timings.grid_ms = 0.f;  // the x-row index is built inside the voxelisation pass
-  c->timings.normals_all_ms = elapsed(c->ev[3], c->ev[4]);
-  c->timings.quadric_ms = elapsed(c->ev[4], c->ev[5]);
-  c->timings.sweep_ms = elapsed(c->ev[5], c->ev[8]);
-  c->timings.hog_svm_ms = elapsed(c->ev[8], c->ev[9]);
-  c->timings.d2h_ms = elapsed(c->ev[6], c->ev[7]);
-  c->timings.total_ms = elapsed(c->ev[0], c->ev[7]);
+  c->timings_pending = true;  // the event differences are read when ag_get_timings asks for them
   c->timings.n_hyp = Hn;
-  c->timings.search_ms = elapsed(c->ev_k[0], c->ev_k[1]);
-  c->timings.moments_ms = elapsed(c->ev_k[1], c->ev_k[2]);
-  c->timings.axes_ms = elapsed(c->ev_k[2], c->ev_k[3]);
   c->timings.kernel_launches = c->launches;
   c->timings.taubin_neighbor_points = int64_t(h->counters[0]);
   c->timings.taubin_candidates = int64_t(h->counters[1]);
   c->timings.hand_neighbor_points = int64_t(h->counters[2]);
   c->timings.hand_candidates = int64_t(h->counters[3]);
-  if (c->attached_svm) c->scores_valid = true;
-  c->last_grasps.assign(res, res + Hn);
+  if (c->attached_svm) {  // what ag_classify hands back for this model: decision value + label per hypothesis
+    c->scores_valid = true;
+    c->last_scores.resize(Hn);
+    c->last_labels.resize(Hn);
+    for (int i = 0; i < Hn; i++) {
+      c->last_scores[i] = res[i].score;
+      c->last_labels[i] = res[i].label;
+    }
+  }
   *out = res;
   *n_out = Hn;
   if (c->gather_pending) return gather_collect(c);
@@ -940,7 +942,23 @@ int ag_get_params(ag_ctx* h, ag_params* p) {
   return AG_OK;
 }
 int ag_get_timings(ag_ctx* h, ag_timings* t) {
-  *t = h->c.timings;
+  Ctx& c = h->c;
+  if (c.timings_pending) {  // stage times of the last ag_localize, from the events recorded in its stream
+    c.timings_pending = false;
+    c.timings.preprocess_ms = elapsed(c.ev[1], c.ev[2]);
+    c.timings.grid_ms = 0.f;  // the x-row index is built inside the voxelisation pass
+    c.timings.normals_all_ms = elapsed(c.ev[3], c.ev[4]);
+    c.timings.quadric_ms = elapsed(c.ev[4], c.ev[5]);
+    c.timings.sweep_ms = elapsed(c.ev[5], c.ev[8]);
+    c.timings.hog_svm_ms = elapsed(c.ev[8], c.ev[9]);
+    c.timings.d2h_ms = elapsed(c.ev[6], c.ev[7]);
+    c.timings.total_ms = elapsed(c.ev[0], c.ev[7]);
+    c.timings.search_ms = elapsed(c.ev_k[0], c.ev_k[1]);
+    c.timings.moments_ms = elapsed(c.ev_k[1], c.ev_k[2]);
+    c.timings.axes_ms = elapsed(c.ev_k[2], c.ev_k[3]);
+    if (c.timings_h2d) c.timings.h2d_ms = elapsed(c.ev[0], c.ev[1]);
+  }
+  *t = c.timings;
   return AG_OK;
 }
 void ag_free(void* p) { std::free(p); }
@@ -989,9 +1007,8 @@ int ag_localize(ag_ctx* h, const void* points, int stride, int n_in, int size_le
   if (c.raw.reserve(bytes)) return AG_ERR_CUDA;
   cudaEventRecord(c.ev[0], c.stream);
   AG_CUDA_CHECK(cudaMemcpyAsync(c.raw.p, points, bytes, cudaMemcpyHostToDevice, c.stream));
-  int rc = localize_run(&c, c.raw.p, stride, n_in, size_left, indices, n_indices, flags, out, n_out);
-  c.timings.h2d_ms = elapsed(c.ev[0], c.ev[1]);
-  return rc;
+  c.timings_h2d = true;
+  return localize_run(&c, c.raw.p, stride, n_in, size_left, indices, n_indices, flags, out, n_out);
 }
 
 int ag_localize_device(ag_ctx* h, const void* d_points, int stride, int n_in, int size_left, const int* indices,
@@ -1004,6 +1021,7 @@ int ag_localize_device(ag_ctx* h, const void* d_points, int stride, int n_in, in
   Ctx& c = h->c;
   cudaSetDevice(c.device);
   cudaEventRecord(c.ev[0], c.stream);
+  c.timings_h2d = false;
   return localize_run(&c, d_points, stride, n_in, size_left, indices, n_indices, flags, out, n_out);
 }
 
@@ -1030,10 +1048,10 @@ int ag_classify(ag_ctx* h, const ag_svm* svm, ag_grasp* grasps, int n, uint8_t* 
   if (c.scores_valid && c.attached_svm == svm->m) {
     // already scored inside ag_localize (ag_set_svm): hand the results back
     for (int i = 0; i < n; i++) {
-      const ag_grasp& r = c.last_grasps[grasps[i].image_id];
-      grasps[i].score = r.score;
-      grasps[i].label = r.label;
-      if (keep) keep[i] = r.label;
+      const int id = grasps[i].image_id;
+      grasps[i].score = c.last_scores[id];
+      grasps[i].label = c.last_labels[id];
+      if (keep) keep[i] = c.last_labels[id];
     }
     return AG_OK;
   }
@@ -1307,6 +1325,56 @@ int ag_get_points(ag_ctx* h, int image_id, double** pts3xm, int32_t** cam, int* 
   return AG_OK;
 }
 
+// Training features (Learning::train / convertData, learning.cpp:76-163,249-290): for every hypothesis the HOG
+// descriptor of its grasp image and of the images made from the points of camera 1 only and camera 2 only
+// (createInstance(h, cam_pos), createInstance(h, cam_pos, 0), createInstance(h, cam_pos, 1)).
+int ag_train_features(ag_ctx* h, const ag_grasp* grasps, int n, float* features) {
+  if (!h || (n > 0 && (!grasps || !features))) return AG_ERR_INVALID;
+  if (n <= 0) return AG_OK;
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  if (!c.images_valid) {
+    set_error("ag_train_features: no grasp images resident (call ag_localize / ag_hand_sweep first)");
+    return AG_ERR_INVALID;
+  }
+  for (int i = 0; i < n; i++)
+    if (grasps[i].image_id < 0 || grasps[i].image_id >= c.n_hyp || grasps[i].reserved != c.stamp) {
+      set_error("ag_train_features: hypothesis does not belong to the last ag_localize / ag_hand_sweep call on this context");
+      return AG_ERR_INVALID;
+    }
+  std::vector<int> raw_slots(c.n_hyp), slots(n);
+  AG_CUDA_CHECK(cudaMemcpyAsync(raw_slots.data(), c.hyp_slots.p, size_t(c.n_hyp) * 4, cudaMemcpyDeviceToHost, c.stream));
+  AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  for (int i = 0; i < n; i++) slots[i] = raw_slots[grasps[i].image_id];
+  DevBuf d_slots, d_img3, d_desc;
+  // images: [n own][n x 2 per camera] -> descriptor rows reordered to (own, camera 1, camera 2) per hypothesis
+  if (d_slots.reserve(size_t(n) * 4) || d_img3.reserve(size_t(n) * 3 * AG_IMAGE_WORDS * 4) ||
+      d_desc.reserve(size_t(n) * 3 * AG_HOG_DIM * 4))
+    return AG_ERR_CUDA;
+  AG_CUDA_CHECK(cudaMemcpyAsync(d_slots.p, slots.data(), size_t(n) * 4, cudaMemcpyHostToDevice, c.stream));
+  uint32_t* img_cam = d_img3.as<uint32_t>() + size_t(n) * AG_IMAGE_WORDS;
+  int rc = camera_images_device(&c, c.n_samples, d_slots.as<int>(), n, img_cam);
+  if (rc == AG_OK) rc = hog_descriptors_device(&c, c.images_raw.as<uint32_t>(), d_slots.as<int>(), n, d_desc.as<float>());
+  if (rc == AG_OK) rc = hog_descriptors_device(&c, img_cam, nullptr, 2 * n, d_desc.as<float>() + size_t(n) * AG_HOG_DIM);
+  if (rc == AG_OK) {
+    const size_t row = size_t(AG_HOG_DIM) * 4;
+    // row 3 i = own image, 3 i + 1 / 3 i + 2 = camera 1 / 2 only
+    cudaMemcpy2DAsync(features, 3 * row, d_desc.p, row, row, n, cudaMemcpyDeviceToHost, c.stream);
+    cudaMemcpy2DAsync(reinterpret_cast<char*>(features) + row, 3 * row, d_desc.as<char>() + size_t(n) * row, 2 * row, row, n,
+                      cudaMemcpyDeviceToHost, c.stream);
+    cudaMemcpy2DAsync(reinterpret_cast<char*>(features) + 2 * row, 3 * row, d_desc.as<char>() + size_t(n) * row + row, 2 * row,
+                      row, n, cudaMemcpyDeviceToHost, c.stream);
+    if (cudaStreamSynchronize(c.stream) != cudaSuccess) {
+      set_error("ag_train_features: copy failed");
+      rc = AG_ERR_CUDA;
+    }
+  }
+  d_slots.release();
+  d_img3.release();
+  d_desc.release();
+  return rc;
+}
+
 int ag_get_normals(ag_ctx* h, double* normals3n, int n) {
   if (!h || !normals3n || n < 0) return AG_ERR_INVALID;
   Ctx& c = h->c;
@@ -1389,6 +1457,42 @@ int ag_preprocess(ag_ctx* h, const void* points, int stride, int n_in, int size_
   *cam_out = cam;
   *n_out = n;
   return AG_OK;
+}
+
+static int copy_cloud_out(Ctx& c, float** xyz_out, int32_t** cam_out, int* n_out) {
+  const int n = c.n_vox;
+  std::vector<GPoint> v(n);
+  if (n > 0) AG_CUDA_CHECK(cudaMemcpyAsync(v.data(), c.vox.p, size_t(n) * 16, cudaMemcpyDeviceToHost, c.stream));
+  AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  float* xyz = static_cast<float*>(std::malloc(std::max<size_t>(1, size_t(n)) * 12));
+  int32_t* cam = static_cast<int32_t*>(std::malloc(std::max<size_t>(1, size_t(n)) * 4));
+  for (int i = 0; i < n; i++) {
+    xyz[3 * i] = v[i].x;
+    xyz[3 * i + 1] = v[i].y;
+    xyz[3 * i + 2] = v[i].z;
+    cam[i] = (v[i].tag & kTagCamBit) ? 1 : 0;
+  }
+  *xyz_out = xyz;
+  *cam_out = cam;
+  *n_out = n;
+  return AG_OK;
+}
+
+int ag_remove_plane(ag_ctx* h, float** xyz_out, int32_t** cam_out, int* n_out) {
+  if (!h || !xyz_out || !cam_out || !n_out) return AG_ERR_INVALID;
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  *xyz_out = nullptr;
+  *cam_out = nullptr;
+  *n_out = 0;
+  c.images_valid = false;
+  int rc = remove_plane_device(&c);
+  if (rc == AG_RETRY_KEYSORT) {
+    set_error("ag_remove_plane: no voxelised cloud (call ag_preprocess / ag_set_cloud first)");
+    return AG_ERR_INVALID;
+  }
+  if (rc) return rc;
+  return copy_cloud_out(c, xyz_out, cam_out, n_out);
 }
 
 int ag_set_cloud(ag_ctx* h, const float* xyz, const int32_t* cam, int n) {

@@ -523,6 +523,31 @@ int svm_to_device(SvmModel* svm, int device) {
   return AG_OK;
 }
 
+static int ensure_hog_tables(Ctx* c) {
+  if (!g_tables_ready[c->device & 63]) {
+    HogTables T;
+    std::memset(&T, 0, sizeof(T));
+    build_tables(T);
+    AG_CUDA_CHECK(cudaMemcpyToSymbol(c_hog, &T, sizeof(T)));
+    g_tables_ready[c->device & 63] = true;
+  }
+  return AG_OK;
+}
+
+// HOG descriptors only (training features, learning.cpp:249-290): n packed images -> n x 3528 floats
+int hog_descriptors_device(Ctx* c, const uint32_t* d_images, const int* d_image_slots, int n, float* d_descriptors) {
+  if (n <= 0) return AG_OK;
+  int rc = ensure_hog_tables(c);
+  if (rc) return rc;
+  SvmDev none;
+  std::memset(&none, 0, sizeof(none));
+  k_hog_svm<<<std::min(n, kNumSMs * 6), kThreads, 0, c->stream>>>(d_images, d_image_slots, n, nullptr, none, d_descriptors,
+                                                                  nullptr, nullptr);
+  c->launches += 1;
+  AG_CUDA_CHECK(cudaGetLastError());
+  return AG_OK;
+}
+
 int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d_image_slots, int n, const int* n_dev,
                    float* d_descriptors, float* d_scores, ag_grasp* d_grasps_out) {
   if (n <= 0) return AG_OK;
@@ -530,12 +555,9 @@ int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d
     set_error("SVM var_count != 3528");
     return AG_ERR_INVALID;
   }
-  if (!g_tables_ready[c->device & 63]) {
-    HogTables T;
-    std::memset(&T, 0, sizeof(T));
-    build_tables(T);
-    AG_CUDA_CHECK(cudaMemcpyToSymbol(c_hog, &T, sizeof(T)));
-    g_tables_ready[c->device & 63] = true;
+  {
+    int rc0 = ensure_hog_tables(c);
+    if (rc0) return rc0;
   }
   int rc = svm_to_device(svm, c->device);
   if (rc) return rc;

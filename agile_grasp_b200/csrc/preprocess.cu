@@ -723,9 +723,196 @@ __global__ void k_radius_search(const GPoint* __restrict__ pts, const int* __res
   }
 }
 
+// uses_clustering (localization.cpp:51-98): RANSAC score of T candidate planes in one pass over the voxel cloud —
+// counts[t] = number of points with |n_t . p + d_t| < thresh (pcl::SampleConsensusModelPlane::countWithinDistance)
+__global__ void __launch_bounds__(256)
+k_plane_score(const GPoint* __restrict__ vox, int n, const double* __restrict__ planes, int T, double thresh,
+              int* __restrict__ counts) {
+  __shared__ double s_pl[128][4];
+  __shared__ int s_cnt[128];
+  for (int i = threadIdx.x; i < T * 4; i += blockDim.x) (&s_pl[0][0])[i] = planes[i];
+  for (int i = threadIdx.x; i < T; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const int i = base + threadIdx.x;
+    GPoint p;
+    p.x = p.y = p.z = 0.f;
+    p.tag = 0;
+    if (i < n) p = vox[i];
+    const double x = double(p.x), y = double(p.y), z = double(p.z);
+    for (int t = 0; t < T; t++) {
+      const double d = (s_pl[t][0] * x + s_pl[t][1] * y) + (s_pl[t][2] * z + s_pl[t][3]);
+      const unsigned m = __ballot_sync(0xffffffffu, i < n && fabs(d) < thresh);
+      if (lane == 0 && m) atomicAdd(&s_cnt[t], __popc(m));
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += blockDim.x)
+    if (s_cnt[t]) atomicAdd(&counts[t], s_cnt[t]);
+}
+
 }  // namespace
 
 static PreState* state_ptr(Ctx* c) { return c->misc.as<PreState>(); }
+
+// ---- uses_clustering: dominant plane removal -------------------------------------------------------------------
+// PCL (not vendored) draws its RANSAC samples from its own generator, so which triples are drawn is this library's
+// choice (splitmix64 of the sample seed); everything else follows pcl::SACSegmentation as configured at
+// localization.cpp:56-68: 100 iterations, inlier = |distance| < 0.01, first best count wins, coefficients refitted
+// to the winner's inliers (centroid + smallest eigenvector of their covariance), the refitted plane's inliers
+// removed.  The 100 x N scoring runs on the GPU; the 3x3 refit and the compaction are host work on the 1-2 MB
+// voxel cloud (training-time path).
+namespace {
+uint64_t mix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+bool inlier_of(const double pl[4], const GPoint& p, double thresh) {
+  const double d = (pl[0] * double(p.x) + pl[1] * double(p.y)) + (pl[2] * double(p.z) + pl[3]);
+  return std::fabs(d) < thresh;
+}
+}  // namespace
+
+int remove_plane_device(Ctx* c) {
+  constexpr int kIter = 100;
+  constexpr double kThresh = 0.01;
+  RowIndex hri;
+  AG_CUDA_CHECK(cudaMemcpyAsync(&hri, c->row_index.p, sizeof(hri), cudaMemcpyDeviceToHost, c->stream));
+  AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (hri.error & kErrBitmapRetry) return AG_RETRY_KEYSORT;
+  const int n = hri.n_points;
+  if (n < 3) {  // no plane can be estimated: the reference returns no hands (localization.cpp:69-74)
+    set_error(" Could not estimate a planar model for the given dataset.");
+    return AG_ERR_EMPTY;
+  }
+  std::vector<GPoint> v(n);
+  AG_CUDA_CHECK(cudaMemcpyAsync(v.data(), c->vox.p, size_t(n) * 16, cudaMemcpyDeviceToHost, c->stream));
+  AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  // candidate planes: three distinct points per iteration
+  std::vector<double> planes(size_t(kIter) * 4, 0.0);
+  std::vector<char> valid(kIter, 0);
+  for (int t = 0; t < kIter; t++) {
+    int idx[3] = {0, 0, 0};
+    uint64_t st = mix64(c->params.seed ^ mix64(uint64_t(t) + 0x1234567ull));
+    for (int k = 0; k < 3; k++)
+      for (;;) {
+        st = mix64(st);
+        const int cand = int(st % uint64_t(n));
+        bool dup = false;
+        for (int q = 0; q < k; q++) dup = dup || idx[q] == cand;
+        if (!dup) {
+          idx[k] = cand;
+          break;
+        }
+      }
+    const GPoint &a = v[idx[0]], &b = v[idx[1]], &d = v[idx[2]];
+    const double e1[3] = {double(b.x) - double(a.x), double(b.y) - double(a.y), double(b.z) - double(a.z)};
+    const double e2[3] = {double(d.x) - double(a.x), double(d.y) - double(a.y), double(d.z) - double(a.z)};
+    const double nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];
+    const double len = std::sqrt(nx * nx + ny * ny + nz * nz);
+    double* pl = &planes[size_t(t) * 4];
+    if (len > 1e-12) {
+      valid[t] = 1;
+      pl[0] = nx / len;
+      pl[1] = ny / len;
+      pl[2] = nz / len;
+      pl[3] = -1.0 * (pl[0] * double(a.x) + pl[1] * double(a.y) + pl[2] * double(a.z));
+    } else {
+      pl[3] = 1e30;  // (scores zero)
+    }
+  }
+  DevBuf dpl;
+  if (dpl.reserve(planes.size() * 8 + kIter * 4 + 64)) return AG_ERR_CUDA;
+  int* d_counts = reinterpret_cast<int*>(dpl.as<double>() + planes.size());
+  AG_CUDA_CHECK(cudaMemcpyAsync(dpl.p, planes.data(), planes.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  AG_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, kIter * 4, c->stream));
+  k_plane_score<<<kNumSMs * 2, 256, 0, c->stream>>>(c->vox.as<GPoint>(), n, dpl.as<double>(), kIter, kThresh, d_counts);
+  c->launches += 1;
+  int counts[kIter];
+  AG_CUDA_CHECK(cudaMemcpyAsync(counts, d_counts, kIter * 4, cudaMemcpyDeviceToHost, c->stream));
+  AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  dpl.release();
+  int best = -1, best_count = 0;
+  for (int t = 0; t < kIter; t++)
+    if (valid[t] && counts[t] > best_count) {
+      best_count = counts[t];
+      best = t;
+    }
+  if (best < 0) {  // localization.cpp:69-74
+    set_error(" Could not estimate a planar model for the given dataset.");
+    return AG_ERR_EMPTY;
+  }
+  // refit to the winner's inliers (index order), then the refitted plane's inliers go
+  double pl[4] = {planes[size_t(best) * 4], planes[size_t(best) * 4 + 1], planes[size_t(best) * 4 + 2], planes[size_t(best) * 4 + 3]};
+  {
+    double ctr[3] = {0, 0, 0};
+    long long m = 0;
+    for (int i = 0; i < n; i++)
+      if (inlier_of(pl, v[i], kThresh)) {
+        ctr[0] += double(v[i].x);
+        ctr[1] += double(v[i].y);
+        ctr[2] += double(v[i].z);
+        m++;
+      }
+    if (m >= 3) {
+      for (int d = 0; d < 3; d++) ctr[d] /= double(m);
+      double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+      for (int i = 0; i < n; i++)
+        if (inlier_of(pl, v[i], kThresh)) {
+          const double w[3] = {double(v[i].x) - ctr[0], double(v[i].y) - ctr[1], double(v[i].z) - ctr[2]};
+          for (int r = 0; r < 3; r++)
+            for (int q = 0; q < 3; q++) C[r][q] += w[r] * w[q];
+        }
+      for (int sweep = 0; sweep < 60; sweep++) {  // cyclic Jacobi
+        if (C[0][1] * C[0][1] + C[0][2] * C[0][2] + C[1][2] * C[1][2] <= 1e-40) break;
+        for (int p = 0; p < 2; p++)
+          for (int q = p + 1; q < 3; q++) {
+            if (C[p][q] == 0.0) continue;
+            const double theta = (C[q][q] - C[p][p]) / (2.0 * C[p][q]);
+            const double tt = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+            const double cs = 1.0 / std::sqrt(tt * tt + 1.0), sn = tt * cs;
+            for (int k = 0; k < 3; k++) {
+              const double akp = C[k][p], akq = C[k][q];
+              C[k][p] = cs * akp - sn * akq;
+              C[k][q] = sn * akp + cs * akq;
+            }
+            for (int k = 0; k < 3; k++) {
+              const double apk = C[p][k], aqk = C[q][k];
+              C[p][k] = cs * apk - sn * aqk;
+              C[q][k] = sn * apk + cs * aqk;
+            }
+            for (int k = 0; k < 3; k++) {
+              const double vkp = V[k][p], vkq = V[k][q];
+              V[k][p] = cs * vkp - sn * vkq;
+              V[k][q] = sn * vkp + cs * vkq;
+            }
+          }
+      }
+      int mi = 0;
+      if (C[1][1] < C[mi][mi]) mi = 1;
+      if (C[2][2] < C[mi][mi]) mi = 2;
+      const double len = std::sqrt(V[0][mi] * V[0][mi] + V[1][mi] * V[1][mi] + V[2][mi] * V[2][mi]);
+      for (int d = 0; d < 3; d++) pl[d] = V[d][mi] / len;
+      pl[3] = -1.0 * (pl[0] * ctr[0] + pl[1] * ctr[1] + pl[2] * ctr[2]);
+    }
+  }
+  size_t w = 0;
+  bool cam1 = false;
+  for (int i = 0; i < n; i++)
+    if (!inlier_of(pl, v[i], kThresh)) {
+      v[w] = v[i];
+      v[w].tag &= kTagCamBit;
+      cam1 = cam1 || (v[w].tag & kTagCamBit);
+      w++;
+    }
+  c->two_cams = c->two_cams && cam1;
+  if (w > 0) AG_CUDA_CHECK(cudaMemcpyAsync(c->vox.p, v.data(), w * 16, cudaMemcpyHostToDevice, c->stream));
+  AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  return set_cloud_device(c, int(w));  // re-index the remaining (still voxel-ordered) cloud
+}
 
 static int row_stride_for(const ag_params& P, int* bx_out) {
   // rows per camera: workspace extent / voxel (+2), rounded up to the key bit budget

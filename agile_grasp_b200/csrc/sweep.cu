@@ -653,6 +653,105 @@ k_box_points(const SweepArgs A, const __grid_constant__ HandConst hc, int s, int
   }
 }
 
+// Training instances of one hypothesis from the points of ONE camera (Learning::createInstance(h, cam_pos, cam),
+// learning.cpp:375-400: the "simulated camera" instances of Learning::train, :76-141): the grasp image rasterised
+// from the box points whose camera source is 0, and from those whose source is 1.  One CTA per hypothesis, the
+// r = 0.08 ball gathered again with the arithmetic of k_hand_sweep; images[2 h], images[2 h + 1] must be zeroed.
+__global__ void __launch_bounds__(256)
+k_camera_images(const SweepArgs A, const __grid_constant__ HandConst hc, const int* __restrict__ slots, int n,
+                uint32_t* __restrict__ images) {
+  __shared__ double s_min[8];
+  __shared__ int s_j0, s_j1;
+  const int h = blockIdx.x;
+  if (h >= n) return;
+  const int slot = slots[h], s = slot >> 3, o = slot & 7;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const RowIndex& ri = *A.ri;
+  const int idx = A.indices[s];
+  const GPoint q = A.pts[idx];
+  const int sample_cam = (q.tag & kTagCamBit) ? 1 : 0;
+  const ag_frame fr = A.frames[s];
+  double F[3][3];
+  {
+    const double* a = fr.normal;
+    const double* b = fr.axis;
+    const double nxa[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    for (int r = 0; r < 3; r++) {
+      F[r][0] = a[r];
+      F[r][1] = nxa[r];
+      F[r][2] = b[r];
+    }
+  }
+  const double cs = hc.cosv[o], sn = hc.sinv[o], msn = -1.0 * sn;
+  const unsigned dbg = unsigned(A.debug[size_t(s) * 8 + o]);
+  const int e_idx = int((dbg >> 4) & 0xFu), last = int((dbg >> 8) & 0xFu);
+  double T[3][3];
+  for (int r = 0; r < 3; r++) {
+    T[r][0] = (F[r][0] * cs + F[r][1] * msn) + F[r][2] * 0.0;
+    T[r][1] = (F[r][0] * sn + F[r][1] * cs) + F[r][2] * 0.0;
+    T[r][2] = (F[r][0] * 0.0 + F[r][1] * 0.0) + F[r][2] * 1.0;
+  }
+  double surface3[3] = {0, 0, 0};
+  bool keep_sign = false;
+  for (int pass = 0; pass < 2; pass++) {
+    double minY = 1e300;
+    for (int c = 0; c < 2; c++) {
+      if (ri.count[c] == 0) continue;
+      int k_lo, k_hi;
+      row_range(ri, c, q.x, A.rpad, k_lo, k_hi);
+      for (int k = k_lo; k <= k_hi; k++) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          int j0, j1;
+          row_run(ri, A.row_ptr, A.col_ptr, A.pts, c, k, q.x, q.y, A.rpad, j0, j1);
+          s_j0 = j0;
+          s_j1 = j1;
+        }
+        __syncthreads();
+        for (int j = s_j0 + int(threadIdx.x); j < s_j1; j += blockDim.x) {
+          const GPoint p = A.pts[j];
+          if (!(dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z) < A.r2)) continue;
+          const double px = double(__fsub_rn(p.x, q.x)), py = double(__fsub_rn(p.y, q.y)), pz = double(__fsub_rn(p.z, q.z));
+          const double hz = (F[0][2] * px + F[1][2] * py) + F[2][2] * pz;
+          if (!(hz > -1.0 * hc.hand_height && hz < hc.hand_height)) continue;
+          const double hx = (F[0][0] * px + F[1][0] * py) + F[2][0] * pz;
+          const double hy = (F[0][1] * px + F[1][1] * py) + F[2][1] * pz;
+          const double rx = cs * hx + msn * hy, ry = sn * hx + cs * hy;
+          if (pass == 0) {
+            minY = fmin(minY, ry);
+          } else if (ry < hc.lim[last]) {  // learning.cpp:320-365 on the box points of one camera
+            const double bx = rx - surface3[0], by = ry - surface3[1];
+            const double hcell = floor(((keep_sign ? bx : -bx) - (-0.05)) / hc.img_cell);
+            const double vcell = floor((by - 0.0) / hc.img_cell);
+            const int hpx = int(fmin(99.0, fmax(0.0, hcell)));
+            const int vpx = int(fmin(79.0, fmax(0.0, vcell)));
+            const int bit = (AG_IMAGE_ROWS - 1 - vpx) * AG_IMAGE_COLS + hpx;
+            uint32_t* img = images + (size_t(2) * h + ((p.tag & kTagCamBit) ? 1 : 0)) * AG_IMAGE_WORDS;
+            atomicOr(&img[bit >> 5], 1u << (bit & 31));
+          }
+        }
+      }
+    }
+    if (pass == 0) {
+      minY = warp_min(minY);
+      if (lane == 0) s_min[warp] = minY;
+      __syncthreads();
+      double m = s_min[0];
+      for (int w2 = 1; w2 < 8; w2++) m = fmin(m, s_min[w2]);
+      const double hor = hc.half_od + hc.spacing[e_idx];
+      double surf_w[3], binormal[3];
+      for (int r = 0; r < 3; r++) {
+        surface3[r] = (T[r][0] * hor + T[r][1] * m) + T[r][2] * 0.0;
+        surf_w[r] = surface3[r] + double(r == 0 ? q.x : r == 1 ? q.y : q.z);
+        binormal[r] = (T[r][0] * 1.0 + T[r][1] * 0.0) + T[r][2] * 0.0;
+      }
+      const double s2c[3] = {surf_w[0] - hc.cam[sample_cam][0], surf_w[1] - hc.cam[sample_cam][1],
+                             surf_w[2] - hc.cam[sample_cam][2]};
+      keep_sign = dot3e(binormal, s2c) > 0;  // learning.cpp:330-333,382-383
+    }
+  }
+}
+
 // caller-supplied cloud_normals_: flag the points whose normal is non-zero
 __global__ void k_flag_normals(GPoint* pts, const double* __restrict__ normals, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -828,6 +927,17 @@ int box_points_device(Ctx* c, int n_samples, int slot, std::vector<double>& pts,
     for (int d = 0; d < 3; d++) pts[size_t(i) * 3 + d] = hp[size_t(order[i]) * 3 + d];
     cam[i] = hc2[order[i]];
   }
+  return AG_OK;
+}
+
+// per-camera grasp images of n hypotheses (raw slots in d_slots) of the last sweep: [n][2][AG_IMAGE_WORDS], zeroed here
+int camera_images_device(Ctx* c, int n_samples, const int* d_slots, int n, uint32_t* d_images) {
+  if (n <= 0) return AG_OK;
+  AG_CUDA_CHECK(cudaMemsetAsync(d_images, 0, size_t(n) * 2 * AG_IMAGE_WORDS * 4, c->stream));
+  SweepArgs A = make_args(c, c->sweep_indices, n_samples, c->sweep_frames, c->sweep_flags);
+  k_camera_images<<<n, 256, 0, c->stream>>>(A, c->hand, d_slots, n, d_images);
+  c->launches += 1;
+  AG_CUDA_CHECK(cudaGetLastError());
   return AG_OK;
 }
 

@@ -23,6 +23,8 @@
  *   ag_find_handles        <- Localization::findHandles -> HandleSearch::findHandles + Handle,
  *                             localization.cpp:390-408, handle_search.cpp:4-118, handle.cpp:3-73
  *   ag_load_pcd            <- pcl::io::loadPCDFile<pcl::PointXYZRGBA> in the file overloads, localization.cpp:169-214
+ *   ag_train_features      <- Learning::train* / convertData feature extraction, learning.cpp:76-163,249-290;
+ *                             AG_FLAG_USE_CLUSTERING <- uses_clustering plane removal, localization.cpp:51-98
  *   ag_localize_batch, ag_gather_*, ag_set_export_buffer, ag_params.shard_*  (no reference counterpart:
  *                             batches of clouds, multi-GPU exchange of the grasp list, sample sharding)
  *
@@ -58,6 +60,7 @@ extern "C" {
 /* flags for ag_localize */
 #define AG_FLAG_CALC_ANTIPODAL 1u   /* calculates_antipodal: all-points r=0.01 normals pass */
 #define AG_FLAG_KEEP_POINTS 2u      /* also materialise points_for_learning on the host */
+#define AG_FLAG_USE_CLUSTERING 4u   /* uses_clustering: remove the dominant (RANSAC) plane before sampling, localization.cpp:51-98 */
 
 /* Parameters = the union of Localization's setters (localization.h:148-259), HandSearch's
  * hard-coded radii (hand_search.h:85, hand_search.cpp:20) and the Localization ctor args. */
@@ -249,6 +252,14 @@ int ag_find_handles(ag_ctx* ctx, const ag_grasp* hands, int n, int min_inliers, 
  * camera source of each column. */
 int ag_get_points(ag_ctx* ctx, int image_id, double** pts3xm, int32_t** cam, int* m);
 int ag_get_images(ag_ctx* ctx, uint32_t** bits, int* n_images);   /* AG_IMAGE_WORDS per image */
+/* Training-data path (Learning::train -> convertData, learning.cpp:76-163,249-290; caller src/nodes/train.cpp:105-129):
+ * HOG descriptors of the three training instances of each hypothesis of the last ag_localize — its grasp image, and
+ * the images made from the points of camera 1 only / camera 2 only (createInstance(h, cam_pos [, 0 | 1])).
+ * features: n x 3 x AG_HOG_DIM floats, row 3 i + k = instance k of hypothesis i.  Labels are the hypotheses'
+ * full_antipodal flags (learning.cpp:379); which hypotheses become instances and the SMO solve (CvSVM::train) stay
+ * with the caller — the model file it saves loads through ag_svm_load. */
+int ag_train_features(ag_ctx* ctx, const ag_grasp* grasps, int n, float* features);
+
 /* cloud_normals_ (hand_search.cpp:13-26,102) as the last ag_localize / ag_hand_sweep left it: 3 doubles for each
  * of the first n voxels (n <= voxel count); zero where no normal was computed. */
 int ag_get_normals(ag_ctx* ctx, double* normals3n, int n);
@@ -258,6 +269,11 @@ int ag_get_normals(ag_ctx* ctx, double* normals3n, int n);
 /* NaN removal + workspace filter + voxelisation. Outputs malloc'ed: xyz (3 floats per voxel), cam. */
 int ag_preprocess(ag_ctx* ctx, const void* points, int stride, int n_in, int size_left,
                   float** xyz_out, int32_t** cam_out, int* n_out);
+
+/* uses_clustering as a stage (localization.cpp:51-98): removes the dominant RANSAC plane (100 iterations, inlier
+ * distance 0.01, refitted coefficients) from the context's current voxelised cloud and re-indexes it; returns the
+ * remaining cloud.  AG_ERR_EMPTY if no plane was found (the reference then returns no hands). */
+int ag_remove_plane(ag_ctx* ctx, float** xyz_out, int32_t** cam_out, int* n_out);
 
 /* Load an already-voxelised cloud (skips preprocessing; must be in voxel order) and build the row index. */
 int ag_set_cloud(ag_ctx* ctx, const float* xyz, const int32_t* cam, int n);

@@ -80,6 +80,16 @@ int ago_grasp_image(const ago_hands* h, int k, const ag_params* P, uint8_t* imag
 int ago_points_image(const double* pts3xm, int m, const double binormal[3], const double surface[3],
                      const double cam_pos[3], uint8_t* image80x100);
 
+/* training instances (learning.cpp:375-400): image of hypothesis k from all box points (cam = -1) or only from the
+ * points of camera 1 / 2 (cam = 0 / 1: the "simulated camera" instances of Learning::train, learning.cpp:76-141) */
+int ago_grasp_image_cam(const ago_hands* h, int k, int cam, const ag_params* P, uint8_t* image80x100);
+
+/* uses_clustering (localization.cpp:51-98): RANSAC plane (100 iterations, threshold 0.01, refitted coefficients)
+ * removed from a voxelised cloud; keep[i] = 0 for plane inliers.  counts_out (may be NULL): inlier count of every
+ * iteration; plane_out (may be NULL): the refitted plane n.p + d = 0.  Returns 1 if no plane was found. */
+int ago_remove_plane(const float* xyz, int n, uint64_t seed, int max_iterations, double thresh, uint8_t* keep,
+                     int32_t* counts_out, double* plane_out);
+
 /* C.3 HOG as configured at learning.cpp:194-195,220 -> 3528 floats */
 int ago_hog(const uint8_t* image80x100, float* desc3528);
 

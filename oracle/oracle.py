@@ -217,6 +217,13 @@ class Hands:
             raise RuntimeError(_err())
         return img
 
+    def image_cam(self, k, cam, params: AgParams):
+        """training instance image (learning.cpp:375-400): cam = -1 all box points, 0 / 1 camera 1 / 2 only"""
+        img = np.zeros((AG_IMAGE_ROWS, AG_IMAGE_COLS), np.uint8)
+        if lib().ago_grasp_image_cam(self.h, k, int(cam), C.byref(params), _p(img, C.c_uint8)) != 0:
+            raise RuntimeError(_err())
+        return img
+
     def classify(self, svm, params: AgParams):
         n = len(self)
         keep = np.zeros(n, np.uint8)
@@ -327,6 +334,17 @@ def find_handles(grasps, min_inliers, min_length):
     lib().ago_free(hp)
     lib().ago_free(ip_)
     return H, [flat[h["inlier_offset"]:h["inlier_offset"] + h["n_inliers"]] for h in H]
+
+
+def remove_plane(xyz, seed, max_iterations=100, thresh=0.01):
+    """uses_clustering (localization.cpp:51-98): (keep mask, per-iteration inlier counts, refitted plane) or None"""
+    X = np.ascontiguousarray(xyz, dtype=np.float32)
+    keep = np.zeros(X.shape[0], np.uint8)
+    counts = np.zeros(max_iterations, np.int32)
+    plane = np.zeros(4)
+    rc = lib().ago_remove_plane(_p(X, C.c_float), X.shape[0], C.c_uint64(seed), int(max_iterations), C.c_double(thresh),
+                                _p(keep, C.c_uint8), _p(counts, C.c_int32), _p(plane, C.c_double))
+    return None if rc else (keep.astype(bool), counts, plane)
 
 
 def glibc_rand(seed, n):

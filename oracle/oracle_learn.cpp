@@ -447,6 +447,27 @@ int ago_grasp_image(const ago_hands* h, int k, const ag_params* P, uint8_t* imag
   return 0;
 }
 
+// Learning::createInstance(h, cam_pos, cam) + convertToImage (learning.cpp:375-400,320-365): cam = -1 all box
+// points, cam = 0 / 1 only the points seen by camera 1 / 2 (the "simulated camera" instances of Learning::train,
+// learning.cpp:76-141)
+int ago_grasp_image_cam(const ago_hands* h, int k, int cam, const ag_params* P, uint8_t* image) {
+  if (k < 0 || k >= int(h->h->grasps.size())) return fail("hypothesis index out of range");
+  const ag_grasp& g = h->h->grasps[k];
+  const double* tf = g.cam_source == 1 ? P->cam_tf_right : P->cam_tf_left;  // learning.cpp:382-383
+  const double cam_pos[3] = {tf[3], tf[7], tf[11]};
+  const std::vector<double>& pts = h->h->pts[k];
+  const std::vector<int32_t>& pc = h->h->pcam[k];
+  if (cam < 0) {
+    points_image(pts.data(), int(pc.size()), g.binormal, g.surface, cam_pos, image);
+    return 0;
+  }
+  std::vector<double> sub;  // columns listed by getIndicesPointsForLearningCam1/2 (rotating_hand.cpp:143-151)
+  for (size_t j = 0; j < pc.size(); j++)
+    if (pc[j] == cam) sub.insert(sub.end(), pts.begin() + 3 * j, pts.begin() + 3 * j + 3);
+  points_image(sub.data(), int(sub.size() / 3), g.binormal, g.surface, cam_pos, image);
+  return 0;
+}
+
 int ago_hog(const uint8_t* image80x100, float* desc3528) {
   hog::compute(image80x100, desc3528);
   return 0;
@@ -500,6 +521,139 @@ int ago_classify(ago_hands* h, const ago_svm* s, const ag_params* P, uint8_t* ke
   return 0;
 }
 
+// uses_clustering (localization.cpp:51-98): remove the dominant plane found by RANSAC (pcl::SACSegmentation,
+// SACMODEL_PLANE / SAC_RANSAC, 100 iterations, distance threshold 0.01, optimised coefficients) from the
+// voxelised cloud.  PCL is not vendored and draws its samples from its own generator, so WHICH triples are drawn
+// is restated, not reproduced: iteration t draws three distinct points from splitmix64(seed, t); all 100
+// iterations run (PCL may stop earlier once its inlier ratio makes more draws pointless — more draws can only
+// find an equal or better plane).  The rest follows PCL: score = number of points with |n.p + d| < threshold,
+// first best wins; coefficients refitted to the winner's inliers (centroid + smallest eigenvector of the
+// covariance); final inliers of the refitted plane removed.
+static uint64_t sm64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+void ransac_triple(int n, uint64_t seed, int t, int idx[3]) {
+  uint64_t s = sm64(seed ^ sm64(uint64_t(t) + 0x1234567ull));
+  for (int k = 0; k < 3; k++) {
+    for (;;) {
+      s = sm64(s);
+      const int v = int(s % uint64_t(n));
+      bool dup = false;
+      for (int q = 0; q < k; q++) dup = dup || idx[q] == v;
+      if (!dup) {
+        idx[k] = v;
+        break;
+      }
+    }
+  }
+}
+// plane through three points: unit normal and offset; false if (nearly) collinear
+bool plane_from_triple(const float* xyz, const int idx[3], double pl[4]) {
+  const double p0[3] = {xyz[3 * idx[0]], xyz[3 * idx[0] + 1], xyz[3 * idx[0] + 2]};
+  double a[3], b[3];
+  for (int d = 0; d < 3; d++) {
+    a[d] = double(xyz[3 * idx[1] + d]) - p0[d];
+    b[d] = double(xyz[3 * idx[2] + d]) - p0[d];
+  }
+  const double nx = a[1] * b[2] - a[2] * b[1], ny = a[2] * b[0] - a[0] * b[2], nz = a[0] * b[1] - a[1] * b[0];
+  const double len = std::sqrt(nx * nx + ny * ny + nz * nz);
+  if (!(len > 1e-12)) return false;
+  pl[0] = nx / len;
+  pl[1] = ny / len;
+  pl[2] = nz / len;
+  pl[3] = -1.0 * (pl[0] * p0[0] + pl[1] * p0[1] + pl[2] * p0[2]);
+  return true;
+}
+static inline bool plane_inlier(const double pl[4], const float* p, double thresh) {
+  const double d = (pl[0] * double(p[0]) + pl[1] * double(p[1])) + (pl[2] * double(p[2]) + pl[3]);
+  return std::fabs(d) < thresh;
+}
+// refit to the inliers: centroid and covariance accumulated in index order, smallest eigenvector (cyclic Jacobi)
+bool refit_plane(const float* xyz, int n, const double pl[4], double thresh, double out[4]) {
+  double c[3] = {0, 0, 0};
+  long long m = 0;
+  for (int i = 0; i < n; i++)
+    if (plane_inlier(pl, xyz + 3 * i, thresh)) {
+      for (int d = 0; d < 3; d++) c[d] += double(xyz[3 * i + d]);
+      m++;
+    }
+  if (m < 3) return false;
+  for (int d = 0; d < 3; d++) c[d] /= double(m);
+  double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int i = 0; i < n; i++)
+    if (plane_inlier(pl, xyz + 3 * i, thresh)) {
+      const double v[3] = {double(xyz[3 * i]) - c[0], double(xyz[3 * i + 1]) - c[1], double(xyz[3 * i + 2]) - c[2]};
+      for (int r = 0; r < 3; r++)
+        for (int q = 0; q < 3; q++) C[r][q] += v[r] * v[q];
+    }
+  // cyclic Jacobi on the symmetric 3x3
+  double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (int sweep = 0; sweep < 60; sweep++) {
+    const double off = C[0][1] * C[0][1] + C[0][2] * C[0][2] + C[1][2] * C[1][2];
+    if (off <= 1e-40) break;
+    for (int p = 0; p < 2; p++)
+      for (int q = p + 1; q < 3; q++) {
+        if (C[p][q] == 0.0) continue;
+        const double theta = (C[q][q] - C[p][p]) / (2.0 * C[p][q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double cs = 1.0 / std::sqrt(t * t + 1.0), sn = t * cs;
+        for (int k = 0; k < 3; k++) {
+          const double akp = C[k][p], akq = C[k][q];
+          C[k][p] = cs * akp - sn * akq;
+          C[k][q] = sn * akp + cs * akq;
+        }
+        for (int k = 0; k < 3; k++) {
+          const double apk = C[p][k], aqk = C[q][k];
+          C[p][k] = cs * apk - sn * aqk;
+          C[q][k] = sn * apk + cs * aqk;
+        }
+        for (int k = 0; k < 3; k++) {
+          const double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = cs * vkp - sn * vkq;
+          V[k][q] = sn * vkp + cs * vkq;
+        }
+      }
+  }
+  int mi = 0;
+  if (C[1][1] < C[mi][mi]) mi = 1;
+  if (C[2][2] < C[mi][mi]) mi = 2;
+  const double len = std::sqrt(V[0][mi] * V[0][mi] + V[1][mi] * V[1][mi] + V[2][mi] * V[2][mi]);
+  for (int d = 0; d < 3; d++) out[d] = V[d][mi] / len;
+  out[3] = -1.0 * (out[0] * c[0] + out[1] * c[1] + out[2] * c[2]);
+  return true;
+}
+
+int ago_remove_plane(const float* xyz, int n, uint64_t seed, int max_iterations, double thresh,
+                                uint8_t* keep, int32_t* counts_out, double* plane_out) {
+  for (int i = 0; i < n; i++) keep[i] = 1;
+  if (n < 3) return 1;
+  int best_t = -1, best_count = 0;
+  double best_pl[4] = {0, 0, 0, 0};
+  for (int t = 0; t < max_iterations; t++) {
+    int idx[3];
+    ransac_triple(n, seed, t, idx);
+    double pl[4];
+    int cnt = 0;
+    if (plane_from_triple(xyz, idx, pl))
+      for (int i = 0; i < n; i++) cnt += plane_inlier(pl, xyz + 3 * i, thresh) ? 1 : 0;
+    if (counts_out) counts_out[t] = cnt;
+    if (cnt > best_count) {
+      best_count = cnt;
+      best_t = t;
+      std::memcpy(best_pl, pl, sizeof(pl));
+    }
+  }
+  if (best_t < 0) return 1;  // "Could not estimate a planar model for the given dataset."
+  double ref[4];
+  if (!refit_plane(xyz, n, best_pl, thresh, ref)) std::memcpy(ref, best_pl, sizeof(ref));
+  if (plane_out) std::memcpy(plane_out, ref, sizeof(ref));
+  for (int i = 0; i < n; i++) keep[i] = plane_inlier(ref, xyz + 3 * i, thresh) ? 0 : 1;
+  return 0;
+}
+
 ago_hands* ago_localize(const void* points, int stride, int n_in, int size_left, const ag_params* P,
                         const int* indices, int n_indices, unsigned flags, const ago_svm* svm, int use_std_set,
                         double* times_ms, int* n_voxels_out) {
@@ -510,6 +664,23 @@ ago_hands* ago_localize(const void* points, int stride, int n_in, int size_left,
   std::vector<float> xyz;
   std::vector<int32_t> cam;
   if (preprocess(points, stride, n_in, size_left, *P, use_std_set != 0, xyz, cam) != 0) return nullptr;
+  if (flags & AG_FLAG_USE_CLUSTERING) {  // localization.cpp:51-98
+    std::vector<uint8_t> keep(cam.size());
+    if (ago_remove_plane(xyz.data(), int(cam.size()), P->seed, 100, 0.01, keep.data(), nullptr, nullptr) != 0) {
+      ago_hands* none = new ago_hands;
+      none->h = new Hands;
+      if (n_voxels_out) *n_voxels_out = 0;
+      return none;  // "Could not estimate a planar model": empty hand list (localization.cpp:69-74)
+    }
+    size_t w = 0;
+    for (size_t i = 0; i < keep.size(); i++)
+      if (keep[i]) {
+        for (int d = 0; d < 3; d++) xyz[3 * w + d] = xyz[3 * i + d];
+        cam[w++] = cam[i];
+      }
+    xyz.resize(3 * w);
+    cam.resize(w);
+  }
   const int n = int(cam.size());
   if (n_voxels_out) *n_voxels_out = n;
   auto t1 = now();

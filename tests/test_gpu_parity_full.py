@@ -322,3 +322,101 @@ def test_classify_rejects_records_of_another_call(ctx, small_scene, linear_svm_p
     other.close()
     gg, keep = ctx.classify(svm, g_new)
     assert np.isfinite(gg["score"]).all()
+
+
+# ---- the training-data path (src/nodes/train.cpp:105-129) --------------------------------------------
+def test_plane_removal_matches_oracle(ctx, oracle, small_scene, two_view_scene):
+    """uses_clustering (localization.cpp:51-98): the cloud without its dominant RANSAC plane, bit-identical to the
+    oracle's (same candidate triples, the 100 x N scoring on the GPU, same refit), as a stage and inside
+    ag_localize."""
+    for s in (small_scene, two_view_scene):
+        ctx.set_params(s["P"])
+        ctx.set_svm(None)
+        ctx.preprocess(s["pts"], s["size_left"])
+        xg, cg = ctx.remove_plane()
+        keep, counts, plane = oracle.remove_plane(s["xyz"], seed=s["P"].seed)
+        assert 0 < keep.sum() < len(keep)
+        assert (_u32(xg) == _u32(s["xyz"][keep])).all() and np.array_equal(cg, s["cam"][keep])
+        # the rest of the path runs on the reduced cloud: explicit indices refer to it
+        idx = oracle.draw_samples(int(keep.sum()), 80, s["P"].seed)
+        g = ctx.localize(s["pts"], s["size_left"], idx, flags=4)
+        assert ctx.timings()["n_voxels"] == keep.sum()
+        H, tm, nv = oracle.localize(s["pts"], s["size_left"], s["P"], idx, 4, None, False)
+        assert nv == keep.sum()
+        ig, io = _match(g, H.grasps)
+        assert len(ig) >= 0.95 * max(len(g), len(H.grasps), 1)
+        # neighbour sets on the re-indexed cloud
+        tree = oracle.Tree(xg)
+        for i in idx[:10]:
+            a = ctx.radius_search(xg[i], 0.03)
+            b, _ = tree.radius_search(xg[i], 0.03, 0)
+            assert np.array_equal(a, np.sort(b))
+    # a cloud without three points has no plane: the reference returns no hands (localization.cpp:69-74)
+    tiny = small_scene["pts"][:1].copy()
+    tiny[0, :3] = [0.5, 0.0, 0.1]
+    with pytest.raises(api.AgError, match="planar model"):
+        ctx.localize(tiny, 1, flags=4)
+
+
+def test_training_features_bit_exact(ctx, oracle, two_view_scene, small_scene):
+    """Learning::train / convertData feature extraction (learning.cpp:76-163,249-290): per hypothesis the HOG
+    descriptors of createInstance(h, cam_pos), (h, cam_pos, 0) and (h, cam_pos, 1) — bit-equal to the oracle's
+    images through the oracle's (cv2-pinned) HOG, on a two-camera and a one-camera scene."""
+    for s in (two_view_scene, small_scene):
+        frames = oracle.fit_quadrics(s["tree"], s["cam"], s["idx"], 0.03, s["P"])["frames"]
+        normals = np.zeros((len(s["xyz"]), 3))
+        normals[s["idx"]] = frames["normal"]
+        ctx.set_params(s["P"])
+        ctx.set_svm(None)
+        ctx.set_cloud(s["xyz"], s["cam"])
+        g = ctx.hand_sweep(s["idx"], frames, normals)
+        H = oracle.find_hands(s["tree"], s["cam"], s["idx"], frames, s["cam"][s["idx"]], normals, s["P"])
+        assert len(g) == len(H) and len(g) > 10
+        sel = np.arange(0, len(g), max(1, len(g) // 40))
+        F = ctx.train_features(g[sel])
+        assert F.shape == (len(sel), 3, 3528)
+        nonempty = [0, 0, 0]
+        for row, k in enumerate(sel):
+            for j, cam in enumerate((-1, 0, 1)):
+                img = H.image_cam(int(k), cam, s["P"])
+                nonempty[j] += int(img.any())
+                assert (_u32(F[row, j]) == _u32(oracle.hog(img))).all(), (k, cam)
+        assert nonempty[0] == len(sel) and nonempty[1] > 0
+        if s is two_view_scene:
+            assert nonempty[2] > 0
+        # stale records are rejected like in ag_classify
+        ctx.hand_sweep(s["idx"][:5], frames[:5], normals)
+        with pytest.raises(api.AgError, match="does not belong"):
+            ctx.train_features(g[sel])
+
+
+def test_trained_model_round_trip(ctx, oracle, small_scene, tmp_path):
+    """train.cpp end to end at small scale: localizeHands(calculates_antipodal, uses_clustering) -> features and
+    labels -> CvSVM::train (cv2 here: the SMO solve stays on the host) -> the saved model file loads through
+    ag_svm_load and ag_classify reproduces cv2's own predictions on the training images."""
+    cv2 = pytest.importorskip("cv2")
+    s = small_scene
+    ctx.set_params(s["P"])
+    ctx.set_svm(None)
+    g = ctx.localize(s["pts"], s["size_left"], flags=1 | 4)
+    assert len(g) > 20
+    # Learning::train(hands, file, cam_pos): every hand that is not merely half antipodal, three instances each
+    use = (g["half_antipodal"] == 0) | (g["full_antipodal"] == 1)
+    F = ctx.train_features(g[use]).reshape(-1, 3528)
+    y = np.repeat(np.where(g["full_antipodal"][use] == 1, 1, -1), 3).astype(np.int32)
+    if len(np.unique(y)) < 2:  # a scene without full-antipodal hands: label by width so that two classes exist
+        y = np.repeat(np.where(g["width"][use] > np.median(g["width"][use]), 1, -1), 3).astype(np.int32)
+    svm = cv2.ml.SVM_create()
+    svm.setType(cv2.ml.SVM_C_SVC)
+    svm.setKernel(cv2.ml.SVM_LINEAR)
+    svm.train(F, cv2.ml.ROW_SAMPLE, y)
+    path = str(tmp_path / "trained_svm")
+    svm.save(path)
+    model = api.Svm(path)  # (OpenCV 4 writes "opencv_ml_svm:" where the reference's 2.4 files say "my_svm: !!opencv-ml-svm")
+    assert model.var_count == 3528
+    gg, keep = ctx.classify(model, g)
+    own = ctx.train_features(g)[:, 0, :]
+    raw = svm.predict(own, flags=cv2.ml.STAT_MODEL_RAW_OUTPUT)[1].ravel()
+    lab = svm.predict(own)[1].ravel()
+    assert np.allclose(gg["score"], raw, rtol=1e-5, atol=1e-5)
+    assert np.array_equal(keep == 1, lab == 1)

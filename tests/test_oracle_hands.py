@@ -99,3 +99,24 @@ def test_pipeline_golden_regression(oracle, linear_svm_path):
     keep = H.classify(oracle.Svm(linear_svm_path), P)
     assert np.array_equal(keep, z["keep"])
     assert np.array_equal(H.grasps["score"].view(np.uint32), gz["score"].view(np.uint32))
+
+
+def test_per_camera_training_images(oracle, two_view_scene):
+    """createInstance(h, cam_pos, cam) (learning.cpp:375-400): the image of camera 1's points and the image of
+    camera 2's points together give the hypothesis' own image; with two registered views both are non-trivial."""
+    s = two_view_scene
+    frames = oracle.fit_quadrics(s["tree"], s["cam"], s["idx"], 0.03, s["P"])["frames"]
+    normals = np.zeros((len(s["xyz"]), 3))
+    normals[s["idx"]] = frames["normal"]
+    H = oracle.find_hands(s["tree"], s["cam"], s["idx"], frames, s["cam"][s["idx"]], normals, s["P"])
+    n = len(H)
+    assert n > 10
+    both = 0
+    for k in range(0, n, max(1, n // 25)):
+        own, c0, c1 = H.image_cam(k, -1, s["P"]), H.image_cam(k, 0, s["P"]), H.image_cam(k, 1, s["P"])
+        assert np.array_equal(own, H.image(k, s["P"]))
+        assert np.array_equal(own, np.maximum(c0, c1))
+        P3, cam = H.points(k)
+        assert (c0.any() == (cam == 0).any()) and (c1.any() == (cam == 1).any())
+        both += int(c0.any() and c1.any())
+    assert both > 0

@@ -78,3 +78,32 @@ def test_workspace_filter_and_empty(oracle):
         assert False
     except RuntimeError as e:
         assert "empty" in str(e)
+
+
+def test_plane_removal_restatement(oracle, small_scene):
+    """uses_clustering (localization.cpp:51-98): the RANSAC plane of the tabletop scene is the table; every
+    iteration's inlier count and the final inlier set agree with an independent numpy statement of the same
+    planes; the refitted plane is the least-squares plane of the winner's inliers."""
+    xyz = small_scene["xyz"]
+    res = oracle.remove_plane(xyz, seed=20150320)
+    assert res is not None
+    keep, counts, plane = res
+    X = xyz.astype(np.float64)
+    d = (plane[0] * X[:, 0] + plane[1] * X[:, 1]) + (plane[2] * X[:, 2] + plane[3])
+    assert np.array_equal(keep, ~(np.abs(d) < 0.01))
+    assert 0.3 < (~keep).mean() < 0.95 and counts.max() >= 0.3 * len(xyz)  # the table dominates the scene
+    from agile_grasp_b200 import scenes
+    n_table = scenes.table_frame()[3]
+    assert abs(abs(plane[:3] @ n_table) - 1.0) < 1e-3 and abs(np.linalg.norm(plane[:3]) - 1.0) < 1e-12
+    # least squares: the normal is the smallest principal direction of the inliers of the best candidate (a superset
+    # check: refitting the final inliers again moves the plane by less than a tenth of a millimetre)
+    P = X[~keep]
+    c = P.mean(0)
+    w, V = np.linalg.eigh((P - c).T @ (P - c))
+    assert abs(abs(V[:, 0] @ plane[:3]) - 1.0) < 1e-4 and abs(plane[:3] @ c + plane[3]) < 1e-4
+    # deterministic, and sensitive to the seed only through which triples are tried
+    keep2, counts2, plane2 = oracle.remove_plane(xyz, seed=20150320)
+    assert np.array_equal(keep, keep2) and np.array_equal(counts, counts2)
+    keep3, counts3, _ = oracle.remove_plane(xyz, seed=7)
+    assert not np.array_equal(counts, counts3) and (keep3 == keep).mean() > 0.99
+    assert oracle.remove_plane(xyz[:2], seed=1) is None
