@@ -68,6 +68,11 @@ class GraspHypothesis {
     }
   }
 
+  // B200 addition (training path): HOG descriptors of the hypothesis' three training instances (own image, camera 1
+  // only, camera 2 only; learning.cpp:76-141), 3 x 3528 floats, filled by Localization when asked to keep them
+  void setTrainFeatures(const float* f, size_t n) { train_features_.assign(f, f + n); }
+  const std::vector<float>& getTrainFeatures() const { return train_features_; }
+
   // B200 additions: the SVM decision value and the underlying record
   float getScore() const { return rec_.score; }
   const ag_grasp& record() const { return rec_; }
@@ -81,6 +86,7 @@ class GraspHypothesis {
   Eigen::Vector3d axis_, approach_, binormal_, grasp_bottom_, grasp_surface_;
   double grasp_width_;
   bool full_antipodal_, half_antipodal_;
+  std::vector<float> train_features_;
   ag_grasp rec_ = ag_grasp();
 };
 

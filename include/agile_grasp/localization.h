@@ -3,7 +3,8 @@
 // Same method names, argument meaning and error behaviour: errors print to stdout and return an empty
 // vector (localization.cpp:9-15,184-189; learning.cpp:172-191).  Differences, all documented in
 // num_threads is accepted and ignored (the GPU path has no thread knob); only
-// NO_PLOTTING is honoured; createVisualsPub needs ROS and is not provided;
+// NO_PLOTTING is honoured; createVisualsPub needs ROS and is not provided; uses_clustering draws its RANSAC
+// triples from the library's own generator (PCL's is not reproducible outside PCL);
 // points_for_learning stay on the device unless requested.
 #ifndef AGILE_GRASP_LOCALIZATION_H_
 #define AGILE_GRASP_LOCALIZATION_H_
@@ -44,7 +45,7 @@ class Localization {
       std::cout << "Input cloud is empty!\n" << size_left << std::endl;
       return hand_list;
     }
-    if (uses_clustering) std::cout << "uses_clustering (training-only RANSAC plane removal) is not part of the hot path; ignored\n";
+    if (uses_clustering) std::cout << "Finding point cloud clusters ... \n";  // localization.cpp:53
     if (!ensure_ctx()) return hand_list;
     // the reference removes NaN points from the CALLER's cloud in place (localization.cpp:27)
     std::vector<pcl::PointXYZRGBA>& pts = cloud_in->points;
@@ -52,7 +53,8 @@ class Localization {
     int n = 0;
     int rc = ag_localize(ctx_, pts.data(), int(sizeof(pcl::PointXYZRGBA)), int(pts.size()), size_left,
                          indices.empty() ? nullptr : indices.data(), int(indices.size()),
-                         calculates_antipodal ? AG_FLAG_CALC_ANTIPODAL : 0u, &out, &n);
+                         (calculates_antipodal ? AG_FLAG_CALC_ANTIPODAL : 0u) | (uses_clustering ? AG_FLAG_USE_CLUSTERING : 0u),
+                         &out, &n);
     size_t w = 0;
     for (size_t i = 0; i < pts.size(); i++)
       if (pts[i].x == pts[i].x && pts[i].y == pts[i].y && pts[i].z == pts[i].z &&
@@ -63,8 +65,17 @@ class Localization {
       return hand_list;
     }
     hand_list.reserve(n);
+    std::vector<float> feats;
+    if (keep_train_features_ && n > 0) {  // training path: the three instances' HOG descriptors of every hypothesis
+      feats.resize(size_t(n) * 3 * AG_HOG_DIM);
+      if (ag_train_features(ctx_, out, n, feats.data()) != AG_OK) {
+        std::cout << ag_last_error() << "\n";
+        feats.clear();
+      }
+    }
     for (int i = 0; i < n; i++) {
       GraspHypothesis g(out[i]);
+      if (!feats.empty()) g.setTrainFeatures(feats.data() + size_t(i) * 3 * AG_HOG_DIM, size_t(3) * AG_HOG_DIM);
       if (keep_points_) {  // materialise points_for_learning + per-camera index lists (grasp_hypothesis.h:217-220)
         double* p = nullptr;
         int32_t* cm = nullptr;
@@ -214,6 +225,10 @@ class Localization {
   // B200 addition: the grasp image is rasterised on the device, so the variable-length members of
   // GraspHypothesis are only copied to the host when asked for
   void setKeepPointsForLearning(bool keep) { keep_points_ = keep; }
+  // B200 addition (training path, src/nodes/train.cpp): keep the HOG descriptors of the three training instances of
+  // every hypothesis (the grasp images live on the device and only for the last call; Learning::train needs them
+  // for the hypotheses of ALL training clouds)
+  void setKeepTrainingFeatures(bool keep) { keep_train_features_ = keep; }
 
   static const int NO_PLOTTING = 0;
   static const int PCL_PLOTTING = 1;
@@ -258,6 +273,7 @@ class Localization {
   ag_params params_;
   bool dirty_;
   bool keep_points_ = false;
+  bool keep_train_features_ = false;
   ag_ctx* ctx_;
   ag_svm* svm_;
   std::string svm_path_;

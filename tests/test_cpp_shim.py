@@ -36,3 +36,4 @@ def test_shim_compiles_and_host_parts_run(tmp_path):
 
 def test_example_cli_compiles(tmp_path):
     _compile(os.path.join(ROOT, "examples", "test_svm.cpp"), str(tmp_path / "test_svm"))
+    _compile(os.path.join(ROOT, "examples", "train_svm.cpp"), str(tmp_path / "train_svm"))

@@ -420,3 +420,52 @@ def test_trained_model_round_trip(ctx, oracle, small_scene, tmp_path):
     lab = svm.predict(own)[1].ravel()
     assert np.allclose(gg["score"], raw, rtol=1e-5, atol=1e-5)
     assert np.array_equal(keep == 1, lab == 1)
+
+
+def test_cpp_train_svm_example(tmp_path):
+    """The reference's training CLI (src/nodes/train.cpp) through the C++ shim: Localization::localizeHands(left,
+    right, calculates_antipodal = true, uses_clustering = true) per cloud pair, Learning::train over all hypotheses;
+    without OpenCV C++ the shim leaves the training matrix next to the model path, cv2 trains on it and the
+    resulting model file loads through ag_svm_load."""
+    import subprocess
+    cv2 = pytest.importorskip("cv2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(api.LIB_PATH)
+    exe = tmp_path / "train_svm"
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "examples", "train_svm.cpp"), "-o", str(exe), "-L" + libdir, "-lag_b200",
+                           "-Wl,-rpath," + libdir, "-L/usr/local/cuda/lib64", "-lcudart"])
+    files = []
+    for k in range(2):
+        pts, size_left, P, S = scenes.config_cloud(3, small=(240, 180, 100), scene_offset=k)
+        for side, sl in (("l", slice(0, size_left)), ("r", slice(size_left, None))):
+            sub = pts[sl]
+            rec = np.zeros(len(sub), dtype=[("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("rgba", "<u4")])
+            rec["x"], rec["y"], rec["z"] = sub[:, 0], sub[:, 1], sub[:, 2]
+            f = tmp_path / f"cloud{k}{side}_reg.pcd"
+            hdr = ("VERSION 0.7\nFIELDS x y z rgba\nSIZE 4 4 4 4\nTYPE F F F U\nCOUNT 1 1 1 1\nWIDTH %d\nHEIGHT 1\n"
+                   "VIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA binary\n" % (len(sub), len(sub))).encode()
+            f.write_bytes(hdr + rec.tobytes())
+            files.append(str(f))
+    model = tmp_path / "svm_trained"
+    out = subprocess.run([str(exe), str(model), "150"] + files, capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-800:] + out.stderr[-400:]
+    assert "Finding point cloud clusters" in out.stdout and "Saved the training matrix" in out.stdout, out.stdout[-800:]
+    raw = np.fromfile(str(model) + ".train", np.uint8)
+    rows, cols = np.frombuffer(raw[:8].tobytes(), np.int32)
+    assert cols == 3528 and rows > 0 and rows % 3 == 0 and len(raw) == 8 + rows * cols * 4 + rows * 4
+    F = np.frombuffer(raw[8:8 + rows * cols * 4].tobytes(), np.float32).reshape(rows, cols)
+    y = np.frombuffer(raw[8 + rows * cols * 4:].tobytes(), np.float32)
+    assert set(np.unique(y)) <= {-1.0, 1.0} and np.isfinite(F).all() and (np.abs(F).sum(1) > 0).mean() > 0.5
+    assert f"# training examples: {rows}" in out.stdout
+    if len(np.unique(y)) == 2:
+        svm = cv2.ml.SVM_create()
+        svm.setType(cv2.ml.SVM_C_SVC)
+        svm.setKernel(cv2.ml.SVM_POLY)
+        svm.setDegree(2)
+        svm.setGamma(1.0)
+        svm.setCoef0(0.0)
+        svm.train(F, cv2.ml.ROW_SAMPLE, y.astype(np.int32))
+        svm.save(str(model))
+        m = api.Svm(str(model))
+        assert m.kernel == 1 and m.var_count == 3528 and m.sv_total >= 1
