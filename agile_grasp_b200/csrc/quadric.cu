@@ -237,6 +237,156 @@ k_ball_search(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr, c
   }
 }
 
+// ---- kernel 0+1 fused: radius search AND Taubin moments ------------------------------------------
+// The accepted points of the search are already in registers, so the 34 monomial moments are accumulated right
+// there instead of being streamed back from the neighbour lists by a second kernel (which made the lists' 16 B
+// per neighbour travel through HBM twice and cost a launch).  Same staging as k_ball_search — one TMA bulk copy
+// per x-row run, one mbarrier transaction count — then per step of 64 staged candidates: FLANN's binary32
+// membership test, ballot-compacted store of the accepted records to the neighbour list (the normal walks and
+// the pick ranking read it later), and 34 predicated binary64 fused multiply-adds per lane on coordinates centred
+// on the sample (a rejected candidate contributes exact zeros).  The 32 x 34 partial sums are transposed through
+// the staging buffer (two rounds of 16 moments, row pitch 33) and scaled by the power-of-two coordinate scale.
+constexpr int kFusedWarps = 4;
+__global__ void __launch_bounds__(kFusedWarps * 32, 4)
+k_ball_moments(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr, const int* __restrict__ col_ptr,
+               RowIndex* __restrict__ rip, const int* __restrict__ indices, int s0, int n_samples_max,
+               const int* __restrict__ d_count, float r2, double rpad, GPoint* __restrict__ pool, int stride,
+               int2* __restrict__ nn_counts, double scale, double* __restrict__ moments) {
+  __shared__ __align__(16) GPoint s_cand[kFusedWarps][kStageCap];
+  __shared__ __align__(8) unsigned long long s_bar[kFusedWarps];
+  static_assert(kStageCap * sizeof(GPoint) >= 16 * 33 * sizeof(double), "the reduction reuses the staging buffer");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sl = blockIdx.x * kFusedWarps + warp;  // slot of this launch
+  const int s = s0 + sl;
+  const RowIndex& ri = *rip;
+  if (s >= n_samples_max) return;
+  const int idx = s < *d_count ? indices[s] : -1;
+  if (idx < 0 || idx >= ri.n_points) {  // not a sample: an empty list
+    if (lane == 0) nn_counts[s] = make_int2(0, 0);
+    return;
+  }
+  const GPoint q = pts[idx];
+  const double qx = double(q.x), qy = double(q.y), qz = double(q.z);
+  const uint32_t cand_s = pin_u32(smem_u32(s_cand[warp])), bar = pin_u32(smem_u32(&s_bar[warp]));
+  const uint32_t lane_s = cand_s + uint32_t(lane) * 16u;
+  if (lane == 0) mbar_init(bar, 1);
+  fence_proxy_async_smem();
+  __syncwarp();
+  uint32_t parity = 0;
+  GPoint* out = pool + size_t(sl) * size_t(stride);
+  int n_cand = 0, n_out = 0, cam1 = 0;
+  const unsigned lt = (1u << lane) - 1u;
+  double acc[kNumMoments];  // acc[0] unused: the count is known
+#pragma unroll
+  for (int i = 0; i < kNumMoments; i++) acc[i] = 0.0;
+  auto accumulate = [&](const GPoint& p, bool ok) {
+    const double x = ok ? double(p.x) - qx : 0.0, y = ok ? double(p.y) - qy : 0.0, z = ok ? double(p.z) - qz : 0.0;
+    const double x2 = x * x, y2 = y * y, z2 = z * z, xy = x * y, yz = y * z, xz = x * z;
+    acc[1] += x; acc[2] += y; acc[3] += z;
+    acc[4] += x2; acc[5] += y2; acc[6] += z2; acc[7] += xy; acc[8] += yz; acc[9] += xz;
+    acc[10] += x2 * x; acc[11] += y2 * y; acc[12] += z2 * z; acc[13] += x2 * y; acc[14] += x2 * z;
+    acc[15] += x * y2; acc[16] += y2 * z; acc[17] += x * z2; acc[18] += y * z2; acc[19] += xy * z;
+    acc[20] += x2 * x2; acc[21] += y2 * y2; acc[22] += z2 * z2; acc[23] += x2 * xy; acc[24] += x2 * xz;
+    acc[25] += xy * y2; acc[26] += y2 * yz; acc[27] += xz * z2; acc[28] += yz * z2; acc[29] += x2 * y2;
+    acc[30] += y2 * z2; acc[31] += x2 * z2; acc[32] += x2 * yz; acc[33] += xy * yz; acc[34] += xz * yz;
+  };
+  int k_lo0 = 0, k_hi0 = -1, k_lo1 = 0, k_hi1 = -1;
+  if (ri.count[0] > 0) row_range(ri, 0, q.x, rpad, k_lo0, k_hi0);
+  if (ri.count[1] > 0) row_range(ri, 1, q.x, rpad, k_lo1, k_hi1);
+  const int nb0 = k_hi0 >= k_lo0 ? (k_hi0 - k_lo0) / 32 + 1 : 0;
+  const int nb1 = k_hi1 >= k_lo1 ? (k_hi1 - k_lo1) / 32 + 1 : 0;
+  for (int t = 0; t < nb0 + nb1; t++) {
+    const int c = t < nb0 ? 0 : 1;
+    const int kb = c ? k_lo1 + (t - nb0) * 32 : k_lo0 + t * 32;
+    const int k_hi = c ? k_hi1 : k_hi0;
+    const int nrows = min(32, k_hi - kb + 1);
+    int j_lo = 0, j_end = 0;
+    if (lane < nrows) row_run(ri, row_ptr, col_ptr, pts, c, kb + lane, q.x, q.y, rpad, j_lo, j_end);
+    int rem = max(0, j_end - j_lo);
+    n_cand += rem;
+    while (true) {
+      int incl = rem;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int total_rem = __shfl_sync(0xffffffffu, incl, 31);
+      if (total_rem == 0) break;
+      const int excl = incl - rem;
+      const int take = min(rem, max(0, kStageCap - excl));
+      const int total = min(total_rem, kStageCap);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_expect_tx(bar, uint32_t(total) * 16u);
+      __syncwarp();
+      if (take > 0) bulk_g2s(cand_s + uint32_t(excl) * 16u, pts + j_lo, uint32_t(take) * 16u, bar);
+      j_lo += take;
+      rem -= take;
+      mbar_wait(bar, parity);
+      parity ^= 1u;
+      for (int base = 0; base < total; base += 64) {
+        GPoint p0 = q, p1 = q;  // padding = the sample itself: distance 0 but masked out below
+        const bool in0 = base + lane < total, in1 = base + lane + 32 < total;
+        if (in0) p0 = lds_point(lane_s + uint32_t(base) * 16u);
+        if (in1) p1 = lds_point(lane_s + uint32_t(base) * 16u + 512u);
+        const bool ok0 = in0 && dist2_flann(q.x, q.y, q.z, p0.x, p0.y, p0.z) < r2;
+        const bool ok1 = in1 && dist2_flann(q.x, q.y, q.z, p1.x, p1.y, p1.z) < r2;
+        const unsigned m0 = __ballot_sync(0xffffffffu, ok0), m1 = __ballot_sync(0xffffffffu, ok1);
+        const int w0 = n_out + __popc(m0 & lt), w1 = n_out + __popc(m0) + __popc(m1 & lt);
+        if (ok0 && w0 < stride) out[w0] = p0;
+        if (ok1 && w1 < stride) out[w1] = p1;
+        n_out += __popc(m0) + __popc(m1);
+        accumulate(p0, ok0);
+        accumulate(p1, ok1);
+        cam1 += (ok0 ? int(p0.tag & kTagCamBit) : 0) + (ok1 ? int(p1.tag & kTagCamBit) : 0);
+      }
+      __syncwarp();
+    }
+  }
+  n_cand = __reduce_add_sync(0xffffffffu, n_cand);
+  cam1 = __reduce_add_sync(0xffffffffu, cam1);
+  // warp reduction of the 34 moments through the (now idle) staging buffer: two rounds of 16 with a 33-double row
+  // pitch; lane i sums half (i >> 4) of row (i & 15), the halves meet by one exchange
+  const double s2 = scale * scale, s4 = s2 * s2;
+  const int mj = lane + 1;  // the moment this lane writes
+  const double scl = mj <= 3 ? scale : mj <= 9 ? s2 : mj <= 19 ? s2 * scale : s4;
+  const uint32_t row_s = cand_s + uint32_t(lane & 15) * (33u * 8u) + uint32_t(lane >> 4) * (16u * 8u);
+  double r01[2];
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 16; j++) sts_f64(cand_s + uint32_t(j * 33) * 8u + uint32_t(lane) * 8u, acc[1 + 16 * r + j]);
+    __syncwarp();
+    double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+      t0 += lds_f64(row_s + uint32_t(k) * 8u);
+      t1 += lds_f64(row_s + uint32_t(k + 1) * 8u);
+    }
+    const double tt = t0 + t1;
+    r01[r] = tt + __shfl_xor_sync(0xffffffffu, tt, 16);
+  }
+  const double mom = lane < 16 ? r01[0] : r01[1];
+  const double m33 = warp_sum(acc[33]), m34 = warp_sum(acc[34]);
+  const int n_list = min(n_out, stride);
+  if (n_list > 0) {
+    double* mo = moments + size_t(s) * kMomentStride;
+    mo[mj] = mom * scl;  // moments 1..32
+    if (lane == 0) {
+      mo[0] = double(n_list);
+      mo[33] = m33 * s4;
+      mo[34] = m34 * s4;
+      mo[35] = double(cam1);
+    }
+  }
+  if (lane == 0) {
+    nn_counts[s] = make_int2(n_list, n_cand);
+    if (n_out > stride) atomicOr(&rip->error, kErrBallOverflow);
+  }
+}
+
 // ---- kernel 1: moments ------------------------------------------------------------------------
 // Roofline-graded kernel: streams each sample's neighbour list (16 B per neighbour, contiguous) and
 // accumulates the 34 monomial moments of degree 1..4 in binary64.  Persistent warps (one CTA slot per SM
@@ -1337,6 +1487,7 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_ball_search, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_ball_moments, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(k_rank_picks<kRankCap>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          int(kWarps * (kRankCap * 6 + kRankBuckets * 4)));
     cudaFuncSetAttribute(k_rank_picks<1024>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -1369,15 +1520,30 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
     d_rand_off = c->rand_off.as<int>();
     c->rand_consumed_bound += n;
   }
+  // search + moments: ONE kernel for launches of a few thousand samples (latency bound: 23.7 vs 26 us at 2000
+  // samples), search -> neighbour lists -> streaming moments kernel for launches that fill the machine (the fused
+  // kernel needs 128 registers = 16 warps/SM and hides its load latencies worse: 0.27 vs 0.24 ms at 82k samples).
+  // AG_MOMENTS=split|fused forces one variant (measurements).
+  static const int forced_variant = [] {
+    const char* e = getenv("AG_MOMENTS");
+    return !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'f' ? 2 : 0));
+  }();
   for (int s0 = 0; s0 < n; s0 += chunk) {
     const int m = std::min(chunk, n - s0);
+    const bool split = forced_variant ? forced_variant == 1 : m > 16384;
     const int blocks = (m + kWarps - 1) / kWarps;
     const bool timed = s0 == 0;  // ag_timings reports the kernels of the first chunk
     if (timed) record_event(c, c->ev_k[0]);
-    k_ball_search<<<blocks, kWarps * 32, 0, c->stream>>>(c->vox.as<GPoint>(), c->row_ptr.as<int>(),
-                                                         c->col_ptr.as<int>(), ri, d_indices, s0, s0 + m, d_count, r2,
-                                                         rpad, c->nbr_pool.as<GPoint>(), stride,
-                                                         c->nn_counts.as<int2>(), c->nbr_heads.as<float4>());
+    if (split)
+      k_ball_search<<<blocks, kWarps * 32, 0, c->stream>>>(c->vox.as<GPoint>(), c->row_ptr.as<int>(),
+                                                           c->col_ptr.as<int>(), ri, d_indices, s0, s0 + m, d_count, r2,
+                                                           rpad, c->nbr_pool.as<GPoint>(), stride,
+                                                           c->nn_counts.as<int2>(), c->nbr_heads.as<float4>());
+    else
+      k_ball_moments<<<blocks, kFusedWarps * 32, 0, c->stream>>>(c->vox.as<GPoint>(), c->row_ptr.as<int>(),
+                                                                 c->col_ptr.as<int>(), ri, d_indices, s0, s0 + m, d_count,
+                                                                 r2, rpad, c->nbr_pool.as<GPoint>(), stride,
+                                                                 c->nn_counts.as<int2>(), inv_r, c->moments.as<double>());
     if (timed) record_event(c, c->ev_k[1]);
     if (rand_mode) {
       // the reference's rand() % n picks depend on the neighbour lists only: ranked on a second stream while
@@ -1397,7 +1563,7 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
       AG_CUDA_CHECK(cudaEventRecord(c->ev_join, c->stream2));
       c->launches += 2;
     }
-    {
+    if (split) {
       // warps per sample.  Measured on B200: a 2000-sample launch takes 10.2 / 11.3 / 14.3 us with 1 / 2 / 4 warps
       // per sample — it is bounded by fixed costs (launch, first-touch latencies, reduction), not by one warp
       // walking a whole list — so teams are only used when asked for (AG_MOM_WPS = 2 | 4, a tuning knob).
@@ -1425,7 +1591,7 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
         h.cam[0][2], h.cam[1][0], h.cam[1][1], h.cam[1][2], d_frames, write_normals ? c->normals.as<double>() : nullptr,
         rand_mode ? c->picks.as<unsigned short>() : nullptr);
     if (timed) record_event(c, c->ev_k[3]);
-    c->launches += 4;
+    c->launches += split ? 4 : 3;
   }
   k_quadric_finish<<<(n + 255) / 256, 256, 0, c->stream>>>(c->vox.as<GPoint>(), ri, d_indices, n, d_count,
                                                           c->nn_counts.as<int2>(), ctr, write_normals ? 1 : 0);
