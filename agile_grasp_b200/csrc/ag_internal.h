@@ -129,6 +129,7 @@ struct Ctx {
   bool gather_connected = false;
   // samples
   DevBuf samples, sample_stage, moments, frames, nn_counts, all_frames;
+  DevBuf samples_all, nn_counts_all, count_all;  // sharded call in the production normal mode: the full sample list
   // CUDA graph of the localize pipeline (second call with the same shapes captures, later calls replay)
   // state between localize_begin and localize_end
   bool pend_active = false;
@@ -190,8 +191,15 @@ int fetch_cloud_size(Ctx* c);  // waits for the stream and reads the voxel count
 int set_cloud_device(Ctx* c, int n);  // cloud already in c->vox (ag_set_cloud)
 int set_normals_device(Ctx* c, const double* h_normals);  // cloud_normals_ supplied by the caller
 // d_count: device int holding the number of valid entries of d_indices (<= n, the launch bound)
+// a context that fits only a share of a call's samples (sample sharding) in the production normal mode: the full
+// sample list, so that the rand() stream is sliced as in the unsharded call; this share = first + j * step
+struct RandShare {
+  const int* d_all;          // device: all sample indices of the call
+  const int* d_count_all;    // device int: how many of them are valid
+  int n_all, first, step;
+};
 int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count, double radius, ag_frame* d_frames,
-                        bool write_normals);
+                        bool write_normals, const RandShare* share = nullptr);
 // restarts the rand() stream of the non-deterministic normal mode (start of every ag_localize / ag_fit_quadrics)
 int quadric_rand_reset(Ctx* c);
 // enqueue only (no sync): sweep + stable compaction; the hypothesis count stays in device memory

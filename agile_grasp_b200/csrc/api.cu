@@ -81,11 +81,12 @@ __host__ __device__ static inline uint64_t splitmix64(uint64_t x) {
 }
 // seeded stratified draw: sample k of S lies in [k n / S, (k + 1) n / S).  A shard handles the samples
 // k = k_first + j k_step, j < count (count = launch bound; k_first = 0, k_step = 1 and count = s_req without sharding).
-__global__ void k_draw_samples(RowIndex* ri, int s_req, uint64_t seed, int* out, int k_first, int k_step, int count) {
+__global__ void k_draw_samples(RowIndex* ri, int s_req, uint64_t seed, int* out, int k_first, int k_step, int count,
+                               int set_count = 1) {
   const int n = ri->n_points;
   const int S = s_req < n ? s_req : n;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j == 0) ri->n_samples = S > k_first ? min((S - k_first + k_step - 1) / k_step, count) : 0;
+  if (j == 0 && set_count) ri->n_samples = S > k_first ? min((S - k_first + k_step - 1) / k_step, count) : 0;
   if (j >= count) return;
   const int k = k_first + j * k_step;
   if (k >= S) {
@@ -525,6 +526,7 @@ static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, in
   cudaStream_t st = c->stream;
   c->two_cams = size_left < n_in;
   const bool given = indices && n_indices > 0;
+  const int* const indices_all = indices;
   const int S_total = given ? n_indices : std::max(0, c->params.num_samples);
   // sample sharding (ag_params.shard_index / shard_count): this context's share of the samples — a contiguous
   // range, or (shard_interleave) every shard_count-th sample, which balances scenes whose hypotheses cluster
@@ -548,6 +550,15 @@ static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, in
       indices += k_lo;
     }
     if (S > 0) AG_CUDA_CHECK(cudaMemcpyAsync(c->sample_stage.p, indices, size_t(S) * 4, cudaMemcpyHostToDevice, st));
+  }
+  // a share of the samples in the production normal mode: the whole sample list is needed once more, to slice the
+  // reference's rand() stream exactly as the unsharded call does (fit_quadrics_device, RandShare)
+  const bool rand_share = sh_n > 1 && c->params.deterministic_normals == 0 && S_total > 0;
+  if (rand_share) {
+    if (c->samples_all.reserve(size_t(S_total) * 4) || c->count_all.reserve(16)) return AG_ERR_CUDA;
+    AG_CUDA_CHECK(cudaMemcpyAsync(c->count_all.p, &S_total, 4, cudaMemcpyHostToDevice, st));
+    if (given)
+      AG_CUDA_CHECK(cudaMemcpyAsync(c->samples_all.p, indices_all, size_t(S_total) * 4, cudaMemcpyHostToDevice, st));
   }
   int* d_nsel = nullptr;
   // Everything from the voxelisation to the scoring: ~25 launches without a host dependency.  The second call
@@ -589,8 +600,18 @@ static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, in
       k_draw_samples<<<(S + 255) / 256, 256, 0, st>>>(ri, S_total, c->params.seed, c->samples.as<int>(), k_first, k_step, S);
     }
     c->launches += 1;
+    RandShare share;
+    if (rand_share) {
+      if (!given)  // (the full draw first: the share's own draw below leaves its count in ri->n_samples)
+        k_draw_samples<<<(S_total + 255) / 256, 256, 0, st>>>(ri, S_total, c->params.seed, c->samples_all.as<int>(), 0, 1, S_total, 0);
+      share.d_all = c->samples_all.as<int>();
+      share.d_count_all = c->count_all.as<int>();
+      share.n_all = S_total;
+      share.first = k_first;
+      share.step = k_step;
+    }
     rc = fit_quadrics_device(c, c->samples.as<int>(), S, &ri->n_samples, c->params.nn_radius_taubin,
-                             c->frames.as<ag_frame>(), true);
+                             c->frames.as<ag_frame>(), true, rand_share ? &share : nullptr);
     if (rc) return rc;
     record_event(c, c->ev[5]);
     rc = hand_sweep_enqueue(c, c->samples.as<int>(), S, c->frames.as<ag_frame>(),
@@ -912,7 +933,7 @@ void ag_destroy(ag_ctx* h) {
   if (c.h_out) cudaFreeHost(c.h_out);
   for (DevBuf* b : {&c.raw, &c.keys, &c.keys_sorted, &c.keys_unique, &c.cub_tmp, &c.block_counts, &c.misc, &c.bitmap, &c.tile_state, &c.vox,
                     &c.row_ptr, &c.col_ptr, &c.row_index, &c.all_frames,
-                    &c.normals, &c.samples, &c.sample_stage, &c.moments, &c.frames, &c.nn_counts, &c.nbr_pool, &c.nbr_heads, &c.rand_raw, &c.rand_off, &c.rand_carry, &c.picks, &c.quad_par, &c.grasps_raw, &c.valid,
+                    &c.normals, &c.samples, &c.sample_stage, &c.samples_all, &c.nn_counts_all, &c.count_all, &c.moments, &c.frames, &c.nn_counts, &c.nbr_pool, &c.nbr_heads, &c.rand_raw, &c.rand_off, &c.rand_carry, &c.picks, &c.quad_par, &c.grasps_raw, &c.valid,
                     &c.images_raw, &c.hyp_slots, &c.grasps, &c.counters, &c.scores, &c.descriptors, &c.kvals, &c.handle_in, &c.handle_bits, &c.sweep_dbg, &c.overflow})
     b->release();
   if (c.h_pinned) cudaFreeHost(c.h_pinned);

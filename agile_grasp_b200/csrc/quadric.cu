@@ -143,6 +143,7 @@ __device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
 // (distance, index) order except through explicit tie-breaks.
 constexpr int kStageCap = 384;  // candidates staged per pass and warp (6 KB); bigger balls take more passes
 
+template <bool WRITE>  // WRITE = false: neighbour counts only (no lists)
 __global__ void __launch_bounds__(kWarps * 32, 8)
 k_ball_search(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr, const int* __restrict__ col_ptr,
               RowIndex* __restrict__ rip, const int* __restrict__ indices, int s0, int n_samples_max,
@@ -159,7 +160,7 @@ k_ball_search(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr, c
   if (idx < 0 || idx >= ri.n_points) {  // not a sample: an empty list
     if (lane == 0) {
       nn_counts[s] = make_int2(0, 0);
-      heads[sl] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+      if (WRITE) heads[sl] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
     }
     return;
   }
@@ -222,8 +223,8 @@ k_ball_search(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr, c
         const bool ok1 = dist2_flann(q.x, q.y, q.z, p1.x, p1.y, p1.z) < r2;
         const unsigned m0 = __ballot_sync(0xffffffffu, ok0), m1 = __ballot_sync(0xffffffffu, ok1);
         const int w0 = n_out + __popc(m0 & lt), w1 = n_out + __popc(m0) + __popc(m1 & lt);
-        if (ok0 && w0 < stride) out[w0] = p0;
-        if (ok1 && w1 < stride) out[w1] = p1;
+        if (WRITE && ok0 && w0 < stride) out[w0] = p0;
+        if (WRITE && ok1 && w1 < stride) out[w1] = p1;
         n_out += __popc(m0) + __popc(m1);
       }
       __syncwarp();
@@ -232,8 +233,8 @@ k_ball_search(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr, c
   n_cand = __reduce_add_sync(0xffffffffu, n_cand);
   if (lane == 0) {
     nn_counts[s] = make_int2(min(n_out, stride), n_cand);
-    heads[sl] = make_float4(q.x, q.y, q.z, __int_as_float(min(n_out, stride)));  // what the moments kernel needs
-    if (n_out > stride) atomicOr(&rip->error, kErrBallOverflow);
+    if (WRITE) heads[sl] = make_float4(q.x, q.y, q.z, __int_as_float(min(n_out, stride)));  // what the moments kernel needs
+    if (WRITE && n_out > stride) atomicOr(&rip->error, kErrBallOverflow);
   }
 }
 
@@ -1076,7 +1077,7 @@ __global__ void __launch_bounds__(kWarps * 32, 8)
 k_rank_picks(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip, const int* __restrict__ indices,
              int s0, int n_samples_max, const int* __restrict__ d_count, const GPoint* __restrict__ pool, int stride,
              const int2* __restrict__ nn_counts, float r2_f, const uint32_t* __restrict__ rand_raw,
-             const int* __restrict__ rand_off, unsigned short* __restrict__ picks_out) {
+             const int* __restrict__ rand_off, int off_first, int off_step, unsigned short* __restrict__ picks_out) {
   extern __shared__ __align__(16) unsigned char s_rank[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sl = blockIdx.x * kWarps + warp;
@@ -1153,7 +1154,7 @@ k_rank_picks(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip,
     }
   }
   __syncwarp();
-  const uint32_t* raw = rand_raw + size_t(50) * size_t(rand_off[s]);
+  const uint32_t* raw = rand_raw + size_t(50) * size_t(rand_off[off_first + s * off_step]);
 #pragma unroll
   for (int u = 0; u < 2; u++) {
     const int t = lane + 32 * u;
@@ -1465,7 +1466,7 @@ int quadric_rand_reset(Ctx* c) {
 }
 
 int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count, double radius, ag_frame* d_frames,
-                        bool write_normals) {
+                        bool write_normals, const RandShare* share) {
   if (n <= 0) return AG_OK;
   const int stride = ball_stride(radius, c->params.voxel_size, c->two_cams);
   // samples are processed in chunks whose neighbour pool stays below kPoolBytes (one chunk for every
@@ -1486,7 +1487,7 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
   RowIndex* ri = c->row_index.as<RowIndex>();
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_ball_search, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_ball_search<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(k_ball_moments, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(k_rank_picks<kRankCap>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          int(kWarps * (kRankCap * 6 + kRankBuckets * 4)));
@@ -1505,7 +1506,7 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
   const uint32_t* d_rand = nullptr;
   int* d_rand_off = nullptr;
   if (rand_mode) {
-    const size_t need = size_t(50) * (size_t(c->rand_consumed_bound) + size_t(n));
+    const size_t need = size_t(50) * (size_t(c->rand_consumed_bound) + size_t(share ? std::max(share->n_all, n) : n));
     if (c->rand_count < need) {
       std::vector<uint32_t> hs;
       glibc_rand_stream(need + need / 2, hs);
@@ -1514,11 +1515,25 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
       AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
       c->rand_count = hs.size();
     }
-    if (c->rand_off.reserve(size_t(n) * 4 + 16) || c->rand_carry.reserve(16) || c->picks.reserve(size_t(n) * 100))
+    const int n_off = share ? std::max(share->n_all, n) : n;
+    if (c->rand_off.reserve(size_t(n_off) * 4 + 16) || c->rand_carry.reserve(16) || c->picks.reserve(size_t(n) * 100) ||
+        (share && c->nn_counts_all.reserve(size_t(share->n_all) * 8)))
       return AG_ERR_CUDA;
     d_rand = c->rand_raw.as<uint32_t>();
     d_rand_off = c->rand_off.as<int>();
-    c->rand_consumed_bound += n;
+    c->rand_consumed_bound += share ? std::max(share->n_all, n) : n;
+  }
+  if (rand_mode && share) {
+    // This context fits a SHARE of the call's samples (ag_params.shard_*), but the reference's rand() stream is
+    // consumed by every sample with more than 50 neighbours in sample order: count the neighbours of ALL samples
+    // (no lists), so that each of this share's samples finds the slice of the stream the unsharded call gives it
+    const int blocks_all = (share->n_all + kWarps - 1) / kWarps;
+    k_ball_search<false><<<blocks_all, kWarps * 32, 0, c->stream>>>(
+        c->vox.as<GPoint>(), c->row_ptr.as<int>(), c->col_ptr.as<int>(), c->row_index.as<RowIndex>(), share->d_all, 0,
+        share->n_all, share->d_count_all, r2, rpad, nullptr, stride, c->nn_counts_all.as<int2>(), nullptr);
+    k_rand_offsets<<<1, 1024, 0, c->stream>>>(c->nn_counts_all.as<int2>(), 0, share->n_all, share->d_count_all, d_rand_off,
+                                              c->rand_carry.as<int>());
+    c->launches += 2;
   }
   // search + moments: ONE kernel for launches of a few thousand samples (latency bound: 23.7 vs 26 us at 2000
   // samples), search -> neighbour lists -> streaming moments kernel for launches that fill the machine (the fused
@@ -1535,7 +1550,7 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
     const bool timed = s0 == 0;  // ag_timings reports the kernels of the first chunk
     if (timed) record_event(c, c->ev_k[0]);
     if (split)
-      k_ball_search<<<blocks, kWarps * 32, 0, c->stream>>>(c->vox.as<GPoint>(), c->row_ptr.as<int>(),
+      k_ball_search<true><<<blocks, kWarps * 32, 0, c->stream>>>(c->vox.as<GPoint>(), c->row_ptr.as<int>(),
                                                            c->col_ptr.as<int>(), ri, d_indices, s0, s0 + m, d_count, r2,
                                                            rpad, c->nbr_pool.as<GPoint>(), stride,
                                                            c->nn_counts.as<int2>(), c->nbr_heads.as<float4>());
@@ -1550,16 +1565,18 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
       // this one accumulates the moments and solves the eigenproblem (fork / join by events, also under capture)
       AG_CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
       AG_CUDA_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-      k_rand_offsets<<<1, 1024, 0, c->stream2>>>(c->nn_counts.as<int2>(), s0, m, d_count, d_rand_off, c->rand_carry.as<int>());
+      if (!share)
+        k_rand_offsets<<<1, 1024, 0, c->stream2>>>(c->nn_counts.as<int2>(), s0, m, d_count, d_rand_off, c->rand_carry.as<int>());
+      const int off_first = share ? share->first : 0, off_step = share ? share->step : 1;
       const size_t rank_smem = size_t(kWarps) * (size_t(stride <= 1024 ? 1024 : kRankCap) * 6 + kRankBuckets * 4);
       if (stride <= 1024)
         k_rank_picks<1024><<<blocks, kWarps * 32, rank_smem, c->stream2>>>(
             c->vox.as<GPoint>(), ri, d_indices, s0, s0 + m, d_count, c->nbr_pool.as<GPoint>(), stride,
-            c->nn_counts.as<int2>(), r2, d_rand, d_rand_off, c->picks.as<unsigned short>());
+            c->nn_counts.as<int2>(), r2, d_rand, d_rand_off, off_first, off_step, c->picks.as<unsigned short>());
       else
         k_rank_picks<kRankCap><<<blocks, kWarps * 32, rank_smem, c->stream2>>>(
             c->vox.as<GPoint>(), ri, d_indices, s0, s0 + m, d_count, c->nbr_pool.as<GPoint>(), stride,
-            c->nn_counts.as<int2>(), r2, d_rand, d_rand_off, c->picks.as<unsigned short>());
+            c->nn_counts.as<int2>(), r2, d_rand, d_rand_off, off_first, off_step, c->picks.as<unsigned short>());
       AG_CUDA_CHECK(cudaEventRecord(c->ev_join, c->stream2));
       c->launches += 2;
     }

@@ -594,15 +594,19 @@ def test_sample_sharding_concatenates_to_the_unsharded_list(ctx, small_scene, li
     ctx.set_svm(svm)
     fields = [f for f in GRASP_FIELDS if f != "image_id"]
     try:
+      for det in (1, 0):  # both normal modes: in the production mode every shard slices the reference's rand() stream
+        # exactly as the unsharded call does (the neighbour counts of ALL samples decide who draws)
+        base = copy.copy(s["P"])
+        base.deterministic_normals = det
         for idx in (None, s["idx"]):
-            ctx.set_params(s["P"])
+            ctx.set_params(base)
             full = ctx.localize(s["pts"], s["size_left"], idx)
             assert (np.diff(full["sample_slot"]) >= 0).all()
             for world in (2, 3):
                 for interleave in (0, 1):
                     parts = []
                     for r in range(world):
-                        P = copy.copy(s["P"])
+                        P = copy.copy(base)
                         P.shard_index, P.shard_count, P.shard_interleave = r, world, interleave
                         ctx.set_params(P)
                         parts.append(ctx.localize(s["pts"], s["size_left"], idx))

