@@ -254,7 +254,7 @@ class Context:
         return it): (n_hyp per rank, merged records from the mapped host copy, device address of the merged list)"""
         n = (C.c_int32 * self._gather_world)()
         tot, dptr, hptr = C.c_int(), C.c_void_p(), C.c_void_p()
-        _check(lib().ag_gather_result(self.h, n, C.byref(tot), C.byref(dptr), C.byref(hptr)))
+        _check(lib().ag_gather_result(self.h, n, C.byref(tot), C.byref(dptr), C.byref(hptr) if copy else None))
         recs = None
         if copy:
             if tot.value == 0:

@@ -118,7 +118,8 @@ struct Ctx {
   void* gather_merged = nullptr;      // merged list of all ranks (device), in the reference's sample-major order
   void* gather_host = nullptr;        // mapped host copy: GatherHost header + merged records
   void* gather_host_dev = nullptr;
-  int gather_cap_total = 0;
+  int gather_cap_total = 0, gather_rec_cap = 0, gather_mask_cap = 0, gather_plan_cap = 0;
+  void* gather_plan = nullptr;        // layout of the merged list (k_gather_plan -> k_gather_place)
   bool gather_pending = false;        // a merge of this call is in the stream
   bool gather_valid = false;          // gather_host describes the last completed call
   int pend_slot_first = 0, pend_slot_step = 1;  // position of this context's samples in the full sample list
@@ -135,7 +136,7 @@ struct Ctx {
   bool pend_active = false;
   int pend_S = 0;
   int* pend_nsel = nullptr;
-  alignas(8) unsigned char pend_peer[128];
+  alignas(8) unsigned char pend_peer[192];
   unsigned long long batch_parent_gen = ~0ull;  // child lane of ag_localize_batch: parent state it mirrors
   GraphSlot gslots[4];
   unsigned long long g_tick = 0, state_gen = 0;

@@ -127,7 +127,7 @@ struct HostOut {
 // list to mapped host memory, to the device copy used by ag_classify / ag_get_*, and to the optional
 // caller-registered device buffer.
 // Peer gather (ag_gather_*): slot `rank` of every rank's gather buffer, reached over NVLink through CUDA IPC
-// mappings.  Slot layout: [uint32 epoch flag, 12 pad][int32 n_hyp, n_vox, n_samples, error][records].
+// mappings.  Slot layout: [uint32 epoch flag, int32 first, step, pad][int32 n_hyp, n_vox, n_samples, error][records][masks].
 struct PeerOut {
   char* slot[AG_MAX_GATHER_RANKS];
   const unsigned* ack;  // this rank's ack words (one per consumer, kAckStride bytes apart): last epoch it has consumed
@@ -136,6 +136,13 @@ struct PeerOut {
   unsigned epoch;
   unsigned* done;    // CTA completion counter of this launch (device, zeroed by the last CTA)
   int final_pass;    // 0: first export of a call (publishes only if no sample needs the large-slab re-run)
+  // per-sample masks of the valid orientations (one byte per local sample, behind the records of the slot): with
+  // them a consumer places every record of a sharded call by a prefix sum instead of searching the other lists
+  size_t mask_off;   // byte offset of the mask area inside a slot
+  int mask_cap;      // bytes of the mask area
+  const uint8_t* valid;  // [local samples x 8] valid flags of this call
+  int n_local;       // local samples (launch bound)
+  int first, step;   // position of local sample j in the full sample list: first + j * step
 };
 constexpr int kAckStride = 64;                                    // bytes between the ack words of two consumers
 constexpr int kAckBytes = AG_MAX_GATHER_RANKS * kAckStride;       // ack area in front of the slots of a gather buffer
@@ -187,6 +194,25 @@ __global__ void k_export(const ag_grasp* __restrict__ raw, const int* __restrict
       for (int r = 0; r < peer.world; r++)
         reinterpret_cast<uint4*>(peer.slot[r] + kSlotHeaderBytes + size_t(i) * sizeof(ag_grasp))[part] = v;
   }
+  if (peer.world > 0 && peer.valid) {
+    // valid-orientation mask of every local sample -> every rank's slot (16 masks per 16-byte store)
+    const int n_s = min(ri->n_samples, min(peer.n_local, peer.mask_cap));
+    for (int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16; j0 < n_s; j0 += gridDim.x * blockDim.x * 16) {
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      for (int t = 0; t < 16 && j0 + t < n_s; t++) {
+        const uint2 v = *reinterpret_cast<const uint2*>(peer.valid + size_t(j0 + t) * 8);
+        uint32_t m = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          m |= ((v.x >> (8 * k)) & 0xFFu ? 1u : 0u) << k;
+          m |= ((v.y >> (8 * k)) & 0xFFu ? 1u : 0u) << (4 + k);
+        }
+        w[t >> 2] |= m << (8 * (t & 3));
+      }
+      for (int r = 0; r < peer.world; r++)
+        *reinterpret_cast<uint4*>(peer.slot[r] + peer.mask_off + j0) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
   if (peer.world > 0) {
     // publish: every CTA fences its peer stores; the last one to finish writes the headers, fences again and
     // raises the epoch flags the consumers (k_gather_merge on each rank) spin on
@@ -197,6 +223,9 @@ __global__ void k_export(const ag_grasp* __restrict__ raw, const int* __restrict
     __syncthreads();
     if (s_last) {
       if (threadIdx.x < peer.world && (peer.final_pass || overflow[0] == 0)) {
+        int* h0 = reinterpret_cast<int*>(peer.slot[threadIdx.x]);
+        h0[1] = peer.first;
+        h0[2] = peer.step;
         int* h4 = reinterpret_cast<int*>(peer.slot[threadIdx.x] + 16);
         h4[0] = min(n, peer.cap);
         h4[1] = ri->n_points;
@@ -237,30 +266,45 @@ struct GatherHost {  // mapped host header of the merged list
 };
 struct MergeArgs {
   const char* buf;         // this epoch's slots of this rank's gather buffer
-  size_t slot_bytes;
+  size_t slot_bytes, mask_off;
   unsigned* ack_peer[AG_MAX_GATHER_RANKS];  // producer p's ack word for this consumer
   int world;
   unsigned epoch;
   const int* overflow;     // [0] != 0: this rank's own list is re-exported after a host-side re-run -> skip this pass
   int final_pass;
   ag_grasp* merged_dev;
-  ag_grasp* merged_host;
   GatherHost* host;
   int cap_total;
   unsigned* done;
+  int* plan;               // device: [0] mode (1 = shards of one call), [1] total, [2] skip, [4 + r] n_r, [12 + r] first_r,
+                           // [20 + r] offset of list r in rank-major order, [28 + r] err_r; [64 ...] base[k] of every sample
+  int plan_cap;            // entries available for base[]
 };
-__device__ __forceinline__ long long grasp_key(const ag_grasp* g) {
-  return (static_cast<long long>(g->sample_slot) << 3) | static_cast<long long>(g->orientation & 7);
-}
-__global__ void __launch_bounds__(256)
-k_gather_merge(const MergeArgs A) {
-  __shared__ int s_n[AG_MAX_GATHER_RANKS], s_err[AG_MAX_GATHER_RANKS], s_bad;
-  __shared__ bool s_last;
-  if (!A.final_pass && A.overflow[0] != 0) return;
-  if (threadIdx.x == 0) s_bad = 0;
+constexpr int kPlanBase = 64;
+
+// Consumer side of the peer gather, kernel 1 (one CTA): waits until every rank's list of this epoch has landed,
+// reads the headers and lays out the merged list.  Shards of one call (every rank reports the same stride = world
+// and its own offset): the merged list is in the reference's order (sample-major, orientation-minor:
+// hand_search.cpp:194-200), so base[k] = number of hypotheses of the samples in front of sample k — a prefix sum
+// over the valid-orientation masks that came with the lists.  Independent calls (weak scaling): rank-major.
+__global__ void __launch_bounds__(1024)
+k_gather_plan(const MergeArgs A) {
+  __shared__ int s_n[AG_MAX_GATHER_RANKS], s_err[AG_MAX_GATHER_RANKS], s_first[AG_MAX_GATHER_RANKS], s_step[AG_MAX_GATHER_RANKS],
+      s_ns[AG_MAX_GATHER_RANKS];
+  __shared__ int s_bad, s_warp[32], s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (!A.final_pass && A.overflow[0] != 0) {
+    if (tid == 0) A.plan[2] = 1;  // skip: the re-export after the host-side re-run brings the final list
+    return;
+  }
+  if (tid == 0) {
+    s_bad = 0;
+    s_carry = 0;
+    A.plan[2] = 0;
+  }
   __syncthreads();
-  if (threadIdx.x < A.world) {
-    const int r = threadIdx.x;
+  if (tid < A.world) {
+    const int r = tid;
     const volatile unsigned* flag = reinterpret_cast<const volatile unsigned*>(A.buf + size_t(r) * A.slot_bytes);
     const long long t0 = clock64();
     bool ok = true;
@@ -269,71 +313,122 @@ k_gather_merge(const MergeArgs A) {
         ok = false;
         break;
       }
-      __nanosleep(100);
+      __nanosleep(64);
     }
     __threadfence_system();
-    const volatile int* h4 = reinterpret_cast<const volatile int*>(A.buf + size_t(r) * A.slot_bytes + 16);
-    s_n[r] = ok ? h4[0] : 0;
-    s_err[r] = ok ? h4[3] : 0x200;
+    const volatile int* h0 = reinterpret_cast<const volatile int*>(A.buf + size_t(r) * A.slot_bytes);
+    s_first[r] = ok ? h0[1] : 0;
+    s_step[r] = ok ? h0[2] : 0;
+    s_n[r] = ok ? h0[4] : 0;
+    s_ns[r] = ok ? h0[6] : 0;
+    s_err[r] = ok ? h0[7] : 0x200;
     if (!ok) atomicOr(&s_bad, 1);
   }
   __syncthreads();
-  int total = 0;
-  for (int r = 0; r < A.world; r++) total += s_n[r];
-  // one record per 10 lanes (16 bytes each), three records per warp pass
+  // shards of one call?  every rank strides by `world` and the offsets are a permutation of 0 .. world - 1
+  bool sharded = A.world > 1;
+  unsigned seen = 0;
+  int total = 0, n_samples_all = 0;
+  for (int r = 0; r < A.world; r++) {
+    sharded = sharded && s_step[r] == A.world && s_first[r] >= 0 && s_first[r] < A.world;
+    if (s_first[r] >= 0 && s_first[r] < 32) seen |= 1u << s_first[r];
+    total += s_n[r];
+    if (s_ns[r] > 0) n_samples_all = max(n_samples_all, s_first[r] + (s_ns[r] - 1) * A.world + 1);
+  }
+  sharded = sharded && seen == (A.world >= 32 ? 0xFFFFFFFFu : (1u << A.world) - 1u) && n_samples_all <= A.plan_cap;
+  if (tid == 0) {
+    A.plan[0] = sharded ? 1 : 0;
+    A.plan[1] = total;
+    int off = 0;
+    for (int r = 0; r < A.world; r++) {
+      A.plan[4 + r] = s_n[r];
+      A.plan[12 + r] = s_first[r];
+      A.plan[20 + r] = off;
+      A.plan[28 + r] = s_err[r];
+      off += s_n[r];
+    }
+    A.host->n_total = min(total, A.cap_total);
+    A.host->world = A.world;
+    A.host->status = s_bad | (total > A.cap_total ? 2 : 0);
+    for (int r = 0; r < A.world; r++) {
+      A.host->n_per_rank[r] = s_n[r];
+      A.host->err_per_rank[r] = s_err[r];
+    }
+  }
+  if (!sharded) return;
+  // rank owning sample k: the one whose offset is k mod world
+  __shared__ int s_owner[AG_MAX_GATHER_RANKS];
+  if (tid < A.world) s_owner[s_first[tid]] = tid;
+  __syncthreads();
+  for (int base = 0; base < n_samples_all; base += 1024) {
+    const int k = base + tid;
+    int cnt = 0;
+    if (k < n_samples_all) {
+      const int r = s_owner[k % A.world], j = k / A.world;
+      cnt = j < s_ns[r] ? __popc(unsigned(*reinterpret_cast<const volatile uint8_t*>(A.buf + size_t(r) * A.slot_bytes + A.mask_off + j))) : 0;
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += v;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    if (k < n_samples_all) A.plan[kPlanBase + k] = s_carry + (warp > 0 ? s_warp[warp - 1] : 0) + incl - cnt;
+    __syncthreads();
+    if (tid == 0) s_carry += s_warp[31];
+    __syncthreads();
+  }
+}
+
+// kernel 2: every record goes to its place in the merged list (device memory), then the epoch is acknowledged to
+// every producer (its slot may be overwritten from now on)
+__global__ void __launch_bounds__(256)
+k_gather_place(const MergeArgs A) {
+  __shared__ bool s_last;
+  if (A.plan[2]) return;
+  const int sharded = A.plan[0], total = A.plan[1];
   const int lane = threadIdx.x & 31, sub = lane / 10, part = lane % 10;
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   for (int base = warp_global * 3; base < total; base += n_warps * 3) {
     const int item = base + sub;
     if (lane >= 30 || item >= total) continue;
-    int r = 0, i = item;
-    while (i >= s_n[r]) {
-      i -= s_n[r];
-      r++;
-    }
-    const ag_grasp* mine = reinterpret_cast<const ag_grasp*>(A.buf + size_t(r) * A.slot_bytes + kSlotHeaderBytes) + i;
-    const long long key = grasp_key(mine);
-    int pos = 0;
-    for (int q = 0; q < A.world; q++) {
-      if (q == r) {
-        pos += i;
-        continue;
-      }
-      // records of list q in front of mine: smaller key, or the same key from a lower rank (ranks that are not
-      // shards of one call produce equal keys: the merge is then stable in rank order)
-      const ag_grasp* lst = reinterpret_cast<const ag_grasp*>(A.buf + size_t(q) * A.slot_bytes + kSlotHeaderBytes);
-      int lo = 0, hi = s_n[q];
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        const long long km = grasp_key(lst + mid);
-        if (km < key || (km == key && q < r)) lo = mid + 1;
-        else hi = mid;
-      }
-      pos += lo;
+    int r = 0;
+    while (r + 1 < A.world && item >= A.plan[20 + r + 1]) r++;
+    const int i = item - A.plan[20 + r];
+    const char* slot = A.buf + size_t(r) * A.slot_bytes;
+    const ag_grasp* mine = reinterpret_cast<const ag_grasp*>(slot + kSlotHeaderBytes) + i;
+    int pos = item;  // rank-major
+    if (sharded) {   // sample-major: hypotheses of earlier samples, then the valid orientations below this one
+      const int k = mine->sample_slot, j = k / A.world, o = mine->orientation & 7;
+      const unsigned mask = *reinterpret_cast<const uint8_t*>(slot + A.mask_off + j);
+      pos = A.plan[kPlanBase + k] + __popc(mask & ((1u << o) - 1u));
     }
     if (pos < A.cap_total) {
       uint4 v = reinterpret_cast<const uint4*>(mine)[part];
       if (part == 9) v.z = uint32_t(-1);  // image_id: the grasp images stay on the producing rank
-      reinterpret_cast<uint4*>(A.merged_dev + pos)[part] = v;
-      reinterpret_cast<uint4*>(A.merged_host + pos)[part] = v;
+      reinterpret_cast<uint4*>(A.merged_dev + pos)[part] = v;  // (the host copy is made when ag_gather_result asks for it)
     }
   }
-  __threadfence_system();
+  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = atomicAdd(A.done, 1u) == gridDim.x - 1;
   __syncthreads();
   if (!s_last) return;
-  if (threadIdx.x < A.world) {  // every list of this epoch has been read: the producers may reuse the slots
-    A.host->n_per_rank[threadIdx.x] = s_n[threadIdx.x];
-    A.host->err_per_rank[threadIdx.x] = s_err[threadIdx.x];
+  if (threadIdx.x < A.world)  // every list of this epoch has been read: the producers may reuse the slots
     *reinterpret_cast<volatile unsigned*>(A.ack_peer[threadIdx.x]) = A.epoch;
-  }
-  if (threadIdx.x == 0) {
-    A.host->n_total = min(total, A.cap_total);
-    A.host->world = A.world;
-    A.host->status = s_bad | (total > A.cap_total ? 2 : 0);
-    *A.done = 0u;
-  }
+  if (threadIdx.x == 0) *A.done = 0u;
 }
 // publishes an empty list (a call without samples still takes part in the exchange)
 __global__ void k_publish_empty(PeerOut peer, const RowIndex* ri) {
@@ -344,6 +439,9 @@ __global__ void k_publish_empty(PeerOut peer, const RowIndex* ri) {
       const long long t0 = clock64();
       while (int(*a - (peer.epoch - 2u)) < 0 && clock64() - t0 < 4000000000ll) __nanosleep(100);
     }
+    int* h0 = reinterpret_cast<int*>(peer.slot[threadIdx.x]);
+    h0[1] = peer.first;
+    h0[2] = peer.step;
     int* h4 = reinterpret_cast<int*>(peer.slot[threadIdx.x] + 16);
     h4[0] = 0;
     h4[1] = ri->n_points;
@@ -505,11 +603,14 @@ static void launch_merge(Ctx* c, const PeerOut& peer) {
   A.final_pass = peer.final_pass;
   A.merged_dev = static_cast<ag_grasp*>(c->gather_merged);
   A.host = static_cast<GatherHost*>(c->gather_host_dev);
-  A.merged_host = reinterpret_cast<ag_grasp*>(static_cast<char*>(c->gather_host_dev) + sizeof(GatherHost));
   A.cap_total = c->gather_cap_total;
   A.done = static_cast<unsigned*>(c->gather_done) + 4;
-  k_gather_merge<<<64, 256, 0, c->stream>>>(A);
-  c->launches += 1;
+  A.mask_off = peer.mask_off;
+  A.plan = static_cast<int*>(c->gather_plan);
+  A.plan_cap = c->gather_plan_cap;
+  k_gather_plan<<<1, 1024, 0, c->stream>>>(A);
+  k_gather_place<<<64, 256, 0, c->stream>>>(A);
+  c->launches += 2;
 }
 
 // First half of a localize call: everything is enqueued on the context's stream, nothing is waited for.
@@ -706,9 +807,15 @@ static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, in
                      size_t(c->gather_rank) * c->gather_slot_bytes;
     peer.ack = static_cast<const unsigned*>(c->gather_buf);
     peer.world = c->gather_world;
-    peer.cap = int((c->gather_slot_bytes - kSlotHeaderBytes) / sizeof(ag_grasp));
+    peer.cap = c->gather_rec_cap;
     peer.epoch = c->gather_epoch;
     peer.done = static_cast<unsigned*>(c->gather_done);
+    peer.mask_off = size_t(kSlotHeaderBytes) + size_t(c->gather_rec_cap) * sizeof(ag_grasp);
+    peer.mask_cap = c->gather_mask_cap;
+    peer.valid = S > 0 ? c->valid.as<uint8_t>() : nullptr;
+    peer.n_local = S;
+    peer.first = k_first;
+    peer.step = k_step;
   }
   static_assert(sizeof(PeerOut) <= sizeof(c->pend_peer), "pending export arguments");
   std::memcpy(c->pend_peer, &peer, sizeof(peer));
@@ -1200,7 +1307,10 @@ int ag_set_export_buffer(ag_ctx* h, void* d_buffer, size_t bytes) {
 }
 
 // ---- peer gather: the grasp-list all-gather fused into the export kernel (NVLink peer stores) ----------
-size_t ag_gather_slot_bytes(int num_samples) { return size_t(kSlotHeaderBytes) + size_t(8) * size_t(num_samples) * sizeof(ag_grasp); }
+// [header][8 records per sample][one valid-orientation mask per sample, padded to 16 bytes]
+size_t ag_gather_slot_bytes(int num_samples) {
+  return size_t(kSlotHeaderBytes) + size_t(8) * size_t(num_samples) * sizeof(ag_grasp) + ((size_t(num_samples) + 31) / 16) * 16;
+}
 
 int ag_gather_create(ag_ctx* h, int num_samples, int world, int rank, unsigned char* ipc_handle_out) {
   if (!h || world < 1 || world > AG_MAX_GATHER_RANKS || rank < 0 || rank >= world || num_samples < 1 || !ipc_handle_out) {
@@ -1214,6 +1324,11 @@ int ag_gather_create(ag_ctx* h, int num_samples, int world, int rank, unsigned c
     return AG_ERR_INVALID;
   }
   c.gather_slot_bytes = ag_gather_slot_bytes(num_samples);
+  c.gather_rec_cap = 8 * num_samples;
+  c.gather_mask_cap = int(((size_t(num_samples) + 31) / 16) * 16);
+  c.gather_plan_cap = num_samples * world + 64;
+  AG_CUDA_CHECK(cudaMalloc(&c.gather_plan, (size_t(kPlanBase) + size_t(c.gather_plan_cap)) * sizeof(int)));
+  AG_CUDA_CHECK(cudaMemset(c.gather_plan, 0, (size_t(kPlanBase) + size_t(c.gather_plan_cap)) * sizeof(int)));
   // [ack words of the consumers][two epochs (parity) x world slots]
   const size_t bytes = kAckBytes + 2 * size_t(world) * c.gather_slot_bytes;
   AG_CUDA_CHECK(cudaMalloc(&c.gather_buf, bytes));
@@ -1272,7 +1387,15 @@ int ag_gather_result(ag_ctx* h, int32_t* n_hyp_per_rank, int* n_total, const ag_
   for (int r = 0; r < c.gather_world && n_hyp_per_rank; r++) n_hyp_per_rank[r] = gh->n_per_rank[r];
   if (n_total) *n_total = gh->n_total;
   if (d_merged) *d_merged = static_cast<const ag_grasp*>(c.gather_merged);
-  if (h_merged) *h_merged = reinterpret_cast<const ag_grasp*>(static_cast<const char*>(c.gather_host) + sizeof(GatherHost));
+  if (h_merged) {  // host copy on demand (the merged list lives in device memory: its consumers are kernels)
+    ag_grasp* dst = reinterpret_cast<ag_grasp*>(static_cast<char*>(c.gather_host) + sizeof(GatherHost));
+    cudaSetDevice(c.device);
+    if (gh->n_total > 0) {
+      AG_CUDA_CHECK(cudaMemcpyAsync(dst, c.gather_merged, size_t(gh->n_total) * sizeof(ag_grasp), cudaMemcpyDeviceToHost, c.stream));
+      AG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    }
+    *h_merged = dst;
+  }
   return AG_OK;
 }
 
@@ -1301,6 +1424,8 @@ int ag_gather_destroy(ag_ctx* h) {
   if (c.gather_buf) cudaFree(c.gather_buf);
   if (c.gather_done) cudaFree(c.gather_done);
   if (c.gather_merged) cudaFree(c.gather_merged);
+  if (c.gather_plan) cudaFree(c.gather_plan);
+  c.gather_plan = nullptr;
   if (c.gather_host) cudaFreeHost(c.gather_host);
   c.gather_buf = c.gather_done = c.gather_merged = c.gather_host = c.gather_host_dev = c.gather_zero = nullptr;
   c.gather_world = 0;

@@ -345,7 +345,11 @@ def main():
             assert np.all(np.diff(lists[r]["sample_index"]) >= 0)
         n_per2, merged, _ = ctx.gather_result()
         assert n_per2 == n_per and len(merged) == sum(n_per)
-        assert np.all(np.diff(merged["sample_slot"].astype(np.int64) * 8 + merged["orientation"]) >= 0)
+        off = 0  # independent calls (one cloud per rank): the merged list is rank-major, each part sample-major
+        for r in range(world):
+            part = merged[off:off + n_per[r]]
+            assert np.all(np.diff(part["sample_slot"].astype(np.int64) * 8 + part["orientation"]) > 0)
+            off += n_per[r]
         gathered = {"per_rank": n_per, "merged": int(len(merged)),
                     "mode": "peer stores over NVLink + on-device merge inside ag_localize (ag_gather_*), no collective per step"}
     elif world > 1:  # decode the last all-gather on the host (outside the timed region)
