@@ -156,6 +156,8 @@ struct Ctx {
   int n_samples = 0;
   // sweep outputs
   DevBuf grasps_raw, valid, images_raw, hyp_slots, grasps, counters, scores, descriptors, kvals, sweep_dbg, overflow;
+  DevBuf hyp_list;             // unordered hypothesis slots (sweep -> scorer)
+  bool scores_by_slot = false; // c->scores is indexed by raw slot (fused linear scoring) instead of hypothesis number
   DevBuf handle_in, handle_bits;  // ag_find_handles: grasp records and the n x n inlier bit matrix
   int n_hyp = 0;
   bool images_valid = false;
@@ -204,15 +206,19 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
 // restarts the rand() stream of the non-deterministic normal mode (start of every ag_localize / ag_fit_quadrics)
 int quadric_rand_reset(Ctx* c);
 // enqueue only (no sync): sweep + stable compaction; the hypothesis count stays in device memory
-int hand_sweep_enqueue(Ctx* c, const int* d_indices, int n, const ag_frame* d_frames, unsigned flags);
+int hand_sweep_enqueue(Ctx* c, const int* d_indices, int n, const ag_frame* d_frames, unsigned flags,
+                       bool fork_compact = false);
+int* hand_sweep_list_ptr(Ctx* c);        // unordered list of hypothesis slots of the last sweep
+int* hand_sweep_list_count_ptr(Ctx* c);
 // after a sync: handles samples whose slab overflowed the small instantiation; returns the hypothesis count
 int hand_sweep_finish(Ctx* c, int n, int n_over, int* n_hyp);
 int box_points_device(Ctx* c, int n_samples, int slot, std::vector<double>& pts, std::vector<int>& cam);
 int* hand_sweep_count_ptr(Ctx* c, int n);     // device address of the hypothesis count of the last enqueue
 int* hand_sweep_overflow_ptr(Ctx* c);         // device address of the overflow counter
 // n_dev (may be null): device int with the number of hypotheses; n is then only the launch bound
+// score_by_slot: d_scores is indexed by the image slot instead of the position in d_image_ids (single-vector models)
 int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d_image_ids, int n, const int* n_dev,
-                   float* d_descriptors, float* d_scores, ag_grasp* d_grasps_out = nullptr);
+                   float* d_descriptors, float* d_scores, ag_grasp* d_grasps_out = nullptr, bool score_by_slot = false);
 int radius_search_device(Ctx* c, const float q[3], double radius, std::vector<int>& out);
 // training-data path
 int hog_descriptors_device(Ctx* c, const uint32_t* d_images, const int* d_image_slots, int n, float* d_descriptors);

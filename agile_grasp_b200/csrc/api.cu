@@ -152,7 +152,7 @@ __global__ void k_export(const ag_grasp* __restrict__ raw, const int* __restrict
                          const float* __restrict__ scores, const RowIndex* ri, const int* overflow,
                          const unsigned long long* counters, HostOut* hdr, ag_grasp* out_host, ag_grasp* out_dev,
                          int* exp_hdr, ag_grasp* out_exp, int cap, int cap_exp, PeerOut peer, unsigned stamp,
-                         int slot_first, int slot_step) {
+                         int slot_first, int slot_step, int scores_by_slot) {
   // a record is 10 x 16 bytes: three records per warp pass, every lane moves one uint4 (coalesced
   // 480-byte stores — the mapped host destination is written over PCIe and needs full-width writes)
   static_assert(sizeof(ag_grasp) == 160, "record layout");
@@ -175,15 +175,16 @@ __global__ void k_export(const ag_grasp* __restrict__ raw, const int* __restrict
     const int i = base + sub;
     if (lane >= 30 || i >= n) continue;
     uint4 v = reinterpret_cast<const uint4*>(raw + slots[i])[part];
+    const float sc = scores ? scores[scores_by_slot ? slots[i] : i] : 0.f;
     if (part == 8) {
-      if (scores) v.x = __float_as_uint(scores[i]);                        // byte 128: score
+      if (scores) v.x = __float_as_uint(sc);                               // byte 128: score
       v.z = uint32_t(slot_first + int(v.z) * slot_step);                   // byte 136: sample_slot, position in the FULL sample list
     }
     if (part == 9) {
       v.z = uint32_t(i);                                                   // byte 152: image_id
       v.w = (v.w & 0x00FFFFFFu) | (stamp << 24);                           // byte 159: call stamp
       if (scores) {                                                        // byte 158: label (+1 <=> sum <= 0)
-        const uint32_t label = scores[i] > 0.f ? 0u : 1u;
+        const uint32_t label = sc > 0.f ? 0u : 1u;
         v.w = (v.w & 0xFF00FFFFu) | (label << 16);
       }
     }
@@ -584,7 +585,7 @@ static void launch_export(Ctx* c, const PeerOut& peer) {
                                       c->attached_svm ? c->scores.as<float>() : nullptr, c->row_index.as<RowIndex>(),
                                       hand_sweep_overflow_ptr(c), c->counters.as<unsigned long long>(), hdr, recs,
                                       c->grasps.as<ag_grasp>(), exp_hdr, exp_recs, int(size_t(c->pend_S) * 8), cap_exp, peer,
-                                      c->stamp, c->pend_slot_first, c->pend_slot_step);
+                                      c->stamp, c->pend_slot_first, c->pend_slot_step, c->scores_by_slot ? 1 : 0);
 }
 
 // consumer side of the peer gather for the current epoch (right behind the export of the same call)
@@ -715,16 +716,28 @@ static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, in
                              c->frames.as<ag_frame>(), true, rand_share ? &share : nullptr);
     if (rc) return rc;
     record_event(c, c->ev[5]);
+    // a single-vector (linear) model is scored straight from the sweep's unordered hypothesis list while the stable
+    // compaction for the export runs beside it; models with many support vectors go through the ordered list
+    const bool fork = c->attached_svm && c->attached_svm->sv_total == 1;
     rc = hand_sweep_enqueue(c, c->samples.as<int>(), S, c->frames.as<ag_frame>(),
-                            c->params.filters_boundaries ? 0x100u : 0u);
+                            c->params.filters_boundaries ? 0x100u : 0u, fork);
     if (rc) return rc;
     d_nsel = hand_sweep_count_ptr(c, S);
     record_event(c, c->ev[8]);
+    c->scores_by_slot = false;
     if (c->attached_svm) {  // fused scoring, hypothesis count read on the device
       if (c->scores.reserve(slots * 8 + 64)) return AG_ERR_CUDA;
-      rc = hog_svm_device(c, c->attached_svm, c->images_raw.as<uint32_t>(), c->hyp_slots.as<int>(), int(slots), d_nsel,
-                          nullptr, c->scores.as<float>(), nullptr);
-      if (rc) return rc;
+      if (fork) {
+        c->scores_by_slot = true;
+        rc = hog_svm_device(c, c->attached_svm, c->images_raw.as<uint32_t>(), hand_sweep_list_ptr(c), int(slots),
+                            hand_sweep_list_count_ptr(c), nullptr, c->scores.as<float>(), nullptr, true);
+        if (rc) return rc;
+        AG_CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_join, 0));  // the ordered list is ready for the export
+      } else {
+        rc = hog_svm_device(c, c->attached_svm, c->images_raw.as<uint32_t>(), c->hyp_slots.as<int>(), int(slots), d_nsel,
+                            nullptr, c->scores.as<float>(), nullptr);
+        if (rc) return rc;
+      }
     }
     record_event(c, c->ev[9]);
     record_event(c, c->ev[6]);
@@ -903,6 +916,7 @@ static int localize_end(Ctx* c, ag_grasp** out, int* n_out) {
     rc = hand_sweep_finish(c, S, h->n_over, &Hn);
     if (rc) return rc;
     if (c->attached_svm && Hn > 0) {
+      c->scores_by_slot = false;
       rc = hog_svm_device(c, c->attached_svm, c->images_raw.as<uint32_t>(), c->hyp_slots.as<int>(), Hn, nullptr, nullptr,
                           c->scores.as<float>(), nullptr);
       if (rc) return rc;
@@ -1041,7 +1055,7 @@ void ag_destroy(ag_ctx* h) {
   for (DevBuf* b : {&c.raw, &c.keys, &c.keys_sorted, &c.keys_unique, &c.cub_tmp, &c.block_counts, &c.misc, &c.bitmap, &c.tile_state, &c.vox,
                     &c.row_ptr, &c.col_ptr, &c.row_index, &c.all_frames,
                     &c.normals, &c.samples, &c.sample_stage, &c.samples_all, &c.nn_counts_all, &c.count_all, &c.moments, &c.frames, &c.nn_counts, &c.nbr_pool, &c.nbr_heads, &c.rand_raw, &c.rand_off, &c.rand_carry, &c.picks, &c.quad_par, &c.grasps_raw, &c.valid,
-                    &c.images_raw, &c.hyp_slots, &c.grasps, &c.counters, &c.scores, &c.descriptors, &c.kvals, &c.handle_in, &c.handle_bits, &c.sweep_dbg, &c.overflow})
+                    &c.images_raw, &c.hyp_slots, &c.hyp_list, &c.grasps, &c.counters, &c.scores, &c.descriptors, &c.kvals, &c.handle_in, &c.handle_bits, &c.sweep_dbg, &c.overflow})
     b->release();
   if (c.h_pinned) cudaFreeHost(c.h_pinned);
   for (auto& ev : c.ev) cudaEventDestroy(ev);

@@ -165,7 +165,7 @@ __device__ __forceinline__ uint32_t bits_at(const uint32_t* img, int bit0) {  //
 __global__ void __launch_bounds__(kThreads, 3)
 k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slots, int n_bound,
           const int* __restrict__ n_dev, SvmDev svm, float* __restrict__ descriptors, float* __restrict__ scores,
-          ag_grasp* __restrict__ grasps_out) {
+          ag_grasp* __restrict__ grasps_out, int score_by_slot) {
   __shared__ uint32_t s_bits[AG_IMAGE_WORDS + 2];
   __shared__ uint32_t s_row[H][RW];                 // row-aligned image
   __shared__ uint32_t s_xp[H][RW], s_xn[H][RW], s_yp[H][RW], s_yn[H][RW];  // gradient sign bit-planes
@@ -361,7 +361,7 @@ k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slo
     double sum = -svm.rho;
     for (int w2 = 0; w2 < kThreads / 32; w2++) sum += s_part[w2];
     const float sc = float(sum);
-    scores[hyp] = sc;
+    scores[score_by_slot ? image_slots[hyp] : hyp] = sc;
     if (grasps_out) {  // fused classify: write score and label into the compacted record
       grasps_out[hyp].score = sc;
       grasps_out[hyp].label = sc > 0.f ? 0 : 1;  // CvSVM::predict: label +1 <=> sum <= 0
@@ -542,15 +542,19 @@ int hog_descriptors_device(Ctx* c, const uint32_t* d_images, const int* d_image_
   SvmDev none;
   std::memset(&none, 0, sizeof(none));
   k_hog_svm<<<std::min(n, kNumSMs * 6), kThreads, 0, c->stream>>>(d_images, d_image_slots, n, nullptr, none, d_descriptors,
-                                                                  nullptr, nullptr);
+                                                                  nullptr, nullptr, 0);
   c->launches += 1;
   AG_CUDA_CHECK(cudaGetLastError());
   return AG_OK;
 }
 
 int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d_image_slots, int n, const int* n_dev,
-                   float* d_descriptors, float* d_scores, ag_grasp* d_grasps_out) {
+                   float* d_descriptors, float* d_scores, ag_grasp* d_grasps_out, bool score_by_slot) {
   if (n <= 0) return AG_OK;
+  if (score_by_slot && (svm->sv_total > 1 || !d_image_slots)) {
+    set_error("hog_svm_device: scores by slot need a single-vector model and a slot list");
+    return AG_ERR_INVALID;
+  }
   if (svm->var_count != AG_HOG_DIM) {
     set_error("SVM var_count != 3528");
     return AG_ERR_INVALID;
@@ -583,7 +587,7 @@ int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d
     if (c->kvals.reserve(size_t(n) * svm->sv_total * sizeof(float))) return AG_ERR_CUDA;
     SvmDev none = sd;
     none.sv_total = 0;
-    k_hog_svm<<<grid, kThreads, 0, c->stream>>>(d_images, d_image_slots, n, n_dev, none, desc, d_scores, nullptr);
+    k_hog_svm<<<grid, kThreads, 0, c->stream>>>(d_images, d_image_slots, n, n_dev, none, desc, d_scores, nullptr, 0);
     const dim3 gg((n + GM - 1) / GM, (svm->sv_total + GN - 1) / GN);
     k_svm_gemm<<<gg, kGemmThreads, 0, c->stream>>>(desc, svm->d_sv, n, n_dev, svm->sv_total, svm->kernel, svm->gamma,
                                                   svm->coef0, svm->degree, c->kvals.as<float>());
@@ -594,7 +598,7 @@ int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d
     c->launches += 3;
   } else {
     k_hog_svm<<<grid, kThreads, 0, c->stream>>>(d_images, d_image_slots, n, n_dev, sd, d_descriptors, d_scores,
-                                                 d_grasps_out);
+                                                 d_grasps_out, score_by_slot ? 1 : 0);
     c->launches += 1;
   }
   AG_CUDA_CHECK(cudaGetLastError());

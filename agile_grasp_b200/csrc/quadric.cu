@@ -1164,13 +1164,14 @@ k_rank_picks(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip,
 
 // ---- kernel 3: gradient normals at the evaluation points, curvature axis, frame ---------------------------
 __global__ void __launch_bounds__(kWarps * 32, 4)
-k_axes_finish(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip,
+k_axes_finish(GPoint* pts_c, const RowIndex* __restrict__ rip,
               const int* __restrict__ indices, int s0, int n_samples_max, const int* __restrict__ d_count,
               const GPoint* __restrict__ pool, int stride, const int2* __restrict__ nn_counts, double inv_r,
               const double* __restrict__ moments, const double* __restrict__ par_in,
               double cam0x, double cam0y, double cam0z, double cam1x, double cam1y, double cam1z,
               ag_frame* __restrict__ frames, double* normals_out /* may be null */,
-              const unsigned short* __restrict__ picks_in /* null = deterministic normals */) {
+              const unsigned short* __restrict__ picks_in /* null = deterministic normals */,
+              unsigned long long* __restrict__ counters) {
   __shared__ double s_T[kWarps][28];  // weighted order-6 normal tensor
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sl = blockIdx.x * kWarps + warp;
@@ -1180,8 +1181,16 @@ k_axes_finish(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip
   const int idx = indices[s];
   if (idx < 0 || idx >= rip->n_points) return;
   const GPoint* list = pool + size_t(sl) * size_t(stride);
-  const int n_list = nn_counts[s].x;
+  const int2 nnc = nn_counts[s];
+  const int n_list = nnc.x;
   const GPoint q = pts_c[idx];
+  if (lane == 0) {
+    // totals of the neighbour / candidate counts (reported through ag_timings) and, when the normal goes to
+    // cloud_normals_, the tag bit that lets the sweep fetch only normals that exist
+    atomicAdd(&counters[0], (unsigned long long)nnc.x);
+    atomicAdd(&counters[1], (unsigned long long)nnc.y);
+    if (normals_out) atomicOr(&pts_c[idx].tag, kTagNormalBit);
+  }
   const double qx = double(q.x), qy = double(q.y), qz = double(q.z);
   const double* mom = moments + size_t(s) * kMomentStride;
   const double n = mom[0];
@@ -1356,36 +1365,6 @@ k_axes_finish(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip
   }
 }
 
-// one thread per sample after the fit: totals of the per-sample neighbour / candidate counts (one atomic
-// pair per CTA, reported through ag_timings) and, when the normals were written to cloud_normals_, the
-// tag bit that lets the sweep fetch only normals that exist
-__global__ void k_quadric_finish(GPoint* pts, const RowIndex* __restrict__ rip, const int* __restrict__ indices, int n,
-                                 const int* __restrict__ d_count, const int2* __restrict__ nn_counts,
-                                 unsigned long long* __restrict__ counters, int mark) {
-  __shared__ unsigned long long s_sum[2];
-  if (threadIdx.x < 2) s_sum[threadIdx.x] = 0ull;
-  __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int nn = 0, nc = 0;
-  if (i < n && i < *d_count) {
-    const int idx = indices[i];
-    if (idx >= 0 && idx < rip->n_points) {
-      if (mark) atomicOr(&pts[idx].tag, kTagNormalBit);
-      const int2 v = nn_counts[i];
-      nn = v.x;
-      nc = v.y;
-    }
-  }
-  nn = __reduce_add_sync(0xffffffffu, nn);
-  nc = __reduce_add_sync(0xffffffffu, nc);
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&s_sum[0], (unsigned long long)nn);
-    atomicAdd(&s_sum[1], (unsigned long long)nc);
-  }
-  __syncthreads();
-  if (threadIdx.x < 2 && s_sum[threadIdx.x]) atomicAdd(&counters[threadIdx.x], s_sum[threadIdx.x]);
-}
-
 }  // namespace
 
 // non-deterministic normal mode: sample s consumes rand() draws [50 k_s, 50 k_s + 50), k_s = number of earlier
@@ -1393,39 +1372,39 @@ __global__ void k_quadric_finish(GPoint* pts, const RowIndex* __restrict__ rip, 
 __global__ void __launch_bounds__(1024)
 k_rand_offsets(const int2* __restrict__ nn_counts, int s0, int m, const int* __restrict__ d_count, int* __restrict__ rand_off,
                int* __restrict__ carry) {
+  // one pass: every thread owns a run of consecutive samples (flag = more than 50 neighbours), one block scan
   __shared__ int s_warp[32];
-  __shared__ int s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_base = *carry;
+  const int per = (m + 1023) / 1024, lo = min(m, tid * per), hi = min(m, lo + per);
+  const int cnt_valid = *d_count;
+  int f = 0;
+  for (int i = lo; i < hi; i++) f += (s0 + i < cnt_valid && nn_counts[s0 + i].x > 50) ? 1 : 0;
+  int v = f;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  if (lane == 31) s_warp[warp] = v;
   __syncthreads();
-  for (int base = 0; base < m; base += 1024) {
-    const int s = s0 + base + tid;
-    const int f = (base + tid < m && s < *d_count && nn_counts[s].x > 50) ? 1 : 0;
-    int v = f;
+  if (warp == 0) {
+    int w = s_warp[lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, v, o);
-      if (lane >= o) v += t;
+      const int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
     }
-    if (lane == 31) s_warp[warp] = v;
-    __syncthreads();
-    if (warp == 0) {
-      int w = s_warp[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, w, o);
-        if (lane >= o) w += t;
-      }
-      s_warp[lane] = w;
-    }
-    __syncthreads();
-    const int excl = v - f + (warp > 0 ? s_warp[warp - 1] : 0);
-    if (base + tid < m) rand_off[s] = s_base + excl;
-    __syncthreads();
-    if (tid == 0) s_base += s_warp[31];
-    __syncthreads();
+    s_warp[lane] = w;
   }
-  if (tid == 0) *carry = s_base;
+  __syncthreads();
+  const int base = *carry;
+  int run = base + v - f + (warp > 0 ? s_warp[warp - 1] : 0);
+  for (int i = lo; i < hi; i++) {
+    rand_off[s0 + i] = run;
+    run += (s0 + i < cnt_valid && nn_counts[s0 + i].x > 50) ? 1 : 0;
+  }
+  __syncthreads();
+  if (tid == 0) *carry = base + s_warp[31];
 }
 
 // glibc rand() outputs after srand(1) — what a process that never seeds gets from the reference's
@@ -1606,13 +1585,10 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
         c->vox.as<GPoint>(), ri, d_indices, s0, s0 + m, d_count, c->nbr_pool.as<GPoint>(), stride,
         c->nn_counts.as<int2>(), inv_r, c->moments.as<double>(), c->quad_par.as<double>(), h.cam[0][0], h.cam[0][1],
         h.cam[0][2], h.cam[1][0], h.cam[1][1], h.cam[1][2], d_frames, write_normals ? c->normals.as<double>() : nullptr,
-        rand_mode ? c->picks.as<unsigned short>() : nullptr);
+        rand_mode ? c->picks.as<unsigned short>() : nullptr, ctr);
     if (timed) record_event(c, c->ev_k[3]);
     c->launches += split ? 4 : 3;
   }
-  k_quadric_finish<<<(n + 255) / 256, 256, 0, c->stream>>>(c->vox.as<GPoint>(), ri, d_indices, n, d_count,
-                                                          c->nn_counts.as<int2>(), ctr, write_normals ? 1 : 0);
-  c->launches += 1;
   AG_CUDA_CHECK(cudaGetLastError());
   return AG_OK;
 }

@@ -45,6 +45,8 @@ struct SweepArgs {
   int* debug;             // [n_samples * 8] or null
   int* slab_counts;       // [n_samples] or null
   unsigned long long* counters;
+  int* hyp_list;          // unordered list of the (sample, orientation) slots that hold a hypothesis (for the scorer)
+  int* hyp_count;
   int* overflow;          // [0] = number of samples whose slab exceeded the capacity, [1..] their slots
   const int* sample_list; // if non-null: blockIdx.x indexes this list of sample slots (fallback pass)
   int n_samples;
@@ -508,6 +510,7 @@ k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
     gr.reserved = 0;
     A.grasps[slot] = gr;
     A.valid[slot] = keep_hyp ? 1 : 0;
+    if (keep_hyp) A.hyp_list[atomicAdd(A.hyp_count, 1)] = int(slot);  // (scoring does not need the sample-major order)
   }
   uint32_t* gimg = A.images + slot * AG_IMAGE_WORDS;
   for (int i = lane; i < AG_IMAGE_WORDS; i += 32) gimg[i] = img[i];
@@ -870,6 +873,8 @@ static SweepArgs make_args(Ctx* c, const int* d_indices, int n, const ag_frame* 
   A.debug = c->sweep_dbg.as<int>() + n;
   A.counters = c->counters.as<unsigned long long>();
   A.overflow = c->overflow.as<int>();
+  A.hyp_list = c->hyp_list.as<int>();
+  A.hyp_count = reinterpret_cast<int*>(c->counters.as<unsigned long long>() + 4);
   A.sample_list = nullptr;
   A.n_samples = n;
   const double radius = c->params.nn_radius_hands;
@@ -880,10 +885,10 @@ static SweepArgs make_args(Ctx* c, const int* d_indices, int n, const ag_frame* 
   return A;
 }
 
-static int compact(Ctx* c, const SweepArgs& A, size_t slots) {
+static int compact(Ctx* c, const SweepArgs& A, size_t slots, cudaStream_t st) {
   int* d_slots = c->hyp_slots.as<int>();
   int* d_nsel = d_slots + slots;
-  k_compact_slots<<<1, 1024, 0, c->stream>>>(A.valid, int(slots), d_slots, d_nsel);
+  k_compact_slots<<<1, 1024, 0, st>>>(A.valid, int(slots), d_slots, d_nsel);
   AG_CUDA_CHECK(cudaGetLastError());
   return AG_OK;
 }
@@ -944,7 +949,10 @@ int camera_images_device(Ctx* c, int n_samples, const int* d_slots, int n, uint3
 int* hand_sweep_count_ptr(Ctx* c, int n) { return c->hyp_slots.as<int>() + size_t(n) * 8; }
 int* hand_sweep_overflow_ptr(Ctx* c) { return c->overflow.as<int>(); }
 
-int hand_sweep_enqueue(Ctx* c, const int* d_indices, int n, const ag_frame* d_frames, unsigned flags) {
+int* hand_sweep_list_ptr(Ctx* c) { return c->hyp_list.as<int>(); }
+int* hand_sweep_list_count_ptr(Ctx* c) { return reinterpret_cast<int*>(c->counters.as<unsigned long long>() + 4); }
+
+int hand_sweep_enqueue(Ctx* c, const int* d_indices, int n, const ag_frame* d_frames, unsigned flags, bool fork_compact) {
   c->n_hyp = 0;
   c->images_valid = false;
   if (n <= 0) return AG_OK;
@@ -952,7 +960,8 @@ int hand_sweep_enqueue(Ctx* c, const int* d_indices, int n, const ag_frame* d_fr
   if (c->grasps_raw.reserve(slots * sizeof(ag_grasp)) || c->valid.reserve(slots + 64) ||
       c->images_raw.reserve(slots * AG_IMAGE_WORDS * 4) || c->hyp_slots.reserve(slots * 4 + 16) ||
       c->grasps.reserve(slots * sizeof(ag_grasp)) || c->counters.reserve(64) ||
-      c->sweep_dbg.reserve(size_t(n) * 4 + slots * 4) || c->overflow.reserve(size_t(n + 1) * 4))
+      c->sweep_dbg.reserve(size_t(n) * 4 + slots * 4) || c->overflow.reserve(size_t(n + 1) * 4) ||
+      c->hyp_list.reserve(slots * 4 + 16))
     return AG_ERR_CUDA;
   SweepArgs A = make_args(c, d_indices, n, d_frames, flags);
   const size_t smem_small = sizeof(SweepShared) + size_t(kSlabCapSmall) * 20;
@@ -970,7 +979,16 @@ int hand_sweep_enqueue(Ctx* c, const int* d_indices, int n, const ag_frame* d_fr
   c->sweep_flags = flags;
   c->sweep_indices = d_indices;
   c->sweep_frames = d_frames;
-  return compact(c, A, slots);
+  if (fork_compact) {
+    // the stable compaction (sample-major order for the export) runs on the side stream while the main stream
+    // scores the hypotheses from the sweep's unordered list; the caller joins on ev_join before the export
+    AG_CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
+    AG_CUDA_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    int rc = compact(c, A, slots, c->stream2);
+    AG_CUDA_CHECK(cudaEventRecord(c->ev_join, c->stream2));
+    return rc;
+  }
+  return compact(c, A, slots, c->stream);
 }
 
 // Called after the stream has been synchronised and the overflow counter read.  Samples whose slab
@@ -988,7 +1006,7 @@ int hand_sweep_finish(Ctx* c, int n, int n_over, int* n_hyp) {
     const size_t smem_big = sizeof(SweepShared) + size_t(kSlabCapBig) * 20;
     k_hand_sweep<kSlabCapBig><<<n_over, kThreads, smem_big, c->stream>>>(A, c->hand);
     c->launches += 2;
-    int rc = compact(c, A, slots);
+    int rc = compact(c, A, slots, c->stream);
     if (rc) return rc;
     int over2 = 0;
     AG_CUDA_CHECK(cudaMemcpyAsync(&over2, A.overflow, 4, cudaMemcpyDeviceToHost, c->stream));

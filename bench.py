@@ -294,9 +294,9 @@ def main():
             gather(g)
             e1.record()
             torch.cuda.synchronize()
-            # peer gather: the stores ride inside ag_localize's export kernel (already in total_ms); what is left
-            # is the wait for the slowest peer, on the library stream -> wall clock of ag_gather_wait
-            cm = 0.0 if world == 1 else ((time.perf_counter() - tg0) * 1e3 if peer_gather else e0.elapsed_time(e1))
+            # peer gather: stores, wait for the slowest peer and merge all run inside ag_localize's stream (in total_ms);
+            # the NCCL variant is a separate collective, timed here
+            cm = 0.0 if (world == 1 or peer_gather) else e0.elapsed_time(e1)
             dev_ms.append(t1["total_ms"] + cm)  # scoring is fused into ag_localize (ag_set_svm): inside total_ms
             comm_ms.append(cm)
             hyps.append(len(g))
