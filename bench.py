@@ -182,6 +182,9 @@ def run_reference(args, rank, world):
                          "other_mode": {"normal_mode": MODE_NAME[1 - det], "value": o_value, "ms_per_cloud": o_ms}},
         "e2e": {"value": value, "unit": "hyp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if args.poly:
+        pv, pms, _, _ = cpu_arm(clouds[:1], det, 1, 0, svm_path=poly_model_path())
+        line["cpu_baseline"]["poly_svm"] = {"value": pv, "ms_per_cloud": pms}
     print(json.dumps(line), flush=True)
 
 
@@ -195,6 +198,7 @@ def main():
     ap.add_argument("--normals", default="rand", choices=["rand", "det"],
                     help="normal mode of the headline numbers: rand = the reference's production default")
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--poly", action="store_true", help="reference arm: also time one cloud with the launch-file POLY model")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (profiling runs)")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU grasp-list exchange: NVLink peer stores fused into the export kernel, or NCCL")
@@ -530,6 +534,8 @@ def main():
             step_device(c0)
             n_vox = ctx.timings()["n_voxels"]
             all_idx = np.arange(n_vox, dtype=np.int32)
+            c0["P"].deterministic_normals = 1  # (no pick ranking on the side stream while the stage is timed)
+            ctx.set_params(c0["P"])
             best = None
             for _ in range(4):
                 flush.fill_(1)
@@ -543,12 +549,18 @@ def main():
             a_sc = b_alg / (ms * 1e-3) / 1e9
             peak, _ = measured_peak()
             line["roofline_at_scale"] = {
-                "kernel": line["roofline"]["kernel"], "samples": int(n_vox), "algorithmic_bytes_per_launch": float(b_alg),
-                "launch_ms": float(ms), "achieved": float(a_sc), "peak": peak, "unit": "GB/s", "frac": float(a_sc / peak),
+                "kernel": "k_ball_search + k_taubin_moments (launches > 16k samples keep the two-kernel variant)",
+                "samples": int(n_vox), "algorithmic_bytes_per_launch": float(b_alg),
+                "launch_ms": float(ms), "search_ms": float(best["search_ms"]), "moments_ms": float(best["moments_ms"]),
+                "achieved": float(a_sc), "peak": peak, "unit": "GB/s", "frac": float(a_sc / peak),
+                "moments_only_frac": float(b_alg / (best["moments_ms"] * 1e-3) / 1e9 / peak),
                 "axes_ms": float(best["axes_ms"]),
                 "note": "all voxels of the bench cloud as samples (L2 flushed before each of 4 launches, best taken)"}
         except Exception as e:  # never lose the bench line over the extra measurement
             line["roofline_at_scale"] = {"error": str(e)}
+        finally:
+            c0["P"].deterministic_normals = det
+            ctx.set_params(c0["P"])
         # ---- throughput mode (BASELINE config 4 on one GPU): 16 clouds through ag_localize_batch, pinned host
         # buffers in, host grasp lists out (wall clock, best of 3); the headline above stays one cloud per call
         try:
@@ -596,25 +608,24 @@ def main():
             line["poly_svm"] = {"error": str(e)}
         finally:
             ctx.set_svm(svm)
-        # ---- CPU baseline: the oracle port on this box's host cores, both normal modes, same scene pool
+        # ---- CPU baseline: the oracle port on this box's host cores, both normal modes, same scene pool — in a fresh
+        # process (= the --impl reference arm): inside this one torch's and numpy's idle worker threads compete with
+        # the oracle's OpenMP team and triple its time
         try:
-            clouds = [(c["host"].numpy(), c["size_left"], c["P"]) for c in pool]
-            v, ms, hyp, cores = cpu_arm(clouds, det, args.cpu_steps, 0)
-            ov, oms, _, _ = cpu_arm(clouds, 1 - det, max(1, args.cpu_steps // 2), 0)
-            line["cpu_baseline"] = {"value": v, "unit": "hyp/s", "cores": cores, "kind": "port", "ms_per_cloud": ms,
-                                    "normal_mode": MODE_NAME[det],
-                                    "sample": f"{args.cpu_steps} full clouds of the same workload and scene pool, all "
-                                              f"{cores} host threads (OpenMP over samples, as the reference)",
-                                    "other_mode": {"normal_mode": MODE_NAME[1 - det], "value": ov, "ms_per_cloud": oms}}
+            cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(args.cpu_steps),
+                   "--warmup", "0", "--normals", args.normals, "--config", str(args.config)]
             if "poly_svm" in line and "e2e" in line["poly_svm"]:
-                pv, pms, _, _ = cpu_arm(clouds[:1], det, 1, 0, svm_path=poly_model_path())
-                line["poly_svm"]["cpu_baseline"] = {"value": pv, "ms_per_cloud": pms, "cores": cores}
+                cmd.append("--poly")
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=900,
+                                 env={k: v for k, v in os.environ.items() if k != "OMP_NUM_THREADS"})
+            ref = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+            cb = ref["cpu_baseline"]
+            if "poly_svm" in cb:
+                line["poly_svm"]["cpu_baseline"] = dict(cb.pop("poly_svm"), cores=cb["cores"])
+            line["cpu_baseline"] = cb
         except Exception as e:  # the oracle is test infrastructure; never let it break the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "hyp/s", "cores": 0, "kind": "port",
                                     "sample": f"unavailable: {e}"}
-        finally:
-            for c in pool:
-                c["P"].deterministic_normals = det
     if rank == 0:
         print(json.dumps(line), flush=True)
     ctx.close()
