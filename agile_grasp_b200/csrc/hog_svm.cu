@@ -7,12 +7,15 @@
 //
 // The image is binary, so after OpenCV's sqrt gamma LUT every pixel gradient is one of 9 cases
 // (dx,dy in {-s,0,+s}, s = sqrt(255.f)); magnitude/angle for the 9 cases are tabulated from
-// cv::cartToPolar (which uses a polynomial atan: the diagonals are NOT k*pi/4).  Block histograms
-// are accumulated by one thread per (block, cell) walking that cell's 144 contributing pixels in
-// exactly OpenCV's order (count1 | count2 | count4 lists, column-major inside the block) with
-// separate binary32 multiply and add, so the descriptor is bit-identical to OpenCV's; the two
-// windows share 4 of their 7 block columns, so only 11x7 = 77 distinct blocks are computed.
-// Compiled with -fmad=false.
+// cv::cartToPolar (which uses a polynomial atan: the diagonals are NOT k*pi/4).  Only pixels on the
+// outline of the rasterised points have a gradient at all (config 2: ~160 of 8000 pixels, 93 % of the
+// 16x16 blocks hold none), so the kernel is driven by those pixels: the gradient planes scatter their
+// set bits into per-column masks and 8x8 tile flags, a block without a flagged tile is never visited
+// (its histogram, its normalised descriptor entries and its terms of the SVM dot product are exact zeros),
+// and a visited (block, cell) walks its contributing pixels in exactly OpenCV's order (count1 | count2 |
+// count4 lists, column-major inside the block) with separate binary32 multiply and add, so the
+// descriptor is bit-identical to OpenCV's; the two windows share 4 of their 7 block columns, so there
+// are only 11x7 = 77 distinct blocks.  Compiled with -fmad=false.
 
 #include <algorithm>
 #include <cmath>
@@ -28,20 +31,21 @@ constexpr int W = AG_IMAGE_COLS, H = AG_IMAGE_ROWS;
 constexpr int NB = 9, BS = 16, CS = 8;
 constexpr int UBX = 11, UBY = 7, NUB = UBX * UBY;  // distinct blocks
 constexpr int CELL_LIST = 144;                      // pixels contributing to one cell of a block
-constexpr int kThreads = 320;                       // >= 77*4 = 308 (block, cell) work items
+constexpr int kThreads = 256;                       // 8 warps per hypothesis (one per (block, cell) item at a time), 6 CTAs per SM
 
 struct CellRun {     // consecutive rows of one block column that feed one cell, in OpenCV's order
   short j, i0, len, first;  // block column, first block row, run length, index of the first weight
 };
 constexpr int kMaxRuns = 24;
 struct HogTables {
-  float w[4][CELL_LIST + 1];     // gradWeight * histWeight per contribution (+1: bank padding)
+  float w[4][CELL_LIST];         // gradWeight * histWeight per contribution
   CellRun runs[4][kMaxRuns];
   int n_runs[4];
-  float g0[9], g1[9];            // magnitude split between the two nearest bins, per gradient case
-  int h0[9], h1[9];
+  float4 cases[9];               // per gradient case: magnitude share of the two nearest bins, and the bins (as int bits)
 };
-__constant__ HogTables c_hog;
+// global memory, read through the read-only path: the lookups are indexed per lane (constant memory would
+// serialise the warp) and only the few (block, cell) items that see an outline pixel ever touch them
+__device__ HogTables g_hog;
 
 // cv::cartToPolar(dx,dy) for (sign dx, sign dy): index (sy+1)*3 + (sx+1); values measured from
 // cv2 4.13 (tests/test_oracle_hog_svm.py checks them against the live library), stored as bit patterns
@@ -63,14 +67,16 @@ void build_tables(HogTables& T) {
     float angle = u2f(kAngBits[k]) * angleScale - 0.5f;
     int hidx = int(std::floor(angle));
     angle -= float(hidx);
-    T.g0[k] = mag * (1.f - angle);
-    T.g1[k] = mag * angle;
+    T.cases[k].x = mag * (1.f - angle);
+    T.cases[k].y = mag * angle;
     if (hidx < 0) hidx += NB;
     else if (hidx >= NB) hidx -= NB;
-    T.h0[k] = hidx;
+    const int h0 = hidx;
     hidx++;
     if (hidx >= NB) hidx = 0;
-    T.h1[k] = hidx;
+    const int h1 = hidx;
+    std::memcpy(&T.cases[k].z, &h0, 4);
+    std::memcpy(&T.cases[k].w, &h1, 4);
   }
   // HOGCache::init: gaussian weights exp(-(di^2+dj^2)/(2 sigma^2)), di = i - 8, sigma = 4, and the
   // bilinear cell interpolation classes; OpenCV's per-pixel lists (pixels touching 1 | 2 | 4 cells, each
@@ -162,91 +168,137 @@ __device__ __forceinline__ uint32_t bits_at(const uint32_t* img, int bit0) {  //
   return __funnelshift_r(img[w], img[w + 1], sh);
 }
 
-__global__ void __launch_bounds__(kThreads, 3)
+// Per-hypothesis flags of the distinct blocks that hold an outline pixel, written next to the descriptors for the
+// batched scorer of many-vector models (3 words: bit ub of word ub / 32).
+constexpr int kFlagWords = 3;
+
+__global__ void __launch_bounds__(kThreads, 6)
 k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slots, int n_bound,
           const int* __restrict__ n_dev, SvmDev svm, float* __restrict__ descriptors, float* __restrict__ scores,
-          ag_grasp* __restrict__ grasps_out, int score_by_slot) {
-  __shared__ uint32_t s_bits[AG_IMAGE_WORDS + 2];
-  __shared__ uint32_t s_row[H][RW];                 // row-aligned image
+          ag_grasp* __restrict__ grasps_out, int score_by_slot, uint32_t* __restrict__ block_flags) {
+  // per warp: the ordered contributions of one cell (step 3); steps 1-2 use the same bytes for the packed and the
+  // row-aligned image
+  __shared__ __align__(16) float4 s_rec[kThreads / 32][CELL_LIST];
+  static_assert(sizeof(float4) * (kThreads / 32) * CELL_LIST >= 4 * (AG_IMAGE_WORDS + 2 + H * RW), "overlay");
+  uint32_t* const s_bits = reinterpret_cast<uint32_t*>(&s_rec[0][0]);
+  uint32_t(*const s_row)[RW] = reinterpret_cast<uint32_t(*)[RW]>(s_bits + AG_IMAGE_WORDS + 2);
   __shared__ uint32_t s_xp[H][RW], s_xn[H][RW], s_yp[H][RW], s_yn[H][RW];  // gradient sign bit-planes
   __shared__ uint32_t s_col[W][3];                  // per column: 80-bit mask of non-zero-gradient pixels
-  __shared__ __align__(16) float s_hist[NUB * 36];
-  __shared__ float s_acc[NB][kThreads];             // step 4: the 9 bins of every (block, cell) thread, [bin][thread]
-  __shared__ float s_K[1];                          // kernel value of the (single) support vector
+  __shared__ uint32_t s_tile[H / 8];                // per row of 8x8 tiles: bit tx = the tile holds such a pixel
+  __shared__ __align__(16) float s_hist[NUB * 36];  // only the entries of flagged blocks are ever written or read
+  __shared__ float4 s_case[9];
+  __shared__ uint8_t s_list[NUB + 3];               // flagged blocks, ascending
+  __shared__ int s_nflag;
   __shared__ double s_part[kThreads / 32];
-  // the lookup tables of step 4 are indexed per lane: shared memory (constant memory would serialise the warp)
-  __shared__ float s_w[4][CELL_LIST + 1];
-  __shared__ CellRun s_runs[4][kMaxRuns];
-  __shared__ float s_g0[9], s_g1[9];
-  __shared__ int s_h0[9], s_h1[9], s_nruns[4];
+  // (independent loads first: the count, this CTA's first image slot and the model's coefficient are in flight together)
+  const int first_slot = (image_slots && int(blockIdx.x) < n_bound) ? image_slots[blockIdx.x] : int(blockIdx.x);
+  const double alpha0 = (svm.sv_total == 1 && svm.sv_count > 0) ? svm.alpha[0] : 0.0;
   const int n = n_dev ? min(*n_dev, n_bound) : n_bound;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < 4 * (CELL_LIST + 1); i += kThreads) (&s_w[0][0])[i] = (&c_hog.w[0][0])[i];
-  for (int i = tid; i < 4 * kMaxRuns; i += kThreads) (&s_runs[0][0])[i] = (&c_hog.runs[0][0])[i];
-  if (tid < 9) {
-    s_g0[tid] = c_hog.g0[tid];
-    s_g1[tid] = c_hog.g1[tid];
-    s_h0[tid] = c_hog.h0[tid];
-    s_h1[tid] = c_hog.h1[tid];
-  }
-  if (tid < 4) s_nruns[tid] = c_hog.n_runs[tid];
-  for (int hyp = blockIdx.x; hyp < n; hyp += gridDim.x) {  // persistent CTAs: the count lives on the device
-  __syncthreads();
-  const uint32_t* src = images + size_t(image_slots ? image_slots[hyp] : hyp) * AG_IMAGE_WORDS;
-  for (int i = tid; i < AG_IMAGE_WORDS + 2; i += kThreads) s_bits[i] = i < AG_IMAGE_WORDS ? src[i] : 0u;
-  __syncthreads();
-  // 1. row-aligned copy: row r = bits [100 r, 100 r + 100)
-  {
-    const int r = tid >> 2, w = tid & 3;  // 320 threads = 80 rows x 4 words
-    uint32_t v = bits_at(s_bits, r * W + 32 * w);
-    if (w == 3) v &= 0xFu;  // columns 96..99
-    s_row[r][w] = v;
-  }
-  __syncthreads();
-  // 2. gradient sign planes ([-1,0,1] derivative with BORDER_REFLECT_101 on the binary image)
-  {
-    const int r = tid >> 2, w = tid & 3;
-    const uint32_t cur = s_row[r][w];
-    const uint32_t prev = w > 0 ? s_row[r][w - 1] : 0u, next = w < 3 ? s_row[r][w + 1] : 0u;
-    uint32_t R = (cur >> 1) | (next << 31);   // pixel x+1
-    uint32_t L = (cur << 1) | (prev >> 31);   // pixel x-1
-    if (w == 0) L = (L & ~1u) | ((cur >> 1) & 1u);                 // x = 0 : left neighbour is pixel 1
-    if (w == 3) R = (R & ~(1u << 3)) | (((cur >> 2) & 1u) << 3);   // x = 99: right neighbour is pixel 98
-    const uint32_t U = s_row[r == 0 ? 1 : r - 1][w], D = s_row[r == H - 1 ? H - 2 : r + 1][w];
-    const uint32_t valid = w == 3 ? 0xFu : 0xFFFFFFFFu;
-    s_xp[r][w] = R & ~L & valid;
-    s_xn[r][w] = L & ~R & valid;
-    s_yp[r][w] = D & ~U & valid;
-    s_yn[r][w] = U & ~D & valid;
-  }
-  __syncthreads();
-  // 3. column masks of pixels with a non-zero gradient: one thread per (column, 32-row segment)
-  if (tid < W * 3) {
-    const int x = tid % W, seg = tid / W, w = x >> 5, sh = x & 31;
-    const int r0 = seg * 32, r1 = min(H, r0 + 32);
-    uint32_t m = 0;
-    for (int r = r0; r < r1; r++) {
-      const uint32_t nz = ((s_xp[r][w] | s_xn[r][w] | s_yp[r][w] | s_yn[r][w]) >> sh) & 1u;
-      m |= nz << (r - r0);
+  const unsigned lt = (1u << lane) - 1u;
+  if (tid < 9) s_case[tid] = g_hog.cases[tid];
+  // block ub = (bx, by) covers the tiles (bx..bx+1, by..by+1)
+  auto flagged = [&](int ub) -> bool {
+    const int bx = ub / UBY, by = ub - bx * UBY;
+    return (((s_tile[by] | s_tile[by + 1]) >> bx) & 3u) != 0u;
+  };
+  for (int hyp = blockIdx.x; hyp < n; hyp += gridDim.x) {
+    __syncthreads();  // the previous hypothesis is finished with the shared arrays
+    const int slot = hyp == int(blockIdx.x) ? first_slot : (image_slots ? image_slots[hyp] : hyp);
+    const uint32_t* src = images + size_t(slot) * AG_IMAGE_WORDS;
+    for (int i = tid; i < AG_IMAGE_WORDS + 2; i += kThreads) s_bits[i] = i < AG_IMAGE_WORDS ? src[i] : 0u;
+    for (int i = tid; i < W * 3; i += kThreads) (&s_col[0][0])[i] = 0u;
+    if (tid < H / 8) s_tile[tid] = 0u;
+    __syncthreads();
+    // 1. row-aligned copy: row r = bits [100 r, 100 r + 100)
+    for (int it = tid; it < H * RW; it += kThreads) {
+      const int r = it >> 2, w = it & 3;
+      uint32_t v = bits_at(s_bits, r * W + 32 * w);
+      if (w == 3) v &= 0xFu;  // columns 96..99
+      s_row[r][w] = v;
     }
-    s_col[x][seg] = m;
-  }
-  __syncthreads();
-  // 4. block histograms: one thread per (distinct block, cell); only pixels with a gradient are visited,
-  //    in OpenCV's accumulation order
-  if (tid < NUB * 4) {
-    const int ub = tid >> 2, cell = tid & 3;
-    const int ox = (ub / UBY) * 8, oy = (ub % UBY) * 8;
+    __syncthreads();
+    // 2. gradient sign planes ([-1,0,1] derivative with BORDER_REFLECT_101 on the binary image); every pixel with
+    //    a gradient is scattered into its column mask and flags its tile
+    for (int it = tid; it < H * RW; it += kThreads) {
+      const int r = it >> 2, w = it & 3;
+      const uint32_t cur = s_row[r][w];
+      const uint32_t prev = w > 0 ? s_row[r][w - 1] : 0u, next = w < 3 ? s_row[r][w + 1] : 0u;
+      uint32_t R = (cur >> 1) | (next << 31);   // pixel x+1
+      uint32_t L = (cur << 1) | (prev >> 31);   // pixel x-1
+      if (w == 0) L = (L & ~1u) | ((cur >> 1) & 1u);                 // x = 0 : left neighbour is pixel 1
+      if (w == 3) R = (R & ~(1u << 3)) | (((cur >> 2) & 1u) << 3);   // x = 99: right neighbour is pixel 98
+      const uint32_t U = s_row[r == 0 ? 1 : r - 1][w], D = s_row[r == H - 1 ? H - 2 : r + 1][w];
+      const uint32_t valid = w == 3 ? 0xFu : 0xFFFFFFFFu;
+      const uint32_t xp = R & ~L & valid, xn = L & ~R & valid, yp = D & ~U & valid, yn = U & ~D & valid;
+      s_xp[r][w] = xp;
+      s_xn[r][w] = xn;
+      s_yp[r][w] = yp;
+      s_yn[r][w] = yn;
+      uint32_t nz = xp | xn | yp | yn;
+      if (nz) {
+        const uint32_t tiles = ((nz & 0xFFu) ? 1u : 0u) | ((nz & 0xFF00u) ? 2u : 0u) | ((nz & 0xFF0000u) ? 4u : 0u) |
+                               ((nz & 0xFF000000u) ? 8u : 0u);
+        atomicOr(&s_tile[r >> 3], tiles << (4 * w));
+        const uint32_t rbit = 1u << (r & 31);
+        while (nz) {
+          const int x = 32 * w + __ffs(nz) - 1;
+          nz &= nz - 1;
+          atomicOr(&s_col[x][r >> 5], rbit);
+        }
+      }
+    }
+    __syncthreads();
+    // compact list of the flagged blocks (warp 0: three ballots over the 77 blocks)
+    if (warp == 0) {
+      int base = 0;
+      for (int u0 = 0; u0 < NUB; u0 += 32) {
+        const int ub = u0 + lane;
+        const bool f = ub < NUB && flagged(ub);
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        if (f) s_list[base + __popc(m & lt)] = uint8_t(ub);
+        base += __popc(m);
+      }
+      if (lane == 0) s_nflag = base;
+    }
+    __syncthreads();
+    const int nflag = s_nflag;
+    // 3. block histograms.  One WARP per (flagged block, cell).  The binary32 additions into a bin are a sequential
+    //    chain in OpenCV's pixel order, but finding the pixels and forming their contributions is not: lane L decodes
+    //    the pixels of run L of the cell (<= 24 runs of consecutive rows, in OpenCV's order) and stores their two
+    //    contributions at the run's prefix offset; then lane b < 9 walks the ordered records and adds what belongs to
+    //    bin b — the same values in the same order as HOGCache::getBlock.
+    for (int item = warp; item < nflag * 4; item += kThreads / 32) {
+      const int ub = s_list[item >> 2], cell = item & 3;
+      const int ox = (ub / UBY) * 8, oy = (ub % UBY) * 8;
+      float* hist = s_hist + ub * 36 + cell * 9;
+      CellRun run = {0, 0, 0, 0};
+      uint32_t m = 0;
+      int x = 0, y0 = 0;
+      if (lane < g_hog.n_runs[cell]) {
+        run = g_hog.runs[cell][lane];
+        x = ox + run.j;
+        y0 = oy + run.i0;
+        // bits y0 .. y0+len-1 of the 80-bit column mask
+        const int wq = y0 >> 5, sh = y0 & 31;
+        const uint32_t lo = s_col[x][wq], hi = wq < 2 ? s_col[x][wq + 1] : 0u;
+        m = __funnelshift_r(lo, hi, sh) & ((1u << run.len) - 1u);
+      }
+      // exclusive prefix of the per-lane pixel counts (< 16: a run has at most 12 rows) from four ballots
+      const int cnt = __popc(m);
+      int excl = 0, total = 0;
 #pragma unroll
-    for (int b = 0; b < 9; b++) s_acc[b][tid] = 0.f;
-    const int nr = s_nruns[cell];
-    for (int rI = 0; rI < nr; rI++) {
-      const CellRun run = s_runs[cell][rI];
-      const int x = ox + run.j, y0 = oy + run.i0;
-      // bits y0 .. y0+len-1 of the 80-bit column mask
-      const int wq = y0 >> 5, sh = y0 & 31;
-      const uint32_t lo = s_col[x][wq], hi = wq < 2 ? s_col[x][wq + 1] : 0u;
-      uint32_t m = __funnelshift_r(lo, hi, sh) & ((1u << run.len) - 1u);
+      for (int k = 0; k < 4; k++) {
+        const unsigned bal = __ballot_sync(0xffffffffu, (cnt >> k) & 1);
+        excl += __popc(bal & lt) << k;
+        total += __popc(bal) << k;
+      }
+      if (total == 0) {  // no outline pixel feeds this cell
+        if (lane < 9) hist[lane] = 0.f;
+        continue;
+      }
+      float4* rec = s_rec[warp];
+      int pos = excl;
       const int wx = x >> 5, bx = x & 31;
       while (m) {
         const int i = __ffs(m) - 1;
@@ -254,119 +306,139 @@ k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slo
         const int y = y0 + i;
         const int sx = int((s_xp[y][wx] >> bx) & 1u) - int((s_xn[y][wx] >> bx) & 1u);
         const int sy = int((s_yp[y][wx] >> bx) & 1u) - int((s_yn[y][wx] >> bx) & 1u);
-        const int c = (sy + 1) * 3 + (sx + 1);
-        const float wgt = s_w[cell][run.first + i];
-        const float a0 = __fmul_rn(s_g0[c], wgt), a1 = __fmul_rn(s_g1[c], wgt);
-        float* h0 = &s_acc[s_h0[c]][tid];
-        *h0 = __fadd_rn(*h0, a0);
-        float* h1 = &s_acc[s_h1[c]][tid];  // (h1 != h0: the two bins of a gradient are adjacent, never equal)
-        *h1 = __fadd_rn(*h1, a1);
+        const float4 cs = s_case[(sy + 1) * 3 + (sx + 1)];
+        const float wgt = __ldg(&g_hog.w[cell][run.first + i]);
+        rec[pos++] = make_float4(__fmul_rn(cs.x, wgt), __fmul_rn(cs.y, wgt), cs.z, cs.w);
+      }
+      __syncwarp();
+      if (lane < 9) {
+        float acc = 0.f;
+        // (the two bins of a gradient are adjacent, never equal)
+        auto take = [&](const float4& c4) {
+          const bool b0 = __float_as_int(c4.z) == lane, b1 = __float_as_int(c4.w) == lane;
+          if (b0 || b1) acc = __fadd_rn(acc, b0 ? c4.x : c4.y);
+        };
+        int r = 0;
+        for (; r + 4 <= total; r += 4) {  // four records in flight: the chain is only the additions
+          const float4 c0 = rec[r], c1 = rec[r + 1], c2 = rec[r + 2], c3 = rec[r + 3];
+          take(c0);
+          take(c1);
+          take(c2);
+          take(c3);
+        }
+        for (; r < total; r++) take(rec[r]);
+        hist[lane] = acc;
+      }
+      __syncwarp();  // the records are consumed before the next item overwrites them
+    }
+    __syncthreads();
+    // 4. L2-Hys normalisation per flagged block (HOGCache::normalizeBlockHistogram).  OpenCV keeps 4 interleaved
+    //    partial sums (element i goes to partial i mod 4) and combines them as (p0+p1)+(p2+p3): thread l of
+    //    a 4-thread group owns partial l, so the binary32 rounding sequence is identical.
+    for (int base = 0; base < nflag * 4; base += kThreads) {  // (CTA-uniform trip count: the shuffles need every lane)
+      const int it = base + tid;
+      const bool act = it < nflag * 4;
+      float* hist = s_hist + (act ? int(s_list[it >> 2]) : 0) * 36;
+      const int l = tid & 3, gbase = lane & ~3;
+      float v[9];
+      float part = 0.f;
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        v[k] = act ? hist[l + 4 * k] : 0.f;
+        part = __fadd_rn(part, __fmul_rn(v[k], v[k]));
+      }
+      float p0 = __shfl_sync(0xffffffffu, part, gbase), p1 = __shfl_sync(0xffffffffu, part, gbase + 1);
+      float p2 = __shfl_sync(0xffffffffu, part, gbase + 2), p3 = __shfl_sync(0xffffffffu, part, gbase + 3);
+      float sum = __fadd_rn(__fadd_rn(p0, p1), __fadd_rn(p2, p3));
+      float scale = __fdiv_rn(1.f, __fadd_rn(__fsqrt_rn(sum), __fmul_rn(36.f, 0.1f)));
+      part = 0.f;
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        v[k] = fminf(__fmul_rn(v[k], scale), 0.2f);
+        part = __fadd_rn(part, __fmul_rn(v[k], v[k]));
+      }
+      p0 = __shfl_sync(0xffffffffu, part, gbase);
+      p1 = __shfl_sync(0xffffffffu, part, gbase + 1);
+      p2 = __shfl_sync(0xffffffffu, part, gbase + 2);
+      p3 = __shfl_sync(0xffffffffu, part, gbase + 3);
+      sum = __fadd_rn(__fadd_rn(p0, p1), __fadd_rn(p2, p3));
+      scale = __fdiv_rn(1.f, __fadd_rn(__fsqrt_rn(sum), 1e-3f));
+      if (act) {  // (every entry is read and rewritten by the same thread)
+#pragma unroll
+        for (int k = 0; k < 9; k++) hist[l + 4 * k] = __fmul_rn(v[k], scale);
       }
     }
-#pragma unroll
-    for (int b = 0; b < 9; b++) s_hist[ub * 36 + cell * 9 + b] = s_acc[b][tid];
-  }
-  __syncthreads();
-  // 5. L2-Hys normalisation per block (HOGCache::normalizeBlockHistogram).  OpenCV keeps 4 interleaved
-  //    partial sums (element i goes to partial i mod 4) and combines them as (p0+p1)+(p2+p3): thread l of
-  //    a 4-thread group owns partial l, so the binary32 rounding sequence is identical.
-  {
-    const bool act = tid < NUB * 4;
-    float* hist = s_hist + (act ? (tid >> 2) : 0) * 36;
-    const int l = tid & 3, gbase = lane & ~3;
-    float v[9];
-    float part = 0.f;
-#pragma unroll
-    for (int k = 0; k < 9; k++) {
-      v[k] = act ? hist[l + 4 * k] : 0.f;  // (idle threads must not read block 0 while its owners rewrite it)
-      part = __fadd_rn(part, __fmul_rn(v[k], v[k]));
+    __syncthreads();
+    // descriptor group k4 (4 consecutive floats) -> distinct block and histogram entry:
+    // k = ((w*7 + bx)*7 + by)*36 + e
+    auto group_block = [&](int k4, int& e) -> int {
+      const int blk = k4 / 9;
+      e = (k4 - blk * 9) * 4;
+      const int by = blk % 7, bxw = blk / 7;          // bxw = w*7 + bx
+      const int ubx = (bxw / 7) * 4 + (bxw % 7);
+      return ubx * UBY + by;
+    };
+    if (descriptors)
+      for (int k4 = tid; k4 < AG_HOG_DIM / 4; k4 += kThreads) {
+        int e;
+        const int ub = group_block(k4, e);
+        float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);  // a block without an outline pixel: exact zeros
+        if (flagged(ub)) d4 = *reinterpret_cast<const float4*>(s_hist + ub * 36 + e);
+        reinterpret_cast<float4*>(descriptors + size_t(hyp) * AG_HOG_DIM)[k4] = d4;
+      }
+    if (block_flags && tid < kFlagWords) {
+      uint32_t f = 0;
+      for (int ub = tid * 32; ub < min(NUB, tid * 32 + 32); ub++) f |= (flagged(ub) ? 1u : 0u) << (ub & 31);
+      block_flags[size_t(hyp) * kFlagWords + tid] = f;
     }
-    float p0 = __shfl_sync(0xffffffffu, part, gbase), p1 = __shfl_sync(0xffffffffu, part, gbase + 1);
-    float p2 = __shfl_sync(0xffffffffu, part, gbase + 2), p3 = __shfl_sync(0xffffffffu, part, gbase + 3);
-    float sum = __fadd_rn(__fadd_rn(p0, p1), __fadd_rn(p2, p3));
-    float scale = __fdiv_rn(1.f, __fadd_rn(__fsqrt_rn(sum), __fmul_rn(36.f, 0.1f)));
-    part = 0.f;
-#pragma unroll
-    for (int k = 0; k < 9; k++) {
-      v[k] = fminf(__fmul_rn(v[k], scale), 0.2f);
-      part = __fadd_rn(part, __fmul_rn(v[k], v[k]));
-    }
-    p0 = __shfl_sync(0xffffffffu, part, gbase);
-    p1 = __shfl_sync(0xffffffffu, part, gbase + 1);
-    p2 = __shfl_sync(0xffffffffu, part, gbase + 2);
-    p3 = __shfl_sync(0xffffffffu, part, gbase + 3);
-    sum = __fadd_rn(__fadd_rn(p0, p1), __fadd_rn(p2, p3));
-    scale = __fdiv_rn(1.f, __fadd_rn(__fsqrt_rn(sum), 1e-3f));
-    if (act) {
-#pragma unroll
-      for (int k = 0; k < 9; k++) hist[l + 4 * k] = __fmul_rn(v[k], scale);
-    }
-  }
-  __syncthreads();
-  // descriptor group k4 (4 consecutive floats) -> histogram entry: k = ((w*7 + bx)*7 + by)*36 + e
-  auto desc4 = [&](int k4) -> float4 {
-    const int blk = k4 / 9, e = (k4 - blk * 9) * 4;
-    const int by = blk % 7, bxw = blk / 7;          // bxw = w*7 + bx
-    const int ubx = (bxw / 7) * 4 + (bxw % 7);
-    return *reinterpret_cast<const float4*>(s_hist + (ubx * UBY + by) * 36 + e);
-  };
-  if (descriptors)
-    for (int k4 = tid; k4 < AG_HOG_DIM / 4; k4 += kThreads)
-      reinterpret_cast<float4*>(descriptors + size_t(hyp) * AG_HOG_DIM)[k4] = desc4(k4);
-  // 6. SVM kernel values (CvSVMKernel::calc_non_rbf_base): binary32 products, 4-term binary32 sums,
-  //    binary64 accumulation.  One support vector: the whole CTA shares the dot product; many: one warp each.
-  auto group_term = [&](const float* sv, int k4) -> double {
-    const float4 s4 = __ldg(reinterpret_cast<const float4*>(sv) + k4);
-    const float4 d4 = desc4(k4);
-    float t = __fmul_rn(s4.x, d4.x);
-    t = __fadd_rn(t, __fmul_rn(s4.y, d4.y));
-    t = __fadd_rn(t, __fmul_rn(s4.z, d4.z));
-    t = __fadd_rn(t, __fmul_rn(s4.w, d4.w));
-    return double(t);
-  };
-  auto kernel_value = [&](double acc) -> float {
-    if (svm.kernel == 0) return float(acc * 1.0 + 0.0);
-    float kv = float(acc * svm.gamma + svm.coef0);
-    float b = kv, a = 1.f;  // cv::pow with an integer exponent: repeated binary32 multiplication
-    int p = svm.degree;
-    while (p > 1) {
-      if (p & 1) a = __fmul_rn(a, b);
-      b = __fmul_rn(b, b);
-      p >>= 1;
-    }
-    return __fmul_rn(a, b);
-  };
-  if (svm.sv_total == 0) continue;  // descriptors only: the batched kernels below score them (CTA uniform)
-  if (svm.sv_total == 1) {
+    if (svm.sv_total != 1) continue;  // descriptors only: the batched kernels below score them (CTA uniform)
+    // 5. SVM kernel value (CvSVMKernel::calc_non_rbf_base): binary32 products, 4-term binary32 sums, binary64
+    //    accumulation; the groups of blocks without an outline pixel are exact zeros and are skipped
+    //    (a distinct block column bx is column bx of window 0 when bx <= 6 and column bx - 4 of window 1 when bx >= 4)
     double acc = 0.0;
-    for (int k4 = tid; k4 < AG_HOG_DIM / 4; k4 += kThreads) acc += group_term(svm.sv, k4);
+    for (int e = tid; e < nflag * 18; e += kThreads) {
+      const int f = e / 18, rem = e - f * 18, w = rem >= 9 ? 1 : 0, g = rem - 9 * w;
+      const int ub = s_list[f], bx = ub / UBY, by = ub - bx * UBY;
+      if (w == 0 ? bx > 6 : bx < 4) continue;
+      const int k4 = ((w * 7 + (bx - 4 * w)) * 7 + by) * 9 + g;
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(svm.sv) + k4);
+      const float4 d4 = *reinterpret_cast<const float4*>(s_hist + ub * 36 + g * 4);
+      float t = __fmul_rn(s4.x, d4.x);
+      t = __fadd_rn(t, __fmul_rn(s4.y, d4.y));
+      t = __fadd_rn(t, __fmul_rn(s4.z, d4.z));
+      t = __fadd_rn(t, __fmul_rn(s4.w, d4.w));
+      acc += double(t);
+    }
     acc = warp_sum(acc);
     if (lane == 0) s_part[warp] = acc;
     __syncthreads();
     if (tid == 0) {
       double t = 0.0;
       for (int w2 = 0; w2 < kThreads / 32; w2++) t += s_part[w2];
-      s_K[0] = kernel_value(t);
+      float kv;
+      if (svm.kernel == 0) {
+        kv = float(t * 1.0 + 0.0);
+      } else {
+        kv = float(t * svm.gamma + svm.coef0);
+        float b = kv, a = 1.f;  // cv::pow with an integer exponent: repeated binary32 multiplication
+        int p = svm.degree;
+        while (p > 1) {
+          if (p & 1) a = __fmul_rn(a, b);
+          b = __fmul_rn(b, b);
+          p >>= 1;
+        }
+        kv = __fmul_rn(a, b);
+      }
+      // decision value: sum = -rho + alpha_0 * K   (CvSVM::predict)
+      double sum = -svm.rho;
+      if (svm.sv_count > 0) sum += alpha0 * double(kv);
+      const float sc = float(sum);
+      scores[score_by_slot ? slot : hyp] = sc;
+      if (grasps_out) {  // fused classify: write score and label into the compacted record
+        grasps_out[hyp].score = sc;
+        grasps_out[hyp].label = sc > 0.f ? 0 : 1;  // CvSVM::predict: label +1 <=> sum <= 0
+      }
     }
-  }
-  __syncthreads();
-  // decision value: sum = -rho + sum_k alpha_k * K[index_k]   (CvSVM::predict)
-  double part = 0.0;  // (one support vector here: models with more go through k_svm_gemm / k_svm_decide)
-  for (int kk = tid; kk < svm.sv_count && kk < 1; kk += kThreads) part += svm.alpha[kk] * double(s_K[0]);
-  part = warp_sum(part);
-  __syncthreads();
-  if (lane == 0) s_part[warp] = part;
-  __syncthreads();
-  if (tid == 0) {
-    double sum = -svm.rho;
-    for (int w2 = 0; w2 < kThreads / 32; w2++) sum += s_part[w2];
-    const float sc = float(sum);
-    scores[score_by_slot ? image_slots[hyp] : hyp] = sc;
-    if (grasps_out) {  // fused classify: write score and label into the compacted record
-      grasps_out[hyp].score = sc;
-      grasps_out[hyp].label = sc > 0.f ? 0 : 1;  // CvSVM::predict: label +1 <=> sum <= 0
-    }
-  }
   }  // hypothesis loop
 }
 
@@ -528,7 +600,8 @@ static int ensure_hog_tables(Ctx* c) {
     HogTables T;
     std::memset(&T, 0, sizeof(T));
     build_tables(T);
-    AG_CUDA_CHECK(cudaMemcpyToSymbol(c_hog, &T, sizeof(T)));
+    AG_CUDA_CHECK(cudaMemcpyToSymbol(g_hog, &T, sizeof(T)));
+    cudaFuncSetAttribute(k_hog_svm, cudaFuncAttributePreferredSharedMemoryCarveout, 100);  // 6 CTAs x 36 KB per SM
     g_tables_ready[c->device & 63] = true;
   }
   return AG_OK;
@@ -541,8 +614,8 @@ int hog_descriptors_device(Ctx* c, const uint32_t* d_images, const int* d_image_
   if (rc) return rc;
   SvmDev none;
   std::memset(&none, 0, sizeof(none));
-  k_hog_svm<<<std::min(n, kNumSMs * 6), kThreads, 0, c->stream>>>(d_images, d_image_slots, n, nullptr, none, d_descriptors,
-                                                                  nullptr, nullptr, 0);
+  k_hog_svm<<<std::min(n, kNumSMs * 16), kThreads, 0, c->stream>>>(d_images, d_image_slots, n, nullptr, none, d_descriptors,
+                                                                  nullptr, nullptr, 0, nullptr);
   c->launches += 1;
   AG_CUDA_CHECK(cudaGetLastError());
   return AG_OK;
@@ -576,7 +649,9 @@ int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d
   sd.gamma = svm->gamma;
   sd.coef0 = svm->coef0;
   sd.rho = svm->rho;
-  const int grid = n_dev ? std::min(n, kNumSMs * 6) : n;  // device-side count: persistent CTAs
+  // one CTA per hypothesis slot; the count lives on the device, CTAs beyond it leave at once and the block scheduler
+  // balances light and heavy images (the outline of a dense image costs 10x the average)
+  const int grid = std::min(n, kNumSMs * 16);
   if (svm->sv_total > 1) {
     // many support vectors: descriptors -> [H x 3528] . [3528 x sv_total] tiled product -> decision values
     float* desc = d_descriptors;
@@ -587,7 +662,7 @@ int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d
     if (c->kvals.reserve(size_t(n) * svm->sv_total * sizeof(float))) return AG_ERR_CUDA;
     SvmDev none = sd;
     none.sv_total = 0;
-    k_hog_svm<<<grid, kThreads, 0, c->stream>>>(d_images, d_image_slots, n, n_dev, none, desc, d_scores, nullptr, 0);
+    k_hog_svm<<<grid, kThreads, 0, c->stream>>>(d_images, d_image_slots, n, n_dev, none, desc, d_scores, nullptr, 0, nullptr);
     const dim3 gg((n + GM - 1) / GM, (svm->sv_total + GN - 1) / GN);
     k_svm_gemm<<<gg, kGemmThreads, 0, c->stream>>>(desc, svm->d_sv, n, n_dev, svm->sv_total, svm->kernel, svm->gamma,
                                                   svm->coef0, svm->degree, c->kvals.as<float>());
@@ -598,7 +673,7 @@ int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d
     c->launches += 3;
   } else {
     k_hog_svm<<<grid, kThreads, 0, c->stream>>>(d_images, d_image_slots, n, n_dev, sd, d_descriptors, d_scores,
-                                                 d_grasps_out, score_by_slot ? 1 : 0);
+                                                 d_grasps_out, score_by_slot ? 1 : 0, nullptr);
     c->launches += 1;
   }
   AG_CUDA_CHECK(cudaGetLastError());

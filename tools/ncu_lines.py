@@ -40,7 +40,7 @@ for r in data:
     tot_e += e; tot_s += s
 print('total warp inst', tot_e, 'samples', tot_s)
 srcs = {}
-for (f, l), (e, s) in sorted(agg.items(), key=lambda x: -x[1][1])[:top]:
+for (f, l), (e, s) in sorted(agg.items(), key=lambda x: (-x[1][1] if os.environ.get("BY","s")=="s" else -x[1][0]))[:top]:
     if f not in srcs:
         p = [os.path.join(os.path.dirname(os.path.abspath(obj)), f), os.path.join(os.path.dirname(os.path.abspath(obj)), '..', '..', 'include', f)]
         srcs[f] = next((open(q).read().splitlines() for q in p if os.path.exists(q)), [])
