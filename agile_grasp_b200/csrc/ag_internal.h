@@ -63,6 +63,7 @@ struct SvmModel {
   // device copies (created lazily per device)
   int device = -1;
   float* d_sv = nullptr;
+  float* d_svT = nullptr;  // many-vector models: support vectors regrouped [882 groups of 4][sv_total] (float4)
   double* d_alpha = nullptr;
   int* d_index = nullptr;
 };
@@ -157,6 +158,7 @@ struct Ctx {
   // sweep outputs
   DevBuf grasps_raw, valid, images_raw, hyp_slots, grasps, counters, scores, descriptors, kvals, sweep_dbg, overflow;
   DevBuf hyp_list;             // unordered hypothesis slots (sweep -> scorer)
+  DevBuf block_flags;          // per hypothesis: which HOG blocks hold an outline pixel (k_hog_svm -> k_svm_sparse)
   bool scores_by_slot = false; // c->scores is indexed by raw slot (fused linear scoring) instead of hypothesis number
   DevBuf handle_in, handle_bits;  // ag_find_handles: grasp records and the n x n inlier bit matrix
   int n_hyp = 0;

@@ -1055,7 +1055,7 @@ void ag_destroy(ag_ctx* h) {
   for (DevBuf* b : {&c.raw, &c.keys, &c.keys_sorted, &c.keys_unique, &c.cub_tmp, &c.block_counts, &c.misc, &c.bitmap, &c.tile_state, &c.vox,
                     &c.row_ptr, &c.col_ptr, &c.row_index, &c.all_frames,
                     &c.normals, &c.samples, &c.sample_stage, &c.samples_all, &c.nn_counts_all, &c.count_all, &c.moments, &c.frames, &c.nn_counts, &c.nbr_pool, &c.nbr_heads, &c.rand_raw, &c.rand_off, &c.rand_carry, &c.picks, &c.quad_par, &c.grasps_raw, &c.valid,
-                    &c.images_raw, &c.hyp_slots, &c.hyp_list, &c.grasps, &c.counters, &c.scores, &c.descriptors, &c.kvals, &c.handle_in, &c.handle_bits, &c.sweep_dbg, &c.overflow})
+                    &c.images_raw, &c.hyp_slots, &c.hyp_list, &c.block_flags, &c.grasps, &c.counters, &c.scores, &c.descriptors, &c.kvals, &c.handle_in, &c.handle_bits, &c.sweep_dbg, &c.overflow})
     b->release();
   if (c.h_pinned) cudaFreeHost(c.h_pinned);
   for (auto& ev : c.ev) cudaEventDestroy(ev);
@@ -1116,6 +1116,7 @@ void ag_svm_free(ag_svm* s) {
   if (!s) return;
   if (s->m->d_sv) {
     cudaFree(s->m->d_sv);
+    if (s->m->d_svT) cudaFree(s->m->d_svT);
     cudaFree(s->m->d_alpha);
     cudaFree(s->m->d_index);
   }

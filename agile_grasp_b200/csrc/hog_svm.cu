@@ -537,6 +537,85 @@ k_svm_gemm(const float* __restrict__ desc, const float* __restrict__ sv, int n_b
   }
 }
 
+// ---- kernel values of many-vector models from the NON-ZERO part of the descriptors ---------------------
+// Only the blocks that hold an outline pixel have non-zero descriptor entries (k_hog_svm), ~8 % of the 3528 at
+// config 2, and a zero group contributes an exact +-0 to calc_non_rbf_base's binary64 accumulation — so the kernel
+// value of (hypothesis, support vector) is the sum over the flagged groups only, in ascending feature order: the
+// same operations on the same values as the dense product above, bit for bit.  One CTA = SB hypotheses x 256
+// support vectors (blockIdx.y): the window blocks flagged in ANY of the SB hypotheses are staged in shared memory
+// (unflagged ones as zeros), thread = support vector: one coalesced 16-byte load of the transposed model per group
+// serves all SB hypotheses.
+constexpr int SB = 4, kSparseThreads = 256, kSparseChunk = 24;  // window blocks staged per pass
+__global__ void __launch_bounds__(kSparseThreads)
+k_svm_sparse(const float* __restrict__ desc, const uint32_t* __restrict__ flags, int n_bound, const int* __restrict__ n_dev,
+             const float4* __restrict__ svT, int nsv, int kernel, double gamma, double coef0, int degree,
+             float* __restrict__ kvals) {
+  __shared__ uint8_t s_wb[2 * 7 * 7];
+  __shared__ int s_nwb;
+  __shared__ __align__(16) float4 s_d[kSparseChunk * 9][SB];
+  const int n = n_dev ? min(*n_dev, n_bound) : n_bound;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int k = blockIdx.y * kSparseThreads + tid;  // this thread's support vector
+  for (int h0 = blockIdx.x * SB; h0 < n; h0 += gridDim.x * SB) {
+    const int nh = min(SB, n - h0);
+    __syncthreads();
+    if (tid < 32) {  // window blocks flagged in any hypothesis of the batch, ascending = ascending feature index
+      uint32_t f[kFlagWords] = {0u, 0u, 0u};
+      for (int i = 0; i < nh; i++)
+        for (int w = 0; w < kFlagWords; w++) f[w] |= flags[size_t(h0 + i) * kFlagWords + w];
+      int base = 0;
+      for (int w0 = 0; w0 < 98; w0 += 32) {
+        const int wb = w0 + lane;
+        bool on = false;
+        if (wb < 98) {
+          const int by = wb % 7, bxw = wb / 7, ub = ((bxw / 7) * 4 + bxw % 7) * UBY + by;
+          on = (f[ub >> 5] >> (ub & 31)) & 1u;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        if (on) s_wb[base + __popc(m & ((1u << lane) - 1u))] = uint8_t(wb);
+        base += __popc(m);
+      }
+      if (lane == 0) s_nwb = base;
+    }
+    __syncthreads();
+    const int nwb = s_nwb;
+    double acc[SB];
+#pragma unroll
+    for (int i = 0; i < SB; i++) acc[i] = 0.0;
+    for (int c0 = 0; c0 < nwb; c0 += kSparseChunk) {
+      const int cn = min(kSparseChunk, nwb - c0);
+      __syncthreads();
+      for (int e = tid; e < cn * 9 * SB; e += kSparseThreads) {  // stage: [window block][group][hypothesis]
+        const int i = e % SB, g = (e / SB) % 9, u = e / (SB * 9);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < nh) v = *reinterpret_cast<const float4*>(desc + size_t(h0 + i) * AG_HOG_DIM + int(s_wb[c0 + u]) * 36 + g * 4);
+        s_d[u * 9 + g][i] = v;
+      }
+      __syncthreads();
+      if (k < nsv) {
+        for (int u = 0; u < cn; u++) {
+          const float4* sv_g = svT + size_t(int(s_wb[c0 + u]) * 9) * nsv + k;
+#pragma unroll
+          for (int g = 0; g < 9; g++) {
+            const float4 b = __ldg(sv_g + size_t(g) * nsv);
+#pragma unroll
+            for (int i = 0; i < SB; i++) {
+              const float4 a = s_d[u * 9 + g][i];
+              float p = __fmul_rn(b.x, a.x);
+              p = __fadd_rn(p, __fmul_rn(b.y, a.y));
+              p = __fadd_rn(p, __fmul_rn(b.z, a.z));
+              p = __fadd_rn(p, __fmul_rn(b.w, a.w));
+              acc[i] += double(p);
+            }
+          }
+        }
+      }
+    }
+    if (k < nsv)
+      for (int i = 0; i < nh; i++) kvals[size_t(h0 + i) * nsv + k] = svm_kernel_value(acc[i], kernel, gamma, coef0, degree);
+  }
+}
+
 // decision value per hypothesis, in CvSVM::predict's order: sum = -rho; sum += alpha_k * K[index_k], k ascending.
 // One warp per 32 hypotheses: tiles of 32 x 32 kernel values are loaded coalesced into shared memory, then
 // lane r walks row r sequentially (binary64 multiply, then add — no contraction).  `identity` = index[k] == k
@@ -581,9 +660,11 @@ int svm_to_device(SvmModel* svm, int device) {
   if (svm->device == device && svm->d_sv) return AG_OK;
   if (svm->d_sv) {
     cudaFree(svm->d_sv);
+    if (svm->d_svT) cudaFree(svm->d_svT);
     cudaFree(svm->d_alpha);
     cudaFree(svm->d_index);
     svm->d_sv = nullptr;
+    svm->d_svT = nullptr;
   }
   AG_CUDA_CHECK(cudaMalloc(&svm->d_sv, svm->sv.size() * sizeof(float)));
   AG_CUDA_CHECK(cudaMalloc(&svm->d_alpha, svm->alpha.size() * sizeof(double)));
@@ -591,6 +672,15 @@ int svm_to_device(SvmModel* svm, int device) {
   AG_CUDA_CHECK(cudaMemcpy(svm->d_sv, svm->sv.data(), svm->sv.size() * sizeof(float), cudaMemcpyHostToDevice));
   AG_CUDA_CHECK(cudaMemcpy(svm->d_alpha, svm->alpha.data(), svm->alpha.size() * sizeof(double), cudaMemcpyHostToDevice));
   AG_CUDA_CHECK(cudaMemcpy(svm->d_index, svm->index.data(), svm->index.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (svm->sv_total > 1 && svm->var_count == AG_HOG_DIM) {
+    // k_svm_sparse reads group g (4 consecutive features) of consecutive support vectors with consecutive lanes
+    const int G = AG_HOG_DIM / 4, nsv = svm->sv_total;
+    std::vector<float> t(size_t(G) * nsv * 4);
+    for (int k = 0; k < nsv; k++)
+      for (int g = 0; g < G; g++) std::memcpy(&t[(size_t(g) * nsv + k) * 4], &svm->sv[size_t(k) * AG_HOG_DIM + g * 4], 16);
+    AG_CUDA_CHECK(cudaMalloc(&svm->d_svT, t.size() * sizeof(float)));
+    AG_CUDA_CHECK(cudaMemcpy(svm->d_svT, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   svm->device = device;
   return AG_OK;
 }
@@ -662,10 +752,21 @@ int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d
     if (c->kvals.reserve(size_t(n) * svm->sv_total * sizeof(float))) return AG_ERR_CUDA;
     SvmDev none = sd;
     none.sv_total = 0;
-    k_hog_svm<<<grid, kThreads, 0, c->stream>>>(d_images, d_image_slots, n, n_dev, none, desc, d_scores, nullptr, 0, nullptr);
-    const dim3 gg((n + GM - 1) / GM, (svm->sv_total + GN - 1) / GN);
-    k_svm_gemm<<<gg, kGemmThreads, 0, c->stream>>>(desc, svm->d_sv, n, n_dev, svm->sv_total, svm->kernel, svm->gamma,
-                                                  svm->coef0, svm->degree, c->kvals.as<float>());
+    if (c->block_flags.reserve(size_t(n) * kFlagWords * 4)) return AG_ERR_CUDA;
+    k_hog_svm<<<grid, kThreads, 0, c->stream>>>(d_images, d_image_slots, n, n_dev, none, desc, d_scores, nullptr, 0,
+                                                c->block_flags.as<uint32_t>());
+    static const bool dense = getenv("AG_SVM_DENSE") != nullptr;  // diagnostics: the dense tiled product
+    if (dense || !svm->d_svT) {
+      const dim3 gg((n + GM - 1) / GM, (svm->sv_total + GN - 1) / GN);
+      k_svm_gemm<<<gg, kGemmThreads, 0, c->stream>>>(desc, svm->d_sv, n, n_dev, svm->sv_total, svm->kernel, svm->gamma,
+                                                    svm->coef0, svm->degree, c->kvals.as<float>());
+    } else {
+      const dim3 gs(std::min((n + SB - 1) / SB, kNumSMs * 8), (svm->sv_total + kSparseThreads - 1) / kSparseThreads);
+      k_svm_sparse<<<gs, kSparseThreads, 0, c->stream>>>(desc, c->block_flags.as<uint32_t>(), n, n_dev,
+                                                         reinterpret_cast<const float4*>(svm->d_svT), svm->sv_total,
+                                                         svm->kernel, svm->gamma, svm->coef0, svm->degree,
+                                                         c->kvals.as<float>());
+    }
     bool identity = svm->sv_count <= svm->sv_total;
     for (int k = 0; k < svm->sv_count && identity; k++) identity = svm->index[k] == k;
     k_svm_decide<<<(n + 31) / 32, 32, 0, c->stream>>>(c->kvals.as<float>(), n, n_dev, sd, identity ? 1 : 0, d_scores,

@@ -238,6 +238,59 @@ k_ball_search(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr, c
   }
 }
 
+// ---- "more than 50 neighbours?" for ALL samples of a sharded call -------------------------------------
+// In the production normal mode a sample consumes 50 rand() draws iff its ball holds more than 50 points
+// (quadric.cpp:177-192), so a shard needs that one bit of every sample of the call to find its slice of the stream.
+// One warp per sample, one lane per x-row of the ball; every lane walks its candidate run from the middle outwards
+// (the points nearest in y first), two candidates per step straight from L2, and the warp stops as soon as the count
+// passes 50 — a few steps for a typical ball of ~260 points.  nn_counts[s].x = min(count, 51).
+__global__ void __launch_bounds__(kWarps * 32, 8)
+k_ball_over50(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr, const int* __restrict__ col_ptr,
+              const RowIndex* __restrict__ rip, const int* __restrict__ indices, int n_samples_max,
+              const int* __restrict__ d_count, float r2, double rpad, int2* __restrict__ nn_counts) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * kWarps + warp;
+  const RowIndex& ri = *rip;
+  if (s >= n_samples_max) return;
+  const int idx = s < *d_count ? indices[s] : -1;
+  if (idx < 0 || idx >= ri.n_points) {
+    if (lane == 0) nn_counts[s] = make_int2(0, 0);
+    return;
+  }
+  const GPoint q = pts[idx];
+  int n_out = 0;
+  int k_lo0 = 0, k_hi0 = -1, k_lo1 = 0, k_hi1 = -1;
+  if (ri.count[0] > 0) row_range(ri, 0, q.x, rpad, k_lo0, k_hi0);
+  if (ri.count[1] > 0) row_range(ri, 1, q.x, rpad, k_lo1, k_hi1);
+  const int nb0 = k_hi0 >= k_lo0 ? (k_hi0 - k_lo0) / 32 + 1 : 0;
+  const int nb1 = k_hi1 >= k_lo1 ? (k_hi1 - k_lo1) / 32 + 1 : 0;
+  for (int t = 0; t < nb0 + nb1 && n_out <= 50; t++) {
+    const int c = t < nb0 ? 0 : 1;
+    const int kb = c ? k_lo1 + (t - nb0) * 32 : k_lo0 + t * 32;
+    const int k_hi = c ? k_hi1 : k_hi0;
+    const int nrows = min(32, k_hi - kb + 1);
+    int j_lo = 0, j_end = 0;
+    if (lane < nrows) row_run(ri, row_ptr, col_ptr, pts, c, kb + lane, q.x, q.y, rpad, j_lo, j_end);
+    const int len = max(0, j_end - j_lo), mid = j_lo + (len >> 1);
+    const int steps = __reduce_max_sync(0xffffffffu, (len + 1) >> 1);
+    for (int i = 0; i < steps; i++) {
+      const int a = mid + i, b = mid - 1 - i;
+      bool oka = false, okb = false;
+      if (a < j_end) {
+        const float4 p = __ldg(reinterpret_cast<const float4*>(pts + a));
+        oka = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z) < r2;
+      }
+      if (b >= j_lo) {
+        const float4 p = __ldg(reinterpret_cast<const float4*>(pts + b));
+        okb = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z) < r2;
+      }
+      n_out += __popc(__ballot_sync(0xffffffffu, oka)) + __popc(__ballot_sync(0xffffffffu, okb));
+      if (n_out > 50) break;
+    }
+  }
+  if (lane == 0) nn_counts[s] = make_int2(min(n_out, 51), 0);
+}
+
 // ---- kernel 0+1 fused: radius search AND Taubin moments ------------------------------------------
 // The accepted points of the search are already in registers, so the 34 monomial moments are accumulated right
 // there instead of being streamed back from the neighbour lists by a second kernel (which made the lists' 16 B
@@ -1504,12 +1557,12 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
   }
   if (rand_mode && share) {
     // This context fits a SHARE of the call's samples (ag_params.shard_*), but the reference's rand() stream is
-    // consumed by every sample with more than 50 neighbours in sample order: count the neighbours of ALL samples
-    // (no lists), so that each of this share's samples finds the slice of the stream the unsharded call gives it
+    // consumed by every sample with more than 50 neighbours in sample order: that one bit of ALL samples is computed
+    // here (k_ball_over50), so that each of this share's samples finds the slice of the stream the unsharded call gives it
     const int blocks_all = (share->n_all + kWarps - 1) / kWarps;
-    k_ball_search<false><<<blocks_all, kWarps * 32, 0, c->stream>>>(
-        c->vox.as<GPoint>(), c->row_ptr.as<int>(), c->col_ptr.as<int>(), c->row_index.as<RowIndex>(), share->d_all, 0,
-        share->n_all, share->d_count_all, r2, rpad, nullptr, stride, c->nn_counts_all.as<int2>(), nullptr);
+    k_ball_over50<<<blocks_all, kWarps * 32, 0, c->stream>>>(c->vox.as<GPoint>(), c->row_ptr.as<int>(), c->col_ptr.as<int>(),
+                                                            c->row_index.as<RowIndex>(), share->d_all, share->n_all,
+                                                            share->d_count_all, r2, rpad, c->nn_counts_all.as<int2>());
     k_rand_offsets<<<1, 1024, 0, c->stream>>>(c->nn_counts_all.as<int2>(), 0, share->n_all, share->d_count_all, d_rand_off,
                                               c->rand_carry.as<int>());
     c->launches += 2;

@@ -61,20 +61,55 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe): NVML polled from a thread
+    every 2 ms (the timed region of a default run is ~40 ms, shorter than nvidia-smi's start-up), with
+    `nvidia-smi --query-gpu -lms` as the fallback when the NVML binding is missing."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.rows = []   # (host time the line arrived, fields)
-        self.proc = None
+        self.rows = []   # (host time, sm MHz, max MHz, [reason flags])
         self.index = index
         self.t_mark = None
+        self.proc = None
+        self.thread = None
+        self.stop_flag = False
+        self.source = None
 
     def mark(self):
-        """start of the timed region: only samples from here on are reported (the sampler itself is started
-        earlier, nvidia-smi needs a few hundred ms to deliver its first line)"""
+        """start of the timed region: only samples from here on are reported"""
         self.t_mark = time.perf_counter()
 
     def start(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            # (CUDA_VISIBLE_DEVICES remaps CUDA ordinals; NVML enumerates physical devices)
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.index < len(ids) and ids[self.index].isdigit():
+                    phys = int(ids[self.index])
+            h = N.nvmlDeviceGetHandleByIndex(phys)
+            mx = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            bits = [N.nvmlClocksThrottleReasonHwSlowdown, N.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    N.nvmlClocksThrottleReasonSwThermalSlowdown, N.nvmlClocksThrottleReasonSwPowerCap]
+
+            def poll():
+                while not self.stop_flag:
+                    try:
+                        sm = float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
+                        r = int(N.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.rows.append((time.perf_counter(), sm, mx, [bool(r & b) for b in bits]))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            self.source = "NVML, 2 ms period"
+            return
+        except Exception:
+            self.thread = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -82,40 +117,59 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
                                           "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+            self.source = "nvidia-smi -lms 20"
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = [r for t, r in self.rows if self.t_mark is None or t >= self.t_mark]
-        window = "timed region"
-        if not rows:  # the timed region was shorter than one sampling period: report the warm-up samples
-            rows, window = [r for t, r in self.rows], "warm-up (timed region shorter than the 20 ms sampling period)"
-        for r in rows:
+            c = [v.strip() for v in line.split(",")]
             try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                for nm, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
+                self.rows.append((time.perf_counter(), float(c[0]), float(c[1]),
+                                  [v.lower().startswith("active") for v in c[3:7]]))
             except Exception:
                 continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "window": window}
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        elif self.thread:
+            self.thread.join(timeout=1)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"]}
+        rows = [r for r in self.rows if self.t_mark is None or r[0] >= self.t_mark]
+        window = "timed region"
+        if not rows:  # the timed region was shorter than one sampling period: report the warm-up samples
+            rows, window = self.rows, "warm-up (timed region shorter than the sampling period)"
+        reasons = sorted({nm for r in rows for nm, f in zip(self.NAMES, r[3]) if f})
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": max(r[2] for r in rows),
+                "reasons": reasons, "samples": len(rows), "window": window, "source": self.source}
+
+
+def bind_to_gpu_cpus(index):
+    """N > 1: run this rank on the CPUs next to its GPU (NVML's ideal affinity) before any pinned buffer is allocated, so
+    that the pinned host clouds live on the GPU's NUMA node and eight concurrent H2D copies do not share one socket's
+    memory controllers.  Best effort."""
+    try:
+        import pynvml as N
+        N.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = index
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                phys = int(ids[index])
+        N.nvmlDeviceSetCpuAffinity(N.nvmlDeviceGetHandleByIndex(phys))
+        return True
+    except Exception:
+        return False
 
 
 def make_cloud(config, scene_offset):
@@ -168,7 +222,8 @@ def run_reference(args, rank, world):
     value, ms, hyp, cores = cpu_arm(clouds, det, args.steps, args.warmup)
     o_value, o_ms, o_hyp, _ = cpu_arm(clouds, 1 - det, max(1, min(args.steps, 2)), 0)
     n_pts = clouds[0][0].shape[0]
-    sample = (f"{args.steps} full clouds of the bench workload (scenes {list(SCENES)} alternating, as the GPU arm), "
+    sample = (f"{args.steps} full clouds of the bench workload after {args.warmup} untimed one(s) (scenes {list(SCENES)} "
+              "alternating, as the GPU arm), "
               f"OpenMP over samples on all {cores} host threads; std::set voxelisation and kd-tree as the reference; "
               "SVM parsed once")
     line = {
@@ -219,6 +274,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    bound = bind_to_gpu_cpus(local_rank) if world > 1 else False
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -417,7 +473,8 @@ def main():
             "e2e": {"value": float(e2e), "unit": "hyp/s", "ms_per_cloud": float(t_dev[1] / args.steps),
                     "h2d_bytes_per_step": int(c0["n"] * c0["stride"]),
                     "d2h_bytes_per_step": int(np.mean(e2e_h) * item + 64),
-                    "timer": "wall clock around ag_localize + ag_classify (+ gather wait), pinned host cloud"},
+                    "timer": "wall clock around ag_localize + ag_classify (+ gather wait), pinned host cloud"
+                             + (", rank bound to its GPU's CPUs" if bound else "")},
             "gpu_launches": int(np.sum(D["launches"])),
             "roofline": {"bound": "hbm",
                          "kernel": "k_ball_moments (radius search + Taubin moments, one kernel)" if fused
@@ -613,7 +670,7 @@ def main():
         # the oracle's OpenMP team and triple its time
         try:
             cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(args.cpu_steps),
-                   "--warmup", "0", "--normals", args.normals, "--config", str(args.config)]
+                   "--warmup", "1", "--normals", args.normals, "--config", str(args.config)]
             if "poly_svm" in line and "e2e" in line["poly_svm"]:
                 cmd.append("--poly")
             out = subprocess.run(cmd, capture_output=True, text=True, timeout=900,
