@@ -18,7 +18,7 @@ _LIB = None
 
 EXPORTS = [
     "ag_last_error", "ag_default_params", "ag_create", "ag_destroy", "ag_set_params", "ag_get_params",
-    "ag_get_timings", "ag_free", "ag_svm_load", "ag_svm_free", "ag_svm_info", "ag_localize", "ag_localize_device",
+    "ag_get_timings", "ag_set_stage_timing", "ag_free", "ag_svm_load", "ag_svm_free", "ag_svm_info", "ag_localize", "ag_localize_device",
     "ag_classify", "ag_set_svm", "ag_set_export_buffer", "ag_get_points", "ag_get_images", "ag_get_normals", "ag_train_features", "ag_remove_plane", "ag_preprocess", "ag_set_cloud", "ag_radius_search",
     "ag_fit_quadrics", "ag_hand_sweep", "ag_sweep_debug", "ag_hog_svm",
     "ag_find_handles", "ag_load_pcd", "ag_localize_batch", "ag_gather_slot_bytes", "ag_gather_create", "ag_gather_connect", "ag_gather_wait", "ag_gather_result", "ag_gather_destroy",
@@ -41,6 +41,7 @@ def lib():
     L.ag_set_params.argtypes = [vp, C.POINTER(AgParams)]
     L.ag_get_params.argtypes = [vp, C.POINTER(AgParams)]
     L.ag_get_timings.argtypes = [vp, C.POINTER(AgTimings)]
+    L.ag_set_stage_timing.argtypes = [vp, C.c_int]
     L.ag_free.argtypes = [vp]
     L.ag_svm_load.restype = vp
     L.ag_svm_load.argtypes = [C.c_char_p]
@@ -140,11 +141,13 @@ def load_pcd(path):
 class Context:
     """One GPU context = one `Localization` object of the reference."""
 
-    def __init__(self, device=0, params: AgParams = None):
+    def __init__(self, device=0, params: AgParams = None, stage_timing=True):
         h = lib().ag_create(int(device))
         if not h:
             raise AgError(lib().ag_last_error().decode())
         self.h = C.c_void_p(h)
+        # (tests and tools read the per-stage times; the library default — and bench.py's headline — is off)
+        lib().ag_set_stage_timing(self.h, 1 if stage_timing else 0)
         if params is not None:
             self.set_params(params)
 
@@ -158,6 +161,9 @@ class Context:
 
     def set_params(self, p: AgParams):
         _check(lib().ag_set_params(self.h, C.byref(p)))
+
+    def set_stage_timing(self, on):
+        lib().ag_set_stage_timing(self.h, 1 if on else 0)
 
     def timings(self):
         t = AgTimings()

@@ -116,6 +116,33 @@ __device__ __forceinline__ void row_run(const RowIndex& ri, const int* __restric
   j1 = lo1 < lo0 ? lo0 : lo1;
 }
 
+// ---- seeded stratified sample draw (replaces the time-seeded pcl::RandomSample, hand_search.cpp:36-39): sample k of
+// S lies in [floor(k n / S), floor((k + 1) n / S)), one index from each stratum -> sorted, distinct.  Runs on the
+// device because the voxel count n never visits the host mid-pipeline.
+__host__ __device__ inline uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+struct DrawArgs {   // a shard handles the samples k = k_first + j k_step, j < count (0, 1, s_req without sharding)
+  int* out;         // null: no draw
+  uint64_t seed;
+  int s_req, k_first, k_step, count;
+};
+__device__ __forceinline__ int draw_count(const DrawArgs& d, int n) {  // valid entries of d.out
+  const int S = d.s_req < n ? d.s_req : n;
+  return S > d.k_first ? min((S - d.k_first + d.k_step - 1) / d.k_step, d.count) : 0;
+}
+__device__ __forceinline__ int draw_sample(const DrawArgs& d, int n, int j) {
+  const int S = d.s_req < n ? d.s_req : n;
+  const int k = d.k_first + j * d.k_step;
+  if (k >= S) return -1;
+  const long long lo = (static_cast<long long>(k) * n) / S, hi = (static_cast<long long>(k + 1) * n) / S;
+  const uint64_t h = splitmix64(d.seed ^ splitmix64(uint64_t(k)));
+  return int(lo + static_cast<long long>(h % uint64_t(hi - lo)));
+}
+
 // ordered-int encoding of floats for atomicMin/atomicMax
 __device__ __forceinline__ int float_to_ordered(float f) {
   int i = __float_as_int(f);

@@ -1,6 +1,7 @@
 // ag_internal.h — host-side context and the launcher prototypes of each stage.
 #pragma once
 
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -179,6 +180,13 @@ struct Ctx {
   cudaEvent_t ev[10];
   cudaEvent_t ev_k[4];   // around k_ball_search / k_taubin_moments / k_taubin_axes
   int launches = 0;      // own-kernel launch counter (reset per localize call)
+  bool stage_timing = false;  // record the per-stage events (ag_set_stage_timing)
+  // ag_localize's pipeline: small resets and the sample draw ride on kernels of the voxelisation instead of being graph
+  // nodes of their own.  fold_resets: bit 0 counters, bit 1 sweep overflow counter, bit 2 rand() carry — set by the
+  // caller of preprocess_device, each bit cleared by the stage that would otherwise issue the memset.
+  unsigned fold_resets = 0;
+  void* fold_draw = nullptr;   // DrawArgs* (host) for the draw to fold into the voxel scan; draw_folded = it was
+  bool draw_folded = false;
 };
 
 int ctx_pinned(Ctx* c, size_t bytes);
@@ -186,6 +194,7 @@ int ctx_pinned(Ctx* c, size_t bytes);
 // timing events: inside a stream capture a plain cudaEventRecord only marks a dependency; the external flavour
 // becomes an event-record node that is executed (and can be timed) at every graph launch
 inline void record_event(Ctx* c, cudaEvent_t ev) {
+  if (!c->stage_timing) return;  // only the call's begin / end events (ag_set_stage_timing)
   if (c->capturing) cudaEventRecordWithFlags(ev, c->stream, cudaEventRecordExternal);
   else cudaEventRecord(ev, c->stream);
 }

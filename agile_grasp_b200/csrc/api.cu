@@ -69,33 +69,12 @@ int ctx_pinned(Ctx* c, size_t bytes) {
 }
 
 
-// ---- device-side sample handling -------------------------------------------------------------
-// stratified sorted distinct sample draw (replaces the time-seeded pcl::RandomSample,
-// hand_search.cpp:36-39): stratum k = [floor(k n/S), floor((k+1) n/S)), one index from each.
-// Runs on the device because the voxel count n never visits the host mid-pipeline.
-__host__ __device__ static inline uint64_t splitmix64(uint64_t x) {
-  x += 0x9E3779B97F4A7C15ull;
-  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-  return x ^ (x >> 31);
-}
-// seeded stratified draw: sample k of S lies in [k n / S, (k + 1) n / S).  A shard handles the samples
-// k = k_first + j k_step, j < count (count = launch bound; k_first = 0, k_step = 1 and count = s_req without sharding).
-__global__ void k_draw_samples(RowIndex* ri, int s_req, uint64_t seed, int* out, int k_first, int k_step, int count,
-                               int set_count = 1) {
+// ---- device-side sample handling (the draw itself: ag_common.cuh; ag_localize folds it into the voxel scan) -----
+__global__ void k_draw_samples(RowIndex* ri, DrawArgs d, int set_count = 1) {
   const int n = ri->n_points;
-  const int S = s_req < n ? s_req : n;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j == 0 && set_count) ri->n_samples = S > k_first ? min((S - k_first + k_step - 1) / k_step, count) : 0;
-  if (j >= count) return;
-  const int k = k_first + j * k_step;
-  if (k >= S) {
-    out[j] = -1;
-    return;
-  }
-  const long long lo = (static_cast<long long>(k) * n) / S, hi = (static_cast<long long>(k + 1) * n) / S;
-  const uint64_t h = splitmix64(seed ^ splitmix64(uint64_t(k)));
-  out[j] = int(lo + static_cast<long long>(h % uint64_t(hi - lo)));
+  if (j == 0 && set_count) ri->n_samples = draw_count(d, n);
+  if (j < d.count) d.out[j] = draw_sample(d, n, j);
 }
 __global__ void k_check_samples(RowIndex* ri, int s_req, const int* idx) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -552,7 +531,10 @@ static SvmModel* load_svm(const char* path) {
 
 static float elapsed(cudaEvent_t a, cudaEvent_t b) {
   float ms = 0.f;
-  cudaEventElapsedTime(&ms, a, b);
+  if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) {  // an event that was not recorded in this call
+    cudaGetLastError();
+    return 0.f;
+  }
   return ms;
 }
 
@@ -668,9 +650,37 @@ static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, in
   // per-kernel launch gaps); any change of shape, parameters or buffers falls back to the eager path.
   auto body = [&]() -> int {
     record_event(c, c->ev[1]);
+    // the buffers the voxelisation kernels reset / fill on the way (fold_resets, fold_draw) exist before it is enqueued
+    struct FoldGuard {  // nothing of this call's folding survives it (error paths included)
+      Ctx* c;
+      ~FoldGuard() {
+        c->fold_resets = 0;
+        c->fold_draw = nullptr;
+      }
+    } fold_guard{c};
+    DrawArgs draw;
+    std::memset(&draw, 0, sizeof(draw));
+    c->fold_resets = 0;
+    c->fold_draw = nullptr;
+    if (S > 0) {
+      if (c->samples.reserve(size_t(std::max(S, n_in)) * 4) || c->counters.reserve(64) ||
+          c->overflow.reserve(size_t(S + 1) * 4))
+        return AG_ERR_CUDA;
+      c->fold_resets = 1u | 2u | (c->params.deterministic_normals == 0 ? 4u : 0u);
+      if (!given && !(flags & (AG_FLAG_USE_CLUSTERING | AG_FLAG_CALC_ANTIPODAL))) {
+        draw.out = c->samples.as<int>();
+        draw.seed = c->params.seed;
+        draw.s_req = S_total;
+        draw.k_first = k_first;
+        draw.k_step = k_step;
+        draw.count = S;
+        c->fold_draw = &draw;
+      }
+    }
     int rc = quadric_rand_reset(c);
     if (rc) return rc;
     rc = preprocess_device(c, d_points, stride, n_in, size_left);
+    c->fold_draw = nullptr;
     if (rc) return rc;
     if (flags & AG_FLAG_USE_CLUSTERING) {  // localization.cpp:51-98 (training-time path: waits for the stream)
       rc = remove_plane_device(c);
@@ -683,7 +693,8 @@ static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, in
     if (c->samples.reserve(size_t(std::max(S, n_in)) * 4) || c->frames.reserve(size_t(S) * sizeof(ag_frame)) ||
         c->counters.reserve(64) || ensure_out(c, sizeof(HostOut) + slots * sizeof(ag_grasp)))
       return AG_ERR_CUDA;
-    AG_CUDA_CHECK(cudaMemsetAsync(c->counters.p, 0, 64, st));
+    if (c->fold_resets & 1u) c->fold_resets &= ~1u;  // (zeroed by k_init_state)
+    else AG_CUDA_CHECK(cudaMemsetAsync(c->counters.p, 0, 64, st));
     if (flags & AG_FLAG_CALC_ANTIPODAL) {
       // hand_search.cpp:17-26: normals for ALL points with radius 0.01 (launch bound = number of inputs)
       DevBuf& all_frames = c->all_frames;
@@ -699,13 +710,20 @@ static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, in
       AG_CUDA_CHECK(cudaMemcpyAsync(c->samples.p, c->sample_stage.p, size_t(S) * 4, cudaMemcpyDeviceToDevice, st));
       k_check_samples<<<(S + 255) / 256, 256, 0, st>>>(ri, S, c->samples.as<int>());
     } else {
-      k_draw_samples<<<(S + 255) / 256, 256, 0, st>>>(ri, S_total, c->params.seed, c->samples.as<int>(), k_first, k_step, S);
+      if (!c->draw_folded) {
+        DrawArgs d2 = {c->samples.as<int>(), c->params.seed, S_total, k_first, k_step, S};
+        k_draw_samples<<<(S + 255) / 256, 256, 0, st>>>(ri, d2);
+        c->launches += 1;
+      }
     }
-    c->launches += 1;
+    if (given) c->launches += 1;
     RandShare share;
     if (rand_share) {
       if (!given)  // (the full draw first: the share's own draw below leaves its count in ri->n_samples)
-        k_draw_samples<<<(S_total + 255) / 256, 256, 0, st>>>(ri, S_total, c->params.seed, c->samples_all.as<int>(), 0, 1, S_total, 0);
+      {
+        DrawArgs d3 = {c->samples_all.as<int>(), c->params.seed, S_total, 0, 1, S_total};
+        k_draw_samples<<<(S_total + 255) / 256, 256, 0, st>>>(ri, d3, 0);
+      }
       share.d_all = c->samples_all.as<int>();
       share.d_count_all = c->count_all.as<int>();
       share.n_all = S_total;
@@ -751,7 +769,7 @@ static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, in
   key.size_left = size_left;
   key.S = S;
   key.given = given ? 1 : 0;
-  key.flags = flags;
+  key.flags = flags | (c->stage_timing ? 0x80000000u : 0u);  // (a graph with and one without the stage events)
   key.state_gen = c->state_gen;
   key.svm = c->attached_svm;
   static const bool graphs_off = getenv("AG_NO_GRAPH") != nullptr;
@@ -1083,10 +1101,19 @@ int ag_get_params(ag_ctx* h, ag_params* p) {
   *p = h->c.params;
   return AG_OK;
 }
+int ag_set_stage_timing(ag_ctx* h, int on) {
+  h->c.stage_timing = on != 0;
+  return AG_OK;
+}
 int ag_get_timings(ag_ctx* h, ag_timings* t) {
   Ctx& c = h->c;
   if (c.timings_pending) {  // stage times of the last ag_localize, from the events recorded in its stream
     c.timings_pending = false;
+    c.timings.total_ms = elapsed(c.ev[0], c.ev[7]);
+    if (!c.stage_timing) {
+      *t = c.timings;
+      return AG_OK;
+    }
     c.timings.preprocess_ms = elapsed(c.ev[1], c.ev[2]);
     c.timings.grid_ms = 0.f;  // the x-row index is built inside the voxelisation pass
     c.timings.normals_all_ms = elapsed(c.ev[3], c.ev[4]);

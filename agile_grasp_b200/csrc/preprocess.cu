@@ -18,6 +18,7 @@
 //  * key sort (any extent): 64-bit keys, CUB radix sort + unique.  Taken when the lattice does not fit the
 //    bitmap; the device reports that (kErrBitmapRetry) and the host re-runs the call on this path.
 
+#include <cstring>
 #include <algorithm>
 
 #include <cub/cub.cuh>
@@ -72,7 +73,11 @@ __device__ __forceinline__ bool load_xyz(const char* base, int stride, int i, fl
   return isfinite(x) && isfinite(y) && isfinite(z);
 }
 
-__global__ void k_init_state(PreState* st) {
+struct ResetList {  // small device buffers zeroed by k_init_state (word counts)
+  unsigned* p[4];
+  int words[4];
+};
+__global__ void k_init_state(PreState* st, ResetList rl) {
   if (threadIdx.x == 0) {
     for (int c = 0; c < 2; c++)
       for (int a = 0; a < 3; a++) st->cam_min[c][a] = float_to_ordered(10000.0f);  // localization.cpp:251-252
@@ -87,6 +92,9 @@ __global__ void k_init_state(PreState* st) {
     st->emit_done = 0;
     st->epoch++;
   }
+  for (int k = 0; k < 4; k++)
+    if (rl.p[k])
+      for (int i = threadIdx.x; i < rl.words[k]; i += blockDim.x) rl.p[k][i] = 0u;
 }
 
 // number of finite points per block (needed only for the reference's label-after-compaction quirk)
@@ -278,7 +286,7 @@ __device__ __forceinline__ unsigned long long tile_pack(unsigned epoch, unsigned
 // (localization.cpp:318-351); cloud_normals_ of the voxel is zeroed (hand_search.cpp:13-14).
 __global__ void __launch_bounds__(kBlock)
 k_emit_bitmap(uint32_t* bitmap, unsigned long long* tile_state, double cell, PreState* st, GPoint* vox,
-              double* normals, RowIndex* ri, int* row_ptr, int row_stride, int* col_ptr) {
+              double* normals, RowIndex* ri, int* row_ptr, int row_stride, int* col_ptr, DrawArgs draw) {
   __shared__ int s_warp[kBlock / 32];
   __shared__ unsigned s_tile;
   __shared__ unsigned s_base;
@@ -327,20 +335,35 @@ k_emit_bitmap(uint32_t* bitmap, unsigned long long* tile_state, double cell, Pre
     __syncthreads();
     const unsigned tile = s_tile;
     if (tile >= n_tiles) {
-      // the last CTA to leave closes the descriptor from the sentinels of the column table
+      // the last CTA to leave closes the descriptor from the sentinels of the column table and, when asked to, draws
+      // the samples (the voxel count is known right here; used to be a launch of its own)
       __threadfence();
-      if (threadIdx.x == 0 && atomicAdd(&st->emit_done, 1u) == gridDim.x - 1 && words > 0) {
-        __threadfence();
-        const volatile int* cp = col_ptr;
-        const bool has0 = nx[0] > 0 && ny[0] > 0 && nzw[0] > 0, has1 = nx[1] > 0 && ny[1] > 0 && nzw[1] > 0;
-        const int end0 = has0 ? cp[col0[0] + nx[0] * ny[0]] : 0;
-        const int end1 = has1 ? cp[col0[1] + nx[1] * ny[1]] : end0;
-        ri->first[0] = 0;
-        ri->count[0] = end0;
-        ri->first[1] = end0;
-        ri->count[1] = end1 - end0;
-        ri->n_points = end1;
-        st->n_vox = end1;
+      if (threadIdx.x == 0) s_tile = atomicAdd(&st->emit_done, 1u) == gridDim.x - 1 ? 1u : 0u;
+      __syncthreads();
+      if (!s_tile) return;
+      if (threadIdx.x == 0) {
+        int n_points = 0;
+        if (words > 0) {
+          __threadfence();
+          const volatile int* cp = col_ptr;
+          const bool has0 = nx[0] > 0 && ny[0] > 0 && nzw[0] > 0, has1 = nx[1] > 0 && ny[1] > 0 && nzw[1] > 0;
+          const int end0 = has0 ? cp[col0[0] + nx[0] * ny[0]] : 0;
+          const int end1 = has1 ? cp[col0[1] + nx[1] * ny[1]] : end0;
+          ri->first[0] = 0;
+          ri->count[0] = end0;
+          ri->first[1] = end0;
+          ri->count[1] = end1 - end0;
+          ri->n_points = end1;
+          st->n_vox = end1;
+          n_points = end1;
+        }
+        s_base = unsigned(n_points);
+        if (draw.out) ri->n_samples = draw_count(draw, n_points);
+      }
+      __syncthreads();
+      if (draw.out) {
+        const int n_points = int(s_base);
+        for (int j = threadIdx.x; j < draw.count; j += blockDim.x) draw.out[j] = draw_sample(draw, n_points, j);
       }
       return;
     }
@@ -959,8 +982,28 @@ int preprocess_device(Ctx* c, const void* d_points, int stride, int n_in, int si
   int* d_block = c->block_counts.as<int>();
   uint8_t* d_flag = reinterpret_cast<uint8_t*>(d_block + nb);
   const char* pts = static_cast<const char*>(d_points);
-  AG_CUDA_CHECK(cudaMemsetAsync(c->row_index.p, 0, sizeof(RowIndex), c->stream));
-  k_init_state<<<1, 32, 0, c->stream>>>(st);
+  ResetList rl;
+  std::memset(&rl, 0, sizeof(rl));
+  rl.p[0] = c->row_index.as<unsigned>();
+  rl.words[0] = int(sizeof(RowIndex) / 4);
+  if ((c->fold_resets & 1u) && c->counters.p) {
+    rl.p[1] = c->counters.as<unsigned>();
+    rl.words[1] = 16;
+  } else {
+    c->fold_resets &= ~1u;
+  }
+  if ((c->fold_resets & 2u) && c->overflow.p) {
+    rl.p[2] = c->overflow.as<unsigned>();
+    rl.words[2] = 1;
+  } else {
+    c->fold_resets &= ~2u;
+  }
+  if ((c->fold_resets & 4u) && c->rand_carry.p) {
+    rl.p[3] = c->rand_carry.as<unsigned>();
+    rl.words[3] = 4;
+  }
+  c->fold_resets &= ~4u;  // (quadric_rand_reset ran before this call)
+  k_init_state<<<1, 64, 0, c->stream>>>(st, rl);
   const bool quirk = !P.fix_cam_source && size_left < n_in;
   if (quirk) {
     k_count_finite<<<nb, kBlock, 0, c->stream>>>(pts, stride, n_in, d_block);
@@ -970,12 +1013,17 @@ int preprocess_device(Ctx* c, const void* d_points, int stride, int n_in, int si
       pts, stride, n_in, size_left, quirk ? d_block : nullptr, P.workspace[0], P.workspace[1], P.workspace[2],
       P.workspace[3], P.workspace[4], P.workspace[5], d_flag, st, P.voxel_size,
       bitmap ? (unsigned long long)(kBitmapBytes / 4) : 0ull, kColCap, kb);
+  DrawArgs draw;
+  std::memset(&draw, 0, sizeof(draw));
+  if (c->fold_draw) draw = *static_cast<const DrawArgs*>(c->fold_draw);
+  c->draw_folded = false;
   if (bitmap) {
     k_mark<<<nb, kBlock, 0, c->stream>>>(pts, stride, n_in, d_flag, P.voxel_size, st, c->bitmap.as<uint32_t>());
     k_emit_bitmap<<<kNumSMs * 4, kBlock, 0, c->stream>>>(c->bitmap.as<uint32_t>(), c->tile_state.as<unsigned long long>(),
                                                          P.voxel_size, st, c->vox.as<GPoint>(), c->normals.as<double>(),
                                                          c->row_index.as<RowIndex>(), c->row_ptr.as<int>(), row_stride,
-                                                         c->col_ptr.as<int>());
+                                                         c->col_ptr.as<int>(), draw);
+    c->draw_folded = draw.out != nullptr;
     c->launches += quirk ? 6 : 4;  // init, [count, scan], classify, mark, emit
     AG_CUDA_CHECK(cudaGetLastError());
     return AG_OK;
@@ -1031,7 +1079,11 @@ int set_cloud_device(Ctx* c, int n) {
   const int one = 1;
   AG_CUDA_CHECK(cudaMemsetAsync(c->row_index.p, 0, sizeof(RowIndex), c->stream));
   AG_CUDA_CHECK(cudaMemcpyAsync(d_ok, &one, 4, cudaMemcpyHostToDevice, c->stream));
-  k_init_state<<<1, 32, 0, c->stream>>>(st);
+  {
+    ResetList none;
+    std::memset(&none, 0, sizeof(none));
+    k_init_state<<<1, 32, 0, c->stream>>>(st, none);
+  }
   if (n > 0) {
     const int nb = (n + kBlock - 1) / kBlock;
     k_cloud_min<<<nb, kBlock, 0, c->stream>>>(c->vox.as<GPoint>(), n, st);

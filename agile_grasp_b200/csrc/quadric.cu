@@ -301,11 +301,57 @@ k_ball_over50(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr, c
 // on the sample (a rejected candidate contributes exact zeros).  The 32 x 34 partial sums are transposed through
 // the staging buffer (two rounds of 16 moments, row pitch 33) and scaled by the power-of-two coordinate scale.
 constexpr int kFusedWarps = 4;
-__global__ void __launch_bounds__(kFusedWarps * 32, 4)
-k_ball_moments(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr, const int* __restrict__ col_ptr,
-               RowIndex* __restrict__ rip, const int* __restrict__ indices, int s0, int n_samples_max,
-               const int* __restrict__ d_count, float r2, double rpad, GPoint* __restrict__ pool, int stride,
-               int2* __restrict__ nn_counts, double scale, double* __restrict__ moments) {
+// non-deterministic normal mode: sample s consumes rand() draws [50 k_s, 50 k_s + 50), k_s = number of earlier
+// samples (in sample order, continuing across the launches of one call) with more than 50 neighbours
+// (one CTA, any multiple of 32 threads up to 1024)
+__device__ __forceinline__ void rand_offsets_block(const int2* __restrict__ nn_counts, int s0, int m, int cnt_valid,
+                                                   int* __restrict__ rand_off, int* __restrict__ carry, int* s_warp) {
+  // every warp owns a contiguous range of samples and walks it 32 at a time (coalesced, independent loads): a ballot
+  // of "more than 50 neighbours" per step; pass 1 counts, one block scan over the warps, pass 2 writes the offsets
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const int per = ((m + nw - 1) / nw + 31) & ~31, lo = min(m, warp * per), hi = min(m, lo + per);
+  auto flag = [&](int i) { return i < hi && s0 + i < cnt_valid && __ldcg(&nn_counts[s0 + i].x) > 50; };
+  // the ballots of pass 1 are kept (shared memory, up to kKeep steps per warp) so that pass 2 issues no loads
+  constexpr int kKeep = 64;
+  __shared__ unsigned s_mask[32][kKeep];
+  int tot = 0;
+#pragma unroll 8
+  for (int i0 = lo; i0 < hi; i0 += 32) {
+    const unsigned mask = __ballot_sync(0xffffffffu, flag(i0 + lane));
+    const int step = (i0 - lo) >> 5;
+    if (lane == 0 && step < kKeep) s_mask[warp][step] = mask;
+    tot += __popc(mask);
+  }
+  if (lane == 0) s_warp[warp] = tot;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < nw ? s_warp[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    s_warp[lane] = w;  // inclusive; entry 31 = the total
+  }
+  __syncthreads();
+  const int base = *carry;
+  int run = base + (warp > 0 ? s_warp[warp - 1] : 0);
+  for (int i0 = lo; i0 < hi; i0 += 32) {
+    const int step = (i0 - lo) >> 5;
+    const unsigned mask = step < kKeep ? s_mask[warp][step] : __ballot_sync(0xffffffffu, flag(i0 + lane));
+    if (i0 + lane < hi) rand_off[s0 + i0 + lane] = run + __popc(mask & lt);
+    run += __popc(mask);
+  }
+  __syncthreads();
+  if (tid == 0) *carry = base + s_warp[31];
+}
+__device__ __forceinline__ void ball_moments_warp(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr,
+                                                  const int* __restrict__ col_ptr, RowIndex* __restrict__ rip,
+                                                  const int* __restrict__ indices, int s0, int n_samples_max,
+                                                  const int* __restrict__ d_count, float r2, double rpad,
+                                                  GPoint* __restrict__ pool, int stride, int2* __restrict__ nn_counts,
+                                                  double scale, double* __restrict__ moments) {
   __shared__ __align__(16) GPoint s_cand[kFusedWarps][kStageCap];
   __shared__ __align__(8) unsigned long long s_bar[kFusedWarps];
   static_assert(kStageCap * sizeof(GPoint) >= 16 * 33 * sizeof(double), "the reduction reuses the staging buffer");
@@ -439,6 +485,30 @@ k_ball_moments(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr, 
     nn_counts[s] = make_int2(n_list, n_cand);
     if (n_out > stride) atomicOr(&rip->error, kErrBallOverflow);
   }
+}
+
+// The kernel: one warp per sample; in the production normal mode (rand_off != null) the CTA that finishes last also
+// lays out the rand() stream — sample s reads draws [50 k_s, 50 k_s + 50), k_s = number of earlier samples with more
+// than 50 neighbours — which used to be a launch of its own in front of the pick ranking.
+__global__ void __launch_bounds__(kFusedWarps * 32, 4)
+k_ball_moments(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr, const int* __restrict__ col_ptr,
+               RowIndex* __restrict__ rip, const int* __restrict__ indices, int s0, int n_samples_max,
+               const int* __restrict__ d_count, float r2, double rpad, GPoint* __restrict__ pool, int stride,
+               int2* __restrict__ nn_counts, double scale, double* __restrict__ moments, int* __restrict__ rand_off,
+               int* __restrict__ rand_carry) {
+  __shared__ int s_scan[32];
+  __shared__ int s_last;
+  ball_moments_warp(pts, row_ptr, col_ptr, rip, indices, s0, n_samples_max, d_count, r2, rpad, pool, stride, nn_counts,
+                    scale, moments);
+  if (!rand_off) return;
+  __threadfence();  // this CTA's neighbour counts are visible before it signs off
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&rand_carry[1], 1) == int(gridDim.x) - 1 ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  rand_offsets_block(nn_counts, s0, n_samples_max - s0, *d_count, rand_off, rand_carry, s_scan);
+  if (threadIdx.x == 0) rand_carry[1] = 0;  // ready for the next launch
 }
 
 // ---- kernel 1: moments ------------------------------------------------------------------------
@@ -1119,11 +1189,11 @@ k_taubin_solve(const RowIndex* __restrict__ rip, const int* __restrict__ indices
 // ---- kernel 2b (production normal mode only): which 50 neighbours the reference's rand() % n picks -------
 // The picks index the kd-tree's result order = ascending (distance, index).  Independent of the fit, so this
 // runs on a second stream next to the moments / solve kernels.  One warp per sample, everything in shared
-// memory: binary32 distances of the neighbours, a counting sort into 256 distance buckets (a monotone function of
-// the distance), then every lane finishes its buckets by insertion on (distance, position) — the list is in
-// index order, so the position breaks distance ties.  Voxel corners sit on a lattice, so whole groups of
-// neighbours share a distance up to rounding noise; sorting each group once is cheaper than ranking inside it
-// for every pick.  Output: 50 list positions per sample (samples with at most 50 neighbours evaluate all of
+// memory: binary32 distances of the neighbours, a STABLE counting sort into 256 distance buckets (a monotone
+// function of the distance), then every lane finishes its buckets by insertion on (distance, position) — the list is
+// in index order, so the position breaks distance ties.  Voxel corners sit on a lattice, so whole groups of
+// neighbours share a distance exactly; the stable scatter leaves them in order and the insertion pass only moves
+// elements of buckets that mix different distances.  Output: 50 list positions per sample (samples with at most 50 neighbours evaluate all of
 // them and get no picks).
 template <int CAP>
 __global__ void __launch_bounds__(kWarps * 32, 8)
@@ -1186,8 +1256,23 @@ k_rank_picks(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip,
     }
   }
   __syncwarp();
-  for (int i = lane; i < n_list; i += 32) order[atomicAdd(&cur[min(nb - 1, int(d2[i] * bscale))], 1)] = (unsigned short)i;
-  __syncwarp();
+  // STABLE scatter: 32 consecutive list positions per step, lanes of the same bucket take consecutive places in lane
+  // order (match.any), so neighbours with EQUAL distances — whole groups of them on the voxel lattice — land in
+  // list order, which is the kd-tree's tie-break; only buckets that mix different distances are left to sort
+  for (int i0 = 0; i0 < n_list; i0 += 32) {
+    const int i = i0 + lane;
+    const bool in = i < n_list;
+    const int b = in ? min(nb - 1, int(d2[i] * bscale)) : nb + lane;  // (idle lanes: a bucket of their own)
+    const unsigned grp = __match_any_sync(0xffffffffu, b);
+    const int rank = __popc(grp & ((1u << lane) - 1u));
+    const int base = in ? cur[b] : 0;
+    __syncwarp();
+    if (in) {
+      order[base + rank] = (unsigned short)i;
+      if (rank == __popc(grp) - 1) cur[b] = base + rank + 1;
+    }
+    __syncwarp();
+  }
   // cur[b] is now the end of bucket b; this lane owns buckets 8 lane .. 8 lane + 7 = one contiguous range
   {
     const int lo = first[0], hi = cur[8 * lane + 7];
@@ -1425,39 +1510,8 @@ k_axes_finish(GPoint* pts_c, const RowIndex* __restrict__ rip,
 __global__ void __launch_bounds__(1024)
 k_rand_offsets(const int2* __restrict__ nn_counts, int s0, int m, const int* __restrict__ d_count, int* __restrict__ rand_off,
                int* __restrict__ carry) {
-  // one pass: every thread owns a run of consecutive samples (flag = more than 50 neighbours), one block scan
   __shared__ int s_warp[32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int per = (m + 1023) / 1024, lo = min(m, tid * per), hi = min(m, lo + per);
-  const int cnt_valid = *d_count;
-  int f = 0;
-  for (int i = lo; i < hi; i++) f += (s0 + i < cnt_valid && nn_counts[s0 + i].x > 50) ? 1 : 0;
-  int v = f;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, v, o);
-    if (lane >= o) v += t;
-  }
-  if (lane == 31) s_warp[warp] = v;
-  __syncthreads();
-  if (warp == 0) {
-    int w = s_warp[lane];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += t;
-    }
-    s_warp[lane] = w;
-  }
-  __syncthreads();
-  const int base = *carry;
-  int run = base + v - f + (warp > 0 ? s_warp[warp - 1] : 0);
-  for (int i = lo; i < hi; i++) {
-    rand_off[s0 + i] = run;
-    run += (s0 + i < cnt_valid && nn_counts[s0 + i].x > 50) ? 1 : 0;
-  }
-  __syncthreads();
-  if (tid == 0) *carry = base + s_warp[31];
+  rand_offsets_block(nn_counts, s0, m, *d_count, rand_off, carry, s_warp);
 }
 
 // glibc rand() outputs after srand(1) — what a process that never seeds gets from the reference's
@@ -1493,6 +1547,7 @@ int quadric_rand_reset(Ctx* c) {
   if (c->params.deterministic_normals != 0) return AG_OK;
   // the carry lives in its own buffer: rand_off is re-sized per launch (DevBuf::reserve does not keep contents)
   if (c->rand_carry.reserve(16)) return AG_ERR_CUDA;
+  if (c->fold_resets & 4u) return AG_OK;  // (ag_localize: zeroed by k_init_state, which runs next)
   AG_CUDA_CHECK(cudaMemsetAsync(c->rand_carry.p, 0, 16, c->stream));
   return AG_OK;
 }
@@ -1590,14 +1645,16 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
       k_ball_moments<<<blocks, kFusedWarps * 32, 0, c->stream>>>(c->vox.as<GPoint>(), c->row_ptr.as<int>(),
                                                                  c->col_ptr.as<int>(), ri, d_indices, s0, s0 + m, d_count,
                                                                  r2, rpad, c->nbr_pool.as<GPoint>(), stride,
-                                                                 c->nn_counts.as<int2>(), inv_r, c->moments.as<double>());
+                                                                 c->nn_counts.as<int2>(), inv_r, c->moments.as<double>(),
+                                                                 (rand_mode && !share) ? d_rand_off : nullptr,
+                                                                 c->rand_carry.as<int>());
     if (timed) record_event(c, c->ev_k[1]);
     if (rand_mode) {
       // the reference's rand() % n picks depend on the neighbour lists only: ranked on a second stream while
       // this one accumulates the moments and solves the eigenproblem (fork / join by events, also under capture)
       AG_CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
       AG_CUDA_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-      if (!share)
+      if (!share && split)  // (the fused kernel's last CTA has laid the stream out already)
         k_rand_offsets<<<1, 1024, 0, c->stream2>>>(c->nn_counts.as<int2>(), s0, m, d_count, d_rand_off, c->rand_carry.as<int>());
       const int off_first = share ? share->first : 0, off_step = share ? share->step : 1;
       const size_t rank_smem = size_t(kWarps) * (size_t(stride <= 1024 ? 1024 : kRankCap) * 6 + kRankBuckets * 4);
@@ -1610,7 +1667,7 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
             c->vox.as<GPoint>(), ri, d_indices, s0, s0 + m, d_count, c->nbr_pool.as<GPoint>(), stride,
             c->nn_counts.as<int2>(), r2, d_rand, d_rand_off, off_first, off_step, c->picks.as<unsigned short>());
       AG_CUDA_CHECK(cudaEventRecord(c->ev_join, c->stream2));
-      c->launches += 2;
+      c->launches += (!share && split) ? 2 : 1;
     }
     if (split) {
       // warps per sample.  Measured on B200: a 2000-sample launch takes 10.2 / 11.3 / 14.3 us with 1 / 2 / 4 warps

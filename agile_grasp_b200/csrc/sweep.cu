@@ -973,7 +973,8 @@ int hand_sweep_enqueue(Ctx* c, const int* d_indices, int n, const ag_frame* d_fr
     cudaFuncSetAttribute(k_hand_sweep<kSlabCapBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_big));
     attr_set = true;
   }
-  AG_CUDA_CHECK(cudaMemsetAsync(A.overflow, 0, 4, c->stream));
+  if (c->fold_resets & 2u) c->fold_resets &= ~2u;  // (ag_localize: zeroed by k_init_state)
+  else AG_CUDA_CHECK(cudaMemsetAsync(A.overflow, 0, 4, c->stream));
   k_hand_sweep<kSlabCapSmall><<<n, kThreads, smem_small, c->stream>>>(A, c->hand);
   c->launches += 2;  // + k_compact_grasps
   c->sweep_flags = flags;

@@ -163,6 +163,11 @@ void ag_destroy(ag_ctx* ctx);
 int ag_set_params(ag_ctx* ctx, const ag_params* p);
 int ag_get_params(ag_ctx* ctx, ag_params* p);
 int ag_get_timings(ag_ctx* ctx, ag_timings* t);
+/* Per-stage times in ag_timings (preprocess_ms ... axes_ms) come from a dozen extra event records inside the
+ * pipeline (about 16 us per call as CUDA-graph nodes); off by default: total_ms and the counters are always
+ * filled, the stage fields read 0.  (The reference has no counterpart: it prints wall-clock times per stage,
+ * localization.cpp:100-135.) */
+int ag_set_stage_timing(ag_ctx* ctx, int on);
 void ag_free(void* p);
 
 /* SVM model in OpenCV-2.4 YAML ("!!opencv-ml-svm"), LINEAR or POLY kernels. */
