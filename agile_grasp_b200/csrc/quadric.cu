@@ -487,9 +487,10 @@ __device__ __forceinline__ void ball_moments_warp(const GPoint* __restrict__ pts
   }
 }
 
-// The kernel: one warp per sample; in the production normal mode (rand_off != null) the CTA that finishes last also
-// lays out the rand() stream — sample s reads draws [50 k_s, 50 k_s + 50), k_s = number of earlier samples with more
-// than 50 neighbours — which used to be a launch of its own in front of the pick ranking.
+// The kernel: one warp per sample.  With rand_off != null the CTA that finishes last also lays out the rand() stream
+// (rand_offsets_block); measured on B200 that epilogue lengthens this kernel — which is on the critical path — by
+// 7 us, while the separate k_rand_offsets launch runs on the side stream next to the eigen-solve, so ag_localize
+// passes null.
 __global__ void __launch_bounds__(kFusedWarps * 32, 4)
 k_ball_moments(const GPoint* __restrict__ pts, const int* __restrict__ row_ptr, const int* __restrict__ col_ptr,
                RowIndex* __restrict__ rip, const int* __restrict__ indices, int s0, int n_samples_max,
@@ -1630,6 +1631,10 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
     const char* e = getenv("AG_MOMENTS");
     return !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'f' ? 2 : 0));
   }();
+  static const bool fold_offsets = [] {  // AG_RAND_FOLD=0|1 (measurements): rand() stream layout inside k_ball_moments
+    const char* e = getenv("AG_RAND_FOLD");
+    return e ? atoi(e) != 0 : true;
+  }();
   for (int s0 = 0; s0 < n; s0 += chunk) {
     const int m = std::min(chunk, n - s0);
     const bool split = forced_variant ? forced_variant == 1 : m > 16384;
@@ -1646,7 +1651,7 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
                                                                  c->col_ptr.as<int>(), ri, d_indices, s0, s0 + m, d_count,
                                                                  r2, rpad, c->nbr_pool.as<GPoint>(), stride,
                                                                  c->nn_counts.as<int2>(), inv_r, c->moments.as<double>(),
-                                                                 (rand_mode && !share) ? d_rand_off : nullptr,
+                                                                 (fold_offsets && rand_mode && !share) ? d_rand_off : nullptr,
                                                                  c->rand_carry.as<int>());
     if (timed) record_event(c, c->ev_k[1]);
     if (rand_mode) {
@@ -1654,7 +1659,7 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
       // this one accumulates the moments and solves the eigenproblem (fork / join by events, also under capture)
       AG_CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
       AG_CUDA_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-      if (!share && split)  // (the fused kernel's last CTA has laid the stream out already)
+      if (!share && (split || !fold_offsets))
         k_rand_offsets<<<1, 1024, 0, c->stream2>>>(c->nn_counts.as<int2>(), s0, m, d_count, d_rand_off, c->rand_carry.as<int>());
       const int off_first = share ? share->first : 0, off_step = share ? share->step : 1;
       const size_t rank_smem = size_t(kWarps) * (size_t(stride <= 1024 ? 1024 : kRankCap) * 6 + kRankBuckets * 4);
@@ -1667,7 +1672,7 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
             c->vox.as<GPoint>(), ri, d_indices, s0, s0 + m, d_count, c->nbr_pool.as<GPoint>(), stride,
             c->nn_counts.as<int2>(), r2, d_rand, d_rand_off, off_first, off_step, c->picks.as<unsigned short>());
       AG_CUDA_CHECK(cudaEventRecord(c->ev_join, c->stream2));
-      c->launches += (!share && split) ? 2 : 1;
+      c->launches += (!share && (split || !fold_offsets)) ? 2 : 1;
     }
     if (split) {
       // warps per sample.  Measured on B200: a 2000-sample launch takes 10.2 / 11.3 / 14.3 us with 1 / 2 / 4 warps

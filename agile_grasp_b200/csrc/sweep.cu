@@ -27,9 +27,9 @@ namespace ag {
 namespace {
 
 constexpr int kThreads = 256;       // 8 warps = 8 orientations (rotating_hand.cpp:13)
-constexpr int kSlabCapSmall = 1920; // slab points kept in shared memory by the common kernel (37.5 KB, 3 CTAs / SM)
+constexpr int kSlabCapSmall = 1920; // slab points kept in shared memory by the common kernel (37.5 KB; 55 KB per CTA, 4 CTAs / SM)
 constexpr int kSlabCapBig = 9600;   // fallback instantiation for dense neighbourhoods (187.5 KB, 1 CTA / SM)
-constexpr int kStage = 2048;        // candidates staged per pass of the ball gather (32 KB, reused by phase B)
+constexpr int kStage = 1024;        // candidates staged per pass of the ball gather (16 KB, reused by phase B)
 
 struct SweepArgs {
   const GPoint* pts;
@@ -101,14 +101,14 @@ __host__ __device__ inline unsigned long long slot_masks_exact(const double* spa
 constexpr float kLutMargin = 1e-4f;  // distance (in slot steps / depth steps) from a threshold below which the
                                      // exact comparisons decide instead of the table
 
-// Shared memory of one CTA.  The 32 KB `u` block is the TMA staging buffer of the ball gather (phase A) and
-// then, per orientation, the depth-level slot masks and the grasp image (phase B).
+// Shared memory of one CTA.  The 16 KB `u` block is the TMA staging buffer of the ball gather (phase A) and
+// then, per orientation, the depth-level slot masks (two lanes share a word: reductions) and — once those are
+// consumed — the grasp image in the same bytes (phase B).
 struct SweepShared {
   union {
     GPoint stage[kStage];
     struct {
-      unsigned long long lvl[8][12][32];  // per warp, depth level and lane: (side << 32 | in) slot masks
-      uint32_t img[8][AG_IMAGE_WORDS];
+      unsigned long long lvl[8][12][16];  // per warp, depth level and lane pair: (side << 32 | in) slot masks
     } b;
   } u;
   unsigned long long lut[AG_SWEEP_LUT];  // slot masks per zone between two slot edges
@@ -121,7 +121,7 @@ struct SweepShared {
 };
 
 template <int CAP>
-__global__ void __launch_bounds__(kThreads, CAP <= 2048 ? 3 : 1)
+__global__ void __launch_bounds__(kThreads, CAP <= 2048 ? 4 : 1)
 k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   SweepShared& sh = *reinterpret_cast<SweepShared*>(s_raw);
@@ -324,8 +324,8 @@ k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
   unsigned fingers_last = 0;
   bool have = false;
   double minY = 1e300, maxY = -1e300;
-  uint32_t* img = sh.u.b.img[warp];
-  for (int i = lane; i < AG_IMAGE_WORDS; i += 32) img[i] = 0u;
+  uint32_t* img = reinterpret_cast<uint32_t*>(&sh.u.b.lvl[warp][0][0]);  // (after the level masks have been read)
+  static_assert(sizeof(unsigned long long) * 12 * 16 >= sizeof(uint32_t) * AG_IMAGE_WORDS, "image fits the level masks");
   const bool cam_ok = !(dot3e(approach, camv0) > 0 && dot3e(approach, camv1) > 0);  // rotating_hand.cpp:99
   if (cam_ok) {
     // pass 1: slot masks per depth level.  Every boolean of FingerHand is "is there a point with y < d_t whose x
@@ -334,9 +334,10 @@ k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
     // by the zone of x (slot edges are two interleaved uniform grids, so the zone is a floor and a fraction
     // test); a point closer than kLutMargin steps to an edge — or a hand geometry without the table — takes the
     // reference's own comparisons slot by slot.  Same for the depth level of y.
-    unsigned long long(*lvl)[32] = sh.u.b.lvl[warp];
-#pragma unroll
-    for (int t = 0; t < 12; t++) lvl[t][lane] = 0ull;
+    unsigned long long(*lvl)[16] = sh.u.b.lvl[warp];
+    uint32_t* lvl32 = reinterpret_cast<uint32_t*>(&lvl[0][lane & 15]);  // level t: words [32 t] (in), [32 t + 1] (side)
+    for (int i = lane; i < 12 * 16; i += 32) (&lvl[0][0])[i] = 0ull;
+    __syncwarp();
     const double deepest = hc.bite[hc.n_depths - 1];
     const float phi = hc.lut_phi;
 #pragma unroll 2
@@ -368,14 +369,16 @@ k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
       }
       // the point is cropped in at every depth level d_t > ry, i.e. at levels t >= L = #{t : d_t <= ry}
       // (L < n_depths here); record it at level L only, the prefix-OR below spreads it upwards
-      lvl[L][lane] |= m;
+      if (unsigned(m)) atomicOr(lvl32 + 32 * L, unsigned(m));
+      if (unsigned(m >> 32)) atomicOr(lvl32 + 32 * L + 1, unsigned(m >> 32));
     }
+    __syncwarp();
     unsigned IN[12], SD[12];
     {
       unsigned long long acc = 0ull;
 #pragma unroll
       for (int t = 0; t < 12; t++) {
-        acc |= lvl[t][lane];
+        acc |= lvl[t][lane & 15];
         IN[t] = unsigned(acc);
         SD[t] = unsigned(acc >> 32);
       }
@@ -417,6 +420,9 @@ k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
     if (lane == 0) A.valid[slot] = 0;
     return;
   }
+  __syncwarp();  // the level masks have been consumed: their bytes become this orientation's grasp image
+  for (int i = lane; i < AG_IMAGE_WORDS; i += 32) img[i] = 0u;
+  __syncwarp();
 
   // ---- grasp parameters (finger_hand.cpp:117-171, rotating_hand.cpp:118-154) --------------------
   const double hor = hc.half_od + hc.spacing[e_idx];
