@@ -152,6 +152,7 @@ struct Ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   size_t rand_count = 0;
   int rand_consumed_bound = 0;
+  int rand_slot = 0;  // word of rand_carry holding the current carry (0 or 2: k_rank_picks reads one, writes the other)
   DevBuf nbr_heads;  // per sample of the chunk: sample xyz + neighbour count (float4)
   DevBuf nbr_pool;   // neighbour lists of the current chunk of samples: stride x 16-byte records per sample
   bool two_cams = false;  // the last cloud had points of both cameras (sizes the neighbour pool)

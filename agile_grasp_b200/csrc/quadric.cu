@@ -1201,11 +1201,40 @@ __global__ void __launch_bounds__(kWarps * 32, 8)
 k_rank_picks(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip, const int* __restrict__ indices,
              int s0, int n_samples_max, const int* __restrict__ d_count, const GPoint* __restrict__ pool, int stride,
              const int2* __restrict__ nn_counts, float r2_f, const uint32_t* __restrict__ rand_raw,
-             const int* __restrict__ rand_off, int off_first, int off_step, unsigned short* __restrict__ picks_out) {
+             const int* __restrict__ rand_off, int off_first, int off_step, unsigned short* __restrict__ picks_out,
+             const int* __restrict__ carry_in, int* __restrict__ carry_out) {
   extern __shared__ __align__(16) unsigned char s_rank[];
+  __shared__ int s_cnt[kWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sl = blockIdx.x * kWarps + warp;
   const int s = s0 + sl;
+  // carry_in != null (launches of a few thousand samples): no separate layout of the rand() stream — the CTA counts
+  // the earlier samples of this launch with more than 50 neighbours itself (coalesced reads of the counts, at most
+  // a few per thread), so sample s reads draws [50 k_s, 50 k_s + 50) with k_s = carry + that count; the last CTA
+  // leaves the carry of the next launch in carry_out (a different word: the other CTAs still read carry_in)
+  int self_off = 0;
+  if (carry_in) {
+    const int cnt_valid = min(*d_count, n_samples_max);
+    const int first = s0 + int(blockIdx.x) * kWarps;
+    int c = 0;
+    for (int i = s0 + int(threadIdx.x); i < first; i += kWarps * 32) c += (i < cnt_valid && nn_counts[i].x > 50) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) s_cnt[warp] = c;
+    __syncthreads();
+    int before = *carry_in;
+    for (int w = 0; w < kWarps; w++) before += s_cnt[w];
+    int mine = 0;  // the samples of this CTA in front of this warp's
+    for (int w = 0; w < kWarps; w++) {
+      const int f = (first + w < cnt_valid && nn_counts[first + w].x > 50) ? 1 : 0;
+      if (w < warp) mine += f;
+      if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0 && w == kWarps - 1) {
+        int tot = before;
+        for (int w2 = 0; w2 < kWarps; w2++) tot += (first + w2 < cnt_valid && nn_counts[first + w2].x > 50) ? 1 : 0;
+        *carry_out = tot;
+      }
+    }
+    self_off = before + mine;
+  }
   if (s >= n_samples_max || s >= *d_count) return;
   const int idx = indices[s];
   if (idx < 0 || idx >= rip->n_points) return;
@@ -1293,7 +1322,7 @@ k_rank_picks(const GPoint* __restrict__ pts_c, const RowIndex* __restrict__ rip,
     }
   }
   __syncwarp();
-  const uint32_t* raw = rand_raw + size_t(50) * size_t(rand_off[off_first + s * off_step]);
+  const uint32_t* raw = rand_raw + size_t(50) * size_t(carry_in ? self_off : rand_off[off_first + s * off_step]);
 #pragma unroll
   for (int u = 0; u < 2; u++) {
     const int t = lane + 32 * u;
@@ -1545,6 +1574,7 @@ static int ball_stride(double radius, double voxel, bool two_cams) {
 
 int quadric_rand_reset(Ctx* c) {
   c->rand_consumed_bound = 0;
+  c->rand_slot = 0;
   if (c->params.deterministic_normals != 0) return AG_OK;
   // the carry lives in its own buffer: rand_off is re-sized per launch (DevBuf::reserve does not keep contents)
   if (c->rand_carry.reserve(16)) return AG_ERR_CUDA;
@@ -1620,7 +1650,7 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
                                                             c->row_index.as<RowIndex>(), share->d_all, share->n_all,
                                                             share->d_count_all, r2, rpad, c->nn_counts_all.as<int2>());
     k_rand_offsets<<<1, 1024, 0, c->stream>>>(c->nn_counts_all.as<int2>(), 0, share->n_all, share->d_count_all, d_rand_off,
-                                              c->rand_carry.as<int>());
+                                              c->rand_carry.as<int>() + c->rand_slot);
     c->launches += 2;
   }
   // search + moments: ONE kernel for launches of a few thousand samples (latency bound: 23.7 vs 26 us at 2000
@@ -1651,28 +1681,37 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
                                                                  c->col_ptr.as<int>(), ri, d_indices, s0, s0 + m, d_count,
                                                                  r2, rpad, c->nbr_pool.as<GPoint>(), stride,
                                                                  c->nn_counts.as<int2>(), inv_r, c->moments.as<double>(),
-                                                                 (fold_offsets && rand_mode && !share) ? d_rand_off : nullptr,
-                                                                 c->rand_carry.as<int>());
+                                                                 (fold_offsets && rand_mode && !share && m > 4096) ? d_rand_off : nullptr,
+                                                                 c->rand_carry.as<int>() + c->rand_slot);
     if (timed) record_event(c, c->ev_k[1]);
     if (rand_mode) {
       // the reference's rand() % n picks depend on the neighbour lists only: ranked on a second stream while
       // this one accumulates the moments and solves the eigenproblem (fork / join by events, also under capture)
       AG_CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
       AG_CUDA_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-      if (!share && (split || !fold_offsets))
-        k_rand_offsets<<<1, 1024, 0, c->stream2>>>(c->nn_counts.as<int2>(), s0, m, d_count, d_rand_off, c->rand_carry.as<int>());
+      // layout of the rand() stream: small launches let k_rank_picks count for itself (no extra node, no serial tail),
+      // large ones fold the scan into k_ball_moments' last CTA (or run k_rand_offsets after the two-kernel search)
+      const bool self_off = !share && !split && m <= 4096 && fold_offsets;
+      int* carry = c->rand_carry.as<int>();
+      const int* carry_in = self_off ? carry + c->rand_slot : nullptr;
+      int* carry_out = self_off ? carry + (c->rand_slot ^ 2) : nullptr;
+      if (!share && !self_off && (split || !fold_offsets))
+        k_rand_offsets<<<1, 1024, 0, c->stream2>>>(c->nn_counts.as<int2>(), s0, m, d_count, d_rand_off, carry + c->rand_slot);
       const int off_first = share ? share->first : 0, off_step = share ? share->step : 1;
       const size_t rank_smem = size_t(kWarps) * (size_t(stride <= 1024 ? 1024 : kRankCap) * 6 + kRankBuckets * 4);
       if (stride <= 1024)
         k_rank_picks<1024><<<blocks, kWarps * 32, rank_smem, c->stream2>>>(
             c->vox.as<GPoint>(), ri, d_indices, s0, s0 + m, d_count, c->nbr_pool.as<GPoint>(), stride,
-            c->nn_counts.as<int2>(), r2, d_rand, d_rand_off, off_first, off_step, c->picks.as<unsigned short>());
+            c->nn_counts.as<int2>(), r2, d_rand, d_rand_off, off_first, off_step, c->picks.as<unsigned short>(), carry_in,
+            carry_out);
       else
         k_rank_picks<kRankCap><<<blocks, kWarps * 32, rank_smem, c->stream2>>>(
             c->vox.as<GPoint>(), ri, d_indices, s0, s0 + m, d_count, c->nbr_pool.as<GPoint>(), stride,
-            c->nn_counts.as<int2>(), r2, d_rand, d_rand_off, off_first, off_step, c->picks.as<unsigned short>());
+            c->nn_counts.as<int2>(), r2, d_rand, d_rand_off, off_first, off_step, c->picks.as<unsigned short>(), carry_in,
+            carry_out);
+      if (self_off) c->rand_slot ^= 2;
       AG_CUDA_CHECK(cudaEventRecord(c->ev_join, c->stream2));
-      c->launches += (!share && (split || !fold_offsets)) ? 2 : 1;
+      c->launches += (!share && !self_off && (split || !fold_offsets)) ? 2 : 1;
     }
     if (split) {
       // warps per sample.  Measured on B200: a 2000-sample launch takes 10.2 / 11.3 / 14.3 us with 1 / 2 / 4 warps
