@@ -149,7 +149,7 @@ struct Ctx {
   DevBuf rand_raw, rand_off, rand_carry, picks;
   DevBuf quad_par;             // quadric parameters per sample (k_taubin_solve -> k_axes_finish)
   cudaStream_t stream2 = nullptr;  // side branch of the pipeline (rank selection next to the eigen-solve)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork0 = nullptr;
   size_t rand_count = 0;
   int rand_consumed_bound = 0;
   int rand_slot = 0;  // word of rand_carry holding the current carry (0 or 2: k_rank_picks reads one, writes the other)
@@ -160,6 +160,8 @@ struct Ctx {
   // sweep outputs
   DevBuf grasps_raw, valid, images_raw, hyp_slots, grasps, counters, scores, descriptors, kvals, sweep_dbg, overflow;
   DevBuf hyp_list;             // unordered hypothesis slots (sweep -> scorer)
+  DevBuf sample_q;             // per sample of the last fit: x, y, z, (index << 1 | camera) — read by the sweep instead of
+                               // the indices -> cloud chain of dependent loads
   DevBuf block_flags;          // per hypothesis: which HOG blocks hold an outline pixel (k_hog_svm -> k_svm_sparse)
   bool scores_by_slot = false; // c->scores is indexed by raw slot (fused linear scoring) instead of hypothesis number
   DevBuf handle_in, handle_bits;  // ag_find_handles: grasp records and the n x n inlier bit matrix
@@ -167,6 +169,7 @@ struct Ctx {
   bool images_valid = false;
   unsigned serial = 0, call_gen = 0;  // context number and call counter behind the record stamp
   uint8_t stamp = 0;                  // ag_grasp.reserved of every record of the last localize / sweep call
+  bool sweep_from_fit = false;       // the last sweep's samples came with sample_q records
   unsigned sweep_flags = 0;          // arguments of the last hand_sweep_enqueue (for the overflow re-run)
   const int* sweep_indices = nullptr;
   const ag_frame* sweep_frames = nullptr;
@@ -219,7 +222,7 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
 int quadric_rand_reset(Ctx* c);
 // enqueue only (no sync): sweep + stable compaction; the hypothesis count stays in device memory
 int hand_sweep_enqueue(Ctx* c, const int* d_indices, int n, const ag_frame* d_frames, unsigned flags,
-                       bool fork_compact = false);
+                       bool fork_compact = false, bool frames_from_fit = false);
 int* hand_sweep_list_ptr(Ctx* c);        // unordered list of hypothesis slots of the last sweep
 int* hand_sweep_list_count_ptr(Ctx* c);
 // after a sync: handles samples whose slab overflowed the small instantiation; returns the hypothesis count

@@ -738,7 +738,7 @@ static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, in
     // compaction for the export runs beside it; models with many support vectors go through the ordered list
     const bool fork = c->attached_svm && c->attached_svm->sv_total == 1;
     rc = hand_sweep_enqueue(c, c->samples.as<int>(), S, c->frames.as<ag_frame>(),
-                            c->params.filters_boundaries ? 0x100u : 0u, fork);
+                            c->params.filters_boundaries ? 0x100u : 0u, fork, true);
     if (rc) return rc;
     d_nsel = hand_sweep_count_ptr(c, S);
     record_event(c, c->ev[8]);
@@ -1051,6 +1051,7 @@ ag_ctx* ag_create(int device) {
   cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c.ev_fork0, cudaEventDisableTiming);
   for (auto& ev : c.ev) cudaEventCreate(&ev);
   for (auto& ev : c.ev_k) cudaEventCreate(&ev);
   ag_default_params(&c.params);
@@ -1073,13 +1074,14 @@ void ag_destroy(ag_ctx* h) {
   for (DevBuf* b : {&c.raw, &c.keys, &c.keys_sorted, &c.keys_unique, &c.cub_tmp, &c.block_counts, &c.misc, &c.bitmap, &c.tile_state, &c.vox,
                     &c.row_ptr, &c.col_ptr, &c.row_index, &c.all_frames,
                     &c.normals, &c.samples, &c.sample_stage, &c.samples_all, &c.nn_counts_all, &c.count_all, &c.moments, &c.frames, &c.nn_counts, &c.nbr_pool, &c.nbr_heads, &c.rand_raw, &c.rand_off, &c.rand_carry, &c.picks, &c.quad_par, &c.grasps_raw, &c.valid,
-                    &c.images_raw, &c.hyp_slots, &c.hyp_list, &c.block_flags, &c.grasps, &c.counters, &c.scores, &c.descriptors, &c.kvals, &c.handle_in, &c.handle_bits, &c.sweep_dbg, &c.overflow})
+                    &c.images_raw, &c.hyp_slots, &c.hyp_list, &c.sample_q, &c.block_flags, &c.grasps, &c.counters, &c.scores, &c.descriptors, &c.kvals, &c.handle_in, &c.handle_bits, &c.sweep_dbg, &c.overflow})
     b->release();
   if (c.h_pinned) cudaFreeHost(c.h_pinned);
   for (auto& ev : c.ev) cudaEventDestroy(ev);
   for (auto& ev : c.ev_k) cudaEventDestroy(ev);
   cudaEventDestroy(c.ev_fork);
   cudaEventDestroy(c.ev_join);
+  cudaEventDestroy(c.ev_fork0);
   cudaStreamDestroy(c.stream2);
   cudaStreamDestroy(c.stream);
   delete h;

@@ -1339,15 +1339,26 @@ k_axes_finish(GPoint* pts_c, const RowIndex* __restrict__ rip,
               double cam0x, double cam0y, double cam0z, double cam1x, double cam1y, double cam1z,
               ag_frame* __restrict__ frames, double* normals_out /* may be null */,
               const unsigned short* __restrict__ picks_in /* null = deterministic normals */,
-              unsigned long long* __restrict__ counters) {
+              unsigned long long* __restrict__ counters, float4* __restrict__ sample_q) {
   __shared__ double s_T[kWarps][28];  // weighted order-6 normal tensor
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sl = blockIdx.x * kWarps + warp;
   const int s = s0 + sl;
-  if (s >= n_samples_max || s >= *d_count) return;
+  if (s >= n_samples_max) return;
   double* sT = s_T[warp];
-  const int idx = indices[s];
-  if (idx < 0 || idx >= rip->n_points) return;
+  const int idx = s < *d_count ? indices[s] : -1;
+  const bool is_sample = idx >= 0 && idx < rip->n_points;
+  // what the hand sweep needs to know about sample s in ONE record (it would otherwise chase indices -> cloud):
+  // x, y, z and (index << 1 | camera); -1 for a slot that holds no sample
+  if (sample_q && lane == 0) {
+    float4 v = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    if (is_sample) {
+      const GPoint qs = pts_c[idx];
+      v = make_float4(qs.x, qs.y, qs.z, __int_as_float((idx << 1) | int(qs.tag & kTagCamBit)));
+    }
+    sample_q[s] = v;
+  }
+  if (!is_sample) return;
   const GPoint* list = pool + size_t(sl) * size_t(stride);
   const int2 nnc = nn_counts[s];
   const int n_list = nnc.x;
@@ -1592,7 +1603,7 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
   constexpr size_t kPoolBytes = size_t(4) << 30;
   const int chunk = int(std::min<size_t>(size_t(n), std::max<size_t>(kWarps, kPoolBytes / (size_t(stride) * sizeof(GPoint)))));
   if (c->moments.reserve(size_t(n) * kMomentStride * sizeof(double)) || c->nn_counts.reserve(size_t(n) * 8) ||
-      c->quad_par.reserve(size_t(n) * 12 * sizeof(double)) ||
+      c->quad_par.reserve(size_t(n) * 12 * sizeof(double)) || c->sample_q.reserve(size_t(n) * sizeof(float4)) ||
       c->counters.reserve(64) || c->nbr_pool.reserve(size_t(chunk) * size_t(stride) * sizeof(GPoint)) ||
       c->nbr_heads.reserve(size_t(chunk) * sizeof(float4)))
     return AG_ERR_CUDA;
@@ -1645,12 +1656,15 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
     // This context fits a SHARE of the call's samples (ag_params.shard_*), but the reference's rand() stream is
     // consumed by every sample with more than 50 neighbours in sample order: that one bit of ALL samples is computed
     // here (k_ball_over50), so that each of this share's samples finds the slice of the stream the unsharded call gives it
+    // (on the side stream, next to this share's own search: only the pick ranking needs the result)
+    AG_CUDA_CHECK(cudaEventRecord(c->ev_fork0, c->stream));
+    AG_CUDA_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_fork0, 0));
     const int blocks_all = (share->n_all + kWarps - 1) / kWarps;
-    k_ball_over50<<<blocks_all, kWarps * 32, 0, c->stream>>>(c->vox.as<GPoint>(), c->row_ptr.as<int>(), c->col_ptr.as<int>(),
-                                                            c->row_index.as<RowIndex>(), share->d_all, share->n_all,
-                                                            share->d_count_all, r2, rpad, c->nn_counts_all.as<int2>());
-    k_rand_offsets<<<1, 1024, 0, c->stream>>>(c->nn_counts_all.as<int2>(), 0, share->n_all, share->d_count_all, d_rand_off,
-                                              c->rand_carry.as<int>() + c->rand_slot);
+    k_ball_over50<<<blocks_all, kWarps * 32, 0, c->stream2>>>(c->vox.as<GPoint>(), c->row_ptr.as<int>(), c->col_ptr.as<int>(),
+                                                             c->row_index.as<RowIndex>(), share->d_all, share->n_all,
+                                                             share->d_count_all, r2, rpad, c->nn_counts_all.as<int2>());
+    k_rand_offsets<<<1, 1024, 0, c->stream2>>>(c->nn_counts_all.as<int2>(), 0, share->n_all, share->d_count_all, d_rand_off,
+                                               c->rand_carry.as<int>() + c->rand_slot);
     c->launches += 2;
   }
   // search + moments: ONE kernel for launches of a few thousand samples (latency bound: 23.7 vs 26 us at 2000
@@ -1739,7 +1753,7 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
         c->vox.as<GPoint>(), ri, d_indices, s0, s0 + m, d_count, c->nbr_pool.as<GPoint>(), stride,
         c->nn_counts.as<int2>(), inv_r, c->moments.as<double>(), c->quad_par.as<double>(), h.cam[0][0], h.cam[0][1],
         h.cam[0][2], h.cam[1][0], h.cam[1][1], h.cam[1][2], d_frames, write_normals ? c->normals.as<double>() : nullptr,
-        rand_mode ? c->picks.as<unsigned short>() : nullptr, ctr);
+        rand_mode ? c->picks.as<unsigned short>() : nullptr, ctr, c->sample_q.as<float4>());
     if (timed) record_event(c, c->ev_k[3]);
     c->launches += split ? 4 : 3;
   }

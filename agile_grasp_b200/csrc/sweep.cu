@@ -49,6 +49,7 @@ struct SweepArgs {
   int* hyp_count;
   int* overflow;          // [0] = number of samples whose slab exceeded the capacity, [1..] their slots
   const int* sample_list; // if non-null: blockIdx.x indexes this list of sample slots (fallback pass)
+  const float4* sample_q; // if non-null: x, y, z, (index << 1 | camera) of every sample slot (left by the fit; -1: no sample)
   int n_samples;
   float r2;
   double rpad;
@@ -132,13 +133,25 @@ k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
   const RowIndex& ri = *A.ri;
-  const int idx = (s < ri.n_samples) ? A.indices[s] : -1;
+  int idx;
+  GPoint q;
+  if (A.sample_q) {  // one load instead of the dependent pair indices -> cloud
+    const float4 v = A.sample_q[s];
+    const int w = __float_as_int(v.w);
+    idx = (s < ri.n_samples && w >= 0) ? (w >> 1) : -1;
+    q.x = v.x;
+    q.y = v.y;
+    q.z = v.z;
+    q.tag = uint32_t(w) & kTagCamBit;
+  } else {
+    idx = (s < ri.n_samples) ? A.indices[s] : -1;
+    if (idx >= 0 && idx < ri.n_points) q = A.pts[idx];
+  }
   if (idx < 0 || idx >= ri.n_points) {  // unused sample slot (fewer voxels than requested samples)
     if (lane == 0) A.valid[size_t(s) * 8 + warp] = 0;
     if (threadIdx.x == 0 && A.slab_counts) A.slab_counts[s] = 0;
     return;
   }
-  const GPoint q = A.pts[idx];
   const int sample_cam = (q.tag & kTagCamBit) ? 1 : 0;  // hands_cam_source (hand_search.cpp:40-42, App. B#3)
   const uint32_t bar = smem_u32(&sh.bar);
   if (threadIdx.x == 0) {
@@ -224,57 +237,67 @@ k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
         if (threadIdx.x < nc && b > a)
           bulk_g2s(smem_u32(&sh.u.stage[a - base]), A.pts + j0 + (a - pre), uint32_t(b - a) * 16u, bar);
       }
-      mbar_wait(bar, parity);
+      if (warp == 0) mbar_wait(bar, parity);  // one warp polls the barrier, the others sleep at the CTA barrier
+      __syncthreads();
       parity ^= 1u;
-      for (int i0 = 0; i0 < cnt; i0 += kThreads) {
-        const int i = i0 + threadIdx.x;
-        bool keep = false, inball = false;
-        GPoint p;
-        float cx = 0.f, cy = 0.f, cz = 0.f;
-        if (i < cnt) {
-          p = sh.u.stage[i];
-          if (dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z) < A.r2) {
+      // two candidates per thread and step (independent loads and tests), one reservation of slab places per warp
+      for (int i0 = 0; i0 < cnt; i0 += 2 * kThreads) {
+        bool keep[2] = {false, false};
+        GPoint p[2];
+        float cx[2], cy[2], cz[2];
+        unsigned in_any = 0;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const int i = i0 + u * kThreads + threadIdx.x;
+          bool inball = false;
+          cx[u] = cy[u] = cz[u] = 0.f;
+          p[u] = sh.u.stage[i < cnt ? i : 0];
+          if (i < cnt && dist2_flann(q.x, q.y, q.z, p[u].x, p[u].y, p[u].z) < A.r2) {
             inball = true;
             // hand_search.cpp:157-158: subtraction in binary32, then cast
-            cx = __fsub_rn(p.x, q.x);
-            cy = __fsub_rn(p.y, q.y);
-            cz = __fsub_rn(p.z, q.z);
+            cx[u] = __fsub_rn(p[u].x, q.x);
+            cy[u] = __fsub_rn(p[u].y, q.y);
+            cz[u] = __fsub_rn(p[u].z, q.z);
             // slab test -h < z_hand < h (rotating_hand.cpp:44): decided in binary32 when the point is clearly
             // inside or outside (the binary32 value is within 1e-7 of the binary64 one), exactly otherwise
-            const float hzf = fmaf(fzx, cx, fmaf(fzy, cy, fzz * cz));
+            const float hzf = fmaf(fzx, cx[u], fmaf(fzy, cy[u], fzz * cz[u]));
             const float az = fabsf(hzf);
-            if (az < hh - 1e-5f) keep = true;
+            if (az < hh - 1e-5f) keep[u] = true;
             else if (az <= hh + 1e-5f) {
-              const double hz = (F[0][2] * double(cx) + F[1][2] * double(cy)) + F[2][2] * double(cz);
-              keep = hz > -1.0 * hc.hand_height && hz < hc.hand_height;
+              const double hz = (F[0][2] * double(cx[u]) + F[1][2] * double(cy[u])) + F[2][2] * double(cz[u]);
+              keep[u] = hz > -1.0 * hc.hand_height && hz < hc.hand_height;
             }
           }
+          in_any += __popc(__ballot_sync(0xffffffffu, inball));
         }
-        n_ball += __popc(__ballot_sync(0xffffffffu, inball));
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (m) {
+        n_ball += in_any;
+        const unsigned m0 = __ballot_sync(0xffffffffu, keep[0]), m1 = __ballot_sync(0xffffffffu, keep[1]);
+        if (m0 | m1) {
           int wbase = 0;
-          if (lane == 0) wbase = atomicAdd(&sh.count, __popc(m));
+          if (lane == 0) wbase = atomicAdd(&sh.count, __popc(m0) + __popc(m1));
           wbase = __shfl_sync(0xffffffffu, wbase, 0);
-          const int pos = wbase + __popc(m & lt);
-          if (keep && pos < CAP) {
-            const double px = double(cx), py = double(cy), pz = double(cz);
-            double2 h;  // frame^T * p (rotating_hand.cpp:26)
-            h.x = (F[0][0] * px + F[1][0] * py) + F[2][0] * pz;
-            h.y = (F[0][1] * px + F[1][1] * py) + F[2][1] * pz;
-            slab_xy[pos] = h;
-            uint32_t tag = p.tag & 3u;
-            if (tag & kTagNormalBit) {  // the point index is only needed to fetch its normal: row of position base + i
-              const int g = base + i;
-              int lo_r = 0, hi_r = nc - 1;
-              while (lo_r < hi_r) {
-                const int mid = (lo_r + hi_r + 1) >> 1;
-                if (sh.run_pre[mid] <= g) lo_r = mid;
-                else hi_r = mid - 1;
+#pragma unroll
+          for (int u = 0; u < 2; u++) {
+            const int pos = wbase + (u ? __popc(m0) + __popc(m1 & lt) : __popc(m0 & lt));
+            if (keep[u] && pos < CAP) {
+              const double px = double(cx[u]), py = double(cy[u]), pz = double(cz[u]);
+              double2 h;  // frame^T * p (rotating_hand.cpp:26)
+              h.x = (F[0][0] * px + F[1][0] * py) + F[2][0] * pz;
+              h.y = (F[0][1] * px + F[1][1] * py) + F[2][1] * pz;
+              slab_xy[pos] = h;
+              uint32_t tag = p[u].tag & 3u;
+              if (tag & kTagNormalBit) {  // the point index is only needed to fetch its normal: row of position base + i
+                const int g = base + i0 + u * kThreads + int(threadIdx.x);
+                int lo_r = 0, hi_r = nc - 1;
+                while (lo_r < hi_r) {
+                  const int mid = (lo_r + hi_r + 1) >> 1;
+                  if (sh.run_pre[mid] <= g) lo_r = mid;
+                  else hi_r = mid - 1;
+                }
+                tag |= uint32_t(sh.run_start[lo_r] + (g - sh.run_pre[lo_r])) << 2;
               }
-              tag |= uint32_t(sh.run_start[lo_r] + (g - sh.run_pre[lo_r])) << 2;
+              slab_tag[pos] = tag;
             }
-            slab_tag[pos] = tag;
           }
         }
       }
@@ -882,6 +905,7 @@ static SweepArgs make_args(Ctx* c, const int* d_indices, int n, const ag_frame* 
   A.hyp_list = c->hyp_list.as<int>();
   A.hyp_count = reinterpret_cast<int*>(c->counters.as<unsigned long long>() + 4);
   A.sample_list = nullptr;
+  A.sample_q = nullptr;
   A.n_samples = n;
   const double radius = c->params.nn_radius_hands;
   A.r2 = float(radius * radius);
@@ -958,7 +982,8 @@ int* hand_sweep_overflow_ptr(Ctx* c) { return c->overflow.as<int>(); }
 int* hand_sweep_list_ptr(Ctx* c) { return c->hyp_list.as<int>(); }
 int* hand_sweep_list_count_ptr(Ctx* c) { return reinterpret_cast<int*>(c->counters.as<unsigned long long>() + 4); }
 
-int hand_sweep_enqueue(Ctx* c, const int* d_indices, int n, const ag_frame* d_frames, unsigned flags, bool fork_compact) {
+int hand_sweep_enqueue(Ctx* c, const int* d_indices, int n, const ag_frame* d_frames, unsigned flags, bool fork_compact,
+                       bool frames_from_fit) {
   c->n_hyp = 0;
   c->images_valid = false;
   if (n <= 0) return AG_OK;
@@ -970,6 +995,8 @@ int hand_sweep_enqueue(Ctx* c, const int* d_indices, int n, const ag_frame* d_fr
       c->hyp_list.reserve(slots * 4 + 16))
     return AG_ERR_CUDA;
   SweepArgs A = make_args(c, d_indices, n, d_frames, flags);
+  c->sweep_from_fit = frames_from_fit && c->sample_q.p != nullptr;
+  if (c->sweep_from_fit) A.sample_q = c->sample_q.as<float4>();
   const size_t smem_small = sizeof(SweepShared) + size_t(kSlabCapSmall) * 20;
   const size_t smem_big = sizeof(SweepShared) + size_t(kSlabCapBig) * 20;
   static bool attr_set = false;
