@@ -1538,7 +1538,7 @@ int ag_train_features(ag_ctx* h, const ag_grasp* grasps, int n, float* features)
   for (int i = 0; i < n; i++) slots[i] = raw_slots[grasps[i].image_id];
   DevBuf d_slots, d_img3, d_desc;
   // images: [n own][n x 2 per camera] -> descriptor rows reordered to (own, camera 1, camera 2) per hypothesis
-  if (d_slots.reserve(size_t(n) * 4) || d_img3.reserve(size_t(n) * 3 * AG_IMAGE_WORDS * 4) ||
+  if (d_slots.reserve(size_t(n) * 4) || d_img3.reserve(size_t(n) * 3 * AG_IMAGE_WORDS * 4 + 64) ||
       d_desc.reserve(size_t(n) * 3 * AG_HOG_DIM * 4))
     return AG_ERR_CUDA;
   AG_CUDA_CHECK(cudaMemcpyAsync(d_slots.p, slots.data(), size_t(n) * 4, cudaMemcpyHostToDevice, c.stream));
@@ -1823,7 +1823,7 @@ int ag_hog_svm(ag_ctx* h, const ag_svm* svm, const uint32_t* images, int n, floa
   cudaSetDevice(c.device);
   if (n <= 0) return AG_OK;
   DevBuf img, sc;
-  if (img.reserve(size_t(n) * AG_IMAGE_WORDS * 4) || sc.reserve(size_t(n) * 4)) return AG_ERR_CUDA;
+  if (img.reserve(size_t(n) * AG_IMAGE_WORDS * 4 + 64) || sc.reserve(size_t(n) * 4)) return AG_ERR_CUDA;
   if (descriptors && c.descriptors.reserve(size_t(n) * AG_HOG_DIM * 4)) return AG_ERR_CUDA;
   AG_CUDA_CHECK(cudaMemcpyAsync(img.p, images, size_t(n) * AG_IMAGE_WORDS * 4, cudaMemcpyHostToDevice, c.stream));
   int rc = hog_svm_device(&c, svm->m, img.as<uint32_t>(), nullptr, n, nullptr, descriptors ? c.descriptors.as<float>() : nullptr,

@@ -163,6 +163,30 @@ struct SvmDev {
 
 constexpr int RW = 4;  // 32-bit words per image row (100 px -> 128-bit rows)
 
+// ---- PTX helpers: mbarrier + TMA bulk copy (global -> shared), as in quadric.cu / sweep.cu ----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done)
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t bits_at(const uint32_t* img, int bit0) {  // 32 bits starting at bit0
   const int w = bit0 >> 5, sh = bit0 & 31;
   return __funnelshift_r(img[w], img[w + 1], sh);
@@ -179,9 +203,10 @@ k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slo
   // per warp: the ordered contributions of one cell (step 3); steps 1-2 use the same bytes for the packed and the
   // row-aligned image
   __shared__ __align__(16) float4 s_rec[kThreads / 32][CELL_LIST];
-  static_assert(sizeof(float4) * (kThreads / 32) * CELL_LIST >= 4 * (AG_IMAGE_WORDS + 2 + H * RW), "overlay");
-  uint32_t* const s_bits = reinterpret_cast<uint32_t*>(&s_rec[0][0]);
-  uint32_t(*const s_row)[RW] = reinterpret_cast<uint32_t(*)[RW]>(s_bits + AG_IMAGE_WORDS + 2);
+  static_assert(sizeof(float4) * (kThreads / 32) * CELL_LIST >= 4 * (256 + H * RW), "overlay");
+  uint32_t* const s_stage = reinterpret_cast<uint32_t*>(&s_rec[0][0]);  // 1 KB: the 16-byte blocks holding the packed image
+  uint32_t(*const s_row)[RW] = reinterpret_cast<uint32_t(*)[RW]>(s_stage + 256);
+  __shared__ __align__(8) unsigned long long s_bar;
   __shared__ uint32_t s_xp[H][RW], s_xn[H][RW], s_yp[H][RW], s_yn[H][RW];  // gradient sign bit-planes
   __shared__ uint32_t s_col[W][3];                  // per column: 80-bit mask of non-zero-gradient pixels
   __shared__ uint32_t s_tile[H / 8];                // per row of 8x8 tiles: bit tx = the tile holds such a pixel
@@ -197,6 +222,12 @@ k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slo
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned lt = (1u << lane) - 1u;
   if (tid < 9) s_case[tid] = g_hog.cases[tid];
+  const uint32_t bar = smem_u32(&s_bar);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_proxy_async_smem();
+  }
+  uint32_t parity = 0;
   // block ub = (bx, by) covers the tiles (bx..bx+1, by..by+1)
   auto flagged = [&](int ub) -> bool {
     const int bx = ub / UBY, by = ub - bx * UBY;
@@ -205,10 +236,21 @@ k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slo
   for (int hyp = blockIdx.x; hyp < n; hyp += gridDim.x) {
     __syncthreads();  // the previous hypothesis is finished with the shared arrays
     const int slot = hyp == int(blockIdx.x) ? first_slot : (image_slots ? image_slots[hyp] : hyp);
-    const uint32_t* src = images + size_t(slot) * AG_IMAGE_WORDS;
-    for (int i = tid; i < AG_IMAGE_WORDS + 2; i += kThreads) s_bits[i] = i < AG_IMAGE_WORDS ? src[i] : 0u;
+    // the packed image (1000 B, contiguous) arrives by ONE TMA bulk copy: the 16-byte blocks that contain it (an image
+    // starts on an 8-byte boundary), tracked by an mbarrier transaction count
+    const char* src = reinterpret_cast<const char*>(images + size_t(slot) * AG_IMAGE_WORDS);
+    const unsigned off = unsigned(reinterpret_cast<uintptr_t>(src) & 15u);
+    const uint32_t bytes = (off + uint32_t(AG_IMAGE_WORDS) * 4u + 15u) & ~15u;
+    if (tid == 0) {
+      fence_proxy_async_smem();  // the generic-proxy accesses of the previous hypothesis precede the async writes
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(smem_u32(s_stage), src - off, bytes, bar);
+    }
+    const uint32_t* s_bits = s_stage + (off >> 2);
     for (int i = tid; i < W * 3; i += kThreads) (&s_col[0][0])[i] = 0u;
     if (tid < H / 8) s_tile[tid] = 0u;
+    if (warp == 0) mbar_wait(bar, parity);
+    parity ^= 1u;
     __syncthreads();
     // 1. row-aligned copy: row r = bits [100 r, 100 r + 100)
     for (int it = tid; it < H * RW; it += kThreads) {

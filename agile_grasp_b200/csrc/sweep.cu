@@ -989,7 +989,7 @@ int hand_sweep_enqueue(Ctx* c, const int* d_indices, int n, const ag_frame* d_fr
   if (n <= 0) return AG_OK;
   const size_t slots = size_t(n) * 8;
   if (c->grasps_raw.reserve(slots * sizeof(ag_grasp)) || c->valid.reserve(slots + 64) ||
-      c->images_raw.reserve(slots * AG_IMAGE_WORDS * 4) || c->hyp_slots.reserve(slots * 4 + 16) ||
+      c->images_raw.reserve(slots * AG_IMAGE_WORDS * 4 + 64) || c->hyp_slots.reserve(slots * 4 + 16) ||
       c->grasps.reserve(slots * sizeof(ag_grasp)) || c->counters.reserve(64) ||
       c->sweep_dbg.reserve(size_t(n) * 4 + slots * 4) || c->overflow.reserve(size_t(n + 1) * 4) ||
       c->hyp_list.reserve(slots * 4 + 16))
