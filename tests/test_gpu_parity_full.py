@@ -474,3 +474,38 @@ def test_cpp_train_svm_example(tmp_path):
         svm.save(str(model))
         m = api.Svm(str(model))
         assert m.kernel == 1 and m.var_count == 3528 and m.sv_total >= 1
+
+
+def test_rand_stream_runs_on_from_the_all_points_pass(ctx, oracle, small_scene):
+    """Production normal mode with calculates_antipodal: the all-points pass (hand_search.cpp:17-26) consumes rand()
+    draws before the sample pass does (quadric.cpp:177-192 knows nothing of passes), so the samples' picks start where
+    that pass stopped.  Here the all-points radius is 0.02 so that its balls hold more than 50 points and the carry
+    is far from zero.  The all-points pass lays the stream out in k_ball_moments' last CTA (or k_rand_offsets), the
+    sample pass in k_rank_picks itself, reading the carry the first pass left: the curvature axes of the hypotheses
+    must be the oracle's (to the dggev noise of the fit), and clearly not those of a stream restarted for the samples."""
+    O = oracle
+    s = small_scene
+    pts, size_left, P, idx = s["pts"], s["size_left"], copy.copy(s["P"]), s["idx"]
+    P.deterministic_normals = 0
+    P.nn_radius_normals = 0.02
+    P.num_threads = os.cpu_count() or 1
+    ctx.set_params(P)
+    ctx.set_svm(None)
+    try:
+        g = ctx.localize(pts, size_left, idx, flags=1)
+        H, tm, nv = O.localize(pts, size_left, P, idx, 1, None, False)
+        go = H.grasps
+        key = lambda a: a["sample_index"].astype(np.int64) * 8 + a["orientation"]  # noqa: E731
+        common, ig, io = np.intersect1d(key(g), key(go), return_indices=True)
+        assert len(common) >= 0.97 * max(len(g), len(go)) and len(common) > 50
+        d_axis = np.linalg.norm(g["axis"][ig] - go["axis"][io], axis=1)
+        assert np.median(d_axis) <= 1e-5 and np.quantile(d_axis, 0.9) <= 1e-3, (np.median(d_axis), d_axis.max())
+        # sensitivity: the same samples with the stream restarted (a stage call) get other picks, hence other axes
+        fr = ctx.fit_quadrics(idx, 0.03)
+        pos = {int(v): k for k, v in enumerate(idx)}
+        rows = np.array([pos[int(v)] for v in g["sample_index"][ig]])
+        big = fr["num_neighbors"][rows] > 50
+        d_restart = np.linalg.norm(fr["axis"][rows] - go["axis"][io], axis=1)
+        assert big.sum() > 30 and np.median(d_restart[big]) > 20 * max(np.median(d_axis[big]), 1e-7)
+    finally:
+        ctx.set_params(s["P"])
