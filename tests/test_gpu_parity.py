@@ -756,3 +756,26 @@ def test_voxelisation_paths_agree(oracle, small_scene, two_view_scene):
         assert c2.timings()["n_voxels"] == len(xo) and _rec_bytes(g_far) == _rec_bytes(g_far2)
         c.close()
         c2.close()
+
+
+def test_stage_timing_switch(small_scene, linear_svm_path):
+    """ag_set_stage_timing: the library default records only the begin / end events of a call (the per-stage event
+    records cost ~16 us as CUDA-graph nodes); total_ms and the counters are filled either way, the stage fields read 0
+    when off, and the grasp list does not depend on the switch (eager call, graph capture, graph replay)."""
+    s = small_scene
+    svm = api.Svm(linear_svm_path)
+    lists, times = {}, {}
+    for on in (False, True):
+        c = api.Context(0, s["P"], stage_timing=on)
+        c.set_svm(svm)
+        for _ in range(3):
+            g = c.localize(s["pts"], s["size_left"])
+        lists[on], times[on] = g, c.timings()
+        c.set_svm(None)
+        c.close()
+    assert len(lists[False]) > 0 and _rec_bytes(lists[False]) == _rec_bytes(lists[True])
+    assert (lists[False]["score"].view(np.uint32) == lists[True]["score"].view(np.uint32)).all()
+    for t in times.values():
+        assert t["total_ms"] > 0 and t["n_hyp"] == len(lists[True]) and t["taubin_neighbor_points"] > 0
+    assert times[True]["sweep_ms"] > 0 and times[True]["preprocess_ms"] > 0 and times[True]["search_ms"] > 0
+    assert times[False]["sweep_ms"] == 0 and times[False]["preprocess_ms"] == 0 and times[False]["search_ms"] == 0
