@@ -199,7 +199,7 @@ constexpr int kFlagWords = 3;
 __global__ void __launch_bounds__(kThreads, 6)
 k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slots, int n_bound,
           const int* __restrict__ n_dev, SvmDev svm, float* __restrict__ descriptors, float* __restrict__ scores,
-          ag_grasp* __restrict__ grasps_out, int score_by_slot, uint32_t* __restrict__ block_flags) {
+          ag_grasp* __restrict__ grasps_out, int score_by_slot, uint32_t* __restrict__ block_flags, int two_ended) {
   // per warp: the ordered contributions of one cell (step 3); steps 1-2 use the same bytes for the packed and the
   // row-aligned image
   __shared__ __align__(16) float4 s_rec[kThreads / 32][CELL_LIST];
@@ -216,9 +216,12 @@ k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slo
   __shared__ int s_nflag;
   __shared__ double s_part[kThreads / 32];
   // (independent loads first: the count, this CTA's first image slot and the model's coefficient are in flight together)
-  const int first_slot = (image_slots && int(blockIdx.x) < n_bound) ? image_slots[blockIdx.x] : int(blockIdx.x);
+  // two_ended (the sweep's list): n_dev[0] entries from the front of image_slots — the heavy images, dispatched first —
+  // and n_dev[1] from its back (index n_bound - 1 downwards)
+  const int first_slot = (image_slots && !two_ended && int(blockIdx.x) < n_bound) ? image_slots[blockIdx.x] : int(blockIdx.x);
   const double alpha0 = (svm.sv_total == 1 && svm.sv_count > 0) ? svm.alpha[0] : 0.0;
-  const int n = n_dev ? min(*n_dev, n_bound) : n_bound;
+  const int n_front = n_dev ? min(n_dev[0], n_bound) : n_bound;
+  const int n = two_ended ? min(n_front + n_dev[1], n_bound) : n_front;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned lt = (1u << lane) - 1u;
   if (tid < 9) s_case[tid] = g_hog.cases[tid];
@@ -235,7 +238,8 @@ k_hog_svm(const uint32_t* __restrict__ images, const int* __restrict__ image_slo
   };
   for (int hyp = blockIdx.x; hyp < n; hyp += gridDim.x) {
     __syncthreads();  // the previous hypothesis is finished with the shared arrays
-    const int slot = hyp == int(blockIdx.x) ? first_slot : (image_slots ? image_slots[hyp] : hyp);
+    const int slot = two_ended ? image_slots[hyp < n_front ? hyp : n_bound - 1 - (hyp - n_front)]
+                               : (hyp == int(blockIdx.x) ? first_slot : (image_slots ? image_slots[hyp] : hyp));
     // the packed image (1000 B, contiguous) arrives by ONE TMA bulk copy: the 16-byte blocks that contain it (an image
     // starts on an 8-byte boundary), tracked by an mbarrier transaction count
     const char* src = reinterpret_cast<const char*>(images + size_t(slot) * AG_IMAGE_WORDS);
@@ -747,7 +751,7 @@ int hog_descriptors_device(Ctx* c, const uint32_t* d_images, const int* d_image_
   SvmDev none;
   std::memset(&none, 0, sizeof(none));
   k_hog_svm<<<std::min(n, kNumSMs * 16), kThreads, 0, c->stream>>>(d_images, d_image_slots, n, nullptr, none, d_descriptors,
-                                                                  nullptr, nullptr, 0, nullptr);
+                                                                  nullptr, nullptr, 0, nullptr, 0);
   c->launches += 1;
   AG_CUDA_CHECK(cudaGetLastError());
   return AG_OK;
@@ -796,7 +800,7 @@ int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d
     none.sv_total = 0;
     if (c->block_flags.reserve(size_t(n) * kFlagWords * 4)) return AG_ERR_CUDA;
     k_hog_svm<<<grid, kThreads, 0, c->stream>>>(d_images, d_image_slots, n, n_dev, none, desc, d_scores, nullptr, 0,
-                                                c->block_flags.as<uint32_t>());
+                                                c->block_flags.as<uint32_t>(), 0);
     static const bool dense = getenv("AG_SVM_DENSE") != nullptr;  // diagnostics: the dense tiled product
     if (dense || !svm->d_svT) {
       const dim3 gg((n + GM - 1) / GM, (svm->sv_total + GN - 1) / GN);
@@ -816,7 +820,7 @@ int hog_svm_device(Ctx* c, SvmModel* svm, const uint32_t* d_images, const int* d
     c->launches += 3;
   } else {
     k_hog_svm<<<grid, kThreads, 0, c->stream>>>(d_images, d_image_slots, n, n_dev, sd, d_descriptors, d_scores,
-                                                 d_grasps_out, score_by_slot ? 1 : 0, nullptr);
+                                                 d_grasps_out, score_by_slot ? 1 : 0, nullptr, score_by_slot ? 1 : 0);
     c->launches += 1;
   }
   AG_CUDA_CHECK(cudaGetLastError());

@@ -29,6 +29,7 @@ namespace {
 constexpr int kThreads = 256;       // 8 warps = 8 orientations (rotating_hand.cpp:13)
 constexpr int kSlabCapSmall = 1920; // slab points kept in shared memory by the common kernel (37.5 KB; 55 KB per CTA, 4 CTAs / SM)
 constexpr int kSlabCapBig = 9600;   // fallback instantiation for dense neighbourhoods (187.5 KB, 1 CTA / SM)
+constexpr int kHeavyImage = 160;    // occupied pixels from which a grasp image goes to the front of the scorer's list
 constexpr int kStage = 1024;        // candidates staged per pass of the ball gather (16 KB, reused by phase B)
 
 struct SweepArgs {
@@ -46,7 +47,7 @@ struct SweepArgs {
   int* slab_counts;       // [n_samples] or null
   unsigned long long* counters;
   int* hyp_list;          // unordered list of the (sample, orientation) slots that hold a hypothesis (for the scorer)
-  int* hyp_count;
+  int* hyp_count;         // [0] entries filled from the front, [1] from the back
   int* overflow;          // [0] = number of samples whose slab exceeded the capacity, [1..] their slots
   const int* sample_list; // if non-null: blockIdx.x indexes this list of sample slots (fallback pass)
   const float4* sample_q; // if non-null: x, y, z, (index << 1 | camera) of every sample slot (left by the fit; -1: no sample)
@@ -539,10 +540,22 @@ k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
     gr.reserved = 0;
     A.grasps[slot] = gr;
     A.valid[slot] = keep_hyp ? 1 : 0;
-    if (keep_hyp) A.hyp_list[atomicAdd(A.hyp_count, 1)] = int(slot);  // (scoring does not need the sample-major order)
   }
   uint32_t* gimg = A.images + slot * AG_IMAGE_WORDS;
-  for (int i = lane; i < AG_IMAGE_WORDS; i += 32) gimg[i] = img[i];
+  int occupied = 0;
+  for (int i = lane; i < AG_IMAGE_WORDS; i += 32) {
+    const uint32_t w = img[i];
+    gimg[i] = w;
+    occupied += __popc(w);
+  }
+  // The scorer's list (its order is free: scoring does not need the sample-major order) is filled from both ends:
+  // images with many occupied pixels — the expensive ones for the HOG kernel, which lasts as long as its heaviest
+  // image — from the front, so that their CTAs are dispatched first; the others from the back.
+  occupied = __reduce_add_sync(0xffffffffu, occupied);
+  if (lane == 0 && keep_hyp) {
+    if (occupied >= kHeavyImage) A.hyp_list[atomicAdd(&A.hyp_count[0], 1)] = int(slot);
+    else A.hyp_list[A.n_samples * 8 - 1 - atomicAdd(&A.hyp_count[1], 1)] = int(slot);
+  }
 }
 
 // Stable compaction of the valid (sample, orientation) slots: slots[h] = raw slot of hypothesis h in
