@@ -48,6 +48,7 @@ struct SweepArgs {
   unsigned long long* counters;
   int* hyp_list;          // unordered list of the (sample, orientation) slots that hold a hypothesis (for the scorer)
   int* hyp_count;         // [0] entries filled from the front, [1] from the back
+  int heavy_image;        // occupied pixels from which a grasp image goes to the front
   int* overflow;          // [0] = number of samples whose slab exceeded the capacity, [1..] their slots
   const int* sample_list; // if non-null: blockIdx.x indexes this list of sample slots (fallback pass)
   const float4* sample_q; // if non-null: x, y, z, (index << 1 | camera) of every sample slot (left by the fit; -1: no sample)
@@ -553,7 +554,7 @@ k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
   // image — from the front, so that their CTAs are dispatched first; the others from the back.
   occupied = __reduce_add_sync(0xffffffffu, occupied);
   if (lane == 0 && keep_hyp) {
-    if (occupied >= kHeavyImage) A.hyp_list[atomicAdd(&A.hyp_count[0], 1)] = int(slot);
+    if (occupied >= A.heavy_image) A.hyp_list[atomicAdd(&A.hyp_count[0], 1)] = int(slot);
     else A.hyp_list[A.n_samples * 8 - 1 - atomicAdd(&A.hyp_count[1], 1)] = int(slot);
   }
 }
@@ -917,6 +918,11 @@ static SweepArgs make_args(Ctx* c, const int* d_indices, int n, const ag_frame* 
   A.overflow = c->overflow.as<int>();
   A.hyp_list = c->hyp_list.as<int>();
   A.hyp_count = reinterpret_cast<int*>(c->counters.as<unsigned long long>() + 4);
+  static const int heavy = [] {  // AG_HEAVY_IMAGE (measurements)
+    const char* e = getenv("AG_HEAVY_IMAGE");
+    return e ? atoi(e) : kHeavyImage;
+  }();
+  A.heavy_image = heavy;
   A.sample_list = nullptr;
   A.sample_q = nullptr;
   A.n_samples = n;
