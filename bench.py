@@ -16,11 +16,15 @@ the reference's component tests is reported next to it (`other_mode` sub-objects
 the headline instead).
 
   value : hyp/s with the cloud already resident in HBM (ag_localize_device), timed with CUDA events on
-          the library's own stream (ag_timings), max over ranks.
+          the library's own stream around the whole call (ag_timings.total_ms), max over ranks.  The library default:
+          no per-stage event records inside the pipeline (ag_set_stage_timing off).
   e2e   : hyp/s through the host-buffer entry points (pinned host cloud in, host grasp list out),
           wall clock around the calls; H2D of the cloud and D2H of the records are inside.
+  stage_pass : a second pass of the same K steps with ag_set_stage_timing(1) (a dozen event-record nodes in the CUDA
+          graph, ~0.04 ms per step): the source of stages_ms and of the kernel durations behind the two rooflines.
   roofline : the Taubin stage (radius search + moment accumulation): algorithmic bytes (16 B per neighbour +
-          292 B out per sample) over the CUDA-event duration of its kernel(s), against MEASURED_PEAKS.json.
+          292 B out per sample) over the CUDA-event duration of its kernel(s), against MEASURED_PEAKS.json;
+          traffic = the kernel's DRAM bytes per launch from the committed ncu capture (profiles/taubin_traffic.json).
   roofline_step : the same for the kernel with the largest share of the step (k_hand_sweep).
   strong_scaling : ONE cloud per step, its samples sharded over the N ranks (ag_params.shard_index / shard_count,
           interleaved shares), every rank ending up with the whole merged grasp list (peer stores + merge inside
