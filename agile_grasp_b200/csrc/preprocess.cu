@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(kBlock)
 k_emit_bitmap(uint32_t* bitmap, unsigned long long* tile_state, double cell, PreState* st, GPoint* vox,
               double* normals, RowIndex* ri, int* row_ptr, int row_stride, int* col_ptr, DrawArgs draw) {
   __shared__ int s_warp[kBlock / 32];
-  __shared__ unsigned s_tile;
+  __shared__ unsigned s_tile, s_last;
   __shared__ unsigned s_base;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const unsigned epoch = st->epoch;  // advanced on the device by k_init_state: a replayed CUDA graph gets a new one
@@ -338,9 +338,10 @@ k_emit_bitmap(uint32_t* bitmap, unsigned long long* tile_state, double cell, Pre
       // the last CTA to leave closes the descriptor from the sentinels of the column table and, when asked to, draws
       // the samples (the voxel count is known right here; used to be a launch of its own)
       __threadfence();
-      if (threadIdx.x == 0) s_tile = atomicAdd(&st->emit_done, 1u) == gridDim.x - 1 ? 1u : 0u;
+      if (threadIdx.x == 0) s_last = atomicAdd(&st->emit_done, 1u) == gridDim.x - 1 ? 1u : 0u;  // (not s_tile: slower
+                                                                                              // warps still read it)
       __syncthreads();
-      if (!s_tile) return;
+      if (!s_last) return;
       if (threadIdx.x == 0) {
         int n_points = 0;
         if (words > 0) {
