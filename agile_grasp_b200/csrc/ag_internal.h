@@ -160,6 +160,8 @@ struct Ctx {
   // sweep outputs
   DevBuf grasps_raw, valid, images_raw, hyp_slots, grasps, counters, scores, descriptors, kvals, sweep_dbg, overflow;
   DevBuf hyp_list;             // unordered hypothesis slots (sweep -> scorer)
+  DevBuf overflow_list;        // [0] count, [1..] samples whose slab exceeded the common kernel's capacity (inline large-slab pass)
+  bool inline_big = false;     // the large-slab pass is part of the pipeline (switched on by the first call that needs it)
   DevBuf sample_q;             // per sample of the last fit: x, y, z, (index << 1 | camera) — read by the sweep instead of
                                // the indices -> cloud chain of dependent loads
   DevBuf block_flags;          // per hypothesis: which HOG blocks hold an outline pixel (k_hog_svm -> k_svm_sparse)
@@ -186,7 +188,7 @@ struct Ctx {
   int launches = 0;      // own-kernel launch counter (reset per localize call)
   bool stage_timing = false;  // record the per-stage events (ag_set_stage_timing)
   // ag_localize's pipeline: small resets and the sample draw ride on kernels of the voxelisation instead of being graph
-  // nodes of their own.  fold_resets: bit 0 counters, bit 1 sweep overflow counter, bit 2 rand() carry — set by the
+  // nodes of their own.  fold_resets: bit 0 counters, bit 1 sweep overflow counter, bit 2 rand() carry, bit 3 counter of the inline large-slab pass — set by the
   // caller of preprocess_device, each bit cleared by the stage that would otherwise issue the memset.
   unsigned fold_resets = 0;
   void* fold_draw = nullptr;   // DrawArgs* (host) for the draw to fold into the voxel scan; draw_folded = it was
@@ -222,11 +224,12 @@ int fit_quadrics_device(Ctx* c, const int* d_indices, int n, const int* d_count,
 int quadric_rand_reset(Ctx* c);
 // enqueue only (no sync): sweep + stable compaction; the hypothesis count stays in device memory
 int hand_sweep_enqueue(Ctx* c, const int* d_indices, int n, const ag_frame* d_frames, unsigned flags,
-                       bool fork_compact = false, bool frames_from_fit = false);
+                       bool fork_compact = false, bool frames_from_fit = false, bool inline_big = false);
 int* hand_sweep_list_ptr(Ctx* c);        // unordered list of hypothesis slots of the last sweep
 int* hand_sweep_list_count_ptr(Ctx* c);
 // after a sync: handles samples whose slab overflowed the small instantiation; returns the hypothesis count
 int hand_sweep_finish(Ctx* c, int n, int n_over, int* n_hyp);
+int hand_sweep_rerun_enqueue(Ctx* c, int n, int n_over, bool fresh_list);  // enqueue only (ag_localize's overflow pass)
 int box_points_device(Ctx* c, int n_samples, int slot, std::vector<double>& pts, std::vector<int>& cam);
 int* hand_sweep_count_ptr(Ctx* c, int n);     // device address of the hypothesis count of the last enqueue
 int* hand_sweep_overflow_ptr(Ctx* c);         // device address of the overflow counter

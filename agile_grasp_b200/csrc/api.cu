@@ -666,7 +666,8 @@ static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, in
       if (c->samples.reserve(size_t(std::max(S, n_in)) * 4) || c->counters.reserve(64) ||
           c->overflow.reserve(size_t(S + 1) * 4))
         return AG_ERR_CUDA;
-      c->fold_resets = 1u | 2u | (c->params.deterministic_normals == 0 ? 4u : 0u);
+      if (c->inline_big && c->overflow_list.reserve(size_t(S + 1) * 4)) return AG_ERR_CUDA;
+      c->fold_resets = 1u | 2u | (c->params.deterministic_normals == 0 ? 4u : 0u) | (c->inline_big ? 8u : 0u);
       if (!given && !(flags & (AG_FLAG_USE_CLUSTERING | AG_FLAG_CALC_ANTIPODAL))) {
         draw.out = c->samples.as<int>();
         draw.seed = c->params.seed;
@@ -738,7 +739,7 @@ static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, in
     // compaction for the export runs beside it; models with many support vectors go through the ordered list
     const bool fork = c->attached_svm && c->attached_svm->sv_total == 1;
     rc = hand_sweep_enqueue(c, c->samples.as<int>(), S, c->frames.as<ag_frame>(),
-                            c->params.filters_boundaries ? 0x100u : 0u, fork, true);
+                            c->params.filters_boundaries ? 0x100u : 0u, fork, true, c->inline_big);
     if (rc) return rc;
     d_nsel = hand_sweep_count_ptr(c, S);
     record_event(c, c->ev[8]);
@@ -769,7 +770,8 @@ static int localize_begin(Ctx* c, const void* d_points, int stride, int n_in, in
   key.size_left = size_left;
   key.S = S;
   key.given = given ? 1 : 0;
-  key.flags = flags | (c->stage_timing ? 0x80000000u : 0u);  // (a graph with and one without the stage events)
+  key.flags = flags | (c->stage_timing ? 0x80000000u : 0u) |  // (a graph with and one without the stage events)
+              (c->inline_big ? 0x40000000u : 0u);              // (... and with the inline large-slab pass)
   key.state_gen = c->state_gen;
   key.svm = c->attached_svm;
   static const bool graphs_off = getenv("AG_NO_GRAPH") != nullptr;
@@ -930,19 +932,35 @@ static int localize_end(Ctx* c, ag_grasp** out, int* n_out) {
   c->n_hyp = Hn;
   c->images_valid = true;
   if (h->n_over > 0) {
-    // rare: some samples need the large-capacity sweep; redo them, rescore, re-export (with syncs)
-    rc = hand_sweep_finish(c, S, h->n_over, &Hn);
+    // some samples need the large-capacity sweep (dense neighbourhoods: ~0.5 % of the samples of the fused 7-view
+    // cloud of config 5): redo them, score THEIR hypotheses, export again — one more enqueue and one more wait.  A
+    // single-vector model scored the first pass by raw slot, so only the redone samples' hypotheses (a fresh scorer's
+    // list) need the HOG kernel; models with many support vectors rescore the ordered list.
+    c->inline_big = true;  // from the next call on the large-slab pass is part of the pipeline (no host round trip)
+    const size_t slots = size_t(S) * 8;
+    const bool by_slot = c->attached_svm && c->scores_by_slot;
+    rc = hand_sweep_rerun_enqueue(c, S, h->n_over, by_slot);
     if (rc) return rc;
-    if (c->attached_svm && Hn > 0) {
-      c->scores_by_slot = false;
-      rc = hog_svm_device(c, c->attached_svm, c->images_raw.as<uint32_t>(), c->hyp_slots.as<int>(), Hn, nullptr, nullptr,
-                          c->scores.as<float>(), nullptr);
+    if (c->attached_svm) {
+      if (by_slot)
+        rc = hog_svm_device(c, c->attached_svm, c->images_raw.as<uint32_t>(), hand_sweep_list_ptr(c), int(slots),
+                            hand_sweep_list_count_ptr(c), nullptr, c->scores.as<float>(), nullptr, true);
+      else
+        rc = hog_svm_device(c, c->attached_svm, c->images_raw.as<uint32_t>(), c->hyp_slots.as<int>(), int(slots),
+                            hand_sweep_count_ptr(c, S), nullptr, c->scores.as<float>(), nullptr);
       if (rc) return rc;
     }
+    c->pend_nsel = hand_sweep_count_ptr(c, S);
     peer.final_pass = 1;
     launch_export(c, peer);
     launch_merge(c, peer);
+    cudaEventRecord(c->ev[7], st);  // (total_ms covers this pass and the host round trip in front of it)
     AG_CUDA_CHECK(cudaStreamSynchronize(st));
+    AG_CUDA_CHECK(cudaGetLastError());
+    if (h->n_over > 0) {  // (the overflow counter was zeroed before the large-slab pass)
+      set_error("hand sweep: a sample's slab exceeded the shared-memory capacity (9600 points)");
+      return AG_ERR_CAPACITY;
+    }
     Hn = h->n_hyp;
     c->n_hyp = Hn;
   }
@@ -1074,7 +1092,7 @@ void ag_destroy(ag_ctx* h) {
   for (DevBuf* b : {&c.raw, &c.keys, &c.keys_sorted, &c.keys_unique, &c.cub_tmp, &c.block_counts, &c.misc, &c.bitmap, &c.tile_state, &c.vox,
                     &c.row_ptr, &c.col_ptr, &c.row_index, &c.all_frames,
                     &c.normals, &c.samples, &c.sample_stage, &c.samples_all, &c.nn_counts_all, &c.count_all, &c.moments, &c.frames, &c.nn_counts, &c.nbr_pool, &c.nbr_heads, &c.rand_raw, &c.rand_off, &c.rand_carry, &c.picks, &c.quad_par, &c.grasps_raw, &c.valid,
-                    &c.images_raw, &c.hyp_slots, &c.hyp_list, &c.sample_q, &c.block_flags, &c.grasps, &c.counters, &c.scores, &c.descriptors, &c.kvals, &c.handle_in, &c.handle_bits, &c.sweep_dbg, &c.overflow})
+                    &c.images_raw, &c.hyp_slots, &c.hyp_list, &c.overflow_list, &c.sample_q, &c.block_flags, &c.grasps, &c.counters, &c.scores, &c.descriptors, &c.kvals, &c.handle_in, &c.handle_bits, &c.sweep_dbg, &c.overflow})
     b->release();
   if (c.h_pinned) cudaFreeHost(c.h_pinned);
   for (auto& ev : c.ev) cudaEventDestroy(ev);

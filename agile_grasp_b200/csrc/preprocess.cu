@@ -74,8 +74,8 @@ __device__ __forceinline__ bool load_xyz(const char* base, int stride, int i, fl
 }
 
 struct ResetList {  // small device buffers zeroed by k_init_state (word counts)
-  unsigned* p[4];
-  int words[4];
+  unsigned* p[5];
+  int words[5];
 };
 __global__ void k_init_state(PreState* st, ResetList rl) {
   if (threadIdx.x == 0) {
@@ -92,7 +92,7 @@ __global__ void k_init_state(PreState* st, ResetList rl) {
     st->emit_done = 0;
     st->epoch++;
   }
-  for (int k = 0; k < 4; k++)
+  for (int k = 0; k < 5; k++)
     if (rl.p[k])
       for (int i = threadIdx.x; i < rl.words[k]; i += blockDim.x) rl.p[k][i] = 0u;
 }
@@ -1004,6 +1004,12 @@ int preprocess_device(Ctx* c, const void* d_points, int stride, int n_in, int si
     rl.words[3] = 4;
   }
   c->fold_resets &= ~4u;  // (quadric_rand_reset ran before this call)
+  if ((c->fold_resets & 8u) && c->overflow_list.p) {
+    rl.p[4] = c->overflow_list.as<unsigned>();
+    rl.words[4] = 1;
+  } else {
+    c->fold_resets &= ~8u;
+  }
   k_init_state<<<1, 64, 0, c->stream>>>(st, rl);
   const bool quirk = !P.fix_cam_source && size_left < n_in;
   if (quirk) {

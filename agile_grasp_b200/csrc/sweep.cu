@@ -50,7 +50,8 @@ struct SweepArgs {
   int* hyp_count;         // [0] entries filled from the front, [1] from the back
   int heavy_image;        // occupied pixels from which a grasp image goes to the front
   int* overflow;          // [0] = number of samples whose slab exceeded the capacity, [1..] their slots
-  const int* sample_list; // if non-null: blockIdx.x indexes this list of sample slots (fallback pass)
+  const int* sample_list; // if non-null: blockIdx.x indexes this list of sample slots (large-slab pass)
+  const int* sample_count;// if non-null: device-side length of sample_list (inline large-slab pass: CTAs beyond it leave)
   const float4* sample_q; // if non-null: x, y, z, (index << 1 | camera) of every sample slot (left by the fit; -1: no sample)
   int n_samples;
   float r2;
@@ -131,6 +132,14 @@ k_hand_sweep(const SweepArgs A, const __grid_constant__ HandConst hc) {
   double2* slab_xy = reinterpret_cast<double2*>(s_raw + sizeof(SweepShared));  // hand-frame x, y of every slab point
   uint32_t* slab_tag = reinterpret_cast<uint32_t*>(slab_xy + CAP);             // point index << 2 | tag bits
 
+  if (A.sample_count) {
+    // inline large-slab pass: the list was written by the common kernel just before; what the grid cannot take is
+    // handed on to the host-side pass (it joins the unresolved list)
+    const int cnt = *A.sample_count;
+    if (blockIdx.x == 0)
+      for (int i = int(gridDim.x) + int(threadIdx.x); i < cnt; i += kThreads) A.overflow[1 + atomicAdd(A.overflow, 1)] = A.sample_list[i];
+    if (int(blockIdx.x) >= cnt) return;
+  }
   const int s = A.sample_list ? A.sample_list[blockIdx.x] : blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
@@ -924,6 +933,7 @@ static SweepArgs make_args(Ctx* c, const int* d_indices, int n, const ag_frame* 
   }();
   A.heavy_image = heavy;
   A.sample_list = nullptr;
+  A.sample_count = nullptr;
   A.sample_q = nullptr;
   A.n_samples = n;
   const double radius = c->params.nn_radius_hands;
@@ -1002,7 +1012,7 @@ int* hand_sweep_list_ptr(Ctx* c) { return c->hyp_list.as<int>(); }
 int* hand_sweep_list_count_ptr(Ctx* c) { return reinterpret_cast<int*>(c->counters.as<unsigned long long>() + 4); }
 
 int hand_sweep_enqueue(Ctx* c, const int* d_indices, int n, const ag_frame* d_frames, unsigned flags, bool fork_compact,
-                       bool frames_from_fit) {
+                       bool frames_from_fit, bool inline_big) {
   c->n_hyp = 0;
   c->images_valid = false;
   if (n <= 0) return AG_OK;
@@ -1027,7 +1037,24 @@ int hand_sweep_enqueue(Ctx* c, const int* d_indices, int n, const ag_frame* d_fr
   }
   if (c->fold_resets & 2u) c->fold_resets &= ~2u;  // (ag_localize: zeroed by k_init_state)
   else AG_CUDA_CHECK(cudaMemsetAsync(A.overflow, 0, 4, c->stream));
-  k_hand_sweep<kSlabCapSmall><<<n, kThreads, smem_small, c->stream>>>(A, c->hand);
+  if (inline_big) {
+    // Dense clouds (the fused 7-view cloud of config 5: ~0.5 % of the samples) overflow the common kernel's slab on
+    // every call: the large-slab instantiation then runs right behind it on the samples the common kernel listed —
+    // count and list stay on the device, no host round trip, one compaction / scoring / export for both.  What is
+    // left in c->overflow afterwards is unresolved (more samples than this grid, or a slab beyond 9600 points).
+    if (c->overflow_list.reserve(size_t(n + 1) * 4)) return AG_ERR_CUDA;
+    if (c->fold_resets & 8u) c->fold_resets &= ~8u;
+    else AG_CUDA_CHECK(cudaMemsetAsync(c->overflow_list.p, 0, 4, c->stream));
+    SweepArgs B = A;
+    A.overflow = c->overflow_list.as<int>();
+    k_hand_sweep<kSlabCapSmall><<<n, kThreads, smem_small, c->stream>>>(A, c->hand);
+    B.sample_list = c->overflow_list.as<int>() + 1;
+    B.sample_count = c->overflow_list.as<int>();
+    k_hand_sweep<kSlabCapBig><<<std::min(n, 2 * kNumSMs), kThreads, smem_big, c->stream>>>(B, c->hand);
+    c->launches += 1;
+  } else {
+    k_hand_sweep<kSlabCapSmall><<<n, kThreads, smem_small, c->stream>>>(A, c->hand);
+  }
   c->launches += 2;  // + k_compact_grasps
   c->sweep_flags = flags;
   c->sweep_indices = d_indices;
@@ -1044,27 +1071,35 @@ int hand_sweep_enqueue(Ctx* c, const int* d_indices, int n, const ag_frame* d_fr
   return compact(c, A, slots, c->stream);
 }
 
-// Called after the stream has been synchronised and the overflow counter read.  Samples whose slab
-// did not fit the 2048-point instantiation (dense neighbourhoods) are redone with the 12k-point one.
+// Samples whose slab did not fit the 1920-point instantiation (dense neighbourhoods) are redone with the 9600-point
+// one: enqueue only.  n_over = the overflow count the host has read; fresh_list: the scorer's list restarts at zero, so
+// that it holds exactly the hypotheses of the redone samples (the others have been scored already).  The overflow
+// counter is zeroed first: after this pass it counts the samples that do not fit the large instantiation either.
+int hand_sweep_rerun_enqueue(Ctx* c, int n, int n_over, bool fresh_list) {
+  const size_t slots = size_t(n) * 8;
+  SweepArgs A = make_args(c, c->sweep_indices, n, c->sweep_frames, c->sweep_flags);
+  if (c->overflow_list.reserve(size_t(n_over) * 4)) return AG_ERR_CUDA;
+  AG_CUDA_CHECK(cudaMemcpyAsync(c->overflow_list.p, A.overflow + 1, size_t(n_over) * 4, cudaMemcpyDeviceToDevice, c->stream));
+  AG_CUDA_CHECK(cudaMemsetAsync(A.overflow, 0, 4, c->stream));
+  if (fresh_list) AG_CUDA_CHECK(cudaMemsetAsync(A.hyp_count, 0, 8, c->stream));
+  A.sample_list = c->overflow_list.as<int>();
+  const size_t smem_big = sizeof(SweepShared) + size_t(kSlabCapBig) * 20;
+  k_hand_sweep<kSlabCapBig><<<n_over, kThreads, smem_big, c->stream>>>(A, c->hand);
+  c->launches += 2;
+  return compact(c, A, slots, c->stream);
+}
+
+// Called after the stream has been synchronised and the overflow counter read (stage call ag_hand_sweep): redo the
+// overflow samples, wait, and read the hypothesis count.
 int hand_sweep_finish(Ctx* c, int n, int n_over, int* n_hyp) {
   const size_t slots = size_t(n) * 8;
   int* d_nsel = c->hyp_slots.as<int>() + slots;
   if (n_over > 0) {
-    SweepArgs A = make_args(c, c->sweep_indices, n, c->sweep_frames, c->sweep_flags);
-    DevBuf list;
-    if (list.reserve(size_t(n_over) * 4)) return AG_ERR_CUDA;
-    AG_CUDA_CHECK(cudaMemcpyAsync(list.p, A.overflow + 1, size_t(n_over) * 4, cudaMemcpyDeviceToDevice, c->stream));
-    AG_CUDA_CHECK(cudaMemsetAsync(A.overflow, 0, 4, c->stream));
-    A.sample_list = list.as<int>();
-    const size_t smem_big = sizeof(SweepShared) + size_t(kSlabCapBig) * 20;
-    k_hand_sweep<kSlabCapBig><<<n_over, kThreads, smem_big, c->stream>>>(A, c->hand);
-    c->launches += 2;
-    int rc = compact(c, A, slots, c->stream);
+    int rc = hand_sweep_rerun_enqueue(c, n, n_over, false);
     if (rc) return rc;
     int over2 = 0;
-    AG_CUDA_CHECK(cudaMemcpyAsync(&over2, A.overflow, 4, cudaMemcpyDeviceToHost, c->stream));
+    AG_CUDA_CHECK(cudaMemcpyAsync(&over2, hand_sweep_overflow_ptr(c), 4, cudaMemcpyDeviceToHost, c->stream));
     AG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    list.release();
     if (over2) {
       set_error("hand sweep: a sample's slab exceeded the shared-memory capacity (9600 points)");
       return AG_ERR_CAPACITY;
