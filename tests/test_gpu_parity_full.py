@@ -509,3 +509,47 @@ def test_rand_stream_runs_on_from_the_all_points_pass(ctx, oracle, small_scene):
         assert big.sum() > 30 and np.median(d_restart[big]) > 20 * max(np.median(d_axis[big]), 1e-7)
     finally:
         ctx.set_params(s["P"])
+
+
+def test_large_slabs_host_pass_and_inline_pass_agree(ctx, oracle, small_scene, linear_svm_path):
+    """Samples whose slab exceeds the common sweep kernel's 1920 points (here forced by a tall hand: |z| < 0.06 keeps
+    most of the r = 0.08 ball) are redone by the 9600-point instantiation — by a host-side pass on the first call
+    that meets one, by the inline pass (device-side count and list, no host round trip) from then on, eagerly and from
+    the captured graph.  All of them return the same list, which is the oracle's (rotating_hand.cpp:19-177 knows no
+    capacity) on the GPU's own frames."""
+    O = oracle
+    s = small_scene
+    P = copy.copy(s["P"])
+    P.hand_height = 0.06
+    P.num_threads = os.cpu_count() or 1
+    svm = api.Svm(linear_svm_path)
+    c = api.Context(0, P)
+    try:
+        c.set_svm(svm)
+        runs = [c.localize(s["pts"], s["size_left"], s["idx"]) for _ in range(4)]
+        slab = c.sweep_debug(len(s["idx"]))["num_slab"]
+        assert (slab > 1920).sum() >= 1, slab.max()  # the scene does exercise the large-slab pass
+        ref = _strip(runs[0])
+        for r in runs[1:]:
+            assert _strip(r) == ref
+        # the same hands as the oracle finds from the same frames
+        c.set_svm(None)
+        fg = c.fit_quadrics(s["idx"], 0.03)
+        normals = np.zeros((len(s["xyz"]), 3))
+        H = O.find_hands(s["tree"], s["cam"], s["idx"], fg, s["cam"][s["idx"]], normals, P)
+        go = H.grasps
+        g = runs[-1]
+        assert len(g) == len(go)
+        for nm in ("sample_index", "orientation", "num_points"):
+            assert np.array_equal(g[nm], go[nm]), nm
+        for nm in ("bottom", "surface", "width"):
+            assert (g[nm].view(np.uint64) == go[nm].view(np.uint64)).all(), nm
+    finally:
+        c.set_svm(None)
+        c.close()
+
+
+def _strip(g):
+    h = g.copy()
+    h["reserved"] = 0
+    return h.tobytes()
